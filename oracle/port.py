@@ -1,0 +1,137 @@
+"""oracle/port.py -- ctypes binding of oracle/libhector_oracle.so, the plain-C restatement
+(TEST INFRASTRUCTURE ONLY: tests/, __graft_entry__.smoke(), bench.py cpu_baseline)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libhector_oracle.so")
+NHALO = 26
+NRAW = 18 + NHALO
+
+OUT_NAMES = ["CO2_concentration", "global_tas", "RF_tot", "RF_CO2", "heatflux", "ocean_c", "HL_pH",
+             "atmos_co2", "sst", "permafrost_c", "CH4_concentration", "N2O_concentration",
+             "O3_concentration", "land_tas", "veg_c", "detritus_c", "soil_c", "thawedp_c",
+             "earth_c", "NBP", "ocean_uptake", "LL_pH", "HL_PCO2", "LL_PCO2", "HL_ocean_c",
+             "LL_ocean_c", "IO_ocean_c", "DO_ocean_c", "RF_CH4", "RF_N2O", "rh_ch4",
+             "ocean_timesteps"]
+NOUT = len(OUT_NAMES)
+STATUS = {0: "OK", 1: "NEGATIVE", 2: "MASS", 3: "RETRIES", 4: "NOROOT", 5: "YEARFRACTION",
+          6: "CO2SARF", 7: "STEPPER"}
+
+
+class Params(C.Structure):
+    _fields_ = (
+        [(n, C.c_int) for n in ("start_year", "end_year", "do_spinup", "max_spinup")]
+        + [(n, C.c_double) for n in (
+            "S", "diff", "qco2", "beta", "q10_rh", "f_nppv", "f_nppd", "f_litterd", "npp_flux0",
+            "C0", "veg_c", "detritus_c", "soil_c", "permafrost_c", "warmingfactor", "rh_ch4_frac",
+            "pf_mu", "pf_sigma", "fpf_static", "tt", "tu", "twi", "tid", "preind_C_surface",
+            "preind_C_ID")]
+        + [("spinup_chem", C.c_int)]
+        + [(n, C.c_double) for n in (
+            "eps_abs", "eps_rel", "dt", "eps_spinup", "baseyear", "aero_scalar", "vol_scalar",
+            "delta_co2", "delta_ch4", "delta_n2o", "rho_bc", "rho_oc", "rho_so2", "rho_nh3",
+            "M0", "Tsoil", "Tstrat", "UC_CH4", "TOH0", "CNOX", "CCO", "CNMVOC", "CCH4", "PO3",
+            "N0", "UC_N2O", "TN2O0")]
+        + [(n, C.c_double * NHALO) for n in (
+            "halo_tau", "halo_rho", "halo_delta", "halo_H0", "halo_molarMass")]
+    )
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "rhs_evals", "steps_accepted", "steps_rejected", "integrate_calls", "newton_iterations",
+        "newton_calls", "spinup_steps")]
+
+
+class SpinState(C.Structure):
+    _fields_ = ([(n, C.c_double) for n in ("atmos", "veg", "det", "soil", "permafrost", "thawed",
+                                           "earth")]
+                + [("ocean", C.c_double * 4), ("alk_HL", C.c_double), ("alk_LL", C.c_double),
+                   ("spinup_steps", C.c_int)])
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            build()
+        L = C.CDLL(SO)
+        L.ho_default_params.argtypes = [C.POINTER(Params)]
+        L.ho_run_member.argtypes = [C.POINTER(Params), C.POINTER(C.c_double), C.c_int,
+                                    C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int),
+                                    C.POINTER(Counters), C.POINTER(SpinState)]
+        L.ho_run_member.restype = C.c_int
+        L.ho_csys.argtypes = [C.c_double] * 6 + [C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.ho_csys.restype = C.c_double
+        L.ho_gas_series.argtypes = [C.POINTER(Params), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ho_doeclim_kernel.argtypes = [C.c_double, C.c_int, C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def default_params(**over):
+    p = Params()
+    lib().ho_default_params(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def run_member(raw, params=None, run_to=-1, **over):
+    """-> (status, fail_year, out[NOUT, nyears], counters dict, spin-up state dict)"""
+    p = params if params is not None else default_params()
+    for k, v in over.items():
+        setattr(p, k, v)
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    assert raw.shape == (p.end_year - p.start_year + 1, NRAW), raw.shape
+    ny = (p.end_year if run_to < 0 else run_to) - p.start_year
+    out = np.empty((NOUT, ny))
+    fy = C.c_int(0)
+    cnt = Counters()
+    sp = SpinState()
+    st = lib().ho_run_member(C.byref(p), _dp(raw), run_to, _dp(out), ny, C.byref(fy),
+                             C.byref(cnt), C.byref(sp))
+    cd = {n: int(getattr(cnt, n)) for n, _ in Counters._fields_}
+    sd = {n: getattr(sp, n) for n in ("atmos", "veg", "det", "soil", "permafrost", "thawed",
+                                      "earth", "alk_HL", "alk_LL", "spinup_steps")}
+    sd["ocean"] = list(sp.ocean)
+    return st, fy.value, out, cd, sd
+
+
+def csys(Tbox, carbon, alk, volume, S=34.5, U=6.7):
+    out = np.empty(8)
+    it = C.c_int(0)
+    h = lib().ho_csys(Tbox, carbon, alk, volume, S, U, _dp(out), C.byref(it))
+    return h, out, it.value
+
+
+def gas_series(raw, params=None):
+    p = params if params is not None else default_params()
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    n = raw.shape[0]
+    n2o = np.empty(n)
+    hrf = np.empty((n, NHALO))
+    lib().ho_gas_series(C.byref(p), _dp(raw), _dp(n2o), _dp(hrf))
+    return n2o, hrf
+
+
+def doeclim_kernel(diff, ns):
+    k = np.empty(ns)
+    lib().ho_doeclim_kernel(diff, ns, _dp(k))
+    return k

@@ -1,0 +1,192 @@
+"""tests/golden/make_golden.py -- regenerates the committed fixtures.  Runs ONLY in the build
+container (needs /root/reference and oracle/_ref/libhector_ref.so); the fixtures it writes are
+what travels to the GPU box.
+
+  scenarios.npz       dense raw scenario tables [556][44] for the 8 shipped SSP inis, read from
+                      /root/reference/inst/input/*.ini + tables/*.csv with the reference's
+                      tseries semantics (exact key / linear interpolation / single value).
+  hector_comp.npz     the reference's own golden trajectories
+                      (/root/reference/tests/testthat/compdata/hector_comp.csv, 10 vars x 556 yr).
+  ref_runs.npz        known-answer trajectories produced by the UNMODIFIED reference
+                      (oracle/_ref) for a set of parameter vectors / scenarios, incl. the
+                      expected-failure member.
+"""
+import csv
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+HALOS = ["CF4", "C2F6", "HFC23", "HFC32", "HFC4310", "HFC125", "HFC134a", "HFC143a", "HFC227ea",
+         "HFC245fa", "SF6", "CFC11", "CFC12", "CFC113", "CFC114", "CFC115", "CCl4", "CH3CCl3",
+         "HCFC22", "HCFC141b", "HCFC142b", "halon1211", "halon1301", "halon2402", "CH3Cl",
+         "CH3Br"]
+# (section, variable) in HO_RAW_* order (oracle/hector_oracle.h)
+RAW = [("simpleNbox", "ffi_emissions"), ("simpleNbox", "daccs_uptake"),
+       ("simpleNbox", "luc_emissions"), ("simpleNbox", "luc_uptake"),
+       ("CH4", "CH4_emissions"), ("CH4", "CH4N"),
+       ("OH", "NOX_emissions"), ("OH", "CO_emissions"), ("OH", "NMVOC_emissions"),
+       ("bc", "BC_emissions"), ("oc", "OC_emissions"), ("so2", "SO2_emissions"),
+       ("nh3", "NH3_emissions"), ("so2", "SV"), ("simpleNbox", "RF_albedo"),
+       ("forcing", "RF_misc"), ("N2O", "N2O_emissions"), ("N2O", "N2O_natural_emissions")]
+RAW += [("%s_halocarbon" % h, "%s_emissions" % h) for h in HALOS]
+RAW_NAMES = [v for _, v in RAW]
+SCENARIOS = ["ssp119", "ssp126", "ssp245", "ssp370", "ssp434", "ssp460", "ssp534-over", "ssp585"]
+
+
+def parse_ini(path):
+    """{section: {key: value-string}} with ';' comments stripped (inih semantics, src/ini.c)."""
+    out, sec = {}, None
+    for line in open(path):
+        line = line.split(";")[0].strip()
+        if not line:
+            continue
+        if line.startswith("["):
+            sec = line[1:line.index("]")]
+            out.setdefault(sec, {})
+        elif "=" in line:
+            k, v = line.split("=", 1)
+            out[sec][k.strip()] = v.strip()
+    return out
+
+
+def read_csv_column(path, var):
+    """csv_table_reader.cpp:115-196 -> {date: value}"""
+    rows = {}
+    header = None
+    for line in open(path, newline=""):
+        line = line.rstrip("\r\n")
+        if not line or line.startswith(";"):
+            continue
+        cells = [c.strip() for c in line.split(",")]
+        if header is None:
+            header = cells
+            col = header.index(var, 1)
+            continue
+        if cells[0] == "UNITS" or cells[col] == "":
+            continue
+        rows[float(cells[0])] = float(cells[col])
+    return rows
+
+
+def tseries_get(series, t):
+    """tseries.hpp:317-334 + h_interpolator.cpp:109-125 (linear, flat ends)"""
+    if len(series) == 1:
+        return next(iter(series.values()))
+    if t in series:
+        return series[t]
+    xs = sorted(series)
+    if t < xs[0]:
+        return series[xs[0]]
+    if t >= xs[-1]:
+        return series[xs[-1]]
+    i = max(k for k, x in enumerate(xs) if x <= t)
+    x0, x1 = xs[i], xs[i + 1]
+    y0, y1 = series[x0], series[x1]
+    return y0 + (t - x0) * (y1 - y0) / (x1 - x0)
+
+
+def scenario_table(scn):
+    ini_path = os.path.join(REF, "inst/input/hector_%s.ini" % scn)
+    ini = parse_ini(ini_path)
+    start, end = int(ini["core"]["startDate"]), int(ini["core"]["endDate"])
+    tab = np.zeros((end - start + 1, len(RAW)))
+    for j, (sec, var) in enumerate(RAW):
+        series = {}
+        for k, v in ini[sec].items():
+            if k == var and v.startswith("csv:"):
+                series = read_csv_column(os.path.join(os.path.dirname(ini_path), v[4:]), var)
+            elif k == var:
+                series = {0.0: float(v)}
+            elif k.startswith(var + "["):
+                series[float(k[len(var) + 1:-1])] = float(v)
+        assert series, (sec, var)
+        for r in range(end - start + 1):
+            tab[r, j] = tseries_get(series, float(start + r))
+    return tab, ini
+
+
+REF_VARS = ["CO2_concentration", "global_tas", "RF_tot", "RF_CO2", "heatflux", "ocean_c", "HL_pH",
+            "atmos_co2", "sst", "permafrost_c", "CH4_concentration", "N2O_concentration",
+            "O3_concentration", "land_tas", "veg_c", "detritus_c", "soil_c", "thawedp_c",
+            "earth_c", "NBP", "ocean_uptake", "LL_pH", "HL_PCO2", "LL_PCO2", "HL_ocean_c",
+            "LL_ocean_c", "IO_ocean_c", "DO_ocean_c", "RF_CH4", "RF_N2O", "rh_ch4"]
+
+
+def lhs(M, seed=20241017):
+    """SURVEY.md section 8(d) sampler: (S, q10_rh, beta, diff) Latin hypercube."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lo = np.array([2.0, 1.0, 0.2, 0.5])
+    hi = np.array([5.0, 2.6, 0.9, 2.5])
+    cols = []
+    for j in range(4):
+        u = (rng.permutation(M) + rng.random(M)) / M
+        cols.append(lo[j] + u * (hi[j] - lo[j]))
+    return np.stack(cols, axis=1)
+
+
+def main():
+    from oracle import ref
+    # 1. scenarios
+    tabs = {}
+    for s in SCENARIOS:
+        tabs[s], _ = scenario_table(s)
+    np.savez_compressed(os.path.join(OUT, "scenarios.npz"), names=np.array(RAW_NAMES),
+                        **{s.replace("-", "_"): t for s, t in tabs.items()})
+    # 2. the reference's own golden file
+    gold = {}
+    for r in csv.DictReader(open(os.path.join(REF, "tests/testthat/compdata/hector_comp.csv"))):
+        gold.setdefault(r["variable"], {})[int(r["year"])] = float(r["value"])
+    gv = sorted(gold)
+    np.savez_compressed(os.path.join(OUT, "hector_comp.npz"), variables=np.array(gv),
+                        years=np.arange(1745, 2301),
+                        values=np.array([[gold[v][y] for y in range(1745, 2301)] for v in gv]))
+    # 3. reference KAT runs
+    cases = []  # (name, scenario, params)
+    cases.append(("default_ssp245", "ssp245", {}))
+    cases.append(("default_ssp585", "ssp585", {}))
+    cases.append(("default_ssp119", "ssp119", {}))
+    cases.append(("default_ssp534-over", "ssp534-over", {}))
+    cases.append(("corner_lo_ssp245", "ssp245", dict(S=1.5, q10_rh=1.0, beta=0.1, diff=0.3)))
+    cases.append(("corner_hi_ssp245", "ssp245", dict(S=6.0, q10_rh=3.5, beta=1.0, diff=3.0)))
+    cases.append(("fail_ssp585", "ssp585", dict(S=8.0, q10_rh=4.0, beta=0.05, diff=0.2)))
+    cases.append(("aero_vol_ssp370", "ssp370", dict(aero_scalar=1.4, vol_scalar=0.85, S=3.7)))
+    cases.append(("nppv_ssp245", "ssp245", dict(f_nppv=0.3)))
+    X = lhs(16)
+    for i in range(16):
+        cases.append(("lhs16_%02d" % i, "ssp245",
+                      dict(S=X[i, 0], q10_rh=X[i, 1], beta=X[i, 2], diff=X[i, 3])))
+    # full variable list for a few cases, a short list for the rest (keeps the fixture small);
+    # rows that were not requested are NaN
+    FULL = {"default_ssp245", "default_ssp585", "corner_hi_ssp245", "aero_vol_ssp370"}
+    SHORT = ["CO2_concentration", "global_tas", "RF_tot", "ocean_c", "HL_pH", "permafrost_c",
+             "CH4_concentration", "rh_ch4"]
+    TINY = ["CO2_concentration", "global_tas"]
+    names, scns, pnames, pvals, outs, oks, errs = [], [], [], [], [], [], []
+    for name, scn, params in cases:
+        want = REF_VARS if name in FULL else (TINY if name.startswith("lhs") else SHORT)
+        ok, err, o, _ = ref.run_member(os.path.join(REF, "inst/input/hector_%s.ini" % scn),
+                                       params, want)
+        out = np.full((len(REF_VARS) + 1, o.shape[1]), np.nan)
+        for k, v in enumerate(want):
+            out[REF_VARS.index(v)] = o[k]
+        out[-1] = o[-1]
+        print(name, ok, err[:80])
+        names.append(name); scns.append(scn); oks.append(ok); errs.append(err)
+        pnames.append(",".join(params.keys()))
+        pvals.append(np.array(list(params.values()) + [np.nan] * (8 - len(params))))
+        outs.append(out)
+    np.savez_compressed(os.path.join(OUT, "ref_runs.npz"), names=np.array(names),
+                        scenarios=np.array(scns), param_names=np.array(pnames),
+                        param_values=np.array(pvals), ok=np.array(oks), errors=np.array(errs),
+                        variables=np.array(REF_VARS + ["ocean_timesteps"]),
+                        values=np.array(outs))
+
+
+if __name__ == "__main__":
+    main()

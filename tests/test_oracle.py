@@ -1,0 +1,116 @@
+"""The CPU oracle (oracle/hector_oracle.c) pinned against (a) the reference's own golden file
+and (b) trajectories produced by the unmodified reference (oracle/_ref), both committed as
+fixtures under tests/golden/ by tests/golden/make_golden.py.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import port
+from tests import util
+
+
+def test_forcing_key_order():
+    """forcing_component.cpp:492-495 sums a std::map<string,...> in byte-wise key order; the
+    oracle hard-codes that order -- re-derive it here."""
+    halos = ["CF4", "C2F6", "HFC23", "HFC32", "HFC4310", "HFC125", "HFC134a", "HFC143a",
+             "HFC227ea", "HFC245fa", "SF6", "CFC11", "CFC12", "CFC113", "CFC114", "CFC115", "CCl4",
+             "CH3CCl3", "HCFC22", "HCFC141b", "HCFC142b", "halon1211", "halon1301", "halon2402",
+             "CH3Cl", "CH3Br"]
+    keys = ["RF_" + h for h in halos] + ["RF_" + k for k in (
+        "BC", "OC", "NH3", "SO2", "aci", "vol", "misc", "albedo", "CO2", "N2O", "CH4",
+        "H2O_strat", "O3_trop")]
+    order = sorted(keys, key=lambda s: s.encode())
+    expect = ("BC C2F6 CCl4 CF4 CFC11 CFC113 CFC114 CFC115 CFC12 CH3Br CH3CCl3 CH3Cl CH4 CO2 "
+              "H2O_strat HCFC141b HCFC142b HCFC22 HFC125 HFC134a HFC143a HFC227ea HFC23 HFC245fa "
+              "HFC32 HFC4310 N2O NH3 O3_trop OC SF6 SO2 aci albedo halon1211 halon1301 halon2402 "
+              "misc vol").split()
+    assert [k[3:] for k in order] == expect
+    assert len(order) == 39
+
+
+def test_golden_file_ssp245():
+    """tests/testthat/test_old-new.R:8-36 uses 20 years and tolerance 1e-10 (mean relative
+    difference); we use all 555 years and also the pointwise metric."""
+    gold, years = util.hector_comp()
+    st, fy, out, cnt, sp = port.run_member(util.scenarios()["ssp245"])
+    assert st == 0
+    for v, g in gold.items():
+        x = out[port.OUT_NAMES.index(v)]
+        r = g[1:]
+        mean_rel = np.abs(x - r).sum() / np.abs(r).sum()
+        assert mean_rel < 1e-11, (v, mean_rel)
+        assert util.parity_err(x, r, v) < 1e-10, v
+    # work counters measured on the unmodified reference
+    assert cnt["spinup_steps"] == 498
+    assert cnt["newton_iterations"] == 122958
+    assert cnt["steps_accepted"] == 2887 and cnt["steps_rejected"] == 0
+    assert cnt["integrate_calls"] == 2339
+
+
+def test_post_spinup_state():
+    """SURVEY.md appendix C (unmodified reference, post-spin-up pools at 1745)."""
+    st, fy, out, cnt, sp = port.run_member(util.scenarios()["ssp245"], run_to=1746)
+    assert st == 0
+    assert sp["veg"] == 561.99999976352547
+    assert sp["det"] == 62.348941166518344
+    assert sp["soil"] == 2030.5895679096495
+    assert sp["atmos"] == 590.32949999999994
+    assert sp["ocean"] == [146.61027582946105, 818.13107318705886, 8784.0600248177307,
+                           27118.260117326001]
+    assert 2100e-6 < sp["alk_HL"] < 2750e-6 and 2100e-6 < sp["alk_LL"] < 2750e-6
+
+
+@pytest.mark.parametrize("case", util.ref_runs(), ids=lambda c: c["name"])
+def test_against_reference_runs(case):
+    """every committed reference trajectory: same failure verdict, same per-year ocean sub-step
+    counts, values equal to ~1 ulp accumulated (observed: bit-identical)."""
+    raw = util.scenarios()[case["scenario"]]
+    st, fy, out, cnt, sp = port.run_member(raw, **case["params"])
+    if not case["ok"]:
+        assert st == 1 and "may not be negative" in case["error"]
+        return
+    assert st == 0
+    for v, ref in case["values"].items():
+        if np.isnan(ref).all():
+            continue
+        x = out[port.OUT_NAMES.index(v)]
+        if v == "ocean_timesteps":
+            assert np.array_equal(x, ref)
+        else:
+            assert np.allclose(x, ref, rtol=1e-12, atol=1e-13), (v, np.abs(x - ref).max())
+
+
+def test_failed_member_reports_year():
+    case = [c for c in util.ref_runs() if not c["ok"]][0]
+    st, fy, out, cnt, sp = port.run_member(util.scenarios()[case["scenario"]], **case["params"])
+    assert st == 1
+    ref_years_done = int(np.sum(~np.isnan(case["values"]["CO2_concentration"])))
+    assert fy == 1746 + ref_years_done
+    assert np.isnan(out[0][ref_years_done:]).all() and not np.isnan(out[0][:ref_years_done]).any()
+
+
+def test_chemistry_spot_values():
+    """SURVEY.md appendix C chemistry spot values (alk = 2300e-6)."""
+    area = 3.6e14
+    h, o, it = port.csys(1.6, 146.61027582946105, 2300e-6, area * 0.15 * 100)
+    assert abs(h - 1.0836826583516344e-8) < 1e-20 and it == 35
+    assert abs(o[0] - 7.965097876380755) < 1e-13
+    h, o, it = port.csys(20.9, 818.13107318705886, 2300e-6, area * (1 - 0.15) * 100)
+    assert abs(h - 1.7116774980069958e-8) < 1e-20 and it == 35
+    assert abs(o[0] - 7.766578058601485) < 1e-13
+
+
+def test_reference_lib_if_present():
+    """when oracle/_ref was built (build container / travelled to the GPU box) the restatement
+    must be bit-identical to it on a fresh run."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    params = dict(S=4.2, q10_rh=1.7, beta=0.4, diff=2.1)
+    ok, err, o, secs = ref.run_member(ref.ini_path("ssp126"), params,
+                                      ["CO2_concentration", "global_tas", "HL_pH"])
+    assert ok, err
+    st, fy, out, cnt, sp = port.run_member(util.scenarios()["ssp126"], **params)
+    assert st == 0
+    for k, v in enumerate(["CO2_concentration", "global_tas", "HL_pH"]):
+        assert np.array_equal(out[port.OUT_NAMES.index(v)], o[k]), v
+    assert np.array_equal(out[-1], o[-1])

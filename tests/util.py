@@ -1,0 +1,64 @@
+"""Shared helpers for the tests: fixtures loading, parity metric."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+_cache = {}
+
+
+def scenarios():
+    if "sc" not in _cache:
+        z = np.load(os.path.join(GOLDEN, "scenarios.npz"))
+        _cache["sc"] = {k.replace("_over", "-over") if k.endswith("_over") else k: z[k]
+                        for k in z.files if k != "names"}
+        _cache["sc_names"] = [str(s) for s in z["names"]]
+    return _cache["sc"]
+
+
+def raw_names():
+    scenarios()
+    return _cache["sc_names"]
+
+
+def hector_comp():
+    z = np.load(os.path.join(GOLDEN, "hector_comp.npz"))
+    return dict(zip([str(v) for v in z["variables"]], z["values"])), z["years"]
+
+
+def ref_runs():
+    z = np.load(os.path.join(GOLDEN, "ref_runs.npz"))
+    cases = []
+    variables = [str(v) for v in z["variables"]]
+    for i, name in enumerate(z["names"]):
+        pn = str(z["param_names"][i])
+        keys = pn.split(",") if pn else []
+        params = {k: float(z["param_values"][i][j]) for j, k in enumerate(keys)}
+        cases.append(dict(name=str(name), scenario=str(z["scenarios"][i]), params=params,
+                          ok=bool(z["ok"][i]), error=str(z["errors"][i]),
+                          values=dict(zip(variables, z["values"][i]))))
+    return cases
+
+
+FLOOR = {"global_tas": 0.01, "CO2_concentration": 1.0, "sst": 0.01, "land_tas": 0.01,
+         "heatflux": 0.1, "RF_tot": 0.01, "RF_CO2": 0.01}
+
+
+def parity_err(x, ref, var):
+    """max_t |x - ref| / max(|ref|, floor_var)  """
+    floor = FLOOR.get(var, 1e-3)
+    return float(np.max(np.abs(x - ref) / np.maximum(np.abs(ref), floor)))
+
+
+def lhs(M, seed=20241017):
+    """SURVEY.md section 8(d) sampler: columns (S, q10_rh, beta, diff)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lo = np.array([2.0, 1.0, 0.2, 0.5])
+    hi = np.array([5.0, 2.6, 0.9, 2.5])
+    cols = []
+    for j in range(4):
+        u = (rng.permutation(M) + rng.random(M)) / M
+        cols.append(lo[j] + u * (hi[j] - lo[j]))
+    return np.stack(cols, axis=1)
