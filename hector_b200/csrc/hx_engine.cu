@@ -1,0 +1,813 @@
+/* hx_engine.cu -- host side of libhector_b200.so: the engine object behind the C ABI
+ * (include/hector_b200.h).  Owns the device buffers, flattens scenarios and parameters into
+ * the SoA layout of hx_layout.h, precomputes the member-independent gas series on the host
+ * (N2O concentration, halocarbon forcings) and drives the kernels of hx_kernels.cu.
+ *
+ * There is no CPU fallback: without a CUDA device hx_create fails.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/hector_b200.h"
+#include "hx_kernels.h"
+#include "hx_names.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      char buf_[512];                                                                    \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+               __FILE__, __LINE__);                                                      \
+      return fail(HX_ERR_CUDA, buf_);                                                    \
+    }                                                                                    \
+  } while (0)
+
+/* ---- small utility kernels ---- */
+__global__ void k_fill(double *p, double v, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+/* dst[dev_of_api[i]] = src[i] */
+__global__ void k_scatter(double *dst, const double *src, const int32_t *dev_of_api, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[dev_of_api[i]] = src[i];
+}
+__global__ void k_gather(double *dst, const double *src, const int32_t *dev_of_api, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[dev_of_api[i]];
+}
+/* out[m_api][k] = src[yidx[k]][dev_of_api[m_api]]  (tile transpose through shared memory) */
+__global__ void k_fetch_transpose(double *out, const double *src, const int32_t *yidx,
+                                  const int32_t *dev_of_api, int n_dates, int M, size_t Mpad) {
+  __shared__ double tile[32][33];
+  const int m0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int k = k0 + j, m = m0 + threadIdx.x;
+    if (k < n_dates && m < M) tile[j][threadIdx.x] = src[(size_t)yidx[k] * Mpad + dev_of_api[m]];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int m = m0 + j, k = k0 + threadIdx.x;
+    if (k < n_dates && m < M) out[(size_t)m * n_dates + k] = tile[threadIdx.x][j];
+  }
+}
+/* copy member `src_m`'s state column into every active member (shared spin-up, E-7) */
+__global__ void k_broadcast_state(double *S, int32_t *spinup_steps, int32_t *status,
+                                  int32_t *fail_year, int src_m, int n_state, size_t Mpad) {
+  size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (m >= Mpad || status[m] < 0 || (int)m == src_m) return;
+  for (int i = 0; i < n_state; ++i) S[(size_t)i * Mpad + m] = S[(size_t)i * Mpad + src_m];
+  spinup_steps[m] = spinup_steps[src_m];
+  status[m] = status[src_m];
+  fail_year[m] = fail_year[src_m];
+}
+
+struct Engine {
+  hx_config cfg{};
+  HxConst C{};
+  HxDev d{};
+  std::string err;
+  int M = 0, Mpad = 0, nrow = 0, nscen = 0;
+  bool prepared = false, params_dirty = false;
+  int cur_row = 0;
+  double last_run_ms = 0.0;
+
+  /* host-side inputs */
+  std::vector<std::vector<double>> raw;      /* [scen][RAW_COUNT * nrow], series-major */
+  std::vector<std::vector<char>> raw_set;    /* [scen][RAW_COUNT] */
+  std::vector<int32_t> member_scen;          /* API order */
+  double pscalar[PI_COUNT];
+  std::vector<double> pvec[PI_COUNT];        /* per-member overrides (API order), host copy */
+  bool pvec_on_device_only[PI_COUNT];
+  double baseyear = 1750, UC_N2O = 4.8, TN2O0 = 132;
+  int max_spinup = 2000;
+  double halo_tau[HX_NHALO], halo_rho[HX_NHALO], halo_delta[HX_NHALO], halo_H0[HX_NHALO],
+      halo_mm[HX_NHALO];
+  std::vector<int> out_sel;                  /* OUT_* ids in slot order */
+
+  /* permutation API <-> device */
+  std::vector<int32_t> dev_of_api;
+  int32_t *d_dev_of_api = nullptr;
+  bool identity_perm = true;
+
+  /* device buffers */
+  double *d_P = nullptr, *d_S = nullptr, *d_S_snap = nullptr, *d_D = nullptr, *d_ker = nullptr,
+         *d_sst = nullptr, *d_tland = nullptr, *d_out = nullptr, *d_scen = nullptr,
+         *d_stage = nullptr;
+  int32_t *d_block_scen = nullptr, *d_status = nullptr, *d_status_snap = nullptr,
+          *d_status_post = nullptr,
+          *d_fail_year = nullptr, *d_spinup_steps = nullptr, *d_yidx = nullptr;
+  unsigned long long *d_counters = nullptr;
+  size_t stage_bytes = 0, yidx_cap = 0;
+  double *h_pinned = nullptr;
+  size_t pinned_bytes = 0;
+
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  int fail(int code, const std::string &msg) {
+    err = msg;
+    return code;
+  }
+
+  int find_param(const char *name) const {
+    for (int i = 0; i < PI_COUNT; ++i)
+      if (!strcmp(hx::kParams[i].name, name)) return i;
+    return -1;
+  }
+  static int find_raw(const char *name) {
+    for (int i = 0; i < RAW_HALO0; ++i)
+      if (!strcmp(hx::kRawNames[i], name)) return i;
+    for (int g = 0; g < HX_NHALO; ++g) {
+      std::string s = std::string(hx::kHaloNames[g]) + "_emissions";
+      if (s == name) return RAW_HALO0 + g;
+    }
+    return -1;
+  }
+  static int find_out(const char *name) {
+    for (int i = 0; i < OUT_COUNT; ++i)
+      if (!strcmp(hx::kOutNames[i], name)) return i;
+    return -1;
+  }
+
+  int ensure_stage(size_t bytes) {
+    if (bytes <= stage_bytes) return HX_OK;
+    if (d_stage) cudaFree(d_stage);
+    d_stage = nullptr;
+    stage_bytes = 0;
+    CUDA_TRY(cudaMalloc(&d_stage, bytes));
+    stage_bytes = bytes;
+    return HX_OK;
+  }
+  int ensure_pinned(size_t bytes) {
+    if (bytes <= pinned_bytes) return HX_OK;
+    if (h_pinned) cudaFreeHost(h_pinned);
+    h_pinned = nullptr;
+    pinned_bytes = 0;
+    CUDA_TRY(cudaMallocHost(&h_pinned, bytes));
+    pinned_bytes = bytes;
+    return HX_OK;
+  }
+
+  /* ---- member-independent gas series on the host (E-5) ----
+   * N2OComponent::run (n2o_component.cpp:150-191): tau = TN2O0 (N2O/N0)^-0.05,
+   *   dN2O = (E + E_nat)/UC_N2O - N2O/tau
+   * HalocarbonComponent::run (halocarbon_component.cpp:181-229): exponential decay + emissions,
+   *   RF = rho Ha (1 + delta) */
+  void gas_series(int s, std::vector<double> &n2o, std::vector<double> &halo_rf) const {
+    const double *R = raw[s].data();
+    auto rawv = [&](int series, int r) { return R[(size_t)series * nrow + r]; };
+    const double N0 = pscalar[PI_N0];
+    n2o.assign(nrow, 0.0);
+    halo_rf.assign((size_t)nrow * HX_NHALO, 0.0);
+    n2o[0] = N0;
+    for (int r = 1; r < nrow; ++r) {
+      const double previous_n2o = n2o[r - 1];
+      const double tau = TN2O0 * (std::pow(previous_n2o / N0, -0.05));
+      const double current_n2oem = rawv(RAW_N2O_E, r) + rawv(RAW_N2O_NAT, r);
+      const double dN2O = current_n2oem / UC_N2O - previous_n2o / tau;
+      n2o[r] = previous_n2o + dN2O;
+    }
+    for (int g = 0; g < HX_NHALO; ++g) {
+      double Ha = halo_H0[g];
+      const double tau = halo_tau[g];
+      for (int r = 1; r < nrow; ++r) {
+        const double timestep = 1.0;
+        const double alpha = 1 / tau;
+        const double emissMol = rawv(RAW_HALO0 + g, r) / halo_mm[g] * timestep;
+        const double concDeltaEmiss = emissMol / (0.1 * 1.8);
+        const double expfac = std::exp(-alpha);
+        Ha = Ha * expfac + concDeltaEmiss * tau * (1.0 - expfac);
+        const double rf_unadjusted = halo_rho[g] * Ha;
+        halo_rf[(size_t)r * HX_NHALO + g] = rf_unadjusted + halo_delta[g] * rf_unadjusted;
+      }
+    }
+  }
+
+  void free_device() {
+    void *ptrs[] = {d_P, d_S, d_S_snap, d_D, d_ker, d_sst, d_tland, d_out, d_scen, d_stage,
+                    d_block_scen, d_status, d_status_snap, d_status_post, d_fail_year, d_spinup_steps, d_yidx,
+                    d_counters, d_dev_of_api};
+    for (void *p : ptrs)
+      if (p) cudaFree(p);
+    d_P = d_S = d_S_snap = d_D = d_ker = d_sst = d_tland = d_out = d_scen = d_stage = nullptr;
+    d_block_scen = d_status = d_status_snap = d_status_post = d_fail_year = d_spinup_steps = d_yidx = nullptr;
+    d_counters = nullptr;
+    d_dev_of_api = nullptr;
+    stage_bytes = 0;
+    yidx_cap = 0;
+  }
+
+  int upload_param(int pi) {
+    double *dst = d_P + (size_t)pi * Mpad;
+    if (pvec_on_device_only[pi]) return HX_OK; /* already resident (hx_set_param_device) */
+    if (pvec[pi].empty()) {
+      k_fill<<<(Mpad + 255) / 256, 256, 0, stream>>>(dst, pscalar[pi], (size_t)Mpad);
+    } else {
+      int rc = ensure_pinned((size_t)Mpad * sizeof(double));
+      if (rc) return rc;
+      /* the pinned buffer may still feed an earlier async copy */
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      for (int i = 0; i < Mpad; ++i) h_pinned[i] = pscalar[pi];
+      for (int i = 0; i < M; ++i) h_pinned[dev_of_api[i]] = pvec[pi][i];
+      CUDA_TRY(cudaMemcpyAsync(dst, h_pinned, (size_t)Mpad * sizeof(double),
+                               cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return HX_OK;
+  }
+
+  bool spinup_shared() const {
+    for (int pi : hx::kSpinupParams)
+      if (!pvec[pi].empty() || pvec_on_device_only[pi]) return false;
+    return true;
+  }
+
+  int first_active = 0;
+
+  int run_setup_and_spinup() {
+    CUDA_TRY(cudaMemcpyAsync(d_status, d_status_snap, (size_t)Mpad * sizeof(int32_t),
+                             cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(hx::launch_setup(d, C, stream));
+    if (spinup_shared() && M > 1) {
+      /* E-7: nothing that shapes the spin-up or the alkalinity equilibration varies across
+       * members, so one member's spin-up serves the ensemble: run it on one thread and
+       * broadcast the state rows it touches (SI_ATMOS .. SI_SOLVER_DT) */
+      CUDA_TRY(hx::launch_spinup_one(d, C, first_active, stream));
+      k_broadcast_state<<<(Mpad + 255) / 256, 256, 0, stream>>>(
+          d_S, d_spinup_steps, d_status, d_fail_year, first_active, SI_SOLVER_DT + 1, (size_t)Mpad);
+      CUDA_TRY(cudaGetLastError());
+    } else {
+      CUDA_TRY(hx::launch_spinup(d, C, stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_S_snap, d_S, (size_t)SI_COUNT * Mpad * sizeof(double),
+                             cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_status_post, d_status, (size_t)Mpad * sizeof(int32_t),
+                             cudaMemcpyDeviceToDevice, stream));
+    cur_row = 0;
+    params_dirty = false;
+    return HX_OK;
+  }
+};
+
+} // namespace
+
+struct hx_engine : Engine {};
+
+using hx::kParams;
+
+extern "C" {
+
+const char *hx_version(void) { return "hector_b200 0.1 (sm_100a)"; }
+
+const char *hx_last_error(hx_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int hx_create(const hx_config *cfg, hx_handle *out) {
+  if (!cfg || !out) {
+    g_create_error = "hx_create: null argument";
+    return HX_ERR_ARG;
+  }
+  *out = nullptr;
+  if (cfg->n_members <= 0 || cfg->n_scenarios <= 0 || cfg->end_year <= cfg->start_year) {
+    g_create_error = "hx_create: need n_members > 0, n_scenarios > 0, end_year > start_year";
+    return HX_ERR_ARG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("hx_create: no CUDA device (") + cudaGetErrorString(e) +
+                     "); the engine has no CPU path";
+    return HX_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = "hx_create: bad device ordinal";
+    return HX_ERR_ARG;
+  }
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return HX_ERR_CUDA;
+  }
+  hx_engine *h = new hx_engine();
+  h->cfg = *cfg;
+  h->M = cfg->n_members;
+  h->nscen = cfg->n_scenarios;
+  h->nrow = cfg->end_year - cfg->start_year + 1;
+  h->raw.assign(h->nscen, std::vector<double>((size_t)RAW_COUNT * h->nrow, 0.0));
+  h->raw_set.assign(h->nscen, std::vector<char>(RAW_COUNT, 0));
+  h->member_scen.assign(h->M, 0);
+  for (int i = 0; i < PI_COUNT; ++i) {
+    h->pscalar[i] = kParams[i].dflt;
+    h->pvec_on_device_only[i] = false;
+  }
+  for (int g = 0; g < HX_NHALO; ++g) {
+    h->halo_tau[g] = hx::kHaloTau[g]; h->halo_rho[g] = hx::kHaloRho[g];
+    h->halo_delta[g] = hx::kHaloDelta[g]; h->halo_H0[g] = hx::kHaloH0[g];
+    h->halo_mm[g] = hx::kHaloMolarMass[g];
+  }
+  h->out_sel = {OUT_CO2, OUT_TAS};
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+    g_create_error = "hx_create: could not create stream/events";
+    delete h;
+    return HX_ERR_CUDA;
+  }
+  h->stream = h->own_stream;
+  *out = h;
+  return HX_OK;
+}
+
+int hx_destroy(hx_handle h) {
+  if (!h) return HX_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->free_device();
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return HX_OK;
+}
+
+int hx_set_stream(hx_handle h, void *cuda_stream) {
+  if (!h) return HX_ERR_ARG;
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return HX_OK;
+}
+
+int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, int32_t year0,
+                           int32_t n, const double *values) {
+  if (!h || !name || !values) return HX_ERR_ARG;
+  if (h->prepared) return h->fail(HX_ERR_STATE, "scenario series must be set before hx_prepare");
+  if (scenario_id < 0 || scenario_id >= h->nscen) return h->fail(HX_ERR_ARG, "bad scenario id");
+  const int si = Engine::find_raw(name);
+  if (si < 0) return h->fail(HX_ERR_ARG, std::string("unknown scenario series: ") + name);
+  if (year0 > h->cfg.start_year || year0 + n - 1 < h->cfg.end_year)
+    return h->fail(HX_ERR_ARG, std::string("series does not cover start..end: ") + name);
+  double *dst = h->raw[scenario_id].data() + (size_t)si * h->nrow;
+  for (int r = 0; r < h->nrow; ++r) dst[r] = values[h->cfg.start_year - year0 + r];
+  h->raw_set[scenario_id][si] = 1;
+  return HX_OK;
+}
+
+int hx_set_scenario_table(hx_handle h, int32_t scenario_id, int32_t n_names,
+                          const char *const *names, int32_t year0, int32_t n_years,
+                          const double *values) {
+  if (!h || !names || !values) return HX_ERR_ARG;
+  std::vector<double> col(n_years);
+  for (int j = 0; j < n_names; ++j) {
+    for (int r = 0; r < n_years; ++r) col[r] = values[(size_t)r * n_names + j];
+    int rc = hx_set_scenario_series(h, scenario_id, names[j], year0, n_years, col.data());
+    if (rc) return rc;
+  }
+  return HX_OK;
+}
+
+int hx_set_member_scenario(hx_handle h, const int32_t *scen, int32_t n) {
+  if (!h || !scen) return HX_ERR_ARG;
+  if (h->prepared) return h->fail(HX_ERR_STATE, "member scenarios must be set before hx_prepare");
+  if (n != h->M) return h->fail(HX_ERR_ARG, "hx_set_member_scenario: n != n_members");
+  for (int i = 0; i < n; ++i)
+    if (scen[i] < 0 || scen[i] >= h->nscen) return h->fail(HX_ERR_ARG, "scenario id out of range");
+  h->member_scen.assign(scen, scen + n);
+  return HX_OK;
+}
+
+static int set_special_scalar(hx_engine *h, const char *name, double v) {
+  if (!strcmp(name, "baseyear")) { h->baseyear = v; return 1; }
+  if (!strcmp(name, "max_spinup")) { h->max_spinup = (int)v; return 1; }
+  if (!strcmp(name, "UC_N2O")) { h->UC_N2O = v; return 1; }
+  if (!strcmp(name, "TN2O0")) { h->TN2O0 = v; return 1; }
+  const char *dot = strchr(name, '.');
+  if (dot) { /* "<gas>.tau" etc. */
+    std::string gas(name, dot - name), field(dot + 1);
+    for (int g = 0; g < HX_NHALO; ++g)
+      if (gas == hx::kHaloNames[g]) {
+        if (field == "tau") h->halo_tau[g] = v;
+        else if (field == "rho") h->halo_rho[g] = v;
+        else if (field == "delta") h->halo_delta[g] = v;
+        else if (field == "H0") h->halo_H0[g] = v;
+        else if (field == "molarMass") h->halo_mm[g] = v;
+        else return 0;
+        return 1;
+      }
+  }
+  return 0;
+}
+
+int hx_set_param_scalar(hx_handle h, const char *name, double value) {
+  if (!h || !name) return HX_ERR_ARG;
+  const int pi = h->find_param(name);
+  if (pi < 0) {
+    if (h->prepared) return h->fail(HX_ERR_STATE, std::string(name) + " must be set before hx_prepare");
+    if (set_special_scalar(h, name, value)) return HX_OK;
+    return h->fail(HX_ERR_ARG, std::string("unknown parameter: ") + name);
+  }
+  if (pi == PI_N0 && h->prepared)
+    return h->fail(HX_ERR_STATE, "N0 feeds the host N2O series; set it before hx_prepare");
+  h->pscalar[pi] = value;
+  h->pvec[pi].clear();
+  h->pvec_on_device_only[pi] = false;
+  if (h->prepared) {
+    cudaSetDevice(h->cfg.device);
+    int rc = h->upload_param(pi);
+    if (rc) return rc;
+    h->params_dirty = true;
+  }
+  return HX_OK;
+}
+
+int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_t n) {
+  if (!h || !name || !per_member) return HX_ERR_ARG;
+  const int pi = h->find_param(name);
+  if (pi < 0) return h->fail(HX_ERR_ARG, std::string("unknown per-member parameter: ") + name);
+  if (pi == PI_N0) return h->fail(HX_ERR_UNSUPPORTED, "N0 is scalar only (host N2O series)");
+  if (n != h->M) return h->fail(HX_ERR_ARG, "hx_set_param: n != n_members");
+  h->pvec[pi].assign(per_member, per_member + n);
+  h->pvec_on_device_only[pi] = false;
+  if (h->prepared) {
+    cudaSetDevice(h->cfg.device);
+    int rc = h->upload_param(pi);
+    if (rc) return rc;
+    h->params_dirty = true;
+  }
+  return HX_OK;
+}
+
+int hx_set_param_device(hx_handle h, const char *name, const double *dev, int32_t n) {
+  if (!h || !name || !dev) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_set_param_device needs hx_prepare first");
+  const int pi = h->find_param(name);
+  if (pi < 0 || pi == PI_N0) return h->fail(HX_ERR_ARG, std::string("bad per-member parameter: ") + name);
+  if (n != h->M) return h->fail(HX_ERR_ARG, "hx_set_param_device: n != n_members");
+  cudaSetDevice(h->cfg.device);
+  double *dst = h->d_P + (size_t)pi * h->Mpad;
+  if (h->identity_perm) {
+    cudaError_t e = cudaMemcpyAsync(dst, dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                    h->stream);
+    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
+  } else {
+    k_scatter<<<(n + 255) / 256, 256, 0, h->stream>>>(dst, dev, h->d_dev_of_api, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
+  }
+  h->pvec[pi].clear();
+  h->pvec_on_device_only[pi] = true;
+  h->params_dirty = true;
+  return HX_OK;
+}
+
+int hx_get_param(hx_handle h, const char *name, double *out, int32_t n) {
+  if (!h || !name || !out) return HX_ERR_ARG;
+  const int pi = h->find_param(name);
+  if (pi < 0) return h->fail(HX_ERR_ARG, std::string("unknown parameter: ") + name);
+  if (n != h->M) return h->fail(HX_ERR_ARG, "hx_get_param: n != n_members");
+  if (h->pvec_on_device_only[pi]) {
+    cudaSetDevice(h->cfg.device);
+    std::vector<double> tmp(h->Mpad);
+    cudaStreamSynchronize(h->stream);
+    cudaError_t e = cudaMemcpy(tmp.data(), h->d_P + (size_t)pi * h->Mpad,
+                               (size_t)h->Mpad * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
+    for (int i = 0; i < n; ++i) out[i] = tmp[h->dev_of_api[i]];
+  } else if (h->pvec[pi].empty()) {
+    for (int i = 0; i < n; ++i) out[i] = h->pscalar[pi];
+  } else {
+    memcpy(out, h->pvec[pi].data(), (size_t)n * sizeof(double));
+  }
+  return HX_OK;
+}
+
+int hx_select_outputs(hx_handle h, int32_t n, const char *const *names) {
+  if (!h || (n > 0 && !names)) return HX_ERR_ARG;
+  if (h->prepared) return h->fail(HX_ERR_STATE, "outputs must be selected before hx_prepare");
+  std::vector<int> sel;
+  for (int i = 0; i < n; ++i) {
+    const int id = Engine::find_out(names[i]);
+    if (id < 0) return h->fail(HX_ERR_ARG, std::string("unknown output variable: ") + names[i]);
+    if (std::find(sel.begin(), sel.end(), id) == sel.end()) sel.push_back(id);
+  }
+  h->out_sel = sel;
+  return HX_OK;
+}
+
+int hx_prepare(hx_handle h) {
+  if (!h) return HX_ERR_ARG;
+  if (h->prepared) return h->fail(HX_ERR_STATE, "hx_prepare called twice");
+  cudaSetDevice(h->cfg.device);
+  for (int s = 0; s < h->nscen; ++s)
+    for (int i = 0; i < RAW_COUNT; ++i)
+      if (!h->raw_set[s][i]) {
+        std::string nm = i < RAW_HALO0 ? hx::kRawNames[i]
+                                       : std::string(hx::kHaloNames[i - RAW_HALO0]) + "_emissions";
+        return h->fail(HX_ERR_STATE, "scenario " + std::to_string(s) + ": series not set: " + nm);
+      }
+  auto fail = [&](int code, const char *msg) { return h->fail(code, msg); };
+  const int M = h->M, nrow = h->nrow;
+
+  /* members grouped by scenario; every scenario segment padded to whole CTAs */
+  std::vector<int> count(h->nscen, 0), seg_start(h->nscen, 0);
+  for (int i = 0; i < M; ++i) count[h->member_scen[i]]++;
+  int Mpad = 0;
+  std::vector<int32_t> block_scen;
+  for (int s = 0; s < h->nscen; ++s) {
+    seg_start[s] = Mpad;
+    const int nb = (count[s] + HX_BLOCK - 1) / HX_BLOCK;
+    for (int b = 0; b < nb; ++b) block_scen.push_back(s);
+    Mpad += nb * HX_BLOCK;
+  }
+  h->Mpad = Mpad;
+  h->dev_of_api.resize(M);
+  std::vector<int> fillp(seg_start);
+  h->identity_perm = true;
+  for (int i = 0; i < M; ++i) {
+    h->dev_of_api[i] = fillp[h->member_scen[i]]++;
+    if (h->dev_of_api[i] != i) h->identity_perm = false;
+  }
+  std::vector<int32_t> status(Mpad, -1);
+  for (int i = 0; i < M; ++i) status[h->dev_of_api[i]] = 0;
+  h->first_active = h->dev_of_api[0];
+
+  /* constants */
+  HxConst &C = h->C;
+  C.start_year = h->cfg.start_year; C.end_year = h->cfg.end_year; C.nrow = nrow;
+  C.baseyear = h->baseyear == 0.0 ? h->cfg.start_year + 1 : (int)h->baseyear;
+  C.max_spinup = h->max_spinup;
+  C.flags = h->cfg.flags;
+  C.S = 34.5; /* ocean_component.cpp:291 */
+  C.sqrtS = std::sqrt(C.S);
+  C.S15 = std::pow(C.S, (3.0 / 2.0));
+  C.bor = 1 * (416.0 * (C.S / 35.0)) * 1.e-6; /* ocean_csys.cpp:287 */
+  {
+    const double part_high = 0.15, part_low = 1 - part_high;
+    const double thick_LL = 100, thick_HL = 100, thick_inter = 1000 - thick_LL,
+                 thick_deep = 3777 - thick_inter - thick_LL;
+    const double ocean_area = 3.6e14;
+    C.vol_LL = ocean_area * part_low * thick_LL;
+    C.vol_HL = ocean_area * part_high * thick_HL;
+    C.vol_IO = ocean_area * thick_inter;
+    C.vol_DO = ocean_area * thick_deep;
+    C.As_HL = ocean_area * part_high;
+    C.As_LL = ocean_area * part_low;
+    C.U = 6.7;
+    C.spy_ocean = 60 * 60 * 24 * 365.25;
+  }
+  {
+    const double ocean_area = (1.0 - 0.29) * 5100656E8;
+    C.powtoheat = ocean_area * (60.0 * 60.0 * 24.0 * 365.2422) / std::pow(10.0, 22);
+  }
+
+  /* device scenario tables */
+  std::vector<double> tab((size_t)h->nscen * nrow * SC_STRIDE, 0.0);
+  for (int s = 0; s < h->nscen; ++s) {
+    std::vector<double> n2o, hrf;
+    h->gas_series(s, n2o, hrf);
+    const double *R = h->raw[s].data();
+    for (int r = 0; r < nrow; ++r) {
+      double *row = tab.data() + ((size_t)s * nrow + r) * SC_STRIDE;
+      for (int c = 0; c <= SC_MISC; ++c) row[c] = R[(size_t)c * nrow + r]; /* RAW_x == SC_x up to MISC */
+      row[SC_N2O] = n2o[r];
+      for (int g = 0; g < HX_NHALO; ++g) row[SC_HALO0 + g] = hrf[(size_t)r * HX_NHALO + g];
+    }
+  }
+
+  const size_t Mp = Mpad;
+  const int nsel = (int)h->out_sel.size();
+  if (cudaMalloc(&h->d_P, PI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_S, SI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_S_snap, SI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_D, DI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_ker, (size_t)(nrow + 1) * Mp * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_sst, (size_t)nrow * Mp * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_tland, (size_t)nrow * Mp * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_out, std::max<size_t>(1, (size_t)nsel * (nrow - 1) * Mp) * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_scen, tab.size() * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_block_scen, block_scen.size() * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&h->d_status, Mp * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&h->d_status_snap, Mp * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&h->d_status_post, Mp * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&h->d_fail_year, Mp * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&h->d_spinup_steps, Mp * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&h->d_counters, HX_NCOUNTERS * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&h->d_dev_of_api, (size_t)M * sizeof(int32_t)) != cudaSuccess) {
+    cudaError_t e = cudaGetLastError();
+    h->free_device();
+    return fail(HX_ERR_CUDA, (std::string("device allocation failed: ") + cudaGetErrorString(e)).c_str());
+  }
+  cudaStream_t st = h->stream;
+  cudaMemcpyAsync(h->d_scen, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(h->d_block_scen, block_scen.data(), block_scen.size() * sizeof(int32_t),
+                  cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(h->d_status_snap, status.data(), Mp * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(h->d_dev_of_api, h->dev_of_api.data(), (size_t)M * sizeof(int32_t),
+                  cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st);
+  cudaMemsetAsync(h->d_fail_year, 0, Mp * sizeof(int32_t), st);
+  cudaMemsetAsync(h->d_spinup_steps, 0, Mp * sizeof(int32_t), st);
+  cudaMemsetAsync(h->d_S, 0, SI_COUNT * Mp * sizeof(double), st);
+  cudaMemsetAsync(h->d_D, 0, DI_COUNT * Mp * sizeof(double), st);
+  cudaMemsetAsync(h->d_ker, 0, (size_t)(nrow + 1) * Mp * sizeof(double), st);
+  cudaMemsetAsync(h->d_sst, 0, (size_t)nrow * Mp * sizeof(double), st);
+  cudaMemsetAsync(h->d_tland, 0, (size_t)nrow * Mp * sizeof(double), st);
+  if (cudaStreamSynchronize(st) != cudaSuccess)
+    return fail(HX_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+
+  HxDev &d = h->d;
+  d.Mpad = Mpad; d.P = h->d_P; d.S = h->d_S; d.D = h->d_D; d.ker = h->d_ker;
+  d.sst_hist = h->d_sst; d.tland_hist = h->d_tland; d.out = h->d_out; d.scen = h->d_scen;
+  d.block_scen = h->d_block_scen; d.status = h->d_status; d.fail_year = h->d_fail_year;
+  d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters;
+  for (int i = 0; i < OUT_COUNT; ++i) d.out_slot[i] = -1;
+  for (int s = 0; s < nsel; ++s) d.out_slot[h->out_sel[s]] = s;
+
+  h->prepared = true; /* upload_param / set_param paths need the buffers */
+  for (int pi = 0; pi < PI_COUNT; ++pi) {
+    int rc = h->upload_param(pi);
+    if (rc) { h->prepared = false; return rc; }
+  }
+  int rc = h->run_setup_and_spinup();
+  if (rc) { h->prepared = false; return rc; }
+  if (cudaStreamSynchronize(st) != cudaSuccess) {
+    h->prepared = false;
+    return fail(HX_ERR_CUDA, (std::string("set-up/spin-up kernels: ") +
+                              cudaGetErrorString(cudaGetLastError())).c_str());
+  }
+  return HX_OK;
+}
+
+int hx_reset(hx_handle h) {
+  if (!h) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_reset before hx_prepare");
+  cudaSetDevice(h->cfg.device);
+  if (h->params_dirty) {
+    /* Core::reset(date < start) re-runs prepareToRun incl. spin-up (core.cpp:511-549) */
+    return h->run_setup_and_spinup();
+  }
+  cudaError_t e = cudaMemcpyAsync(h->d_S, h->d_S_snap, (size_t)SI_COUNT * h->Mpad * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, h->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h->d_status, h->d_status_post, (size_t)h->Mpad * sizeof(int32_t),
+                        cudaMemcpyDeviceToDevice, h->stream);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
+  h->cur_row = 0;
+  return HX_OK;
+}
+
+int hx_run(hx_handle h, double run_to_date) {
+  if (!h) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_run before hx_prepare");
+  cudaSetDevice(h->cfg.device);
+  if (h->params_dirty) {
+    int rc = h->run_setup_and_spinup();
+    if (rc) return rc;
+  }
+  int to = run_to_date < 0 ? h->cfg.end_year : (int)run_to_date;
+  if (to > h->cfg.end_year) return h->fail(HX_ERR_ARG, "run_to_date beyond end_year");
+  const int r1 = to - h->cfg.start_year;
+  if (r1 <= h->cur_row) return HX_OK; /* "Requested run-to date <= current date. Models not run." */
+  cudaStream_t st = h->stream;
+  cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st);
+  cudaEventRecord(h->ev0, st);
+  cudaError_t e = hx::launch_run(h->d, h->C, h->cur_row, r1, st);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("run kernel launch: ") + cudaGetErrorString(e));
+  if (!h->out_sel.empty()) {
+    e = hx::launch_nan_fill(h->d, h->C, (int)h->out_sel.size(), h->cur_row, r1, st);
+    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("nan fill launch: ") + cudaGetErrorString(e));
+  }
+  cudaEventRecord(h->ev1, st);
+  h->cur_row = r1;
+  return HX_OK;
+}
+
+int hx_synchronize(hx_handle h) {
+  if (!h) return HX_ERR_ARG;
+  cudaSetDevice(h->cfg.device);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
+  return HX_OK;
+}
+
+double hx_last_run_ms(hx_handle h) {
+  if (!h || !h->prepared) return -1.0;
+  cudaSetDevice(h->cfg.device);
+  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+double hx_current_date(hx_handle h) { return h ? h->cfg.start_year + h->cur_row : -1.0; }
+
+int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates, double *out) {
+  if (!h || !name || !dates || !out || n_dates <= 0) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_fetch before hx_prepare");
+  const int id = Engine::find_out(name);
+  if (id < 0) return h->fail(HX_ERR_ARG, std::string("unknown output variable: ") + name);
+  const int slot = h->d.out_slot[id];
+  if (slot < 0) return h->fail(HX_ERR_ARG, std::string(name) + " was not selected with hx_select_outputs");
+  cudaSetDevice(h->cfg.device);
+  std::vector<int32_t> yidx(n_dates);
+  for (int k = 0; k < n_dates; ++k) {
+    const int r = (int)dates[k] - h->cfg.start_year;
+    if (r < 1 || r > h->cur_row)
+      return h->fail(HX_ERR_ARG, "date outside (start_year, current date]");
+    yidx[k] = r - 1;
+  }
+  int rc = h->ensure_stage((size_t)h->M * n_dates * sizeof(double));
+  if (rc) return rc;
+  if ((size_t)n_dates > h->yidx_cap) {
+    if (h->d_yidx) cudaFree(h->d_yidx);
+    h->d_yidx = nullptr;
+    if (cudaMalloc(&h->d_yidx, (size_t)n_dates * sizeof(int32_t)) != cudaSuccess)
+      return h->fail(HX_ERR_CUDA, "cudaMalloc yidx");
+    h->yidx_cap = n_dates;
+  }
+  cudaStream_t st = h->stream;
+  cudaMemcpyAsync(h->d_yidx, yidx.data(), (size_t)n_dates * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  const double *src = h->d_out + (size_t)slot * (h->nrow - 1) * h->Mpad;
+  dim3 grid((h->M + 31) / 32, (n_dates + 31) / 32), block(32, 8);
+  k_fetch_transpose<<<grid, block, 0, st>>>(h->d_stage, src, h->d_yidx, h->d_dev_of_api, n_dates,
+                                           h->M, (size_t)h->Mpad);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(out, h->d_stage, (size_t)h->M * n_dates * sizeof(double),
+                        cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_fetch: ") + cudaGetErrorString(e));
+  return HX_OK;
+}
+
+int hx_output_device(hx_handle h, const char *name, const double **dev_ptr, int64_t *member_stride,
+                     int32_t *n_years) {
+  if (!h || !name || !dev_ptr) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_output_device before hx_prepare");
+  const int id = Engine::find_out(name);
+  if (id < 0 || h->d.out_slot[id] < 0) return h->fail(HX_ERR_ARG, std::string("output not recorded: ") + name);
+  *dev_ptr = h->d_out + (size_t)h->d.out_slot[id] * (h->nrow - 1) * h->Mpad;
+  if (member_stride) *member_stride = h->Mpad;
+  if (n_years) *n_years = h->nrow - 1;
+  return HX_OK;
+}
+
+int hx_member_status(hx_handle h, int32_t *status, int32_t *fail_year, int32_t n) {
+  if (!h || n != h->M) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_member_status before hx_prepare");
+  cudaSetDevice(h->cfg.device);
+  std::vector<int32_t> st(h->Mpad), fy(h->Mpad);
+  cudaStreamSynchronize(h->stream);
+  cudaError_t e = cudaMemcpy(st.data(), h->d_status, (size_t)h->Mpad * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(fy.data(), h->d_fail_year, (size_t)h->Mpad * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
+  for (int i = 0; i < n; ++i) {
+    if (status) status[i] = st[h->dev_of_api[i]];
+    if (fail_year) fail_year[i] = fy[h->dev_of_api[i]];
+  }
+  return HX_OK;
+}
+
+int hx_counters(hx_handle h, uint64_t *out, int32_t n) {
+  if (!h || !out || n < 1) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_counters before hx_prepare");
+  cudaSetDevice(h->cfg.device);
+  unsigned long long tmp[HX_NCOUNTERS];
+  cudaStreamSynchronize(h->stream);
+  cudaError_t e = cudaMemcpy(tmp, h->d_counters, sizeof tmp, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
+  for (int i = 0; i < n && i < HX_NCOUNTERS; ++i) out[i] = tmp[i];
+  return HX_OK;
+}
+
+int hx_spinup_state(hx_handle h, int32_t member, double *out14) {
+  if (!h || !out14 || member < 0 || member >= h->M) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_spinup_state before hx_prepare");
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  const int dm = h->dev_of_api[member];
+  static const int idx[13] = {SI_ATMOS, SI_VEG, SI_DET, SI_SOIL, SI_PERMAFROST, SI_THAWED, SI_EARTH,
+                              SI_BOX_HL, SI_BOX_LL, SI_BOX_IO, SI_BOX_DO, SI_ALK_HL, SI_ALK_LL};
+  for (int k = 0; k < 13; ++k) {
+    cudaError_t e = cudaMemcpy(out14 + k, h->d_S_snap + (size_t)idx[k] * h->Mpad + dm, sizeof(double),
+                               cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
+  }
+  int32_t steps = 0;
+  cudaMemcpy(&steps, h->d_spinup_steps + dm, sizeof steps, cudaMemcpyDeviceToHost);
+  out14[13] = steps;
+  return HX_OK;
+}
+
+} /* extern "C" */

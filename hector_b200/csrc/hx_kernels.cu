@@ -1,0 +1,709 @@
+/* hx_kernels.cu -- sm_100a kernels of the Hector ensemble engine.
+ *
+ *   hx_setup_kernel   per member: derived constants (ocean exchange rates, DOECLIM matrices and
+ *                     lag kernel) and the pre-spin-up state          [prepareToRun of every component]
+ *   hx_spinup_kernel  per member: spin the carbon cycle up to steady state, then equilibrate the
+ *                     surface-box alkalinities (Brent)               [Core::run_spinup + chem_equilibrate]
+ *   hx_run_kernel     per member: the yearly coupled step for a run segment; the scenario table
+ *                     is streamed through shared memory in slabs with cp.async.bulk + mbarrier
+ *                                                                   [Core::run year loop]
+ *
+ * One thread owns one member; all per-member arrays are SoA so warps read/write 256 B rows.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "hx_kernels.h"
+#include "hx_model.cuh"
+
+namespace hx {
+
+/* ---- small PTX wrappers: mbarrier + bulk async copy (TMA engine, UBLKCP in SASS) ---- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                         uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+#define PAR(i) __ldg(d.P + (size_t)(i) * d.Mpad + m)
+#define STATE(i) d.S[(size_t)(i) * d.Mpad + m]
+#define DER(i) d.D[(size_t)(i) * d.Mpad + m]
+
+__device__ __forceinline__ LandPar load_landpar(const HxDev &d, int m) {
+  LandPar p;
+  p.beta = PAR(PI_BETA); p.q10 = PAR(PI_Q10); p.f_nppv = PAR(PI_F_NPPV); p.f_nppd = PAR(PI_F_NPPD);
+  p.f_litterd = PAR(PI_F_LITTERD); p.npp_flux0 = PAR(PI_NPP_FLUX0); p.C0 = PAR(PI_C0);
+  p.wf = PAR(PI_WARMINGFACTOR); p.rh_ch4_frac = PAR(PI_RH_CH4_FRAC); p.pf_mu = PAR(PI_PF_MU);
+  p.pf_sigma = PAR(PI_PF_SIGMA); p.fpf_static = PAR(PI_FPF_STATIC); p.eps_abs = PAR(PI_EPS_ABS);
+  p.eps_rel = PAR(PI_EPS_REL);
+  p.k_LL_HL = DER(DI_K_LL_HL); p.k_LL_IO = DER(DI_K_LL_IO); p.k_HL_DO = DER(DI_K_HL_DO);
+  p.k_IO_LL = DER(DI_K_IO_LL); p.k_IO_HL = DER(DI_K_IO_HL); p.k_IO_DO = DER(DI_K_IO_DO);
+  p.k_DO_IO = DER(DI_K_DO_IO);
+  return p;
+}
+
+__device__ __forceinline__ void load_member(const HxDev &d, int m, Member &mb) {
+  mb.atmos = STATE(SI_ATMOS); mb.veg = STATE(SI_VEG); mb.det = STATE(SI_DET);
+  mb.soil = STATE(SI_SOIL); mb.perm = STATE(SI_PERMAFROST); mb.thawed = STATE(SI_THAWED);
+  mb.earth = STATE(SI_EARTH);
+  mb.bHL = STATE(SI_BOX_HL); mb.bLL = STATE(SI_BOX_LL); mb.bIO = STATE(SI_BOX_IO);
+  mb.bDO = STATE(SI_BOX_DO);
+  mb.alkHL = STATE(SI_ALK_HL); mb.alkLL = STATE(SI_ALK_LL);
+  mb.hHL = STATE(SI_H_HL); mb.hLL = STATE(SI_H_LL);
+  mb.tempferts_last = STATE(SI_TEMPFERTS); mb.f_frozen = STATE(SI_F_FROZEN);
+  mb.cum_luc_va = STATE(SI_CUM_LUC_VA); mb.eos_vegc = STATE(SI_EOS_VEGC);
+  mb.masstot = STATE(SI_MASSTOT); mb.cum_pf_ch4 = STATE(SI_CUM_PF_CH4);
+  mb.rh_ch4 = STATE(SI_RH_CH4);
+  mb.max_timestep = STATE(SI_MAX_TIMESTEP); mb.timeout = (int)STATE(SI_TIMEOUT);
+  mb.lastflux_ann = STATE(SI_LASTFLUX_ANN); mb.solver_dt = STATE(SI_SOLVER_DT);
+  mb.status = 0; mb.neg = false; mb.timesteps = 0; mb.flux_sum = 0.0; mb.nbp = 0.0;
+  mb.pco2HL = mb.pco2LL = 0.0;
+}
+
+__device__ __forceinline__ void store_member(const HxDev &d, int m, const Member &mb) {
+  STATE(SI_ATMOS) = mb.atmos; STATE(SI_VEG) = mb.veg; STATE(SI_DET) = mb.det;
+  STATE(SI_SOIL) = mb.soil; STATE(SI_PERMAFROST) = mb.perm; STATE(SI_THAWED) = mb.thawed;
+  STATE(SI_EARTH) = mb.earth;
+  STATE(SI_BOX_HL) = mb.bHL; STATE(SI_BOX_LL) = mb.bLL; STATE(SI_BOX_IO) = mb.bIO;
+  STATE(SI_BOX_DO) = mb.bDO;
+  STATE(SI_ALK_HL) = mb.alkHL; STATE(SI_ALK_LL) = mb.alkLL;
+  STATE(SI_H_HL) = mb.hHL; STATE(SI_H_LL) = mb.hLL;
+  STATE(SI_TEMPFERTS) = mb.tempferts_last; STATE(SI_F_FROZEN) = mb.f_frozen;
+  STATE(SI_CUM_LUC_VA) = mb.cum_luc_va; STATE(SI_EOS_VEGC) = mb.eos_vegc;
+  STATE(SI_MASSTOT) = mb.masstot; STATE(SI_CUM_PF_CH4) = mb.cum_pf_ch4;
+  STATE(SI_RH_CH4) = mb.rh_ch4;
+  STATE(SI_MAX_TIMESTEP) = mb.max_timestep; STATE(SI_TIMEOUT) = (double)mb.timeout;
+  STATE(SI_LASTFLUX_ANN) = mb.lastflux_ann; STATE(SI_SOLVER_DT) = mb.solver_dt;
+}
+
+__device__ __forceinline__ void flush_work(const HxDev &d, const Work &w, unsigned years,
+                                           unsigned failed) {
+  /* integer atomics only: sums are order-independent, results stay bit-reproducible */
+  unsigned long long *c = d.counters;
+  atomicAdd(c + HX_CNT_RHS_EVALS, (unsigned long long)w.rhs);
+  atomicAdd(c + HX_CNT_RK_STEPS, (unsigned long long)w.steps);
+  atomicAdd(c + HX_CNT_RK_REJECTED, (unsigned long long)w.rejected);
+  atomicAdd(c + HX_CNT_STASHES, (unsigned long long)w.stashes);
+  atomicAdd(c + HX_CNT_NEWTON_ITERS, (unsigned long long)w.newton_it);
+  atomicAdd(c + HX_CNT_NEWTON_CALLS, (unsigned long long)w.newton_calls);
+  atomicAdd(c + HX_CNT_FAILED_MEMBERS, (unsigned long long)failed);
+  atomicAdd(c + HX_CNT_MEMBER_YEARS, (unsigned long long)years);
+}
+
+/* ======================================================================================== */
+/* set-up: OceanComponent::prepareToRun (ocean_component.cpp:202-319),
+ * TemperatureComponent::prepareToRun (temperature_component.cpp:196-413),
+ * SimpleNbox::prepareToRun (simpleNbox-runtime.cpp:61-197) and the CH4/solver initial values. */
+__global__ void __launch_bounds__(HX_BLOCK)
+hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C) {
+  const int m = blockIdx.x * HX_BLOCK + threadIdx.x;
+  if (m >= d.Mpad) return;
+  if (d.status[m] < 0) return; /* padding lane */
+
+  /* ocean exchange rates (fraction of the box per year), ocean_component.cpp:262-284 */
+  const double spy = C.spy_ocean;
+  const double tt = PAR(PI_TT), tu = PAR(PI_TU), twi = PAR(PI_TWI), tid = PAR(PI_TID);
+  const double LL_HL = (tt * spy) / C.vol_LL;
+  const double HL_DO = ((tt + tu) * spy) / C.vol_HL;
+  const double DO_IO = ((tt + tu) * spy) / C.vol_DO;
+  const double IO_HL = (tu * spy) / C.vol_IO;
+  const double IO_LL = (tt * spy) / C.vol_IO;
+  const double IO_LLex = (twi * spy) / C.vol_IO;
+  const double LL_IOex = (twi * spy) / C.vol_LL;
+  const double DO_IOex = (tid * spy) / C.vol_DO;
+  const double IO_DOex = (tid * spy) / C.vol_IO;
+  DER(DI_K_LL_HL) = LL_HL; DER(DI_K_LL_IO) = LL_IOex; DER(DI_K_HL_DO) = HL_DO;
+  DER(DI_K_IO_LL) = IO_LL + IO_LLex; DER(DI_K_IO_HL) = IO_HL; DER(DI_K_IO_DO) = IO_DOex;
+  DER(DI_K_DO_IO) = DO_IO + DO_IOex;
+
+  /* DOECLIM, temperature_component.cpp:248-412 */
+  const double dt = 1.0, ak = DC_AK, bk = DC_BK, csw = DC_CSW, rlam = DC_RLAM, bsi = DC_BSI,
+               cal = DC_CAL, cas = DC_CAS, flnd = DC_FLND, fso = DC_FSO;
+  const double S = PAR(PI_S), diff = PAR(PI_DIFF), qco2 = PAR(PI_QCO2);
+  const double kcon = DC_SECS_PER_YEAR / 10000;
+  const double cnum = rlam * flnd + bsi * (1.0 - flnd);
+  const double cden = rlam * flnd - ak * (rlam - bsi);
+  const double cfl = flnd * cnum / cden * qco2 / S - bk * (rlam - bsi) / cden;
+  const double cfs = (rlam * flnd - ak / (1.0 - flnd) * (rlam - bsi)) * cnum / cden * qco2 / S +
+                     rlam * flnd / (1.0 - flnd) * bk * (rlam - bsi) / cden;
+  const double kls = bk * rlam * flnd / cden - ak * flnd * cnum / cden * qco2 / S;
+  const double keff = kcon * diff;
+  const double taubot = (DC_ZBOT * DC_ZBOT) / keff;
+  const double taucfs = cas / cfs;
+  const double taucfl = cal / cfl;
+  const double taudif = (cas * cas) / (csw * csw) * M_PI / keff;
+  const double tauksl = (1.0 - flnd) * cas / kls;
+  const double taukls = flnd * cal / kls;
+
+  /* lag kernel K(j), j = 1..nrow (E-4); Ker[i] of the reference is K(ns - i) */
+  const double tau = taubot / dt;
+  double *ker = d.ker + m;
+  const size_t Mp = d.Mpad;
+  ker[0] = 0.0;
+  const double K1v = ker_first(tau);
+  ker[1 * Mp] = K1v;
+  KerTerm tm1 = ker_term(tau, 1.0), tc = ker_term(tau, 2.0);
+  for (int j = 2; j <= C.nrow; ++j) {
+    KerTerm tp = ker_term(tau, (double)(j + 1));
+    ker[(size_t)j * Mp] = ker_combine(tau, tm1, tc, tp);
+    tm1 = tc;
+    tc = tp;
+  }
+
+  double Cc[4], A[4], B[4];
+  Cc[0] = 1.0 / (taucfl * taucfl) + 1.0 / (taukls * taukls) + 2.0 / taucfl / taukls +
+          bsi / taukls / tauksl;
+  Cc[1] = -1 * bsi / (taukls * taukls) - bsi / taucfl / taukls - bsi / taucfs / taukls -
+          (bsi * bsi) / taukls / tauksl;
+  Cc[2] = -1 * bsi / (tauksl * tauksl) - 1.0 / taucfs / tauksl - 1.0 / taucfl / tauksl -
+          1.0 / taukls / tauksl;
+  Cc[3] = 1.0 / (taucfs * taucfs) + (bsi * bsi) / (tauksl * tauksl) + 2.0 * bsi / taucfs / tauksl +
+          bsi / taukls / tauksl;
+  for (int i = 0; i < 4; i++) Cc[i] = Cc[i] * ((dt * dt) / 12.0);
+  const double sqdt = sqrt(dt / taudif);
+  B[0] = 1.0 + dt / (2.0 * taucfl) + dt / (2.0 * taukls);
+  B[1] = -dt / (2.0 * taukls) * bsi;
+  B[2] = -dt / (2.0 * tauksl);
+  B[3] = 1.0 + dt / (2.0 * taucfs) + dt / (2.0 * tauksl) * bsi + 2.0 * fso * sqdt;
+  A[0] = 1.0 - dt / (2.0 * taucfl) - dt / (2.0 * taukls);
+  A[1] = dt / (2.0 * taukls) * bsi;
+  A[2] = dt / (2.0 * tauksl);
+  A[3] = 1.0 - dt / (2.0 * taucfs) - dt / (2.0 * tauksl) * bsi + K1v * fso * sqdt;
+  for (int i = 0; i < 4; i++) {
+    B[i] = B[i] + Cc[i];
+    A[i] = A[i] + Cc[i];
+  }
+  /* invert_1d_2x2_matrix, temperature_component.cpp:81-94 */
+  const double det = (B[0] * B[3] - B[1] * B[2]);
+  const double inv = 1 / det;
+  DER(DI_A0) = A[0]; DER(DI_A1) = A[1]; DER(DI_A2) = A[2]; DER(DI_A3) = A[3];
+  DER(DI_IB0) = inv * B[3]; DER(DI_IB1) = inv * -1 * B[1]; DER(DI_IB2) = inv * -1 * B[2];
+  DER(DI_IB3) = inv * B[0];
+  DER(DI_TAUCFL) = taucfl; DER(DI_TAUKLS) = taukls; DER(DI_TAUCFS) = taucfs;
+  DER(DI_TAUKSL) = tauksl;
+  DER(DI_SQDT_TAUDIF) = sqdt;
+  DER(DI_HF_INT) = cas * fso / sqrt(taudif * dt);
+
+  /* initial pools: ocean_component.cpp:224-260, simpleNbox.cpp:45-81, simpleNbox-runtime.cpp:172 */
+  const double LL_vol_frac = C.vol_LL / (C.vol_LL + C.vol_HL);
+  const double HL_vol_frac = 1 - LL_vol_frac;
+  const double I_vol_frac = C.vol_IO / (C.vol_IO + C.vol_DO);
+  const double D_vol_frac = 1 - I_vol_frac;
+  const double pre_s = PAR(PI_PREIND_SURF), pre_id = PAR(PI_PREIND_ID);
+  STATE(SI_BOX_LL) = LL_vol_frac * pre_s;
+  STATE(SI_BOX_HL) = HL_vol_frac * pre_s;
+  STATE(SI_BOX_IO) = I_vol_frac * pre_id;
+  STATE(SI_BOX_DO) = D_vol_frac * pre_id;
+  STATE(SI_ATMOS) = PAR(PI_C0) * HX_PPMVCO2_TO_PGC;
+  STATE(SI_VEG) = PAR(PI_VEG_C0); STATE(SI_DET) = PAR(PI_DET_C0); STATE(SI_SOIL) = PAR(PI_SOIL_C0);
+  STATE(SI_PERMAFROST) = PAR(PI_PERMAFROST_C0); STATE(SI_THAWED) = 0.0; STATE(SI_EARTH) = 5500;
+  STATE(SI_ALK_HL) = 0.0; STATE(SI_ALK_LL) = 0.0; STATE(SI_H_HL) = 0.0; STATE(SI_H_LL) = 0.0;
+  STATE(SI_TEMPFERTS) = 1.0; STATE(SI_F_FROZEN) = 1.0; STATE(SI_CUM_LUC_VA) = 0.0;
+  STATE(SI_EOS_VEGC) = PAR(PI_VEG_C0); STATE(SI_MASSTOT) = 0.0; STATE(SI_CUM_PF_CH4) = 0.0;
+  STATE(SI_RH_CH4) = 0.0;
+  STATE(SI_MAX_TIMESTEP) = HX_OCEAN_MAX_TIMESTEP; STATE(SI_TIMEOUT) = 0.0;
+  STATE(SI_LASTFLUX_ANN) = 0.0; STATE(SI_SOLVER_DT) = PAR(PI_DT);
+  STATE(SI_CH4) = PAR(PI_M0); STATE(SI_TLAND) = 0.0; STATE(SI_SST) = 0.0;
+  STATE(SI_HEAT_MIXED) = 0.0; STATE(SI_HEAT_INTERIOR) = 0.0; STATE(SI_RF_PREV) = 0.0;
+  STATE(SI_BASE_TOT) = 0.0; STATE(SI_BASE_CO2) = 0.0; STATE(SI_BASE_CH4) = 0.0;
+  STATE(SI_BASE_N2O) = 0.0;
+  d.sst_hist[m] = 0.0;   /* row 0: temp_sst[0] = 0 */
+  d.tland_hist[m] = 0.0;
+  d.fail_year[m] = 0;
+  d.spinup_steps[m] = 0;
+}
+
+/* ======================================================================================== */
+/* oceanbox::chem_equilibrate (oceanbox.cpp:382-445): 21-point scan, then
+ * boost::math::tools::brent_find_minima(fmin, 2100e-6, 2750e-6, 31) on
+ * |flux(alk) - f_target|; alk is left at the LAST point evaluated (oceanbox.cpp:338). */
+struct EqBox {
+  const HxConst *C;
+  ChemK k;
+  double carbon, volume, As, CO2, target, alk, h;
+  bool ok;
+};
+__device__ __noinline__ double eq_fmin(EqBox &b, double alk, Work &w) {
+  b.alk = alk;
+  b.h = 0.0;
+  const double pco2 = csys_solve(*b.C, b.k, b.carbon, alk, b.volume, b.h, true, b.ok, w);
+  return fabs(surface_flux(b.CO2, pco2, 1.0, b.k.Tr, b.As) - b.target);
+}
+__device__ __noinline__ void chem_equilibrate(EqBox &b, Work &w) {
+  const double alk_min = 2100e-6, alk_max = 2750e-6;
+  for (double alk1 = alk_min; alk1 <= alk_max; alk1 += (alk_max - alk_min) / 20)
+    (void)eq_fmin(b, alk1, w);
+  const double tolerance = 5.9604644775390625e-08; /* ldexp(1.0, 1 - 26) */
+  double min = alk_min, max = alk_max;
+  double x, wv, v, u, delta, delta2, fu, fv, fw, fx, mid, fract1, fract2;
+  const double golden = 0.3819660f;
+  x = wv = v = max;
+  fw = fv = fx = eq_fmin(b, x, w);
+  delta2 = delta = 0;
+  for (int it = 0; it < 1000; ++it) {
+    mid = (min + max) / 2;
+    fract1 = tolerance * fabs(x) + tolerance / 4;
+    fract2 = 2 * fract1;
+    if (fabs(x - mid) <= (fract2 - (max - min) / 2)) break;
+    if (fabs(delta2) > fract1) {
+      double r = (x - wv) * (fx - fv);
+      double q = (x - v) * (fx - fw);
+      double pp = (x - v) * q - (x - wv) * r;
+      q = 2 * (q - r);
+      if (q > 0) pp = -pp;
+      q = fabs(q);
+      const double td = delta2;
+      delta2 = delta;
+      if ((fabs(pp) >= fabs(q * td / 2)) || (pp <= q * (min - x)) || (pp >= q * (max - x))) {
+        delta2 = (x >= mid) ? min - x : max - x;
+        delta = golden * delta2;
+      } else {
+        delta = pp / q;
+        u = x + delta;
+        if (((u - min) < fract2) || ((max - u) < fract2))
+          delta = (mid - x) < 0 ? -fabs(fract1) : fabs(fract1);
+      }
+    } else {
+      delta2 = (x >= mid) ? min - x : max - x;
+      delta = golden * delta2;
+    }
+    u = (fabs(delta) >= fract1) ? (x + delta)
+                                : (delta > 0 ? (x + fabs(fract1)) : (x - fabs(fract1)));
+    fu = eq_fmin(b, u, w);
+    if (fu <= fx) {
+      if (u >= x) min = x; else max = x;
+      v = wv; wv = x; x = u;
+      fv = fw; fw = fx; fx = fu;
+    } else {
+      if (u < x) min = u; else max = u;
+      if ((fu <= fw) || (wv == x)) {
+        v = wv; wv = u;
+        fv = fw; fw = fu;
+      } else if ((fu <= fv) || (v == x) || (v == wv)) {
+        v = u;
+        fv = fu;
+      }
+    }
+  }
+}
+
+/* Core::run_spinup (core.cpp:394-420) + CarbonCycleSolver::run_spinup
+ * (carbon-cycle-solver.cpp:313-370); then the first-year chemistry switch-on of
+ * OceanComponent::run (ocean_component.cpp:392-400). */
+__global__ void __launch_bounds__(HX_BLOCK)
+hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int m_offset,
+                 int only_member) {
+  const int m = m_offset + blockIdx.x * HX_BLOCK + threadIdx.x;
+  if (m >= d.Mpad) return;
+  if (d.status[m] < 0) return;
+  if (only_member >= 0 && m != only_member) return;
+  Member mb;
+  load_member(d, m, mb);
+  const LandPar p = load_landpar(d, m);
+  Work w = {0, 0, 0, 0, 0, 0};
+  const double eps_spinup = PAR(PI_EPS_SPINUP);
+  int steps = 0;
+  if (!(C.flags & HX_FLAG_NO_SPINUP)) {
+    mb.co2fert = 1.0; mb.tfd = 1.0; mb.tfs = 1.0; mb.f_new_thaw = 0.0; mb.f_frozen = 1.0;
+    mb.luc_e = mb.luc_u = mb.ffi = mb.daccs = 0.0;
+    bool spunup = false;
+    int step = 0;
+    while (!spunup && ++step < C.max_spinup) {
+      mb.flux_sum = 0.0; mb.timesteps = 0;
+      mb.npp_luc_adjust = (mb.eos_vegc - mb.cum_luc_va) / mb.eos_vegc;
+      const double o0 = mb.atmos, o1 = mb.veg, o2 = mb.det, o3 = mb.soil, o4 = mb.perm,
+                   o5 = mb.thawed, o6 = total_ocean(mb), o7 = mb.earth;
+      solver_year<true>(mb, C, p, (double)(step - 1), (double)step, true, w);
+      if (mb.status) break;
+      double mx = fabs(mb.atmos - o0);
+      mx = fmax(mx, fabs(mb.veg - o1)); mx = fmax(mx, fabs(mb.det - o2));
+      mx = fmax(mx, fabs(mb.soil - o3)); mx = fmax(mx, fabs(mb.perm - o4));
+      mx = fmax(mx, fabs(mb.thawed - o5)); mx = fmax(mx, fabs(total_ocean(mb) - o6));
+      mx = fmax(mx, fabs(mb.earth - o7));
+      spunup = (mx < eps_spinup);
+    }
+    steps = step;
+    mb.rh_ch4 = 0.0;           /* record_state in spin-up: simpleNbox.cpp:809-814 */
+    mb.tempferts_last = 1.0;
+  }
+  mb.eos_vegc = mb.veg;        /* SimpleNbox::run first call: simpleNbox-runtime.cpp:209-213 */
+  if (mb.status == 0) {
+    /* chem_equilibrate both surface boxes at SST = 0 and the post-spin-up CO2 */
+    const double CO2 = mb.atmos * HX_PGC_TO_PPMVCO2;
+    EqBox b;
+    b.C = &C; b.ok = true; b.CO2 = CO2;
+    b.k = chem_constants(C, 0.0 + HX_MEAN_TOS_TEMP + HX_DT_HL);
+    b.carbon = mb.bHL; b.volume = C.vol_HL; b.As = C.As_HL; b.target = 1.000;
+    chem_equilibrate(b, w);
+    mb.alkHL = b.alk; mb.hHL = b.h;
+    b.k = chem_constants(C, 0.0 + HX_MEAN_TOS_TEMP + HX_DT_LL);
+    b.carbon = mb.bLL; b.volume = C.vol_LL; b.As = C.As_LL; b.target = -1.000;
+    chem_equilibrate(b, w);
+    mb.alkLL = b.alk; mb.hLL = b.h;
+    if (!b.ok) mb.status = HX_MEMBER_NOROOT;
+  }
+  store_member(d, m, mb);
+  d.spinup_steps[m] = steps;
+  if (mb.status) {
+    d.status[m] = mb.status;
+    d.fail_year[m] = C.start_year;
+  }
+}
+
+/* ======================================================================================== */
+/* the yearly coupled step, rows r0+1 .. r1 (row = year - start_year) */
+__global__ void __launch_bounds__(HX_BLOCK)
+hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
+  __shared__ __align__(128) double slab[2][(HX_SLAB_YEARS + 1) * SC_STRIDE];
+  __shared__ __align__(16) double row0[SC_STRIDE];
+  __shared__ __align__(8) uint64_t bars[2];
+
+  const int tid = threadIdx.x;
+  const int m = blockIdx.x * HX_BLOCK + tid;
+  const int scen = d.block_scen[blockIdx.x];
+  const double *table = d.scen + (size_t)scen * C.nrow * SC_STRIDE;
+  const bool lane_ok = (m < d.Mpad) && (d.status[m] == 0);
+  const int nyears_total = C.nrow - 1;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < SC_STRIDE; i += HX_BLOCK) row0[i] = table[i];
+  __syncthreads();
+
+  /* slab s covers table rows base .. base+HX_SLAB_YEARS (one overlap row for the y-1 emissions),
+   * serving years base+1 .. base+HX_SLAB_YEARS */
+  const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
+  auto issue = [&](int s) {
+    const int base = r0 + s * HX_SLAB_YEARS;
+    int rows = HX_SLAB_YEARS + 1;
+    if (base + rows > C.nrow) rows = C.nrow - base;
+    const uint32_t bytes = (uint32_t)(rows * SC_STRIDE * sizeof(double));
+    fence_proxy_async();
+    mbar_arrive_expect_tx(&bars[s & 1], bytes);
+    bulk_g2s(slab[s & 1], table + (size_t)base * SC_STRIDE, bytes, &bars[s & 1]);
+  };
+  if (tid == 0 && nslab > 0) issue(0);
+
+  Member mb;
+  LandPar p;
+  ForcPar fp;
+  Work w = {0, 0, 0, 0, 0, 0};
+  double ch4 = 0, tland = 0, sst = 0, heat_mixed = 0, heat_interior = 0, rf_prev = 0;
+  double base_tot = 0, base_co2 = 0, base_ch4 = 0, base_n2o = 0;
+  unsigned years_done = 0;
+  if (lane_ok) {
+    load_member(d, m, mb);
+    p = load_landpar(d, m);
+    fp.C0 = p.C0; fp.M0 = PAR(PI_M0); fp.N0 = PAR(PI_N0); fp.aero = PAR(PI_AERO);
+    fp.vol = PAR(PI_VOL); fp.delta_co2 = PAR(PI_DELTA_CO2); fp.delta_ch4 = PAR(PI_DELTA_CH4);
+    fp.delta_n2o = PAR(PI_DELTA_N2O); fp.rho_bc = PAR(PI_RHO_BC); fp.rho_oc = PAR(PI_RHO_OC);
+    fp.rho_so2 = PAR(PI_RHO_SO2); fp.rho_nh3 = PAR(PI_RHO_NH3);
+    ch4 = STATE(SI_CH4); tland = STATE(SI_TLAND); sst = STATE(SI_SST);
+    heat_mixed = STATE(SI_HEAT_MIXED); heat_interior = STATE(SI_HEAT_INTERIOR);
+    rf_prev = STATE(SI_RF_PREV);
+    base_tot = STATE(SI_BASE_TOT); base_co2 = STATE(SI_BASE_CO2); base_ch4 = STATE(SI_BASE_CH4);
+    base_n2o = STATE(SI_BASE_N2O);
+  } else {
+    mb.status = -1;
+  }
+  const bool cold = (C.flags & HX_FLAG_COLD_NEWTON) != 0;
+  const size_t Mp = d.Mpad;
+
+  for (int s = 0; s < nslab; ++s) {
+    if (tid == 0 && s + 1 < nslab) issue(s + 1); /* buffer (s+1)&1 was released by the sync below */
+    mbar_wait(&bars[s & 1], (uint32_t)((s >> 1) & 1));
+    const double *sl = slab[s & 1];
+    const int base = r0 + s * HX_SLAB_YEARS;
+    const int rend = min(base + HX_SLAB_YEARS, r1);
+    if (mb.status == 0) {
+      for (int r = base + 1; r <= rend; ++r) {
+        const double *sc = sl + (size_t)(r - base) * SC_STRIDE;     /* year y */
+        const double *scm1 = sl + (size_t)(r - 1 - base) * SC_STRIDE; /* year y-1 */
+        const int y = C.start_year + r;
+
+        /* --- OH, CH4, O3: oh_component.cpp:137-174, ch4_component.cpp:152-199,
+         *     o3_component.cpp:126-146 --- */
+        const double M0 = fp.M0;
+        {
+          const double previous_ch4 = ch4;
+          double toh = 0.0;
+          if (previous_ch4 != M0) {
+            const double a = PAR(PI_CCH4) * ((1.0 * log(previous_ch4)) - log(M0));
+            const double b = PAR(PI_CNOX) * ((1.0 * sc[SC_NOX]) - row0[SC_NOX]);
+            const double c = PAR(PI_CCO) * ((1.0 * sc[SC_CO]) - row0[SC_CO]);
+            const double dd = PAR(PI_CNMVOC) * ((1.0 * sc[SC_NMVOC]) - row0[SC_NMVOC]);
+            toh = a + b + c + dd;
+          }
+          const double tau_oh = PAR(PI_TOH0) * exp(-toh);
+          const double rh_ch4_tg = mb.rh_ch4 * (1000.0 * 16.04 / 12.01);
+          const double emisTocon = (sc[SC_CH4_E] + rh_ch4_tg + sc[SC_CH4N]) / PAR(PI_UC_CH4);
+          const double soil_sink = previous_ch4 / PAR(PI_TSOIL);
+          const double strat_sink = previous_ch4 / PAR(PI_TSTRAT);
+          const double oh_sink = previous_ch4 / tau_oh;
+          const double dCH4 = emisTocon - soil_sink - strat_sink - oh_sink;
+          ch4 = previous_ch4 + dCH4;
+        }
+        const double o3 = (5 * log(ch4)) + (0.125 * sc[SC_NOX]) + (0.0011 * sc[SC_CO]) +
+                          (0.0033 * sc[SC_NMVOC]);
+
+        /* --- OceanComponent::run: ocean_component.cpp:356-407 --- */
+        mb.flux_sum = 0.0;
+        mb.timesteps = 0;
+        mb.kHL = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_HL);
+        mb.kLL = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_LL);
+        {
+          bool ok = true;
+          mb.pco2HL = csys_solve(C, mb.kHL, mb.bHL, mb.alkHL, C.vol_HL, mb.hHL, cold, ok, w);
+          mb.pco2LL = csys_solve(C, mb.kLL, mb.bLL, mb.alkLL, C.vol_LL, mb.hLL, cold, ok, w);
+          if (!ok) mb.status = HX_MEMBER_NOROOT;
+        }
+
+        /* --- SimpleNbox::run + slowparameval: simpleNbox-runtime.cpp:206-227, 945-1072 --- */
+        d.tland_hist[(size_t)r * Mp + m] = tland; /* Tland_record[y] = land tas of year y-1 */
+        mb.luc_e = scm1[SC_LUC_E]; mb.luc_u = scm1[SC_LUC_U];
+        mb.ffi = scm1[SC_FFI]; mb.daccs = scm1[SC_DACCS];
+        mb.neg |= (mb.luc_e < 0.0) | (mb.luc_u < 0.0) | (mb.ffi < 0.0) | (mb.daccs < 0.0);
+        double window = 0.0;
+        if (r >= 2) {
+          /* for (i = t-200; i < t; i++) Tland_rm += Tland_record.get(i) * wf; keys below the
+           * first record (start+1) extrapolate flat to it, and that record is exactly 0 */
+          int k0 = r - 201;
+          if (k0 < 1) k0 = 1;
+          const double *th = d.tland_hist + m;
+          for (int k = k0; k <= r - 2; ++k) window += th[(size_t)k * Mp] * p.wf;
+          window /= 200;
+        }
+        slow_params(mb, p, tland, r == 1, window);
+
+        /* --- CarbonCycleSolver::run --- */
+        solver_year<false>(mb, C, p, (double)(y - 1), (double)y, cold, w);
+        if (mb.status) {
+          d.status[m] = mb.status;
+          d.fail_year[m] = y;
+          break;
+        }
+        /* record_state: simpleNbox.cpp:789-840 */
+        {
+          double npp, rh_fda, rh_fsa, rh_co2, rh_ch4v;
+          land_fluxes<false>(mb, p, npp, rh_fda, rh_fsa, rh_co2, rh_ch4v);
+          mb.rh_ch4 = rh_ch4v;
+          mb.tempferts_last = mb.tfs;
+        }
+        const double CO2_conc = mb.atmos * HX_PGC_TO_PPMVCO2;
+        mb.neg |= (CO2_conc < 0.0);
+        if (mb.neg) {
+          mb.status = HX_MEMBER_NEGATIVE;
+          d.status[m] = mb.status;
+          d.fail_year[m] = y;
+          break;
+        }
+
+        /* --- ForcingComponent::run --- */
+        double rf_tot = 0.0, rf_co2 = 0.0, rf_ch4 = 0.0, rf_n2o = 0.0;
+        if (y >= C.baseyear) {
+          double fco2, fch4, fn2o;
+          const double F = forcing_total(fp, sc, CO2_conc, ch4, o3, fco2, fch4, fn2o, mb.status);
+          if (y == C.baseyear) {
+            base_tot = F; base_co2 = fco2; base_ch4 = fch4; base_n2o = fn2o;
+          }
+          rf_tot = F - base_tot; rf_co2 = fco2 - base_co2; rf_ch4 = fch4 - base_ch4;
+          rf_n2o = fn2o - base_n2o;
+          if (mb.status) {
+            d.status[m] = mb.status;
+            d.fail_year[m] = y;
+            break;
+          }
+        }
+
+        /* --- TemperatureComponent::run: temperature_component.cpp:417-557 (tstep = r > 0) --- */
+        double tas, heatflux;
+        {
+          const double dt = 1.0, bsi = DC_BSI, cal = DC_CAL, cas = DC_CAS, flnd = DC_FLND,
+                       fso = DC_FSO;
+          const double taucfl = DER(DI_TAUCFL), taukls = DER(DI_TAUKLS), taucfs = DER(DI_TAUCFS),
+                       tauksl = DER(DI_TAUKSL);
+          const double DelQL = rf_tot - rf_prev, DelQO = rf_tot - rf_prev;
+          double QC1 = (DelQL / cal * (1.0 / taucfl + 1.0 / taukls) - bsi * DelQO / cas / taukls);
+          double QC2 = (DelQO / cas * (1.0 / taucfs + bsi / tauksl) - DelQL / cal / tauksl);
+          QC1 = QC1 * (dt * dt) / 12.0;
+          QC2 = QC2 * (dt * dt) / 12.0;
+          double DQ1 = 0.5 * dt / cal * (rf_tot + rf_prev);
+          double DQ2 = 0.5 * dt / cas * (rf_tot + rf_prev);
+          DQ1 = DQ1 + QC1;
+          DQ2 = DQ2 + QC2;
+          /* one pass over the SST history feeds both convolutions (E-4):
+           *   DPAST2   = sum_{i<=t} sst[i] K(t-i+1)   (:488-491; the i = t term is 0)
+           *   interior = sum_{i<t}  sst[i] K(t-i)     (:534-537) */
+          double DPAST2 = 0.0, hint = 0.0;
+          {
+            const double *sh = d.sst_hist + m;
+            const double *kk = d.ker + m;
+            double kj1 = kk[(size_t)(r + 1 <= C.nrow ? r + 1 : C.nrow) * Mp]; /* K(t+1) */
+            for (int i = 0; i < r; ++i) {
+              const int j = r - i;
+              const double sv = sh[(size_t)i * Mp];
+              const double kj = kk[(size_t)j * Mp];
+              DPAST2 = DPAST2 + sv * kj1;
+              hint = hint + sv * kj;
+              kj1 = kj;
+            }
+          }
+          DPAST2 = DPAST2 * fso * DER(DI_SQDT_TAUDIF);
+          const double DPAST1 = 0.0;
+          const double DTEAUX1 = DER(DI_A0) * tland + DER(DI_A1) * sst;
+          const double DTEAUX2 = DER(DI_A2) * tland + DER(DI_A3) * sst;
+          const double TL = DER(DI_IB0) * (DQ1 + DPAST1 + DTEAUX1) +
+                            DER(DI_IB1) * (DQ2 + DPAST2 + DTEAUX2);
+          const double TS = DER(DI_IB2) * (DQ1 + DPAST1 + DTEAUX1) +
+                            DER(DI_IB3) * (DQ2 + DPAST2 + DTEAUX2);
+          tas = flnd * TL + (1.0 - flnd) * bsi * TS;
+          const double hf_mixed = cas * (TS - sst);
+          const double hf_int = DER(DI_HF_INT) * (2.0 * TS - hint);
+          heat_mixed = heat_mixed + hf_mixed * (C.powtoheat * dt);
+          heat_interior = heat_interior + hf_int * (fso * C.powtoheat * dt);
+          heatflux = hf_mixed + fso * hf_int;
+          tland = TL;
+          sst = TS;
+          d.sst_hist[(size_t)r * Mp + m] = TS;
+          rf_prev = rf_tot;
+        }
+        ++years_done;
+
+        /* --- outputs (record_state / getData of each component) --- */
+        const int yi = r - 1;
+#define EMIT(id, val)                                                              \
+  do {                                                                             \
+    const int slot_ = d.out_slot[id];                                              \
+    if (slot_ >= 0) d.out[((size_t)slot_ * nyears_total + yi) * Mp + m] = (val);   \
+  } while (0)
+        EMIT(OUT_CO2, CO2_conc);
+        EMIT(OUT_TAS, tas);
+        EMIT(OUT_RF_TOT, rf_tot);
+        EMIT(OUT_RF_CO2, rf_co2);
+        EMIT(OUT_HEATFLUX, heatflux);
+        EMIT(OUT_OCEAN_C, mb.bDO + mb.bIO + mb.bLL + mb.bHL);
+        if (d.out_slot[OUT_HL_PH] >= 0) EMIT(OUT_HL_PH, -log10(mb.hHL));
+        EMIT(OUT_ATMOS_C, mb.atmos);
+        EMIT(OUT_SST, sst);
+        EMIT(OUT_PERMAFROST_C, mb.perm);
+        EMIT(OUT_CH4, ch4);
+        EMIT(OUT_N2O, sc[SC_N2O]);
+        EMIT(OUT_O3, o3);
+        EMIT(OUT_LAND_TAS, tland);
+        EMIT(OUT_VEG_C, mb.veg);
+        EMIT(OUT_DETRITUS_C, mb.det);
+        EMIT(OUT_SOIL_C, mb.soil);
+        EMIT(OUT_THAWEDP_C, mb.thawed);
+        EMIT(OUT_EARTH_C, mb.earth);
+        EMIT(OUT_NBP, mb.nbp);
+        EMIT(OUT_OCEAN_UPTAKE, mb.flux_sum);
+        if (d.out_slot[OUT_LL_PH] >= 0) EMIT(OUT_LL_PH, -log10(mb.hLL));
+        EMIT(OUT_PCO2_HL, mb.pco2HL);
+        EMIT(OUT_PCO2_LL, mb.pco2LL);
+        EMIT(OUT_CARBON_HL, mb.bHL);
+        EMIT(OUT_CARBON_LL, mb.bLL);
+        EMIT(OUT_CARBON_IO, mb.bIO);
+        EMIT(OUT_CARBON_DO, mb.bDO);
+        EMIT(OUT_RF_CH4, rf_ch4);
+        EMIT(OUT_RF_N2O, rf_n2o);
+        EMIT(OUT_RH_CH4, mb.rh_ch4);
+        EMIT(OUT_TIMESTEPS, (double)mb.timesteps);
+#undef EMIT
+      }
+    }
+    __syncthreads(); /* everyone is done with slab[s & 1] before it is refilled */
+  }
+
+  if (lane_ok) {
+    if (mb.status == 0) {
+      store_member(d, m, mb);
+      STATE(SI_CH4) = ch4; STATE(SI_TLAND) = tland; STATE(SI_SST) = sst;
+      STATE(SI_HEAT_MIXED) = heat_mixed; STATE(SI_HEAT_INTERIOR) = heat_interior;
+      STATE(SI_RF_PREV) = rf_prev;
+      STATE(SI_BASE_TOT) = base_tot; STATE(SI_BASE_CO2) = base_co2;
+      STATE(SI_BASE_CH4) = base_ch4; STATE(SI_BASE_N2O) = base_n2o;
+    }
+    flush_work(d, w, years_done, mb.status != 0 ? 1u : 0u);
+  }
+}
+
+/* failed members report NaN from the failing year on (the reference stops producing output) */
+__global__ void hx_nan_fill_kernel(const __grid_constant__ HxDev d, int start_year, int nyears,
+                                   int nsel, int yr0, int yr1) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= d.Mpad) return;
+  const int st = d.status[m];
+  if (st <= 0) return;
+  int first = d.fail_year[m] - start_year - 1; /* output index of the failing year */
+  if (first < yr0) first = yr0;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int s = 0; s < nsel; ++s)
+    for (int yi = first; yi < yr1; ++yi) d.out[((size_t)s * nyears + yi) * d.Mpad + m] = nan;
+}
+
+/* ---- host-callable launchers ---- */
+cudaError_t launch_setup(const HxDev &d, const HxConst &C, cudaStream_t st) {
+  hx_setup_kernel<<<d.Mpad / HX_BLOCK, HX_BLOCK, 0, st>>>(d, C);
+  return cudaGetLastError();
+}
+cudaError_t launch_spinup(const HxDev &d, const HxConst &C, cudaStream_t st) {
+  hx_spinup_kernel<<<d.Mpad / HX_BLOCK, HX_BLOCK, 0, st>>>(d, C, 0, -1);
+  return cudaGetLastError();
+}
+cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cudaStream_t st) {
+  hx_spinup_kernel<<<1, HX_BLOCK, 0, st>>>(d, C, member - member % HX_BLOCK, member);
+  return cudaGetLastError();
+}
+cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
+  hx_run_kernel<<<d.Mpad / HX_BLOCK, HX_BLOCK, 0, st>>>(d, C, r0, r1);
+  return cudaGetLastError();
+}
+cudaError_t launch_nan_fill(const HxDev &d, const HxConst &C, int nsel, int yr0, int yr1,
+                            cudaStream_t st) {
+  hx_nan_fill_kernel<<<(d.Mpad + 255) / 256, 256, 0, st>>>(d, C.start_year, C.nrow - 1, nsel, yr0,
+                                                           yr1);
+  return cudaGetLastError();
+}
+
+} // namespace hx

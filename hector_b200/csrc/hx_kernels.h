@@ -1,0 +1,39 @@
+/* hx_kernels.h -- device pointer bundle + kernel launchers (host <-> device boundary inside
+ * the library). */
+#ifndef HX_KERNELS_H
+#define HX_KERNELS_H
+
+#include <cuda_runtime.h>
+
+#include "hx_layout.h"
+
+#define HX_BLOCK 128      /* threads (= members) per CTA; one scenario per CTA */
+#define HX_SLAB_YEARS 16  /* scenario rows staged per bulk copy */
+
+struct HxDev {
+  int32_t Mpad;             /* padded member count, multiple of HX_BLOCK */
+  const double *P;          /* [PI_COUNT][Mpad] */
+  double *S;                /* [SI_COUNT][Mpad] */
+  double *D;                /* [DI_COUNT][Mpad] */
+  double *ker;              /* [nrow+1][Mpad]  DOECLIM lag kernel K(j) */
+  double *sst_hist;         /* [nrow][Mpad] */
+  double *tland_hist;       /* [nrow][Mpad] */
+  double *out;              /* [nsel][nrow-1][Mpad] */
+  const double *scen;       /* [n_scen][nrow][SC_STRIDE] */
+  const int32_t *block_scen; /* [Mpad / HX_BLOCK] scenario of each CTA */
+  int32_t *status;          /* [Mpad]; -1 = padding lane */
+  int32_t *fail_year;       /* [Mpad] */
+  int32_t *spinup_steps;    /* [Mpad] */
+  unsigned long long *counters; /* [HX_NCOUNTERS] */
+  int32_t out_slot[OUT_COUNT];  /* output id -> slot in `out`, -1 = not recorded */
+};
+
+namespace hx {
+cudaError_t launch_setup(const HxDev &d, const HxConst &C, cudaStream_t st);
+cudaError_t launch_spinup(const HxDev &d, const HxConst &C, cudaStream_t st);
+cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cudaStream_t st);
+cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st);
+cudaError_t launch_nan_fill(const HxDev &d, const HxConst &C, int nsel, int yr0, int yr1,
+                            cudaStream_t st);
+}
+#endif

@@ -1,0 +1,104 @@
+/* hx_layout.h -- data layout shared by the host engine and the device kernels.
+ *
+ * Everything per-member is structure-of-arrays with the member index fastest:
+ *   params  P[PI_COUNT][Mpad]      state  S[SI_COUNT][Mpad]      derived D[DI_COUNT][Mpad]
+ *   histories  sst_hist / tland_hist / ker [nrow][Mpad]          outputs O[nsel][nyears][Mpad]
+ * so a warp touches 32 consecutive doubles (256 B) per access.  Scenario tables are
+ * [scenario][row][SC_STRIDE] doubles, row = year - start_year, staged to shared memory in
+ * slabs of consecutive rows with one bulk copy each.
+ */
+#ifndef HX_LAYOUT_H
+#define HX_LAYOUT_H
+
+#include <stdint.h>
+
+#define HX_NHALO 26
+
+/* ---- raw scenario series (what callers hand in), reference input names ---- */
+enum {
+  RAW_FFI = 0, RAW_DACCS, RAW_LUC_E, RAW_LUC_U, RAW_CH4_E, RAW_CH4N, RAW_NOX, RAW_CO, RAW_NMVOC,
+  RAW_BC, RAW_OC, RAW_SO2, RAW_NH3, RAW_SV, RAW_ALBEDO, RAW_MISC, RAW_N2O_E, RAW_N2O_NAT,
+  RAW_HALO0,
+  RAW_COUNT = RAW_HALO0 + HX_NHALO
+};
+
+/* ---- device scenario table columns ---- */
+enum {
+  SC_FFI = 0, SC_DACCS, SC_LUC_E, SC_LUC_U, SC_CH4_E, SC_CH4N, SC_NOX, SC_CO, SC_NMVOC,
+  SC_BC, SC_OC, SC_SO2, SC_NH3, SC_SV, SC_ALBEDO, SC_MISC,
+  SC_N2O,   /* N2O concentration, host-precomputed (member independent) */
+  SC_HALO0, /* 26 halocarbon forcings, host-precomputed */
+  SC_USED = SC_HALO0 + HX_NHALO, /* 43 */
+  SC_STRIDE = 44                 /* 352 B per row: multiple of 16 B for cp.async.bulk */
+};
+
+/* ---- per-member parameters ---- */
+enum {
+  PI_S = 0, PI_DIFF, PI_QCO2,
+  PI_BETA, PI_Q10, PI_F_NPPV, PI_F_NPPD, PI_F_LITTERD, PI_NPP_FLUX0, PI_C0,
+  PI_VEG_C0, PI_DET_C0, PI_SOIL_C0, PI_PERMAFROST_C0,
+  PI_WARMINGFACTOR, PI_RH_CH4_FRAC, PI_PF_MU, PI_PF_SIGMA, PI_FPF_STATIC,
+  PI_TT, PI_TU, PI_TWI, PI_TID, PI_PREIND_SURF, PI_PREIND_ID,
+  PI_EPS_ABS, PI_EPS_REL, PI_DT, PI_EPS_SPINUP,
+  PI_AERO, PI_VOL, PI_DELTA_CO2, PI_DELTA_CH4, PI_DELTA_N2O,
+  PI_RHO_BC, PI_RHO_OC, PI_RHO_SO2, PI_RHO_NH3,
+  PI_M0, PI_TSOIL, PI_TSTRAT, PI_UC_CH4, PI_TOH0, PI_CNOX, PI_CCO, PI_CNMVOC, PI_CCH4, PI_PO3,
+  PI_N0,
+  PI_COUNT
+};
+
+/* ---- per-member dynamic state ---- */
+enum {
+  SI_ATMOS = 0, SI_VEG, SI_DET, SI_SOIL, SI_PERMAFROST, SI_THAWED, SI_EARTH,
+  SI_BOX_HL, SI_BOX_LL, SI_BOX_IO, SI_BOX_DO,
+  SI_ALK_HL, SI_ALK_LL, SI_H_HL, SI_H_LL,        /* alkalinity, last [H+] root (warm start) */
+  SI_TEMPFERTS, SI_F_FROZEN, SI_CUM_LUC_VA, SI_EOS_VEGC, SI_MASSTOT, SI_CUM_PF_CH4, SI_RH_CH4,
+  SI_MAX_TIMESTEP, SI_TIMEOUT, SI_LASTFLUX_ANN, SI_SOLVER_DT,
+  SI_CH4, SI_TLAND, SI_SST, SI_HEAT_MIXED, SI_HEAT_INTERIOR, SI_RF_PREV,
+  SI_BASE_TOT, SI_BASE_CO2, SI_BASE_CH4, SI_BASE_N2O,
+  SI_COUNT
+};
+
+/* ---- per-member derived constants (set-up kernel) ---- */
+enum {
+  DI_K_LL_HL = 0, DI_K_LL_IO, DI_K_HL_DO, DI_K_IO_LL, DI_K_IO_HL, DI_K_IO_DO, DI_K_DO_IO,
+  DI_A0, DI_A1, DI_A2, DI_A3, DI_IB0, DI_IB1, DI_IB2, DI_IB3,
+  DI_TAUCFL, DI_TAUKLS, DI_TAUCFS, DI_TAUKSL,
+  DI_SQDT_TAUDIF, /* pow(dt/taudif, 0.5)            temperature_component.cpp:491 */
+  DI_HF_INT,      /* cas*fso/pow(taudif*dt, 0.5)    temperature_component.cpp:539 */
+  DI_COUNT
+};
+
+/* ---- recorded outputs ---- */
+enum {
+  OUT_CO2 = 0, OUT_TAS, OUT_RF_TOT, OUT_RF_CO2, OUT_HEATFLUX, OUT_OCEAN_C, OUT_HL_PH, OUT_ATMOS_C,
+  OUT_SST, OUT_PERMAFROST_C, OUT_CH4, OUT_N2O, OUT_O3, OUT_LAND_TAS, OUT_VEG_C, OUT_DETRITUS_C,
+  OUT_SOIL_C, OUT_THAWEDP_C, OUT_EARTH_C, OUT_NBP, OUT_OCEAN_UPTAKE, OUT_LL_PH, OUT_PCO2_HL,
+  OUT_PCO2_LL, OUT_CARBON_HL, OUT_CARBON_LL, OUT_CARBON_IO, OUT_CARBON_DO, OUT_RF_CH4,
+  OUT_RF_N2O, OUT_RH_CH4, OUT_TIMESTEPS,
+  OUT_COUNT
+};
+
+/* ---- engine-wide constants handed to every kernel ---- */
+struct HxConst {
+  int32_t start_year, end_year, nrow; /* nrow = end - start + 1 */
+  int32_t baseyear;
+  int32_t max_spinup;
+  uint32_t flags;
+  /* salinity-only chemistry constants, computed on the host with the C library so they are
+   * the doubles the reference computes (ocean_csys.cpp:225-287) */
+  double S, sqrtS, S15, bor;
+  /* geometry (ocean_component.cpp:207-303) */
+  double vol_HL, vol_LL, vol_IO, vol_DO, As_HL, As_LL, U;
+  double spy_ocean;
+  /* DOECLIM (temperature_component.hpp:77-98) */
+  double powtoheat;
+};
+
+/* status words live next to the state */
+struct HxStatus {
+  int32_t *status;    /* [Mpad] */
+  int32_t *fail_year; /* [Mpad] */
+};
+
+#endif

@@ -1,0 +1,205 @@
+"""Ensemble: the batched counterpart of a reference Core.
+
+    reference (R, one member)                      here (M members at once)
+    -------------------------                      ------------------------
+    core <- newcore(inifile)                       ens = Ensemble(M, scenario tables)
+    setvar(core, NA, ECS(), 3.5, "degC")           ens.setvar("S", per_member_array or scalar)
+    reset(core); run(core, 2100)                   ens.reset(); ens.run(2100)
+    fetchvars(core, 1746:2100, c(...))             ens.fetchvars(range(1746, 2101), [...])
+
+Variable / parameter names are the reference's capability strings
+(inst/include/component_data.hpp).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import HxError
+
+HALOS = ["CF4", "C2F6", "HFC23", "HFC32", "HFC4310", "HFC125", "HFC134a", "HFC143a", "HFC227ea",
+         "HFC245fa", "SF6", "CFC11", "CFC12", "CFC113", "CFC114", "CFC115", "CCl4", "CH3CCl3",
+         "HCFC22", "HCFC141b", "HCFC142b", "halon1211", "halon1301", "halon2402", "CH3Cl",
+         "CH3Br"]
+RAW_SERIES = ["ffi_emissions", "daccs_uptake", "luc_emissions", "luc_uptake", "CH4_emissions",
+              "CH4N", "NOX_emissions", "CO_emissions", "NMVOC_emissions", "BC_emissions",
+              "OC_emissions", "SO2_emissions", "NH3_emissions", "SV", "RF_albedo", "RF_misc",
+              "N2O_emissions", "N2O_natural_emissions"] + ["%s_emissions" % h for h in HALOS]
+PARAMETERS = ["S", "diff", "qco2", "beta", "q10_rh", "f_nppv", "f_nppd", "f_litterd", "npp_flux0",
+              "C0", "veg_c", "detritus_c", "soil_c", "permafrost_c", "warmingfactor",
+              "rh_ch4_frac", "pf_mu", "pf_sigma", "fpf_static", "tt", "tu", "twi", "tid",
+              "preind_surface_c", "preind_interdeep_c", "eps_abs", "eps_rel", "dt", "eps_spinup",
+              "aero_scalar", "vol_scalar", "delta_co2", "delta_ch4", "delta_n2o", "rho_bc",
+              "rho_oc", "rho_so2", "rho_nh3", "M0", "Tsoil", "Tstrat", "UC_CH4", "TOH0", "CNOX",
+              "CCO", "CNMVOC", "CCH4", "PO3", "N0"]
+OUTPUT_VARIABLES = ["CO2_concentration", "global_tas", "RF_tot", "RF_CO2", "heatflux", "ocean_c",
+                    "HL_pH", "atmos_co2", "sst", "permafrost_c", "CH4_concentration",
+                    "N2O_concentration", "O3_concentration", "land_tas", "veg_c", "detritus_c",
+                    "soil_c", "thawedp_c", "earth_c", "NBP", "ocean_uptake", "LL_pH", "HL_PCO2",
+                    "LL_PCO2", "HL_ocean_c", "LL_ocean_c", "IO_ocean_c", "DO_ocean_c", "RF_CH4",
+                    "RF_N2O", "rh_ch4", "ocean_timesteps"]
+MEMBER_STATUS = {0: "ok", 1: "negative flux/pool", 2: "mass not conserved",
+                 3: "solver retries exhausted", 4: "no [H+] root", 5: "yearfraction out of bounds",
+                 6: "CO2 SARF condition", 7: "ODE stepper", 8: "spin-up did not converge"}
+
+
+def load_scenario_tables(path):
+    """{scenario: table[nrow, len(RAW_SERIES)]} from an .npz written by
+    tests/golden/make_golden.py (columns in RAW_SERIES order)."""
+    z = np.load(path)
+    names = [str(s) for s in z["names"]]
+    if names != RAW_SERIES:
+        raise HxError("scenario file columns do not match RAW_SERIES")
+    return {(k[:-5] + "-over" if k.endswith("_over") else k): np.ascontiguousarray(z[k])
+            for k in z.files if k != "names"}
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Ensemble:
+    def __init__(self, n_members, scenarios, member_scenario=None, start_year=1745, end_year=2300,
+                 device=0, outputs=("CO2_concentration", "global_tas"), cold_newton=False,
+                 spinup=True, stream=None):
+        """scenarios: one table [nrow, 44] (RAW_SERIES columns), or a list of them;
+        member_scenario: int array [n_members] of indices into that list."""
+        self.L = _capi.lib()
+        if isinstance(scenarios, np.ndarray):
+            scenarios = [scenarios]
+        self.n_members = int(n_members)
+        self.start_year, self.end_year = int(start_year), int(end_year)
+        flags = (_capi.HX_FLAG_COLD_NEWTON if cold_newton else 0) | \
+                (0 if spinup else _capi.HX_FLAG_NO_SPINUP)
+        cfg = _capi.HxConfig(self.n_members, len(scenarios), self.start_year, self.end_year,
+                             int(device), flags)
+        self.h = C.c_void_p()
+        rc = self.L.hx_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise HxError("hx_create: %s" % self.L.hx_last_error(None).decode())
+        if stream is not None:
+            self._chk(self.L.hx_set_stream(self.h, C.c_void_p(int(stream))))
+        names = (C.c_char_p * len(RAW_SERIES))(*[s.encode() for s in RAW_SERIES])
+        nrow = self.end_year - self.start_year + 1
+        for sid, tab in enumerate(scenarios):
+            tab = np.ascontiguousarray(tab, dtype=np.float64)
+            if tab.shape != (nrow, len(RAW_SERIES)):
+                raise HxError("scenario table must be [%d, %d]" % (nrow, len(RAW_SERIES)))
+            self._chk(self.L.hx_set_scenario_table(self.h, sid, len(RAW_SERIES), names,
+                                                   self.start_year, nrow, _dp(tab)))
+        if member_scenario is not None:
+            ms = np.ascontiguousarray(member_scenario, dtype=np.int32)
+            self._chk(self.L.hx_set_member_scenario(
+                self.h, ms.ctypes.data_as(C.POINTER(C.c_int32)), len(ms)))
+        self.outputs = list(outputs)
+        arr = (C.c_char_p * len(self.outputs))(*[s.encode() for s in self.outputs])
+        self._chk(self.L.hx_select_outputs(self.h, len(self.outputs), arr))
+        self.prepared = False
+
+    # -- plumbing --
+    def _chk(self, rc):
+        if rc != 0:
+            raise HxError("%s (code %d)" % (self.L.hx_last_error(self.h).decode(), rc))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- reference-shaped surface --
+    def setvar(self, name, values):
+        """R setvar (R/messages.R:107-140): scalar for all members or one value per member."""
+        if np.isscalar(values):
+            self._chk(self.L.hx_set_param_scalar(self.h, name.encode(), float(values)))
+        else:
+            v = np.ascontiguousarray(values, dtype=np.float64)
+            self._chk(self.L.hx_set_param(self.h, name.encode(), _dp(v), v.size))
+
+    def setvar_device(self, name, dev_ptr, n):
+        self._chk(self.L.hx_set_param_device(self.h, name.encode(), C.c_void_p(int(dev_ptr)), n))
+
+    def getvar(self, name):
+        out = np.empty(self.n_members)
+        self._chk(self.L.hx_get_param(self.h, name.encode(), _dp(out), out.size))
+        return out
+
+    def prepare(self):
+        """Core::prepareToRun incl. spin-up."""
+        self._chk(self.L.hx_prepare(self.h))
+        self.prepared = True
+
+    def run(self, to_date=-1):
+        if not self.prepared:
+            self.prepare()
+        self._chk(self.L.hx_run(self.h, float(to_date)))
+
+    def reset(self):
+        self._chk(self.L.hx_reset(self.h))
+
+    def synchronize(self):
+        self._chk(self.L.hx_synchronize(self.h))
+
+    def fetch(self, var, dates, out=None):
+        """-> array [n_members, n_dates]; `out` may be a preallocated (pinned) buffer address
+        holder: a numpy array or anything with .ctypes / an int address."""
+        dates = np.ascontiguousarray(dates, dtype=np.float64)
+        if out is None:
+            out = np.empty((self.n_members, dates.size))
+        addr = out.ctypes.data if hasattr(out, "ctypes") else int(out)
+        self._chk(self.L.hx_fetch(self.h, var.encode(), _dp(dates), dates.size,
+                                  C.c_void_p(addr)))
+        return out
+
+    def fetchvars(self, dates, variables=None):
+        """R fetchvars (R/messages.R:46-88): {variable: array[n_members, n_dates]}"""
+        variables = variables or self.outputs
+        return {v: self.fetch(v, dates) for v in variables}
+
+    def output_device(self, var):
+        """(device pointer, member stride, n_years) of the [year][member] block of `var`."""
+        p = C.c_void_p()
+        stride = C.c_int64()
+        ny = C.c_int32()
+        self._chk(self.L.hx_output_device(self.h, var.encode(), C.byref(p), C.byref(stride),
+                                          C.byref(ny)))
+        return p.value, stride.value, ny.value
+
+    def status(self):
+        st = np.empty(self.n_members, dtype=np.int32)
+        fy = np.empty(self.n_members, dtype=np.int32)
+        ip = C.POINTER(C.c_int32)
+        self._chk(self.L.hx_member_status(self.h, st.ctypes.data_as(ip), fy.ctypes.data_as(ip),
+                                          self.n_members))
+        return st, fy
+
+    def counters(self):
+        out = (C.c_uint64 * _capi.HX_NCOUNTERS)()
+        self._chk(self.L.hx_counters(self.h, out, _capi.HX_NCOUNTERS))
+        return dict(zip(_capi.COUNTER_NAMES, [int(x) for x in out]))
+
+    def spinup_state(self, member=0):
+        out = np.empty(14)
+        self._chk(self.L.hx_spinup_state(self.h, member, _dp(out)))
+        keys = ["atmos", "veg", "det", "soil", "permafrost", "thawed", "earth", "HL", "LL", "IO",
+                "DO", "alk_HL", "alk_LL", "spinup_steps"]
+        return dict(zip(keys, out))
+
+    @property
+    def current_date(self):
+        return self.L.hx_current_date(self.h)
+
+    @property
+    def last_run_ms(self):
+        return self.L.hx_last_run_ms(self.h)

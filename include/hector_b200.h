@@ -1,0 +1,149 @@
+/* include/hector_b200.h -- C ABI of libhector_b200.so, the B200 ensemble engine for Hector's
+ * per-year coupled hot path (carbon-cycle ODE + ocean boxes/chemistry + forcing + DOECLIM),
+ * batched over ensemble members.
+ *
+ * Plain C types, caller-allocated buffers, FP64 throughout.  Each entry point replaces a
+ * piece of the reference's C++ surface for this path (paths relative to JGCRI/hector v3.5.0):
+ *
+ *   hx_create / hx_destroy     Core::mkcore / Core::delcore + Core::init   src/core.cpp:817-857, 90-196
+ *   hx_set_scenario_series     Core::setData(component, var, (date,value)) src/core.cpp:219-268 as driven by
+ *                              CSVTableReader::process                     src/csv_table_reader.cpp:115-196
+ *   hx_set_param[_scalar]      Core::sendMessage(M_SETDATA, var, value)    src/core.cpp:752-772
+ *                              (R: setvar, R/messages.R:107-140)
+ *   hx_prepare                 Core::prepareToRun incl. run_spinup         src/core.cpp:302-420
+ *   hx_run                     Core::run(runtodate)                        src/core.cpp:448-509
+ *   hx_reset                   Core::reset(date < start)                   src/core.cpp:511-549
+ *   hx_fetch                   Core::sendMessage(M_GETDATA, var, date)     src/core.cpp:716-778
+ *                              (R: fetchvars, R/messages.R:46-88)
+ *   hx_member_status           h_exception propagation                     inst/include/h_exception.hpp:26-102
+ *
+ * Errors never cross the ABI as exceptions: every call returns HX_OK or a negative code and
+ * hx_last_error() describes it.  Members that the reference would abort with an h_exception
+ * get a non-zero per-member status and NaN outputs from the failing year on; the rest of the
+ * batch continues.
+ */
+#ifndef HECTOR_B200_H
+#define HECTOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hx_engine *hx_handle;
+
+/* return codes */
+#define HX_OK 0
+#define HX_ERR_ARG (-1)     /* bad argument / unknown name */
+#define HX_ERR_STATE (-2)   /* call out of order (e.g. run before prepare) */
+#define HX_ERR_CUDA (-3)    /* CUDA runtime error, see hx_last_error */
+#define HX_ERR_UNSUPPORTED (-4)
+
+/* per-member status words (0 = ok); the comment names the reference exception */
+#define HX_MEMBER_OK 0
+#define HX_MEMBER_NEGATIVE 1     /* "Flux and pool values may not be negative" fluxpool.hpp:100-102 */
+#define HX_MEMBER_MASS 2         /* "Mass not conserved" simpleNbox-runtime.cpp:556-563 */
+#define HX_MEMBER_RETRIES 3      /* "solver failure: t != tnew" carbon-cycle-solver.cpp:294 */
+#define HX_MEMBER_NOROOT 4       /* newton_raphson_iterate lost its bracket / produced NaN */
+#define HX_MEMBER_YEARFRACTION 5 /* "yearfraction out of bounds" ocean_component.cpp:665 */
+#define HX_MEMBER_CO2SARF 6      /* forcing_component.cpp:353 */
+#define HX_MEMBER_STEPPER 7      /* odeint: 500 failed step-size searches */
+#define HX_MEMBER_SPINUP 8       /* spin-up did not converge within max_spinup (reference only logs) */
+
+/* hx_config.flags */
+#define HX_FLAG_COLD_NEWTON 1u   /* start every [H+] solve from the Fujiwara bound like the
+                                    reference (ocean_csys.cpp:141-153) instead of last root */
+#define HX_FLAG_NO_SPINUP 2u     /* do_spinup = 0 */
+
+typedef struct {
+  int32_t n_members;   /* ensemble members owned by this engine (this GPU's shard) */
+  int32_t n_scenarios; /* distinct scenario tables */
+  int32_t start_year;  /* [core] startDate, e.g. 1745 */
+  int32_t end_year;    /* [core] endDate,   e.g. 2300 */
+  int32_t device;      /* CUDA device ordinal */
+  uint32_t flags;
+} hx_config;
+
+/* counters returned by hx_counters (sums over members of the last hx_run segment) */
+#define HX_NCOUNTERS 8
+#define HX_CNT_RHS_EVALS 0
+#define HX_CNT_RK_STEPS 1
+#define HX_CNT_RK_REJECTED 2
+#define HX_CNT_STASHES 3
+#define HX_CNT_NEWTON_ITERS 4
+#define HX_CNT_NEWTON_CALLS 5
+#define HX_CNT_FAILED_MEMBERS 6
+#define HX_CNT_MEMBER_YEARS 7
+
+int hx_create(const hx_config *cfg, hx_handle *out);
+int hx_destroy(hx_handle h); /* idempotent on NULL */
+const char *hx_last_error(hx_handle h); /* h may be NULL: error of the last failed hx_create */
+
+/* Use an existing CUDA stream (a cudaStream_t passed as void*) for all engine work; NULL
+ * selects the engine's own stream. */
+int hx_set_stream(hx_handle h, void *cuda_stream);
+
+/* Raw scenario series, one value per integer year year0 .. year0+n-1 (must cover
+ * start_year..end_year).  Names are the reference's input names: ffi_emissions, daccs_uptake,
+ * luc_emissions, luc_uptake, CH4_emissions, CH4N, NOX_emissions, CO_emissions,
+ * NMVOC_emissions, BC_emissions, OC_emissions, SO2_emissions, NH3_emissions, SV, RF_albedo,
+ * RF_misc, N2O_emissions, N2O_natural_emissions, <gas>_emissions for the 26 halocarbons. */
+int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, int32_t year0,
+                           int32_t n, const double *values);
+/* whole table at once: values[n_years][n_names] row-major */
+int hx_set_scenario_table(hx_handle h, int32_t scenario_id, int32_t n_names,
+                          const char *const *names, int32_t year0, int32_t n_years,
+                          const double *values);
+/* scenario of every member (default: all members use scenario 0) */
+int hx_set_member_scenario(hx_handle h, const int32_t *scenario_of_member, int32_t n);
+
+/* Parameters by the reference's names (S, diff, qco2, beta, q10_rh, f_nppv, f_nppd, f_litterd,
+ * npp_flux0, C0, veg_c, detritus_c, soil_c, permafrost_c, warmingfactor, rh_ch4_frac, pf_mu,
+ * pf_sigma, fpf_static, tt, tu, twi, tid, preind_surface_c, preind_interdeep_c, eps_abs,
+ * eps_rel, dt, eps_spinup, aero_scalar, vol_scalar, delta_co2, delta_ch4, delta_n2o, rho_bc,
+ * rho_oc, rho_so2, rho_nh3, M0, Tsoil, Tstrat, UC_CH4, TOH0, CNOX, CCO, CNMVOC, CCH4, PO3, N0
+ * per member or scalar; baseyear, max_spinup, UC_N2O, TN2O0 and the halocarbon
+ * tau/rho/delta/H0/molarMass (<gas>.tau ...) scalar only).  Defaults = inst/input/hector_ssp245.ini. */
+int hx_set_param_scalar(hx_handle h, const char *name, double value);
+int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_t n);
+/* same, from a DEVICE pointer (no host round trip) */
+int hx_set_param_device(hx_handle h, const char *name, const double *per_member_dev, int32_t n);
+int hx_get_param(hx_handle h, const char *name, double *per_member_out, int32_t n);
+
+/* Variables recorded per year (subset of: CO2_concentration, global_tas, RF_tot, RF_CO2,
+ * heatflux, ocean_c, HL_pH, atmos_co2, sst, permafrost_c, CH4_concentration,
+ * N2O_concentration, O3_concentration, land_tas, veg_c, detritus_c, soil_c, thawedp_c, earth_c,
+ * NBP, ocean_uptake, LL_pH, HL_PCO2, LL_PCO2, HL_ocean_c, LL_ocean_c, IO_ocean_c, DO_ocean_c,
+ * RF_CH4, RF_N2O, rh_ch4, ocean_timesteps).  Default: CO2_concentration, global_tas.
+ * Must be called before hx_prepare. */
+int hx_select_outputs(hx_handle h, int32_t n, const char *const *names);
+
+int hx_prepare(hx_handle h);
+int hx_run(hx_handle h, double run_to_date); /* < 0: run to end_year; resumes where it left off */
+int hx_reset(hx_handle h);                   /* back to the post-spin-up state at start_year */
+int hx_synchronize(hx_handle h);
+
+/* out[member][date] (row-major, n_members x n_dates) on the host; dates before/at
+ * start_year or beyond the current date are an error, as in the reference */
+int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates, double *out);
+/* device-resident view: pointer to the [year][member_stride] block of `name` (year index 0 =
+ * start_year+1); valid until hx_destroy.  For NCCL gathers / zero-copy consumers. */
+int hx_output_device(hx_handle h, const char *name, const double **dev_ptr,
+                     int64_t *member_stride, int32_t *n_years);
+
+int hx_member_status(hx_handle h, int32_t *status, int32_t *fail_year, int32_t n);
+int hx_counters(hx_handle h, uint64_t *out, int32_t n);
+double hx_current_date(hx_handle h);
+/* device time of the last hx_run segment measured with CUDA events on the engine stream */
+double hx_last_run_ms(hx_handle h);
+/* post-spin-up snapshot of member m: atmos, veg, det, soil, permafrost, thawed, earth,
+ * HL, LL, IO, DO, alk_HL, alk_LL, spinup_steps (14 doubles; alk valid after the first year) */
+int hx_spinup_state(hx_handle h, int32_t member, double *out14);
+
+const char *hx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HECTOR_B200_H */

@@ -1,0 +1,208 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the CPU oracle
+(oracle/hector_oracle.c -- bit-identical to the unmodified reference) on the same inputs.
+
+Tolerance (BASELINE.json north_star): 1e-10 relative on CO2 and Tgav, with the metric of
+SURVEY.md section 8(d): max_t |x - ref| / max(|ref|, floor), floor_tas = 0.01 degC."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+ALL_OUT = None
+
+
+def _engine(n, scen="ssp245", outputs=None, **kw):
+    import hector_b200 as hb
+    tabs = util.scenarios()
+    outputs = outputs or hb.OUTPUT_VARIABLES
+    return hb.Ensemble(n, tabs[scen], outputs=outputs, **kw)
+
+
+def _years(a=1746, b=2300):
+    return np.arange(a, b + 1, dtype=np.float64)
+
+
+def test_default_member_all_outputs_vs_oracle_and_golden():
+    from oracle import port
+    import hector_b200 as hb
+    ens = _engine(1)
+    ens.run()
+    st, fy = ens.status()
+    assert st[0] == 0
+    got = ens.fetchvars(_years())
+    ost, ofy, out, cnt, sp = port.run_member(util.scenarios()["ssp245"])
+    assert ost == 0
+    worst = {}
+    for v in hb.OUTPUT_VARIABLES:
+        x = got[v][0]
+        r = out[port.OUT_NAMES.index(v)]
+        if v == "ocean_timesteps":
+            assert np.array_equal(x, r), "sub-step counts differ in years %s" % (
+                1746 + np.nonzero(x != r)[0][:5])
+            continue
+        worst[v] = util.parity_err(x, r, v)
+    bad = {k: e for k, e in worst.items() if e > TOL}
+    assert not bad, bad
+    # the reference's own golden file (tests/testthat/compdata/hector_comp.csv)
+    gold, _ = util.hector_comp()
+    for v, g in gold.items():
+        assert util.parity_err(got[v][0], g[1:], v) < TOL, v
+    # post-spin-up state
+    s = ens.spinup_state(0)
+    assert s["spinup_steps"] == 498
+    assert abs(s["veg"] - 561.99999976352547) < 1e-9
+    assert abs(s["soil"] - 2030.5895679096495) < 1e-9
+    assert abs(s["alk_HL"] - sp["alk_HL"]) < 1e-13 and abs(s["alk_LL"] - sp["alk_LL"]) < 1e-13
+    # work counters: E-1 removes exactly the doomed attempts, so stashes match the oracle
+    c = ens.counters()
+    assert c["member_years"] == 555
+    assert c["rk_rejected"] == 0
+    ens.close()
+
+
+@pytest.mark.parametrize("cold", [False, True])
+def test_reference_kat_cases(cold):
+    """every committed reference trajectory (unmodified reference via oracle/_ref)"""
+    import hector_b200 as hb
+    cases = [c for c in util.ref_runs()]
+    by_scen = {}
+    for c in cases:
+        by_scen.setdefault(c["scenario"], []).append(c)
+    for scen, cs in by_scen.items():
+        ens = _engine(len(cs), scen, cold_newton=cold)
+        names = sorted({k for c in cs for k in c["params"]})
+        for nme in names:
+            dflt = ens.getvar(nme)
+            vals = np.array([c["params"].get(nme, dflt[i]) for i, c in enumerate(cs)])
+            ens.setvar(nme, vals)
+        ens.run()
+        st, fy = ens.status()
+        got = ens.fetchvars(_years())
+        for i, c in enumerate(cs):
+            if not c["ok"]:
+                assert st[i] == 1, (c["name"], st[i])
+                ndone = int(np.sum(~np.isnan(c["values"]["CO2_concentration"])))
+                assert fy[i] == 1746 + ndone
+                assert np.isnan(got["CO2_concentration"][i][ndone:]).all()
+                assert not np.isnan(got["CO2_concentration"][i][:ndone]).any()
+                continue
+            assert st[i] == 0, (c["name"], st[i], fy[i])
+            for v, ref in c["values"].items():
+                if np.isnan(ref).all():
+                    continue
+                x = got[v][i]
+                if v == "ocean_timesteps":
+                    assert np.array_equal(x, ref), c["name"]
+                else:
+                    assert util.parity_err(x, ref, v) < TOL, (c["name"], v)
+        ens.close()
+
+
+def test_lhs_1024_members_vs_oracle():
+    """BASELINE.json config 2: 1 024-member (S, q10_rh, beta, diff) Latin hypercube, SSP2-4.5"""
+    from oracle import port
+    M = 1024
+    X = util.lhs(M)
+    ens = _engine(M, outputs=["CO2_concentration", "global_tas", "ocean_timesteps"])
+    for j, nme in enumerate(["S", "q10_rh", "beta", "diff"]):
+        ens.setvar(nme, X[:, j])
+    ens.run()
+    st, fy = ens.status()
+    got = ens.fetchvars(_years())
+    raw = util.scenarios()["ssp245"]
+    worst_co2 = worst_tas = 0.0
+    mism = 0
+    for i in range(M):
+        ost, ofy, out, _, _ = port.run_member(raw, S=X[i, 0], q10_rh=X[i, 1], beta=X[i, 2],
+                                              diff=X[i, 3])
+        assert (ost != 0) == (st[i] != 0), i
+        if ost:
+            continue
+        worst_co2 = max(worst_co2, util.parity_err(got["CO2_concentration"][i], out[0],
+                                                   "CO2_concentration"))
+        worst_tas = max(worst_tas, util.parity_err(got["global_tas"][i], out[1], "global_tas"))
+        mism += int(np.sum(got["ocean_timesteps"][i] != out[-1]))
+    assert mism == 0
+    assert worst_co2 < TOL and worst_tas < TOL, (worst_co2, worst_tas)
+    ens.close()
+
+
+def test_bit_reproducible_and_reset_and_resume():
+    M = 256
+    X = util.lhs(M, seed=7)
+    ens = _engine(M, outputs=["CO2_concentration", "global_tas"])
+    for j, nme in enumerate(["S", "q10_rh", "beta", "diff"]):
+        ens.setvar(nme, X[:, j])
+    ens.run()
+    a = ens.fetchvars(_years())
+    ens.reset()
+    ens.run(2000)           # run(d1); run(d2) resumes (core.cpp:448-509)
+    assert ens.current_date == 2000
+    ens.run(2300)
+    b = ens.fetchvars(_years())
+    for v in a:
+        assert np.array_equal(a[v], b[v]), v
+    # changing a parameter then reset re-runs set-up + spin-up, like setvar -> reset(0) -> run
+    ens.setvar("S", np.full(M, 3.0))
+    ens.reset()
+    ens.run()
+    c = ens.fetchvars(_years())
+    assert not np.array_equal(a["global_tas"], c["global_tas"])
+    ens.close()
+
+
+def test_multi_scenario_interleaved():
+    """BASELINE.json config 4 shape: members interleaved over scenarios in API order"""
+    from oracle import port
+    import hector_b200 as hb
+    tabs = util.scenarios()
+    names = ["ssp119", "ssp245", "ssp585"]
+    M = 3 * 50
+    ms = np.arange(M) % 3
+    X = util.lhs(M, seed=11)
+    ens = hb.Ensemble(M, [tabs[n] for n in names], member_scenario=ms,
+                      outputs=["CO2_concentration", "global_tas"])
+    ens.setvar("S", X[:, 0])
+    ens.setvar("diff", X[:, 3])
+    ens.run()
+    got = ens.fetchvars(_years())
+    for i in list(range(0, M, 17)):
+        ost, _, out, _, _ = port.run_member(tabs[names[ms[i]]], S=X[i, 0], diff=X[i, 3])
+        assert ost == 0
+        assert util.parity_err(got["CO2_concentration"][i], out[0], "CO2_concentration") < TOL
+        assert util.parity_err(got["global_tas"][i], out[1], "global_tas") < TOL
+    ens.close()
+
+
+def test_per_member_spinup_parameters():
+    """f_nppv per member => spin-up not shared (device spin-up for every member)"""
+    from oracle import port
+    M = 8
+    f = np.linspace(0.25, 0.4, M)
+    ens = _engine(M, outputs=["CO2_concentration", "global_tas"])
+    ens.setvar("f_nppv", f)
+    ens.run()
+    got = ens.fetchvars(_years())
+    for i in (0, 3, 7):
+        ost, _, out, _, sp = port.run_member(util.scenarios()["ssp245"], f_nppv=f[i])
+        assert util.parity_err(got["CO2_concentration"][i], out[0], "CO2_concentration") < TOL
+        assert abs(ens.spinup_state(i)["veg"] - sp["veg"]) < 1e-9
+    ens.close()
+
+
+def test_error_behaviour():
+    import hector_b200 as hb
+    ens = _engine(2, outputs=["CO2_concentration"])
+    with pytest.raises(hb.HxError):
+        ens.setvar("no_such_parameter", 1.0)
+    ens.run(1800)
+    with pytest.raises(hb.HxError):
+        ens.fetch("CO2_concentration", [1900.0])      # beyond the current date
+    with pytest.raises(hb.HxError):
+        ens.fetch("global_tas", [1800.0])             # not selected
+    x = ens.fetch("CO2_concentration", [1800.0])      # engine still usable after errors
+    assert x.shape == (2, 1) and x[0, 0] > 277
+    ens.close()
