@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Hector ensemble hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA engine
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU path
+
+Metric (BASELINE.json): ensemble-member-years/s, SSP2-4.5, 1745->2300 (555 yearly steps per
+member).  One "step" = one complete run of the whole ensemble (reset to the post-spin-up
+state + 555 coupled years for every member).  Workload at N GPUs: --members per GPU
+(default 65 536 = BASELINE.json configs[2], "1 GPU, HBM-bound sizing"; weak scaling), the
+(S, q10_rh, beta, diff) Latin hypercube of SURVEY.md section 8(d), seed 20241017.
+
+Numbers on the JSON line:
+  value     member-years/s with parameters already resident in HBM (timed: state restore + run
+            kernel [+ the final NCCL all-gather of CO2/Tgav trajectories when N > 1])
+  e2e       same metric through the public API with HOST buffers: per step the 4 parameter
+            vectors go host->device, set-up + spin-up + run execute, and the CO2 and Tgav
+            trajectories of every member come back to (pinned) host memory
+  roofline  algorithmic bytes (5 048 B per member-year) / run-kernel
+            time measured with CUDA events, against the measured HBM copy bandwidth
+  cpu_baseline  the unmodified reference (oracle/_ref) or the C oracle port on this box's host
+            cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+YEARS = 555
+B_ALG = 5048.0  # algorithmic bytes per member-year, SURVEY.md section 8(d)
+METRIC = "ensemble_member_years_per_sec"
+UNIT = "member-years/s"
+PARAMS = ["S", "q10_rh", "beta", "diff"]
+LO = np.array([2.0, 1.0, 0.2, 0.5])
+HI = np.array([5.0, 2.6, 0.9, 2.5])
+
+
+def lhs(M, seed=20241017):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cols = []
+    for j in range(4):
+        u = (rng.permutation(M) + rng.random(M)) / M
+        cols.append(LO[j] + u * (HI[j] - LO[j]))
+    return np.stack(cols, axis=1)
+
+
+def scenario_table(name="ssp245"):
+    import hector_b200 as hb
+    return hb.load_scenario_tables(os.path.join(ROOT, "tests", "golden", "scenarios.npz"))[name]
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except Exception:
+                continue
+            for k, nm in ((5, "hw_slowdown"), (6, "hw_thermal_slowdown"),
+                          (7, "sw_thermal_slowdown"), (8, "sw_power_cap")):
+                if len(r) > k and r[k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own implementation on the host cores
+def _ref_worker(args):
+    kind, rows, to_date = args
+    secs, years = 0.0, 0
+    if kind == "reference":
+        from oracle import ref
+        for S, q10, beta, diff in rows:
+            ok, err, _, s = ref.run_member(ref.ini_path("ssp245"),
+                                           dict(S=S, q10_rh=q10, beta=beta, diff=diff), (),
+                                           to_date)
+            secs += s
+            years += YEARS
+    else:
+        from oracle import port
+        raw = scenario_table()
+        for S, q10, beta, diff in rows:
+            t0 = time.perf_counter()
+            port.run_member(raw, S=S, q10_rh=q10, beta=beta, diff=diff)
+            secs += time.perf_counter() - t0   # includes the spin-up: the port has one entry
+            years += YEARS
+    return secs, years
+
+
+def cpu_reference_pass(members_per_core=2, cores=None):
+    """One bounded sample: `cores` processes x members_per_core member-runs each; returns
+    (member-years/s over run() time, kind, cores, sample description)."""
+    import multiprocessing as mp
+    from oracle import ref
+    kind = "reference" if ref.available() else "port"
+    cores = cores or os.cpu_count() or 1
+    if kind == "port":
+        members_per_core = max(members_per_core, 64)
+    X = lhs(cores * members_per_core)
+    chunks = [(kind, [tuple(r) for r in X[i::cores]], -1.0) for i in range(cores)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_ref_worker, chunks)
+    worst = max(s for s, _ in res)
+    years = sum(y for _, y in res)
+    value = years / worst
+    what = ("%d member-runs (first %d of the LHS) x 555 yr, %d processes, timing %s" %
+            (len(X), len(X), cores,
+             "Core::run() only (ini parse + spin-up excluded)" if kind == "reference"
+             else "ho_run_member (spin-up included)"))
+    return value, kind, cores, what
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        v, kind, cores, what = cpu_reference_pass(args.ref_members_per_core)
+        if i >= args.warmup:
+            vals.append((v, time.perf_counter() - t0))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([t for _, t in vals])) * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": what},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "%d-member-per-GPU (S, q10_rh, beta, diff) Latin-hypercube ensemble, "
+                        "SSP2-4.5, 1745->2300 (BASELINE.json configs[2] sizing)" % args.members,
+            "members_per_gpu": args.members, "years": YEARS, "scenario": "ssp245",
+            "sampler": "LHS seed 20241017",
+            "cache": "working set (state + histories + outputs) >> 126 MB L2"
+                     if args.members >= 16384 else "L2 flushed between timed iterations"}
+
+
+# ------------------------------------------------------------------------------------------
+class CudaArrayView:
+    """zero-copy view of an engine output block for torch (NCCL gathers)"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--members", type=int, default=65536, help="members per GPU")
+    ap.add_argument("--small-members", type=int, default=1024,
+                    help="also time BASELINE.json configs[1] (0 = skip)")
+    ap.add_argument("--ref-members-per-core", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cold-newton", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import hector_b200 as hb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    M = args.members
+    X_all = lhs(M * world)
+    X = np.ascontiguousarray(X_all[rank * M:(rank + 1) * M])
+    table = scenario_table()
+    # a dedicated (non-default) stream: the engine launches on it and torch's events time it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    years = np.arange(1746, 2301, dtype=np.float64)
+
+    def make_engine(m, x):
+        e = hb.Ensemble(m, table, device=local_rank, outputs=["CO2_concentration", "global_tas"],
+                        cold_newton=args.cold_newton, stream=stream.cuda_stream)
+        for j, nme in enumerate(PARAMS):
+            e.setvar(nme, np.ascontiguousarray(x[:, j]))
+        e.prepare()
+        e.synchronize()
+        return e
+
+    ens = make_engine(M, X)
+    gather_buf = None
+    views = []
+    if world > 1:
+        for v in ("CO2_concentration", "global_tas"):
+            ptr, stride, ny = ens.output_device(v)
+            views.append(torch.as_tensor(CudaArrayView(ptr, (ny, stride)), device="cuda"))
+        gather_buf = [torch.empty((world,) + tuple(t.shape), dtype=torch.float64, device="cuda")
+                      for t in views]
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")  # 256 MB > L2
+
+    def step_device(e, do_gather=True):
+        e.reset()
+        e.run()
+        if world > 1 and do_gather:
+            # the job's single collective: every rank ends up with all members' trajectories
+            for t, g in zip(views, gather_buf):
+                dist.all_gather_into_tensor(g, t)
+
+    def timed(e, fn, steps, warmup, flush_l2):
+        for _ in range(warmup):
+            fn(e)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        kernel_ms = []
+        t_ms = 0.0
+        for _ in range(steps):
+            if flush_l2:
+                flush.fill_(1.0)
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            fn(e)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            t_ms += ev0.elapsed_time(ev1)
+            kernel_ms.append(e.last_run_ms)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), float(np.mean(kernel_ms))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms, kernel_ms = timed(ens, step_device, args.steps, args.warmup, M < 16384)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * M * YEARS / (ms_per_step * 1e-3)
+    cnt = ens.counters()
+    st, _ = ens.status()
+    failed = int((st != 0).sum())
+
+    # ---- end to end through the public API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        pinned_in = [torch.from_numpy(np.ascontiguousarray(X[:, j])).pin_memory() for j in range(4)]
+        pinned_out = [torch.empty((M, YEARS), dtype=torch.float64).pin_memory() for _ in range(2)]
+
+        def step_e2e(e):
+            for j, nme in enumerate(PARAMS):
+                e.setvar(nme, pinned_in[j].numpy())      # host -> device
+            e.reset()                                    # set-up + spin-up (parameters changed)
+            e.run()
+            e.fetch("CO2_concentration", years, out=pinned_out[0].numpy())   # device -> host
+            e.fetch("global_tas", years, out=pinned_out[1].numpy())
+
+        e2e_ms, _ = timed(ens, step_e2e, max(2, args.steps // 2), 1, False)
+        e2e_ms /= max(2, args.steps // 2)
+        e2e = {"value": world * M * YEARS / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(4 * M * 8), "d2h_bytes_per_step": int(2 * M * YEARS * 8),
+               "ms_per_step": e2e_ms,
+               "includes": "4 parameter vectors H2D, set-up + spin-up, run, CO2+Tgav x 555 yr D2H"}
+
+    # ---- BASELINE.json configs[1]: the 1 024-member ensemble on one GPU ----
+    small = None
+    if args.small_members and rank == 0 and world == 1:
+        ms_ = args.small_members
+        es = make_engine(ms_, lhs(ms_))
+        sm_ms, sm_k = timed(es, lambda e: (e.reset(), e.run()), args.steps, 3, True)
+        small = {"members": ms_, "value": ms_ * YEARS / (sm_ms / args.steps * 1e-3), "unit": UNIT,
+                 "ms_per_step": sm_ms / args.steps, "note": "BASELINE.json configs[1]; fills "
+                 "%d of 148 SMs' worth of CTAs" % ((ms_ + 127) // 128)}
+        es.close()
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = M * YEARS * B_ALG / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))[
+            "dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks
+                else "B200_PROFILING.md fallback (of fallback)",
+                "kernel": "hx_run_kernel", "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_member_year": B_ALG,
+                "note": "FP64 issue/latency binds before HBM on this path (SURVEY.md 8(d))"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            v, kind, cores, what = cpu_reference_pass(args.ref_members_per_core)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": what}
+        except Exception as ex:  # the checker is optional for the measurement
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable",
+                   "sample": repr(ex)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": 2 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+        "work_per_member_year": {k: cnt[k] / max(1, cnt["member_years"]) for k in
+                                 ("rhs_evals", "rk_steps", "stashes", "newton_iterations",
+                                  "newton_calls")},
+        "failed_members": failed, "small_ensemble": small,
+    }
+    print(json.dumps(line))
+    ens.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

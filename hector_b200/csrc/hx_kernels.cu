@@ -271,7 +271,7 @@ __device__ __noinline__ void chem_equilibrate(EqBox &b, Work &w) {
   const double alk_min = 2100e-6, alk_max = 2750e-6;
   for (double alk1 = alk_min; alk1 <= alk_max; alk1 += (alk_max - alk_min) / 20)
     (void)eq_fmin(b, alk1, w);
-  const double tolerance = 5.9604644775390625e-08; /* ldexp(1.0, 1 - 26) */
+  const double tolerance = 2.9802322387695312e-08; /* ldexp(1.0, 1 - 26) = 2^-25 */
   double min = alk_min, max = alk_max;
   double x, wv, v, u, delta, delta2, fu, fv, fw, fx, mid, fract1, fract2;
   const double golden = 0.3819660f;

@@ -42,8 +42,11 @@ def ref_runs():
     return cases
 
 
+# natural scale below which a relative error is meaningless (outputs that pass through zero
+# or are differences of large pools); CO2 / Tgav floors are SURVEY.md section 8(d)'s
 FLOOR = {"global_tas": 0.01, "CO2_concentration": 1.0, "sst": 0.01, "land_tas": 0.01,
-         "heatflux": 0.1, "RF_tot": 0.01, "RF_CO2": 0.01}
+         "heatflux": 0.1, "RF_tot": 0.01, "RF_CO2": 0.01, "RF_CH4": 0.01, "RF_N2O": 0.01,
+         "NBP": 1.0, "ocean_uptake": 1.0, "thawedp_c": 1.0, "rh_ch4": 1e-3}
 
 
 def parity_err(x, ref, var):
