@@ -569,6 +569,7 @@ int hx_prepare(hx_handle h) {
     const double ocean_area = (1.0 - 0.29) * 5100656E8;
     C.powtoheat = ocean_area * (60.0 * 60.0 * 24.0 * 365.2422) / std::pow(10.0, 22);
   }
+  C.rk_grow_max = 9.0 / 10.0 * std::pow(std::pow(5.0, -5.0), -1.0 / 5.0);
 
   /* device scenario tables */
   std::vector<double> tab((size_t)h->nscen * nrow * SC_STRIDE, 0.0);

@@ -74,6 +74,7 @@ __device__ __forceinline__ LandPar load_landpar(const HxDev &d, int m) {
   p.wf = PAR(PI_WARMINGFACTOR); p.rh_ch4_frac = PAR(PI_RH_CH4_FRAC); p.pf_mu = PAR(PI_PF_MU);
   p.pf_sigma = PAR(PI_PF_SIGMA); p.fpf_static = PAR(PI_FPF_STATIC); p.eps_abs = PAR(PI_EPS_ABS);
   p.eps_rel = PAR(PI_EPS_REL);
+  p.lnq10 = log(p.q10);
   p.k_LL_HL = DER(DI_K_LL_HL); p.k_LL_IO = DER(DI_K_LL_IO); p.k_HL_DO = DER(DI_K_HL_DO);
   p.k_IO_LL = DER(DI_K_IO_LL); p.k_IO_HL = DER(DI_K_IO_HL); p.k_IO_DO = DER(DI_K_IO_DO);
   p.k_DO_IO = DER(DI_K_DO_IO);
@@ -245,6 +246,7 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   STATE(SI_HEAT_MIXED) = 0.0; STATE(SI_HEAT_INTERIOR) = 0.0; STATE(SI_RF_PREV) = 0.0;
   STATE(SI_BASE_TOT) = 0.0; STATE(SI_BASE_CO2) = 0.0; STATE(SI_BASE_CH4) = 0.0;
   STATE(SI_BASE_N2O) = 0.0;
+  STATE(SI_TLAND_WSUM) = 0.0; STATE(SI_TLAND_WCOMP) = 0.0;
   d.sst_hist[m] = 0.0;   /* row 0: temp_sst[0] = 0 */
   d.tland_hist[m] = 0.0;
   d.fail_year[m] = 0;
@@ -264,8 +266,8 @@ struct EqBox {
 __device__ __noinline__ double eq_fmin(EqBox &b, double alk, Work &w) {
   b.alk = alk;
   b.h = 0.0;
-  const double pco2 = csys_solve(*b.C, b.k, b.carbon, alk, b.volume, b.h, true, b.ok, w);
-  return fabs(surface_flux(b.CO2, pco2, 1.0, b.k.Tr, b.As) - b.target);
+  const double pco2 = csys_box(*b.C, b.k, b.carbon, alk, b.volume, b.h, true, b.ok, w);
+  return fabs(surface_flux(b.CO2, pco2, 1.0, b.k.G) - b.target);
 }
 __device__ __noinline__ void chem_equilibrate(EqBox &b, Work &w) {
   const double alk_min = 2100e-6, alk_max = 2750e-6;
@@ -370,11 +372,11 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
     const double CO2 = mb.atmos * HX_PGC_TO_PPMVCO2;
     EqBox b;
     b.C = &C; b.ok = true; b.CO2 = CO2;
-    b.k = chem_constants(C, 0.0 + HX_MEAN_TOS_TEMP + HX_DT_HL);
+    b.k = chem_constants(C, 0.0 + HX_MEAN_TOS_TEMP + HX_DT_HL, C.As_HL);
     b.carbon = mb.bHL; b.volume = C.vol_HL; b.As = C.As_HL; b.target = 1.000;
     chem_equilibrate(b, w);
     mb.alkHL = b.alk; mb.hHL = b.h;
-    b.k = chem_constants(C, 0.0 + HX_MEAN_TOS_TEMP + HX_DT_LL);
+    b.k = chem_constants(C, 0.0 + HX_MEAN_TOS_TEMP + HX_DT_LL, C.As_LL);
     b.carbon = mb.bLL; b.volume = C.vol_LL; b.As = C.As_LL; b.target = -1.000;
     chem_equilibrate(b, w);
     mb.alkLL = b.alk; mb.hLL = b.h;
@@ -431,6 +433,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
   Work w = {0, 0, 0, 0, 0, 0};
   double ch4 = 0, tland = 0, sst = 0, heat_mixed = 0, heat_interior = 0, rf_prev = 0;
   double base_tot = 0, base_co2 = 0, base_ch4 = 0, base_n2o = 0;
+  double wsum = 0, wcomp = 0;
   unsigned years_done = 0;
   if (lane_ok) {
     load_member(d, m, mb);
@@ -444,6 +447,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     rf_prev = STATE(SI_RF_PREV);
     base_tot = STATE(SI_BASE_TOT); base_co2 = STATE(SI_BASE_CO2); base_ch4 = STATE(SI_BASE_CH4);
     base_n2o = STATE(SI_BASE_N2O);
+    wsum = STATE(SI_TLAND_WSUM); wcomp = STATE(SI_TLAND_WCOMP);
   } else {
     mb.status = -1;
   }
@@ -490,12 +494,12 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         /* --- OceanComponent::run: ocean_component.cpp:356-407 --- */
         mb.flux_sum = 0.0;
         mb.timesteps = 0;
-        mb.kHL = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_HL);
-        mb.kLL = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_LL);
+        mb.kHL = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_HL, C.As_HL);
+        mb.kLL = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_LL, C.As_LL);
         {
           bool ok = true;
-          mb.pco2HL = csys_solve(C, mb.kHL, mb.bHL, mb.alkHL, C.vol_HL, mb.hHL, cold, ok, w);
-          mb.pco2LL = csys_solve(C, mb.kLL, mb.bLL, mb.alkLL, C.vol_LL, mb.hLL, cold, ok, w);
+          mb.pco2HL = csys_box(C, mb.kHL, mb.bHL, mb.alkHL, C.vol_HL, mb.hHL, cold, ok, w);
+          mb.pco2LL = csys_box(C, mb.kLL, mb.bLL, mb.alkLL, C.vol_LL, mb.hLL, cold, ok, w);
           if (!ok) mb.status = HX_MEMBER_NOROOT;
         }
 
@@ -504,15 +508,24 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         mb.luc_e = scm1[SC_LUC_E]; mb.luc_u = scm1[SC_LUC_U];
         mb.ffi = scm1[SC_FFI]; mb.daccs = scm1[SC_DACCS];
         mb.neg |= (mb.luc_e < 0.0) | (mb.luc_u < 0.0) | (mb.ffi < 0.0) | (mb.daccs < 0.0);
+        /* Tland_rm: for (i = t-200; i < t; i++) Tland_rm += Tland_record.get(i) * wf; /= 200
+         * (:1041-1050).  Keys below the first record (start+1) extrapolate flat to it and that
+         * record is exactly 0, so the window is sum_{k = max(1, r-201)}^{r-2} hist[k] * wf.  It is
+         * carried as a compensated (Neumaier) running sum: one term enters and one leaves per
+         * year instead of re-reading 200 history rows. */
         double window = 0.0;
         if (r >= 2) {
-          /* for (i = t-200; i < t; i++) Tland_rm += Tland_record.get(i) * wf; keys below the
-           * first record (start+1) extrapolate flat to it, and that record is exactly 0 */
-          int k0 = r - 201;
-          if (k0 < 1) k0 = 1;
           const double *th = d.tland_hist + m;
-          for (int k = k0; k <= r - 2; ++k) window += th[(size_t)k * Mp] * p.wf;
-          window /= 200;
+          double add = 0.0, sub = 0.0;
+          if (r - 2 >= 1) add = th[(size_t)(r - 2) * Mp] * p.wf;
+          if (r - 202 >= 1) sub = -(th[(size_t)(r - 202) * Mp] * p.wf);
+          double t1 = wsum + add;
+          wcomp += (fabs(wsum) >= fabs(add)) ? ((wsum - t1) + add) : ((add - t1) + wsum);
+          wsum = t1;
+          t1 = wsum + sub;
+          wcomp += (fabs(wsum) >= fabs(sub)) ? ((wsum - t1) + sub) : ((sub - t1) + wsum);
+          wsum = t1;
+          window = (wsum + wcomp) / 200;
         }
         slow_params(mb, p, tland, r == 1, window);
 
@@ -577,16 +590,35 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
            *   interior = sum_{i<t}  sst[i] K(t-i)     (:534-537) */
           double DPAST2 = 0.0, hint = 0.0;
           {
-            const double *sh = d.sst_hist + m;
-            const double *kk = d.ker + m;
-            double kj1 = kk[(size_t)(r + 1 <= C.nrow ? r + 1 : C.nrow) * Mp]; /* K(t+1) */
-            for (int i = 0; i < r; ++i) {
-              const int j = r - i;
-              const double sv = sh[(size_t)i * Mp];
-              const double kj = kk[(size_t)j * Mp];
+            /* oldest first, like the reference; 8 history rows are fetched per trip so the
+             * loads of a trip are all in flight together */
+            const double *ps = d.sst_hist + m;                   /* sst[i], i ascending */
+            const double *pk = d.ker + m + (size_t)r * Mp;       /* K(r - i), descending */
+            double kj1 = pk[Mp];                                 /* K(r + 1) */
+            int i = 0;
+            for (; i + 8 <= r; i += 8) {
+              double sv[8], kv[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                sv[u] = ps[(size_t)u * Mp];
+                kv[u] = *(pk - (size_t)u * Mp);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                DPAST2 = DPAST2 + sv[u] * kj1;
+                hint = hint + sv[u] * kv[u];
+                kj1 = kv[u];
+              }
+              ps += 8 * Mp;
+              pk -= 8 * Mp;
+            }
+            for (; i < r; ++i) {
+              const double sv = *ps, kj = *pk;
               DPAST2 = DPAST2 + sv * kj1;
               hint = hint + sv * kj;
               kj1 = kj;
+              ps += Mp;
+              pk -= Mp;
             }
           }
           DPAST2 = DPAST2 * fso * DER(DI_SQDT_TAUDIF);
@@ -663,6 +695,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
       STATE(SI_RF_PREV) = rf_prev;
       STATE(SI_BASE_TOT) = base_tot; STATE(SI_BASE_CO2) = base_co2;
       STATE(SI_BASE_CH4) = base_ch4; STATE(SI_BASE_N2O) = base_n2o;
+      STATE(SI_TLAND_WSUM) = wsum; STATE(SI_TLAND_WCOMP) = wcomp;
     }
     flush_work(d, w, years_done, mb.status != 0 ? 1u : 0u);
   }

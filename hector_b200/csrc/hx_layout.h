@@ -56,6 +56,7 @@ enum {
   SI_MAX_TIMESTEP, SI_TIMEOUT, SI_LASTFLUX_ANN, SI_SOLVER_DT,
   SI_CH4, SI_TLAND, SI_SST, SI_HEAT_MIXED, SI_HEAT_INTERIOR, SI_RF_PREV,
   SI_BASE_TOT, SI_BASE_CO2, SI_BASE_CH4, SI_BASE_N2O,
+  SI_TLAND_WSUM, SI_TLAND_WCOMP, /* 200-year land-temperature window: compensated running sum */
   SI_COUNT
 };
 
@@ -93,6 +94,8 @@ struct HxConst {
   double spy_ocean;
   /* DOECLIM (temperature_component.hpp:77-98) */
   double powtoheat;
+  /* odeint default_step_adjuster growth at the error floor: 0.9 * pow(pow(5,-5), -1/5) */
+  double rk_grow_max;
 };
 
 /* status words live next to the state */
