@@ -29,7 +29,8 @@ class HxConfig(C.Structure):
 
 
 def lib_path():
-    return os.path.join(HERE, "libhector_b200.so")
+    # HECTOR_B200_LIB: alternative build of the same library (tuning experiments)
+    return os.environ.get("HECTOR_B200_LIB") or os.path.join(HERE, "libhector_b200.so")
 
 
 def lib():

@@ -69,15 +69,7 @@ __device__ __forceinline__ void fence_proxy_async() {
 
 __device__ __forceinline__ LandPar load_landpar(const HxDev &d, int m) {
   LandPar p;
-  p.beta = PAR(PI_BETA); p.q10 = PAR(PI_Q10); p.f_nppv = PAR(PI_F_NPPV); p.f_nppd = PAR(PI_F_NPPD);
-  p.f_litterd = PAR(PI_F_LITTERD); p.npp_flux0 = PAR(PI_NPP_FLUX0); p.C0 = PAR(PI_C0);
-  p.wf = PAR(PI_WARMINGFACTOR); p.rh_ch4_frac = PAR(PI_RH_CH4_FRAC); p.pf_mu = PAR(PI_PF_MU);
-  p.pf_sigma = PAR(PI_PF_SIGMA); p.fpf_static = PAR(PI_FPF_STATIC); p.eps_abs = PAR(PI_EPS_ABS);
-  p.eps_rel = PAR(PI_EPS_REL);
-  p.lnq10 = log(p.q10);
-  p.k_LL_HL = DER(DI_K_LL_HL); p.k_LL_IO = DER(DI_K_LL_IO); p.k_HL_DO = DER(DI_K_HL_DO);
-  p.k_IO_LL = DER(DI_K_IO_LL); p.k_IO_HL = DER(DI_K_IO_HL); p.k_IO_DO = DER(DI_K_IO_DO);
-  p.k_DO_IO = DER(DI_K_DO_IO);
+  p.P = d.P; p.D = d.D; p.Mp = (size_t)d.Mpad; p.m = m;
   return p;
 }
 
@@ -222,6 +214,7 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   DER(DI_TAUKSL) = tauksl;
   DER(DI_SQDT_TAUDIF) = sqdt;
   DER(DI_HF_INT) = cas * fso / sqrt(taudif * dt);
+  DER(DI_LNQ10) = log(PAR(PI_Q10));
 
   /* initial pools: ocean_component.cpp:224-260, simpleNbox.cpp:45-81, simpleNbox-runtime.cpp:172 */
   const double LL_vol_frac = C.vol_LL / (C.vol_LL + C.vol_HL);
@@ -341,6 +334,8 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
   load_member(d, m, mb);
   const LandPar p = load_landpar(d, m);
   Work w = {0, 0, 0, 0, 0, 0};
+  ChemRef ck;
+  ck.base = nullptr; ck.stride = 0; ck.tid = 0; /* no chemistry during spin-up */
   const double eps_spinup = PAR(PI_EPS_SPINUP);
   int steps = 0;
   if (!(C.flags & HX_FLAG_NO_SPINUP)) {
@@ -353,7 +348,7 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
       mb.npp_luc_adjust = (mb.eos_vegc - mb.cum_luc_va) / mb.eos_vegc;
       const double o0 = mb.atmos, o1 = mb.veg, o2 = mb.det, o3 = mb.soil, o4 = mb.perm,
                    o5 = mb.thawed, o6 = total_ocean(mb), o7 = mb.earth;
-      solver_year<true>(mb, C, p, (double)(step - 1), (double)step, true, w);
+      solver_year<true>(mb, C, p, ck, (double)(step - 1), (double)step, true, w);
       if (mb.status) break;
       double mx = fabs(mb.atmos - o0);
       mx = fmax(mx, fabs(mb.veg - o1)); mx = fmax(mx, fabs(mb.det - o2));
@@ -392,10 +387,11 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
 
 /* ======================================================================================== */
 /* the yearly coupled step, rows r0+1 .. r1 (row = year - start_year) */
-__global__ void __launch_bounds__(HX_BLOCK)
+__global__ void __launch_bounds__(HX_BLOCK, HX_RUN_MIN_CTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   __shared__ __align__(128) double slab[2][(HX_SLAB_YEARS + 1) * SC_STRIDE];
   __shared__ __align__(16) double row0[SC_STRIDE];
+  __shared__ double chemk[10][HX_BLOCK]; /* K1, K2, Kb, Kw, Kh of the HL and LL boxes */
   __shared__ __align__(8) uint64_t bars[2];
 
   const int tid = threadIdx.x;
@@ -428,29 +424,13 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
   if (tid == 0 && nslab > 0) issue(0);
 
   Member mb;
-  LandPar p;
-  ForcPar fp;
   Work w = {0, 0, 0, 0, 0, 0};
-  double ch4 = 0, tland = 0, sst = 0, heat_mixed = 0, heat_interior = 0, rf_prev = 0;
-  double base_tot = 0, base_co2 = 0, base_ch4 = 0, base_n2o = 0;
-  double wsum = 0, wcomp = 0;
   unsigned years_done = 0;
-  if (lane_ok) {
-    load_member(d, m, mb);
-    p = load_landpar(d, m);
-    fp.C0 = p.C0; fp.M0 = PAR(PI_M0); fp.N0 = PAR(PI_N0); fp.aero = PAR(PI_AERO);
-    fp.vol = PAR(PI_VOL); fp.delta_co2 = PAR(PI_DELTA_CO2); fp.delta_ch4 = PAR(PI_DELTA_CH4);
-    fp.delta_n2o = PAR(PI_DELTA_N2O); fp.rho_bc = PAR(PI_RHO_BC); fp.rho_oc = PAR(PI_RHO_OC);
-    fp.rho_so2 = PAR(PI_RHO_SO2); fp.rho_nh3 = PAR(PI_RHO_NH3);
-    ch4 = STATE(SI_CH4); tland = STATE(SI_TLAND); sst = STATE(SI_SST);
-    heat_mixed = STATE(SI_HEAT_MIXED); heat_interior = STATE(SI_HEAT_INTERIOR);
-    rf_prev = STATE(SI_RF_PREV);
-    base_tot = STATE(SI_BASE_TOT); base_co2 = STATE(SI_BASE_CO2); base_ch4 = STATE(SI_BASE_CH4);
-    base_n2o = STATE(SI_BASE_N2O);
-    wsum = STATE(SI_TLAND_WSUM); wcomp = STATE(SI_TLAND_WCOMP);
-  } else {
-    mb.status = -1;
-  }
+  const LandPar p = load_landpar(d, lane_ok ? m : 0);
+  ChemRef ck;
+  ck.base = &chemk[0][0]; ck.stride = HX_BLOCK; ck.tid = tid;
+  if (lane_ok) load_member(d, m, mb);
+  else mb.status = -1;
   const bool cold = (C.flags & HX_FLAG_COLD_NEWTON) != 0;
   const size_t Mp = d.Mpad;
 
@@ -466,11 +446,10 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         const double *scm1 = sl + (size_t)(r - 1 - base) * SC_STRIDE; /* year y-1 */
         const int y = C.start_year + r;
 
-        /* --- OH, CH4, O3: oh_component.cpp:137-174, ch4_component.cpp:152-199,
-         *     o3_component.cpp:126-146 --- */
-        const double M0 = fp.M0;
+        /* --- OH, CH4: oh_component.cpp:137-174, ch4_component.cpp:152-199 --- */
         {
-          const double previous_ch4 = ch4;
+          const double M0 = PAR(PI_M0);
+          const double previous_ch4 = STATE(SI_CH4);
           double toh = 0.0;
           if (previous_ch4 != M0) {
             const double a = PAR(PI_CCH4) * ((1.0 * log(previous_ch4)) - log(M0));
@@ -486,51 +465,60 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           const double strat_sink = previous_ch4 / PAR(PI_TSTRAT);
           const double oh_sink = previous_ch4 / tau_oh;
           const double dCH4 = emisTocon - soil_sink - strat_sink - oh_sink;
-          ch4 = previous_ch4 + dCH4;
+          STATE(SI_CH4) = previous_ch4 + dCH4;
         }
-        const double o3 = (5 * log(ch4)) + (0.125 * sc[SC_NOX]) + (0.0011 * sc[SC_CO]) +
-                          (0.0033 * sc[SC_NMVOC]);
 
         /* --- OceanComponent::run: ocean_component.cpp:356-407 --- */
         mb.flux_sum = 0.0;
         mb.timesteps = 0;
-        mb.kHL = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_HL, C.As_HL);
-        mb.kLL = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_LL, C.As_LL);
         {
+          const double sst = STATE(SI_SST);
           bool ok = true;
-          mb.pco2HL = csys_box(C, mb.kHL, mb.bHL, mb.alkHL, C.vol_HL, mb.hHL, cold, ok, w);
-          mb.pco2LL = csys_box(C, mb.kLL, mb.bLL, mb.alkLL, C.vol_LL, mb.hLL, cold, ok, w);
+          ChemK k = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_HL, C.As_HL);
+          ck.store(0, k);
+          mb.gHL = k.G;
+          mb.pco2HL = csys_box(C, k, mb.bHL, mb.alkHL, C.vol_HL, mb.hHL, cold, ok, w);
+          k = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_LL, C.As_LL);
+          ck.store(1, k);
+          mb.gLL = k.G;
+          mb.pco2LL = csys_box(C, k, mb.bLL, mb.alkLL, C.vol_LL, mb.hLL, cold, ok, w);
           if (!ok) mb.status = HX_MEMBER_NOROOT;
         }
 
         /* --- SimpleNbox::run + slowparameval: simpleNbox-runtime.cpp:206-227, 945-1072 --- */
-        d.tland_hist[(size_t)r * Mp + m] = tland; /* Tland_record[y] = land tas of year y-1 */
-        mb.luc_e = scm1[SC_LUC_E]; mb.luc_u = scm1[SC_LUC_U];
-        mb.ffi = scm1[SC_FFI]; mb.daccs = scm1[SC_DACCS];
-        mb.neg |= (mb.luc_e < 0.0) | (mb.luc_u < 0.0) | (mb.ffi < 0.0) | (mb.daccs < 0.0);
-        /* Tland_rm: for (i = t-200; i < t; i++) Tland_rm += Tland_record.get(i) * wf; /= 200
-         * (:1041-1050).  Keys below the first record (start+1) extrapolate flat to it and that
-         * record is exactly 0, so the window is sum_{k = max(1, r-201)}^{r-2} hist[k] * wf.  It is
-         * carried as a compensated (Neumaier) running sum: one term enters and one leaves per
-         * year instead of re-reading 200 history rows. */
-        double window = 0.0;
-        if (r >= 2) {
-          const double *th = d.tland_hist + m;
-          double add = 0.0, sub = 0.0;
-          if (r - 2 >= 1) add = th[(size_t)(r - 2) * Mp] * p.wf;
-          if (r - 202 >= 1) sub = -(th[(size_t)(r - 202) * Mp] * p.wf);
-          double t1 = wsum + add;
-          wcomp += (fabs(wsum) >= fabs(add)) ? ((wsum - t1) + add) : ((add - t1) + wsum);
-          wsum = t1;
-          t1 = wsum + sub;
-          wcomp += (fabs(wsum) >= fabs(sub)) ? ((wsum - t1) + sub) : ((sub - t1) + wsum);
-          wsum = t1;
-          window = (wsum + wcomp) / 200;
+        {
+          const double tland = STATE(SI_TLAND);
+          const double wf = LP_WF(p);
+          d.tland_hist[(size_t)r * Mp + m] = tland; /* Tland_record[y] = land tas of year y-1 */
+          mb.luc_e = scm1[SC_LUC_E]; mb.luc_u = scm1[SC_LUC_U];
+          mb.ffi = scm1[SC_FFI]; mb.daccs = scm1[SC_DACCS];
+          mb.neg |= (mb.luc_e < 0.0) | (mb.luc_u < 0.0) | (mb.ffi < 0.0) | (mb.daccs < 0.0);
+          /* Tland_rm: for (i = t-200; i < t; i++) Tland_rm += Tland_record.get(i) * wf; /= 200
+           * (:1041-1050).  Keys below the first record (start+1) extrapolate flat to it and
+           * that record is exactly 0, so the window is sum_{k = max(1, r-201)}^{r-2} hist[k] wf.
+           * It is carried as a compensated (Neumaier) running sum: one term enters and one
+           * leaves per year instead of re-reading 200 history rows. */
+          double window = 0.0;
+          if (r >= 2) {
+            const double *th = d.tland_hist + m;
+            double wsum = STATE(SI_TLAND_WSUM), wcomp = STATE(SI_TLAND_WCOMP);
+            double add = 0.0, sub = 0.0;
+            if (r - 2 >= 1) add = th[(size_t)(r - 2) * Mp] * wf;
+            if (r - 202 >= 1) sub = -(th[(size_t)(r - 202) * Mp] * wf);
+            double t1 = wsum + add;
+            wcomp += (fabs(wsum) >= fabs(add)) ? ((wsum - t1) + add) : ((add - t1) + wsum);
+            wsum = t1;
+            t1 = wsum + sub;
+            wcomp += (fabs(wsum) >= fabs(sub)) ? ((wsum - t1) + sub) : ((sub - t1) + wsum);
+            wsum = t1;
+            window = (wsum + wcomp) / 200;
+            STATE(SI_TLAND_WSUM) = wsum; STATE(SI_TLAND_WCOMP) = wcomp;
+          }
+          slow_params(mb, p, tland, r == 1, window);
         }
-        slow_params(mb, p, tland, r == 1, window);
 
         /* --- CarbonCycleSolver::run --- */
-        solver_year<false>(mb, C, p, (double)(y - 1), (double)y, cold, w);
+        solver_year<false>(mb, C, p, ck, (double)(y - 1), (double)y, cold, w);
         if (mb.status) {
           d.status[m] = mb.status;
           d.fail_year[m] = y;
@@ -552,16 +540,25 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           break;
         }
 
-        /* --- ForcingComponent::run --- */
+        /* --- OzoneComponent::run (o3_component.cpp:126-146) + ForcingComponent::run --- */
+        const double ch4 = STATE(SI_CH4);
+        const double o3 = (5 * log(ch4)) + (0.125 * sc[SC_NOX]) + (0.0011 * sc[SC_CO]) +
+                          (0.0033 * sc[SC_NMVOC]);
         double rf_tot = 0.0, rf_co2 = 0.0, rf_ch4 = 0.0, rf_n2o = 0.0;
         if (y >= C.baseyear) {
+          ForcPar fp;
+          fp.C0 = LP_C0(p); fp.M0 = PAR(PI_M0); fp.N0 = PAR(PI_N0); fp.aero = PAR(PI_AERO);
+          fp.vol = PAR(PI_VOL); fp.delta_co2 = PAR(PI_DELTA_CO2); fp.delta_ch4 = PAR(PI_DELTA_CH4);
+          fp.delta_n2o = PAR(PI_DELTA_N2O); fp.rho_bc = PAR(PI_RHO_BC); fp.rho_oc = PAR(PI_RHO_OC);
+          fp.rho_so2 = PAR(PI_RHO_SO2); fp.rho_nh3 = PAR(PI_RHO_NH3);
           double fco2, fch4, fn2o;
           const double F = forcing_total(fp, sc, CO2_conc, ch4, o3, fco2, fch4, fn2o, mb.status);
           if (y == C.baseyear) {
-            base_tot = F; base_co2 = fco2; base_ch4 = fch4; base_n2o = fn2o;
+            STATE(SI_BASE_TOT) = F; STATE(SI_BASE_CO2) = fco2; STATE(SI_BASE_CH4) = fch4;
+            STATE(SI_BASE_N2O) = fn2o;
           }
-          rf_tot = F - base_tot; rf_co2 = fco2 - base_co2; rf_ch4 = fch4 - base_ch4;
-          rf_n2o = fn2o - base_n2o;
+          rf_tot = F - STATE(SI_BASE_TOT); rf_co2 = fco2 - STATE(SI_BASE_CO2);
+          rf_ch4 = fch4 - STATE(SI_BASE_CH4); rf_n2o = fn2o - STATE(SI_BASE_N2O);
           if (mb.status) {
             d.status[m] = mb.status;
             d.fail_year[m] = y;
@@ -570,10 +567,11 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         }
 
         /* --- TemperatureComponent::run: temperature_component.cpp:417-557 (tstep = r > 0) --- */
-        double tas, heatflux;
+        double tas, heatflux, tland_new, sst_new;
         {
           const double dt = 1.0, bsi = DC_BSI, cal = DC_CAL, cas = DC_CAS, flnd = DC_FLND,
                        fso = DC_FSO;
+          const double tland = STATE(SI_TLAND), sst = STATE(SI_SST), rf_prev = STATE(SI_RF_PREV);
           const double taucfl = DER(DI_TAUCFL), taukls = DER(DI_TAUKLS), taucfs = DER(DI_TAUCFS),
                        tauksl = DER(DI_TAUKSL);
           const double DelQL = rf_tot - rf_prev, DelQO = rf_tot - rf_prev;
@@ -632,13 +630,15 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           tas = flnd * TL + (1.0 - flnd) * bsi * TS;
           const double hf_mixed = cas * (TS - sst);
           const double hf_int = DER(DI_HF_INT) * (2.0 * TS - hint);
-          heat_mixed = heat_mixed + hf_mixed * (C.powtoheat * dt);
-          heat_interior = heat_interior + hf_int * (fso * C.powtoheat * dt);
+          STATE(SI_HEAT_MIXED) = STATE(SI_HEAT_MIXED) + hf_mixed * (C.powtoheat * dt);
+          STATE(SI_HEAT_INTERIOR) = STATE(SI_HEAT_INTERIOR) + hf_int * (fso * C.powtoheat * dt);
           heatflux = hf_mixed + fso * hf_int;
-          tland = TL;
-          sst = TS;
+          tland_new = TL;
+          sst_new = TS;
+          STATE(SI_TLAND) = TL;
+          STATE(SI_SST) = TS;
+          STATE(SI_RF_PREV) = rf_tot;
           d.sst_hist[(size_t)r * Mp + m] = TS;
-          rf_prev = rf_tot;
         }
         ++years_done;
 
@@ -657,12 +657,12 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_OCEAN_C, mb.bDO + mb.bIO + mb.bLL + mb.bHL);
         if (d.out_slot[OUT_HL_PH] >= 0) EMIT(OUT_HL_PH, -log10(mb.hHL));
         EMIT(OUT_ATMOS_C, mb.atmos);
-        EMIT(OUT_SST, sst);
+        EMIT(OUT_SST, sst_new);
         EMIT(OUT_PERMAFROST_C, mb.perm);
         EMIT(OUT_CH4, ch4);
         EMIT(OUT_N2O, sc[SC_N2O]);
         EMIT(OUT_O3, o3);
-        EMIT(OUT_LAND_TAS, tland);
+        EMIT(OUT_LAND_TAS, tland_new);
         EMIT(OUT_VEG_C, mb.veg);
         EMIT(OUT_DETRITUS_C, mb.det);
         EMIT(OUT_SOIL_C, mb.soil);
@@ -688,15 +688,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
   }
 
   if (lane_ok) {
-    if (mb.status == 0) {
-      store_member(d, m, mb);
-      STATE(SI_CH4) = ch4; STATE(SI_TLAND) = tland; STATE(SI_SST) = sst;
-      STATE(SI_HEAT_MIXED) = heat_mixed; STATE(SI_HEAT_INTERIOR) = heat_interior;
-      STATE(SI_RF_PREV) = rf_prev;
-      STATE(SI_BASE_TOT) = base_tot; STATE(SI_BASE_CO2) = base_co2;
-      STATE(SI_BASE_CH4) = base_ch4; STATE(SI_BASE_N2O) = base_n2o;
-      STATE(SI_TLAND_WSUM) = wsum; STATE(SI_TLAND_WCOMP) = wcomp;
-    }
+    if (mb.status == 0) store_member(d, m, mb);
     flush_work(d, w, years_done, mb.status != 0 ? 1u : 0u);
   }
 }

@@ -67,6 +67,7 @@ enum {
   DI_TAUCFL, DI_TAUKLS, DI_TAUCFS, DI_TAUKSL,
   DI_SQDT_TAUDIF, /* pow(dt/taudif, 0.5)            temperature_component.cpp:491 */
   DI_HF_INT,      /* cas*fso/pow(taudif*dt, 0.5)    temperature_component.cpp:539 */
+  DI_LNQ10,       /* log(q10_rh): pow(q10, x) is evaluated as exp(x * lnq10) */
   DI_COUNT
 };
 

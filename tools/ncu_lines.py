@@ -82,3 +82,15 @@ for (f, line), v in agg_in.items():
 print("==== by function: instr% samples% long_sb%")
 for k, v in sorted(g.items(), key=lambda kv: -kv[1][0]):
     print("%-28s %6.2f %6.2f %6.2f" % (k, 100 * v[0] / tot[0], 100 * v[1] / tot[1], 100 * v[2] / max(1, tot[2])))
+
+# ---- static SASS size by function ----
+st = collections.Counter()
+for (f, line, _, _) in lines_by_idx:
+    if f == "hx_model.cuh":
+        i = bisect.bisect_right([s for s, _ in gm], line) - 1
+        st[gm[i][1] if i >= 0 else "?"] += 1
+    else:
+        st[f] += 1
+print("==== static SASS instruction count by function (x16 B)")
+for k, v in st.most_common(20):
+    print("%-28s %6d" % (k, v))
