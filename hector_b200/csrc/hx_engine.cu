@@ -39,14 +39,21 @@ __global__ void k_fill(double *p, double v, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
-/* dst[dev_of_api[i]] = src[i] */
-__global__ void k_scatter(double *dst, const double *src, const int32_t *dev_of_api, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[dev_of_api[i]] = src[i];
+/* field `f` of a CTA-tiled array (hx_layout.h) for every device member: A[f][m] = v */
+__global__ void k_fill_field(double *A, int f, int nfields, double v, int Mpad) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < Mpad) A[HX_TILED(f, m, nfields)] = v;
 }
-__global__ void k_gather(double *dst, const double *src, const int32_t *dev_of_api, int n) {
+/* A[f][dev_of_api[i]] = src[i]  (src in API member order) */
+__global__ void k_scatter_field(double *A, int f, int nfields, const double *src,
+                                const int32_t *dev_of_api, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[dev_of_api[i]];
+  if (i < n) A[HX_TILED(f, dev_of_api[i], nfields)] = src[i];
+}
+__global__ void k_gather_field(double *dst, const double *A, int f, int nfields,
+                               const int32_t *dev_of_api, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = A[HX_TILED(f, dev_of_api[i], nfields)];
 }
 /* out[m_api][k] = src[yidx[k]][dev_of_api[m_api]]  (tile transpose through shared memory) */
 __global__ void k_fetch_transpose(double *out, const double *src, const int32_t *yidx,
@@ -68,7 +75,8 @@ __global__ void k_broadcast_state(double *S, int32_t *spinup_steps, int32_t *sta
                                   int32_t *fail_year, int src_m, int n_state, size_t Mpad) {
   size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (m >= Mpad || status[m] < 0 || (int)m == src_m) return;
-  for (int i = 0; i < n_state; ++i) S[(size_t)i * Mpad + m] = S[(size_t)i * Mpad + src_m];
+  for (int i = 0; i < n_state; ++i)
+    S[HX_TILED(i, m, SI_COUNT)] = S[HX_TILED(i, src_m, SI_COUNT)];
   spinup_steps[m] = spinup_steps[src_m];
   status[m] = status[src_m];
   fail_year[m] = fail_year[src_m];
@@ -211,19 +219,21 @@ struct Engine {
   }
 
   int upload_param(int pi) {
-    double *dst = d_P + (size_t)pi * Mpad;
     if (pvec_on_device_only[pi]) return HX_OK; /* already resident (hx_set_param_device) */
-    if (pvec[pi].empty()) {
-      k_fill<<<(Mpad + 255) / 256, 256, 0, stream>>>(dst, pscalar[pi], (size_t)Mpad);
-    } else {
-      int rc = ensure_pinned((size_t)Mpad * sizeof(double));
+    k_fill_field<<<(Mpad + 255) / 256, 256, 0, stream>>>(d_P, pi, PI_COUNT, pscalar[pi], Mpad);
+    CUDA_TRY(cudaGetLastError());
+    if (!pvec[pi].empty()) {
+      int rc = ensure_pinned((size_t)M * sizeof(double));
+      if (rc) return rc;
+      rc = ensure_stage((size_t)M * sizeof(double));
       if (rc) return rc;
       /* the pinned buffer may still feed an earlier async copy */
       CUDA_TRY(cudaStreamSynchronize(stream));
-      for (int i = 0; i < Mpad; ++i) h_pinned[i] = pscalar[pi];
-      for (int i = 0; i < M; ++i) h_pinned[dev_of_api[i]] = pvec[pi][i];
-      CUDA_TRY(cudaMemcpyAsync(dst, h_pinned, (size_t)Mpad * sizeof(double),
+      memcpy(h_pinned, pvec[pi].data(), (size_t)M * sizeof(double));
+      CUDA_TRY(cudaMemcpyAsync(d_stage, h_pinned, (size_t)M * sizeof(double),
                                cudaMemcpyHostToDevice, stream));
+      k_scatter_field<<<(M + 255) / 256, 256, 0, stream>>>(d_P, pi, PI_COUNT, d_stage, d_dev_of_api, M);
+      CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaStreamSynchronize(stream));
     }
     return HX_OK;
@@ -454,13 +464,8 @@ int hx_set_param_device(hx_handle h, const char *name, const double *dev, int32_
   if (pi < 0 || pi == PI_N0) return h->fail(HX_ERR_ARG, std::string("bad per-member parameter: ") + name);
   if (n != h->M) return h->fail(HX_ERR_ARG, "hx_set_param_device: n != n_members");
   cudaSetDevice(h->cfg.device);
-  double *dst = h->d_P + (size_t)pi * h->Mpad;
-  if (h->identity_perm) {
-    cudaError_t e = cudaMemcpyAsync(dst, dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice,
-                                    h->stream);
-    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
-  } else {
-    k_scatter<<<(n + 255) / 256, 256, 0, h->stream>>>(dst, dev, h->d_dev_of_api, n);
+  k_scatter_field<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_P, pi, PI_COUNT, dev, h->d_dev_of_api, n);
+  {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
   }
@@ -477,12 +482,13 @@ int hx_get_param(hx_handle h, const char *name, double *out, int32_t n) {
   if (n != h->M) return h->fail(HX_ERR_ARG, "hx_get_param: n != n_members");
   if (h->pvec_on_device_only[pi]) {
     cudaSetDevice(h->cfg.device);
-    std::vector<double> tmp(h->Mpad);
-    cudaStreamSynchronize(h->stream);
-    cudaError_t e = cudaMemcpy(tmp.data(), h->d_P + (size_t)pi * h->Mpad,
-                               (size_t)h->Mpad * sizeof(double), cudaMemcpyDeviceToHost);
+    if (h->ensure_stage((size_t)n * sizeof(double))) return HX_ERR_CUDA;
+    k_gather_field<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_stage, h->d_P, pi, PI_COUNT,
+                                                          h->d_dev_of_api, n);
+    cudaError_t e = cudaMemcpyAsync(out, h->d_stage, (size_t)n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
-    for (int i = 0; i < n; ++i) out[i] = tmp[h->dev_of_api[i]];
   } else if (h->pvec[pi].empty()) {
     for (int i = 0; i < n; ++i) out[i] = h->pscalar[pi];
   } else {
@@ -801,8 +807,8 @@ int hx_spinup_state(hx_handle h, int32_t member, double *out14) {
   static const int idx[13] = {SI_ATMOS, SI_VEG, SI_DET, SI_SOIL, SI_PERMAFROST, SI_THAWED, SI_EARTH,
                               SI_BOX_HL, SI_BOX_LL, SI_BOX_IO, SI_BOX_DO, SI_ALK_HL, SI_ALK_LL};
   for (int k = 0; k < 13; ++k) {
-    cudaError_t e = cudaMemcpy(out14 + k, h->d_S_snap + (size_t)idx[k] * h->Mpad + dm, sizeof(double),
-                               cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(out14 + k, h->d_S_snap + HX_TILED(idx[k], dm, SI_COUNT),
+                               sizeof(double), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
   }
   int32_t steps = 0;

@@ -19,6 +19,13 @@
 
 namespace hx {
 
+/* run-kernel dynamic shared memory map (bytes) */
+#define HX_SMEM_SLAB_BYTES (2 * (HX_SLAB_YEARS + 1) * SC_STRIDE * 8)
+#define HX_SMEM_ROW0 HX_SMEM_SLAB_BYTES
+#define HX_SMEM_CHEMK (HX_SMEM_ROW0 + SC_STRIDE * 8)
+#define HX_SMEM_RK (HX_SMEM_CHEMK + 10 * HX_BLOCK * 8)
+#define HX_SMEM_RUN_BYTES (HX_SMEM_RK + HX_RK_SLOTS * HX_BLOCK * 8)
+
 /* ---- small PTX wrappers: mbarrier + bulk async copy (TMA engine, UBLKCP in SASS) ---- */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -63,48 +70,53 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-#define PAR(i) __ldg(d.P + (size_t)(i) * d.Mpad + m)
-#define STATE(i) d.S[(size_t)(i) * d.Mpad + m]
-#define DER(i) d.D[(size_t)(i) * d.Mpad + m]
+/* CTA-tiled SoA accessors: one base pointer per array, compile-time field offsets */
+struct Bases {
+  const double *P;
+  double *S, *D, *ker, *sst, *tland;
+};
+__device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, int m) {
+  const size_t tile = (size_t)(m / HX_BLOCK), ln = (size_t)(m % HX_BLOCK);
+  Bases b;
+  b.P = d.P + tile * PI_COUNT * HX_BLOCK + ln;
+  b.S = d.S + tile * SI_COUNT * HX_BLOCK + ln;
+  b.D = d.D + tile * DI_COUNT * HX_BLOCK + ln;
+  b.ker = d.ker + tile * (size_t)(C.nrow + 1) * HX_BLOCK + ln;
+  b.sst = d.sst_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
+  b.tland = d.tland_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
+  return b;
+}
+#define PAR(i) __ldg(BS.P + (i) * HX_BLOCK)
+#define STATE(i) BS.S[(i) * HX_BLOCK]
+#define DER(i) BS.D[(i) * HX_BLOCK]
 
-__device__ __forceinline__ LandPar load_landpar(const HxDev &d, int m) {
+__device__ __forceinline__ LandPar load_landpar(const Bases &BS) {
   LandPar p;
-  p.P = d.P; p.D = d.D; p.Mp = (size_t)d.Mpad; p.m = m;
+  p.P = BS.P; p.D = BS.D;
   return p;
 }
 
-__device__ __forceinline__ void load_member(const HxDev &d, int m, Member &mb) {
+__device__ __forceinline__ void load_member(const Bases &BS, Member &mb) {
+  mb.S = BS.S;
   mb.atmos = STATE(SI_ATMOS); mb.veg = STATE(SI_VEG); mb.det = STATE(SI_DET);
   mb.soil = STATE(SI_SOIL); mb.perm = STATE(SI_PERMAFROST); mb.thawed = STATE(SI_THAWED);
   mb.earth = STATE(SI_EARTH);
   mb.bHL = STATE(SI_BOX_HL); mb.bLL = STATE(SI_BOX_LL); mb.bIO = STATE(SI_BOX_IO);
   mb.bDO = STATE(SI_BOX_DO);
-  mb.alkHL = STATE(SI_ALK_HL); mb.alkLL = STATE(SI_ALK_LL);
-  mb.hHL = STATE(SI_H_HL); mb.hLL = STATE(SI_H_LL);
-  mb.tempferts_last = STATE(SI_TEMPFERTS); mb.f_frozen = STATE(SI_F_FROZEN);
-  mb.cum_luc_va = STATE(SI_CUM_LUC_VA); mb.eos_vegc = STATE(SI_EOS_VEGC);
-  mb.masstot = STATE(SI_MASSTOT); mb.cum_pf_ch4 = STATE(SI_CUM_PF_CH4);
-  mb.rh_ch4 = STATE(SI_RH_CH4);
   mb.max_timestep = STATE(SI_MAX_TIMESTEP); mb.timeout = (int)STATE(SI_TIMEOUT);
-  mb.lastflux_ann = STATE(SI_LASTFLUX_ANN); mb.solver_dt = STATE(SI_SOLVER_DT);
-  mb.status = 0; mb.neg = false; mb.timesteps = 0; mb.flux_sum = 0.0; mb.nbp = 0.0;
-  mb.pco2HL = mb.pco2LL = 0.0;
+  mb.solver_dt = STATE(SI_SOLVER_DT);
+  mb.status = 0; mb.neg = false; mb.timesteps = 0;
+  mb.pco2HL = mb.pco2LL = 0.0; mb.gHL = mb.gLL = 0.0; mb.luc_e = mb.luc_u = 0.0;
 }
 
-__device__ __forceinline__ void store_member(const HxDev &d, int m, const Member &mb) {
+__device__ __forceinline__ void store_member(const Bases &BS, const Member &mb) {
   STATE(SI_ATMOS) = mb.atmos; STATE(SI_VEG) = mb.veg; STATE(SI_DET) = mb.det;
   STATE(SI_SOIL) = mb.soil; STATE(SI_PERMAFROST) = mb.perm; STATE(SI_THAWED) = mb.thawed;
   STATE(SI_EARTH) = mb.earth;
   STATE(SI_BOX_HL) = mb.bHL; STATE(SI_BOX_LL) = mb.bLL; STATE(SI_BOX_IO) = mb.bIO;
   STATE(SI_BOX_DO) = mb.bDO;
-  STATE(SI_ALK_HL) = mb.alkHL; STATE(SI_ALK_LL) = mb.alkLL;
-  STATE(SI_H_HL) = mb.hHL; STATE(SI_H_LL) = mb.hLL;
-  STATE(SI_TEMPFERTS) = mb.tempferts_last; STATE(SI_F_FROZEN) = mb.f_frozen;
-  STATE(SI_CUM_LUC_VA) = mb.cum_luc_va; STATE(SI_EOS_VEGC) = mb.eos_vegc;
-  STATE(SI_MASSTOT) = mb.masstot; STATE(SI_CUM_PF_CH4) = mb.cum_pf_ch4;
-  STATE(SI_RH_CH4) = mb.rh_ch4;
   STATE(SI_MAX_TIMESTEP) = mb.max_timestep; STATE(SI_TIMEOUT) = (double)mb.timeout;
-  STATE(SI_LASTFLUX_ANN) = mb.lastflux_ann; STATE(SI_SOLVER_DT) = mb.solver_dt;
+  STATE(SI_SOLVER_DT) = mb.solver_dt;
 }
 
 __device__ __forceinline__ void flush_work(const HxDev &d, const Work &w, unsigned years,
@@ -130,6 +142,7 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   const int m = blockIdx.x * HX_BLOCK + threadIdx.x;
   if (m >= d.Mpad) return;
   if (d.status[m] < 0) return; /* padding lane */
+  const Bases BS = make_bases(d, C, m);
 
   /* ocean exchange rates (fraction of the box per year), ocean_component.cpp:262-284 */
   const double spy = C.spy_ocean;
@@ -168,8 +181,8 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
 
   /* lag kernel K(j), j = 1..nrow (E-4); Ker[i] of the reference is K(ns - i) */
   const double tau = taubot / dt;
-  double *ker = d.ker + m;
-  const size_t Mp = d.Mpad;
+  double *ker = BS.ker;
+  const size_t Mp = HX_BLOCK; /* row stride inside the tile */
   ker[0] = 0.0;
   const double K1v = ker_first(tau);
   ker[1 * Mp] = K1v;
@@ -240,8 +253,8 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   STATE(SI_BASE_TOT) = 0.0; STATE(SI_BASE_CO2) = 0.0; STATE(SI_BASE_CH4) = 0.0;
   STATE(SI_BASE_N2O) = 0.0;
   STATE(SI_TLAND_WSUM) = 0.0; STATE(SI_TLAND_WCOMP) = 0.0;
-  d.sst_hist[m] = 0.0;   /* row 0: temp_sst[0] = 0 */
-  d.tland_hist[m] = 0.0;
+  BS.sst[0] = 0.0;   /* row 0: temp_sst[0] = 0 */
+  BS.tland[0] = 0.0;
   d.fail_year[m] = 0;
   d.spinup_steps[m] = 0;
 }
@@ -326,29 +339,31 @@ __device__ __noinline__ void chem_equilibrate(EqBox &b, Work &w) {
 __global__ void __launch_bounds__(HX_BLOCK)
 hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int m_offset,
                  int only_member) {
+  __shared__ double rk[HX_RK_SLOTS][HX_BLOCK]; /* Runge-Kutta stage derivatives k1..k7 */
   const int m = m_offset + blockIdx.x * HX_BLOCK + threadIdx.x;
   if (m >= d.Mpad) return;
   if (d.status[m] < 0) return;
   if (only_member >= 0 && m != only_member) return;
+  const Bases BS = make_bases(d, C, m);
   Member mb;
-  load_member(d, m, mb);
-  const LandPar p = load_landpar(d, m);
+  load_member(BS, mb);
+  const LandPar p = load_landpar(BS);
   Work w = {0, 0, 0, 0, 0, 0};
   ChemRef ck;
   ck.base = nullptr; ck.stride = 0; ck.tid = 0; /* no chemistry during spin-up */
   const double eps_spinup = PAR(PI_EPS_SPINUP);
   int steps = 0;
   if (!(C.flags & HX_FLAG_NO_SPINUP)) {
-    mb.co2fert = 1.0; mb.tfd = 1.0; mb.tfs = 1.0; mb.f_new_thaw = 0.0; mb.f_frozen = 1.0;
-    mb.luc_e = mb.luc_u = mb.ffi = mb.daccs = 0.0;
+    mb.S[SI_X_CO2FERT * HX_TILE] = 1.0; mb.S[SI_X_TFD * HX_TILE] = 1.0; mb.S[SI_X_TFS * HX_TILE] = 1.0; mb.S[SI_X_FNEWTHAW * HX_TILE] = 0.0; mb.S[SI_F_FROZEN * HX_TILE] = 1.0;
+    mb.luc_e = mb.luc_u = mb.S[SI_X_FFI * HX_TILE] = mb.S[SI_X_DACCS * HX_TILE] = 0.0;
     bool spunup = false;
     int step = 0;
     while (!spunup && ++step < C.max_spinup) {
-      mb.flux_sum = 0.0; mb.timesteps = 0;
-      mb.npp_luc_adjust = (mb.eos_vegc - mb.cum_luc_va) / mb.eos_vegc;
+      mb.S[SI_X_FLUXSUM * HX_TILE] = 0.0; mb.timesteps = 0;
+      mb.S[SI_X_NPPLUC * HX_TILE] = (mb.S[SI_EOS_VEGC * HX_TILE] - mb.S[SI_CUM_LUC_VA * HX_TILE]) / mb.S[SI_EOS_VEGC * HX_TILE];
       const double o0 = mb.atmos, o1 = mb.veg, o2 = mb.det, o3 = mb.soil, o4 = mb.perm,
                    o5 = mb.thawed, o6 = total_ocean(mb), o7 = mb.earth;
-      solver_year<true>(mb, C, p, ck, (double)(step - 1), (double)step, true, w);
+      solver_year<true>(mb, C, p, ck, &rk[0][threadIdx.x], HX_BLOCK, (double)(step - 1), (double)step, true, w);
       if (mb.status) break;
       double mx = fabs(mb.atmos - o0);
       mx = fmax(mx, fabs(mb.veg - o1)); mx = fmax(mx, fabs(mb.det - o2));
@@ -358,10 +373,10 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
       spunup = (mx < eps_spinup);
     }
     steps = step;
-    mb.rh_ch4 = 0.0;           /* record_state in spin-up: simpleNbox.cpp:809-814 */
-    mb.tempferts_last = 1.0;
+    mb.S[SI_RH_CH4 * HX_TILE] = 0.0;           /* record_state in spin-up: simpleNbox.cpp:809-814 */
+    mb.S[SI_TEMPFERTS * HX_TILE] = 1.0;
   }
-  mb.eos_vegc = mb.veg;        /* SimpleNbox::run first call: simpleNbox-runtime.cpp:209-213 */
+  mb.S[SI_EOS_VEGC * HX_TILE] = mb.veg;        /* SimpleNbox::run first call: simpleNbox-runtime.cpp:209-213 */
   if (mb.status == 0) {
     /* chem_equilibrate both surface boxes at SST = 0 and the post-spin-up CO2 */
     const double CO2 = mb.atmos * HX_PGC_TO_PPMVCO2;
@@ -370,14 +385,14 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
     b.k = chem_constants(C, 0.0 + HX_MEAN_TOS_TEMP + HX_DT_HL, C.As_HL);
     b.carbon = mb.bHL; b.volume = C.vol_HL; b.As = C.As_HL; b.target = 1.000;
     chem_equilibrate(b, w);
-    mb.alkHL = b.alk; mb.hHL = b.h;
+    mb.S[SI_ALK_HL * HX_TILE] = b.alk; mb.S[SI_H_HL * HX_TILE] = b.h;
     b.k = chem_constants(C, 0.0 + HX_MEAN_TOS_TEMP + HX_DT_LL, C.As_LL);
     b.carbon = mb.bLL; b.volume = C.vol_LL; b.As = C.As_LL; b.target = -1.000;
     chem_equilibrate(b, w);
-    mb.alkLL = b.alk; mb.hLL = b.h;
+    mb.S[SI_ALK_LL * HX_TILE] = b.alk; mb.S[SI_H_LL * HX_TILE] = b.h;
     if (!b.ok) mb.status = HX_MEMBER_NOROOT;
   }
-  store_member(d, m, mb);
+  store_member(BS, mb);
   d.spinup_steps[m] = steps;
   if (mb.status) {
     d.status[m] = mb.status;
@@ -389,9 +404,13 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
 /* the yearly coupled step, rows r0+1 .. r1 (row = year - start_year) */
 __global__ void __launch_bounds__(HX_BLOCK, HX_RUN_MIN_CTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
-  __shared__ __align__(128) double slab[2][(HX_SLAB_YEARS + 1) * SC_STRIDE];
-  __shared__ __align__(16) double row0[SC_STRIDE];
-  __shared__ double chemk[10][HX_BLOCK]; /* K1, K2, Kb, Kw, Kh of the HL and LL boxes */
+  /* dynamic shared memory (> 48 KB): scenario slabs | row 0 | chemistry constants | RK stages */
+  extern __shared__ __align__(128) unsigned char hx_smem[];
+  double (*slab)[(HX_SLAB_YEARS + 1) * SC_STRIDE] =
+      reinterpret_cast<double (*)[(HX_SLAB_YEARS + 1) * SC_STRIDE]>(hx_smem);
+  double *row0 = reinterpret_cast<double *>(hx_smem + HX_SMEM_ROW0);
+  double (*chemk)[HX_BLOCK] = reinterpret_cast<double (*)[HX_BLOCK]>(hx_smem + HX_SMEM_CHEMK);
+  double (*rk)[HX_BLOCK] = reinterpret_cast<double (*)[HX_BLOCK]>(hx_smem + HX_SMEM_RK);
   __shared__ __align__(8) uint64_t bars[2];
 
   const int tid = threadIdx.x;
@@ -426,13 +445,15 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
   Member mb;
   Work w = {0, 0, 0, 0, 0, 0};
   unsigned years_done = 0;
-  const LandPar p = load_landpar(d, lane_ok ? m : 0);
+  const Bases BS = make_bases(d, C, m < d.Mpad ? m : 0);
+  const LandPar p = load_landpar(BS);
   ChemRef ck;
   ck.base = &chemk[0][0]; ck.stride = HX_BLOCK; ck.tid = tid;
-  if (lane_ok) load_member(d, m, mb);
+  if (lane_ok) load_member(BS, mb);
   else mb.status = -1;
   const bool cold = (C.flags & HX_FLAG_COLD_NEWTON) != 0;
-  const size_t Mp = d.Mpad;
+  const size_t Mp = d.Mpad;          /* member stride of the output block */
+  const size_t Hs = HX_BLOCK;        /* row stride of the tiled history arrays */
 
   for (int s = 0; s < nslab; ++s) {
     if (tid == 0 && s + 1 < nslab) issue(s + 1); /* buffer (s+1)&1 was released by the sync below */
@@ -459,7 +480,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
             toh = a + b + c + dd;
           }
           const double tau_oh = PAR(PI_TOH0) * exp(-toh);
-          const double rh_ch4_tg = mb.rh_ch4 * (1000.0 * 16.04 / 12.01);
+          const double rh_ch4_tg = mb.S[SI_RH_CH4 * HX_TILE] * (1000.0 * 16.04 / 12.01);
           const double emisTocon = (sc[SC_CH4_E] + rh_ch4_tg + sc[SC_CH4N]) / PAR(PI_UC_CH4);
           const double soil_sink = previous_ch4 / PAR(PI_TSOIL);
           const double strat_sink = previous_ch4 / PAR(PI_TSTRAT);
@@ -469,7 +490,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         }
 
         /* --- OceanComponent::run: ocean_component.cpp:356-407 --- */
-        mb.flux_sum = 0.0;
+        mb.S[SI_X_FLUXSUM * HX_TILE] = 0.0;
         mb.timesteps = 0;
         {
           const double sst = STATE(SI_SST);
@@ -477,11 +498,15 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           ChemK k = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_HL, C.As_HL);
           ck.store(0, k);
           mb.gHL = k.G;
-          mb.pco2HL = csys_box(C, k, mb.bHL, mb.alkHL, C.vol_HL, mb.hHL, cold, ok, w);
+          double hq = STATE(SI_H_HL);
+          mb.pco2HL = csys_box(C, k, mb.bHL, STATE(SI_ALK_HL), C.vol_HL, hq, cold, ok, w);
+          STATE(SI_H_HL) = hq;
           k = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_LL, C.As_LL);
           ck.store(1, k);
           mb.gLL = k.G;
-          mb.pco2LL = csys_box(C, k, mb.bLL, mb.alkLL, C.vol_LL, mb.hLL, cold, ok, w);
+          hq = STATE(SI_H_LL);
+          mb.pco2LL = csys_box(C, k, mb.bLL, STATE(SI_ALK_LL), C.vol_LL, hq, cold, ok, w);
+          STATE(SI_H_LL) = hq;
           if (!ok) mb.status = HX_MEMBER_NOROOT;
         }
 
@@ -489,10 +514,10 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         {
           const double tland = STATE(SI_TLAND);
           const double wf = LP_WF(p);
-          d.tland_hist[(size_t)r * Mp + m] = tland; /* Tland_record[y] = land tas of year y-1 */
+          BS.tland[(size_t)r * Hs] = tland; /* Tland_record[y] = land tas of year y-1 */
           mb.luc_e = scm1[SC_LUC_E]; mb.luc_u = scm1[SC_LUC_U];
-          mb.ffi = scm1[SC_FFI]; mb.daccs = scm1[SC_DACCS];
-          mb.neg |= (mb.luc_e < 0.0) | (mb.luc_u < 0.0) | (mb.ffi < 0.0) | (mb.daccs < 0.0);
+          mb.S[SI_X_FFI * HX_TILE] = scm1[SC_FFI]; mb.S[SI_X_DACCS * HX_TILE] = scm1[SC_DACCS];
+          mb.neg |= (mb.luc_e < 0.0) | (mb.luc_u < 0.0) | (mb.S[SI_X_FFI * HX_TILE] < 0.0) | (mb.S[SI_X_DACCS * HX_TILE] < 0.0);
           /* Tland_rm: for (i = t-200; i < t; i++) Tland_rm += Tland_record.get(i) * wf; /= 200
            * (:1041-1050).  Keys below the first record (start+1) extrapolate flat to it and
            * that record is exactly 0, so the window is sum_{k = max(1, r-201)}^{r-2} hist[k] wf.
@@ -500,11 +525,11 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
            * leaves per year instead of re-reading 200 history rows. */
           double window = 0.0;
           if (r >= 2) {
-            const double *th = d.tland_hist + m;
+            const double *th = BS.tland;
             double wsum = STATE(SI_TLAND_WSUM), wcomp = STATE(SI_TLAND_WCOMP);
             double add = 0.0, sub = 0.0;
-            if (r - 2 >= 1) add = th[(size_t)(r - 2) * Mp] * wf;
-            if (r - 202 >= 1) sub = -(th[(size_t)(r - 202) * Mp] * wf);
+            if (r - 2 >= 1) add = th[(size_t)(r - 2) * Hs] * wf;
+            if (r - 202 >= 1) sub = -(th[(size_t)(r - 202) * Hs] * wf);
             double t1 = wsum + add;
             wcomp += (fabs(wsum) >= fabs(add)) ? ((wsum - t1) + add) : ((add - t1) + wsum);
             wsum = t1;
@@ -518,7 +543,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         }
 
         /* --- CarbonCycleSolver::run --- */
-        solver_year<false>(mb, C, p, ck, (double)(y - 1), (double)y, cold, w);
+        solver_year<false>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
         if (mb.status) {
           d.status[m] = mb.status;
           d.fail_year[m] = y;
@@ -528,8 +553,8 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         {
           double npp, rh_fda, rh_fsa, rh_co2, rh_ch4v;
           land_fluxes<false>(mb, p, npp, rh_fda, rh_fsa, rh_co2, rh_ch4v);
-          mb.rh_ch4 = rh_ch4v;
-          mb.tempferts_last = mb.tfs;
+          mb.S[SI_RH_CH4 * HX_TILE] = rh_ch4v;
+          mb.S[SI_TEMPFERTS * HX_TILE] = mb.S[SI_X_TFS * HX_TILE];
         }
         const double CO2_conc = mb.atmos * HX_PGC_TO_PPMVCO2;
         mb.neg |= (CO2_conc < 0.0);
@@ -590,16 +615,16 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           {
             /* oldest first, like the reference; 8 history rows are fetched per trip so the
              * loads of a trip are all in flight together */
-            const double *ps = d.sst_hist + m;                   /* sst[i], i ascending */
-            const double *pk = d.ker + m + (size_t)r * Mp;       /* K(r - i), descending */
-            double kj1 = pk[Mp];                                 /* K(r + 1) */
+            const double *ps = BS.sst;                           /* sst[i], i ascending */
+            const double *pk = BS.ker + (size_t)r * Hs;           /* K(r - i), descending */
+            double kj1 = pk[Hs];                                 /* K(r + 1) */
             int i = 0;
             for (; i + 8 <= r; i += 8) {
               double sv[8], kv[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                sv[u] = ps[(size_t)u * Mp];
-                kv[u] = *(pk - (size_t)u * Mp);
+                sv[u] = ps[u * Hs];
+                kv[u] = *(pk - u * Hs);
               }
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
@@ -607,16 +632,16 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
                 hint = hint + sv[u] * kv[u];
                 kj1 = kv[u];
               }
-              ps += 8 * Mp;
-              pk -= 8 * Mp;
+              ps += 8 * Hs;
+              pk -= 8 * Hs;
             }
             for (; i < r; ++i) {
               const double sv = *ps, kj = *pk;
               DPAST2 = DPAST2 + sv * kj1;
               hint = hint + sv * kj;
               kj1 = kj;
-              ps += Mp;
-              pk -= Mp;
+              ps += Hs;
+              pk -= Hs;
             }
           }
           DPAST2 = DPAST2 * fso * DER(DI_SQDT_TAUDIF);
@@ -638,7 +663,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           STATE(SI_TLAND) = TL;
           STATE(SI_SST) = TS;
           STATE(SI_RF_PREV) = rf_tot;
-          d.sst_hist[(size_t)r * Mp + m] = TS;
+          BS.sst[(size_t)r * Hs] = TS;
         }
         ++years_done;
 
@@ -655,7 +680,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_RF_CO2, rf_co2);
         EMIT(OUT_HEATFLUX, heatflux);
         EMIT(OUT_OCEAN_C, mb.bDO + mb.bIO + mb.bLL + mb.bHL);
-        if (d.out_slot[OUT_HL_PH] >= 0) EMIT(OUT_HL_PH, -log10(mb.hHL));
+        if (d.out_slot[OUT_HL_PH] >= 0) EMIT(OUT_HL_PH, -log10(mb.S[SI_H_HL * HX_TILE]));
         EMIT(OUT_ATMOS_C, mb.atmos);
         EMIT(OUT_SST, sst_new);
         EMIT(OUT_PERMAFROST_C, mb.perm);
@@ -668,9 +693,9 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_SOIL_C, mb.soil);
         EMIT(OUT_THAWEDP_C, mb.thawed);
         EMIT(OUT_EARTH_C, mb.earth);
-        EMIT(OUT_NBP, mb.nbp);
-        EMIT(OUT_OCEAN_UPTAKE, mb.flux_sum);
-        if (d.out_slot[OUT_LL_PH] >= 0) EMIT(OUT_LL_PH, -log10(mb.hLL));
+        EMIT(OUT_NBP, mb.S[SI_X_NBP * HX_TILE]);
+        EMIT(OUT_OCEAN_UPTAKE, mb.S[SI_X_FLUXSUM * HX_TILE]);
+        if (d.out_slot[OUT_LL_PH] >= 0) EMIT(OUT_LL_PH, -log10(mb.S[SI_H_LL * HX_TILE]));
         EMIT(OUT_PCO2_HL, mb.pco2HL);
         EMIT(OUT_PCO2_LL, mb.pco2LL);
         EMIT(OUT_CARBON_HL, mb.bHL);
@@ -679,7 +704,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_CARBON_DO, mb.bDO);
         EMIT(OUT_RF_CH4, rf_ch4);
         EMIT(OUT_RF_N2O, rf_n2o);
-        EMIT(OUT_RH_CH4, mb.rh_ch4);
+        EMIT(OUT_RH_CH4, mb.S[SI_RH_CH4 * HX_TILE]);
         EMIT(OUT_TIMESTEPS, (double)mb.timesteps);
 #undef EMIT
       }
@@ -688,7 +713,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
   }
 
   if (lane_ok) {
-    if (mb.status == 0) store_member(d, m, mb);
+    if (mb.status == 0) store_member(BS, mb);
     flush_work(d, w, years_done, mb.status != 0 ? 1u : 0u);
   }
 }
@@ -721,7 +746,14 @@ cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cuda
   return cudaGetLastError();
 }
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
-  hx_run_kernel<<<d.Mpad / HX_BLOCK, HX_BLOCK, 0, st>>>(d, C, r0, r1);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         HX_SMEM_RUN_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  hx_run_kernel<<<d.Mpad / HX_BLOCK, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_nan_fill(const HxDev &d, const HxConst &C, int nsel, int yr0, int yr1,

@@ -1,9 +1,14 @@
 /* hx_layout.h -- data layout shared by the host engine and the device kernels.
  *
- * Everything per-member is structure-of-arrays with the member index fastest:
- *   params  P[PI_COUNT][Mpad]      state  S[SI_COUNT][Mpad]      derived D[DI_COUNT][Mpad]
- *   histories  sst_hist / tland_hist / ker [nrow][Mpad]          outputs O[nsel][nyears][Mpad]
- * so a warp touches 32 consecutive doubles (256 B) per access.  Scenario tables are
+ * Per-member data is structure-of-arrays, tiled by CTA ("CTA-tiled SoA"): the HX_TILE = 128
+ * members of one CTA own a contiguous block
+ *   params     P[tile][PI_COUNT][128]     state  S[tile][SI_COUNT][128]   derived D[tile][DI_COUNT][128]
+ *   histories  sst_hist / tland_hist [tile][nrow][128],  ker [tile][nrow+1][128]
+ * so (a) a warp touches 32 consecutive doubles (256 B) per access, (b) every field of a thread
+ * sits at a COMPILE-TIME offset (field * 1 KiB) from one base pointer -- no per-field address
+ * registers or 64-bit index arithmetic in the kernels -- and (c) consecutive history rows of a
+ * tile are contiguous (1 KiB per row) for bulk copies.  Outputs stay O[nsel][nyears][Mpad]
+ * (what fetches and the NCCL all-gather consume).  Scenario tables are
  * [scenario][row][SC_STRIDE] doubles, row = year - start_year, staged to shared memory in
  * slabs of consecutive rows with one bulk copy each.
  */
@@ -13,6 +18,11 @@
 #include <stdint.h>
 
 #define HX_NHALO 26
+#define HX_TILE 128 /* members per tile = threads per CTA (HX_BLOCK) */
+
+/* element index of (field, member) in a tiled array with `nfields` rows per tile */
+#define HX_TILED(field, m, nfields) \
+  ((((size_t)(m) / HX_TILE) * (size_t)(nfields) + (size_t)(field)) * HX_TILE + ((size_t)(m) % HX_TILE))
 
 /* ---- raw scenario series (what callers hand in), reference input names ---- */
 enum {
@@ -57,6 +67,9 @@ enum {
   SI_CH4, SI_TLAND, SI_SST, SI_HEAT_MIXED, SI_HEAT_INTERIOR, SI_RF_PREV,
   SI_BASE_TOT, SI_BASE_CO2, SI_BASE_CH4, SI_BASE_N2O,
   SI_TLAND_WSUM, SI_TLAND_WCOMP, /* 200-year land-temperature window: compensated running sum */
+  /* per-year scratch (slowparameval results, emissions, annual sums) parked between phases */
+  SI_X_CO2FERT, SI_X_TFD, SI_X_TFS, SI_X_FNEWTHAW, SI_X_NPPLUC, SI_X_FFI, SI_X_DACCS, SI_X_NBP,
+  SI_X_FLUXSUM,
   SI_COUNT
 };
 
