@@ -259,7 +259,7 @@ def main():
         for v in ("CO2_concentration", "global_tas"):
             ptr, stride, ny = ens.output_device(v)
             views.append(torch.as_tensor(CudaArrayView(ptr, (ny, stride)), device="cuda"))
-        gather_buf = [torch.empty((world,) + tuple(t.shape), dtype=torch.float64, device="cuda")
+        gather_buf = [torch.empty(world * t.numel(), dtype=torch.float64, device="cuda")
                       for t in views]
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")  # 256 MB > L2
 
@@ -269,7 +269,7 @@ def main():
         if world > 1 and do_gather:
             # the job's single collective: every rank ends up with all members' trajectories
             for t, g in zip(views, gather_buf):
-                dist.all_gather_into_tensor(g, t)
+                dist.all_gather_into_tensor(g, t.reshape(-1))
 
     def timed(e, fn, steps, warmup, flush_l2):
         for _ in range(warmup):

@@ -613,27 +613,27 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
            *   interior = sum_{i<t}  sst[i] K(t-i)     (:534-537) */
           double DPAST2 = 0.0, hint = 0.0;
           {
-            /* oldest first, like the reference; 8 history rows are fetched per trip so the
+            /* oldest first, like the reference; HX_CONV_UNROLL history rows are fetched per trip so the
              * loads of a trip are all in flight together */
             const double *ps = BS.sst;                           /* sst[i], i ascending */
             const double *pk = BS.ker + (size_t)r * Hs;           /* K(r - i), descending */
             double kj1 = pk[Hs];                                 /* K(r + 1) */
             int i = 0;
-            for (; i + 8 <= r; i += 8) {
-              double sv[8], kv[8];
+            for (; i + HX_CONV_UNROLL <= r; i += HX_CONV_UNROLL) {
+              double sv[HX_CONV_UNROLL], kv[HX_CONV_UNROLL];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                sv[u] = ps[u * Hs];
-                kv[u] = *(pk - u * Hs);
+              for (int u = 0; u < HX_CONV_UNROLL; ++u) {
+                sv[u] = __ldcs(ps + u * Hs);
+                kv[u] = __ldcs(pk - u * Hs);
               }
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
+              for (int u = 0; u < HX_CONV_UNROLL; ++u) {
                 DPAST2 = DPAST2 + sv[u] * kj1;
                 hint = hint + sv[u] * kv[u];
                 kj1 = kv[u];
               }
-              ps += 8 * Hs;
-              pk -= 8 * Hs;
+              ps += HX_CONV_UNROLL * Hs;
+              pk -= HX_CONV_UNROLL * Hs;
             }
             for (; i < r; ++i) {
               const double sv = *ps, kj = *pk;

@@ -9,6 +9,9 @@
 
 #define HX_BLOCK 128      /* threads (= members) per CTA; one scenario per CTA */
 #define HX_SLAB_YEARS 16  /* scenario rows staged per bulk copy */
+#ifndef HX_CONV_UNROLL
+#define HX_CONV_UNROLL 32 /* history rows (x2 arrays) in flight per thread in the DOECLIM convolution */
+#endif
 #ifndef HX_RUN_MIN_CTAS
 #define HX_RUN_MIN_CTAS 2 /* resident CTAs per SM the run kernel is register-limited to */
 #endif
