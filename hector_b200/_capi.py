@@ -11,7 +11,7 @@ COUNTER_NAMES = ["rhs_evals", "rk_steps", "rk_rejected", "stashes", "newton_iter
 HX_FLAG_COLD_NEWTON = 1
 HX_FLAG_NO_SPINUP = 2
 
-EXPORTS = ["hx_create", "hx_destroy", "hx_last_error", "hx_set_stream", "hx_set_scenario_series",
+EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "hx_destroy", "hx_last_error", "hx_set_stream", "hx_set_scenario_series",
            "hx_set_scenario_table", "hx_set_member_scenario", "hx_set_param_scalar",
            "hx_set_param", "hx_set_param_device", "hx_get_param", "hx_select_outputs",
            "hx_prepare", "hx_run", "hx_reset", "hx_synchronize", "hx_fetch", "hx_output_device",
@@ -50,6 +50,10 @@ def lib():
     L.hx_last_error.restype = C.c_char_p
     L.hx_last_error.argtypes = [vp]
     L.hx_create.argtypes = [C.POINTER(HxConfig), C.POINTER(vp)]
+    L.hx_create_from_ini.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_uint32, C.POINTER(vp)]
+    L.hx_ini_read.argtypes = [C.c_char_p, ip, ip, dp, C.c_int32]
+    L.hx_ini_scalar.argtypes = [C.c_char_p, C.c_char_p, dp]
     L.hx_destroy.argtypes = [vp]
     L.hx_set_stream.argtypes = [vp, vp]
     L.hx_set_scenario_series.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, dp]

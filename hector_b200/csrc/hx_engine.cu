@@ -284,6 +284,8 @@ const char *hx_version(void) { return "hector_b200 0.1 (sm_100a)"; }
 
 const char *hx_last_error(hx_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+void hx_set_create_error(const char *msg) { g_create_error = msg ? msg : ""; }
+
 int hx_create(const hx_config *cfg, hx_handle *out) {
   if (!cfg || !out) {
     g_create_error = "hx_create: null argument";

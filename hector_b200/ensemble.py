@@ -96,6 +96,37 @@ class Ensemble:
         self._chk(self.L.hx_select_outputs(self.h, len(self.outputs), arr))
         self.prepared = False
 
+    @classmethod
+    def from_ini(cls, ini_paths, n_members, member_scenario=None, device=0,
+                 outputs=("CO2_concentration", "global_tas"), cold_newton=False, stream=None):
+        """newcore(inifile): scenario series and scalar parameters come from Hector ini files
+        (one scenario per file), read by the library's own ini/csv reader."""
+        if isinstance(ini_paths, str):
+            ini_paths = [ini_paths]
+        self = cls.__new__(cls)
+        self.L = _capi.lib()
+        self.n_members = int(n_members)
+        arr = (C.c_char_p * len(ini_paths))(*[p.encode() for p in ini_paths])
+        self.h = C.c_void_p()
+        flags = _capi.HX_FLAG_COLD_NEWTON if cold_newton else 0
+        rc = self.L.hx_create_from_ini(arr, len(ini_paths), self.n_members, int(device), flags,
+                                       C.byref(self.h))
+        if rc != 0:
+            raise HxError("hx_create_from_ini: %s (code %d)" % (
+                self.L.hx_last_error(None).decode(), rc))
+        if stream is not None:
+            self._chk(self.L.hx_set_stream(self.h, C.c_void_p(int(stream))))
+        if member_scenario is not None:
+            ms = np.ascontiguousarray(member_scenario, dtype=np.int32)
+            self._chk(self.L.hx_set_member_scenario(
+                self.h, ms.ctypes.data_as(C.POINTER(C.c_int32)), len(ms)))
+        self.outputs = list(outputs)
+        oarr = (C.c_char_p * len(self.outputs))(*[s.encode() for s in self.outputs])
+        self._chk(self.L.hx_select_outputs(self.h, len(self.outputs), oarr))
+        self.prepared = False
+        self.start_year = self.end_year = None
+        return self
+
     # -- plumbing --
     def _chk(self, rc):
         if rc != 0:

@@ -77,6 +77,18 @@ typedef struct {
 #define HX_CNT_MEMBER_YEARS 7
 
 int hx_create(const hx_config *cfg, hx_handle *out);
+/* newcore(inifile): create an engine from n_inis Hector ini files (one scenario each; csv:
+ * tables resolved like the reference does, src/ini_to_core_reader.cpp:134-167).  Scalar
+ * parameters come from the first file, start/end dates must agree.  Replaces
+ * INIToCoreReader::parse + Core::setData (src/ini_to_core_reader.cpp:74-180). */
+int hx_create_from_ini(const char *const *ini_paths, int32_t n_inis, int32_t n_members,
+                       int32_t device, uint32_t flags, hx_handle *out);
+/* host-only access to the ini/csv reader (no GPU needed): run dates, the dense raw table
+ * [end-start+1][44] in the series order listed at hx_set_scenario_series, scalar values by
+ * engine parameter name ("S", "beta", "CF4.tau", ...) */
+int hx_ini_read(const char *ini_path, int32_t *start_year, int32_t *end_year, double *table,
+                int32_t table_rows);
+int hx_ini_scalar(const char *ini_path, const char *name, double *out);
 int hx_destroy(hx_handle h); /* idempotent on NULL */
 const char *hx_last_error(hx_handle h); /* h may be NULL: error of the last failed hx_create */
 

@@ -213,3 +213,52 @@ def test_error_behaviour():
     x = ens.fetch("CO2_concentration", [1800.0])      # engine still usable after errors
     assert x.shape == (2, 1) and x[0, 0] > 277
     ens.close()
+
+
+def test_engine_from_ini_equals_engine_from_tables():
+    """newcore(inifile) path: the library's own ini/csv reader feeds the same run"""
+    import os
+    import hector_b200 as hb
+    from tests.test_ini_reader_cpu import INPUT_DIRS
+    d = [x for x in INPUT_DIRS if os.path.exists(os.path.join(x, "hector_ssp245.ini"))]
+    if not d:
+        pytest.skip("reference input data not available")
+    a = hb.Ensemble.from_ini(os.path.join(d[0], "hector_ssp245.ini"), 4)
+    b = _engine(4, outputs=["CO2_concentration", "global_tas"])
+    S = np.array([2.0, 3.0, 4.0, 5.0])
+    for e in (a, b):
+        e.setvar("S", S)
+        e.run()
+    ya = a.fetchvars(_years())
+    yb = b.fetchvars(_years())
+    for v in ya:
+        assert np.array_equal(ya[v], yb[v]), v
+    a.close()
+    b.close()
+
+
+def test_extension_to_2500():
+    """BASELINE.json config 5 inputs (SSP5-8.5, series held at 2300 values to 2500), no tracking"""
+    from oracle import port
+    import hector_b200 as hb
+    raw = util.scenarios()["ssp585"]
+    ext = np.vstack([raw, np.repeat(raw[-1:], 200, axis=0)])
+    M = 33
+    X = util.lhs(M, seed=20241018)
+    ens = hb.Ensemble(M, ext, end_year=2500, outputs=["CO2_concentration", "global_tas",
+                                                     "ocean_timesteps"])
+    ens.setvar("S", X[:, 0])
+    ens.setvar("q10_rh", X[:, 1])
+    ens.setvar("aero_scalar", 0.5 + X[:, 2])
+    ens.run()
+    yrs = np.arange(1746, 2501, dtype=np.float64)
+    got = ens.fetchvars(yrs)
+    st, _ = ens.status()
+    for i in (0, 16, 32):
+        p = port.default_params(end_year=2500, S=X[i, 0], q10_rh=X[i, 1], aero_scalar=0.5 + X[i, 2])
+        ost, _, out, _, _ = port.run_member(ext, p)
+        assert ost == 0 and st[i] == 0
+        assert np.array_equal(got["ocean_timesteps"][i], out[-1])
+        assert util.parity_err(got["CO2_concentration"][i], out[0], "CO2_concentration") < TOL
+        assert util.parity_err(got["global_tas"][i], out[1], "global_tas") < TOL
+    ens.close()

@@ -1,0 +1,70 @@
+"""The library's own ini/csv reader (hx_ini.cpp) against the fixture tables, which were produced
+from the same reference input files by an independent Python reader (tests/golden/make_golden.py).
+Needs the reference input data: /root/reference (build container) or oracle/_ref/input (travels
+to the GPU box)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from hector_b200 import _capi
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INPUT_DIRS = ["/root/reference/inst/input", os.path.join(ROOT, "oracle", "_ref", "input")]
+
+
+def input_dir():
+    for d in INPUT_DIRS:
+        if os.path.exists(os.path.join(d, "hector_ssp245.ini")):
+            return d
+    pytest.skip("reference input data not available")
+
+
+def need_lib():
+    if not os.path.exists(_capi.lib_path()):
+        pytest.skip("libhector_b200.so not built")
+    return _capi.lib()
+
+
+@pytest.mark.parametrize("scn", ["ssp119", "ssp126", "ssp245", "ssp370", "ssp434", "ssp460",
+                                 "ssp534-over", "ssp585"])
+def test_tables_match_fixtures(scn):
+    L = need_lib()
+    ini = os.path.join(input_dir(), "hector_%s.ini" % scn).encode()
+    s, e = C.c_int32(), C.c_int32()
+    assert L.hx_ini_read(ini, C.byref(s), C.byref(e), None, 0) == 0, L.hx_last_error(None)
+    assert (s.value, e.value) == (1745, 2300)
+    tab = np.empty((556, 44))
+    assert L.hx_ini_read(ini, None, None, tab.ctypes.data_as(C.POINTER(C.c_double)), 556) == 0
+    assert np.array_equal(tab, util.scenarios()[scn])
+
+
+def test_scalars_match_ini_defaults():
+    L = need_lib()
+    ini = os.path.join(input_dir(), "hector_ssp245.ini").encode()
+    expect = {"S": 3.0, "diff": 1.042, "beta": 0.65, "q10_rh": 1.2, "C0": 277.15, "baseyear": 1750,
+              "rho_so2": -7.469841e-06, "delta_ch4": -.14, "CF4.tau": 50000.0, "CH3Br.H0": 5.8,
+              "CFC11.delta": 0.13, "HFC125.rho": 0.000234, "TN2O0": 132, "dt": 0.25,
+              "max_spinup": 2000, "preind_interdeep_c": 37100}
+    for k, v in expect.items():
+        out = C.c_double()
+        assert L.hx_ini_scalar(ini, k.encode(), C.byref(out)) == 0, k
+        assert out.value == v, (k, out.value)
+
+
+def test_unsupported_inputs_are_reported(tmp_path):
+    L = need_lib()
+    src = open(os.path.join(input_dir(), "hector_ssp245.ini")).read()
+    d = input_dir()
+    bad = tmp_path / "constrained.ini"
+    bad.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
+        "[temperature]", "[temperature]\ntas_constrain=csv:%s/tables/tas_historical.csv" % d))
+    assert L.hx_ini_read(str(bad).encode(), None, None, None, 0) == -4
+    assert b"constrain" in L.hx_last_error(None)
+    bad2 = tmp_path / "unknown.ini"
+    bad2.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
+        "[temperature]", "[temperature]\nnot_a_variable=1"))
+    assert L.hx_ini_read(str(bad2).encode(), None, None, None, 0) == -1
+    assert b"Unknown variable" in L.hx_last_error(None)

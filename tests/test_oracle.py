@@ -114,3 +114,15 @@ def test_reference_lib_if_present():
     for k, v in enumerate(["CO2_concentration", "global_tas", "HL_pH"]):
         assert np.array_equal(out[port.OUT_NAMES.index(v)], o[k]), v
     assert np.array_equal(out[-1], o[-1])
+
+
+def test_extension_to_2500_kat():
+    """SURVEY.md appendix C (unmodified reference): SSP5-8.5 with every series held at its 2300
+    value to 2500 (BASELINE.json config 5 inputs, without tracking)."""
+    raw = util.scenarios()["ssp585"]
+    ext = np.vstack([raw, np.repeat(raw[-1:], 200, axis=0)])
+    st, fy, out, cnt, sp = port.run_member(ext, port.default_params(end_year=2500))
+    assert st == 0
+    assert abs(out[0][2300 - 1746] - 1272.74969152107) < 1e-9
+    assert abs(out[0][-1] - 1102.05842133113) < 1e-9
+    assert abs(out[1][-1] - 6.60192887012203) < 1e-11
