@@ -228,6 +228,13 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   DER(DI_SQDT_TAUDIF) = sqdt;
   DER(DI_HF_INT) = cas * fso / sqrt(taudif * dt);
   DER(DI_LNQ10) = log(PAR(PI_Q10));
+  /* QL = QO = forcing (temperature_component.cpp:462-463), so DelQL = DelQO = dQ and
+   * QC1 = dQ (1/cal (1/taucfl + 1/taukls) - bsi/cas/taukls) dt^2/12, QC2 likewise */
+  DER(DI_QC1) = (1.0 / cal * (1.0 / taucfl + 1.0 / taukls) - bsi * 1.0 / cas / taukls) * (dt * dt) / 12.0;
+  DER(DI_QC2) = (1.0 / cas * (1.0 / taucfs + bsi / tauksl) - 1.0 / cal / tauksl) * (dt * dt) / 12.0;
+  DER(DI_INV_UC_CH4) = 1.0 / PAR(PI_UC_CH4);
+  DER(DI_INV_TSOIL) = 1.0 / PAR(PI_TSOIL);
+  DER(DI_INV_TSTRAT) = 1.0 / PAR(PI_TSTRAT);
 
   /* initial pools: ocean_component.cpp:224-260, simpleNbox.cpp:45-81, simpleNbox-runtime.cpp:172 */
   const double LL_vol_frac = C.vol_LL / (C.vol_LL + C.vol_HL);
@@ -481,9 +488,9 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           }
           const double tau_oh = PAR(PI_TOH0) * exp(-toh);
           const double rh_ch4_tg = mb.S[SI_RH_CH4 * HX_TILE] * (1000.0 * 16.04 / 12.01);
-          const double emisTocon = (sc[SC_CH4_E] + rh_ch4_tg + sc[SC_CH4N]) / PAR(PI_UC_CH4);
-          const double soil_sink = previous_ch4 / PAR(PI_TSOIL);
-          const double strat_sink = previous_ch4 / PAR(PI_TSTRAT);
+          const double emisTocon = (sc[SC_CH4_E] + rh_ch4_tg + sc[SC_CH4N]) * DER(DI_INV_UC_CH4);
+          const double soil_sink = previous_ch4 * DER(DI_INV_TSOIL);
+          const double strat_sink = previous_ch4 * DER(DI_INV_TSTRAT);
           const double oh_sink = previous_ch4 / tau_oh;
           const double dCH4 = emisTocon - soil_sink - strat_sink - oh_sink;
           STATE(SI_CH4) = previous_ch4 + dCH4;
@@ -494,20 +501,15 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         mb.timesteps = 0;
         {
           const double sst = STATE(SI_SST);
-          bool ok = true;
-          ChemK k = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_HL, C.As_HL);
-          ck.store(0, k);
-          mb.gHL = k.G;
-          double hq = STATE(SI_H_HL);
-          mb.pco2HL = csys_box(C, k, mb.bHL, STATE(SI_ALK_HL), C.vol_HL, hq, cold, ok, w);
-          STATE(SI_H_HL) = hq;
-          k = chem_constants(C, sst + HX_MEAN_TOS_TEMP + HX_DT_LL, C.As_LL);
-          ck.store(1, k);
-          mb.gLL = k.G;
-          hq = STATE(SI_H_LL);
-          mb.pco2LL = csys_box(C, k, mb.bLL, STATE(SI_ALK_LL), C.vol_LL, hq, cold, ok, w);
-          STATE(SI_H_LL) = hq;
-          if (!ok) mb.status = HX_MEMBER_NOROOT;
+          const ChemG g = chem_constants2(C, sst, ck.base + ck.tid, ck.stride);
+          mb.gHL = g.gHL; mb.gLL = g.gLL;
+          const Csys2Out o = csys_solve2(ck.base + ck.tid, ck.stride, C.bor, mb.bHL, mb.bLL,
+                                         STATE(SI_ALK_HL), STATE(SI_ALK_LL), C.vol_HL, C.vol_LL,
+                                         STATE(SI_H_HL), STATE(SI_H_LL), cold);
+          mb.pco2HL = o.pco2[0]; mb.pco2LL = o.pco2[1];
+          STATE(SI_H_HL) = o.h[0]; STATE(SI_H_LL) = o.h[1];
+          w.newton_it += o.iters; w.newton_calls += 2;
+          if (!o.ok) mb.status = HX_MEMBER_NOROOT;
         }
 
         /* --- SimpleNbox::run + slowparameval: simpleNbox-runtime.cpp:206-227, 945-1072 --- */
@@ -597,13 +599,9 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           const double dt = 1.0, bsi = DC_BSI, cal = DC_CAL, cas = DC_CAS, flnd = DC_FLND,
                        fso = DC_FSO;
           const double tland = STATE(SI_TLAND), sst = STATE(SI_SST), rf_prev = STATE(SI_RF_PREV);
-          const double taucfl = DER(DI_TAUCFL), taukls = DER(DI_TAUKLS), taucfs = DER(DI_TAUCFS),
-                       tauksl = DER(DI_TAUKSL);
-          const double DelQL = rf_tot - rf_prev, DelQO = rf_tot - rf_prev;
-          double QC1 = (DelQL / cal * (1.0 / taucfl + 1.0 / taukls) - bsi * DelQO / cas / taukls);
-          double QC2 = (DelQO / cas * (1.0 / taucfs + bsi / tauksl) - DelQL / cal / tauksl);
-          QC1 = QC1 * (dt * dt) / 12.0;
-          QC2 = QC2 * (dt * dt) / 12.0;
+          const double dQ = rf_tot - rf_prev;
+          const double QC1 = dQ * DER(DI_QC1);
+          const double QC2 = dQ * DER(DI_QC2);
           double DQ1 = 0.5 * dt / cal * (rf_tot + rf_prev);
           double DQ2 = 0.5 * dt / cas * (rf_tot + rf_prev);
           DQ1 = DQ1 + QC1;

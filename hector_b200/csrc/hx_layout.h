@@ -81,6 +81,8 @@ enum {
   DI_SQDT_TAUDIF, /* pow(dt/taudif, 0.5)            temperature_component.cpp:491 */
   DI_HF_INT,      /* cas*fso/pow(taudif*dt, 0.5)    temperature_component.cpp:539 */
   DI_LNQ10,       /* log(q10_rh): pow(q10, x) is evaluated as exp(x * lnq10) */
+  DI_QC1, DI_QC2, /* forcing-increment correction per unit dQ (temperature_component.cpp:471-475) */
+  DI_INV_UC_CH4, DI_INV_TSOIL, DI_INV_TSTRAT, /* reciprocals of the CH4 constants */
   DI_COUNT
 };
 
