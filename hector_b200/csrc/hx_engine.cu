@@ -118,6 +118,7 @@ struct Engine {
           *d_status_post = nullptr,
           *d_fail_year = nullptr, *d_spinup_steps = nullptr, *d_yidx = nullptr;
   unsigned long long *d_counters = nullptr;
+  unsigned *d_sched = nullptr;
   size_t stage_bytes = 0, yidx_cap = 0;
   double *h_pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -207,12 +208,13 @@ struct Engine {
   void free_device() {
     void *ptrs[] = {d_P, d_S, d_S_snap, d_D, d_ker, d_sst, d_tland, d_out, d_scen, d_stage,
                     d_block_scen, d_status, d_status_snap, d_status_post, d_fail_year, d_spinup_steps, d_yidx,
-                    d_counters, d_dev_of_api};
+                    d_counters, d_dev_of_api, d_sched};
     for (void *p : ptrs)
       if (p) cudaFree(p);
     d_P = d_S = d_S_snap = d_D = d_ker = d_sst = d_tland = d_out = d_scen = d_stage = nullptr;
     d_block_scen = d_status = d_status_snap = d_status_post = d_fail_year = d_spinup_steps = d_yidx = nullptr;
     d_counters = nullptr;
+    d_sched = nullptr;
     d_dev_of_api = nullptr;
     stage_bytes = 0;
     yidx_cap = 0;
@@ -611,6 +613,7 @@ int hx_prepare(hx_handle h) {
       cudaMalloc(&h->d_fail_year, Mp * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc(&h->d_spinup_steps, Mp * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc(&h->d_counters, HX_NCOUNTERS * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&h->d_sched, (block_scen.size() + 1) * sizeof(unsigned)) != cudaSuccess ||
       cudaMalloc(&h->d_dev_of_api, (size_t)M * sizeof(int32_t)) != cudaSuccess) {
     cudaError_t e = cudaGetLastError();
     h->free_device();
@@ -638,7 +641,7 @@ int hx_prepare(hx_handle h) {
   d.Mpad = Mpad; d.P = h->d_P; d.S = h->d_S; d.D = h->d_D; d.ker = h->d_ker;
   d.sst_hist = h->d_sst; d.tland_hist = h->d_tland; d.out = h->d_out; d.scen = h->d_scen;
   d.block_scen = h->d_block_scen; d.status = h->d_status; d.fail_year = h->d_fail_year;
-  d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters;
+  d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters; d.sched = h->d_sched;
   for (int i = 0; i < OUT_COUNT; ++i) d.out_slot[i] = -1;
   for (int s = 0; s < nsel; ++s) d.out_slot[h->out_sel[s]] = s;
 

@@ -20,7 +20,7 @@
 namespace hx {
 
 /* run-kernel dynamic shared memory map (bytes) */
-#define HX_SMEM_SLAB_BYTES (2 * (HX_SLAB_YEARS + 1) * SC_STRIDE * 8)
+#define HX_SMEM_SLAB_BYTES ((HX_SLAB_YEARS + 1) * SC_STRIDE * 8)
 #define HX_SMEM_ROW0 HX_SMEM_SLAB_BYTES
 #define HX_SMEM_CHEMK (HX_SMEM_ROW0 + SC_STRIDE * 8)
 #define HX_SMEM_RK (HX_SMEM_CHEMK + 10 * HX_BLOCK * 8)
@@ -418,56 +418,78 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
   double *row0 = reinterpret_cast<double *>(hx_smem + HX_SMEM_ROW0);
   double (*chemk)[HX_BLOCK] = reinterpret_cast<double (*)[HX_BLOCK]>(hx_smem + HX_SMEM_CHEMK);
   double (*rk)[HX_BLOCK] = reinterpret_cast<double (*)[HX_BLOCK]>(hx_smem + HX_SMEM_RK);
-  __shared__ __align__(8) uint64_t bars[2];
-
+  __shared__ __align__(8) uint64_t bars[1];
+  __shared__ unsigned s_ticket;
   const int tid = threadIdx.x;
-  const int m = blockIdx.x * HX_BLOCK + tid;
-  const int scen = d.block_scen[blockIdx.x];
-  const double *table = d.scen + (size_t)scen * C.nrow * SC_STRIDE;
-  const bool lane_ok = (m < d.Mpad) && (d.status[m] == 0);
   const int nyears_total = C.nrow - 1;
-
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_fence_init();
-  }
-  for (int i = tid; i < SC_STRIDE; i += HX_BLOCK) row0[i] = table[i];
-  __syncthreads();
-
-  /* slab s covers table rows base .. base+HX_SLAB_YEARS (one overlap row for the y-1 emissions),
-   * serving years base+1 .. base+HX_SLAB_YEARS */
-  const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
-  auto issue = [&](int s) {
-    const int base = r0 + s * HX_SLAB_YEARS;
-    int rows = HX_SLAB_YEARS + 1;
-    if (base + rows > C.nrow) rows = C.nrow - base;
-    const uint32_t bytes = (uint32_t)(rows * SC_STRIDE * sizeof(double));
-    fence_proxy_async();
-    mbar_arrive_expect_tx(&bars[s & 1], bytes);
-    bulk_g2s(slab[s & 1], table + (size_t)base * SC_STRIDE, bytes, &bars[s & 1]);
-  };
-  if (tid == 0 && nslab > 0) issue(0);
-
-  Member mb;
-  Work w = {0, 0, 0, 0, 0, 0};
-  unsigned years_done = 0;
-  const Bases BS = make_bases(d, C, m < d.Mpad ? m : 0);
-  const LandPar p = load_landpar(BS);
-  ChemRef ck;
-  ck.base = &chemk[0][0]; ck.stride = HX_BLOCK; ck.tid = tid;
-  if (lane_ok) load_member(BS, mb);
-  else mb.status = -1;
   const bool cold = (C.flags & HX_FLAG_COLD_NEWTON) != 0;
   const size_t Mp = d.Mpad;          /* member stride of the output block */
   const size_t Hs = HX_BLOCK;        /* row stride of the tiled history arrays */
+  ChemRef ck;
+  ck.base = &chemk[0][0]; ck.stride = HX_BLOCK; ck.tid = tid;
+  Work w = {0, 0, 0, 0, 0, 0};
+  unsigned years_done = 0, failed = 0;
 
-  for (int s = 0; s < nslab; ++s) {
-    if (tid == 0 && s + 1 < nslab) issue(s + 1); /* buffer (s+1)&1 was released by the sync below */
-    mbar_wait(&bars[s & 1], (uint32_t)((s >> 1) & 1));
-    const double *sl = slab[s & 1];
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  /* Persistent CTAs over a work queue of (tile, slab) items, slab-major: item t covers the
+   * HX_SLAB_YEARS years of slab t / ntiles for the 128 members of tile t % ntiles.  A tile's
+   * slabs are sequentially dependent (state in S), so an item waits until the tile's previous
+   * slab has been published; with slab-major tickets that predecessor was handed out ntiles
+   * tickets earlier.  All tiles therefore advance together and every SM stays full until the
+   * last slab -- a static one-CTA-per-tile grid needs ceil(tiles / resident CTAs) full rounds
+   * (2 rounds for 512 tiles on 296 resident CTAs; 1.73 here). */
+  const int ntiles = d.Mpad / HX_BLOCK;
+  const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
+  const unsigned total_items = (unsigned)ntiles * (unsigned)nslab;
+  unsigned *ticket = d.sched;
+  unsigned *progress = d.sched + 1; /* [ntiles]: slabs of this launch already published */
+  unsigned item_no = 0;             /* items this CTA has processed: mbarrier phase */
+
+  for (;;) {
+    if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned t = s_ticket;
+    if (t >= total_items) break;
+    const int tile = (int)(t % (unsigned)ntiles);
+    const int s = (int)(t / (unsigned)ntiles);
+    const int m = tile * HX_BLOCK + tid;
+    const double *table = d.scen + (size_t)d.block_scen[tile] * C.nrow * SC_STRIDE;
+    /* slab s covers table rows base .. base+HX_SLAB_YEARS (one overlap row for the y-1
+     * emissions), serving years base+1 .. base+HX_SLAB_YEARS */
     const int base = r0 + s * HX_SLAB_YEARS;
     const int rend = min(base + HX_SLAB_YEARS, r1);
+    if (tid == 0) {
+      int rows = HX_SLAB_YEARS + 1;
+      if (base + rows > C.nrow) rows = C.nrow - base;
+      const uint32_t bytes = (uint32_t)(rows * SC_STRIDE * sizeof(double));
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&bars[0], bytes);
+      bulk_g2s(slab[0], table + (size_t)base * SC_STRIDE, bytes, &bars[0]);
+      /* wait for the tile's previous slab (acquire: also drops stale L1 lines of its state) */
+      unsigned seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + tile) : "memory");
+        if (seen < (unsigned)s) __nanosleep(200);
+      } while (seen < (unsigned)s);
+    }
+    for (int i = tid; i < SC_STRIDE; i += HX_BLOCK) row0[i] = table[i];
+    __syncthreads();
+    __threadfence(); /* every thread orders its state loads after the acquire above */
+
+    const bool lane_ok = (d.status[m] == 0);
+    const Bases BS = make_bases(d, C, m);
+    const LandPar p = load_landpar(BS);
+    Member mb;
+    if (lane_ok) load_member(BS, mb);
+    else mb.status = -1;
+    mbar_wait(&bars[0], item_no & 1u);
+    ++item_no;
+    const double *sl = slab[0];
     if (mb.status == 0) {
       for (int r = base + 1; r <= rend; ++r) {
         const double *sc = sl + (size_t)(r - base) * SC_STRIDE;     /* year y */
@@ -707,13 +729,19 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 #undef EMIT
       }
     }
-    __syncthreads(); /* everyone is done with slab[s & 1] before it is refilled */
+    if (lane_ok) {
+      if (mb.status == 0) store_member(BS, mb);
+      else ++failed;
+    }
+    /* publish the tile's state: make this CTA's global stores visible, then release */
+    __threadfence();
+    __syncthreads(); /* also: everyone is done with slab[0] / row0 before they are refilled */
+    if (tid == 0) {
+      const unsigned done = (unsigned)s + 1u;
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + tile), "r"(done) : "memory");
+    }
   }
-
-  if (lane_ok) {
-    if (mb.status == 0) store_member(BS, mb);
-    flush_work(d, w, years_done, mb.status != 0 ? 1u : 0u);
-  }
+  flush_work(d, w, years_done, failed);
 }
 
 /* failed members report NaN from the failing year on (the reference stops producing output) */
@@ -751,7 +779,22 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  hx_run_kernel<<<d.Mpad / HX_BLOCK, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
+  static int resident = 0;
+  if (!resident) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel, HX_BLOCK,
+                                                                  HX_SMEM_RUN_BYTES);
+    if (e != cudaSuccess) return e;
+    resident = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  /* persistent CTAs: never more than can be co-resident (an item may wait on another CTA) */
+  const int ntiles = d.Mpad / HX_BLOCK;
+  const int grid = ntiles < resident ? ntiles : resident;
+  cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1) * sizeof(unsigned), st);
+  if (e != cudaSuccess) return e;
+  hx_run_kernel<<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_nan_fill(const HxDev &d, const HxConst &C, int nsel, int yr0, int yr1,

@@ -31,6 +31,7 @@ struct HxDev {
   int32_t *fail_year;       /* [Mpad] */
   int32_t *spinup_steps;    /* [Mpad] */
   unsigned long long *counters; /* [HX_NCOUNTERS] */
+  unsigned *sched;              /* [1 + Mpad / HX_BLOCK]: work-queue ticket, per-tile progress */
   int32_t out_slot[OUT_COUNT];  /* output id -> slot in `out`, -1 = not recorded */
 };
 
