@@ -502,13 +502,13 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           const double previous_ch4 = STATE(SI_CH4);
           double toh = 0.0;
           if (previous_ch4 != M0) {
-            const double a = PAR(PI_CCH4) * ((1.0 * log(previous_ch4)) - log(M0));
+            const double a = PAR(PI_CCH4) * ((1.0 * hx_log(previous_ch4)) - hx_log(M0));
             const double b = PAR(PI_CNOX) * ((1.0 * sc[SC_NOX]) - row0[SC_NOX]);
             const double c = PAR(PI_CCO) * ((1.0 * sc[SC_CO]) - row0[SC_CO]);
             const double dd = PAR(PI_CNMVOC) * ((1.0 * sc[SC_NMVOC]) - row0[SC_NMVOC]);
             toh = a + b + c + dd;
           }
-          const double tau_oh = PAR(PI_TOH0) * exp(-toh);
+          const double tau_oh = PAR(PI_TOH0) * hx_exp(-toh);
           const double rh_ch4_tg = mb.S[SI_RH_CH4 * HX_TILE] * (1000.0 * 16.04 / 12.01);
           const double emisTocon = (sc[SC_CH4_E] + rh_ch4_tg + sc[SC_CH4N]) * DER(DI_INV_UC_CH4);
           const double soil_sink = previous_ch4 * DER(DI_INV_TSOIL);
@@ -591,7 +591,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 
         /* --- OzoneComponent::run (o3_component.cpp:126-146) + ForcingComponent::run --- */
         const double ch4 = STATE(SI_CH4);
-        const double o3 = (5 * log(ch4)) + (0.125 * sc[SC_NOX]) + (0.0011 * sc[SC_CO]) +
+        const double o3 = (5 * hx_log(ch4)) + (0.125 * sc[SC_NOX]) + (0.0011 * sc[SC_CO]) +
                           (0.0033 * sc[SC_NMVOC]);
         double rf_tot = 0.0, rf_co2 = 0.0, rf_ch4 = 0.0, rf_n2o = 0.0;
         if (y >= C.baseyear) {
