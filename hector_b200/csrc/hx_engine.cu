@@ -111,7 +111,7 @@ struct Engine {
   bool identity_perm = true;
 
   /* device buffers */
-  double *d_P = nullptr, *d_S = nullptr, *d_S_snap = nullptr, *d_D = nullptr, *d_ker = nullptr,
+  double *d_P = nullptr, *d_S = nullptr, *d_S_snap = nullptr, *d_D = nullptr, *d_ker = nullptr, *d_conv = nullptr,
          *d_sst = nullptr, *d_tland = nullptr, *d_out = nullptr, *d_scen = nullptr,
          *d_stage = nullptr;
   int32_t *d_block_scen = nullptr, *d_status = nullptr, *d_status_snap = nullptr,
@@ -206,12 +206,12 @@ struct Engine {
   }
 
   void free_device() {
-    void *ptrs[] = {d_P, d_S, d_S_snap, d_D, d_ker, d_sst, d_tland, d_out, d_scen, d_stage,
+    void *ptrs[] = {d_P, d_S, d_S_snap, d_D, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
                     d_block_scen, d_status, d_status_snap, d_status_post, d_fail_year, d_spinup_steps, d_yidx,
                     d_counters, d_dev_of_api, d_sched};
     for (void *p : ptrs)
       if (p) cudaFree(p);
-    d_P = d_S = d_S_snap = d_D = d_ker = d_sst = d_tland = d_out = d_scen = d_stage = nullptr;
+    d_P = d_S = d_S_snap = d_D = d_ker = d_conv = d_sst = d_tland = d_out = d_scen = d_stage = nullptr;
     d_block_scen = d_status = d_status_snap = d_status_post = d_fail_year = d_spinup_steps = d_yidx = nullptr;
     d_counters = nullptr;
     d_sched = nullptr;
@@ -601,7 +601,8 @@ int hx_prepare(hx_handle h) {
       cudaMalloc(&h->d_S, SI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_S_snap, SI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_D, DI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&h->d_ker, (size_t)(nrow + 1) * Mp * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_ker, (size_t)HX_KER_ROWS(nrow) * Mp * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_conv, (size_t)HX_SLAB_YEARS * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_sst, (size_t)nrow * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_tland, (size_t)nrow * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_out, std::max<size_t>(1, (size_t)nsel * (nrow - 1) * Mp) * sizeof(double)) != cudaSuccess ||
@@ -631,14 +632,15 @@ int hx_prepare(hx_handle h) {
   cudaMemsetAsync(h->d_spinup_steps, 0, Mp * sizeof(int32_t), st);
   cudaMemsetAsync(h->d_S, 0, SI_COUNT * Mp * sizeof(double), st);
   cudaMemsetAsync(h->d_D, 0, DI_COUNT * Mp * sizeof(double), st);
-  cudaMemsetAsync(h->d_ker, 0, (size_t)(nrow + 1) * Mp * sizeof(double), st);
+  cudaMemsetAsync(h->d_ker, 0, (size_t)HX_KER_ROWS(nrow) * Mp * sizeof(double), st);
+  cudaMemsetAsync(h->d_conv, 0, (size_t)HX_SLAB_YEARS * Mp * sizeof(double), st);
   cudaMemsetAsync(h->d_sst, 0, (size_t)nrow * Mp * sizeof(double), st);
   cudaMemsetAsync(h->d_tland, 0, (size_t)nrow * Mp * sizeof(double), st);
   if (cudaStreamSynchronize(st) != cudaSuccess)
     return fail(HX_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
 
   HxDev &d = h->d;
-  d.Mpad = Mpad; d.P = h->d_P; d.S = h->d_S; d.D = h->d_D; d.ker = h->d_ker;
+  d.Mpad = Mpad; d.P = h->d_P; d.S = h->d_S; d.D = h->d_D; d.ker = h->d_ker; d.conv = h->d_conv;
   d.sst_hist = h->d_sst; d.tland_hist = h->d_tland; d.out = h->d_out; d.scen = h->d_scen;
   d.block_scen = h->d_block_scen; d.status = h->d_status; d.fail_year = h->d_fail_year;
   d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters; d.sched = h->d_sched;

@@ -73,7 +73,7 @@ __device__ __forceinline__ void fence_proxy_async() {
 /* CTA-tiled SoA accessors: one base pointer per array, compile-time field offsets */
 struct Bases {
   const double *P;
-  double *S, *D, *ker, *sst, *tland;
+  double *S, *D, *ker, *sst, *tland, *conv;
 };
 __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, int m) {
   const size_t tile = (size_t)(m / HX_BLOCK), ln = (size_t)(m % HX_BLOCK);
@@ -81,7 +81,8 @@ __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, in
   b.P = d.P + tile * PI_COUNT * HX_BLOCK + ln;
   b.S = d.S + tile * SI_COUNT * HX_BLOCK + ln;
   b.D = d.D + tile * DI_COUNT * HX_BLOCK + ln;
-  b.ker = d.ker + tile * (size_t)(C.nrow + 1) * HX_BLOCK + ln;
+  b.ker = d.ker + tile * (size_t)HX_KER_ROWS(C.nrow) * HX_BLOCK + ln;
+  b.conv = d.conv + tile * (size_t)HX_SLAB_YEARS * HX_BLOCK + ln;
   b.sst = d.sst_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
   b.tland = d.tland_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
   return b;
@@ -259,7 +260,7 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   STATE(SI_HEAT_MIXED) = 0.0; STATE(SI_HEAT_INTERIOR) = 0.0; STATE(SI_RF_PREV) = 0.0;
   STATE(SI_BASE_TOT) = 0.0; STATE(SI_BASE_CO2) = 0.0; STATE(SI_BASE_CH4) = 0.0;
   STATE(SI_BASE_N2O) = 0.0;
-  STATE(SI_TLAND_WSUM) = 0.0; STATE(SI_TLAND_WCOMP) = 0.0;
+  STATE(SI_TLAND_WSUM) = 0.0; STATE(SI_TLAND_WCOMP) = 0.0; STATE(SI_DPAST_RAW) = 0.0;
   BS.sst[0] = 0.0;   /* row 0: temp_sst[0] = 0 */
   BS.tland[0] = 0.0;
   d.fail_year[m] = 0;
@@ -407,6 +408,70 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
   }
 }
 
+
+/* ======================================================================================== */
+/* Slab prepass of the DOECLIM convolution (temperature_component.cpp:488-491, 534-537).
+ *
+ * Year r needs DPAST2(r) = sum_{i<r} sst[i] K(r-i+1), an O(r) pass over the member's SST history
+ * and lag kernel -- streamed from HBM every year that is 16 r bytes per member-year and it
+ * dominated both the DRAM traffic and the stall profile of the run kernel.  A work item covers
+ * B = HX_SLAB_YEARS consecutive years r_j = base+1+j, and the history rows i < n_pre <= base+1
+ * are common to all of them, so ONE pass accumulates the B partial sums
+ *     acc[j] = sum_{i<n_pre} sst[i] K(r_j-i+1)
+ * with a register window over K that slides one row per history row; each year then only adds
+ * its last r - n_pre < B + U terms.  Every acc[j] chain adds the same products in the same
+ * (ascending i) order as a year-by-year loop, so results are bit-identical; history traffic
+ * drops by B.  (The second convolution of the reference, sum_{i<r} sst[i] K(r-i), is last
+ * year's DPAST2 sum plus one term -- see the year loop -- and needs no pass of its own.)
+ *
+ * U rows are fetched per trip while the B*U FMAs of the previous trip issue. */
+template <int B, int U>
+__device__ __forceinline__ void conv_prepass(const double *__restrict__ sst,
+                                             const double *__restrict__ ker, int base, int n_pre,
+                                             double *__restrict__ out) {
+  constexpr size_t Hs = HX_BLOCK;
+  double acc[B];
+#pragma unroll
+  for (int j = 0; j < B; ++j) acc[j] = 0.0;
+  if (n_pre > 0) {
+    /* V[p] = K(base + 2 - i0 - (U-1) + p), p = 0 .. B+U-2: the rows K(r_j - i + 1) that the
+     * history rows i = i0 .. i0+U-1 of the current trip meet */
+    double V[B + U - 1], s[U], sn[U], vn[U];
+    const double *pk = ker + (size_t)(base + 2 - (U - 1)) * Hs;
+#pragma unroll
+    for (int p = 0; p < B + U - 1; ++p) V[p] = __ldcs(pk + (size_t)p * Hs);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      s[u] = __ldcs(sst + (size_t)u * Hs);
+      sn[u] = 0.0; vn[u] = 0.0;
+    }
+    for (int i0 = 0; i0 < n_pre; i0 += U) {
+      if (i0 + U < n_pre) {
+        const double *ns = sst + (size_t)(i0 + U) * Hs;
+        const double *nk = pk - (size_t)(i0 + U) * Hs;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          sn[u] = __ldcs(ns + (size_t)u * Hs);
+          vn[u] = __ldcs(nk + (size_t)u * Hs);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < B; ++j) acc[j] = fma(s[u], V[j + (U - 1) - u], acc[j]);
+#pragma unroll
+      for (int p = B + U - 2; p >= U; --p) V[p] = V[p - U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        V[u] = vn[u];
+        s[u] = sn[u];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < B; ++j) out[(size_t)j * Hs] = acc[j];
+}
+
 /* ======================================================================================== */
 /* the yearly coupled step, rows r0+1 .. r1 (row = year - start_year) */
 __global__ void __launch_bounds__(HX_BLOCK, HX_RUN_MIN_CTAS)
@@ -483,6 +548,9 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 
     const bool lane_ok = (d.status[m] == 0);
     const Bases BS = make_bases(d, C, m);
+    /* history rows [0, n_pre) of the DOECLIM convolution, for all years of the slab at once */
+    const int n_pre = ((base + 1) / HX_CONV_UNROLL) * HX_CONV_UNROLL;
+    conv_prepass<HX_SLAB_YEARS, HX_CONV_UNROLL>(BS.sst, BS.ker, base, n_pre, BS.conv);
     const LandPar p = load_landpar(BS);
     Member mb;
     if (lane_ok) load_member(BS, mb);
@@ -628,42 +696,26 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           double DQ2 = 0.5 * dt / cas * (rf_tot + rf_prev);
           DQ1 = DQ1 + QC1;
           DQ2 = DQ2 + QC2;
-          /* one pass over the SST history feeds both convolutions (E-4):
+          /* the two history convolutions (E-4):
            *   DPAST2   = sum_{i<=t} sst[i] K(t-i+1)   (:488-491; the i = t term is 0)
-           *   interior = sum_{i<t}  sst[i] K(t-i)     (:534-537) */
-          double DPAST2 = 0.0, hint = 0.0;
+           *   interior = sum_{i<t}  sst[i] K(t-i)     (:534-537)
+           * interior(t) adds, oldest first, exactly the products of DPAST2(t-1) and then the
+           * one term sst[t-1] K(1): it is last year's unscaled sum plus one FMA.  DPAST2 takes
+           * the rows i < n_pre from the slab prepass and adds its last rows here, oldest first
+           * like the reference. */
+          const double hint = fma(sst, BS.ker[Hs], STATE(SI_DPAST_RAW));
+          double DPAST2 = BS.conv[(size_t)(r - base - 1) * Hs];
           {
-            /* oldest first, like the reference; HX_CONV_UNROLL history rows are fetched per trip so the
-             * loads of a trip are all in flight together */
-            const double *ps = BS.sst;                           /* sst[i], i ascending */
-            const double *pk = BS.ker + (size_t)r * Hs;           /* K(r - i), descending */
-            double kj1 = pk[Hs];                                 /* K(r + 1) */
-            int i = 0;
-            for (; i + HX_CONV_UNROLL <= r; i += HX_CONV_UNROLL) {
-              double sv[HX_CONV_UNROLL], kv[HX_CONV_UNROLL];
-#pragma unroll
-              for (int u = 0; u < HX_CONV_UNROLL; ++u) {
-                sv[u] = __ldcs(ps + u * Hs);
-                kv[u] = __ldcs(pk - u * Hs);
-              }
-#pragma unroll
-              for (int u = 0; u < HX_CONV_UNROLL; ++u) {
-                DPAST2 = DPAST2 + sv[u] * kj1;
-                hint = hint + sv[u] * kv[u];
-                kj1 = kv[u];
-              }
-              ps += HX_CONV_UNROLL * Hs;
-              pk -= HX_CONV_UNROLL * Hs;
-            }
-            for (; i < r; ++i) {
-              const double sv = *ps, kj = *pk;
-              DPAST2 = DPAST2 + sv * kj1;
-              hint = hint + sv * kj;
-              kj1 = kj;
+            const double *ps = BS.sst + (size_t)n_pre * Hs;          /* sst[i], i ascending */
+            const double *pk = BS.ker + (size_t)(r - n_pre + 1) * Hs; /* K(r - i + 1), descending */
+#pragma unroll 4
+            for (int i = n_pre; i < r; ++i) {
+              DPAST2 = fma(*ps, *pk, DPAST2);
               ps += Hs;
               pk -= Hs;
             }
           }
+          STATE(SI_DPAST_RAW) = DPAST2;
           DPAST2 = DPAST2 * fso * DER(DI_SQDT_TAUDIF);
           const double DPAST1 = 0.0;
           const double DTEAUX1 = DER(DI_A0) * tland + DER(DI_A1) * sst;

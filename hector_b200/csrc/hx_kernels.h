@@ -8,9 +8,8 @@
 #include "hx_layout.h"
 
 #define HX_BLOCK 128      /* threads (= members) per CTA; one scenario per CTA */
-#define HX_SLAB_YEARS 16  /* scenario rows staged per bulk copy */
 #ifndef HX_CONV_UNROLL
-#define HX_CONV_UNROLL 32 /* history rows (x2 arrays) in flight per thread in the DOECLIM convolution */
+#define HX_CONV_UNROLL 8 /* history rows per trip of the slab prepass of the DOECLIM convolution */
 #endif
 #ifndef HX_RUN_MIN_CTAS
 #define HX_RUN_MIN_CTAS 2 /* resident CTAs per SM the run kernel is register-limited to */
@@ -21,7 +20,8 @@ struct HxDev {
   const double *P;          /* [PI_COUNT][Mpad] */
   double *S;                /* [SI_COUNT][Mpad] */
   double *D;                /* [DI_COUNT][Mpad] */
-  double *ker;              /* [nrow+1][Mpad]  DOECLIM lag kernel K(j) */
+  double *ker;              /* [HX_KER_ROWS(nrow)][Mpad]  DOECLIM lag kernel K(j), zero padded */
+  double *conv;             /* [HX_SLAB_YEARS][Mpad] per-slab partial convolution sums */
   double *sst_hist;         /* [nrow][Mpad] */
   double *tland_hist;       /* [nrow][Mpad] */
   double *out;              /* [nsel][nrow-1][Mpad] */

@@ -3,7 +3,8 @@
  * Per-member data is structure-of-arrays, tiled by CTA ("CTA-tiled SoA"): the HX_TILE = 128
  * members of one CTA own a contiguous block
  *   params     P[tile][PI_COUNT][128]     state  S[tile][SI_COUNT][128]   derived D[tile][DI_COUNT][128]
- *   histories  sst_hist / tland_hist [tile][nrow][128],  ker [tile][nrow+1][128]
+ *   histories  sst_hist / tland_hist [tile][nrow][128],  ker [tile][HX_KER_ROWS(nrow)][128]
+ *   scratch    conv [tile][HX_SLAB_YEARS][128]   (per-slab partial convolution sums)
  * so (a) a warp touches 32 consecutive doubles (256 B) per access, (b) every field of a thread
  * sits at a COMPILE-TIME offset (field * 1 KiB) from one base pointer -- no per-field address
  * registers or 64-bit index arithmetic in the kernels -- and (c) consecutive history rows of a
@@ -19,6 +20,10 @@
 
 #define HX_NHALO 26
 #define HX_TILE 128 /* members per tile = threads per CTA (HX_BLOCK) */
+#define HX_SLAB_YEARS 16 /* years per work item = scenario rows staged per bulk copy */
+/* rows of the DOECLIM lag-kernel table K(0..nrow), zero-padded so the slab prepass of the
+ * convolution may read K(j) up to j = nrow + HX_SLAB_YEARS without a bounds test */
+#define HX_KER_ROWS(nrow) ((nrow) + 1 + HX_SLAB_YEARS)
 
 /* element index of (field, member) in a tiled array with `nfields` rows per tile */
 #define HX_TILED(field, m, nfields) \
@@ -67,6 +72,8 @@ enum {
   SI_CH4, SI_TLAND, SI_SST, SI_HEAT_MIXED, SI_HEAT_INTERIOR, SI_RF_PREV,
   SI_BASE_TOT, SI_BASE_CO2, SI_BASE_CH4, SI_BASE_N2O,
   SI_TLAND_WSUM, SI_TLAND_WCOMP, /* 200-year land-temperature window: compensated running sum */
+  SI_DPAST_RAW, /* last year's unscaled DOECLIM convolution sum_i sst[i] K(t-i+1): next year's
+                   interior-flux sum is this plus one term */
   /* per-year scratch (slowparameval results, emissions, annual sums) parked between phases */
   SI_X_CO2FERT, SI_X_TFD, SI_X_TFS, SI_X_FNEWTHAW, SI_X_NPPLUC, SI_X_FFI, SI_X_DACCS, SI_X_NBP,
   SI_X_FLUXSUM,
