@@ -1,0 +1,139 @@
+// tests/cpp/test_core_facade.cpp -- drives the C++ facade (include/hector_b200_core.hpp) the way
+// the reference's own callers drive Hector::Core: src/main.cpp:41-112 (init / parse /
+// prepareToRun / run), src/rcpp_hector.cpp:31-365 (mkcore / getcore / sendMessage / reset) and
+// tests/testthat/test_wrapper.R:135-145 (a core stays usable after an exception).
+//
+//   test_core_facade <ini> [nogpu]
+// prints KEY=VALUE lines (doubles as %.17g) that tests/test_core_facade.py checks against the
+// oracle; exits non-zero on any behavioural mismatch.
+#define HECTOR_B200_AS_HECTOR
+#include "hector_b200_core.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+
+using namespace Hector;
+
+static int failures = 0;
+#define EXPECT(cond)                                                     \
+  do {                                                                   \
+    if (!(cond)) {                                                       \
+      std::printf("FAILED %s:%d %s\n", __FILE__, __LINE__, #cond);       \
+      ++failures;                                                        \
+    }                                                                    \
+  } while (0)
+
+template <class F>
+static bool throws(F f) {
+  try {
+    f();
+  } catch (const h_exception &) {
+    return true;
+  }
+  return false;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 2) return 2;
+  const std::string ini = argv[1];
+  const bool nogpu = argc > 2 && std::string(argv[2]) == "nogpu";
+
+  if (nogpu) { /* the product has no CPU path: parse must throw, naming CUDA */
+    Core core(Logger::SEVERE, false, false);
+    core.init();
+    bool thrown = false;
+    try {
+      INIToCoreReader(&core).parse(ini);
+    } catch (const h_exception &e) {
+      thrown = true;
+      std::printf("NOGPU_MSG=%s\n", e.what());
+    }
+    EXPECT(thrown);
+    EXPECT(throws([&] { core.run(); })); /* nothing parsed */
+    return failures ? 1 : 0;
+  }
+
+  /* ---- single core through the registry, like the R glue ---- */
+  const int idx = Core::mkcore(false, Logger::SEVERE, false);
+  Core *core = Core::getcore(idx);
+  EXPECT(core != nullptr);
+  EXPECT(Core::getcore(idx + 7) == nullptr);
+  core->init();
+  INIToCoreReader(core).parse(ini);
+  EXPECT(core->getStartDate() == 1745 && core->getEndDate() == 2300);
+  core->prepareToRun();
+  core->run(2100);
+  EXPECT(core->getCurrentDate() == 2100);
+  std::printf("D_CO2_2100=%.17g\n", (double)core->sendMessage(M_GETDATA, "CO2_concentration", message_data(2100.0)));
+  core->run(); /* resume to the end date */
+  const unitval tas = core->sendMessage(M_GETDATA, "global_tas", message_data(2300.0));
+  EXPECT(tas.units() == U_DEGC);
+  EXPECT(tas.unitsName() == "degC");
+  std::printf("D_TAS_2300=%.17g\n", tas.value(U_DEGC));
+  std::printf("D_CO2_2300=%.17g\n", (double)core->sendMessage(M_GETDATA, "CO2_concentration", message_data(2300.0)));
+  std::printf("D_PH_2000=%.17g\n", (double)core->sendMessage(M_GETDATA, "HL_pH", message_data(2000.0)));
+  /* parameters read back with their units */
+  const unitval S0 = core->sendMessage(M_GETDATA, "S");
+  EXPECT((double)S0 == 3.0 && S0.units() == U_DEGC);
+
+  /* ---- errors: same places as the reference, and the core stays usable ---- */
+  EXPECT(throws([&] { core->sendMessage(M_GETDATA, "no_such_variable", message_data(2000.0)); }));
+  EXPECT(throws([&] { core->sendMessage(M_GETDATA, "global_tas", message_data(2301.0)); }));
+  EXPECT(throws([&] { core->sendMessage(M_GETDATA, "global_tas", message_data(1745.0)); }));
+  EXPECT(throws([&] { core->sendMessage("noSuchMessage", "global_tas"); }));
+  EXPECT(throws([&] { core->sendMessage(M_SETDATA, "S", message_data(unitval(3.0, U_PGC))); }));
+  EXPECT(throws([&] { tas.value(U_PGC); }));
+  EXPECT(throws([&] { core->run(2400); }));
+  EXPECT(throws([&] { unitval::parseUnitsName("furlongs"); }));
+
+  /* ---- setvar + reset + run (R: setvar(core, NA, ECS(), 4.5, "degC"); reset(core); run(core)) ---- */
+  core->sendMessage(M_SETDATA, "S", message_data(unitval(4.5, unitval::parseUnitsName("degC"))));
+  core->sendMessage(M_SETDATA, "beta", message_data(unitval(0.4, U_UNITLESS)));
+  core->reset(0);
+  EXPECT(core->getCurrentDate() == 1745);
+  core->run();
+  std::printf("S45_CO2_2300=%.17g\n", (double)core->sendMessage(M_GETDATA, "CO2_concentration", message_data(2300.0)));
+  std::printf("S45_TAS_2300=%.17g\n", (double)core->sendMessage(M_GETDATA, "global_tas", message_data(2300.0)));
+
+  /* a member the reference aborts: run() must throw, and the core must survive it */
+  core->sendMessage(M_SETDATA, "beta", message_data(unitval(50.0, U_UNITLESS)));
+  core->reset(0);
+  bool failed = false;
+  try {
+    core->run();
+  } catch (const h_exception &e) {
+    failed = true;
+    std::printf("FAIL_MSG=%s\n", e.what());
+  }
+  std::printf("BETA50_FAILED=%d\n", failed ? 1 : 0);
+  core->sendMessage(M_SETDATA, "beta", message_data(unitval(0.65, U_UNITLESS)));
+  core->sendMessage(M_SETDATA, "S", message_data(unitval(3.0, U_DEGC)));
+  core->reset(0);
+  core->run();
+  std::printf("AGAIN_CO2_2300=%.17g\n", (double)core->sendMessage(M_GETDATA, "CO2_concentration", message_data(2300.0)));
+  Core::delcore(idx);
+  EXPECT(Core::getcore(idx) == nullptr);
+  Core::delcore(idx); /* idempotent */
+
+  /* ---- the batch face: 4 members, per-member S ---- */
+  EnsembleCore ens(4);
+  INIToCoreReader(&ens).parse(ini);
+  ens.selectOutputs({"CO2_concentration", "global_tas"});
+  ens.setMembers("S", {2.0, 3.0, 4.5, 6.0}, U_DEGC);
+  EXPECT(throws([&] { ens.setMembers("S", {2.0, 3.0, 4.5, 6.0}, U_PGC); }));
+  ens.sendMessage(M_SETDATA, "beta", message_data(unitval(0.4, U_UNITLESS)), 2); /* member 2 only */
+  ens.run(-1, false);
+  std::vector<double> out(4 * 2);
+  ens.fetch("global_tas", {2100.0, 2300.0}, out.data());
+  for (int m = 0; m < 4; ++m) std::printf("ENS_TAS_2300_%d=%.17g\n", m, out[m * 2 + 1]);
+  std::printf("ENS_CO2_2300_2=%.17g\n", (double)ens.sendMessage(M_GETDATA, "CO2_concentration", message_data(2300.0), 2));
+  std::vector<int32_t> st, fy;
+  ens.memberStatus(st, fy);
+  for (int m = 0; m < 4; ++m) EXPECT(st[m] == 0);
+  EXPECT(throws([&] { ens.fetch("RF_tot", {2100.0}, out.data()); })); /* not selected */
+  ens.shutDown();
+  ens.shutDown();
+
+  std::printf("FAILURES=%d\n", failures);
+  return failures ? 1 : 0;
+}
