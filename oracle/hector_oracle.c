@@ -44,8 +44,23 @@ typedef struct {
   double K0, Tr, PCO2o, pH, CO3, TCO2o, HCO3, OmegaCa, OmegaAr, Kh, Kw;
 } csys_t;
 
+/* Carbon tracking (fluxpool.hpp): a fluxpool's unordered_map<source name, fraction> restated as
+ * a fixed vector over the 12 possible source names plus a presence mask (a key that is in
+ * the map with fraction 0 is not the same as an absent key: it counts in the 1/n split of a
+ * zero total and it is printed by the tracking visitor).  Source / pool order:
+ * atmos_co2 earth_c veg_c detritus_c soil_c permafrost_c thawedp_c HL LL intermediate deep
+ * untracked. */
+typedef struct {
+  double f[HO_NSRC];
+  unsigned mask;
+} tmap_t;
+enum { TP_ATMOS = 0, TP_EARTH, TP_VEG, TP_DET, TP_SOIL, TP_PERMAFROST, TP_THAWEDP, TP_BOX0,
+       TP_UNTRACKED = 11 };
+
 /* one ocean box (oceanbox.hpp, oceanbox.cpp) */
 typedef struct {
+  tmap_t cmap, addmap, aomap, oamap; /* source maps of carbon, CarbonAdditions, ao_flux, oa_flux */
+  int tracking, ao_tracking;
   double carbon, additions, subtractions;
   double Tbox, deltaT, atmosphere_flux, preindustrial_flux, ao_flux, oa_flux;
   int surfacebox, active_chemistry;
@@ -88,6 +103,13 @@ typedef struct {
   /* solver (carbon-cycle-solver.hpp:86-98) */
   double c[NC], t, dt;
 
+  /* carbon tracking: maps of atmos_c, earth_c and the five land pools (TP_* order), and the
+   * ocean's copy of the atmosphere (set_atmosphere_sources, ocean_component.hpp:78,106) */
+  int tracking_date, tracking;
+  tmap_t tm[7];
+  tmap_t atmosphere_cpool;
+  int atmosphere_cpool_tracking;
+
   /* gas components */
   double *CH4, *O3, *N2O, *halo_rf; /* per-row series */
   double tau_oh;
@@ -115,6 +137,43 @@ static void fail_member(member_t *m, int code) {
 static inline double FP(member_t *m, double v) {
   if (v < 0) fail_member(m, HO_ERR_NEGATIVE);
   return v;
+}
+
+/* fluxpool::set(v, u, track, name): ctmap[name] = 1.0 -- other keys are NOT erased
+ * (fluxpool.hpp:118-127) */
+static void tm_set_self(tmap_t *t, int self) {
+  t->f[self] = 1.0;
+  t->mask |= 1u << self;
+}
+static void tm_init(tmap_t *t, int self) {
+  memset(t, 0, sizeof *t);
+  tm_set_self(t, self);
+}
+/* private constructor checks (fluxpool.hpp:93-113): every fraction in [0, 1], sum - 1 < 1e-6 */
+static void tm_check(member_t *m, const tmap_t *t) {
+  double frac = 0.0;
+  for (int s = 0; s < HO_NSRC; ++s)
+    if (t->mask >> s & 1u) {
+      if (!(t->f[s] >= 0 && t->f[s] <= 1)) fail_member(m, HO_ERR_TRACKING);
+      frac += t->f[s];
+    }
+  if (!(frac - 1.0 < 1e-6)) fail_member(m, HO_ERR_TRACKING);
+}
+/* operator+(fluxpool, fluxpool) with tracking on (fluxpool.hpp:197-257): the map of
+ * (a, A) + (b, B) is written to A.  Per source in the union of the key sets:
+ * (a fa + b fb) / (a + b), or 1/n for every key when the new total is zero. */
+static void tm_add(member_t *m, double a, tmap_t *A, double b, const tmap_t *B) {
+  const double new_total = a + b;
+  const unsigned un = A->mask | B->mask;
+  int n = 0;
+  for (int s = 0; s < HO_NSRC; ++s) n += (int)(un >> s & 1u);
+  for (int s = 0; s < HO_NSRC; ++s)
+    if (un >> s & 1u) {
+      const double pool = a * A->f[s] + b * B->f[s]; /* get_fraction() is 0 for absent keys */
+      A->f[s] = new_total ? pool / new_total : 1.0 / n;
+    }
+  A->mask = un;
+  tm_check(m, A);
 }
 
 /* ---------------------------------------------------------------------------------- */
@@ -336,6 +395,11 @@ double ho_csys(double Tbox, double carbon_pgc, double alk, double volume, double
 /* ---------------------------------------------------------------------------------- */
 /* oceanbox                                                                            */
 static void box_separate_surface_fluxes(member_t *m, box_t *b) { /* oceanbox.cpp:262-271 */
+  /* ao_flux = atmosphere_pool.flux_from_unitval(..), oa_flux = carbon.flux_from_unitval(..):
+   * the fluxes inherit the source map (and tracking flag) of the pool they leave */
+  b->aomap = m->atmosphere_cpool;
+  b->ao_tracking = m->atmosphere_cpool_tracking;
+  b->oamap = b->cmap;
   if (b->atmosphere_flux > 0) {
     b->ao_flux = FP(m, b->atmosphere_flux);
     b->oa_flux = FP(m, 0.0);
@@ -361,6 +425,7 @@ static void box_compute_fluxes(member_t *m, int ib, double current_Ca, double yf
     for (int i = 0; i < b->nconn; ++i) {
       double closs = FP(m, FP(m, b->carbon * b->conn_k[i]) * yf);
       box_t *dst = &m->box[b->conn_to[i]];
+      if (b->tracking) tm_add(m, dst->additions, &dst->addmap, closs, &b->cmap);
       dst->additions = FP(m, dst->additions + closs);   /* add_carbon, oceanbox.cpp:85-90 */
       b->subtractions = FP(m, b->subtractions + closs);
     }
@@ -368,14 +433,21 @@ static void box_compute_fluxes(member_t *m, int ib, double current_Ca, double yf
 }
 
 /* oceanbox.cpp:297-303 */
-static void box_update_state(member_t *m, box_t *b) {
+static void box_update_state(member_t *m, int ib) {
+  box_t *b = &m->box[ib];
+  if (b->tracking) tm_add(m, b->carbon, &b->cmap, b->additions, &b->addmap);
   double v = FP(m, b->carbon + b->additions);
+  if (b->tracking) {
+    tm_add(m, v, &b->cmap, b->ao_flux, &b->aomap);
+  }
+  if (b->tracking != b->ao_tracking) fail_member(m, HO_ERR_TRACKING); /* "tracking mismatch" */
   v = FP(m, v + b->ao_flux);
   v = FP(m, v - b->oa_flux);
   v = FP(m, v - b->subtractions);
   b->carbon = v;
   b->additions = 0.0;
   b->subtractions = 0.0;
+  tm_set_self(&b->addmap, TP_BOX0 + ib); /* CarbonAdditions.set(0.0, U_PGC, tracking, Name) */
 }
 
 /* oceanbox.cpp:309-323 */
@@ -486,7 +558,13 @@ static void ocean_prepareToRun(member_t *m) { /* ocean_component.cpp:202-319 */
   const double D_preind_C = D_vol_frac * p->preind_C_ID;
 
   memset(m->box, 0, sizeof m->box);
-  for (int i = 0; i < 4; ++i) m->box[i].Tbox = -999;
+  for (int i = 0; i < 4; ++i) {
+    m->box[i].Tbox = -999;
+    tm_init(&m->box[i].cmap, TP_BOX0 + i); /* initbox: carbon.set(boxc, U_PGC, false, name) */
+    tm_init(&m->box[i].addmap, TP_BOX0 + i);
+    tm_init(&m->box[i].aomap, TP_BOX0 + i);
+    tm_init(&m->box[i].oamap, TP_BOX0 + i);
+  }
   m->box[HL].carbon = FP(m, HL_preind_C);
   m->box[HL].surfacebox = 1;
   m->box[HL].preindustrial_flux = 1.000;
@@ -551,7 +629,10 @@ static double ocean_annual_totalcflux(member_t *m, double CO2_conc, double cpool
 }
 
 /* ocean_component.cpp:356-407; co2_conc = D_CO2_CONC(runToDate), sst = current D_SST */
-static void ocean_run(member_t *m, double co2_conc, double sst) {
+static void ocean_run(member_t *m, double runToDate, double co2_conc, double sst) {
+  /* tracking start: ocean_component.cpp:358-366 (ocean_in_spinup is last call's flag) */
+  if (!m->ocean_in_spinup && runToDate == (double)m->tracking_date)
+    for (int i = 0; i < 4; ++i) m->box[i].tracking = 1;
   m->ocean_CO2_conc = co2_conc;
   m->SST = sst;
   m->ocean_in_spinup = m->in_spinup;
@@ -626,17 +707,29 @@ static void ocean_stashCValues(member_t *m, double t, const double c[]) {
   m->annualflux_sum = m->annualflux_sum + lastflux;
   m->lastflux_annualized = lastflux / yearfraction;
 
-  box_update_state(m, &m->box[HL]);
-  box_update_state(m, &m->box[LL]);
-  box_update_state(m, &m->box[IO]);
-  box_update_state(m, &m->box[DO]);
+  box_update_state(m, HL);
+  box_update_state(m, LL);
+  box_update_state(m, IO);
+  box_update_state(m, DO);
   m->ocean_ODEstartdate = t;
 }
 
 /* M_DUMP_TO_DEEP_OCEAN: ocean_component.cpp:146-154 */
 static void ocean_dump_to_deep(member_t *m, double carbon) {
   carbon = carbon + m->box[DO].carbon;
-  m->box[DO].carbon = carbon; /* adjust_pool_to_val: no sign check (fluxpool.hpp:181-192) */
+  /* set_carbon -> adjust_pool_to_val(C, allow_untracked = true): a positive difference enters
+   * as source "untracked"; no sign check on the value (fluxpool.hpp:181-192) */
+  box_t *b = &m->box[DO];
+  const double diff = carbon - b->carbon;
+  if (b->tracking && diff > 0) {
+    tmap_t u;
+    memset(&u, 0, sizeof u);
+    tm_set_self(&u, TP_UNTRACKED);
+    tmap_t adj = b->cmap;
+    tm_add(m, b->carbon, &adj, FP(m, diff), &u);
+    b->cmap = adj;
+  }
+  b->carbon = carbon;
 }
 
 /* ---------------------------------------------------------------------------------- */
@@ -825,8 +918,19 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
 
   double ffi_flux = FP(m, m->current_ffi_e);   /* earth_c.flux_from_fluxpool */
   double ccs_flux = FP(m, m->current_daccs_u);
+  /* Carbon tracking: a flux made by X.flux_from_fluxpool(..) carries a COPY of X's source map
+   * as of that statement.  T = tracking on; *_0 = maps at the top of this stash. */
+  const int T = m->tracking;
+  const tmap_t atm_0 = m->tm[TP_ATMOS], earth_0 = m->tm[TP_EARTH], veg_0 = m->tm[TP_VEG],
+               det_0 = m->tm[TP_DET], soil_0 = m->tm[TP_SOIL], perm_0 = m->tm[TP_PERMAFROST],
+               thawed_0 = m->tm[TP_THAWEDP];
 
   ocean_stashCValues(m, t, c);
+  tmap_t oa_map = m->box[LL].oamap, ao_map = m->box[LL].aomap;
+  if (T) {
+    tm_add(m, m->box[LL].oa_flux, &oa_map, m->box[HL].oa_flux, &m->box[HL].oamap);
+    tm_add(m, m->box[LL].ao_flux, &ao_map, m->box[HL].ao_flux, &m->box[HL].aomap);
+  }
   double oa_flux = FP(m, m->box[LL].oa_flux + m->box[HL].oa_flux); /* get_oaflux */
   double ao_flux = FP(m, m->box[LL].ao_flux + m->box[HL].ao_flux);
 
@@ -886,11 +990,15 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
     m->RH_ch4 = rh_fpa_ch4_flux;
 
     /* luc fluxes :458-462 */
+    if (T) tm_add(m, m->atmos_c, &m->tm[TP_ATMOS], luc_fva_biome_flux, &veg_0);
     double a = FP(m, m->atmos_c + luc_fva_biome_flux);
     a = FP(m, a - luc_fav_biome_flux);
+    if (T) tm_add(m, a, &m->tm[TP_ATMOS], luc_fda_biome_flux, &det_0);
     a = FP(m, a + luc_fda_biome_flux);
+    if (T) tm_add(m, a, &m->tm[TP_ATMOS], luc_fsa_biome_flux, &soil_0);
     a = FP(m, a + luc_fsa_biome_flux);
     m->atmos_c = a;
+    if (T) tm_add(m, m->veg_c, &m->tm[TP_VEG], luc_fav_biome_flux, &atm_0);
     double vg = FP(m, m->veg_c + luc_fav_biome_flux);
     vg = FP(m, vg - luc_fva_biome_flux);
     m->veg_c = vg;
@@ -898,6 +1006,11 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
     m->soil_c = FP(m, m->soil_c - luc_fsa_biome_flux);
 
     /* npp fluxes :465-469 */
+    if (T) {
+      tm_add(m, m->veg_c, &m->tm[TP_VEG], npp_fav_biome_flux, &atm_0);
+      tm_add(m, m->detritus_c, &m->tm[TP_DET], npp_fad_biome_flux, &atm_0);
+      tm_add(m, m->soil_c, &m->tm[TP_SOIL], npp_fas_biome_flux, &atm_0);
+    }
     m->veg_c = FP(m, m->veg_c + npp_fav_biome_flux);
     m->detritus_c = FP(m, m->detritus_c + npp_fad_biome_flux);
     m->soil_c = FP(m, m->soil_c + npp_fas_biome_flux);
@@ -907,8 +1020,11 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
     m->atmos_c = a;
 
     /* rh fluxes :472-481 */
+    if (T) tm_add(m, m->atmos_c, &m->tm[TP_ATMOS], rh_fda_flux, &det_0);
     a = FP(m, m->atmos_c + rh_fda_flux);
+    if (T) tm_add(m, a, &m->tm[TP_ATMOS], rh_fsa_flux, &soil_0);
     a = FP(m, a + rh_fsa_flux);
+    if (T) tm_add(m, a, &m->tm[TP_ATMOS], rh_fpa_co2_flux, &thawed_0);
     a = FP(m, a + rh_fpa_co2_flux);
     m->atmos_c = a;
     m->detritus_c = FP(m, m->detritus_c - rh_fda_flux);
@@ -924,10 +1040,16 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
       double pf_thaw = FP(m, FP(m, FP(m, x)) * yf);
       double pf_refreeze_tp = FP(m, FP(m, FP(m, y)) * yf);
       double pf_refreeze_soil = FP(m, FP(m, FP(m, z)) * yf);
+      /* pf_thaw carries permafrost's map, pf_refreeze_tp thawed permafrost's, pf_refreeze_soil
+       * the soil's map as of now (after the luc and npp additions above) */
+      const tmap_t soil_now = m->tm[TP_SOIL];
       double pc = FP(m, m->permafrost_c - pf_thaw);
+      if (T) tm_add(m, pc, &m->tm[TP_PERMAFROST], pf_refreeze_tp, &thawed_0);
       pc = FP(m, pc + pf_refreeze_tp);
+      if (T) tm_add(m, pc, &m->tm[TP_PERMAFROST], pf_refreeze_soil, &soil_now);
       pc = FP(m, pc + pf_refreeze_soil);
       m->permafrost_c = pc;
+      if (T) tm_add(m, m->thawed_permafrost_c, &m->tm[TP_THAWEDP], pf_thaw, &perm_0);
       tp = FP(m, m->thawed_permafrost_c + pf_thaw);
       tp = FP(m, tp - pf_refreeze_tp);
       m->thawed_permafrost_c = tp;
@@ -938,12 +1060,17 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
     double litter_flux = FP(m, m->veg_c * (0.035 * yf));
     double litter_fvd_flux = FP(m, litter_flux * p->f_litterd);
     double litter_fvs_flux = FP(m, litter_flux * (1 - p->f_litterd));
+    if (T) {
+      tm_add(m, m->detritus_c, &m->tm[TP_DET], litter_fvd_flux, &m->tm[TP_VEG]);
+      tm_add(m, m->soil_c, &m->tm[TP_SOIL], litter_fvs_flux, &m->tm[TP_VEG]);
+    }
     m->detritus_c = FP(m, m->detritus_c + litter_fvd_flux);
     m->soil_c = FP(m, m->soil_c + litter_fvs_flux);
     m->veg_c = FP(m, m->veg_c - litter_flux);
 
     /* detritus -> soil :514-521 */
     double detsoil_flux = FP(m, m->detritus_c * (0.6 * yf));
+    if (T) tm_add(m, m->soil_c, &m->tm[TP_SOIL], detsoil_flux, &m->tm[TP_DET]);
     m->soil_c = FP(m, m->soil_c + detsoil_flux);
     m->detritus_c = FP(m, m->detritus_c - detsoil_flux);
 
@@ -957,10 +1084,13 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
 
   /* :534-541 */
   double e = FP(m, m->earth_c - ffi_flux);
+  if (T) tm_add(m, e, &m->tm[TP_EARTH], ccs_flux, &atm_0);
   e = FP(m, e + ccs_flux);
   m->earth_c = e;
+  if (T) tm_add(m, m->atmos_c, &m->tm[TP_ATMOS], ffi_flux, &earth_0);
   double a = FP(m, m->atmos_c + ffi_flux);
   a = FP(m, a - ccs_flux);
+  if (T) tm_add(m, a, &m->tm[TP_ATMOS], oa_flux, &oa_map);
   a = FP(m, a + oa_flux);
   a = FP(m, a - ao_flux);
   m->atmos_c = a;
@@ -1474,11 +1604,39 @@ void ho_default_params(ho_params *p) {
   p->halo_H0[25] = 5.8;     /* CH3Br */
 }
 
+/* test hook for the fluxpool KATs: (a, fa, mask_a) + (b, fb, mask_b) -> fa, mask_a; returns the
+ * member status (HO_ERR_TRACKING if the private-constructor checks fail) */
+int ho_tm_add(double a, double *fa, uint32_t *mask_a, double b, const double *fb, uint32_t mask_b) {
+  member_t *m = (member_t *)calloc(1, sizeof(member_t));
+  tmap_t A, B;
+  memcpy(A.f, fa, sizeof A.f); A.mask = *mask_a;
+  memcpy(B.f, fb, sizeof B.f); B.mask = mask_b;
+  int status = HO_OK;
+  if (setjmp(m->fail)) status = m->status;
+  else tm_add(m, a, &A, b, &B);
+  memcpy(fa, A.f, sizeof A.f);
+  *mask_a = A.mask;
+  free(m);
+  return status;
+}
+
 static double *dalloc(int n) { return (double *)calloc((size_t)n, sizeof(double)); }
 
 int ho_run_member(const ho_params *p, const double *raw, int run_to, double *out, int nyears_cap,
                   int *fail_year, ho_counters *counters, ho_spinup_state *spin) {
+  return ho_run_member_tracked(p, raw, run_to, out, nyears_cap, fail_year, counters, spin, 9999,
+                               NULL, NULL);
+}
+
+int ho_run_member_tracked(const ho_params *p, const double *raw, int run_to, double *out,
+                          int nyears_cap, int *fail_year, ho_counters *counters,
+                          ho_spinup_state *spin, int tracking_date, double *track_frac,
+                          uint32_t *track_mask) {
   member_t *m = (member_t *)calloc(1, sizeof(member_t));
+  m->tracking_date = tracking_date; /* core.cpp:60: default 9999 = never */
+  if (track_frac)
+    for (size_t i = 0; i < (size_t)nyears_cap * HO_NPOOL * HO_NSRC; ++i) track_frac[i] = NAN;
+  if (track_mask) memset(track_mask, 0, (size_t)nyears_cap * HO_NPOOL * sizeof(uint32_t));
   const int nrow = p->end_year - p->start_year + 1;
   m->p = p; m->raw = raw; m->nrow = nrow;
   m->Tland_record = dalloc(nrow + 1);
@@ -1521,6 +1679,9 @@ int ho_run_member(const ho_params *p, const double *raw, int run_to, double *out
   m->cumulative_pf_ch4 = 0.0;
   m->has_been_run_before = 0;
   m->atmos_c = FP(m, p->C0 * PPMVCO2_TO_PGC);
+  for (int i = 0; i < 7; ++i) tm_init(&m->tm[i], i); /* every pool starts as {own name: 1} */
+  m->atmosphere_cpool = m->tm[TP_ATMOS];            /* simpleNbox-runtime.cpp:195 */
+  m->atmosphere_cpool_tracking = 0;
   m->masstot = 0.0;
   m->RH_ch4 = 0.0;
   m->t = p->start_year; /* solver prepareToRun, carbon-cycle-solver.cpp:126 */
@@ -1533,7 +1694,7 @@ int ho_run_member(const ho_params *p, const double *raw, int run_to, double *out
     int spunup = 0, step = 0, solver_in_spinup = 0;
     while (!spunup && ++step < p->max_spinup) {
       /* ocean run_spinup -> run(step): CO2 from atmos_c_ts (flat), SST = 0 */
-      ocean_run(m, snbox_CO2_conc(m), m->sst);
+      ocean_run(m, (double)step, snbox_CO2_conc(m), m->sst);
       if (!solver_in_spinup) {
         solver_in_spinup = 1;
         m->t = step - 1;
@@ -1605,7 +1766,7 @@ int ho_run_member(const ho_params *p, const double *raw, int run_to, double *out
                (0.0033 * row[HO_RAW_NMVOC]);
 
     /* ocean: CO2 = atmos_c_ts.get(y) = flat extrapolation of year y-1; SST current */
-    ocean_run(m, FP(m, m->co2_ts[r - 1] * PGC_TO_PPMVCO2), m->sst);
+    ocean_run(m, (double)y, FP(m, m->co2_ts[r - 1] * PGC_TO_PPMVCO2), m->sst);
     if (spin && y == p->start_year + 1) {
       spin->alk_HL = m->box[HL].chem.alk;
       spin->alk_LL = m->box[LL].chem.alk;
@@ -1615,7 +1776,11 @@ int ho_run_member(const ho_params *p, const double *raw, int run_to, double *out
       m->end_of_spinup_vegc = FP(m, 0.0 + m->veg_c);
       m->has_been_run_before = 1;
     }
+    /* tracking start (:215-220), then tell the ocean what the atmosphere is made of (:225) */
+    if ((double)y == (double)m->tracking_date) m->tracking = 1;
     m->Tland_record[r] = m->tas_land;
+    m->atmosphere_cpool = m->tm[TP_ATMOS];
+    m->atmosphere_cpool_tracking = m->tracking;
     /* solver */
     solver_run(m, (double)y, m->tas_land);
     m->co2_ts[r] = m->atmos_c;
@@ -1674,6 +1839,18 @@ int ho_run_member(const ho_params *p, const double *raw, int run_to, double *out
       OUT(HO_OUT_RH_CH4, m->RH_ch4);
       OUT(HO_OUT_TIMESTEPS, (double)m->timesteps);
 #undef OUT
+    }
+    /* what the CSVFluxPoolVisitor would print for this year (csv_tracking_visitor.cpp:80-137) */
+    if (m->tracking && r - 1 < nyears_cap) {
+      const tmap_t *maps[HO_NPOOL] = {&m->tm[0], &m->tm[1], &m->tm[2], &m->tm[3], &m->tm[4],
+                                      &m->tm[5], &m->tm[6], &m->box[HL].cmap, &m->box[LL].cmap,
+                                      &m->box[IO].cmap, &m->box[DO].cmap};
+      for (int k = 0; k < HO_NPOOL; ++k) {
+        if (track_frac)
+          memcpy(track_frac + ((size_t)(r - 1) * HO_NPOOL + k) * HO_NSRC, maps[k]->f,
+                 sizeof(double) * HO_NSRC);
+        if (track_mask) track_mask[(size_t)(r - 1) * HO_NPOOL + k] = maps[k]->mask;
+      }
     }
   }
 

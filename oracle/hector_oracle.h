@@ -19,6 +19,8 @@ extern "C" {
 #endif
 
 #define HO_NHALO 26
+#define HO_NPOOL 11 /* tracked pools */
+#define HO_NSRC 12  /* source names: the 11 pool names + "untracked" */
 
 /* raw scenario series: one dense value per integer year start..end, as the reference's
  * tseries::get(year) would return it (exact key, linear interpolation, or constant) */
@@ -77,7 +79,8 @@ enum {
   HO_ERR_NOROOT = 4,       /* newton bracket lost */
   HO_ERR_YEARFRACTION = 5, /* simpleNbox-runtime.cpp:275, ocean_component.cpp:665 */
   HO_ERR_CO2SARF = 6,      /* forcing_component.cpp:353 */
-  HO_ERR_STEPPER = 7       /* odeint: 500 failed step-size searches */
+  HO_ERR_STEPPER = 7,      /* odeint: 500 failed step-size searches */
+  HO_ERR_TRACKING = 8      /* fluxpool.hpp:105-112 source fractions out of range / tracking mismatch */
 };
 
 typedef struct {
@@ -130,6 +133,20 @@ void ho_default_params(ho_params *p);
 int ho_run_member(const ho_params *p, const double *raw, int run_to, double *out,
                   int nyears_cap, int *fail_year, ho_counters *counters,
                   ho_spinup_state *spin);
+
+/* Same with carbon tracking switched on in year `tracking_date` (core.cpp:228-235; 9999 =
+ * never).  For every year >= tracking_date:
+ *   track_frac [nyears_cap][HO_NPOOL][HO_NSRC]  source fractions of the 11 tracked pools
+ *   track_mask [nyears_cap][HO_NPOOL]           bit s set = source s is a key of the pool's map
+ * pool / source order: atmos_co2 earth_c veg_c detritus_c soil_c permafrost_c thawedp_c HL LL
+ * intermediate deep (+ source 11 "untracked").  Either pointer may be NULL. */
+int ho_run_member_tracked(const ho_params *p, const double *raw, int run_to, double *out,
+                          int nyears_cap, int *fail_year, ho_counters *counters,
+                          ho_spinup_state *spin, int tracking_date, double *track_frac,
+                          uint32_t *track_mask);
+
+/* fluxpool operator+ on explicit maps (unit-test hook, cf. src/unit-testing/test_tracking.cpp) */
+int ho_tm_add(double a, double *fa, uint32_t *mask_a, double b, const double *fb, uint32_t mask_b);
 
 /* carbonate chemistry spot check (ocean_csys.cpp:166-366): returns [H+]; fills 8 outputs
  * {pH, PCO2o, Tr, K0, CO3, TCO2o, HCO3, OmegaCa} and the Newton iteration count */

@@ -19,7 +19,10 @@ OUT_NAMES = ["CO2_concentration", "global_tas", "RF_tot", "RF_CO2", "heatflux", 
              "ocean_timesteps"]
 NOUT = len(OUT_NAMES)
 STATUS = {0: "OK", 1: "NEGATIVE", 2: "MASS", 3: "RETRIES", 4: "NOROOT", 5: "YEARFRACTION",
-          6: "CO2SARF", 7: "STEPPER"}
+          6: "CO2SARF", 7: "STEPPER", 8: "TRACKING"}
+TRACK_POOLS = ["atmos_co2", "earth_c", "veg_c", "detritus_c", "soil_c", "permafrost_c",
+               "thawedp_c", "HL", "LL", "intermediate", "deep"]
+TRACK_SOURCES = TRACK_POOLS + ["untracked"]
 
 
 class Params(C.Structure):
@@ -72,6 +75,9 @@ def lib():
                                     C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int),
                                     C.POINTER(Counters), C.POINTER(SpinState)]
         L.ho_run_member.restype = C.c_int
+        L.ho_run_member_tracked.argtypes = L.ho_run_member.argtypes + [
+            C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
+        L.ho_run_member_tracked.restype = C.c_int
         L.ho_csys.argtypes = [C.c_double] * 6 + [C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ho_csys.restype = C.c_double
         L.ho_gas_series.argtypes = [C.POINTER(Params), C.POINTER(C.c_double),
@@ -112,6 +118,25 @@ def run_member(raw, params=None, run_to=-1, **over):
                                       "earth", "alk_HL", "alk_LL", "spinup_steps")}
     sd["ocean"] = list(sp.ocean)
     return st, fy.value, out, cd, sd
+
+
+def run_member_tracked(raw, tracking_date, params=None, run_to=-1, **over):
+    """run_member with carbon tracking from `tracking_date`:
+    -> (status, fail_year, out, frac[nyears, 11, 12] (NaN before tracking), mask[nyears, 11])"""
+    p = params if params is not None else default_params()
+    for k, v in over.items():
+        setattr(p, k, v)
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    assert raw.shape == (p.end_year - p.start_year + 1, NRAW), raw.shape
+    ny = (p.end_year if run_to < 0 else run_to) - p.start_year
+    out = np.empty((NOUT, ny))
+    frac = np.empty((ny, len(TRACK_POOLS), len(TRACK_SOURCES)))
+    mask = np.zeros((ny, len(TRACK_POOLS)), dtype=np.uint32)
+    fy = C.c_int(0)
+    st = lib().ho_run_member_tracked(C.byref(p), _dp(raw), run_to, _dp(out), ny, C.byref(fy),
+                                     None, None, int(tracking_date), _dp(frac),
+                                     mask.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return st, fy.value, out, frac, mask
 
 
 def csys(Tbox, carbon, alk, volume, S=34.5, U=6.7):

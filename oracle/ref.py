@@ -26,6 +26,12 @@ PARAM_COMPONENT = {
 }
 
 
+# tracked pools (fluxpool names) and the universe of source names, fixed order
+TRACK_POOLS = ["atmos_co2", "earth_c", "veg_c", "detritus_c", "soil_c", "permafrost_c",
+               "thawedp_c", "HL", "LL", "intermediate", "deep"]
+TRACK_SOURCES = TRACK_POOLS + ["untracked"]
+
+
 def available():
     return os.path.exists(REF_SO)
 
@@ -53,6 +59,11 @@ def lib():
             f.argtypes = [C.c_int]
             f.restype = C.c_double
         L.ref_close.argtypes = [C.c_int]
+        L.ref_tracking_pool.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_char_p),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_int)]
+        L.ref_tracking_data.argtypes = [C.c_int, C.c_char_p, C.c_long]
+        L.ref_tracking_data.restype = C.c_long
         L.ref_counters.argtypes = [C.POINTER(C.c_uint64), C.c_int]
         L.ref_run_member.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p),
                                      C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.c_int,
@@ -115,6 +126,35 @@ class RefCore:
         self._chk(self.L.ref_fetch_component(self.h, component.encode(), var.encode(), date,
                                              C.byref(out)))
         return out.value
+
+    def tracking_state(self):
+        """-> (tracking?, value[11], frac[11, 12], present[11, 12]) at the current date, pools
+        in TRACK_POOLS order, sources in TRACK_SOURCES order (full precision)."""
+        ns = len(TRACK_SOURCES)
+        srcs = (C.c_char_p * ns)(*[s.encode() for s in TRACK_SOURCES])
+        val = np.zeros(len(TRACK_POOLS))
+        frac = np.zeros((len(TRACK_POOLS), ns))
+        pres = np.zeros((len(TRACK_POOLS), ns), dtype=np.int32)
+        on = True
+        for i, p in enumerate(TRACK_POOLS):
+            v = C.c_double()
+            rc = self.L.ref_tracking_pool(self.h, p.encode(), ns, srcs, C.byref(v),
+                                          frac[i].ctypes.data_as(C.POINTER(C.c_double)),
+                                          pres[i].ctypes.data_as(C.POINTER(C.c_int)))
+            if rc < 0:
+                raise RefError(self.L.ref_last_error().decode())
+            on = on and rc == 1
+            val[i] = v.value
+        return on, val, frac, pres
+
+    def tracking_csv(self):
+        """Core::getTrackingData() as text"""
+        n = self.L.ref_tracking_data(self.h, None, 0)
+        if n < 0:
+            raise RefError(self.L.ref_last_error().decode())
+        buf = C.create_string_buffer(n + 1)
+        self.L.ref_tracking_data(self.h, buf, n + 1)
+        return buf.value.decode()
 
     @property
     def start_date(self):

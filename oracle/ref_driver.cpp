@@ -7,12 +7,30 @@
  * src/rcpp_hector.cpp:31-365).  Used (a) to pin the C restatement (oracle/hector_oracle.c)
  * and the CUDA engine, (b) as the CPU baseline ("kind": "reference") in bench.py.
  */
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
 #include <string>
+#include <unordered_map>
+#include <vector>
 
+/* The tracked pools (fluxpool source maps) are private members read only by the friend class
+ * CSVFluxPoolVisitor, whose CSV carries six significant digits.  To pin the tracking arithmetic
+ * at full precision this TEST driver -- and only this translation unit; the reference objects
+ * are compiled unmodified -- reads them directly.  Access specifiers do not change layout. */
+#define private public
+#define protected public
 #include "hector.hpp"
+#include "ocean_component.hpp"
+#include "simpleNbox.hpp"
+#undef private
+#undef protected
 #include "imodel_component.hpp"
 #include "ini_to_core_reader.hpp"
 #include "logger.hpp"
@@ -157,6 +175,70 @@ int ref_fetch_component(int h, const char *component, const char *var, double da
                                message_data(date < 0 ? Core::undefinedIndex() : date));
     *out = v.value(v.units());
     return 0;
+  } catch (h_exception &e) {
+    return fail(std::string("h_exception: ") + e.what());
+  } catch (std::exception &e) {
+    return fail(std::string("exception: ") + e.what());
+  }
+}
+
+/* Core::getTrackingData() (core.cpp:199-209): the CSVFluxPoolVisitor's buffered rows
+ * "year,component,pool_name,pool_value,pool_units,source_name,source_fraction" for every year
+ * >= trackingDate.  Copies at most cap-1 bytes; returns the full length (call again with a
+ * larger buffer if it is >= cap), or -1. */
+long ref_tracking_data(int h, char *buf, long cap) {
+  try {
+    Core *core = Core::getcore(h);
+    if (!core) return fail("bad handle");
+    const std::string s = core->getTrackingData();
+    if (buf && cap > 0) {
+      const long n = (long)s.size() < cap - 1 ? (long)s.size() : cap - 1;
+      memcpy(buf, s.data(), (size_t)n);
+      buf[n] = 0;
+    }
+    return (long)s.size();
+  } catch (h_exception &e) {
+    return fail(std::string("h_exception: ") + e.what());
+  } catch (std::exception &e) {
+    return fail(std::string("exception: ") + e.what());
+  }
+}
+
+/* Full-precision view of one tracked pool at the core's current date.  pool / source names:
+ * atmos_co2 earth_c veg_c detritus_c soil_c permafrost_c thawedp_c HL LL intermediate deep
+ * (+ source "untracked").  frac[i] / present[i] follow the order of `sources` (n of them);
+ * a source missing from the pool's map reports present 0, frac 0.  Returns 1 if the pool is
+ * tracking, 0 if not, -1 on error. */
+int ref_tracking_pool(int h, const char *pool, int n, const char **sources, double *value,
+                      double *frac, int *present) {
+  try {
+    Core *core = Core::getcore(h);
+    if (!core) return fail("bad handle");
+    SimpleNbox *nb = dynamic_cast<SimpleNbox *>(core->getComponentByName(SIMPLENBOX_COMPONENT_NAME));
+    OceanComponent *oc = dynamic_cast<OceanComponent *>(core->getComponentByName(OCEAN_COMPONENT_NAME));
+    if (!nb || !oc) return fail("components not found");
+    const std::string p(pool);
+    fluxpool x;
+    if (p == "atmos_co2") x = nb->atmos_c;
+    else if (p == "earth_c") x = nb->earth_c;
+    else if (p == "veg_c") x = nb->veg_c.at(SNBOX_DEFAULT_BIOME);
+    else if (p == "detritus_c") x = nb->detritus_c.at(SNBOX_DEFAULT_BIOME);
+    else if (p == "soil_c") x = nb->soil_c.at(SNBOX_DEFAULT_BIOME);
+    else if (p == "permafrost_c") x = nb->permafrost_c.at(SNBOX_DEFAULT_BIOME);
+    else if (p == "thawedp_c") x = nb->thawed_permafrost_c.at(SNBOX_DEFAULT_BIOME);
+    else if (p == "HL") x = oc->surfaceHL.get_carbon();
+    else if (p == "LL") x = oc->surfaceLL.get_carbon();
+    else if (p == "intermediate") x = oc->inter.get_carbon();
+    else if (p == "deep") x = oc->deep.get_carbon();
+    else return fail("unknown pool " + p);
+    *value = x.value(U_PGC);
+    const std::unordered_map<std::string, double> m = x.get_tracking_map();
+    for (int i = 0; i < n; ++i) {
+      auto it = m.find(sources[i]);
+      present[i] = it != m.end();
+      frac[i] = present[i] ? it->second : 0.0;
+    }
+    return x.tracking ? 1 : 0;
   } catch (h_exception &e) {
     return fail(std::string("h_exception: ") + e.what());
   } catch (std::exception &e) {

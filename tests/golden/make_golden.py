@@ -10,6 +10,10 @@ what travels to the GPU box.
   ref_runs.npz        known-answer trajectories produced by the UNMODIFIED reference
                       (oracle/_ref) for a set of parameter vectors / scenarios, incl. the
                       expected-failure member.
+  ref_tracking.npz    carbon-tracking known answers from the UNMODIFIED reference: source
+                      fractions + key masks of the 11 tracked pools at selected years (read at
+                      full precision through oracle/ref_driver.cpp), and the reference's own
+                      6-digit getTrackingData() CSV for one short run.
 """
 import csv
 import os
@@ -188,5 +192,62 @@ def main():
                         values=np.array(outs))
 
 
+TRACK_CASES = [  # (name, scenario, trackingDate, params)
+    ("ssp245_1750", "ssp245", 1750, {}),
+    ("ssp585_1850_pert", "ssp585", 1850, dict(S=4.2, q10_rh=2.0, beta=0.4, diff=1.8)),
+    ("ssp119_2000", "ssp119", 2000, {}),
+    ("ssp245_1750_corner_hi", "ssp245", 1750, dict(S=6.0, q10_rh=3.5, beta=1.0, diff=3.0)),
+]
+
+
+def tracking_years(tdate):
+    ys = set(range(tdate, tdate + 4)) | set(range(tdate + 10 - tdate % 10, 2301, 10)) | {2300}
+    return sorted(y for y in ys if y <= 2300)
+
+
+def make_tracking():
+    from oracle import ref
+    names, scns, tdates, pnames, pvals = [], [], [], [], []
+    years, fracs, masks, values = [], [], [], []
+    for name, scn, tdate, params in TRACK_CASES:
+        c = ref.RefCore(os.path.join(REF, "inst/input/hector_%s.ini" % scn))
+        c.setdata("core", "trackingDate", tdate)
+        for k, v in params.items():
+            c.setdata(ref.PARAM_COMPONENT[k], k, v)
+        c.prepare()
+        ys = tracking_years(tdate)
+        Y = np.full(64, -1); F = np.full((64, 11, 12), np.nan); K = np.zeros((64, 11), np.uint32)
+        V = np.full((64, 11), np.nan)
+        for i, y in enumerate(ys):
+            c.run(y)
+            on, v, f, pres = c.tracking_state()
+            assert on
+            Y[i] = y; F[i] = f; V[i] = v
+            K[i] = (pres.astype(np.uint32) << np.arange(12, dtype=np.uint32)).sum(1)
+        c.close()
+        print(name, len(ys), "years")
+        names.append(name); scns.append(scn); tdates.append(tdate)
+        pnames.append(",".join(params.keys()))
+        pvals.append(np.array(list(params.values()) + [np.nan] * (8 - len(params))))
+        years.append(Y); fracs.append(F); masks.append(K); values.append(V)
+    # the reference's own output format, one short run
+    c = ref.RefCore(os.path.join(REF, "inst/input/hector_ssp245.ini"))
+    c.setdata("core", "trackingDate", 1750)
+    c.prepare()
+    c.run(1755)
+    csv_text = c.tracking_csv()
+    c.close()
+    np.savez_compressed(os.path.join(OUT, "ref_tracking.npz"), names=np.array(names),
+                        scenarios=np.array(scns), tracking_dates=np.array(tdates),
+                        param_names=np.array(pnames), param_values=np.array(pvals),
+                        years=np.array(years), frac=np.array(fracs), mask=np.array(masks),
+                        pool_values=np.array(values), pools=np.array(ref.TRACK_POOLS),
+                        sources=np.array(ref.TRACK_SOURCES), csv_1750_1755=np.array(csv_text))
+
+
 if __name__ == "__main__":
-    main()
+    if "tracking" in sys.argv[1:]:
+        make_tracking()
+    else:
+        main()
+        make_tracking()

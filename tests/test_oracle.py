@@ -126,3 +126,64 @@ def test_extension_to_2500_kat():
     assert abs(out[0][2300 - 1746] - 1272.74969152107) < 1e-9
     assert abs(out[0][-1] - 1102.05842133113) < 1e-9
     assert abs(out[1][-1] - 6.60192887012203) < 1e-11
+
+
+@pytest.mark.parametrize("case", util.ref_tracking(), ids=lambda c: c["name"])
+def test_tracking_against_reference(case):
+    """carbon tracking (fluxpool.hpp:197-257 through stashCValues / oceanbox): source fractions
+    and key sets of the 11 tracked pools equal the unmodified reference's at every committed
+    year (observed: bit-identical), nothing is reported before trackingDate, and switching
+    tracking on leaves the trajectories bit-identical."""
+    raw = util.scenarios()[case["scenario"]]
+    st, fy, out, frac, mask = port.run_member_tracked(raw, case["tracking_date"],
+                                                      **case["params"])
+    assert st == 0
+    st0, _, out0, _, _ = port.run_member(raw, **case["params"])
+    assert st0 == 0 and np.array_equal(out, out0)
+    first = case["tracking_date"] - 1746
+    assert np.isnan(frac[:first]).all() and not mask[:first].any()
+    idx = case["years"] - 1746
+    assert np.array_equal(mask[idx], case["mask"])
+    assert np.abs(frac[idx] - case["frac"]).max() <= 1e-15
+    assert np.abs(frac[first:].sum(axis=2) - 1.0).max() < 1e-12
+    # pool totals that go with the fractions
+    names = ["atmos_co2", "earth_c", "veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c",
+             "HL_ocean_c", "LL_ocean_c", "IO_ocean_c", "DO_ocean_c"]
+    for k, v in enumerate(names):
+        assert np.allclose(out[port.OUT_NAMES.index(v)][idx], case["pool_values"][:, k],
+                           rtol=1e-13, atol=1e-13), v
+
+
+def test_tracking_fluxpool_kats():
+    """src/unit-testing/test_tracking.cpp:65-315 restated on the oracle's map algebra: adding a
+    flux mixes source fractions by mass; subtraction and scaling keep them; a zero total splits
+    evenly over the keys."""
+    import ctypes as C
+    L = port.lib()
+    L.ho_tm_add.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_double,
+                            C.POINTER(C.c_double), C.c_uint32]
+    L.ho_tm_add.restype = C.c_int
+
+    def add(a, fa, ma, b, fb, mb):
+        fa = np.array(fa + [0.0] * (12 - len(fa)))
+        fb = np.array(fb + [0.0] * (12 - len(fb)))
+        m = C.c_uint32(ma)
+        rc = L.ho_tm_add(a, fa.ctypes.data_as(C.POINTER(C.c_double)), C.byref(m), b,
+                         fb.ctypes.data_as(C.POINTER(C.c_double)), mb)
+        return rc, fa, m.value
+
+    # test_tracking.cpp: c1 = 1 Pg from "a", c2 = 2 Pg from "b" -> 1/3, 2/3
+    rc, f, m = add(1.0, [1.0], 0b01, 2.0, [0.0, 1.0], 0b10)
+    assert rc == 0 and m == 0b11 and f[0] == 1.0 / 3.0 and f[1] == 2.0 / 3.0
+    # adding more of the same source keeps fractions
+    rc, f, m = add(3.0, [1.0 / 3.0, 2.0 / 3.0], 0b11, 3.0, [1.0 / 3.0, 2.0 / 3.0], 0b11)
+    assert rc == 0 and abs(f[0] - 1.0 / 3.0) < 1e-16 and abs(f[1] - 2.0 / 3.0) < 1e-16
+    # zero total: 1/n over the union of keys (fluxpool.hpp:248-250)
+    rc, f, m = add(0.0, [1.0], 0b001, 0.0, [0.0, 0.0, 1.0], 0b100)
+    assert rc == 0 and m == 0b101 and f[0] == 0.5 and f[2] == 0.5 and f[1] == 0.0
+    # a key with fraction 0 stays a key
+    rc, f, m = add(5.0, [1.0, 0.0], 0b11, 0.0, [0.0, 0.0, 1.0], 0b100)
+    assert rc == 0 and m == 0b111 and f[0] == 1.0 and f[1] == 0.0 and f[2] == 0.0
+    # fractions outside [0, 1] are rejected like the private constructor does (:105-112)
+    rc, f, m = add(1.0, [1.5], 0b1, 1.0, [1.0], 0b1)
+    assert rc != 0

@@ -42,6 +42,26 @@ def ref_runs():
     return cases
 
 
+def ref_tracking():
+    """carbon-tracking known answers of the unmodified reference (tests/golden/make_golden.py)"""
+    z = np.load(os.path.join(GOLDEN, "ref_tracking.npz"))
+    cases = []
+    for i, name in enumerate(z["names"]):
+        pn = str(z["param_names"][i])
+        keys = pn.split(",") if pn else []
+        n = int((z["years"][i] >= 0).sum())
+        cases.append(dict(name=str(name), scenario=str(z["scenarios"][i]),
+                          tracking_date=int(z["tracking_dates"][i]),
+                          params={k: float(z["param_values"][i][j]) for j, k in enumerate(keys)},
+                          years=z["years"][i][:n], frac=z["frac"][i][:n], mask=z["mask"][i][:n],
+                          pool_values=z["pool_values"][i][:n]))
+    return cases
+
+
+def ref_tracking_csv():
+    return str(np.load(os.path.join(GOLDEN, "ref_tracking.npz"))["csv_1750_1755"])
+
+
 # natural scale below which a relative error is meaningless (outputs that pass through zero
 # or are differences of large pools); CO2 / Tgav floors are SURVEY.md section 8(d)'s
 FLOOR = {"global_tas": 0.01, "CO2_concentration": 1.0, "sst": 0.01, "land_tas": 0.01,
