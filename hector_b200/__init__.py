@@ -7,7 +7,7 @@ sm_100a CUDA); there is no CPU fallback.
 """
 from ._capi import HxError, lib, lib_path  # noqa: F401
 from .ensemble import (Ensemble, OUTPUT_VARIABLES, PARAMETERS, RAW_SERIES,  # noqa: F401
-                       load_scenario_tables)
+                       TRACK_POOLS, TRACK_POOL_OUTPUT, TRACK_SOURCES, load_scenario_tables)
 
 __all__ = ["Ensemble", "HxError", "OUTPUT_VARIABLES", "PARAMETERS", "RAW_SERIES",
-           "load_scenario_tables", "lib", "lib_path"]
+           "TRACK_POOLS", "TRACK_POOL_OUTPUT", "TRACK_SOURCES", "load_scenario_tables", "lib", "lib_path"]

@@ -70,6 +70,25 @@ __global__ void k_fetch_transpose(double *out, const double *src, const int32_t 
     if (k < n_dates && m < M) out[(size_t)m * n_dates + k] = tile[threadIdx.x][j];
   }
 }
+/* out[m_api][k] = src[k][dev_of_api[m_api]] for 32-bit words (tracking key masks) */
+__global__ void k_fetch_masks(uint32_t *out, const uint32_t *src, const int32_t *dev_of_api, int nk,
+                              int M, size_t Mpad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * nk) return;
+  const int m = i / nk, k = i % nk;
+  out[i] = src[(size_t)k * Mpad + dev_of_api[m]];
+}
+/* live tracking maps of the first HX_NPOOL slots: out[m_api][q] = T[tile][q][lane] */
+__global__ void k_gather_track(double *out, uint32_t *out_mask, const double *T, const uint32_t *TK,
+                               const int32_t *dev_of_api, int M) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nq = HX_NPOOL * HX_NSRC;
+  if (i >= M * nq) return;
+  const int m = i / nq, q = i % nq;
+  const int dm = dev_of_api[m];
+  out[i] = T[HX_TILED(q, dm, TS_COUNT * HX_NSRC)];
+  if (q < HX_NPOOL) out_mask[m * HX_NPOOL + q] = TK[HX_TILED(q, dm, TS_COUNT)];
+}
 /* copy member `src_m`'s state column into every active member (shared spin-up, E-7) */
 __global__ void k_broadcast_state(double *S, int32_t *spinup_steps, int32_t *status,
                                   int32_t *fail_year, int src_m, int n_state, size_t Mpad) {
@@ -101,6 +120,8 @@ struct Engine {
   bool pvec_on_device_only[PI_COUNT];
   double baseyear = 1750, UC_N2O = 4.8, TN2O0 = 132;
   int max_spinup = 2000;
+  int tracking_date = 9999, track_every = 1; /* [core] trackingDate; recording stride in years */
+  std::vector<int> track_years;              /* recorded years, slot order */
   double halo_tau[HX_NHALO], halo_rho[HX_NHALO], halo_delta[HX_NHALO], halo_H0[HX_NHALO],
       halo_mm[HX_NHALO];
   std::vector<int> out_sel;                  /* OUT_* ids in slot order */
@@ -119,6 +140,8 @@ struct Engine {
           *d_fail_year = nullptr, *d_spinup_steps = nullptr, *d_yidx = nullptr;
   unsigned long long *d_counters = nullptr;
   unsigned *d_sched = nullptr;
+  double *d_T = nullptr, *d_TO = nullptr;
+  uint32_t *d_TK = nullptr, *d_TOK = nullptr;
   size_t stage_bytes = 0, yidx_cap = 0;
   double *h_pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -208,13 +231,15 @@ struct Engine {
   void free_device() {
     void *ptrs[] = {d_P, d_S, d_S_snap, d_D, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
                     d_block_scen, d_status, d_status_snap, d_status_post, d_fail_year, d_spinup_steps, d_yidx,
-                    d_counters, d_dev_of_api, d_sched};
+                    d_counters, d_dev_of_api, d_sched, d_T, d_TO, d_TK, d_TOK};
     for (void *p : ptrs)
       if (p) cudaFree(p);
     d_P = d_S = d_S_snap = d_D = d_ker = d_conv = d_sst = d_tland = d_out = d_scen = d_stage = nullptr;
     d_block_scen = d_status = d_status_snap = d_status_post = d_fail_year = d_spinup_steps = d_yidx = nullptr;
     d_counters = nullptr;
     d_sched = nullptr;
+    d_T = d_TO = nullptr;
+    d_TK = d_TOK = nullptr;
     d_dev_of_api = nullptr;
     stage_bytes = 0;
     yidx_cap = 0;
@@ -264,6 +289,7 @@ struct Engine {
     } else {
       CUDA_TRY(hx::launch_spinup(d, C, stream));
     }
+    if (d_T) CUDA_TRY(hx::launch_track_init(d, stream));
     CUDA_TRY(cudaMemcpyAsync(d_S_snap, d_S, (size_t)SI_COUNT * Mpad * sizeof(double),
                              cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(d_status_post, d_status, (size_t)Mpad * sizeof(int32_t),
@@ -401,6 +427,7 @@ int hx_set_member_scenario(hx_handle h, const int32_t *scen, int32_t n) {
 }
 
 static int set_special_scalar(hx_engine *h, const char *name, double v) {
+  if (!strcmp(name, "trackingDate")) { h->tracking_date = (int)v; return 1; }
   if (!strcmp(name, "baseyear")) { h->baseyear = v; return 1; }
   if (!strcmp(name, "max_spinup")) { h->max_spinup = (int)v; return 1; }
   if (!strcmp(name, "UC_N2O")) { h->UC_N2O = v; return 1; }
@@ -581,6 +608,21 @@ int hx_prepare(hx_handle h) {
   }
   C.rk_grow_max = 9.0 / 10.0 * std::pow(std::pow(5.0, -5.0), -1.0 / 5.0);
 
+  /* carbon tracking: recorded years */
+  const bool tracking = h->tracking_date <= h->cfg.end_year;
+  h->track_years.clear();
+  if (tracking) {
+    if (h->tracking_date <= h->cfg.start_year)
+      return fail(HX_ERR_ARG, "trackingDate must lie in (startDate, endDate]"); /* core.cpp:228-235 */
+    if (h->track_every > 0)
+      for (int y = h->tracking_date; y <= h->cfg.end_year; y += h->track_every) h->track_years.push_back(y);
+    if (h->track_years.empty() || h->track_years.back() != h->cfg.end_year)
+      h->track_years.push_back(h->cfg.end_year);
+  }
+  C.tracking_date = tracking ? h->tracking_date : 0x7fffffff;
+  C.track_every = h->track_every;
+  C.track_nrec = (int)h->track_years.size();
+
   /* device scenario tables */
   std::vector<double> tab((size_t)h->nscen * nrow * SC_STRIDE, 0.0);
   for (int s = 0; s < h->nscen; ++s) {
@@ -615,7 +657,12 @@ int hx_prepare(hx_handle h) {
       cudaMalloc(&h->d_spinup_steps, Mp * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc(&h->d_counters, HX_NCOUNTERS * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMalloc(&h->d_sched, (block_scen.size() + 1) * sizeof(unsigned)) != cudaSuccess ||
-      cudaMalloc(&h->d_dev_of_api, (size_t)M * sizeof(int32_t)) != cudaSuccess) {
+      cudaMalloc(&h->d_dev_of_api, (size_t)M * sizeof(int32_t)) != cudaSuccess ||
+      (tracking &&
+       (cudaMalloc(&h->d_T, (size_t)TS_COUNT * HX_NSRC * Mp * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_TK, (size_t)TS_COUNT * Mp * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&h->d_TO, h->track_years.size() * HX_NPOOL * HX_NSRC * Mp * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_TOK, h->track_years.size() * HX_NPOOL * Mp * sizeof(uint32_t)) != cudaSuccess))) {
     cudaError_t e = cudaGetLastError();
     h->free_device();
     return fail(HX_ERR_CUDA, (std::string("device allocation failed: ") + cudaGetErrorString(e)).c_str());
@@ -644,6 +691,7 @@ int hx_prepare(hx_handle h) {
   d.sst_hist = h->d_sst; d.tland_hist = h->d_tland; d.out = h->d_out; d.scen = h->d_scen;
   d.block_scen = h->d_block_scen; d.status = h->d_status; d.fail_year = h->d_fail_year;
   d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters; d.sched = h->d_sched;
+  d.T = h->d_T; d.TK = h->d_TK; d.TO = h->d_TO; d.TOK = h->d_TOK;
   for (int i = 0; i < OUT_COUNT; ++i) d.out_slot[i] = -1;
   for (int s = 0; s < nsel; ++s) d.out_slot[h->out_sel[s]] = s;
 
@@ -675,6 +723,7 @@ int hx_reset(hx_handle h) {
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(h->d_status, h->d_status_post, (size_t)h->Mpad * sizeof(int32_t),
                         cudaMemcpyDeviceToDevice, h->stream);
+  if (e == cudaSuccess && h->d_T) e = hx::launch_track_init(h->d, h->stream);
   if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
   h->cur_row = 0;
   return HX_OK;
@@ -761,6 +810,78 @@ int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates
                         cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_fetch: ") + cudaGetErrorString(e));
+  return HX_OK;
+}
+
+int hx_set_tracking(hx_handle h, int32_t tracking_date, int32_t record_every) {
+  if (!h) return HX_ERR_ARG;
+  if (h->prepared) return h->fail(HX_ERR_STATE, "tracking must be configured before hx_prepare");
+  if (record_every < 0) return h->fail(HX_ERR_ARG, "record_every must be >= 0");
+  h->tracking_date = tracking_date;
+  h->track_every = record_every;
+  return HX_OK;
+}
+
+int hx_fetch_tracking(hx_handle h, double date, double *frac, uint32_t *mask) {
+  if (!h || !frac) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_fetch_tracking before hx_prepare");
+  if (!h->d_T) return h->fail(HX_ERR_STATE, "carbon tracking is off (no trackingDate set)");
+  const int y = (int)date;
+  const int cur = h->cfg.start_year + h->cur_row;
+  if (y < h->tracking_date || y > cur)
+    return h->fail(HX_ERR_ARG, "date outside [trackingDate, current date]");
+  cudaSetDevice(h->cfg.device);
+  const int nq = HX_NPOOL * HX_NSRC;
+  const size_t fbytes = (size_t)h->M * nq * sizeof(double);
+  const size_t mbytes = (size_t)h->M * HX_NPOOL * sizeof(uint32_t);
+  int rc = h->ensure_stage(fbytes + mbytes);
+  if (rc) return rc;
+  double *sf = h->d_stage;
+  uint32_t *sm = (uint32_t *)((char *)h->d_stage + fbytes);
+  cudaStream_t st = h->stream;
+  cudaError_t e = cudaSuccess;
+  int rec = -1;
+  for (size_t i = 0; i < h->track_years.size(); ++i)
+    if (h->track_years[i] == y) rec = (int)i;
+  if (rec >= 0) {
+    std::vector<int32_t> yidx(nq);
+    for (int k = 0; k < nq; ++k) yidx[k] = k;
+    if ((size_t)nq > h->yidx_cap) {
+      if (h->d_yidx) cudaFree(h->d_yidx);
+      h->d_yidx = nullptr;
+      if (cudaMalloc(&h->d_yidx, (size_t)nq * sizeof(int32_t)) != cudaSuccess)
+        return h->fail(HX_ERR_CUDA, "cudaMalloc yidx");
+      h->yidx_cap = nq;
+    }
+    cudaMemcpyAsync(h->d_yidx, yidx.data(), (size_t)nq * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    dim3 grid((h->M + 31) / 32, (nq + 31) / 32), block(32, 8);
+    k_fetch_transpose<<<grid, block, 0, st>>>(sf, h->d_TO + (size_t)rec * nq * h->Mpad, h->d_yidx,
+                                             h->d_dev_of_api, nq, h->M, (size_t)h->Mpad);
+    k_fetch_masks<<<(h->M * HX_NPOOL + 255) / 256, 256, 0, st>>>(
+        sm, h->d_TOK + (size_t)rec * HX_NPOOL * h->Mpad, h->d_dev_of_api, HX_NPOOL, h->M,
+        (size_t)h->Mpad);
+    e = cudaGetLastError();
+  } else if (y == cur) {
+    /* not a recorded year, but the live maps are this year's */
+    k_gather_track<<<(h->M * nq + 255) / 256, 256, 0, st>>>(sf, sm, h->d_T, h->d_TK,
+                                                           h->d_dev_of_api, h->M);
+    e = cudaGetLastError();
+  } else {
+    return h->fail(HX_ERR_ARG, "year was not recorded (see hx_set_tracking record_every)");
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(frac, sf, fbytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && mask) e = cudaMemcpyAsync(mask, sm, mbytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_fetch_tracking: ") + cudaGetErrorString(e));
+  /* failed members report NaN like every other output */
+  std::vector<int32_t> stt(h->M), fy(h->M);
+  rc = hx_member_status(h, stt.data(), fy.data(), h->M);
+  if (rc) return rc;
+  for (int i = 0; i < h->M; ++i)
+    if (stt[i] > 0 && fy[i] <= y) {
+      for (int k = 0; k < nq; ++k) frac[(size_t)i * nq + k] = NAN;
+      if (mask) for (int k = 0; k < HX_NPOOL; ++k) mask[(size_t)i * HX_NPOOL + k] = 0;
+    }
   return HX_OK;
 }
 

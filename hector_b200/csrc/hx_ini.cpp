@@ -376,6 +376,10 @@ extern "C" int hx_create_from_ini(const char *const *ini_paths, int32_t n_inis, 
     hx_destroy(h);
     return code;
   };
+  if (in[0].tracking_date < 9999) {
+    rc = hx_set_tracking(h, (int32_t)in[0].tracking_date, 1);
+    if (rc) return bail(rc);
+  }
   for (std::map<std::string, double>::const_iterator it = in[0].scalars.begin();
        it != in[0].scalars.end(); ++it) {
     rc = hx_set_param_scalar(h, it->first.c_str(), it->second);

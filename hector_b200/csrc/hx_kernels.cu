@@ -74,6 +74,8 @@ __device__ __forceinline__ void fence_proxy_async() {
 struct Bases {
   const double *P;
   double *S, *D, *ker, *sst, *tland, *conv;
+  double *T;     /* carbon-tracking maps (null when tracking is off) */
+  uint32_t *TK;
 };
 __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, int m) {
   const size_t tile = (size_t)(m / HX_BLOCK), ln = (size_t)(m % HX_BLOCK);
@@ -85,6 +87,8 @@ __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, in
   b.conv = d.conv + tile * (size_t)HX_SLAB_YEARS * HX_BLOCK + ln;
   b.sst = d.sst_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
   b.tland = d.tland_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
+  b.T = d.T ? d.T + tile * (size_t)(TS_COUNT * HX_NSRC) * HX_BLOCK + ln : nullptr;
+  b.TK = d.TK ? d.TK + tile * (size_t)TS_COUNT * HX_BLOCK + ln : nullptr;
   return b;
 }
 #define PAR(i) __ldg(BS.P + (i) * HX_BLOCK)
@@ -108,6 +112,7 @@ __device__ __forceinline__ void load_member(const Bases &BS, Member &mb) {
   mb.solver_dt = STATE(SI_SOLVER_DT);
   mb.status = 0; mb.neg = false; mb.timesteps = 0;
   mb.pco2HL = mb.pco2LL = 0.0; mb.gHL = mb.gLL = 0.0; mb.luc_e = mb.luc_u = 0.0;
+  mb.T = BS.T; mb.TK = BS.TK; mb.trk = false; mb.trk_bad = false;
 }
 
 __device__ __forceinline__ void store_member(const Bases &BS, const Member &mb) {
@@ -371,7 +376,7 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
       mb.S[SI_X_NPPLUC * HX_TILE] = (mb.S[SI_EOS_VEGC * HX_TILE] - mb.S[SI_CUM_LUC_VA * HX_TILE]) / mb.S[SI_EOS_VEGC * HX_TILE];
       const double o0 = mb.atmos, o1 = mb.veg, o2 = mb.det, o3 = mb.soil, o4 = mb.perm,
                    o5 = mb.thawed, o6 = total_ocean(mb), o7 = mb.earth;
-      solver_year<true>(mb, C, p, ck, &rk[0][threadIdx.x], HX_BLOCK, (double)(step - 1), (double)step, true, w);
+      solver_year<true, false>(mb, C, p, ck, &rk[0][threadIdx.x], HX_BLOCK, (double)(step - 1), (double)step, true, w);
       if (mb.status) break;
       double mx = fabs(mb.atmos - o0);
       mx = fmax(mx, fabs(mb.veg - o1)); mx = fmax(mx, fabs(mb.det - o2));
@@ -473,7 +478,9 @@ __device__ __forceinline__ void conv_prepass(const double *__restrict__ sst,
 }
 
 /* ======================================================================================== */
-/* the yearly coupled step, rows r0+1 .. r1 (row = year - start_year) */
+/* the yearly coupled step, rows r0+1 .. r1 (row = year - start_year).  TRACK = carbon tracking
+ * compiled in (a second instantiation: the plain kernel carries none of its code). */
+template <bool TRACK>
 __global__ void __launch_bounds__(HX_BLOCK, HX_RUN_MIN_CTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   /* dynamic shared memory (> 48 KB): scenario slabs | row 0 | chemistry constants | RK stages */
@@ -607,6 +614,13 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           const double tland = STATE(SI_TLAND);
           const double wf = LP_WF(p);
           BS.tland[(size_t)r * Hs] = tland; /* Tland_record[y] = land tas of year y-1 */
+          if (TRACK) {
+            /* tracking starts in year tracking_date (simpleNbox-runtime.cpp:215-220,
+             * ocean_component.cpp:358-366); the ocean gets this year's copy of the atmosphere's
+             * source map (set_atmosphere_sources, :225) */
+            mb.trk = (y >= C.tracking_date);
+            if (mb.trk) tm_copy(mb, TS_ATM_CPOOL, TS_ATMOS);
+          }
           mb.luc_e = scm1[SC_LUC_E]; mb.luc_u = scm1[SC_LUC_U];
           mb.S[SI_X_FFI * HX_TILE] = scm1[SC_FFI]; mb.S[SI_X_DACCS * HX_TILE] = scm1[SC_DACCS];
           mb.neg |= (mb.luc_e < 0.0) | (mb.luc_u < 0.0) | (mb.S[SI_X_FFI * HX_TILE] < 0.0) | (mb.S[SI_X_DACCS * HX_TILE] < 0.0);
@@ -635,7 +649,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         }
 
         /* --- CarbonCycleSolver::run --- */
-        solver_year<false>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
+        solver_year<false, TRACK>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
         if (mb.status) {
           d.status[m] = mb.status;
           d.fail_year[m] = y;
@@ -739,6 +753,22 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         }
         ++years_done;
 
+        /* --- what the CSVFluxPoolVisitor would print this year (csv_tracking_visitor.cpp:
+         * 80-137): source fractions and key masks of the 11 tracked pools --- */
+        if (TRACK && mb.trk) {
+          const int k = y - C.tracking_date;
+          int rec = -1;
+          if (C.track_every > 0 && k % C.track_every == 0) rec = k / C.track_every;
+          else if (y == C.end_year) rec = C.track_nrec - 1;
+          if (rec >= 0) {
+            double *to = d.TO + (size_t)rec * (HX_NPOOL * HX_NSRC) * Mp + m;
+            for (int q = 0; q < HX_NPOOL * HX_NSRC; ++q)
+              to[(size_t)q * Mp] = mb.T[(size_t)q * HX_TILE];
+            uint32_t *tk = d.TOK + (size_t)rec * HX_NPOOL * Mp + m;
+            for (int q = 0; q < HX_NPOOL; ++q) tk[(size_t)q * Mp] = mb.TK[q * HX_TILE];
+          }
+        }
+
         /* --- outputs (record_state / getData of each component) --- */
         const int yi = r - 1;
 #define EMIT(id, val)                                                              \
@@ -796,6 +826,24 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
   flush_work(d, w, years_done, failed);
 }
 
+/* every map slot back to its initial state: pools and their CarbonAdditions are {own name: 1}
+ * (fluxpool::set), the ocean's atmosphere copy is the atmosphere's, scratch slots are empty */
+__global__ void hx_track_init_kernel(const __grid_constant__ HxDev d) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= d.Mpad) return;
+  const size_t tile = (size_t)(m / HX_BLOCK), ln = (size_t)(m % HX_BLOCK);
+  double *T = d.T + tile * (size_t)(TS_COUNT * HX_NSRC) * HX_BLOCK + ln;
+  uint32_t *K = d.TK + tile * (size_t)TS_COUNT * HX_BLOCK + ln;
+  for (int i = 0; i < TS_COUNT; ++i) {
+    int self = -1;
+    if (i < HX_NPOOL) self = i;
+    else if (i == TS_ATM_CPOOL) self = TS_ATMOS;
+    else if (i >= TS_ADD_HL) self = TS_HL + (i - TS_ADD_HL);
+    for (int s = 0; s < HX_NSRC; ++s) T[((size_t)i * HX_NSRC + s) * HX_BLOCK] = (s == self) ? 1.0 : 0.0;
+    K[(size_t)i * HX_BLOCK] = self >= 0 ? (1u << self) : 0u;
+  }
+}
+
 /* failed members report NaN from the failing year on (the reference stops producing output) */
 __global__ void hx_nan_fill_kernel(const __grid_constant__ HxDev d, int start_year, int nyears,
                                    int nsel, int yr0, int yr1) {
@@ -823,10 +871,12 @@ cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cuda
   hx_spinup_kernel<<<1, HX_BLOCK, 0, st>>>(d, C, member - member % HX_BLOCK, member);
   return cudaGetLastError();
 }
-cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
+template <bool TRACK>
+static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -836,8 +886,8 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel, HX_BLOCK,
-                                                                  HX_SMEM_RUN_BYTES);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK>,
+                                                                  HX_BLOCK, HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
     resident = sms * (per_sm > 0 ? per_sm : 1);
   }
@@ -846,7 +896,14 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
   const int grid = ntiles < resident ? ntiles : resident;
   cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  hx_run_kernel<<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
+  hx_run_kernel<TRACK><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
+  return cudaGetLastError();
+}
+cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
+  return d.T ? launch_run_t<true>(d, C, r0, r1, st) : launch_run_t<false>(d, C, r0, r1, st);
+}
+cudaError_t launch_track_init(const HxDev &d, cudaStream_t st) {
+  hx_track_init_kernel<<<(d.Mpad + 255) / 256, 256, 0, st>>>(d);
   return cudaGetLastError();
 }
 cudaError_t launch_nan_fill(const HxDev &d, const HxConst &C, int nsel, int yr0, int yr1,

@@ -33,6 +33,11 @@ struct HxDev {
   unsigned long long *counters; /* [HX_NCOUNTERS] */
   unsigned *sched;              /* [1 + Mpad / HX_BLOCK]: work-queue ticket, per-tile progress */
   int32_t out_slot[OUT_COUNT];  /* output id -> slot in `out`, -1 = not recorded */
+  /* carbon tracking (null unless a tracking date was set) */
+  double *T;                /* [tile][TS_COUNT * HX_NSRC][128] source fractions */
+  uint32_t *TK;             /* [tile][TS_COUNT][128] key masks */
+  double *TO;               /* [track_nrec][HX_NPOOL * HX_NSRC][Mpad] recorded fractions */
+  uint32_t *TOK;            /* [track_nrec][HX_NPOOL][Mpad] recorded key masks */
 };
 
 namespace hx {
@@ -40,6 +45,7 @@ cudaError_t launch_setup(const HxDev &d, const HxConst &C, cudaStream_t st);
 cudaError_t launch_spinup(const HxDev &d, const HxConst &C, cudaStream_t st);
 cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cudaStream_t st);
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st);
+cudaError_t launch_track_init(const HxDev &d, cudaStream_t st);
 cudaError_t launch_nan_fill(const HxDev &d, const HxConst &C, int nsel, int yr0, int yr1,
                             cudaStream_t st);
 }

@@ -103,12 +103,35 @@ enum {
   OUT_COUNT
 };
 
+/* ---- carbon tracking (fluxpool source maps, inst/include/fluxpool.hpp) ----
+ * A tracked pool's unordered_map<source name, fraction> is a vector over the HX_NSRC possible
+ * source names plus a key mask (a key with fraction 0 is not an absent key: it counts in the
+ * 1/n split of a zero total and the tracking visitor prints it).  Pool / source order:
+ * atmos_co2 earth_c veg_c detritus_c soil_c permafrost_c thawedp_c HL LL intermediate deep
+ * (+ source "untracked").  Per member the maps live in a CTA-tiled array
+ * T[tile][TS_COUNT * HX_NSRC][128] (+ masks K[tile][TS_COUNT][128]): the 11 pools, the ocean's
+ * year-start copy of the atmosphere (ocean_component.hpp:78,106), the stash-start copies
+ * that fluxes made by flux_from_fluxpool() carry, and the four CarbonAdditions maps. */
+#define HX_NPOOL 11
+#define HX_NSRC 12
+enum {
+  TS_ATMOS = 0, TS_EARTH, TS_VEG, TS_DET, TS_SOIL, TS_PERM, TS_THAWED, TS_HL, TS_LL, TS_IO, TS_DO,
+  TS_ATM_CPOOL,
+  TS_ATM0, TS_EARTH0, TS_DET0, TS_SOIL0, TS_PERM0, TS_OA,
+  TS_ADD_HL, TS_ADD_LL, TS_ADD_IO, TS_ADD_DO,
+  TS_COUNT
+};
+#define HX_SRC_UNTRACKED 11
+
 /* ---- engine-wide constants handed to every kernel ---- */
 struct HxConst {
   int32_t start_year, end_year, nrow; /* nrow = end - start + 1 */
   int32_t baseyear;
   int32_t max_spinup;
   uint32_t flags;
+  /* carbon tracking: first tracked year (core.cpp:228-235; 9999 = off); recorded years are
+   * tracking_date + k * track_every (k >= 0) and end_year (track_every = 0: end_year only) */
+  int32_t tracking_date, track_every, track_nrec;
   /* salinity-only chemistry constants, computed on the host with the C library so they are
    * the doubles the reference computes (ocean_csys.cpp:225-287) */
   double S, sqrtS, S15, bor;

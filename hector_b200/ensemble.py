@@ -40,7 +40,16 @@ OUTPUT_VARIABLES = ["CO2_concentration", "global_tas", "RF_tot", "RF_CO2", "heat
                     "RF_N2O", "rh_ch4", "ocean_timesteps"]
 MEMBER_STATUS = {0: "ok", 1: "negative flux/pool", 2: "mass not conserved",
                  3: "solver retries exhausted", 4: "no [H+] root", 5: "yearfraction out of bounds",
-                 6: "CO2 SARF condition", 7: "ODE stepper", 8: "spin-up did not converge"}
+                 6: "CO2 SARF condition", 7: "ODE stepper", 8: "spin-up did not converge",
+                 9: "tracking fractions out of range"}
+# carbon tracking: tracked pools (fluxpool names) and the possible source names
+TRACK_POOLS = ["atmos_co2", "earth_c", "veg_c", "detritus_c", "soil_c", "permafrost_c",
+               "thawedp_c", "HL", "LL", "intermediate", "deep"]
+TRACK_SOURCES = TRACK_POOLS + ["untracked"]
+TRACK_COMPONENT = ["simpleNbox"] * 7 + ["ocean"] * 4
+# output variable holding each tracked pool's total (Pg C)
+TRACK_POOL_OUTPUT = ["atmos_co2", "earth_c", "veg_c", "detritus_c", "soil_c", "permafrost_c",
+                     "thawedp_c", "HL_ocean_c", "LL_ocean_c", "IO_ocean_c", "DO_ocean_c"]
 
 
 def load_scenario_tables(path):
@@ -61,9 +70,11 @@ def _dp(a):
 class Ensemble:
     def __init__(self, n_members, scenarios, member_scenario=None, start_year=1745, end_year=2300,
                  device=0, outputs=("CO2_concentration", "global_tas"), cold_newton=False,
-                 spinup=True, stream=None):
+                 spinup=True, stream=None, tracking_date=None, track_every=1):
         """scenarios: one table [nrow, 44] (RAW_SERIES columns), or a list of them;
-        member_scenario: int array [n_members] of indices into that list."""
+        member_scenario: int array [n_members] of indices into that list;
+        tracking_date: [core] trackingDate -- carbon tracking from that year on, recorded every
+        `track_every` years and in the end year (0: end year only)."""
         self.L = _capi.lib()
         if isinstance(scenarios, np.ndarray):
             scenarios = [scenarios]
@@ -94,6 +105,8 @@ class Ensemble:
         self.outputs = list(outputs)
         arr = (C.c_char_p * len(self.outputs))(*[s.encode() for s in self.outputs])
         self._chk(self.L.hx_select_outputs(self.h, len(self.outputs), arr))
+        if tracking_date is not None:
+            self._chk(self.L.hx_set_tracking(self.h, int(tracking_date), int(track_every)))
         self.prepared = False
 
     @classmethod
@@ -206,6 +219,33 @@ class Ensemble:
         self._chk(self.L.hx_output_device(self.h, var.encode(), C.byref(p), C.byref(stride),
                                           C.byref(ny)))
         return p.value, stride.value, ny.value
+
+    def fetch_tracking(self, date):
+        """-> (frac[n_members, 11, 12], mask[n_members, 11]): source fractions of the tracked
+        pools (TRACK_POOLS x TRACK_SOURCES) in year `date`, and which sources are keys of each
+        pool's map (bit s of mask) -- the rows Core::getTrackingData prints."""
+        frac = np.empty((self.n_members, len(TRACK_POOLS), len(TRACK_SOURCES)))
+        mask = np.zeros((self.n_members, len(TRACK_POOLS)), dtype=np.uint32)
+        self._chk(self.L.hx_fetch_tracking(self.h, float(date), _dp(frac),
+                                           mask.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return frac, mask
+
+    def tracking_data(self, member, dates):
+        """get_tracking_data (R/messages.R, Core::getTrackingData, csv_tracking_visitor.cpp:88-103)
+        for one member: rows (year, component, pool_name, pool_value, pool_units, source_name,
+        source_fraction).  Pool totals need the pool outputs to be selected."""
+        rows = []
+        for y in dates:
+            frac, mask = self.fetch_tracking(y)
+            for k, pool in enumerate(TRACK_POOLS):
+                val = float("nan")
+                if TRACK_POOL_OUTPUT[k] in self.outputs:
+                    val = float(self.fetch(TRACK_POOL_OUTPUT[k], [y])[member, 0])
+                for s, src in enumerate(TRACK_SOURCES):
+                    if mask[member, k] >> s & 1:
+                        rows.append((int(y), TRACK_COMPONENT[k], pool, val, "Pg C", src,
+                                     float(frac[member, k, s])))
+        return rows
 
     def status(self):
         st = np.empty(self.n_members, dtype=np.int32)

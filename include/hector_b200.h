@@ -50,6 +50,7 @@ typedef struct hx_engine *hx_handle;
 #define HX_MEMBER_CO2SARF 6      /* forcing_component.cpp:353 */
 #define HX_MEMBER_STEPPER 7      /* odeint: 500 failed step-size searches */
 #define HX_MEMBER_SPINUP 8       /* spin-up did not converge within max_spinup (reference only logs) */
+#define HX_MEMBER_TRACKING 9     /* "fractions must be 0-1" / "pool_map must sum to ~1.0" fluxpool.hpp:105-112 */
 
 /* hx_config.flags */
 #define HX_FLAG_COLD_NEWTON 1u   /* start every [H+] solve from the Fujiwara bound like the
@@ -143,6 +144,22 @@ int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates
  * start_year+1); valid until hx_destroy.  For NCCL gathers / zero-copy consumers. */
 int hx_output_device(hx_handle h, const char *name, const double **dev_ptr,
                      int64_t *member_stride, int32_t *n_years);
+
+/* Carbon tracking ([core] trackingDate, Core::getTrackingData: src/core.cpp:199-209, 228-235;
+ * CSVFluxPoolVisitor: src/csv_tracking_visitor.cpp:80-137; the algebra: inst/include/fluxpool.hpp:
+ * 197-257).  From year `tracking_date` on (startDate < tracking_date <= endDate) the source
+ * fractions of the 11 tracked pools are carried per member and recorded for the years
+ * tracking_date + k * record_every and for end_year (record_every = 0: end_year only).  Call
+ * before hx_prepare; "trackingDate" via hx_set_param_scalar / the ini reader is the same switch
+ * with record_every = 1.  Pool and source order: atmos_co2 earth_c veg_c detritus_c soil_c
+ * permafrost_c thawedp_c HL LL intermediate deep (+ source 11 "untracked"). */
+#define HX_TRACK_NPOOL 11
+#define HX_TRACK_NSRC 12
+int hx_set_tracking(hx_handle h, int32_t tracking_date, int32_t record_every);
+/* frac[member][pool][source] (n_members x 11 x 12) and, if mask != NULL, mask[member][pool] whose
+ * bit s says that source s is a key of the pool's map (the rows the reference's tracking CSV
+ * prints; a key can carry fraction 0).  `date` must be a recorded year or the current date. */
+int hx_fetch_tracking(hx_handle h, double date, double *frac, uint32_t *mask);
 
 int hx_member_status(hx_handle h, int32_t *status, int32_t *fail_year, int32_t n);
 int hx_counters(hx_handle h, uint64_t *out, int32_t n);
