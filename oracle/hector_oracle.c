@@ -103,6 +103,10 @@ typedef struct {
   /* solver (carbon-cycle-solver.hpp:86-98) */
   double c[NC], t, dt;
 
+  /* user constraints (NULL = none) and the preindustrial values they may overwrite */
+  const ho_constraints *cn;
+  double M0_ch4, N0_n2o; /* CH4Component::M0 / N2OComponent::N0 after prepareToRun */
+
   /* carbon tracking: maps of atmos_c, earth_c and the five land pools (TP_* order), and the
    * ocean's copy of the atmosphere (set_atmosphere_sources, ocean_component.hpp:78,106) */
   int tracking_date, tracking;
@@ -767,6 +771,17 @@ static double snbox_rh(member_t *m) { /* :717-721 */
   return FP(m, r + snbox_rh_ftpa_co2(m));
 }
 
+/* tseries::exists(year) && get(year) for a constraint series stored densely per model year
+ * (NaN = no entry for that year) */
+static int cn_get(const member_t *m, const double *series, int year, double *v) {
+  if (!series) return 0;
+  const int r = year - m->p->start_year;
+  if (r < 0 || r >= m->nrow) return 0;
+  if (isnan(series[r])) return 0;
+  *v = series[r];
+  return 1;
+}
+
 /* :744-772 */
 static void snbox_compute_pf_thaw_refreeze(member_t *m, double rh_co2, double rh_ch4, double *x,
                                            double *y, double *z) {
@@ -835,6 +850,28 @@ static int snbox_calcderivs(member_t *m, double t, const double c[], double dcdt
     pf_thaw_c = FP(m, 0.0 + FP(m, x));
     pf_refreeze_tp = FP(m, 0.0 + FP(m, y));
     pf_refreeze_soil = FP(m, 0.0 + FP(m, z));
+  }
+
+  /* NBP constraint :871-898: NPP and RH (and their parts) are scaled so that their net
+   * matches the user's NBP of year round(t) */
+  {
+    double nbp_c;
+    if (!m->in_spinup && cn_get(m, m->cn ? m->cn->nbp : NULL, (int)round(t), &nbp_c)) {
+      const double nbp = npp_current - rh_current - m->current_luc_e + m->current_luc_u;
+      const double diff = nbp_c - nbp;
+      const double npp_current_old = npp_current;
+      npp_current = FP(m, npp_current + diff / 2.0);
+      const double npp_ratio = npp_current / npp_current_old;
+      npp_fav = FP(m, npp_fav * npp_ratio);
+      npp_fad = FP(m, npp_fad * npp_ratio);
+      npp_fas = FP(m, npp_fas * npp_ratio);
+      const double rh_current_old = rh_current;
+      rh_current = FP(m, rh_current - diff / 2.0);
+      const double rh_ratio = rh_current / rh_current_old;
+      rh_fda_current = FP(m, rh_fda_current * rh_ratio);
+      rh_fsa_current = FP(m, rh_fsa_current * rh_ratio);
+      rh_ftpa_co2_current = FP(m, rh_ftpa_co2_current * rh_ratio);
+    }
   }
 
   dcdt[C_ATMOS] = m->current_ffi_e - m->current_daccs_u + m->current_luc_e - m->current_luc_u +
@@ -952,6 +989,25 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
   double newthawedpf = FP(m, solver_tpf);
 
   double rh_nbp_constraint_adjust = 1.0;
+  /* NBP constraint :343-383 */
+  {
+    double nbp_c;
+    const int rounded_t = (int)round(t);
+    if (!m->in_spinup && cn_get(m, m->cn ? m->cn->nbp : NULL, rounded_t, &nbp_c)) {
+      const double diff = nbp_c - alf;
+      npp_total = FP(m, npp_total + diff / 2.0);
+      rh_nbp_constraint_adjust = FP(m, rh_total - diff / 2.0) / rh_total;
+      rh_total = FP(m, rh_total - diff / 2.0);
+      const double pool_diff = diff * yf;
+      const double total_land = c[C_DET] + c[C_VEG] + c[C_SOIL] + c[C_THAWEDP];
+      newdet = FP(m, newdet + pool_diff * c[C_DET] / total_land);
+      newveg = FP(m, newveg + pool_diff * c[C_VEG] / total_land);
+      newsoil = FP(m, newsoil + pool_diff * c[C_SOIL] / total_land);
+      newthawedpf = FP(m, newthawedpf + pool_diff * c[C_THAWEDP] / total_land);
+      ocean_dump_to_deep(m, -pool_diff);
+      alf = npp_total - rh_total - luc_e_untracked + luc_u_untracked;
+    }
+  }
   m->nbp = alf;
 
   const double total = c[C_VEG] + c[C_DET] + c[C_SOIL];
@@ -1105,7 +1161,18 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
   if (m->masstot > 0.0 && diff > MB_EPSILON) fail_member(m, HO_ERR_MASS);
   m->masstot = sum;
 
-  /* spin-up pinning :567-603 */
+  /* spin-up pinning / CO2 constraint :567-603 (CO2_constrain.exists(t): exact key only, so a
+   * stash that ends inside a year is never constrained) */
+  double co2_c = 0.0;
+  const int have_co2_c = !m->in_spinup && t == floor(t) &&
+                         cn_get(m, m->cn ? m->cn->co2 : NULL, (int)t, &co2_c);
+  if (have_co2_c) {
+    FP(m, co2_c); /* fluxpool atmppmv.set(...) */
+    double atmos_cpool_to_match = FP(m, co2_c / PGC_TO_PPMVCO2);
+    double Ca_residual = m->atmos_c - atmos_cpool_to_match;
+    ocean_dump_to_deep(m, Ca_residual);
+    m->atmos_c = FP(m, m->atmos_c - Ca_residual);
+  }
   if (m->in_spinup) {
     double atmos_cpool_to_match = FP(m, p->C0 / PGC_TO_PPMVCO2);
     double Ca_residual = m->atmos_c - atmos_cpool_to_match;
@@ -1259,12 +1326,25 @@ static void solver_run(member_t *m, const double tnew, double Tland) {
 /* ---------------------------------------------------------------------------------- */
 /* member-independent gas series                                                       */
 void ho_gas_series(const ho_params *p, const double *raw, double *n2o, double *halo_rf) {
+  ho_gas_series_constrained(p, raw, NULL, n2o, halo_rf);
+}
+
+/* with optional N2O / halocarbon concentration constraints (n2o_component.cpp:136-160,
+ * halocarbon_component.cpp:189-192).  Returns N0 as N2OComponent::prepareToRun leaves it. */
+double ho_gas_series_constrained(const ho_params *p, const double *raw, const ho_constraints *cn,
+                                 double *n2o, double *halo_rf) {
   const int nrow = p->end_year - p->start_year + 1;
-  n2o[0] = p->N0; /* n2o_component.cpp:136-147 */
+  double N0 = p->N0;
+  if (cn && cn->n2o && !isnan(cn->n2o[0])) N0 = cn->n2o[0]; /* n2o_component.cpp:141-146 */
+  n2o[0] = N0; /* n2o_component.cpp:136-147 */
   for (int r = 1; r < nrow; ++r) { /* :150-191 */
+    if (cn && cn->n2o && !isnan(cn->n2o[r])) {
+      n2o[r] = cn->n2o[r];
+      continue;
+    }
     const double *row = raw + (size_t)r * HO_NRAW;
     double previous_n2o = n2o[r - 1];
-    double tau = p->TN2O0 * (pow(previous_n2o / p->N0, -0.05));
+    double tau = p->TN2O0 * (pow(previous_n2o / N0, -0.05));
     const double current_n2oem = row[HO_RAW_N2O_E] + row[HO_RAW_N2O_NAT];
     const double dN2O = current_n2oem / p->UC_N2O - previous_n2o / tau;
     n2o[r] = previous_n2o + dN2O;
@@ -1281,11 +1361,14 @@ void ho_gas_series(const ho_params *p, const double *raw, double *n2o, double *h
       double concDeltaEmiss = emissMol / (0.1 * 1.8);
       double expfac = exp(-alpha);
       Ha = Ha * expfac + concDeltaEmiss * tau * (1.0 - expfac);
+      if (cn && cn->halo && !isnan(cn->halo[(size_t)r * HO_NHALO + g]))
+        Ha = cn->halo[(size_t)r * HO_NHALO + g]; /* concentration-forced year */
       double rf_unadjusted = p->halo_rho[g] * Ha;
       double adjusted_rf = rf_unadjusted + p->halo_delta[g] * rf_unadjusted;
       halo_rf[(size_t)r * HO_NHALO + g] = adjusted_rf;
     }
   }
+  return N0;
 }
 
 /* ---------------------------------------------------------------------------------- */
@@ -1452,6 +1535,13 @@ static void doeclim_run(member_t *m, int tstep, double rf_tot) {
     temp_sst[0] = 0.0;
   }
   m->temp[tstep] = flnd * temp_landair[tstep] + (1.0 - flnd) * bsi * temp_sst[tstep];
+  /* user-supplied global temperature (:510-525): overwrite, then back-calculate land and
+   * sea-surface values */
+  if (m->cn && m->cn->tas && tstep >= m->cn->tas_first_row && tstep <= m->cn->tas_last_row) {
+    m->temp[tstep] = m->cn->tas[tstep];
+    temp_landair[tstep] = (m->temp[tstep] - (1.0 - flnd) * bsi * temp_sst[tstep]) / flnd;
+    temp_sst[tstep] = (m->temp[tstep] - flnd * temp_landair[tstep]) / ((1.0 - flnd) * bsi);
+  }
   if (tstep > 0) {
     m->heatflux_mixed[tstep] = cas * (temp_sst[tstep] - temp_sst[tstep - 1]);
     for (int i = 0; i < tstep; i++)
@@ -1481,7 +1571,7 @@ static double forcing_total(member_t *m, int r, double CO2_conc, double Ma, doub
                s_SO2 = (260.34644166 * 1000) * (32.065 / 64.066);
   const double *row = m->raw + (size_t)r * HO_NRAW;
   const double *hrf = m->halo_rf + (size_t)r * HO_NHALO;
-  const double C0 = p->C0, M0 = p->M0, N0 = p->N0;
+  const double C0 = p->C0, M0 = m->M0_ch4, N0 = m->N0_n2o;
 
   double C_alpha_max = C0 - (b1 / (2 * a1));
   double n2o_alpha = c1 * sqrt(Na);
@@ -1624,15 +1714,24 @@ static double *dalloc(int n) { return (double *)calloc((size_t)n, sizeof(double)
 
 int ho_run_member(const ho_params *p, const double *raw, int run_to, double *out, int nyears_cap,
                   int *fail_year, ho_counters *counters, ho_spinup_state *spin) {
-  return ho_run_member_tracked(p, raw, run_to, out, nyears_cap, fail_year, counters, spin, 9999,
-                               NULL, NULL);
+  return ho_run_member_ex(p, raw, NULL, run_to, out, nyears_cap, fail_year, counters, spin, 9999,
+                          NULL, NULL);
 }
 
 int ho_run_member_tracked(const ho_params *p, const double *raw, int run_to, double *out,
                           int nyears_cap, int *fail_year, ho_counters *counters,
                           ho_spinup_state *spin, int tracking_date, double *track_frac,
                           uint32_t *track_mask) {
+  return ho_run_member_ex(p, raw, NULL, run_to, out, nyears_cap, fail_year, counters, spin,
+                          tracking_date, track_frac, track_mask);
+}
+
+int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints *cn, int run_to,
+                     double *out, int nyears_cap, int *fail_year, ho_counters *counters,
+                     ho_spinup_state *spin, int tracking_date, double *track_frac,
+                     uint32_t *track_mask) {
   member_t *m = (member_t *)calloc(1, sizeof(member_t));
+  m->cn = cn;
   m->tracking_date = tracking_date; /* core.cpp:60: default 9999 = never */
   if (track_frac)
     for (size_t i = 0; i < (size_t)nyears_cap * HO_NPOOL * HO_NSRC; ++i) track_frac[i] = NAN;
@@ -1659,8 +1758,13 @@ int ho_run_member_tracked(const ho_params *p, const double *raw, int run_to, dou
   }
 
   /* ---- prepareToRun of every component ---- */
-  ho_gas_series(p, raw, m->N2O, m->halo_rf);
-  m->CH4[0] = p->M0;     /* ch4_component.cpp:137-147 */
+  m->N0_n2o = ho_gas_series_constrained(p, raw, cn, m->N2O, m->halo_rf);
+  /* OHComponent::prepareToRun reads CH4's M0 first (dependency order), THEN
+   * CH4Component::prepareToRun overwrites its M0 with a start-date constraint
+   * (oh_component.cpp:131, ch4_component.cpp:137-147) */
+  m->M0_ch4 = p->M0;
+  if (cn && cn->ch4 && !isnan(cn->ch4[0])) m->M0_ch4 = cn->ch4[0];
+  m->CH4[0] = m->M0_ch4;
   m->O3[0] = p->PO3;     /* o3_component.cpp:118-123 */
   m->tau_oh = p->TOH0;
   ocean_prepareToRun(m);
@@ -1748,7 +1852,10 @@ int ho_run_member_tracked(const ho_params *p, const double *raw, int run_to, dou
       m->tau_oh = p->TOH0 * exp(-toh);
     }
     /* CH4: ch4_component.cpp:152-199 */
-    {
+    double ch4_c;
+    if (cn_get(m, cn ? cn->ch4 : NULL, y, &ch4_c)) {
+      m->CH4[r] = ch4_c;
+    } else {
       const double current_ch4em = row[HO_RAW_CH4_E];
       const double current_toh = m->tau_oh;
       const double rh_ch4 = m->RH_ch4 * (1000.0 * 16.04 / 12.01);
@@ -1791,6 +1898,9 @@ int ho_run_member_tracked(const ho_params *p, const double *raw, int run_to, dou
     if (!((double)y < p->baseyear)) {
       double fco2, fch4, fn2o;
       double Ftot = forcing_total(m, r, CO2_conc, m->CH4[r], m->N2O[r], m->O3[r], &fco2, &fch4, &fn2o);
+      /* user-supplied total forcing (forcing_component.cpp:498-505): every year up to the
+       * series' last date, Ftot_constrain.get() interpolating / extrapolating flat */
+      if (cn && cn->rf_tot && r <= cn->rf_tot_last_row) Ftot = cn->rf_tot[r];
       if ((double)y == p->baseyear) {
         m->base_tot = Ftot; m->base_co2 = fco2; m->base_ch4 = fch4; m->base_n2o = fn2o;
       }

@@ -110,6 +110,21 @@ typedef struct {
       halo_molarMass[HO_NHALO];
 } ho_params;
 
+/* User constraints: dense per-model-year series [nrow] (row = year - start_year), NaN = no
+ * entry for that year; NULL = no such constraint.
+ *   co2, nbp, ch4, n2o, halo[nrow][26]  applied in the years that have an entry
+ *        (tseries::exists(year): simpleNbox-runtime.cpp:345, 568, 871; ch4_component.cpp:141,
+ *        156; n2o_component.cpp:141, 157; halocarbon_component.cpp:189)
+ *   rf_tot   applied in every year <= rf_tot_last_row (forcing_component.cpp:498); the caller
+ *            fills the rows below the first entry flat and interpolates gaps linearly, which
+ *            is what Ftot_constrain.get() returns
+ *   tas      applied for tas_first_row <= row <= tas_last_row (temperature_component.cpp:
+ *            510-512), gaps interpolated by the caller */
+typedef struct {
+  const double *co2, *nbp, *ch4, *n2o, *halo, *rf_tot, *tas;
+  int rf_tot_last_row, tas_first_row, tas_last_row;
+} ho_constraints;
+
 typedef struct {
   uint64_t rhs_evals, steps_accepted, steps_rejected, integrate_calls, newton_iterations,
       newton_calls, spinup_steps;
@@ -144,6 +159,14 @@ int ho_run_member_tracked(const ho_params *p, const double *raw, int run_to, dou
                           int nyears_cap, int *fail_year, ho_counters *counters,
                           ho_spinup_state *spin, int tracking_date, double *track_frac,
                           uint32_t *track_mask);
+
+/* everything at once: optional constraints and carbon tracking */
+int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints *cn, int run_to,
+                     double *out, int nyears_cap, int *fail_year, ho_counters *counters,
+                     ho_spinup_state *spin, int tracking_date, double *track_frac,
+                     uint32_t *track_mask);
+double ho_gas_series_constrained(const ho_params *p, const double *raw, const ho_constraints *cn,
+                                 double *n2o, double *halo_rf);
 
 /* fluxpool operator+ on explicit maps (unit-test hook, cf. src/unit-testing/test_tracking.cpp) */
 int ho_tm_add(double a, double *fa, uint32_t *mask_a, double b, const double *fb, uint32_t mask_b);

@@ -57,6 +57,70 @@ class SpinState(C.Structure):
                    ("spinup_steps", C.c_int)])
 
 
+class Constraints(C.Structure):
+    _fields_ = ([(n, C.POINTER(C.c_double)) for n in ("co2", "nbp", "ch4", "n2o", "halo", "rf_tot",
+                                                      "tas")]
+                + [(n, C.c_int) for n in ("rf_tot_last_row", "tas_first_row", "tas_last_row")])
+
+
+HALOS = ["CF4", "C2F6", "HFC23", "HFC32", "HFC4310", "HFC125", "HFC134a", "HFC143a", "HFC227ea",
+         "HFC245fa", "SF6", "CFC11", "CFC12", "CFC113", "CFC114", "CFC115", "CCl4", "CH3CCl3",
+         "HCFC22", "HCFC141b", "HCFC142b", "halon1211", "halon1301", "halon2402", "CH3Cl",
+         "CH3Br"]
+
+
+def make_constraints(nrow, start_year, spec):
+    """spec: {name: {year: value}} with names CO2_constrain, NBP_constrain, CH4_constrain,
+    N2O_constrain, <gas>_constrain, RF_tot_constrain, tas_constrain.  Returns (Constraints,
+    keep-alive list).  RF_tot / tas are densified the way tseries::get does it (linear
+    interpolation between entries; RF_tot flat below its first entry)."""
+    cn = Constraints()
+    keep = []
+
+    def dense(d):
+        a = np.full(nrow, np.nan)
+        for y, v in d.items():
+            a[int(y) - start_year] = v
+        return a
+
+    def interp(d, flat_below):
+        ys = np.array(sorted(d))
+        vs = np.array([d[y] for y in ys], dtype=np.float64)
+        a = np.full(nrow, np.nan)
+        for r in range(nrow):
+            y = start_year + r
+            if y in d:
+                a[r] = d[y]
+            elif y < ys[0]:
+                if flat_below:
+                    a[r] = vs[0]
+            elif y <= ys[-1]:
+                i = np.searchsorted(ys, y) - 1
+                a[r] = vs[i] + (y - ys[i]) * (vs[i + 1] - vs[i]) / (ys[i + 1] - ys[i])
+        return a, int(ys[0]) - start_year, int(ys[-1]) - start_year
+
+    halo = None
+    for name, d in spec.items():
+        if name == "RF_tot_constrain":
+            a, _, last = interp(d, True)
+            cn.rf_tot = _dp(a); cn.rf_tot_last_row = last; keep.append(a)
+        elif name == "tas_constrain":
+            a, first, last = interp(d, False)
+            cn.tas = _dp(a); cn.tas_first_row = first; cn.tas_last_row = last; keep.append(a)
+        elif name in ("CO2_constrain", "NBP_constrain", "CH4_constrain", "N2O_constrain"):
+            a = dense(d)
+            setattr(cn, name.split("_")[0].lower(), _dp(a)); keep.append(a)
+        elif name.endswith("_constrain") and name[:-10] in HALOS:
+            if halo is None:
+                halo = np.full((nrow, NHALO), np.nan)
+            halo[:, HALOS.index(name[:-10])] = dense(d)
+        else:
+            raise KeyError(name)
+    if halo is not None:
+        cn.halo = _dp(halo); keep.append(halo)
+    return cn, keep
+
+
 _lib = None
 
 
@@ -78,6 +142,12 @@ def lib():
         L.ho_run_member_tracked.argtypes = L.ho_run_member.argtypes + [
             C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
         L.ho_run_member_tracked.restype = C.c_int
+        L.ho_run_member_ex.argtypes = [C.POINTER(Params), C.POINTER(C.c_double),
+                                       C.POINTER(Constraints), C.c_int, C.POINTER(C.c_double),
+                                       C.c_int, C.POINTER(C.c_int), C.POINTER(Counters),
+                                       C.POINTER(SpinState), C.c_int, C.POINTER(C.c_double),
+                                       C.POINTER(C.c_uint32)]
+        L.ho_run_member_ex.restype = C.c_int
         L.ho_csys.argtypes = [C.c_double] * 6 + [C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ho_csys.restype = C.c_double
         L.ho_gas_series.argtypes = [C.POINTER(Params), C.POINTER(C.c_double),
@@ -118,6 +188,23 @@ def run_member(raw, params=None, run_to=-1, **over):
                                       "earth", "alk_HL", "alk_LL", "spinup_steps")}
     sd["ocean"] = list(sp.ocean)
     return st, fy.value, out, cd, sd
+
+
+def run_member_constrained(raw, spec, params=None, run_to=-1, **over):
+    """run_member with user constraints (see make_constraints) -> (status, fail_year, out)"""
+    p = params if params is not None else default_params()
+    for k, v in over.items():
+        setattr(p, k, v)
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    nrow = p.end_year - p.start_year + 1
+    assert raw.shape == (nrow, NRAW), raw.shape
+    cn, keep = make_constraints(nrow, p.start_year, spec)
+    ny = (p.end_year if run_to < 0 else run_to) - p.start_year
+    out = np.empty((NOUT, ny))
+    fy = C.c_int(0)
+    st = lib().ho_run_member_ex(C.byref(p), _dp(raw), C.byref(cn), run_to, _dp(out), ny,
+                                C.byref(fy), None, None, 9999, None, None)
+    return st, fy.value, out
 
 
 def run_member_tracked(raw, tracking_date, params=None, run_to=-1, **over):

@@ -14,6 +14,9 @@ what travels to the GPU box.
                       fractions + key masks of the 11 tracked pools at selected years (read at
                       full precision through oracle/ref_driver.cpp), and the reference's own
                       6-digit getTrackingData() CSV for one short run.
+  ref_constraints.npz known answers of the UNMODIFIED reference under user constraints (CO2, NBP,
+                      tas, RF_tot, CH4, N2O, halocarbon concentrations), incl. two expected
+                      failures.
 """
 import csv
 import os
@@ -245,9 +248,97 @@ def make_tracking():
                         sources=np.array(ref.TRACK_SOURCES), csv_1750_1755=np.array(csv_text))
 
 
+CONSTRAINT_UNITS = {"CH4_constrain": "ppbv CH4", "N2O_constrain": "ppbv N2O",
+                    "HFC23_constrain": "pptv", "CFC11_constrain": "pptv",
+                    "RF_tot_constrain": "W/m2", "tas_constrain": "degC",
+                    "CO2_constrain": "ppmv CO2", "NBP_constrain": "Pg C/yr"}
+CONSTRAINT_VARS = ["CO2_concentration", "global_tas", "RF_tot", "CH4_concentration",
+                   "N2O_concentration", "NBP", "ocean_c", "veg_c", "soil_c", "sst", "land_tas",
+                   "heatflux", "RF_CH4", "RF_N2O", "DO_ocean_c", "thawedp_c"]
+
+
+def constraint_cases():
+    """name -> {constraint: {year: value}}; built from the emission-driven SSP2-4.5 run of the
+    unmodified reference, like tests/testthat/test_constraints.R does"""
+    from oracle import ref
+    ok, err, o, _ = ref.run_member(os.path.join(REF, "inst/input/hector_ssp245.ini"), {},
+                                   ["CO2_concentration", "CH4_concentration",
+                                    "N2O_concentration", "NBP"])
+    assert ok, err
+    co2, ch4, n2o, nbp = o[0], o[1], o[2], o[3]
+    yrs = range(1746, 2301)
+    return {
+        "ch4_all": {"CH4_constrain": dict([(1745, 731.41 * 1.2)] +
+                                          [(y, ch4[y - 1746] * 1.2) for y in yrs])},
+        "ch4_part": {"CH4_constrain": {y: ch4[y - 1746] * 0.9 for y in range(1900, 2051)}},
+        "n2o_all": {"N2O_constrain": dict([(1745, 273.87 * 1.1)] +
+                                          [(y, n2o[y - 1746] * 1.1) for y in yrs])},
+        "n2o_part": {"N2O_constrain": {y: 300.0 + 0.1 * (y - 1950) for y in range(1950, 2101)}},
+        "halo": {"HFC23_constrain": {y: 5.0 + 0.2 * (y - 1990) for y in range(1990, 2201)},
+                 "CFC11_constrain": {y: 100.0 for y in range(1800, 1900)}},
+        "rf_tot": {"RF_tot_constrain": {y: 0.01 * (y - 1850) for y in range(1850, 2001)}},
+        "rf_tot_sparse": {"RF_tot_constrain": {1800: 0.1, 1900: 0.5, 2000: 2.0, 2050: 3.0}},
+        "tas": {"tas_constrain": {y: 0.005 * (y - 1900) for y in range(1900, 2051)}},
+        "tas_sparse": {"tas_constrain": {1850: 0.0, 1950: 0.4, 2100: 2.5}},
+        "co2": {"CO2_constrain": {y: co2[y - 1746] * 1.02 for y in range(1746, 2101)}},
+        "co2_part": {"CO2_constrain": {y: 300.0 + 1.0 * (y - 1950) for y in range(1950, 2021)}},
+        "nbp_near": {"NBP_constrain": {y: nbp[y - 1746] + 0.2 for y in range(1950, 2051)}},
+        "nbp_fail_mass": {"NBP_constrain": {y: 1.0 for y in range(1900, 2101)}},
+        "nbp_fail_negative": {"NBP_constrain": {y: nbp[y - 1746] for y in range(1850, 2301)}},
+        "combo": {"CO2_constrain": {y: co2[y - 1746] * 0.99 for y in range(1850, 2015)},
+                  "tas_constrain": {y: 0.004 * (y - 1850) for y in range(1850, 2015)},
+                  "CH4_constrain": {y: ch4[y - 1746] for y in range(1850, 2015)}},
+    }
+
+
+def make_constraints():
+    """ref_constraints.npz: the unmodified reference run with user constraints set through
+    sendMessage(M_SETDATA) before prepareToRun; NaN from the failing year on."""
+    from oracle import ref
+    cases = constraint_cases()
+    names, specs, vals, fails = [], [], [], []
+    for name, spec in cases.items():
+        c = ref.RefCore(os.path.join(REF, "inst/input/hector_ssp245.ini"))
+        for var, d in spec.items():
+            for y, v in d.items():
+                c.setvar(var, float(v), CONSTRAINT_UNITS[var], float(y))
+        c.prepare()
+        out = np.full((len(CONSTRAINT_VARS), 555), np.nan)
+        fail = 0
+        for y in range(1746, 2301):
+            try:
+                c.run(y)
+            except ref.RefError as e:
+                fail = y
+                print("  ", name, "fails in", y, str(e)[:70])
+                break
+            for k, v in enumerate(CONSTRAINT_VARS):
+                out[k, y - 1746] = c.fetch(v, y)
+        c.close()
+        print(name, "ok" if not fail else "failed")
+        names.append(name); vals.append(out); fails.append(fail)
+        # spec as a flat table: rows (constraint index, year, value)
+        rows = []
+        for var, d in spec.items():
+            for y, v in d.items():
+                rows.append((list(CONSTRAINT_UNITS).index(var), y, v))
+        specs.append(np.array(rows, dtype=np.float64))
+    width = max(len(r) for r in specs)
+    S = np.full((len(specs), width, 3), np.nan)
+    for i, r in enumerate(specs):
+        S[i, :len(r)] = r
+    np.savez_compressed(os.path.join(OUT, "ref_constraints.npz"), names=np.array(names),
+                        constraint_names=np.array(list(CONSTRAINT_UNITS)), spec=S,
+                        variables=np.array(CONSTRAINT_VARS), values=np.array(vals),
+                        fail_year=np.array(fails))
+
+
 if __name__ == "__main__":
     if "tracking" in sys.argv[1:]:
         make_tracking()
+    elif "constraints" in sys.argv[1:]:
+        make_constraints()
     else:
         main()
         make_tracking()
+        make_constraints()

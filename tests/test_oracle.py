@@ -187,3 +187,23 @@ def test_tracking_fluxpool_kats():
     # fractions outside [0, 1] are rejected like the private constructor does (:105-112)
     rc, f, m = add(1.0, [1.5], 0b1, 1.0, [1.0], 0b1)
     assert rc != 0
+
+
+@pytest.mark.parametrize("case", util.ref_constraints(), ids=lambda c: c["name"])
+def test_constraints_against_reference(case):
+    """user constraints (tests/testthat/test_constraints.R territory): CO2 / NBP / tas / RF_tot /
+    CH4 / N2O / halocarbon concentration series applied exactly where the reference applies them
+    (simpleNbox-runtime.cpp:343-383, 567-603, 871-898; temperature_component.cpp:510-525;
+    forcing_component.cpp:498-505; ch4/n2o/halocarbon run()).  Observed: bit-identical,
+    including the year and kind of the two expected failures."""
+    raw = util.scenarios()["ssp245"]
+    st, fy, out = port.run_member_constrained(raw, case["spec"])
+    if case["fail_year"]:
+        assert st in (1, 2) and fy == case["fail_year"]
+    else:
+        assert st == 0
+    n = 555 if not case["fail_year"] else case["fail_year"] - 1746
+    for v, ref in case["values"].items():
+        x = out[port.OUT_NAMES.index(v)]
+        assert np.allclose(x[:n], ref[:n], rtol=1e-12, atol=1e-13), (v, np.abs(x[:n] - ref[:n]).max())
+        assert np.isnan(ref[n:]).all()

@@ -62,6 +62,22 @@ def ref_tracking_csv():
     return str(np.load(os.path.join(GOLDEN, "ref_tracking.npz"))["csv_1750_1755"])
 
 
+def ref_constraints():
+    """constraint known answers of the unmodified reference (tests/golden/make_golden.py)"""
+    z = np.load(os.path.join(GOLDEN, "ref_constraints.npz"))
+    cnames = [str(s) for s in z["constraint_names"]]
+    variables = [str(v) for v in z["variables"]]
+    cases = []
+    for i, name in enumerate(z["names"]):
+        spec = {}
+        for k, y, v in z["spec"][i]:
+            if not np.isnan(k):
+                spec.setdefault(cnames[int(k)], {})[int(y)] = float(v)
+        cases.append(dict(name=str(name), spec=spec, fail_year=int(z["fail_year"][i]),
+                          values=dict(zip(variables, z["values"][i]))))
+    return cases
+
+
 # natural scale below which a relative error is meaningless (outputs that pass through zero
 # or are differences of large pools); CO2 / Tgav floors are SURVEY.md section 8(d)'s
 FLOOR = {"global_tas": 0.01, "CO2_concentration": 1.0, "sst": 0.01, "land_tas": 0.01,
