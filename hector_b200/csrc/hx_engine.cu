@@ -114,6 +114,9 @@ struct Engine {
   /* host-side inputs */
   std::vector<std::vector<double>> raw;      /* [scen][RAW_COUNT * nrow], series-major */
   std::vector<std::vector<char>> raw_set;    /* [scen][RAW_COUNT] */
+  /* user constraints, [scen][CN_COUNT * nrow] series-major, NaN = no entry for that year */
+  std::vector<std::vector<double>> cons;
+  bool tables_dirty = false;                 /* a series changed after hx_prepare */
   std::vector<int32_t> member_scen;          /* API order */
   double pscalar[PI_COUNT];
   std::vector<double> pvec[PI_COUNT];        /* per-member overrides (API order), host copy */
@@ -168,6 +171,48 @@ struct Engine {
     }
     return -1;
   }
+  static int find_constraint(const char *name) {
+    static const char *const base[CN_HALO0] = {"CO2_constrain", "NBP_constrain", "CH4_constrain",
+                                               "N2O_constrain", "RF_tot_constrain",
+                                               "tas_constrain"};
+    for (int i = 0; i < CN_HALO0; ++i)
+      if (!strcmp(base[i], name)) return i;
+    for (int g = 0; g < HX_NHALO; ++g) {
+      std::string s = std::string(hx::kHaloNames[g]) + "_constrain";
+      if (s == name) return CN_HALO0 + g;
+    }
+    return -1;
+  }
+  const double *con(int s, int series) const { return cons[s].data() + (size_t)series * nrow; }
+  bool has_constraint(int s, int series) const {
+    const double *c = con(s, series);
+    for (int r = 0; r < nrow; ++r)
+      if (c[r] == c[r]) return true;
+    return false;
+  }
+  /* tseries::get() of a series that allows interpolation (tas_constrain, RF_tot_constrain:
+   * temperature_component.cpp:112, forcing_component.cpp:112): linear between entries;
+   * `flat_below` extends the first entry downwards (RF_tot is applied for every year up to the
+   * last entry, forcing_component.cpp:498; tas only between first and last, :510-512) */
+  std::vector<double> densify(int s, int series, bool flat_below) const {
+    const double *c = con(s, series);
+    std::vector<double> out(nrow, NAN);
+    int first = -1, last = -1;
+    for (int r = 0; r < nrow; ++r)
+      if (c[r] == c[r]) { if (first < 0) first = r; last = r; }
+    if (first < 0) return out;
+    int lo = first;
+    for (int r = flat_below ? 0 : first; r <= last; ++r) {
+      if (r < first) { out[r] = c[first]; continue; }
+      if (c[r] == c[r]) { out[r] = c[r]; lo = r; continue; }
+      int hi = r;
+      while (!(c[hi] == c[hi])) ++hi;
+      const double x0 = cfg.start_year + lo, x1 = cfg.start_year + hi, t = cfg.start_year + r;
+      out[r] = c[lo] + (t - x0) * (c[hi] - c[lo]) / (x1 - x0);
+    }
+    return out;
+  }
+
   static int find_out(const char *name) {
     for (int i = 0; i < OUT_COUNT; ++i)
       if (!strcmp(hx::kOutNames[i], name)) return i;
@@ -201,11 +246,17 @@ struct Engine {
   void gas_series(int s, std::vector<double> &n2o, std::vector<double> &halo_rf) const {
     const double *R = raw[s].data();
     auto rawv = [&](int series, int r) { return R[(size_t)series * nrow + r]; };
-    const double N0 = pscalar[PI_N0];
+    double N0 = pscalar[PI_N0];
+    const double *cn2o = con(s, CN_N2O);
+    if (cn2o[0] == cn2o[0]) N0 = cn2o[0]; /* n2o_component.cpp:141-146 */
     n2o.assign(nrow, 0.0);
     halo_rf.assign((size_t)nrow * HX_NHALO, 0.0);
     n2o[0] = N0;
     for (int r = 1; r < nrow; ++r) {
+      if (cn2o[r] == cn2o[r]) { /* concentration-forced year, :157-158 */
+        n2o[r] = cn2o[r];
+        continue;
+      }
       const double previous_n2o = n2o[r - 1];
       const double tau = TN2O0 * (std::pow(previous_n2o / N0, -0.05));
       const double current_n2oem = rawv(RAW_N2O_E, r) + rawv(RAW_N2O_NAT, r);
@@ -215,6 +266,7 @@ struct Engine {
     for (int g = 0; g < HX_NHALO; ++g) {
       double Ha = halo_H0[g];
       const double tau = halo_tau[g];
+      const double *cha = con(s, CN_HALO0 + g);
       for (int r = 1; r < nrow; ++r) {
         const double timestep = 1.0;
         const double alpha = 1 / tau;
@@ -222,6 +274,7 @@ struct Engine {
         const double concDeltaEmiss = emissMol / (0.1 * 1.8);
         const double expfac = std::exp(-alpha);
         Ha = Ha * expfac + concDeltaEmiss * tau * (1.0 - expfac);
+        if (cha[r] == cha[r]) Ha = cha[r]; /* halocarbon_component.cpp:189-192 */
         const double rf_unadjusted = halo_rho[g] * Ha;
         halo_rf[(size_t)r * HX_NHALO + g] = rf_unadjusted + halo_delta[g] * rf_unadjusted;
       }
@@ -266,6 +319,39 @@ struct Engine {
     return HX_OK;
   }
 
+  /* device scenario tables [scen][row][SC_STRIDE]: raw series, host gas series, constraints */
+  void build_tables(std::vector<double> &tab, bool &any_constraint) const {
+    tab.assign((size_t)nscen * nrow * SC_STRIDE, 0.0);
+    any_constraint = false;
+    for (int s = 0; s < nscen; ++s) {
+      std::vector<double> n2o, hrf;
+      gas_series(s, n2o, hrf);
+      const double *R = raw[s].data();
+      const std::vector<double> rftot = densify(s, CN_RFTOT, true), tas = densify(s, CN_TAS, false);
+      const double *cco2 = con(s, CN_CO2), *cch4 = con(s, CN_CH4);
+      for (int r = 0; r < nrow; ++r) {
+        double *row = tab.data() + ((size_t)s * nrow + r) * SC_STRIDE;
+        for (int c = 0; c <= SC_MISC; ++c) row[c] = R[(size_t)c * nrow + r]; /* RAW_x == SC_x up to MISC */
+        row[SC_N2O] = n2o[r];
+        for (int g = 0; g < HX_NHALO; ++g) row[SC_HALO0 + g] = hrf[(size_t)r * HX_NHALO + g];
+        row[SC_C_CO2] = cco2[r]; row[SC_C_CH4] = cch4[r];
+        row[SC_C_RFTOT] = rftot[r]; row[SC_C_TAS] = tas[r];
+        for (int c = SC_C_CO2; c <= SC_C_TAS; ++c)
+          if (row[c] == row[c]) any_constraint = true;
+      }
+    }
+  }
+  int upload_tables() {
+    std::vector<double> tab;
+    bool any = false;
+    build_tables(tab, any);
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaMemcpy(d_scen, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    d.constrained = any ? 1 : 0;
+    tables_dirty = false;
+    return HX_OK;
+  }
+
   bool spinup_shared() const {
     for (int pi : hx::kSpinupParams)
       if (!pvec[pi].empty() || pvec_on_device_only[pi]) return false;
@@ -275,6 +361,10 @@ struct Engine {
   int first_active = 0;
 
   int run_setup_and_spinup() {
+    if (tables_dirty) {
+      int rc = upload_tables();
+      if (rc) return rc;
+    }
     CUDA_TRY(cudaMemcpyAsync(d_status, d_status_snap, (size_t)Mpad * sizeof(int32_t),
                              cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(hx::launch_setup(d, C, stream));
@@ -347,6 +437,7 @@ int hx_create(const hx_config *cfg, hx_handle *out) {
   h->nrow = cfg->end_year - cfg->start_year + 1;
   h->raw.assign(h->nscen, std::vector<double>((size_t)RAW_COUNT * h->nrow, 0.0));
   h->raw_set.assign(h->nscen, std::vector<char>(RAW_COUNT, 0));
+  h->cons.assign(h->nscen, std::vector<double>((size_t)CN_COUNT * h->nrow, NAN));
   h->member_scen.assign(h->M, 0);
   for (int i = 0; i < PI_COUNT; ++i) {
     h->pscalar[i] = kParams[i].dflt;
@@ -391,8 +482,21 @@ int hx_set_stream(hx_handle h, void *cuda_stream) {
 int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, int32_t year0,
                            int32_t n, const double *values) {
   if (!h || !name || !values) return HX_ERR_ARG;
-  if (h->prepared) return h->fail(HX_ERR_STATE, "scenario series must be set before hx_prepare");
   if (scenario_id < 0 || scenario_id >= h->nscen) return h->fail(HX_ERR_ARG, "bad scenario id");
+  const int ci = Engine::find_constraint(name);
+  if (ci >= 0) {
+    /* a constraint series may cover any part of the run; NaN = no entry for that year */
+    if (ci == CN_NBP)
+      return h->fail(HX_ERR_UNSUPPORTED, "NBP_constrain is not supported by the ensemble engine");
+    double *dst = h->cons[scenario_id].data() + (size_t)ci * h->nrow;
+    for (int r = 0; r < h->nrow; ++r) dst[r] = NAN;
+    for (int k = 0; k < n; ++k) {
+      const int r = year0 + k - h->cfg.start_year;
+      if (r >= 0 && r < h->nrow) dst[r] = values[k];
+    }
+    if (h->prepared) { h->tables_dirty = true; h->params_dirty = true; }
+    return HX_OK;
+  }
   const int si = Engine::find_raw(name);
   if (si < 0) return h->fail(HX_ERR_ARG, std::string("unknown scenario series: ") + name);
   if (year0 > h->cfg.start_year || year0 + n - 1 < h->cfg.end_year)
@@ -400,6 +504,7 @@ int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, i
   double *dst = h->raw[scenario_id].data() + (size_t)si * h->nrow;
   for (int r = 0; r < h->nrow; ++r) dst[r] = values[h->cfg.start_year - year0 + r];
   h->raw_set[scenario_id][si] = 1;
+  if (h->prepared) { h->tables_dirty = true; h->params_dirty = true; } /* R: setvar + reset */
   return HX_OK;
 }
 
@@ -624,18 +729,9 @@ int hx_prepare(hx_handle h) {
   C.track_nrec = (int)h->track_years.size();
 
   /* device scenario tables */
-  std::vector<double> tab((size_t)h->nscen * nrow * SC_STRIDE, 0.0);
-  for (int s = 0; s < h->nscen; ++s) {
-    std::vector<double> n2o, hrf;
-    h->gas_series(s, n2o, hrf);
-    const double *R = h->raw[s].data();
-    for (int r = 0; r < nrow; ++r) {
-      double *row = tab.data() + ((size_t)s * nrow + r) * SC_STRIDE;
-      for (int c = 0; c <= SC_MISC; ++c) row[c] = R[(size_t)c * nrow + r]; /* RAW_x == SC_x up to MISC */
-      row[SC_N2O] = n2o[r];
-      for (int g = 0; g < HX_NHALO; ++g) row[SC_HALO0 + g] = hrf[(size_t)r * HX_NHALO + g];
-    }
-  }
+  std::vector<double> tab;
+  bool any_constraint = false;
+  h->build_tables(tab, any_constraint);
 
   const size_t Mp = Mpad;
   const int nsel = (int)h->out_sel.size();
@@ -692,6 +788,7 @@ int hx_prepare(hx_handle h) {
   d.block_scen = h->d_block_scen; d.status = h->d_status; d.fail_year = h->d_fail_year;
   d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters; d.sched = h->d_sched;
   d.T = h->d_T; d.TK = h->d_TK; d.TO = h->d_TO; d.TOK = h->d_TOK;
+  d.constrained = any_constraint ? 1 : 0;
   for (int i = 0; i < OUT_COUNT; ++i) d.out_slot[i] = -1;
   for (int s = 0; s < nsel; ++s) d.out_slot[h->out_sel[s]] = s;
 

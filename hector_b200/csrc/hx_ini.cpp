@@ -158,6 +158,21 @@ static int raw_index(const std::string &name) {
   return -1;
 }
 
+static const char *const kConstraintNames[CN_HALO0] = {"CO2_constrain", "NBP_constrain",
+                                                       "CH4_constrain", "N2O_constrain",
+                                                       "RF_tot_constrain", "tas_constrain"};
+static int constraint_index(const std::string &name) {
+  for (int i = 0; i < CN_HALO0; ++i)
+    if (name == kConstraintNames[i]) return i;
+  for (int g = 0; g < HX_NHALO; ++g)
+    if (name == std::string(kHaloNames[g]) + "_constrain") return CN_HALO0 + g;
+  return -1;
+}
+static std::string constraint_name(int i) {
+  return i < CN_HALO0 ? std::string(kConstraintNames[i])
+                      : std::string(kHaloNames[i - CN_HALO0]) + "_constrain";
+}
+
 static bool is_engine_param(const std::string &name) {
   for (int i = 0; i < PI_COUNT; ++i)
     if (name == kParams[i].name) return true;
@@ -171,7 +186,7 @@ bool read_ini(const std::string &path, IniInputs &out) {
     return false;
   }
   out.start_year = 0; out.end_year = 0; out.do_spinup = true; out.tracking_date = 9999;
-  std::map<int, Series> series;
+  std::map<int, Series> series, cons;
   const std::string dir = dirname_of(path);
   std::string line, section;
   int lineno = 0;
@@ -291,6 +306,38 @@ bool read_ini(const std::string &path, IniInputs &out) {
       continue;
     }
 
+    /* ---- user constraints: dated entries or a csv column ---- */
+    const int cni = constraint_index(pname);
+    if (cni >= 0) {
+      if (cni == CN_NBP) {
+        out.error = "[" + section + "] " + name + ": NBP constraints are not supported by the ensemble engine";
+        out.unsupported = true;
+        return false;
+      }
+      Series tmp;
+      if (value.compare(0, 4, "csv:") == 0) {
+        std::string csv = value.substr(4);
+        if (!file_exists(csv)) csv = dir + "/" + csv;
+        if (!read_csv_column(csv, pname, tmp, out.error)) return false;
+      } else {
+        double v;
+        if (std::isnan(date) || !parse_number(value, v)) {
+          out.error = "[" + section + "] " + name + ": a constraint needs a date and a number";
+          return false;
+        }
+        tmp[date] = v;
+      }
+      for (Series::const_iterator it = tmp.begin(); it != tmp.end(); ++it) {
+        if (it->first != std::floor(it->first)) {
+          out.error = "[" + section + "] " + name + ": constraint dates must be whole years";
+          out.unsupported = true;
+          return false;
+        }
+        cons[cni][it->first] = it->second;
+      }
+      continue;
+    }
+
     /* ---- scalars ---- */
     double v;
     if (is_engine_param(pname) || pname.find('.') != std::string::npos) {
@@ -302,7 +349,7 @@ bool read_ini(const std::string &path, IniInputs &out) {
       continue;
     }
     if (name.find("constrain") != std::string::npos || name == "lo_warming_ratio") {
-      out.error = "[" + section + "] " + name + ": constraints are not supported by the ensemble engine";
+      out.error = "[" + section + "] " + name + ": not supported by the ensemble engine";
       out.unsupported = true;
       return false;
     }
@@ -315,6 +362,15 @@ bool read_ini(const std::string &path, IniInputs &out) {
   }
   /* dense per-year tables */
   const int nrow = out.end_year - out.start_year + 1;
+  out.constraints.clear();
+  for (std::map<int, Series>::const_iterator it = cons.begin(); it != cons.end(); ++it) {
+    std::vector<double> dense(nrow, NAN);
+    for (Series::const_iterator e = it->second.begin(); e != it->second.end(); ++e) {
+      const int r = (int)e->first - out.start_year;
+      if (r >= 0 && r < nrow) dense[r] = e->second;
+    }
+    out.constraints[it->first] = dense;
+  }
   out.series.assign(RAW_COUNT, std::vector<double>());
   for (int i = 0; i < RAW_COUNT; ++i) {
     std::string nm = i < RAW_HALO0 ? kRawNames[i] : std::string(kHaloNames[i - RAW_HALO0]) + "_emissions";
@@ -391,6 +447,13 @@ extern "C" int hx_create_from_ini(const char *const *ini_paths, int32_t n_inis, 
       std::string nm = i < RAW_HALO0 ? hx::kRawNames[i]
                                      : std::string(hx::kHaloNames[i - RAW_HALO0]) + "_emissions";
       rc = hx_set_scenario_series(h, s, nm.c_str(), cfg.start_year, nrow, in[s].series[i].data());
+      if (rc) return bail(rc);
+    }
+  for (int s = 0; s < n_inis; ++s)
+    for (std::map<int, std::vector<double> >::const_iterator it = in[s].constraints.begin();
+         it != in[s].constraints.end(); ++it) {
+      rc = hx_set_scenario_series(h, s, hx::constraint_name(it->first).c_str(), cfg.start_year,
+                                  nrow, it->second.data());
       if (rc) return bail(rc);
     }
   *out = h;

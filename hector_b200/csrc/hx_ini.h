@@ -13,6 +13,7 @@ struct IniInputs {
   std::string run_name;
   std::map<std::string, double> scalars;   /* engine parameter name -> value */
   std::vector<std::vector<double>> series; /* [RAW_COUNT][nrow] dense per-year values */
+  std::map<int, std::vector<double>> constraints; /* CN_* -> [nrow], NaN = no entry */
   std::string error;
   bool unsupported = false;
 };

@@ -261,7 +261,13 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   STATE(SI_RH_CH4) = 0.0;
   STATE(SI_MAX_TIMESTEP) = HX_OCEAN_MAX_TIMESTEP; STATE(SI_TIMEOUT) = 0.0;
   STATE(SI_LASTFLUX_ANN) = 0.0; STATE(SI_SOLVER_DT) = PAR(PI_DT);
-  STATE(SI_CH4) = PAR(PI_M0); STATE(SI_TLAND) = 0.0; STATE(SI_SST) = 0.0;
+  {
+    /* CH4Component::prepareToRun (ch4_component.cpp:137-147): a CH4 constraint at the start
+     * date replaces the preindustrial value M0 (OH keeps the parameter: it read M0 earlier) */
+    const double c0 = d.scen[(size_t)d.block_scen[blockIdx.x] * C.nrow * SC_STRIDE + SC_C_CH4];
+    STATE(SI_CH4) = (c0 == c0) ? c0 : PAR(PI_M0);
+  }
+  STATE(SI_TLAND) = 0.0; STATE(SI_SST) = 0.0;
   STATE(SI_HEAT_MIXED) = 0.0; STATE(SI_HEAT_INTERIOR) = 0.0; STATE(SI_RF_PREV) = 0.0;
   STATE(SI_BASE_TOT) = 0.0; STATE(SI_BASE_CO2) = 0.0; STATE(SI_BASE_CH4) = 0.0;
   STATE(SI_BASE_N2O) = 0.0;
@@ -376,7 +382,7 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
       mb.S[SI_X_NPPLUC * HX_TILE] = (mb.S[SI_EOS_VEGC * HX_TILE] - mb.S[SI_CUM_LUC_VA * HX_TILE]) / mb.S[SI_EOS_VEGC * HX_TILE];
       const double o0 = mb.atmos, o1 = mb.veg, o2 = mb.det, o3 = mb.soil, o4 = mb.perm,
                    o5 = mb.thawed, o6 = total_ocean(mb), o7 = mb.earth;
-      solver_year<true, false>(mb, C, p, ck, &rk[0][threadIdx.x], HX_BLOCK, (double)(step - 1), (double)step, true, w);
+      solver_year<true, false, false>(mb, C, p, ck, &rk[0][threadIdx.x], HX_BLOCK, (double)(step - 1), (double)step, true, w);
       if (mb.status) break;
       double mx = fabs(mb.atmos - o0);
       mx = fmax(mx, fabs(mb.veg - o1)); mx = fmax(mx, fabs(mb.det - o2));
@@ -480,8 +486,8 @@ __device__ __forceinline__ void conv_prepass(const double *__restrict__ sst,
 /* ======================================================================================== */
 /* the yearly coupled step, rows r0+1 .. r1 (row = year - start_year).  TRACK = carbon tracking
  * compiled in (a second instantiation: the plain kernel carries none of its code). */
-template <bool TRACK>
-__global__ void __launch_bounds__(HX_BLOCK, HX_RUN_MIN_CTAS)
+template <bool TRACK, bool CONSTR, int MINCTAS>
+__global__ void __launch_bounds__(HX_BLOCK, MINCTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   /* dynamic shared memory (> 48 KB): scenario slabs | row 0 | chemistry constants | RK stages */
   extern __shared__ __align__(128) unsigned char hx_smem[];
@@ -590,7 +596,12 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           const double strat_sink = previous_ch4 * DER(DI_INV_TSTRAT);
           const double oh_sink = previous_ch4 / tau_oh;
           const double dCH4 = emisTocon - soil_sink - strat_sink - oh_sink;
-          STATE(SI_CH4) = previous_ch4 + dCH4;
+          double ch4_new = previous_ch4 + dCH4;
+          if (CONSTR) { /* concentration-forced year: ch4_component.cpp:156-158 */
+            const double c = sc[SC_C_CH4];
+            if (c == c) ch4_new = c;
+          }
+          STATE(SI_CH4) = ch4_new;
         }
 
         /* --- OceanComponent::run: ocean_component.cpp:356-407 --- */
@@ -623,6 +634,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           }
           mb.luc_e = scm1[SC_LUC_E]; mb.luc_u = scm1[SC_LUC_U];
           mb.S[SI_X_FFI * HX_TILE] = scm1[SC_FFI]; mb.S[SI_X_DACCS * HX_TILE] = scm1[SC_DACCS];
+          if (CONSTR) mb.S[SI_X_C_CO2 * HX_TILE] = sc[SC_C_CO2];
           mb.neg |= (mb.luc_e < 0.0) | (mb.luc_u < 0.0) | (mb.S[SI_X_FFI * HX_TILE] < 0.0) | (mb.S[SI_X_DACCS * HX_TILE] < 0.0);
           /* Tland_rm: for (i = t-200; i < t; i++) Tland_rm += Tland_record.get(i) * wf; /= 200
            * (:1041-1050).  Keys below the first record (start+1) extrapolate flat to it and
@@ -649,7 +661,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         }
 
         /* --- CarbonCycleSolver::run --- */
-        solver_year<false, TRACK>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
+        solver_year<false, TRACK, CONSTR>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
         if (mb.status) {
           d.status[m] = mb.status;
           d.fail_year[m] = y;
@@ -678,12 +690,23 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         double rf_tot = 0.0, rf_co2 = 0.0, rf_ch4 = 0.0, rf_n2o = 0.0;
         if (y >= C.baseyear) {
           ForcPar fp;
-          fp.C0 = LP_C0(p); fp.M0 = PAR(PI_M0); fp.N0 = PAR(PI_N0); fp.aero = PAR(PI_AERO);
+          /* preindustrial CH4 / N2O as the CH4 and N2O components hold them after prepareToRun:
+           * a start-date constraint replaces the parameter (ch4_component.cpp:141-146,
+           * n2o_component.cpp:141-146; row 0 of the N2O series is N0 by construction) */
+          fp.C0 = LP_C0(p); fp.M0 = PAR(PI_M0); fp.N0 = row0[SC_N2O]; fp.aero = PAR(PI_AERO);
+          if (CONSTR) {
+            const double c0 = row0[SC_C_CH4];
+            if (c0 == c0) fp.M0 = c0;
+          }
           fp.vol = PAR(PI_VOL); fp.delta_co2 = PAR(PI_DELTA_CO2); fp.delta_ch4 = PAR(PI_DELTA_CH4);
           fp.delta_n2o = PAR(PI_DELTA_N2O); fp.rho_bc = PAR(PI_RHO_BC); fp.rho_oc = PAR(PI_RHO_OC);
           fp.rho_so2 = PAR(PI_RHO_SO2); fp.rho_nh3 = PAR(PI_RHO_NH3);
           double fco2, fch4, fn2o;
-          const double F = forcing_total(fp, sc, CO2_conc, ch4, o3, fco2, fch4, fn2o, mb.status);
+          double F = forcing_total(fp, sc, CO2_conc, ch4, o3, fco2, fch4, fn2o, mb.status);
+          if (CONSTR) { /* user-supplied total forcing: forcing_component.cpp:498-505 */
+            const double c = sc[SC_C_RFTOT];
+            if (c == c) F = c;
+          }
           if (y == C.baseyear) {
             STATE(SI_BASE_TOT) = F; STATE(SI_BASE_CO2) = fco2; STATE(SI_BASE_CH4) = fch4;
             STATE(SI_BASE_N2O) = fn2o;
@@ -734,11 +757,21 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           const double DPAST1 = 0.0;
           const double DTEAUX1 = DER(DI_A0) * tland + DER(DI_A1) * sst;
           const double DTEAUX2 = DER(DI_A2) * tland + DER(DI_A3) * sst;
-          const double TL = DER(DI_IB0) * (DQ1 + DPAST1 + DTEAUX1) +
-                            DER(DI_IB1) * (DQ2 + DPAST2 + DTEAUX2);
-          const double TS = DER(DI_IB2) * (DQ1 + DPAST1 + DTEAUX1) +
-                            DER(DI_IB3) * (DQ2 + DPAST2 + DTEAUX2);
+          double TL = DER(DI_IB0) * (DQ1 + DPAST1 + DTEAUX1) +
+                      DER(DI_IB1) * (DQ2 + DPAST2 + DTEAUX2);
+          double TS = DER(DI_IB2) * (DQ1 + DPAST1 + DTEAUX1) +
+                      DER(DI_IB3) * (DQ2 + DPAST2 + DTEAUX2);
           tas = flnd * TL + (1.0 - flnd) * bsi * TS;
+          if (CONSTR) {
+            /* user-supplied global temperature (:510-525): overwrite, then back-calculate the
+             * land and sea-surface values that go into the histories */
+            const double c = sc[SC_C_TAS];
+            if (c == c) {
+              tas = c;
+              TL = (tas - (1.0 - flnd) * bsi * TS) / flnd;
+              TS = (tas - flnd * TL) / ((1.0 - flnd) * bsi);
+            }
+          }
           const double hf_mixed = cas * (TS - sst);
           const double hf_int = DER(DI_HF_INT) * (2.0 * TS - hint);
           STATE(SI_HEAT_MIXED) = STATE(SI_HEAT_MIXED) + hf_mixed * (C.powtoheat * dt);
@@ -871,11 +904,11 @@ cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cuda
   hx_spinup_kernel<<<1, HX_BLOCK, 0, st>>>(d, C, member - member % HX_BLOCK, member);
   return cudaGetLastError();
 }
-template <bool TRACK>
+template <bool TRACK, bool CONSTR, int MINCTAS>
 static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK>,
+    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
@@ -886,7 +919,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS>,
                                                                   HX_BLOCK, HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
     resident = sms * (per_sm > 0 ? per_sm : 1);
@@ -896,11 +929,27 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   const int grid = ntiles < resident ? ntiles : resident;
   cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  hx_run_kernel<TRACK><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
+  hx_run_kernel<TRACK, CONSTR, MINCTAS><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
-  return d.T ? launch_run_t<true>(d, C, r0, r1, st) : launch_run_t<false>(d, C, r0, r1, st);
+  /* Two register budgets.  Big ensembles run the 168-register build: 3 CTAs (12 warps) per SM
+   * hide more FP64 latency than its few spills cost (39.1 vs 40.8 ms at 65 536 members).  When
+   * every tile is resident anyway at 2 CTAs per SM the run is pure latency and the spill-free
+   * 230-register build wins (17.0 vs 20.5 ms at 1 024 members).  The tracking build is bound by
+   * its map traffic, not by occupancy, and spills badly at 168 registers. */
+  if (d.T)
+    return d.constrained ? launch_run_t<true, true, 2>(d, C, r0, r1, st)
+                         : launch_run_t<true, false, 2>(d, C, r0, r1, st);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool small = d.Mpad / HX_BLOCK <= 2 * sms;
+  if (d.constrained)
+    return small ? launch_run_t<false, true, 2>(d, C, r0, r1, st)
+                 : launch_run_t<false, true, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
+  return small ? launch_run_t<false, false, 2>(d, C, r0, r1, st)
+               : launch_run_t<false, false, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
 }
 cudaError_t launch_track_init(const HxDev &d, cudaStream_t st) {
   hx_track_init_kernel<<<(d.Mpad + 255) / 256, 256, 0, st>>>(d);

@@ -12,7 +12,7 @@
 #define HX_CONV_UNROLL 8 /* history rows per trip of the slab prepass of the DOECLIM convolution */
 #endif
 #ifndef HX_RUN_MIN_CTAS
-#define HX_RUN_MIN_CTAS 2 /* resident CTAs per SM the run kernel is register-limited to */
+#define HX_RUN_MIN_CTAS 3 /* resident CTAs per SM the run kernel is compiled for (168 registers: a few spills, but 12 instead of 8 warps per SM hide more FP64 latency; measured 39.3 vs 40.8 ms) */
 #endif
 
 struct HxDev {
@@ -33,6 +33,7 @@ struct HxDev {
   unsigned long long *counters; /* [HX_NCOUNTERS] */
   unsigned *sched;              /* [1 + Mpad / HX_BLOCK]: work-queue ticket, per-tile progress */
   int32_t out_slot[OUT_COUNT];  /* output id -> slot in `out`, -1 = not recorded */
+  int32_t constrained;      /* some scenario carries a CO2 / CH4 / RF_tot / tas constraint */
   /* carbon tracking (null unless a tracking date was set) */
   double *T;                /* [tile][TS_COUNT * HX_NSRC][128] source fractions */
   uint32_t *TK;             /* [tile][TS_COUNT][128] key masks */

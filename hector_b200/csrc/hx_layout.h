@@ -43,8 +43,18 @@ enum {
   SC_BC, SC_OC, SC_SO2, SC_NH3, SC_SV, SC_ALBEDO, SC_MISC,
   SC_N2O,   /* N2O concentration, host-precomputed (member independent) */
   SC_HALO0, /* 26 halocarbon forcings, host-precomputed */
-  SC_USED = SC_HALO0 + HX_NHALO, /* 43 */
-  SC_STRIDE = 44                 /* 352 B per row: multiple of 16 B for cp.async.bulk */
+  /* user constraints of the year (NaN = none): atmospheric CO2 [ppmv], CH4 [ppbv], total
+   * forcing [W/m2], global mean temperature [degC]; N2O and halocarbon constraints are already
+   * folded into SC_N2O / SC_HALO0.. on the host */
+  SC_C_CO2 = SC_HALO0 + HX_NHALO, SC_C_CH4, SC_C_RFTOT, SC_C_TAS,
+  SC_USED,                       /* 47 */
+  SC_STRIDE = 48                 /* 384 B per row: multiple of 16 B for cp.async.bulk */
+};
+
+/* ---- constraint series (what callers hand in), reference input names ---- */
+enum {
+  CN_CO2 = 0, CN_NBP, CN_CH4, CN_N2O, CN_RFTOT, CN_TAS, CN_HALO0,
+  CN_COUNT = CN_HALO0 + HX_NHALO
 };
 
 /* ---- per-member parameters ---- */
@@ -77,6 +87,7 @@ enum {
   /* per-year scratch (slowparameval results, emissions, annual sums) parked between phases */
   SI_X_CO2FERT, SI_X_TFD, SI_X_TFS, SI_X_FNEWTHAW, SI_X_NPPLUC, SI_X_FFI, SI_X_DACCS, SI_X_NBP,
   SI_X_FLUXSUM,
+  SI_X_C_CO2, /* this year's CO2 constraint (NaN = none), read by the year's last stash */
   SI_COUNT
 };
 

@@ -171,6 +171,20 @@ class Ensemble:
             v = np.ascontiguousarray(values, dtype=np.float64)
             self._chk(self.L.hx_set_param(self.h, name.encode(), _dp(v), v.size))
 
+    def setvar_series(self, name, years, values, scenario=0):
+        """R setvar(core, dates, var, values): a dated input of one scenario -- an emissions
+        series (must cover start..end) or a user constraint (CO2_constrain, tas_constrain,
+        RF_tot_constrain, CH4_constrain, N2O_constrain, <gas>_constrain; any subset of years,
+        tests/testthat/test_constraints.R).  After prepare() it takes effect at the next
+        reset()/run(), like the reference's setvar + reset."""
+        years = np.asarray(years, dtype=np.int64)
+        values = np.asarray(values, dtype=np.float64)
+        y0, y1 = int(years.min()), int(years.max())
+        dense = np.full(y1 - y0 + 1, np.nan)
+        dense[years - y0] = values
+        self._chk(self.L.hx_set_scenario_series(self.h, int(scenario), name.encode(), y0,
+                                                dense.size, _dp(dense)))
+
     def setvar_device(self, name, dev_ptr, n):
         self._chk(self.L.hx_set_param_device(self.h, name.encode(), C.c_void_p(int(dev_ptr)), n))
 

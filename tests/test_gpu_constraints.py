@@ -1,0 +1,167 @@
+"""GPU parity of user constraints (tests/testthat/test_constraints.R
+territory): CO2 / tas / RF_tot / CH4 / N2O / halocarbon concentration series, through the C ABI,
+against the unmodified reference's committed known answers (tests/golden/ref_constraints.npz)."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+YEARS = np.arange(1746, 2301, dtype=np.float64)
+CASES = [c for c in util.ref_constraints() if not c["name"].startswith("nbp")]
+
+
+def _apply(ens, spec, scenario=0):
+    for name, d in spec.items():
+        ys = sorted(d)
+        ens.setvar_series(name, ys, [d[y] for y in ys], scenario=scenario)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
+def test_constraints_vs_reference_golden(case):
+    import hector_b200 as hb
+    variables = list(case["values"])
+    ens = hb.Ensemble(2, util.scenarios()["ssp245"], outputs=variables)
+    _apply(ens, case["spec"])
+    ens.run()
+    st, _ = ens.status()
+    assert (st == 0).all()
+    got = ens.fetchvars(YEARS)
+    bad = {}
+    for v in variables:
+        e = util.parity_err(got[v][0], case["values"][v], v)
+        if e > TOL:
+            bad[v] = e
+        assert np.array_equal(got[v][0], got[v][1])
+    assert not bad, bad
+    ens.close()
+
+
+def test_constraint_roundtrip_like_the_reference_test():
+    """test_constraints.R: feed a run's own CH4 / N2O / CO2 back as constraints (setvar after
+    the run, then reset) and get the same climate; scale the CH4 constraint and see it come
+    back verbatim and warm the planet."""
+    import hector_b200 as hb
+    outs = ["global_tas", "CH4_concentration", "N2O_concentration", "CO2_concentration", "RF_CH4"]
+    ens = hb.Ensemble(4, util.scenarios()["ssp245"], outputs=outs)
+    S = np.array([2.5, 3.0, 3.5, 4.0])
+    ens.setvar("S", S)
+    ens.run()
+    free = ens.fetchvars(YEARS)
+    yrs = YEARS.astype(int)
+    # all members share the CH4 / N2O trajectories only if rh_ch4 is negligible; use member 1
+    ens.setvar_series("N2O_constrain", yrs, free["N2O_concentration"][1])
+    ens.reset()
+    ens.run()
+    con = ens.fetchvars(YEARS)
+    for v in outs:
+        assert util.parity_err(con[v][1], free[v][1], v) < TOL, v
+    # now a perturbed CH4 constraint
+    new_ch4 = free["CH4_concentration"][1] * 3
+    ens.setvar_series("CH4_constrain", yrs, new_ch4)
+    ens.reset()
+    ens.run()
+    pert = ens.fetchvars(YEARS)
+    assert np.array_equal(pert["CH4_concentration"][0], new_ch4)
+    assert np.array_equal(pert["CH4_concentration"][3], new_ch4)
+    sel = (YEARS >= 2000) & (YEARS <= 2100)
+    assert (pert["global_tas"][:, sel] >= con["global_tas"][:, sel]).all()
+    assert (pert["RF_CH4"][:, sel] > con["RF_CH4"][:, sel]).all()
+    ens.close()
+
+
+def test_constraints_per_scenario_and_perturbed_members_vs_oracle():
+    """two scenarios in one engine, only one of them constrained; perturbed members against
+    the oracle"""
+    from oracle import port
+    import hector_b200 as hb
+    tabs = util.scenarios()
+    case = [c for c in util.ref_constraints() if c["name"] == "combo"][0]
+    M = 12
+    X = util.lhs(M, seed=7)
+    scen = np.arange(M) % 2
+    ens = hb.Ensemble(M, [tabs["ssp245"], tabs["ssp245"]], member_scenario=scen,
+                      outputs=["CO2_concentration", "global_tas", "ocean_timesteps"])
+    for j, n in enumerate(["S", "q10_rh", "beta", "diff"]):
+        ens.setvar(n, X[:, j])
+    _apply(ens, case["spec"], scenario=1)
+    ens.run()
+    st, _ = ens.status()
+    assert (st == 0).all()
+    got = ens.fetchvars(YEARS)
+    for i in (0, 1, 6, 11):
+        kw = dict(S=X[i, 0], q10_rh=X[i, 1], beta=X[i, 2], diff=X[i, 3])
+        if scen[i] == 1:
+            ost, _, out = port.run_member_constrained(tabs["ssp245"], case["spec"], **kw)
+        else:
+            ost, _, out, _, _ = port.run_member(tabs["ssp245"], **kw)
+        assert ost == 0
+        assert np.array_equal(got["ocean_timesteps"][i], out[-1]), i
+        assert util.parity_err(got["CO2_concentration"][i], out[0], "CO2_concentration") < TOL
+        assert util.parity_err(got["global_tas"][i], out[1], "global_tas") < TOL
+    ens.close()
+
+
+def test_co2_constraint_with_tracking_sends_untracked_carbon_to_the_deep_ocean():
+    """CO2 constraint + carbon tracking: the residual dumped into the deep box shows up as
+    source "untracked" (fluxpool.hpp:181-192 via ocean_component.cpp:146-154)"""
+    from oracle import port
+    import hector_b200 as hb
+    tab = util.scenarios()["ssp245"]
+    case = [c for c in util.ref_constraints() if c["name"] == "co2_part"][0]
+    ens = hb.Ensemble(1, tab, outputs=["CO2_concentration"], tracking_date=1900, track_every=0)
+    _apply(ens, case["spec"])
+    ens.run()
+    frac, mask = ens.fetch_tracking(2300)
+    deep = hb.TRACK_POOLS.index("deep")
+    unt = hb.TRACK_SOURCES.index("untracked")
+    assert mask[0, deep] >> unt & 1
+    assert frac[0, deep, unt] > 0
+    assert abs(frac[0].sum(axis=1) - 1).max() < 1e-12
+    got = ens.fetch("CO2_concentration", YEARS)
+    assert util.parity_err(got[0], case["values"]["CO2_concentration"], "CO2_concentration") < TOL
+    ens.close()
+
+
+def test_nbp_constraint_is_reported_unsupported():
+    import hector_b200 as hb
+    ens = hb.Ensemble(1, util.scenarios()["ssp245"])
+    with pytest.raises(hb.HxError):
+        ens.setvar_series("NBP_constrain", [1900, 1901], [1.0, 1.0])
+    ens.close()
+
+
+def test_constraints_from_ini_file(tmp_path):
+    """newcore(ini) with tas_constrain=csv:tables/tas_historical.csv (the table the reference
+    ships) and a dated CO2_constrain entry == the same constraints set through the API, and ==
+    the oracle"""
+    import csv
+    import os
+    from oracle import port
+    import hector_b200 as hb
+    from tests.test_ini_reader_cpu import constrained_ini, input_dir
+    ini = constrained_ini(tmp_path)
+    tas = {}
+    for row in csv.reader(open(os.path.join(input_dir(), "tables", "tas_historical.csv"))):
+        if len(row) == 2 and row[0].strip().isdigit():
+            tas[int(row[0])] = float(row[1])
+    spec = {"tas_constrain": tas, "CO2_constrain": {1900: 296.0}}
+    a = hb.Ensemble.from_ini(ini, 2, outputs=["CO2_concentration", "global_tas", "sst"])
+    b = hb.Ensemble(2, util.scenarios()["ssp245"], outputs=["CO2_concentration", "global_tas", "sst"])
+    _apply(b, spec)
+    for e in (a, b):
+        e.setvar("S", np.array([2.5, 4.0]))
+        e.run()
+    ya, yb = a.fetchvars(YEARS), b.fetchvars(YEARS)
+    for v in ya:
+        assert np.array_equal(ya[v], yb[v]), v
+    ost, _, out = port.run_member_constrained(util.scenarios()["ssp245"], spec, S=4.0)
+    assert ost == 0
+    assert util.parity_err(ya["CO2_concentration"][1], out[0], "CO2_concentration") < TOL
+    assert util.parity_err(ya["global_tas"][1], out[1], "global_tas") < TOL
+    yrs = np.array(sorted(tas))
+    assert np.allclose(ya["global_tas"][1][yrs - 1746], [tas[y] for y in yrs], rtol=0, atol=1e-15)
+    a.close()
+    b.close()

@@ -60,11 +60,34 @@ def test_unsupported_inputs_are_reported(tmp_path):
     d = input_dir()
     bad = tmp_path / "constrained.ini"
     bad.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
-        "[temperature]", "[temperature]\ntas_constrain=csv:%s/tables/tas_historical.csv" % d))
+        "[simpleNbox]", "[simpleNbox]\nNBP_constrain[2000]=1.0"))
     assert L.hx_ini_read(str(bad).encode(), None, None, None, 0) == -4
-    assert b"constrain" in L.hx_last_error(None)
+    assert b"NBP" in L.hx_last_error(None)
+    bad3 = tmp_path / "lo.ini"
+    bad3.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
+        "[temperature]", "[temperature]\nlo_warming_ratio=1.6"))
+    assert L.hx_ini_read(str(bad3).encode(), None, None, None, 0) == -4
     bad2 = tmp_path / "unknown.ini"
     bad2.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
         "[temperature]", "[temperature]\nnot_a_variable=1"))
     assert L.hx_ini_read(str(bad2).encode(), None, None, None, 0) == -1
     assert b"Unknown variable" in L.hx_last_error(None)
+
+
+def constrained_ini(tmp_path):
+    """hector_ssp245.ini + the shipped HadCRUT temperature constraint table + a dated CO2 entry"""
+    d = input_dir()
+    src = open(os.path.join(d, "hector_ssp245.ini")).read()
+    p = tmp_path / "ssp245_tas.ini"
+    p.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
+        "[temperature]", "[temperature]\ntas_constrain=csv:%s/tables/tas_historical.csv" % d).replace(
+        "[simpleNbox]", "[simpleNbox]\nCO2_constrain[1900]=296.0"))
+    return str(p)
+
+
+def test_constraint_inputs_are_read(tmp_path):
+    """tas_constrain=csv:... and dated CO2_constrain[...] entries parse (host-only check)"""
+    L = need_lib()
+    y0, y1 = C.c_int32(), C.c_int32()
+    assert L.hx_ini_read(constrained_ini(tmp_path).encode(), C.byref(y0), C.byref(y1), None, 0) == 0
+    assert (y0.value, y1.value) == (1745, 2300)
