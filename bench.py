@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--members", type=int, default=65536, help="members per GPU")
     ap.add_argument("--small-members", type=int, default=1024,
                     help="also time BASELINE.json configs[1] (0 = skip)")
+    ap.add_argument("--tracked-members", type=int, default=65536,
+                    help="also time a carbon-tracking ensemble to 2500 (0 = skip)")
     ap.add_argument("--ref-members-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -342,6 +344,32 @@ def main():
                  "%d of 148 SMs' worth of CTAs" % ((ms_ + 127) // 128)}
         es.close()
 
+    # ---- BASELINE.json configs[4] flavour: SSP5-8.5 to 2500 with carbon tracking on ----
+    tracked = None
+    if args.tracked_members and rank == 0 and world == 1:
+        raw = scenario_table("ssp585")
+        ext = np.vstack([raw, np.repeat(raw[-1:], 200, axis=0)])  # series held at 2300 values
+        mt = args.tracked_members
+        rng = np.random.Generator(np.random.PCG64(20241018))
+        lo6 = np.array([2.0, 1.0, 0.2, 0.5, 0.5, 0.8]); hi6 = np.array([5.0, 2.6, 0.9, 2.5, 1.5, 1.2])
+        X6 = lo6 + rng.random((mt, 6)) * (hi6 - lo6)
+        et = hb.Ensemble(mt, ext, end_year=2500, device=local_rank,
+                         outputs=["CO2_concentration", "global_tas"], tracking_date=1750,
+                         track_every=0, stream=stream.cuda_stream)
+        for j, nme in enumerate(PARAMS + ["aero_scalar", "vol_scalar"]):
+            et.setvar(nme, np.ascontiguousarray(X6[:, j]))
+        et.prepare()
+        et.synchronize()
+        tr_ms, _ = timed(et, lambda e: (e.reset(), e.run()), max(2, args.steps // 2), 3, False)
+        tr_ms /= max(2, args.steps // 2)
+        stt, _ = et.status()
+        tracked = {"members": mt, "years": 755, "value": mt * 755 / (tr_ms * 1e-3), "unit": UNIT,
+                   "ms_per_step": tr_ms, "failed_members": int((stt != 0).sum()),
+                   "note": "BASELINE.json configs[4] flavour on one GPU: Monte-Carlo over (S, "
+                           "q10_rh, beta, diff, aero_scalar, vol_scalar), SSP5-8.5 1745->2500, "
+                           "carbon tracking from 1750 (11 pools x 12 sources per member)"}
+        et.close()
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -386,7 +414,7 @@ def main():
         "work_per_member_year": {k: cnt[k] / max(1, cnt["member_years"]) for k in
                                  ("rhs_evals", "rk_steps", "stashes", "newton_iterations",
                                   "newton_calls")},
-        "failed_members": failed, "small_ensemble": small,
+        "failed_members": failed, "small_ensemble": small, "tracked_ensemble": tracked,
     }
     print(json.dumps(line))
     ens.close()

@@ -15,7 +15,7 @@ EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "h
            "hx_set_scenario_table", "hx_set_member_scenario", "hx_set_param_scalar",
            "hx_set_param", "hx_set_param_device", "hx_get_param", "hx_select_outputs",
            "hx_prepare", "hx_run", "hx_reset", "hx_synchronize", "hx_fetch", "hx_output_device",
-           "hx_member_status", "hx_set_tracking", "hx_fetch_tracking", "hx_counters", "hx_current_date", "hx_last_run_ms",
+           "hx_member_status", "hx_set_tracking", "hx_fetch_tracking", "hx_tracking_years", "hx_counters", "hx_current_date", "hx_last_run_ms",
            "hx_spinup_state", "hx_version"]
 
 
@@ -73,6 +73,7 @@ def lib():
     L.hx_output_device.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_int64), ip]
     L.hx_set_tracking.argtypes = [vp, C.c_int32, C.c_int32]
     L.hx_fetch_tracking.argtypes = [vp, C.c_double, dp, C.POINTER(C.c_uint32)]
+    L.hx_tracking_years.argtypes = [vp, ip, C.c_int32]
     L.hx_member_status.argtypes = [vp, ip, ip, C.c_int32]
     L.hx_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int32]
     L.hx_current_date.argtypes = [vp]

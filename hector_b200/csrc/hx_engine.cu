@@ -489,8 +489,7 @@ int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, i
     if (ci == CN_NBP)
       return h->fail(HX_ERR_UNSUPPORTED, "NBP_constrain is not supported by the ensemble engine");
     double *dst = h->cons[scenario_id].data() + (size_t)ci * h->nrow;
-    for (int r = 0; r < h->nrow; ++r) dst[r] = NAN;
-    for (int k = 0; k < n; ++k) {
+    for (int k = 0; k < n; ++k) { /* entries outside [year0, year0 + n) are kept */
       const int r = year0 + k - h->cfg.start_year;
       if (r >= 0 && r < h->nrow) dst[r] = values[k];
     }
@@ -917,6 +916,14 @@ int hx_set_tracking(hx_handle h, int32_t tracking_date, int32_t record_every) {
   h->tracking_date = tracking_date;
   h->track_every = record_every;
   return HX_OK;
+}
+
+int hx_tracking_years(hx_handle h, int32_t *years, int32_t cap) {
+  if (!h) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_tracking_years before hx_prepare");
+  const int n = (int)h->track_years.size();
+  for (int i = 0; i < n && i < cap && years; ++i) years[i] = h->track_years[i];
+  return n;
 }
 
 int hx_fetch_tracking(hx_handle h, double date, double *frac, uint32_t *mask) {

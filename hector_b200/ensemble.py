@@ -244,6 +244,14 @@ class Ensemble:
                                            mask.ctypes.data_as(C.POINTER(C.c_uint32))))
         return frac, mask
 
+    def tracking_years(self):
+        n = self.L.hx_tracking_years(self.h, None, 0)
+        if n < 0:
+            self._chk(n)
+        out = np.zeros(max(n, 1), dtype=np.int32)
+        self.L.hx_tracking_years(self.h, out.ctypes.data_as(C.POINTER(C.c_int32)), n)
+        return out[:n]
+
     def tracking_data(self, member, dates):
         """get_tracking_data (R/messages.R, Core::getTrackingData, csv_tracking_visitor.cpp:88-103)
         for one member: rows (year, component, pool_name, pool_value, pool_units, source_name,

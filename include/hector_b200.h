@@ -172,6 +172,9 @@ int hx_set_tracking(hx_handle h, int32_t tracking_date, int32_t record_every);
  * bit s says that source s is a key of the pool's map (the rows the reference's tracking CSV
  * prints; a key can carry fraction 0).  `date` must be a recorded year or the current date. */
 int hx_fetch_tracking(hx_handle h, double date, double *frac, uint32_t *mask);
+/* the recorded years, ascending; returns their count (0 when tracking is off) or a negative
+ * error; at most `cap` are written */
+int hx_tracking_years(hx_handle h, int32_t *years, int32_t cap);
 
 int hx_member_status(hx_handle h, int32_t *status, int32_t *fail_year, int32_t n);
 int hx_counters(hx_handle h, uint64_t *out, int32_t n);

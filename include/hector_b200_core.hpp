@@ -71,7 +71,7 @@ class h_exception : public std::exception {
 /* ---- units (unitval.hpp:68-130): the ones variables of this path carry ---- */
 enum unit_types {
   U_UNITLESS, U_PPMV_CO2, U_PPBV_CH4, U_PPBV_N2O, U_DU_O3, U_TG_PPBV, U_DEGC, U_CM2_S, U_PGC,
-  U_PGC_YR, U_W_M2, U_W_M2_TG, U_W_M2_GG, U_M3_S, U_PH, U_UATM, U_YRS, U_UNDEFINED
+  U_PGC_YR, U_W_M2, U_W_M2_TG, U_W_M2_GG, U_M3_S, U_PH, U_UATM, U_YRS, U_PPTV, U_UNDEFINED
 };
 
 class unitval {
@@ -85,7 +85,7 @@ class unitval {
     static const char *const names[] = {"(unitless)", "ppmv CO2", "ppbv CH4", "ppbv N2O", "DU O3",
                                         "Tg/ppbv", "degC", "cm2/s", "Pg C", "Pg C/yr", "W/m2",
                                         "W/m2/Tg", "W/m2/Gg", "m3/s", "pH", "uatm", "Years",
-                                        "(undefined)"};
+                                        "pptv", "(undefined)"};
     return names[(int)u];
   }
   static unit_types parseUnitsName(const std::string &s) {
@@ -173,9 +173,16 @@ inline unit_types units_of(const std::string &v) {
       {"rho_oc", U_W_M2_TG}, {"rho_so2", U_W_M2_GG}, {"rho_nh3", U_W_M2_TG}, {"M0", U_PPBV_CH4},
       {"N0", U_PPBV_N2O}, {"Tsoil", U_YRS}, {"Tstrat", U_YRS}, {"TOH0", U_YRS},
       {"UC_CH4", U_TG_PPBV}, {"CNOX", U_UNITLESS}, {"CCO", U_UNITLESS}, {"CNMVOC", U_UNITLESS},
-      {"CCH4", U_UNITLESS}};
+      {"CCH4", U_UNITLESS},
+      /* user constraints (component_data.hpp:46, 263, 273, 379-381) and [core] trackingDate */
+      {"CO2_constrain", U_PPMV_CO2}, {"tas_constrain", U_DEGC}, {"RF_tot_constrain", U_W_M2},
+      {"CH4_constrain", U_PPBV_CH4}, {"N2O_constrain", U_PPBV_N2O}, {"NBP_constrain", U_PGC_YR},
+      {"trackingDate", U_UNITLESS}};
   for (const VarUnit &e : tab)
     if (v == e.name) return e.units;
+  const std::string suffix = "_constrain"; /* <gas>_constrain: halocarbon concentrations */
+  if (v.size() > suffix.size() && v.compare(v.size() - suffix.size(), suffix.size(), suffix) == 0)
+    return U_PPTV;
   return U_UNDEFINED;
 }
 inline const char *member_failure(int status) { /* the reference's exception text */
@@ -188,6 +195,7 @@ inline const char *member_failure(int status) { /* the reference's exception tex
     case HX_MEMBER_CO2SARF: return "CO2 SARF could not be calculated";
     case HX_MEMBER_STEPPER: return "Max number of iterations exceeded in odeint";
     case HX_MEMBER_SPINUP: return "spin-up did not converge";
+    case HX_MEMBER_TRACKING: return "fractions must be 0-1";
     default: return "model failure";
   }
 }
@@ -232,7 +240,10 @@ class EnsembleCore {
     need();
     const unit_types want = detail::units_of(varName);
     const unitval v = data.getUnitval(want);
-    if (data.date != message_data::undefined()) {
+    if (varName == "trackingDate") { /* [core] trackingDate, core.cpp:228-235 */
+      chk(hx_set_tracking(h_, (int32_t)(double)v, 1));
+    } else if (data.date != message_data::undefined()) {
+      /* a dated input: one entry of a user constraint (emission series come from the ini) */
       const double d = v;
       chk(hx_set_scenario_series(h_, 0, varName.c_str(), (int32_t)data.date, 1, &d));
     } else {
@@ -324,6 +335,42 @@ class EnsembleCore {
     std::vector<double> col(n_);
     chk(hx_fetch(h_, varName.c_str(), &date, 1, col.data()));
     return unitval(col[member], u);
+  }
+  /* Core::getTrackingData (core.cpp:199-209): the CSVFluxPoolVisitor's text for one member,
+   * "year,component,pool_name,pool_value,pool_units,source_name,source_fraction" for every
+   * recorded year up to the current date (csv_tracking_visitor.cpp:80-137); "" when tracking
+   * is off.  Numbers are printed with the stream's default 6 significant digits, like there. */
+  std::string getTrackingData(int member = 0) {
+    need();
+    if (member < 0 || member >= n_) HXB_THROW("member index out of range");
+    static const char *const pools[HX_TRACK_NPOOL] = {"atmos_co2", "earth_c", "veg_c", "detritus_c",
+                                                      "soil_c", "permafrost_c", "thawedp_c", "HL",
+                                                      "LL", "intermediate", "deep"};
+    static const char *const pool_var[HX_TRACK_NPOOL] = {
+        "atmos_co2", "earth_c", "veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c",
+        "HL_ocean_c", "LL_ocean_c", "IO_ocean_c", "DO_ocean_c"};
+    const int ny = prepared_ ? hx_tracking_years(h_, nullptr, 0) : 0;
+    if (ny <= 0) return std::string();
+    std::vector<int32_t> years(ny);
+    hx_tracking_years(h_, years.data(), ny);
+    std::vector<double> frac((size_t)n_ * HX_TRACK_NPOOL * HX_TRACK_NSRC), col(n_);
+    std::vector<uint32_t> mask((size_t)n_ * HX_TRACK_NPOOL);
+    std::ostringstream os;
+    os << "year,component,pool_name,pool_value,pool_units,source_name,source_fraction\n";
+    for (int32_t y : years) {
+      if (y > getCurrentDate()) break;
+      chk(hx_fetch_tracking(h_, (double)y, frac.data(), mask.data()));
+      for (int k = 0; k < HX_TRACK_NPOOL; ++k) {
+        const double date = y;
+        chk(hx_fetch(h_, pool_var[k], &date, 1, col.data()));
+        for (int s = 0; s < HX_TRACK_NSRC; ++s)
+          if (mask[(size_t)member * HX_TRACK_NPOOL + k] >> s & 1u)
+            os << y << "," << (k < 7 ? "simpleNbox" : "ocean") << "," << pools[k] << ","
+               << col[member] << ",Pg C," << (s < HX_TRACK_NPOOL ? pools[s] : "untracked") << ","
+               << frac[((size_t)member * HX_TRACK_NPOOL + k) * HX_TRACK_NSRC + s] << "\n";
+      }
+    }
+    return os.str();
   }
   /* R fetchvars for the whole ensemble: out[member][date] */
   void fetch(const std::string &varName, const std::vector<double> &dates, double *out) {

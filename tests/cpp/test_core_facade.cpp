@@ -115,6 +115,37 @@ int main(int argc, char **argv) {
   EXPECT(Core::getcore(idx) == nullptr);
   Core::delcore(idx); /* idempotent */
 
+  /* ---- carbon tracking + a user constraint, like tests/testthat/test_tracking.R and
+   * test_constraints.R drive them: setData before prepareToRun, getTrackingData after ---- */
+  {
+    Core tc(Logger::SEVERE, false, false);
+    tc.init();
+    INIToCoreReader(&tc).parse(ini);
+    EXPECT(tc.getTrackingData().empty());
+    tc.setData("core", "trackingDate", message_data(unitval(1990, U_UNITLESS)));
+    for (int y = 2000; y <= 2010; ++y) /* dated entries accumulate, one setData per year */
+      tc.setData("CH4", "CH4_constrain", message_data((double)y, unitval(1800.0, U_PPBV_CH4)));
+    EXPECT(throws([&] {
+      tc.setData("simpleNbox", "NBP_constrain", message_data(2000.0, unitval(1.0, U_PGC_YR)));
+    }));
+    EXPECT(throws([&] {
+      tc.setData("CH4", "CH4_constrain", message_data(2000.0, unitval(1800.0, U_PGC)));
+    }));
+    tc.prepareToRun();
+    tc.run(2020);
+    EXPECT((double)tc.sendMessage(M_GETDATA, "CH4_concentration", message_data(2005.0)) == 1800.0);
+    EXPECT((double)tc.sendMessage(M_GETDATA, "CH4_concentration", message_data(2011.0)) != 1800.0);
+    const std::string csv = tc.getTrackingData();
+    EXPECT(csv.compare(0, 5, "year,") == 0);
+    size_t rows = 0;
+    for (char ch : csv) rows += ch == '\n';
+    std::printf("TRACK_ROWS=%zu\n", rows);
+    EXPECT(csv.find("\n1990,simpleNbox,atmos_co2,") != std::string::npos);
+    EXPECT(csv.find("\n2020,ocean,deep,") != std::string::npos);
+    EXPECT(csv.find("\n1989,") == std::string::npos && csv.find("\n2021,") == std::string::npos);
+    std::printf("TRACK_CH4_2020=%.17g\n", (double)tc.sendMessage(M_GETDATA, "CH4_concentration", message_data(2020.0)));
+  }
+
   /* ---- the batch face: 4 members, per-member S ---- */
   EnsembleCore ens(4);
   INIToCoreReader(&ens).parse(ini);

@@ -90,6 +90,10 @@ def test_facade_matches_oracle(exe):
     for m, S in ((0, 2.0), (1, 3.0), (3, 6.0)):
         st, _, out, _, _ = port.run_member(raw, S=S)
         close("ENS_TAS_2300_%d" % m, out[tas][yr(2300)], 0.01)
+    # tracking + CH4 constraint block: 31 recorded years, at least 11 pools x 1 source each
+    assert int(kv["TRACK_ROWS"]) > 31 * 11
+    st, _, out = port.run_member_constrained(raw, {"CH4_constrain": {y: 1800.0 for y in range(2000, 2011)}})
+    close("TRACK_CH4_2020", out[port.OUT_NAMES.index("CH4_concentration")][yr(2020)])
     # beta = 50: the oracle and the engine must agree on whether the reference aborts
     st, _, _, _, _ = port.run_member(raw, beta=50.0)
     assert (st != 0) == (kv["BETA50_FAILED"] == "1")
