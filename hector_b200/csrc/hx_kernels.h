@@ -11,6 +11,9 @@
 #ifndef HX_CONV_UNROLL
 #define HX_CONV_UNROLL 8 /* history rows per trip of the slab prepass of the DOECLIM convolution */
 #endif
+#ifndef HX_YEAR_SYNC
+#define HX_YEAR_SYNC 1 /* one CTA barrier per simulated year: the warps share instruction fetches */
+#endif
 #ifndef HX_RUN_MIN_CTAS
 #define HX_RUN_MIN_CTAS 3 /* resident CTAs per SM the run kernel is compiled for (168 registers: a few spills, but 12 instead of 8 warps per SM hide more FP64 latency; measured 39.3 vs 40.8 ms) */
 #endif
