@@ -328,15 +328,15 @@ struct Engine {
       gas_series(s, n2o, hrf);
       const double *R = raw[s].data();
       const std::vector<double> rftot = densify(s, CN_RFTOT, true), tas = densify(s, CN_TAS, false);
-      const double *cco2 = con(s, CN_CO2), *cch4 = con(s, CN_CH4);
+      const double *cco2 = con(s, CN_CO2), *cch4 = con(s, CN_CH4), *cnbp = con(s, CN_NBP);
       for (int r = 0; r < nrow; ++r) {
         double *row = tab.data() + ((size_t)s * nrow + r) * SC_STRIDE;
         for (int c = 0; c <= SC_MISC; ++c) row[c] = R[(size_t)c * nrow + r]; /* RAW_x == SC_x up to MISC */
         row[SC_N2O] = n2o[r];
         for (int g = 0; g < HX_NHALO; ++g) row[SC_HALO0 + g] = hrf[(size_t)r * HX_NHALO + g];
         row[SC_C_CO2] = cco2[r]; row[SC_C_CH4] = cch4[r];
-        row[SC_C_RFTOT] = rftot[r]; row[SC_C_TAS] = tas[r];
-        for (int c = SC_C_CO2; c <= SC_C_TAS; ++c)
+        row[SC_C_RFTOT] = rftot[r]; row[SC_C_TAS] = tas[r]; row[SC_C_NBP] = cnbp[r];
+        for (int c = SC_C_CO2; c <= SC_C_NBP; ++c)
           if (row[c] == row[c]) any_constraint = true;
       }
     }
@@ -486,8 +486,6 @@ int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, i
   const int ci = Engine::find_constraint(name);
   if (ci >= 0) {
     /* a constraint series may cover any part of the run; NaN = no entry for that year */
-    if (ci == CN_NBP)
-      return h->fail(HX_ERR_UNSUPPORTED, "NBP_constrain is not supported by the ensemble engine");
     double *dst = h->cons[scenario_id].data() + (size_t)ci * h->nrow;
     for (int k = 0; k < n; ++k) { /* entries outside [year0, year0 + n) are kept */
       const int r = year0 + k - h->cfg.start_year;

@@ -309,11 +309,6 @@ bool read_ini(const std::string &path, IniInputs &out) {
     /* ---- user constraints: dated entries or a csv column ---- */
     const int cni = constraint_index(pname);
     if (cni >= 0) {
-      if (cni == CN_NBP) {
-        out.error = "[" + section + "] " + name + ": NBP constraints are not supported by the ensemble engine";
-        out.unsupported = true;
-        return false;
-      }
       Series tmp;
       if (value.compare(0, 4, "csv:") == 0) {
         std::string csv = value.substr(4);

@@ -653,7 +653,11 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           }
           mb.luc_e = scm1[SC_LUC_E]; mb.luc_u = scm1[SC_LUC_U];
           mb.S[SI_X_FFI * HX_TILE] = scm1[SC_FFI]; mb.S[SI_X_DACCS * HX_TILE] = scm1[SC_DACCS];
-          if (CONSTR) mb.S[SI_X_C_CO2 * HX_TILE] = sc[SC_C_CO2];
+          if (CONSTR) {
+            mb.S[SI_X_C_CO2 * HX_TILE] = sc[SC_C_CO2];
+            mb.S[SI_X_C_NBP0 * HX_TILE] = scm1[SC_C_NBP];
+            mb.S[SI_X_C_NBP1 * HX_TILE] = sc[SC_C_NBP];
+          }
           mb.neg |= (mb.luc_e < 0.0) | (mb.luc_u < 0.0) | (mb.S[SI_X_FFI * HX_TILE] < 0.0) | (mb.S[SI_X_DACCS * HX_TILE] < 0.0);
           /* Tland_rm: for (i = t-200; i < t; i++) Tland_rm += Tland_record.get(i) * wf; /= 200
            * (:1041-1050).  Keys below the first record (start+1) extrapolate flat to it and

@@ -44,10 +44,10 @@ enum {
   SC_N2O,   /* N2O concentration, host-precomputed (member independent) */
   SC_HALO0, /* 26 halocarbon forcings, host-precomputed */
   /* user constraints of the year (NaN = none): atmospheric CO2 [ppmv], CH4 [ppbv], total
-   * forcing [W/m2], global mean temperature [degC]; N2O and halocarbon constraints are already
+   * forcing [W/m2], global mean temperature [degC], net biome production [Pg C/yr]; N2O and halocarbon constraints are already
    * folded into SC_N2O / SC_HALO0.. on the host */
-  SC_C_CO2 = SC_HALO0 + HX_NHALO, SC_C_CH4, SC_C_RFTOT, SC_C_TAS,
-  SC_USED,                       /* 47 */
+  SC_C_CO2 = SC_HALO0 + HX_NHALO, SC_C_CH4, SC_C_RFTOT, SC_C_TAS, SC_C_NBP,
+  SC_USED,                       /* 48 */
   SC_STRIDE = 48                 /* 384 B per row: multiple of 16 B for cp.async.bulk */
 };
 
@@ -88,6 +88,7 @@ enum {
   SI_X_CO2FERT, SI_X_TFD, SI_X_TFS, SI_X_FNEWTHAW, SI_X_NPPLUC, SI_X_FFI, SI_X_DACCS, SI_X_NBP,
   SI_X_FLUXSUM,
   SI_X_C_CO2, /* this year's CO2 constraint (NaN = none), read by the year's last stash */
+  SI_X_C_NBP0, SI_X_C_NBP1, /* NBP constraints of year y-1 and y: round(t) picks one */
   SI_COUNT
 };
 

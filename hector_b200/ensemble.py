@@ -173,7 +173,7 @@ class Ensemble:
 
     def setvar_series(self, name, years, values, scenario=0):
         """R setvar(core, dates, var, values): a dated input of one scenario -- an emissions
-        series (must cover start..end) or a user constraint (CO2_constrain, tas_constrain,
+        series (must cover start..end) or a user constraint (CO2_constrain, NBP_constrain, tas_constrain,
         RF_tot_constrain, CH4_constrain, N2O_constrain, <gas>_constrain; any subset of years,
         tests/testthat/test_constraints.R).  After prepare() it takes effect at the next
         reset()/run(), like the reference's setvar + reset."""

@@ -103,14 +103,13 @@ int hx_set_stream(hx_handle h, void *cuda_stream);
  * NMVOC_emissions, BC_emissions, OC_emissions, SO2_emissions, NH3_emissions, SV, RF_albedo,
  * RF_misc, N2O_emissions, N2O_natural_emissions, <gas>_emissions for the 26 halocarbons.
  *
- * User constraints use the same call with the reference's names CO2_constrain, tas_constrain,
- * RF_tot_constrain, CH4_constrain, N2O_constrain and <gas>_constrain (simpleNbox-runtime.cpp:
- * 567-603, temperature_component.cpp:510-525, forcing_component.cpp:498-505, ch4_component.cpp:
+ * User constraints use the same call with the reference's names CO2_constrain, NBP_constrain,
+ * tas_constrain, RF_tot_constrain, CH4_constrain, N2O_constrain and <gas>_constrain
+ * (simpleNbox-runtime.cpp:343-383, 567-603, 871-898, temperature_component.cpp:510-525, forcing_component.cpp:498-505, ch4_component.cpp:
  * 141-158, n2o_component.cpp:141-158, halocarbon_component.cpp:189-192): any sub-range of years,
- * NaN = no entry for that year.  Entries act where the reference's tseries would: CO2 / CH4 /
- * N2O / halocarbons in the years that have an entry; RF_tot in every year up to its last entry
- * and tas between its first and last entry, gaps interpolated linearly.  NBP_constrain
- * (simpleNbox-runtime.cpp:343-383, 871-898) returns HX_ERR_UNSUPPORTED.
+ * NaN = no entry for that year.  Entries act where the reference's tseries would: CO2 / NBP /
+ * CH4 / N2O / halocarbons in the years that have an entry; RF_tot in every year up to its last
+ * entry and tas between its first and last entry, gaps interpolated linearly.
  *
  * Series may also be (re)set after hx_prepare; like the reference's setvar they take effect at
  * the next hx_reset / hx_run, which re-runs set-up and spin-up. */

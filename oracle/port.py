@@ -190,8 +190,9 @@ def run_member(raw, params=None, run_to=-1, **over):
     return st, fy.value, out, cd, sd
 
 
-def run_member_constrained(raw, spec, params=None, run_to=-1, **over):
-    """run_member with user constraints (see make_constraints) -> (status, fail_year, out)"""
+def run_member_constrained(raw, spec, params=None, run_to=-1, tracking_date=None, **over):
+    """run_member with user constraints (see make_constraints) -> (status, fail_year, out), or
+    (status, fail_year, out, frac, mask) when carbon tracking is requested as well"""
     p = params if params is not None else default_params()
     for k, v in over.items():
         setattr(p, k, v)
@@ -202,9 +203,16 @@ def run_member_constrained(raw, spec, params=None, run_to=-1, **over):
     ny = (p.end_year if run_to < 0 else run_to) - p.start_year
     out = np.empty((NOUT, ny))
     fy = C.c_int(0)
+    if tracking_date is None:
+        st = lib().ho_run_member_ex(C.byref(p), _dp(raw), C.byref(cn), run_to, _dp(out), ny,
+                                    C.byref(fy), None, None, 9999, None, None)
+        return st, fy.value, out
+    frac = np.empty((ny, len(TRACK_POOLS), len(TRACK_SOURCES)))
+    mask = np.zeros((ny, len(TRACK_POOLS)), dtype=np.uint32)
     st = lib().ho_run_member_ex(C.byref(p), _dp(raw), C.byref(cn), run_to, _dp(out), ny,
-                                C.byref(fy), None, None, 9999, None, None)
-    return st, fy.value, out
+                                C.byref(fy), None, None, int(tracking_date), _dp(frac),
+                                mask.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return st, fy.value, out, frac, mask
 
 
 def run_member_tracked(raw, tracking_date, params=None, run_to=-1, **over):

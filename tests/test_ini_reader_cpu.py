@@ -58,11 +58,11 @@ def test_unsupported_inputs_are_reported(tmp_path):
     L = need_lib()
     src = open(os.path.join(input_dir(), "hector_ssp245.ini")).read()
     d = input_dir()
-    bad = tmp_path / "constrained.ini"
+    bad = tmp_path / "biome.ini"
     bad.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
-        "[simpleNbox]", "[simpleNbox]\nNBP_constrain[2000]=1.0"))
+        "[simpleNbox]", "[simpleNbox]\nboreal.veg_c=100"))
     assert L.hx_ini_read(str(bad).encode(), None, None, None, 0) == -4
-    assert b"NBP" in L.hx_last_error(None)
+    assert b"biome" in L.hx_last_error(None)
     bad3 = tmp_path / "lo.ini"
     bad3.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
         "[temperature]", "[temperature]\nlo_warming_ratio=1.6"))
