@@ -149,8 +149,8 @@ struct Engine {
   double *h_pinned = nullptr;
   size_t pinned_bytes = 0;
 
-  cudaStream_t stream = nullptr, own_stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_seg = nullptr, ev_copy = nullptr;
 
   int fail(int code, const std::string &msg) {
     err = msg;
@@ -468,6 +468,9 @@ int hx_destroy(hx_handle h) {
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_seg) cudaEventDestroy(h->ev_seg);
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return HX_OK;
@@ -846,6 +849,84 @@ int hx_run(hx_handle h, double run_to_date) {
   }
   cudaEventRecord(h->ev1, st);
   h->cur_row = r1;
+  return HX_OK;
+}
+
+/* Run and stream the results out while running: the run is cut into `segments` launches (whole
+ * 16-year slabs) and the recorded years of each finished segment go to the host over the copy
+ * engine while the next segment computes, so that of the device-to-host time only the last
+ * segment's share is exposed.  Year-major output (the device layout) needs no transpose kernel,
+ * which could not run next to the persistent run kernel anyway. */
+int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *const *names,
+                  double *const *outs, int32_t segments) {
+  if (!h || n_vars <= 0 || !names || !outs) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_run_stream before hx_prepare");
+  cudaSetDevice(h->cfg.device);
+  if (h->params_dirty) {
+    int rc = h->run_setup_and_spinup();
+    if (rc) return rc;
+  }
+  const int to = run_to_date < 0 ? h->cfg.end_year : (int)run_to_date;
+  if (to > h->cfg.end_year) return h->fail(HX_ERR_ARG, "run_to_date beyond end_year");
+  const int r0 = h->cur_row, r1 = to - h->cfg.start_year;
+  if (r1 <= r0) return HX_OK;
+  std::vector<int> slot(n_vars);
+  for (int v = 0; v < n_vars; ++v) {
+    const int id = Engine::find_out(names[v]);
+    if (id < 0 || h->d.out_slot[id] < 0)
+      return h->fail(HX_ERR_ARG, std::string("output not recorded: ") + (names[v] ? names[v] : "?"));
+    if (!outs[v]) return HX_ERR_ARG;
+    slot[v] = h->d.out_slot[id];
+  }
+  if (!h->identity_perm)
+    return h->fail(HX_ERR_UNSUPPORTED,
+                   "hx_run_stream needs members in API order on the device (one scenario, or "
+                   "members grouped by scenario); use hx_run + hx_fetch");
+  if (!h->copy_stream) {
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_seg, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) != cudaSuccess)
+      return h->fail(HX_ERR_CUDA, "hx_run_stream: could not create the copy stream");
+  }
+  if (segments < 1) segments = 1;
+  const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
+  if (segments > nslab) segments = nslab;
+  cudaStream_t st = h->stream;
+  const int ny = r1 - r0; /* columns... rows of the caller's [year][member] blocks */
+  cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st);
+  cudaEventRecord(h->ev0, st);
+  int ra = r0;
+  for (int sg = 0; sg < segments; ++sg) {
+    const int rb = (sg == segments - 1)
+                       ? r1
+                       : r0 + (int)(((long long)nslab * (sg + 1)) / segments) * HX_SLAB_YEARS;
+    if (rb <= ra) continue;
+    cudaError_t e = hx::launch_run(h->d, h->C, ra, rb, st);
+    if (e == cudaSuccess && !h->out_sel.empty())
+      e = hx::launch_nan_fill(h->d, h->C, (int)h->out_sel.size(), ra, rb, st);
+    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("run segment: ") + cudaGetErrorString(e));
+    cudaEventRecord(h->ev_seg, st);
+    cudaStreamWaitEvent(h->copy_stream, h->ev_seg, 0);
+    for (int v = 0; v < n_vars; ++v) {
+      /* years ra+1 .. rb are output rows ra .. rb-1 of the variable's [year][Mpad] block */
+      const double *src = h->d_out + ((size_t)slot[v] * (h->nrow - 1) + ra) * h->Mpad;
+      double *dst = outs[v] + (size_t)(ra - r0) * h->M;
+      e = cudaMemcpy2DAsync(dst, (size_t)h->M * sizeof(double), src, (size_t)h->Mpad * sizeof(double),
+                            (size_t)h->M * sizeof(double), (size_t)(rb - ra), cudaMemcpyDeviceToHost,
+                            h->copy_stream);
+      if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_run_stream copy: ") + cudaGetErrorString(e));
+    }
+    ra = rb;
+  }
+  (void)ny;
+  cudaEventRecord(h->ev1, st);
+  /* the caller's stream must see the copies as done */
+  cudaEventRecord(h->ev_copy, h->copy_stream);
+  cudaStreamWaitEvent(st, h->ev_copy, 0);
+  h->cur_row = r1;
+  cudaError_t e = cudaStreamSynchronize(h->copy_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_run_stream: ") + cudaGetErrorString(e));
   return HX_OK;
 }
 

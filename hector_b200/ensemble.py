@@ -203,6 +203,31 @@ class Ensemble:
             self.prepare()
         self._chk(self.L.hx_run(self.h, float(to_date)))
 
+    def run_stream(self, variables=None, to_date=-1, outs=None, segments=4):
+        """run(to_date) and fetch every year of the segment for `variables` in one call, the
+        device-to-host copies overlapped with the computation.  Returns {variable: array
+        [n_years, n_members]} (year-major, R fetchvars' long format); `outs` may supply
+        preallocated (pinned) arrays of that shape."""
+        if not self.prepared:
+            self.prepare()
+        variables = list(variables or self.outputs)
+        first = int(self.current_date) + 1
+        last = int(to_date) if to_date >= 0 else int(self._end_year())
+        ny = last - first + 1
+        if outs is None:
+            outs = [np.empty((ny, self.n_members)) for _ in variables]
+        names = (C.c_char_p * len(variables))(*[v.encode() for v in variables])
+        ptrs = (C.c_void_p * len(variables))(*[
+            (o.ctypes.data if hasattr(o, "ctypes") else int(o)) for o in outs])
+        self._chk(self.L.hx_run_stream(self.h, float(to_date), len(variables), names, ptrs,
+                                       int(segments)))
+        return dict(zip(variables, outs))
+
+    def _end_year(self):
+        if self.end_year is not None:
+            return self.end_year
+        raise HxError("run_stream on an ini-built engine needs an explicit to_date")
+
     def reset(self):
         self._chk(self.L.hx_reset(self.h))
 

@@ -147,6 +147,16 @@ int hx_prepare(hx_handle h);
 int hx_run(hx_handle h, double run_to_date); /* < 0: run to end_year; resumes where it left off */
 int hx_reset(hx_handle h);                   /* back to the post-spin-up state at start_year */
 int hx_synchronize(hx_handle h);
+/* hx_run + fetch of every year of the segment in one call, with the device-to-host copies
+ * overlapped with the computation (the run is cut into `segments` launches; each finished
+ * segment streams out over the copy engine while the next one computes).  outs[v] receives
+ * names[v] YEAR-major: outs[v][(year - first_year) * n_members + member], first_year = the date
+ * before the call + 1 -- the long format R's fetchvars returns (R/messages.R:46-88), and the
+ * device layout, so no transpose stands between the kernel and the copy.  Use pinned host
+ * memory for the copies to be asynchronous.  Needs members in API order on the device (a single
+ * scenario, or members listed scenario by scenario); returns when everything has arrived. */
+int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *const *names,
+                  double *const *outs, int32_t segments);
 
 /* out[member][date] (row-major, n_members x n_dates) on the host; dates before/at
  * start_year or beyond the current date are an error, as in the reference */

@@ -262,3 +262,35 @@ def test_extension_to_2500():
         assert util.parity_err(got["CO2_concentration"][i], out[0], "CO2_concentration") < TOL
         assert util.parity_err(got["global_tas"][i], out[1], "global_tas") < TOL
     ens.close()
+
+
+def test_run_stream_equals_run_plus_fetch():
+    """hx_run_stream (run cut into segments, copies overlapped) returns what run + fetch return,
+    year-major; also when resumed mid-run and with a failing member in the batch"""
+    import hector_b200 as hb
+    M = 300
+    X = util.lhs(M, seed=5)
+    X[7] = [8.0, 4.0, 0.05, 0.2]          # the reference aborts this member on SSP5-8.5
+    tab = util.scenarios()["ssp585"]
+    outs = ["CO2_concentration", "global_tas", "HL_pH"]
+
+    def make():
+        e = hb.Ensemble(M, tab, outputs=outs)
+        for j, n in enumerate(["S", "q10_rh", "beta", "diff"]):
+            e.setvar(n, X[:, j])
+        return e
+    a, b = make(), make()
+    a.run()
+    ref = a.fetchvars(_years())
+    got1 = b.run_stream(outs, to_date=1900, segments=3)
+    got2 = b.run_stream(outs[:2], segments=5)
+    for v in outs:
+        assert np.array_equal(got1[v], ref[v][:, :1900 - 1745].T, equal_nan=True), v
+    for v in outs[:2]:
+        assert np.array_equal(got2[v], ref[v][:, 1900 - 1745:].T, equal_nan=True), v
+    sa, _ = a.status()
+    sb, _ = b.status()
+    assert np.array_equal(sa, sb) and sa[7] != 0 and (np.delete(sa, 7) == 0).all()
+    assert a.counters()["member_years"] > 0
+    a.close()
+    b.close()
