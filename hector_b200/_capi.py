@@ -14,7 +14,7 @@ HX_FLAG_NO_SPINUP = 2
 EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "hx_destroy", "hx_last_error", "hx_set_stream", "hx_set_scenario_series",
            "hx_set_scenario_table", "hx_set_member_scenario", "hx_set_param_scalar",
            "hx_set_param", "hx_set_param_device", "hx_get_param", "hx_select_outputs",
-           "hx_prepare", "hx_run", "hx_run_stream", "hx_reset", "hx_synchronize", "hx_fetch", "hx_output_device",
+           "hx_prepare", "hx_run", "hx_run_stream", "hx_reset", "hx_reset_date", "hx_synchronize", "hx_fetch", "hx_output_device",
            "hx_member_status", "hx_set_tracking", "hx_fetch_tracking", "hx_tracking_years", "hx_counters", "hx_current_date", "hx_last_run_ms",
            "hx_spinup_state", "hx_version"]
 
@@ -70,6 +70,7 @@ def lib():
     L.hx_run_stream.argtypes = [vp, C.c_double, C.c_int32, C.POINTER(C.c_char_p),
                                 C.POINTER(C.c_void_p), C.c_int32]
     L.hx_reset.argtypes = [vp]
+    L.hx_reset_date.argtypes = [vp, C.c_double]
     L.hx_synchronize.argtypes = [vp]
     L.hx_fetch.argtypes = [vp, C.c_char_p, dp, C.c_int32, vp]
     L.hx_output_device.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_int64), ip]

@@ -826,6 +826,23 @@ int hx_reset(hx_handle h) {
   return HX_OK;
 }
 
+int hx_reset_date(hx_handle h, double date) {
+  if (!h) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_reset_date before hx_prepare");
+  const int y = (int)date;
+  if (y <= h->cfg.start_year) return hx_reset(h);
+  if (y > h->cfg.start_year + h->cur_row)
+    return h->fail(HX_ERR_ARG, "reset date is after the current date"); /* core.cpp:520-523 */
+  if (h->params_dirty)
+    return h->fail(HX_ERR_UNSUPPORTED,
+                   "reset to a date inside the run after parameters or inputs changed: the "
+                   "engine keeps no per-year state history; reset to the start date instead");
+  /* the run is deterministic (bit-reproducible), so the state at `date` is re-derived */
+  int rc = hx_reset(h);
+  if (rc) return rc;
+  return hx_run(h, (double)y);
+}
+
 int hx_run(hx_handle h, double run_to_date) {
   if (!h) return HX_ERR_ARG;
   if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_run before hx_prepare");

@@ -52,6 +52,31 @@ TRACK_POOL_OUTPUT = ["atmos_co2", "earth_c", "veg_c", "detritus_c", "soil_c", "p
                      "thawedp_c", "HL_ocean_c", "LL_ocean_c", "IO_ocean_c", "DO_ocean_c"]
 
 
+# units and owning component of every recorded variable, as the reference reports them
+# (unitval::unitsName, inst/include/unitval.hpp:68-130; getComponentName of the component that
+# registers the capability)
+VARIABLE_UNITS = {
+    "CO2_concentration": "ppmv CO2", "global_tas": "degC", "RF_tot": "W/m2", "RF_CO2": "W/m2",
+    "heatflux": "W/m2", "ocean_c": "Pg C", "HL_pH": "pH", "atmos_co2": "Pg C", "sst": "degC",
+    "permafrost_c": "Pg C", "CH4_concentration": "ppbv CH4", "N2O_concentration": "ppbv N2O",
+    "O3_concentration": "DU O3", "land_tas": "degC", "veg_c": "Pg C", "detritus_c": "Pg C",
+    "soil_c": "Pg C", "thawedp_c": "Pg C", "earth_c": "Pg C", "NBP": "Pg C/yr",
+    "ocean_uptake": "Pg C/yr", "LL_pH": "pH", "HL_PCO2": "uatm", "LL_PCO2": "uatm",
+    "HL_ocean_c": "Pg C", "LL_ocean_c": "Pg C", "IO_ocean_c": "Pg C", "DO_ocean_c": "Pg C",
+    "RF_CH4": "W/m2", "RF_N2O": "W/m2", "rh_ch4": "Pg C/yr", "ocean_timesteps": "(unitless)"}
+VARIABLE_COMPONENT = {
+    "CO2_concentration": "simpleNbox", "atmos_co2": "simpleNbox", "veg_c": "simpleNbox",
+    "detritus_c": "simpleNbox", "soil_c": "simpleNbox", "permafrost_c": "simpleNbox",
+    "thawedp_c": "simpleNbox", "earth_c": "simpleNbox", "NBP": "simpleNbox",
+    "rh_ch4": "simpleNbox", "global_tas": "temperature", "land_tas": "temperature",
+    "sst": "temperature", "heatflux": "temperature", "RF_tot": "forcing", "RF_CO2": "forcing",
+    "RF_CH4": "forcing", "RF_N2O": "forcing", "ocean_c": "ocean", "ocean_uptake": "ocean",
+    "HL_pH": "ocean", "LL_pH": "ocean", "HL_PCO2": "ocean", "LL_PCO2": "ocean",
+    "HL_ocean_c": "ocean", "LL_ocean_c": "ocean", "IO_ocean_c": "ocean", "DO_ocean_c": "ocean",
+    "ocean_timesteps": "ocean", "CH4_concentration": "CH4", "N2O_concentration": "N2O",
+    "O3_concentration": "ozone"}
+
+
 def load_scenario_tables(path):
     """{scenario: table[nrow, len(RAW_SERIES)]} from an .npz written by
     tests/golden/make_golden.py (columns in RAW_SERIES order)."""
@@ -228,8 +253,13 @@ class Ensemble:
             return self.end_year
         raise HxError("run_stream on an ini-built engine needs an explicit to_date")
 
-    def reset(self):
-        self._chk(self.L.hx_reset(self.h))
+    def reset(self, date=None):
+        """R reset(core, date = 0): back to the start (re-running the spin-up if parameters or
+        inputs changed), or to a year inside the run already made."""
+        if date is None:
+            self._chk(self.L.hx_reset(self.h))
+        else:
+            self._chk(self.L.hx_reset_date(self.h, float(date)))
 
     def synchronize(self):
         self._chk(self.L.hx_synchronize(self.h))
@@ -249,6 +279,43 @@ class Ensemble:
         """R fetchvars (R/messages.R:46-88): {variable: array[n_members, n_dates]}"""
         variables = variables or self.outputs
         return {v: self.fetch(v, dates) for v in variables}
+
+    def fetchvars_frame(self, dates, variables=None, members=None, scenario="ensemble"):
+        """R fetchvars (R/messages.R:46-88, src/rcpp_hector.cpp:349-355) as a long data frame:
+        columns scenario, member, year, variable, value, units (one row per member x year x
+        variable; `member` is the column the single-core reference does not have)."""
+        import pandas as pd
+        variables = list(variables or self.outputs)
+        dates = np.asarray(dates, dtype=np.float64)
+        members = np.arange(self.n_members) if members is None else np.asarray(members)
+        frames = []
+        for v in variables:
+            x = self.fetch(v, dates)[members]
+            frames.append(pd.DataFrame({
+                "scenario": scenario, "member": np.repeat(members, dates.size),
+                "year": np.tile(dates.astype(int), members.size), "variable": v,
+                "value": x.reshape(-1), "units": VARIABLE_UNITS.get(v, "(unitless)")}))
+        return pd.concat(frames, ignore_index=True)
+
+    def write_outputstream(self, path, member=0, run_name="hector_b200", dates=None,
+                           variables=None):
+        """One member as the reference's outputstream_<run>.csv (CSVOutputStreamVisitor,
+        src/csv_outputstream_visitor.cpp:55-71, 100-140): a comment line, then
+        year,run_name,spinup,component,variable,value,units rows, values with the C++ stream's
+        default six significant digits."""
+        variables = list(variables or self.outputs)
+        if dates is None:
+            dates = np.arange(self.start_year + 1, int(self.current_date) + 1)
+        dates = np.asarray(dates, dtype=np.float64)
+        cols = {v: self.fetch(v, dates)[member] for v in variables}
+        with open(path, "w") as f:
+            f.write("# Output from hector_b200 (Hector v3.5.0 hot path) member %d\n" % member)
+            f.write("year,run_name,spinup,component,variable,value,units\n")
+            for k, y in enumerate(dates.astype(int)):
+                for v in variables:
+                    f.write("%d,%s,0,%s,%s,%.6g,%s\n" % (
+                        y, run_name, VARIABLE_COMPONENT.get(v, "?"), v, cols[v][k],
+                        VARIABLE_UNITS.get(v, "(unitless)")))
 
     def output_device(self, var):
         """(device pointer, member stride, n_years) of the [year][member] block of `var`."""

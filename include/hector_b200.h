@@ -146,6 +146,12 @@ int hx_select_outputs(hx_handle h, int32_t n, const char *const *names);
 int hx_prepare(hx_handle h);
 int hx_run(hx_handle h, double run_to_date); /* < 0: run to end_year; resumes where it left off */
 int hx_reset(hx_handle h);                   /* back to the post-spin-up state at start_year */
+/* Core::reset(resetdate) (core.cpp:511-549): date <= start_year is hx_reset; a date inside the
+ * run restores the state of that year so that hx_run continues from it.  The engine keeps no
+ * per-year state history (the reference keeps one tvector per state variable); it re-derives the
+ * state by re-running to `date`, which is exact because runs are bit-reproducible -- and is
+ * therefore refused (HX_ERR_UNSUPPORTED) if parameters or inputs changed since the last run. */
+int hx_reset_date(hx_handle h, double date);
 int hx_synchronize(hx_handle h);
 /* hx_run + fetch of every year of the segment in one call, with the device-to-host copies
  * overlapped with the computation (the run is cut into `segments` launches; each finished

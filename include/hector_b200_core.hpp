@@ -283,13 +283,12 @@ class EnsembleCore {
         }
     }
   }
-  /* Core::reset (core.cpp:511-549): the engine supports the R wrapper's use, a reset to (or
-   * before) the start date; parameters changed since the last spin-up trigger a new one */
+  /* Core::reset (core.cpp:511-549): to (or before) the start date -- parameters changed since
+   * the last spin-up trigger a new one --, or to a year inside the run already made */
   void reset(double resetdate) {
     need();
     if (!prepared_) return;
-    if (resetdate > getStartDate()) HXB_THROW("reset to a date inside the run is not supported");
-    chk(hx_reset(h_));
+    chk(hx_reset_date(h_, resetdate));
   }
   void shutDown() {
     if (h_) hx_destroy(h_);

@@ -294,3 +294,59 @@ def test_run_stream_equals_run_plus_fetch():
     assert a.counters()["member_years"] > 0
     a.close()
     b.close()
+
+
+def test_output_adapters_have_the_reference_shapes(tmp_path):
+    """fetchvars' long data frame (src/rcpp_hector.cpp:349-355) and the outputstream csv
+    (src/csv_outputstream_visitor.cpp:69-71)"""
+    import csv
+    import hector_b200 as hb
+    ens = _engine(3, outputs=["CO2_concentration", "global_tas", "HL_pH"])
+    ens.setvar("S", np.array([2.0, 3.0, 4.0]))
+    ens.run(1800)
+    df = ens.fetchvars_frame(range(1790, 1801), ["CO2_concentration", "global_tas"])
+    assert list(df.columns) == ["scenario", "member", "year", "variable", "value", "units"]
+    assert len(df) == 3 * 11 * 2
+    row = df[(df.member == 1) & (df.year == 1800) & (df.variable == "global_tas")].iloc[0]
+    assert row.units == "degC" and row.value == ens.fetch("global_tas", [1800.0])[1, 0]
+    assert set(df[df.variable == "CO2_concentration"].units) == {"ppmv CO2"}
+    path = tmp_path / "outputstream_test.csv"
+    ens.write_outputstream(str(path), member=2, run_name="ssp245")
+    lines = open(path).read().splitlines()
+    assert lines[0].startswith("#")
+    assert lines[1] == "year,run_name,spinup,component,variable,value,units"
+    rows = list(csv.reader(lines[2:]))
+    assert len(rows) == 55 * 3
+    assert rows[0][:5] == ["1746", "ssp245", "0", "simpleNbox", "CO2_concentration"]
+    last = [r for r in rows if r[0] == "1800" and r[4] == "HL_pH"][0]
+    assert last[3] == "ocean" and last[6] == "pH"
+    assert abs(float(last[5]) - ens.fetch("HL_pH", [1800.0])[2, 0]) < 1e-5
+    ens.close()
+
+
+def test_reset_to_a_date_inside_the_run():
+    """Core::reset(date) (core.cpp:511-549, tests/testthat/test_hector.R "reset"): run, reset to
+    an earlier year, run again: same results; after a parameter change only a reset to the
+    start is possible"""
+    import hector_b200 as hb
+    ens = _engine(5, outputs=["CO2_concentration", "global_tas"])
+    ens.setvar("S", np.linspace(2, 4, 5))
+    ens.run(2100)
+    first = ens.fetchvars(_years(1746, 2100))
+    ens.reset(2000)
+    assert ens.current_date == 2000
+    with pytest.raises(hb.HxError):
+        ens.fetch("global_tas", [2050.0])      # beyond the current date again
+    ens.run(2100)
+    again = ens.fetchvars(_years(1746, 2100))
+    for v in first:
+        assert np.array_equal(first[v], again[v]), v
+    with pytest.raises(hb.HxError):
+        ens.reset(2200)                        # after the current date
+    ens.setvar("beta", 0.5)
+    with pytest.raises(hb.HxError):
+        ens.reset(2000)                        # state history of the old parameters is gone
+    ens.reset()
+    ens.run(1800)
+    assert ens.current_date == 1800
+    ens.close()
