@@ -211,6 +211,10 @@ def main():
     ap.add_argument("--tracked-members", type=int, default=65536,
                     help="also time a carbon-tracking ensemble to 2500 (0 = skip)")
     ap.add_argument("--e2e-segments", type=int, default=4)
+    ap.add_argument("--gather-segments", type=int, default=1,
+                    help="N > 1: run segments per step, each followed by its share of the "
+                         "all-gather (measured at N = 2 and 8: no gain over one gather at the "
+                         "end, NCCL's CTAs do not fit next to the persistent run kernel)")
     ap.add_argument("--ref-members-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -262,17 +266,31 @@ def main():
         for v in ("CO2_concentration", "global_tas"):
             ptr, stride, ny = ens.output_device(v)
             views.append(torch.as_tensor(CudaArrayView(ptr, (ny, stride)), device="cuda"))
-        gather_buf = [torch.empty(world * t.numel(), dtype=torch.float64, device="cuda")
-                      for t in views]
+        # The job's one exchange: every rank ends up with all members' CO2 / Tgav trajectories --
+        # by default a single all-gather per variable after the last year.  --gather-segments k
+        # issues it per finished run segment (whole 16-year slabs) instead, asynchronously.
+        nseg = max(1, args.gather_segments)
+        nslab = (YEARS + 15) // 16
+        cuts = sorted({min(YEARS, ((nslab * (k + 1)) // nseg) * 16) for k in range(nseg)} | {YEARS})
+        cuts = [c for c in cuts if c > 0]
+        seg_rows = list(zip([0] + cuts[:-1], cuts))
+        gather_buf = [[torch.empty(world * (b - a) * t.shape[1], dtype=torch.float64, device="cuda")
+                       for (a, b) in seg_rows] for t in views]
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")  # 256 MB > L2
 
     def step_device(e, do_gather=True):
         e.reset()
-        e.run()
         if world > 1 and do_gather:
-            # the job's single collective: every rank ends up with all members' trajectories
-            for t, g in zip(views, gather_buf):
-                dist.all_gather_into_tensor(g, t.reshape(-1))
+            works = []
+            for k, (a, b) in enumerate(seg_rows):
+                e.run(1745 + b)
+                for t, g in zip(views, gather_buf):
+                    works.append(dist.all_gather_into_tensor(g[k], t[a:b].reshape(-1),
+                                                             async_op=True))
+            for wk in works:
+                wk.wait()
+        else:
+            e.run()
 
     def timed(e, fn, steps, warmup, flush_l2):
         for _ in range(warmup):
@@ -307,6 +325,9 @@ def main():
         sampler.start()
     total_ms, kernel_ms = timed(ens, step_device, args.steps, args.warmup, M < 16384)
     clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        # the step above runs in segments; the roofline wants the whole run kernel's duration
+        _, kernel_ms = timed(ens, lambda e: (e.reset(), e.run()), 2, 1, False)
     ms_per_step = total_ms / args.steps
     value = world * M * YEARS / (ms_per_step * 1e-3)
     cnt = ens.counters()
