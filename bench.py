@@ -35,6 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 YEARS = 555
+E2E_VARS = ["CO2_concentration", "global_tas"]
 B_ALG = 5048.0  # algorithmic bytes per member-year, SURVEY.md section 8(d)
 METRIC = "ensemble_member_years_per_sec"
 UNIT = "member-years/s"
@@ -211,6 +212,9 @@ def main():
     ap.add_argument("--tracked-members", type=int, default=65536,
                     help="also time a carbon-tracking ensemble to 2500 (0 = skip)")
     ap.add_argument("--e2e-segments", type=int, default=4)
+    ap.add_argument("--exchange", default="ipc", choices=["ipc", "nccl"],
+                    help="N > 1: how the trajectories are exchanged (peer-memory pulls or NCCL)")
+    ap.add_argument("--exchange-segments", type=int, default=4)
     ap.add_argument("--gather-segments", type=int, default=1,
                     help="N > 1: run segments per step, each followed by its share of the "
                          "all-gather (measured at N = 2 and 8: no gain over one gather at the "
@@ -278,7 +282,26 @@ def main():
                        for (a, b) in seg_rows] for t in views]
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")  # 256 MB > L2
 
+    # Exchange over peer memory (default at N > 1): every rank opens its peers' output blocks
+    # through CUDA IPC and pulls each finished run segment with copy-engine transfers over
+    # NVLink while its own kernel computes the next segment -- no collective kernel has to find
+    # room next to the persistent run kernel.  Host-side ordering: a gloo barrier per segment.
+    peer_all = None
+    gloo = None
+    exchange = None
+    if world > 1 and args.exchange == "ipc":
+        from hector_b200.sharding import PeerExchange
+        gloo = dist.new_group(backend="gloo")
+        exchange = PeerExchange(ens, E2E_VARS, gloo, segments=args.exchange_segments)
+        peer_all = [exchange.blocks[v] for v in E2E_VARS]
+
+    def step_ipc(e):
+        e.reset()
+        exchange.run()
+
     def step_device(e, do_gather=True):
+        if world > 1 and do_gather and peer_all is not None:
+            return step_ipc(e)
         e.reset()
         if world > 1 and do_gather:
             works = []
@@ -319,6 +342,17 @@ def main():
         if dist:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), float(np.mean(kernel_ms))
+
+    if peer_all is not None:
+        # one-off check of the exchange against NCCL's all-gather of the same blocks
+        step_ipc(ens)
+        for t, g in zip(views, peer_all):
+            ref = torch.empty_like(g)
+            dist.all_gather_into_tensor(ref.reshape(-1), t.reshape(-1))
+            torch.cuda.synchronize()
+            if not torch.equal(torch.nan_to_num(ref), torch.nan_to_num(g)):
+                raise SystemExit("bench.py: peer-memory exchange differs from the NCCL all-gather")
+        dist.barrier(group=gloo)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -15,7 +15,8 @@ EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "h
            "hx_set_scenario_table", "hx_set_member_scenario", "hx_set_param_scalar",
            "hx_set_param", "hx_set_param_device", "hx_get_param", "hx_select_outputs",
            "hx_prepare", "hx_run", "hx_run_stream", "hx_reset", "hx_reset_date", "hx_synchronize", "hx_fetch", "hx_output_device",
-           "hx_member_status", "hx_set_tracking", "hx_fetch_tracking", "hx_tracking_years", "hx_counters", "hx_current_date", "hx_last_run_ms",
+           "hx_ipc_export", "hx_ipc_open", "hx_ipc_pull", "hx_ipc_wait", "hx_ipc_close",
+           "hx_event_record", "hx_event_synchronize", "hx_member_status", "hx_set_tracking", "hx_fetch_tracking", "hx_tracking_years", "hx_counters", "hx_current_date", "hx_last_run_ms",
            "hx_spinup_state", "hx_version"]
 
 
@@ -74,6 +75,13 @@ def lib():
     L.hx_synchronize.argtypes = [vp]
     L.hx_fetch.argtypes = [vp, C.c_char_p, dp, C.c_int32, vp]
     L.hx_output_device.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_int64), ip]
+    L.hx_ipc_export.argtypes = [vp, vp, C.POINTER(C.c_int64)]
+    L.hx_ipc_open.argtypes = [vp, C.c_int32, vp, C.c_int32]
+    L.hx_ipc_pull.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32, vp]
+    L.hx_ipc_wait.argtypes = [vp]
+    L.hx_ipc_close.argtypes = [vp]
+    L.hx_event_record.argtypes = [vp, C.c_int32]
+    L.hx_event_synchronize.argtypes = [vp, C.c_int32]
     L.hx_set_tracking.argtypes = [vp, C.c_int32, C.c_int32]
     L.hx_fetch_tracking.argtypes = [vp, C.c_double, dp, C.POINTER(C.c_uint32)]
     L.hx_tracking_years.argtypes = [vp, ip, C.c_int32]

@@ -151,6 +151,10 @@ struct Engine {
 
   cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_seg = nullptr, ev_copy = nullptr;
+  /* multi-GPU exchange over peer memory: peers' output blocks opened through CUDA IPC */
+  std::vector<double *> peer_out;
+  int peer_self = -1;
+  cudaEvent_t ev_user[16] = {};
 
   int fail(int code, const std::string &msg) {
     err = msg;
@@ -396,6 +400,15 @@ struct hx_engine : Engine {};
 
 using hx::kParams;
 
+static int ensure_copy_stream(hx_engine *h) {
+  if (h->copy_stream) return HX_OK;
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_seg, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) != cudaSuccess)
+    return h->fail(HX_ERR_CUDA, "could not create the copy stream");
+  return HX_OK;
+}
+
 extern "C" {
 
 const char *hx_version(void) { return "hector_b200 0.1 (sm_100a)"; }
@@ -468,6 +481,9 @@ int hx_destroy(hx_handle h) {
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  hx_ipc_close(h);
+  for (cudaEvent_t e : h->ev_user)
+    if (e) cudaEventDestroy(e);
   if (h->ev_seg) cudaEventDestroy(h->ev_seg);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -899,11 +915,9 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
     return h->fail(HX_ERR_UNSUPPORTED,
                    "hx_run_stream needs members in API order on the device (one scenario, or "
                    "members grouped by scenario); use hx_run + hx_fetch");
-  if (!h->copy_stream) {
-    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_seg, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) != cudaSuccess)
-      return h->fail(HX_ERR_CUDA, "hx_run_stream: could not create the copy stream");
+  {
+    int rc = ensure_copy_stream(h);
+    if (rc) return rc;
   }
   if (segments < 1) segments = 1;
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
@@ -944,6 +958,99 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
   cudaError_t e = cudaStreamSynchronize(h->copy_stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_run_stream: ") + cudaGetErrorString(e));
+  return HX_OK;
+}
+
+/* ---- exchange of the recorded outputs between the GPUs of one node over peer memory ---- */
+int hx_ipc_export(hx_handle h, void *handle64, int64_t *bytes) {
+  if (!h || !handle64) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_ipc_export before hx_prepare");
+  cudaSetDevice(h->cfg.device);
+  cudaIpcMemHandle_t mh;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  cudaError_t e = cudaIpcGetMemHandle(&mh, h->d_out);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  memcpy(handle64, &mh, 64);
+  if (bytes) *bytes = (int64_t)h->out_sel.size() * (h->nrow - 1) * h->Mpad * (int64_t)sizeof(double);
+  return HX_OK;
+}
+
+int hx_ipc_open(hx_handle h, int32_t n_peers, const void *handles, int32_t self_index) {
+  if (!h || n_peers < 1 || !handles || self_index < 0 || self_index >= n_peers) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_ipc_open before hx_prepare");
+  cudaSetDevice(h->cfg.device);
+  hx_ipc_close(h);
+  h->peer_out.assign(n_peers, nullptr);
+  h->peer_self = self_index;
+  for (int p = 0; p < n_peers; ++p) {
+    if (p == self_index) { h->peer_out[p] = h->d_out; continue; }
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, (const char *)handles + (size_t)p * 64, 64);
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      hx_ipc_close(h);
+      return h->fail(HX_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    }
+    h->peer_out[p] = (double *)ptr;
+  }
+  return ensure_copy_stream(h);
+}
+
+int hx_ipc_close(hx_handle h) {
+  if (!h) return HX_OK;
+  for (size_t p = 0; p < h->peer_out.size(); ++p)
+    if ((int)p != h->peer_self && h->peer_out[p]) cudaIpcCloseMemHandle(h->peer_out[p]);
+  h->peer_out.clear();
+  h->peer_self = -1;
+  return HX_OK;
+}
+
+int hx_ipc_pull(hx_handle h, const char *name, int32_t year_a, int32_t year_b, double *dst_dev) {
+  if (!h || !name || !dst_dev) return HX_ERR_ARG;
+  if (h->peer_out.empty()) return h->fail(HX_ERR_STATE, "hx_ipc_pull before hx_ipc_open");
+  const int id = Engine::find_out(name);
+  if (id < 0 || h->d.out_slot[id] < 0) return h->fail(HX_ERR_ARG, std::string("output not recorded: ") + name);
+  const int ra = year_a - h->cfg.start_year - 1, rb = year_b - h->cfg.start_year; /* rows [ra, rb) */
+  if (ra < 0 || rb > h->nrow - 1 || rb <= ra) return h->fail(HX_ERR_ARG, "hx_ipc_pull: bad year range");
+  cudaSetDevice(h->cfg.device);
+  const size_t block = (size_t)(h->nrow - 1) * h->Mpad;
+  const size_t off = ((size_t)h->d.out_slot[id] * (h->nrow - 1) + ra) * h->Mpad;
+  const int n = (int)h->peer_out.size();
+  for (int k = 0; k < n; ++k) {
+    const int p = (h->peer_self + 1 + k) % n; /* every rank starts with a different peer */
+    cudaError_t e = cudaMemcpyAsync(dst_dev + (size_t)p * block + (size_t)ra * h->Mpad,
+                                    h->peer_out[p] + off, (size_t)(rb - ra) * h->Mpad * sizeof(double),
+                                    cudaMemcpyDefault, h->copy_stream);
+    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_ipc_pull: ") + cudaGetErrorString(e));
+  }
+  return HX_OK;
+}
+
+int hx_ipc_wait(hx_handle h) {
+  if (!h || !h->copy_stream) return HX_ERR_ARG;
+  cudaSetDevice(h->cfg.device);
+  cudaError_t e = cudaStreamSynchronize(h->copy_stream);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_ipc_wait: ") + cudaGetErrorString(e));
+  return HX_OK;
+}
+
+int hx_event_record(hx_handle h, int32_t idx) {
+  if (!h || idx < 0 || idx >= 16) return HX_ERR_ARG;
+  cudaSetDevice(h->cfg.device);
+  if (!h->ev_user[idx] &&
+      cudaEventCreateWithFlags(&h->ev_user[idx], cudaEventDisableTiming) != cudaSuccess)
+    return h->fail(HX_ERR_CUDA, "cudaEventCreate");
+  cudaError_t e = cudaEventRecord(h->ev_user[idx], h->stream);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
+  return HX_OK;
+}
+
+int hx_event_synchronize(hx_handle h, int32_t idx) {
+  if (!h || idx < 0 || idx >= 16 || !h->ev_user[idx]) return HX_ERR_ARG;
+  cudaSetDevice(h->cfg.device);
+  cudaError_t e = cudaEventSynchronize(h->ev_user[idx]);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
   return HX_OK;
 }
 

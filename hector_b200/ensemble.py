@@ -361,6 +361,30 @@ class Ensemble:
                                      float(frac[member, k, s])))
         return rows
 
+    # -- exchange between the GPUs of a node over peer memory (no kernels) --
+    def ipc_export(self):
+        """64-byte CUDA IPC handle of this engine's output block"""
+        buf = C.create_string_buffer(64)
+        self._chk(self.L.hx_ipc_export(self.h, buf, None))
+        return buf.raw
+
+    def ipc_open(self, handles, self_index):
+        blob = b"".join(handles)
+        self._chk(self.L.hx_ipc_open(self.h, len(handles), blob, int(self_index)))
+
+    def ipc_pull(self, var, year_a, year_b, dst_dev_ptr):
+        self._chk(self.L.hx_ipc_pull(self.h, var.encode(), int(year_a), int(year_b),
+                                     C.c_void_p(int(dst_dev_ptr))))
+
+    def ipc_wait(self):
+        self._chk(self.L.hx_ipc_wait(self.h))
+
+    def event_record(self, idx):
+        self._chk(self.L.hx_event_record(self.h, int(idx)))
+
+    def event_synchronize(self, idx):
+        self._chk(self.L.hx_event_synchronize(self.h, int(idx)))
+
     def status(self):
         st = np.empty(self.n_members, dtype=np.int32)
         fy = np.empty(self.n_members, dtype=np.int32)

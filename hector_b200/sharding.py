@@ -1,6 +1,12 @@
 """Multi-GPU plumbing: ensembles shard by member (no exchange during the run); the single
-collective of the job is an all-gather of the per-member summary outputs at the end
-(SURVEY.md section 8(e)).  Works with NCCL (GPU) and gloo (CPU tests)."""
+exchange of the job is an all-gather of the per-member summary outputs.
+
+  gather_summary   torch.distributed all-gather (NCCL on GPUs, gloo in the CPU tests)
+  PeerExchange     the same result over peer memory: every rank opens its peers' output blocks
+                   through CUDA IPC and pulls finished run segments with copy-engine transfers
+                   over NVLink while its own kernel computes the next segment.  A collective
+                   kernel cannot do that: it finds no room next to the persistent run kernel.
+"""
 import torch
 import torch.distributed as dist
 
@@ -31,3 +37,52 @@ def gather_summary(block, n_members, world):
         a, b = shard_range(n_members, k, world)
         parts.append(out[k][..., : b - a])
     return torch.cat(parts, dim=-1)
+
+
+class PeerExchange:
+    """All ranks (one engine each, same outputs / years / padded member count) end up with every
+    rank's trajectories of `variables`: self.blocks[v] is a device tensor [world, n_years,
+    member_stride], rank k's block at index k.
+
+        ex = PeerExchange(ens, ["CO2_concentration", "global_tas"], gloo_group)
+        ens.reset(); ex.run()          # run to the end date, exchanging as segments finish
+
+    Ordering across ranks is done on the host: a rank pulls segment k only after its own event
+    for k has completed and a barrier on `group` (a gloo group: an NCCL barrier is a kernel and
+    would queue behind the run kernel) says everybody's has."""
+
+    def __init__(self, ens, variables, group, segments=4):
+        import numpy as np
+        self.ens, self.variables, self.group = ens, list(variables), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, ens.ipc_export(), group=group)
+        ens.ipc_open(handles, self.rank)
+        _, stride, ny = ens.output_device(self.variables[0])
+        self.n_years, self.stride = ny, stride
+        self.blocks = {v: torch.empty((self.world, ny, stride), dtype=torch.float64,
+                                      device="cuda") for v in self.variables}
+        first = int(ens.start_year) + 1
+        nslab = (ny + 15) // 16
+        segments = max(1, min(int(segments), nslab))
+        cuts = sorted({min(ny, ((nslab * (k + 1)) // segments) * 16) for k in range(segments)}
+                      | {ny})
+        cuts = [c for c in cuts if c > 0]
+        self.segments = [(first + a, first + b - 1) for a, b in zip([0] + cuts[:-1], cuts)]
+        assert len(self.segments) <= 16
+        del np
+
+    def run(self):
+        ens = self.ens
+        for k, (ya, yb) in enumerate(self.segments):   # every segment is queued right away
+            ens.run(yb)
+            ens.event_record(k)
+        for k, (ya, yb) in enumerate(self.segments):
+            ens.event_synchronize(k)                   # my segment k is done ...
+            dist.barrier(group=self.group)             # ... and so is everybody's
+            for v in self.variables:
+                ens.ipc_pull(v, ya, yb, self.blocks[v].data_ptr())
+        ens.ipc_wait()
+        # nobody may overwrite its outputs (the next reset / run) while a peer still reads them
+        dist.barrier(group=self.group)
+        return self.blocks

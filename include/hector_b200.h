@@ -191,6 +191,25 @@ int hx_fetch_tracking(hx_handle h, double date, double *frac, uint32_t *mask);
  * error; at most `cap` are written */
 int hx_tracking_years(hx_handle h, int32_t *years, int32_t cap);
 
+/* Exchange of recorded outputs between the GPUs of one node WITHOUT kernels: every rank exports
+ * its output block through CUDA IPC (64-byte handle; pass the handles around with any host-side
+ * collective), opens its peers' blocks, and pulls finished year ranges with copy-engine
+ * transfers over NVLink while its own run kernel keeps every SM (a collective kernel finds no
+ * room next to the persistent run kernel).  All ranks must have the
+ * same outputs, years and padded member count.  dst_dev is a device buffer
+ * [n_peers][n_years][member_stride] (hx_output_device gives n_years and member_stride); rows
+ * year_a .. year_b (inclusive, calendar years) of every peer land at their place in it.  The
+ * caller orders things across ranks: pull a range only after every rank has finished it
+ * (hx_event_record after the run segment, hx_event_synchronize, then a host barrier). */
+int hx_ipc_export(hx_handle h, void *handle64, int64_t *bytes);
+int hx_ipc_open(hx_handle h, int32_t n_peers, const void *handles, int32_t self_index);
+int hx_ipc_pull(hx_handle h, const char *name, int32_t year_a, int32_t year_b, double *dst_dev);
+int hx_ipc_wait(hx_handle h);  /* all pulls issued so far have landed */
+int hx_ipc_close(hx_handle h);
+/* markers on the engine's stream (idx 0..15): record after a launch, wait for it on the host */
+int hx_event_record(hx_handle h, int32_t idx);
+int hx_event_synchronize(hx_handle h, int32_t idx);
+
 int hx_member_status(hx_handle h, int32_t *status, int32_t *fail_year, int32_t n);
 int hx_counters(hx_handle h, uint64_t *out, int32_t n);
 double hx_current_date(hx_handle h);
