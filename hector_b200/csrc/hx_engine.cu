@@ -153,6 +153,7 @@ struct Engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_seg = nullptr, ev_copy = nullptr;
   /* multi-GPU exchange over peer memory: peers' output blocks opened through CUDA IPC */
   std::vector<double *> peer_out;
+  std::vector<cudaStream_t> peer_stream; /* one per peer: the pulls spread over the copy engines */
   int peer_self = -1;
   cudaEvent_t ev_user[16] = {};
 
@@ -994,6 +995,12 @@ int hx_ipc_open(hx_handle h, int32_t n_peers, const void *handles, int32_t self_
     }
     h->peer_out[p] = (double *)ptr;
   }
+  h->peer_stream.assign(n_peers, nullptr);
+  for (int p = 0; p < n_peers; ++p)
+    if (cudaStreamCreateWithFlags(&h->peer_stream[p], cudaStreamNonBlocking) != cudaSuccess) {
+      hx_ipc_close(h);
+      return h->fail(HX_ERR_CUDA, "hx_ipc_open: could not create the copy streams");
+    }
   return ensure_copy_stream(h);
 }
 
@@ -1001,6 +1008,9 @@ int hx_ipc_close(hx_handle h) {
   if (!h) return HX_OK;
   for (size_t p = 0; p < h->peer_out.size(); ++p)
     if ((int)p != h->peer_self && h->peer_out[p]) cudaIpcCloseMemHandle(h->peer_out[p]);
+  for (cudaStream_t s : h->peer_stream)
+    if (s) cudaStreamDestroy(s);
+  h->peer_stream.clear();
   h->peer_out.clear();
   h->peer_self = -1;
   return HX_OK;
@@ -1021,17 +1031,19 @@ int hx_ipc_pull(hx_handle h, const char *name, int32_t year_a, int32_t year_b, d
     const int p = (h->peer_self + 1 + k) % n; /* every rank starts with a different peer */
     cudaError_t e = cudaMemcpyAsync(dst_dev + (size_t)p * block + (size_t)ra * h->Mpad,
                                     h->peer_out[p] + off, (size_t)(rb - ra) * h->Mpad * sizeof(double),
-                                    cudaMemcpyDefault, h->copy_stream);
+                                    cudaMemcpyDefault, h->peer_stream[p]);
     if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_ipc_pull: ") + cudaGetErrorString(e));
   }
   return HX_OK;
 }
 
 int hx_ipc_wait(hx_handle h) {
-  if (!h || !h->copy_stream) return HX_ERR_ARG;
+  if (!h) return HX_ERR_ARG;
   cudaSetDevice(h->cfg.device);
-  cudaError_t e = cudaStreamSynchronize(h->copy_stream);
-  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_ipc_wait: ") + cudaGetErrorString(e));
+  for (cudaStream_t s : h->peer_stream) {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_ipc_wait: ") + cudaGetErrorString(e));
+  }
   return HX_OK;
 }
 
