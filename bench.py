@@ -469,11 +469,20 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args), "clocks": clocks, "e2e": e2e,
-        "gpu_launches": 2 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+        # per step: one run kernel + one NaN-fill kernel per run segment (1 segment at N = 1,
+        # --exchange-segments / --gather-segments of them at N > 1); restores and exchanges
+        # are copies, not kernels
+        "gpu_launches": 2 * args.steps * (1 if world == 1 else
+                                          (len(exchange.segments) if exchange is not None
+                                           else len(seg_rows))),
+        "roofline": roofline, "cpu_baseline": cpu,
         "work_per_member_year": {k: cnt[k] / max(1, cnt["member_years"]) for k in
                                  ("rhs_evals", "rk_steps", "stashes", "newton_iterations",
                                   "newton_calls")},
         "failed_members": failed, "small_ensemble": small, "tracked_ensemble": tracked,
+        "exchange": None if world == 1 else
+        ("peer memory (CUDA IPC pulls, %d run segments)" % len(exchange.segments)
+         if exchange is not None else "NCCL all-gather (%d run segments)" % len(seg_rows)),
     }
     print(json.dumps(line))
     ens.close()

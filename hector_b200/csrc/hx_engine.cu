@@ -35,10 +35,6 @@ thread_local std::string g_create_error;
   } while (0)
 
 /* ---- small utility kernels ---- */
-__global__ void k_fill(double *p, double v, size_t n) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
-}
 /* field `f` of a CTA-tiled array (hx_layout.h) for every device member: A[f][m] = v */
 __global__ void k_fill_field(double *A, int f, int nfields, double v, int Mpad) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,12 +185,6 @@ struct Engine {
     return -1;
   }
   const double *con(int s, int series) const { return cons[s].data() + (size_t)series * nrow; }
-  bool has_constraint(int s, int series) const {
-    const double *c = con(s, series);
-    for (int r = 0; r < nrow; ++r)
-      if (c[r] == c[r]) return true;
-    return false;
-  }
   /* tseries::get() of a series that allows interpolation (tas_constrain, RF_tot_constrain:
    * temperature_component.cpp:112, forcing_component.cpp:112): linear between entries;
    * `flat_below` extends the first entry downwards (RF_tot is applied for every year up to the
