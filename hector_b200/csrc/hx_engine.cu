@@ -139,7 +139,8 @@ struct Engine {
           *d_fail_year = nullptr, *d_spinup_steps = nullptr, *d_yidx = nullptr;
   unsigned long long *d_counters = nullptr;
   unsigned *d_sched = nullptr;
-  double *d_T = nullptr, *d_TO = nullptr;
+  double *d_T = nullptr, *d_TO = nullptr, *d_REC = nullptr;
+  unsigned char *d_YCNT = nullptr;
   uint32_t *d_TK = nullptr, *d_TOK = nullptr;
   size_t stage_bytes = 0, yidx_cap = 0;
   double *h_pinned = nullptr;
@@ -279,14 +280,15 @@ struct Engine {
   void free_device() {
     void *ptrs[] = {d_P, d_S, d_S_snap, d_D, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
                     d_block_scen, d_status, d_status_snap, d_status_post, d_fail_year, d_spinup_steps, d_yidx,
-                    d_counters, d_dev_of_api, d_sched, d_T, d_TO, d_TK, d_TOK};
+                    d_counters, d_dev_of_api, d_sched, d_T, d_TO, d_TK, d_TOK, d_REC, d_YCNT};
     for (void *p : ptrs)
       if (p) cudaFree(p);
     d_P = d_S = d_S_snap = d_D = d_ker = d_conv = d_sst = d_tland = d_out = d_scen = d_stage = nullptr;
     d_block_scen = d_status = d_status_snap = d_status_post = d_fail_year = d_spinup_steps = d_yidx = nullptr;
     d_counters = nullptr;
     d_sched = nullptr;
-    d_T = d_TO = nullptr;
+    d_T = d_TO = d_REC = nullptr;
+    d_YCNT = nullptr;
     d_TK = d_TOK = nullptr;
     d_dev_of_api = nullptr;
     stage_bytes = 0;
@@ -354,6 +356,23 @@ struct Engine {
   }
 
   int first_active = 0;
+
+  /* rows ra+1 .. rb of the run.  With carbon tracking on the run kernel only records each
+   * stash's flux scalars, one 16-year slab per launch, and the replay kernel folds them into
+   * the source maps before the next slab overwrites the record. */
+  cudaError_t launch_rows(int ra, int rb) {
+    if (!d_T) return hx::launch_run(d, C, ra, rb, stream);
+    const int slab = hx::track_slab_years();
+    while (ra < rb) {
+      const int re = std::min(rb, ra + slab);
+      cudaError_t e = hx::launch_run(d, C, ra, re, stream);
+      if (e == cudaSuccess && cfg.start_year + re >= C.tracking_date)
+        e = hx::launch_track(d, C, ra, re, stream);
+      if (e != cudaSuccess) return e;
+      ra = re;
+    }
+    return cudaSuccess;
+  }
 
   int run_setup_and_spinup() {
     if (tables_dirty) {
@@ -742,6 +761,7 @@ int hx_prepare(hx_handle h) {
 
   const size_t Mp = Mpad;
   const int nsel = (int)h->out_sel.size();
+
   if (cudaMalloc(&h->d_P, PI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_S, SI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_S_snap, SI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
@@ -765,7 +785,9 @@ int hx_prepare(hx_handle h) {
        (cudaMalloc(&h->d_T, (size_t)TS_COUNT * HX_NSRC * Mp * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_TK, (size_t)TS_COUNT * Mp * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&h->d_TO, h->track_years.size() * HX_NPOOL * HX_NSRC * Mp * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&h->d_TOK, h->track_years.size() * HX_NPOOL * Mp * sizeof(uint32_t)) != cudaSuccess))) {
+        cudaMalloc(&h->d_TOK, h->track_years.size() * HX_NPOOL * Mp * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&h->d_REC, block_scen.size() * hx::track_record_bytes_per_cta()) != cudaSuccess ||
+        cudaMalloc(&h->d_YCNT, block_scen.size() * hx::track_ycnt_bytes_per_tile()) != cudaSuccess))) {
     cudaError_t e = cudaGetLastError();
     h->free_device();
     return fail(HX_ERR_CUDA, (std::string("device allocation failed: ") + cudaGetErrorString(e)).c_str());
@@ -794,7 +816,7 @@ int hx_prepare(hx_handle h) {
   d.sst_hist = h->d_sst; d.tland_hist = h->d_tland; d.out = h->d_out; d.scen = h->d_scen;
   d.block_scen = h->d_block_scen; d.status = h->d_status; d.fail_year = h->d_fail_year;
   d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters; d.sched = h->d_sched;
-  d.T = h->d_T; d.TK = h->d_TK; d.TO = h->d_TO; d.TOK = h->d_TOK;
+  d.T = h->d_T; d.TK = h->d_TK; d.TO = h->d_TO; d.TOK = h->d_TOK; d.REC = h->d_REC; d.YCNT = h->d_YCNT;
   d.constrained = any_constraint ? 1 : 0;
   for (int i = 0; i < OUT_COUNT; ++i) d.out_slot[i] = -1;
   for (int s = 0; s < nsel; ++s) d.out_slot[h->out_sel[s]] = s;
@@ -865,7 +887,7 @@ int hx_run(hx_handle h, double run_to_date) {
   cudaStream_t st = h->stream;
   cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st);
   cudaEventRecord(h->ev0, st);
-  cudaError_t e = hx::launch_run(h->d, h->C, h->cur_row, r1, st);
+  cudaError_t e = h->launch_rows(h->cur_row, r1);
   if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("run kernel launch: ") + cudaGetErrorString(e));
   if (!h->out_sel.empty()) {
     e = hx::launch_nan_fill(h->d, h->C, (int)h->out_sel.size(), h->cur_row, r1, st);
@@ -923,7 +945,7 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
                        ? r1
                        : r0 + (int)(((long long)nslab * (sg + 1)) / segments) * HX_SLAB_YEARS;
     if (rb <= ra) continue;
-    cudaError_t e = hx::launch_run(h->d, h->C, ra, rb, st);
+    cudaError_t e = h->launch_rows(ra, rb);
     if (e == cudaSuccess && !h->out_sel.empty())
       e = hx::launch_nan_fill(h->d, h->C, (int)h->out_sel.size(), ra, rb, st);
     if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("run segment: ") + cudaGetErrorString(e));

@@ -117,7 +117,7 @@ __device__ __forceinline__ void load_member(const Bases &BS, Member &mb) {
   mb.solver_dt = STATE(SI_SOLVER_DT);
   mb.status = 0; mb.neg = false; mb.timesteps = 0;
   mb.pco2HL = mb.pco2LL = 0.0; mb.gHL = mb.gLL = 0.0; mb.luc_e = mb.luc_u = 0.0;
-  mb.T = BS.T; mb.TK = BS.TK; mb.trk = false; mb.trk_bad = false;
+  mb.REC = nullptr; mb.rec_n = 0; mb.trk = false; mb.trk_bad = false;
 }
 
 __device__ __forceinline__ void store_member(const Bases &BS, const Member &mb) {
@@ -584,6 +584,13 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
      * running at the top of each year, members that stopped early (failed, or padding lanes)
      * in the drain loop below.  The arrivals come from divergent code, hence the non-aligned
      * barrier.sync on a named barrier of its own. */
+    unsigned char ycnt[HX_SLAB_YEARS]; /* stashes recorded up to the end of each year (TRACK) */
+    if (TRACK) {
+#pragma unroll
+      for (int j = 0; j < HX_SLAB_YEARS; ++j) ycnt[j] = 0;
+      mb.REC = d.REC + ((size_t)tile * HX_BLOCK + tid) * (HX_REC_STASH_MAX * HX_REC_N);
+      mb.rec_n = 0;
+    }
     int r = base + 1;
     const bool entered = (mb.status == 0);
     if (entered) {
@@ -649,7 +656,6 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
              * ocean_component.cpp:358-366); the ocean gets this year's copy of the atmosphere's
              * source map (set_atmosphere_sources, :225) */
             mb.trk = (y >= C.tracking_date);
-            if (mb.trk) tm_copy(mb, TS_ATM_CPOOL, TS_ATMOS);
           }
           mb.luc_e = scm1[SC_LUC_E]; mb.luc_u = scm1[SC_LUC_U];
           mb.S[SI_X_FFI * HX_TILE] = scm1[SC_FFI]; mb.S[SI_X_DACCS * HX_TILE] = scm1[SC_DACCS];
@@ -809,21 +815,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         }
         ++years_done;
 
-        /* --- what the CSVFluxPoolVisitor would print this year (csv_tracking_visitor.cpp:
-         * 80-137): source fractions and key masks of the 11 tracked pools --- */
-        if (TRACK && mb.trk) {
-          const int k = y - C.tracking_date;
-          int rec = -1;
-          if (C.track_every > 0 && k % C.track_every == 0) rec = k / C.track_every;
-          else if (y == C.end_year) rec = C.track_nrec - 1;
-          if (rec >= 0) {
-            double *to = d.TO + (size_t)rec * (HX_NPOOL * HX_NSRC) * Mp + m;
-            for (int q = 0; q < HX_NPOOL * HX_NSRC; ++q)
-              to[(size_t)q * Mp] = mb.T[(size_t)q * HX_TILE];
-            uint32_t *tk = d.TOK + (size_t)rec * HX_NPOOL * Mp + m;
-            for (int q = 0; q < HX_NPOOL; ++q) tk[(size_t)q * Mp] = mb.TK[q * HX_TILE];
-          }
-        }
+        if (TRACK) ycnt[r - base - 1] = (unsigned char)mb.rec_n;
 
         /* --- outputs (record_state / getData of each component) --- */
         const int yi = r - 1;
@@ -873,6 +865,21 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
      * member that ran the whole slab, base + 1 with no arrivals yet for a lane that never ran */
     for (int q = entered ? r + 1 : r; q <= rend; ++q) year_barrier();
 #endif
+    if (TRACK) {
+      /* hand the slab's record to the replay kernel: years a stopped member never reached carry
+       * the last count forward; a record that overflowed fails the member */
+      unsigned char *yc = d.YCNT + (size_t)tile * (HX_SLAB_YEARS * HX_BLOCK) + tid;
+#pragma unroll
+      for (int j = 0; j < HX_SLAB_YEARS; ++j) {
+        if (j > 0 && ycnt[j] < ycnt[j - 1]) ycnt[j] = ycnt[j - 1];
+        yc[j * HX_BLOCK] = entered ? ycnt[j] : 0;
+      }
+      if (entered && mb.trk_bad && mb.status == 0) {
+        mb.status = HX_MEMBER_TRACKING;
+        d.status[m] = mb.status;
+        d.fail_year[m] = C.start_year + base + 1;
+      }
+    }
     if (lane_ok) {
       if (mb.status == 0) store_member(BS, mb);
       else ++failed;
@@ -903,6 +910,82 @@ __global__ void hx_track_init_kernel(const __grid_constant__ HxDev d) {
     else if (i >= TS_ADD_HL) self = TS_HL + (i - TS_ADD_HL);
     for (int s = 0; s < HX_NSRC; ++s) T[((size_t)i * HX_NSRC + s) * HX_BLOCK] = (s == self) ? 1.0 : 0.0;
     K[(size_t)i * HX_BLOCK] = self >= 0 ? (1u << self) : 0u;
+  }
+}
+
+/* Replay of one slab's stash records into the members' source maps: one thread per (member,
+ * source), 16 lanes per member (12 of them mixing) so that a member never straddles a warp.
+ * The sixteen lanes stage the member's record through shared memory: while stash st is mixed,
+ * the (a, b) pairs of stash st+1 are already in flight as whole 128-byte lines. */
+#define HX_TRK_MEMBERS 8 /* members per 128-thread CTA */
+struct StagedRecord {
+  const double *rec;   /* the member's record, [stash][HX_REC_N] */
+  double *sh;          /* this member's two staging buffers, [2][HX_REC_MIX * HX_REC_ROW] */
+  int lane, nst;
+  unsigned mask;       /* the member's 16 lanes within the warp */
+  double v[(HX_REC_N + 15) / 16]; /* next stash in flight */
+  int staged;          /* stash whose pairs are in v, -1: none */
+  __device__ __forceinline__ void prefetch(int st) {
+    staged = st;
+    if (st >= nst) return;
+    const double *p = rec + (size_t)st * HX_REC_N;
+#pragma unroll
+    for (int j = 0; j < (HX_REC_N + 15) / 16; ++j) {
+      const int i = lane + 16 * j;
+      v[j] = (i < HX_REC_N) ? __ldcs(p + i) : 0.0;
+    }
+  }
+  /* rows (a, b, 1 / (a + b)) of stash st in shared memory; st advances by one per call */
+  __device__ __forceinline__ const double *stash(int st) {
+    double *buf = sh + (st & 1) * (HX_REC_MIX * HX_REC_ROW);
+    if (staged != st) prefetch(st);
+#pragma unroll
+    for (int j = 0; j < (HX_REC_N + 15) / 16; ++j) {
+      const int i = lane + 16 * j; /* pair element i = 2 k + {0, 1} */
+      if (i < HX_REC_N) buf[(i >> 1) * HX_REC_ROW + (i & 1)] = v[j];
+    }
+    __syncwarp(mask);
+#pragma unroll
+    for (int j = 0; j < (HX_REC_MIX + 15) / 16; ++j) {
+      const int kx = lane + 16 * j;
+      if (kx < HX_REC_MIX) {
+        const double total = __dadd_rn(buf[kx * HX_REC_ROW], buf[kx * HX_REC_ROW + 1]);
+        buf[kx * HX_REC_ROW + 2] = (total != 0.0) ? 1.0 / total : 0.0;
+      }
+    }
+    prefetch(st + 1);
+    __syncwarp(mask);
+    return buf;
+  }
+};
+
+__global__ void __launch_bounds__(128, 5)
+hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
+  __shared__ double sh[HX_TRK_MEMBERS][2][HX_REC_MIX * HX_REC_ROW];
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = gid >> 4, s = gid & 15;
+  if (m >= d.Mpad) return;
+  if (d.status[m] < 0) return; /* padding lane (all 16 lanes of the member leave together) */
+  const size_t tile = (size_t)(m / HX_BLOCK), ln = (size_t)(m % HX_BLOCK);
+  double *T = d.T + tile * (size_t)(TS_COUNT * HX_NSRC) * HX_BLOCK + ln;
+  uint32_t *TK = d.TK + tile * (size_t)TS_COUNT * HX_BLOCK + ln;
+  const unsigned char *yc = d.YCNT + tile * (size_t)(HX_SLAB_YEARS * HX_BLOCK) + ln;
+  const int nyears = r1 - r0;
+  StagedRecord fetch;
+  fetch.rec = d.REC + (size_t)m * (HX_REC_STASH_MAX * HX_REC_N);
+  fetch.sh = &sh[threadIdx.x >> 4][0][0];
+  fetch.lane = s;
+  fetch.nst = yc[(nyears - 1) * HX_BLOCK];
+  fetch.mask = 0xFFFFu << (threadIdx.x & 16);
+  fetch.staged = -1;
+  /* the four idle lanes of a member help with the staging and mix a source that is written
+   * nowhere: source index 12 .. 15 is outside every map */
+  const bool good = track_replay<1>(T, TK, fetch, yc, HX_BLOCK, nyears, C.start_year + r0 + 1, s,
+                                    s + 1, C.tracking_date, C.track_every, C.track_nrec,
+                                    C.end_year, d.TO + m, d.TOK + m, (size_t)d.Mpad);
+  if (s < HX_NSRC && !good && d.status[m] == 0) {
+    d.status[m] = HX_MEMBER_TRACKING;
+    d.fail_year[m] = C.start_year + r0 + 1;
   }
 }
 
@@ -979,6 +1062,16 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
                  : launch_run_t<false, true, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
   return small ? launch_run_t<false, false, 2>(d, C, r0, r1, st)
                : launch_run_t<false, false, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
+}
+size_t track_record_bytes_per_cta() {
+  return (size_t)HX_REC_STASH_MAX * HX_REC_N * HX_BLOCK * sizeof(double);
+}
+size_t track_ycnt_bytes_per_tile() { return (size_t)HX_SLAB_YEARS * HX_BLOCK; }
+int track_slab_years() { return HX_SLAB_YEARS; }
+cudaError_t launch_track(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
+  const long long threads = (long long)d.Mpad * 16;
+  hx_track_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(d, C, r0, r1);
+  return cudaGetLastError();
 }
 cudaError_t launch_track_init(const HxDev &d, cudaStream_t st) {
   hx_track_init_kernel<<<(d.Mpad + 255) / 256, 256, 0, st>>>(d);

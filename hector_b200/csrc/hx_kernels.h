@@ -40,6 +40,9 @@ struct HxDev {
   /* carbon tracking (null unless a tracking date was set) */
   double *T;                /* [tile][TS_COUNT * HX_NSRC][128] source fractions */
   uint32_t *TK;             /* [tile][TS_COUNT][128] key masks */
+  double *REC;              /* [member][HX_REC_STASH_MAX][HX_REC_N] stash records of the slab
+                               being run (hx_model.cuh, "Carbon tracking") */
+  unsigned char *YCNT;      /* [tile][HX_SLAB_YEARS][128] stashes recorded up to each year's end */
   double *TO;               /* [track_nrec][HX_NPOOL * HX_NSRC][Mpad] recorded fractions */
   uint32_t *TOK;            /* [track_nrec][HX_NPOOL][Mpad] recorded key masks */
 };
@@ -50,6 +53,11 @@ cudaError_t launch_spinup(const HxDev &d, const HxConst &C, cudaStream_t st);
 cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cudaStream_t st);
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st);
 cudaError_t launch_track_init(const HxDev &d, cudaStream_t st);
+size_t track_record_bytes_per_cta(); /* size of one tile's REC block */
+size_t track_ycnt_bytes_per_tile();
+int track_slab_years();
+/* replay the records of rows r0+1 .. r1 (one slab, as just run) into the source maps */
+cudaError_t launch_track(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st);
 cudaError_t launch_nan_fill(const HxDev &d, const HxConst &C, int nsel, int yr0, int yr1,
                             cudaStream_t st);
 }
