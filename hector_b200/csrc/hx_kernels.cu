@@ -917,21 +917,25 @@ __global__ void hx_track_init_kernel(const __grid_constant__ HxDev d) {
  * source), 16 lanes per member (12 of them mixing) so that a member never straddles a warp.
  * The sixteen lanes stage the member's record through shared memory: while stash st is mixed,
  * the (a, b) pairs of stash st+1 are already in flight as whole 128-byte lines. */
-#define HX_TRK_MEMBERS 8 /* members per 128-thread CTA */
+#ifndef HX_TRK_NS
+#define HX_TRK_NS 2 /* sources per replay thread: 2-way ILP in every mix (150 vs 163 ms with 1) */
+#endif
+#define HX_TRK_LANES (16 / HX_TRK_NS)            /* lanes per member */
+#define HX_TRK_MEMBERS (128 / HX_TRK_LANES)      /* members per 128-thread CTA */
 struct StagedRecord {
   const double *rec;   /* the member's record, [stash][HX_REC_N] */
   double *sh;          /* this member's two staging buffers, [2][HX_REC_MIX * HX_REC_ROW] */
   int lane, nst;
   unsigned mask;       /* the member's 16 lanes within the warp */
-  double v[(HX_REC_N + 15) / 16]; /* next stash in flight */
+  double v[(HX_REC_N + HX_TRK_LANES - 1) / HX_TRK_LANES]; /* next stash in flight */
   int staged;          /* stash whose pairs are in v, -1: none */
   __device__ __forceinline__ void prefetch(int st) {
     staged = st;
     if (st >= nst) return;
     const double *p = rec + (size_t)st * HX_REC_N;
 #pragma unroll
-    for (int j = 0; j < (HX_REC_N + 15) / 16; ++j) {
-      const int i = lane + 16 * j;
+    for (int j = 0; j < (HX_REC_N + HX_TRK_LANES - 1) / HX_TRK_LANES; ++j) {
+      const int i = lane + HX_TRK_LANES * j;
       v[j] = (i < HX_REC_N) ? __ldcs(p + i) : 0.0;
     }
   }
@@ -940,14 +944,14 @@ struct StagedRecord {
     double *buf = sh + (st & 1) * (HX_REC_MIX * HX_REC_ROW);
     if (staged != st) prefetch(st);
 #pragma unroll
-    for (int j = 0; j < (HX_REC_N + 15) / 16; ++j) {
-      const int i = lane + 16 * j; /* pair element i = 2 k + {0, 1} */
+    for (int j = 0; j < (HX_REC_N + HX_TRK_LANES - 1) / HX_TRK_LANES; ++j) {
+      const int i = lane + HX_TRK_LANES * j; /* pair element i = 2 k + {0, 1} */
       if (i < HX_REC_N) buf[(i >> 1) * HX_REC_ROW + (i & 1)] = v[j];
     }
     __syncwarp(mask);
 #pragma unroll
-    for (int j = 0; j < (HX_REC_MIX + 15) / 16; ++j) {
-      const int kx = lane + 16 * j;
+    for (int j = 0; j < (HX_REC_MIX + HX_TRK_LANES - 1) / HX_TRK_LANES; ++j) {
+      const int kx = lane + HX_TRK_LANES * j;
       if (kx < HX_REC_MIX) {
         const double total = __dadd_rn(buf[kx * HX_REC_ROW], buf[kx * HX_REC_ROW + 1]);
         buf[kx * HX_REC_ROW + 2] = (total != 0.0) ? 1.0 / total : 0.0;
@@ -959,11 +963,11 @@ struct StagedRecord {
   }
 };
 
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, HX_TRK_NS == 1 ? 5 : 3)
 hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   __shared__ double sh[HX_TRK_MEMBERS][2][HX_REC_MIX * HX_REC_ROW];
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m = gid >> 4, s = gid & 15;
+  const int m = gid / HX_TRK_LANES, s = gid % HX_TRK_LANES;
   if (m >= d.Mpad) return;
   if (d.status[m] < 0) return; /* padding lane (all 16 lanes of the member leave together) */
   const size_t tile = (size_t)(m / HX_BLOCK), ln = (size_t)(m % HX_BLOCK);
@@ -973,17 +977,19 @@ hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   const int nyears = r1 - r0;
   StagedRecord fetch;
   fetch.rec = d.REC + (size_t)m * (HX_REC_STASH_MAX * HX_REC_N);
-  fetch.sh = &sh[threadIdx.x >> 4][0][0];
+  fetch.sh = &sh[threadIdx.x / HX_TRK_LANES][0][0];
   fetch.lane = s;
   fetch.nst = yc[(nyears - 1) * HX_BLOCK];
-  fetch.mask = 0xFFFFu << (threadIdx.x & 16);
+  fetch.mask = ((HX_TRK_LANES == 16) ? 0xFFFFu : 0xFFu)
+               << ((threadIdx.x & 31) / HX_TRK_LANES * HX_TRK_LANES);
   fetch.staged = -1;
   /* the four idle lanes of a member help with the staging and mix a source that is written
    * nowhere: source index 12 .. 15 is outside every map */
-  const bool good = track_replay<1>(T, TK, fetch, yc, HX_BLOCK, nyears, C.start_year + r0 + 1, s,
-                                    s + 1, C.tracking_date, C.track_every, C.track_nrec,
+  const bool good = track_replay<HX_TRK_NS>(T, TK, fetch, yc, HX_BLOCK, nyears,
+                                            C.start_year + r0 + 1, s * HX_TRK_NS,
+                                            (s + 1) * HX_TRK_NS, C.tracking_date, C.track_every, C.track_nrec,
                                     C.end_year, d.TO + m, d.TOK + m, (size_t)d.Mpad);
-  if (s < HX_NSRC && !good && d.status[m] == 0) {
+  if (s * HX_TRK_NS < HX_NSRC && !good && d.status[m] == 0) {
     d.status[m] = HX_MEMBER_TRACKING;
     d.fail_year[m] = C.start_year + r0 + 1;
   }
@@ -1069,7 +1075,7 @@ size_t track_record_bytes_per_cta() {
 size_t track_ycnt_bytes_per_tile() { return (size_t)HX_SLAB_YEARS * HX_BLOCK; }
 int track_slab_years() { return HX_SLAB_YEARS; }
 cudaError_t launch_track(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
-  const long long threads = (long long)d.Mpad * 16;
+  const long long threads = (long long)d.Mpad * HX_TRK_LANES;
   hx_track_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
