@@ -360,17 +360,51 @@ struct Engine {
   /* rows ra+1 .. rb of the run.  With carbon tracking on the run kernel only records each
    * stash's flux scalars, one 16-year slab per launch, and the replay kernel folds them into
    * the source maps before the next slab overwrites the record. */
+  cudaStream_t track_stream = nullptr;
+  cudaEvent_t ev_rec_full[2] = {nullptr, nullptr}, ev_rec_free[2] = {nullptr, nullptr};
+  size_t rec_elems = 0, ycnt_bytes = 0; /* size of one of the two record buffers */
+
+  /* The record is double buffered and the replay runs on a stream of its own, so the run
+   * kernel of slab s+1 overlaps the replay of slab s (the replay's CTAs fill the SMs that the
+   * run kernel's last wave leaves idle, and vice versa).  Replays stay in order on their
+   * stream; a record buffer is rewritten only after its replay has finished. */
   cudaError_t launch_rows(int ra, int rb) {
     if (!d_T) return hx::launch_run(d, C, ra, rb, stream);
+    if (!track_stream) {
+      cudaError_t e = cudaStreamCreateWithFlags(&track_stream, cudaStreamNonBlocking);
+      for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&ev_rec_full[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_rec_free[i], cudaEventDisableTiming);
+      }
+      if (e != cudaSuccess) return e;
+    }
     const int slab = hx::track_slab_years();
-    while (ra < rb) {
+    bool used[2] = {false, false};
+    for (int i = 0; ra < rb; ++i) {
       const int re = std::min(rb, ra + slab);
-      cudaError_t e = hx::launch_run(d, C, ra, re, stream);
-      if (e == cudaSuccess && cfg.start_year + re >= C.tracking_date)
-        e = hx::launch_track(d, C, ra, re, stream);
+      const int b = i & 1;
+      HxDev db = d;
+      db.REC = d_REC + (size_t)b * rec_elems;
+      db.YCNT = d_YCNT + (size_t)b * ycnt_bytes;
+      cudaError_t e = cudaSuccess;
+      if (used[b]) e = cudaStreamWaitEvent(stream, ev_rec_free[b], 0);
+      if (e == cudaSuccess) e = hx::launch_run(db, C, ra, re, stream);
+      if (e == cudaSuccess && cfg.start_year + re >= C.tracking_date) {
+        e = cudaEventRecord(ev_rec_full[b], stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(track_stream, ev_rec_full[b], 0);
+        if (e == cudaSuccess) e = hx::launch_track(db, C, ra, re, track_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_rec_free[b], track_stream);
+        used[b] = true;
+      }
       if (e != cudaSuccess) return e;
       ra = re;
     }
+    /* whatever follows on the engine's stream sees the maps and statuses of every replay */
+    for (int b = 0; b < 2; ++b)
+      if (used[b]) {
+        cudaError_t e = cudaStreamWaitEvent(stream, ev_rec_free[b], 0);
+        if (e != cudaSuccess) return e;
+      }
     return cudaSuccess;
   }
 
@@ -492,6 +526,11 @@ int hx_destroy(hx_handle h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   hx_ipc_close(h);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_rec_full[i]) cudaEventDestroy(h->ev_rec_full[i]);
+    if (h->ev_rec_free[i]) cudaEventDestroy(h->ev_rec_free[i]);
+  }
+  if (h->track_stream) cudaStreamDestroy(h->track_stream);
   for (cudaEvent_t e : h->ev_user)
     if (e) cudaEventDestroy(e);
   if (h->ev_seg) cudaEventDestroy(h->ev_seg);
@@ -786,8 +825,8 @@ int hx_prepare(hx_handle h) {
         cudaMalloc(&h->d_TK, (size_t)TS_COUNT * Mp * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&h->d_TO, h->track_years.size() * HX_NPOOL * HX_NSRC * Mp * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_TOK, h->track_years.size() * HX_NPOOL * Mp * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMalloc(&h->d_REC, block_scen.size() * hx::track_record_bytes_per_cta()) != cudaSuccess ||
-        cudaMalloc(&h->d_YCNT, block_scen.size() * hx::track_ycnt_bytes_per_tile()) != cudaSuccess))) {
+        cudaMalloc(&h->d_REC, 2 * block_scen.size() * hx::track_record_bytes_per_cta()) != cudaSuccess ||
+        cudaMalloc(&h->d_YCNT, 2 * block_scen.size() * hx::track_ycnt_bytes_per_tile()) != cudaSuccess))) {
     cudaError_t e = cudaGetLastError();
     h->free_device();
     return fail(HX_ERR_CUDA, (std::string("device allocation failed: ") + cudaGetErrorString(e)).c_str());
@@ -817,6 +856,8 @@ int hx_prepare(hx_handle h) {
   d.block_scen = h->d_block_scen; d.status = h->d_status; d.fail_year = h->d_fail_year;
   d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters; d.sched = h->d_sched;
   d.T = h->d_T; d.TK = h->d_TK; d.TO = h->d_TO; d.TOK = h->d_TOK; d.REC = h->d_REC; d.YCNT = h->d_YCNT;
+  h->rec_elems = block_scen.size() * hx::track_record_bytes_per_cta() / sizeof(double);
+  h->ycnt_bytes = block_scen.size() * hx::track_ycnt_bytes_per_tile();
   d.constrained = any_constraint ? 1 : 0;
   for (int i = 0; i < OUT_COUNT; ++i) d.out_slot[i] = -1;
   for (int s = 0; s < nsel; ++s) d.out_slot[h->out_sel[s]] = s;
