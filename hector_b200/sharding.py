@@ -55,9 +55,24 @@ class PeerExchange:
         import numpy as np
         self.ens, self.variables, self.group = ens, list(variables), group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        # every rank must reach both collectives even if its own CUDA IPC call fails
+        try:
+            mine, err = ens.ipc_export(), None
+        except Exception as ex:
+            mine, err = None, ex
         handles = [None] * self.world
-        dist.all_gather_object(handles, ens.ipc_export(), group=group)
-        ens.ipc_open(handles, self.rank)
+        dist.all_gather_object(handles, mine, group=group)
+        if err is None and all(h is not None for h in handles):
+            try:
+                ens.ipc_open(handles, self.rank)
+            except Exception as ex:
+                err = ex
+        elif err is None:
+            err = RuntimeError("a peer could not export its output block")
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            raise err if err is not None else RuntimeError("a peer could not open the blocks")
         _, stride, ny = ens.output_device(self.variables[0])
         self.n_years, self.stride = ny, stride
         self.blocks = {v: torch.empty((self.world, ny, stride), dtype=torch.float64,
