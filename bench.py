@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--members", type=int, default=65536, help="members per GPU")
     ap.add_argument("--small-members", type=int, default=1024,
                     help="also time BASELINE.json configs[1] (0 = skip)")
+    ap.add_argument("--multi-scenario-members", type=int, default=65536,
+                    help="also time an ensemble over all 8 SSP scenarios interleaved (0 = skip)")
     ap.add_argument("--tracked-members", type=int, default=65536,
                     help="also time a carbon-tracking ensemble to 2500 (0 = skip)")
     ap.add_argument("--e2e-segments", type=int, default=4)
@@ -416,6 +418,30 @@ def main():
                  "%d of 148 SMs' worth of CTAs" % ((ms_ + 127) // 128)}
         es.close()
 
+    # ---- BASELINE.json configs[3] flavour: all 8 SSP scenarios interleaved in one engine ----
+    multi = None
+    if args.multi_scenario_members and rank == 0 and world == 1:
+        names = ["ssp119", "ssp126", "ssp245", "ssp370", "ssp434", "ssp460", "ssp534-over",
+                 "ssp585"]
+        mm = args.multi_scenario_members
+        em = hb.Ensemble(mm, [scenario_table(n) for n in names],
+                         member_scenario=np.arange(mm) % 8, device=local_rank,
+                         outputs=["CO2_concentration", "global_tas"], stream=stream.cuda_stream)
+        Xm = lhs(mm)
+        for j, nme in enumerate(PARAMS):
+            em.setvar(nme, np.ascontiguousarray(Xm[:, j]))
+        em.prepare()
+        em.synchronize()
+        mm_ms, _ = timed(em, lambda e: (e.reset(), e.run()), max(2, args.steps // 2), 3, False)
+        mm_ms /= max(2, args.steps // 2)
+        stm, _ = em.status()
+        multi = {"members": mm, "scenarios": 8, "value": mm * YEARS / (mm_ms * 1e-3), "unit": UNIT,
+                 "ms_per_step": mm_ms, "failed_members": int((stm != 0).sum()),
+                 "note": "BASELINE.json configs[3] flavour on one GPU: member i runs scenario "
+                         "i mod 8 (the engine groups members by scenario internally and "
+                         "un-permutes on fetch)"}
+        em.close()
+
     # ---- BASELINE.json configs[4] flavour: SSP5-8.5 to 2500 with carbon tracking on ----
     tracked = None
     if args.tracked_members and rank == 0 and world == 1:
@@ -492,7 +518,8 @@ def main():
         "work_per_member_year": {k: cnt[k] / max(1, cnt["member_years"]) for k in
                                  ("rhs_evals", "rk_steps", "stashes", "newton_iterations",
                                   "newton_calls")},
-        "failed_members": failed, "small_ensemble": small, "tracked_ensemble": tracked,
+        "failed_members": failed, "small_ensemble": small, "multi_scenario_ensemble": multi,
+        "tracked_ensemble": tracked,
         "exchange": None if world == 1 else
         ("peer memory (CUDA IPC pulls, %d run segments)" % len(exchange.segments)
          if exchange is not None else "NCCL all-gather (%d run segments)" % len(seg_rows)),
