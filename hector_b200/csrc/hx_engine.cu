@@ -861,6 +861,9 @@ int hx_prepare(hx_handle h) {
   d.constrained = any_constraint ? 1 : 0;
   for (int i = 0; i < OUT_COUNT; ++i) d.out_slot[i] = -1;
   for (int s = 0; s < nsel; ++s) d.out_slot[h->out_sel[s]] = s;
+  d.out_minimal = 1;
+  for (int s = 0; s < nsel; ++s)
+    if (h->out_sel[s] != OUT_CO2 && h->out_sel[s] != OUT_TAS) d.out_minimal = 0;
 
   h->prepared = true; /* upload_param / set_param paths need the buffers */
   for (int pi = 0; pi < PI_COUNT; ++pi) {

@@ -491,7 +491,7 @@ __device__ __forceinline__ void conv_prepass(const double *__restrict__ sst,
 /* ======================================================================================== */
 /* the yearly coupled step, rows r0+1 .. r1 (row = year - start_year).  TRACK = carbon tracking
  * compiled in (a second instantiation: the plain kernel carries none of its code). */
-template <bool TRACK, bool CONSTR, int MINCTAS>
+template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT>
 __global__ void __launch_bounds__(HX_BLOCK, MINCTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   /* dynamic shared memory (> 48 KB): scenario slabs | row 0 | chemistry constants | RK stages */
@@ -826,6 +826,8 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
   } while (0)
         EMIT(OUT_CO2, CO2_conc);
         EMIT(OUT_TAS, tas);
+        if (ALLOUT) { /* the default outputs (CO2, Tgav) have a build without the other thirty:
+                         less code in the year body is worth 5 % (36.5 -> 34.6 ms) */
         EMIT(OUT_RF_TOT, rf_tot);
         EMIT(OUT_RF_CO2, rf_co2);
         EMIT(OUT_HEATFLUX, heatflux);
@@ -856,6 +858,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_RF_N2O, rf_n2o);
         EMIT(OUT_RH_CH4, mb.S[SI_RH_CH4 * HX_TILE]);
         EMIT(OUT_TIMESTEPS, (double)mb.timesteps);
+        }
 #undef EMIT
         }
       }
@@ -1022,11 +1025,11 @@ cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cuda
   hx_spinup_kernel<<<1, HX_BLOCK, 0, st>>>(d, C, member - member % HX_BLOCK, member);
   return cudaGetLastError();
 }
-template <bool TRACK, bool CONSTR, int MINCTAS>
+template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT = true>
 static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS>,
+    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
@@ -1037,7 +1040,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT>,
                                                                   HX_BLOCK, HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
     resident = sms * (per_sm > 0 ? per_sm : 1);
@@ -1047,7 +1050,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   const int grid = ntiles < resident ? ntiles : resident;
   cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  hx_run_kernel<TRACK, CONSTR, MINCTAS><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
+  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
@@ -1066,6 +1069,9 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
   if (d.constrained)
     return small ? launch_run_t<false, true, 2>(d, C, r0, r1, st)
                  : launch_run_t<false, true, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
+  if (d.out_minimal)
+    return small ? launch_run_t<false, false, 2, false>(d, C, r0, r1, st)
+                 : launch_run_t<false, false, HX_RUN_MIN_CTAS, false>(d, C, r0, r1, st);
   return small ? launch_run_t<false, false, 2>(d, C, r0, r1, st)
                : launch_run_t<false, false, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
 }

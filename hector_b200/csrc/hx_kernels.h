@@ -37,6 +37,7 @@ struct HxDev {
   unsigned *sched;              /* [1 + Mpad / HX_BLOCK]: work-queue ticket, per-tile progress */
   int32_t out_slot[OUT_COUNT];  /* output id -> slot in `out`, -1 = not recorded */
   int32_t constrained;      /* some scenario carries a CO2 / CH4 / RF_tot / tas constraint */
+  int32_t out_minimal;      /* only CO2_concentration and/or global_tas are recorded */
   /* carbon tracking (null unless a tracking date was set) */
   double *T;                /* [tile][TS_COUNT * HX_NSRC][128] source fractions */
   uint32_t *TK;             /* [tile][TS_COUNT][128] key masks */
