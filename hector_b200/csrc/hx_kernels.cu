@@ -832,7 +832,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_RF_CO2, rf_co2);
         EMIT(OUT_HEATFLUX, heatflux);
         EMIT(OUT_OCEAN_C, mb.bDO + mb.bIO + mb.bLL + mb.bHL);
-        if (d.out_slot[OUT_HL_PH] >= 0) EMIT(OUT_HL_PH, -log10(mb.S[SI_H_HL * HX_TILE]));
+        if (d.out_slot[OUT_HL_PH] >= 0) EMIT(OUT_HL_PH, -hx_log10(mb.S[SI_H_HL * HX_TILE]));
         EMIT(OUT_ATMOS_C, mb.atmos);
         EMIT(OUT_SST, sst_new);
         EMIT(OUT_PERMAFROST_C, mb.perm);
@@ -847,7 +847,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_EARTH_C, mb.earth);
         EMIT(OUT_NBP, mb.S[SI_X_NBP * HX_TILE]);
         EMIT(OUT_OCEAN_UPTAKE, mb.S[SI_X_FLUXSUM * HX_TILE]);
-        if (d.out_slot[OUT_LL_PH] >= 0) EMIT(OUT_LL_PH, -log10(mb.S[SI_H_LL * HX_TILE]));
+        if (d.out_slot[OUT_LL_PH] >= 0) EMIT(OUT_LL_PH, -hx_log10(mb.S[SI_H_LL * HX_TILE]));
         EMIT(OUT_PCO2_HL, mb.pco2HL);
         EMIT(OUT_PCO2_LL, mb.pco2LL);
         EMIT(OUT_CARBON_HL, mb.bHL);

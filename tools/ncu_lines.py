@@ -94,3 +94,19 @@ for (f, line, _, _) in lines_by_idx:
 print("==== static SASS instruction count by function (x16 B)")
 for k, v in st.most_common(20):
     print("%-28s %6d" % (k, v))
+
+# ---- cold but bulky: source lines with many SASS instructions that almost never execute ----
+# (candidates to move out of the hot instruction stream: the year body is I-cache bound)
+per_line = collections.defaultdict(lambda: [0, 0])  # static count, executed
+for i, r in enumerate(data):
+    if i >= len(lines_by_idx):
+        break
+    k = lines_by_idx[i][:2]
+    per_line[k][0] += 1
+    per_line[k][1] += int(float(r[ci["Instructions Executed"]] or 0))
+hot = max(v[1] / max(1, v[0]) for v in per_line.values())
+print("==== cold code inside the kernel: file:line  static instrs  executions per instr / hottest")
+cold = [(k, v) for k, v in per_line.items() if v[0] >= 12 and v[1] / v[0] < 0.02 * hot]
+for k, v in sorted(cold, key=lambda kv: -kv[1][0])[:25]:
+    print("%-22s %5d  %.4f" % ("%s:%d" % k, v[0], v[1] / v[0] / hot))
+print("cold static instrs total: %d of %d" % (sum(v[0] for _, v in cold), sum(v[0] for v in per_line.values())))
