@@ -145,3 +145,33 @@ def test_tracking_csv_matches_reference_text():
         assert abs(val - rv) <= 6e-6 * max(abs(rv), 1e-30) + 1e-12, (y, pool, val, rv)
         assert abs(fr - rf) <= 6e-6 * max(abs(rf), 1e-30) + 1e-12, (y, pool, src, fr, rf)
     ens.close()
+
+
+def test_tracking_with_run_stream_and_reset_to_date():
+    """the streaming run (segments of whole slabs) and reset(date) drive the same record/replay
+    pipeline: identical maps"""
+    import hector_b200 as hb
+    tab = util.scenarios()["ssp245"]
+    outs = ["CO2_concentration", "global_tas"]
+    a = hb.Ensemble(130, tab, outputs=outs, tracking_date=1760, track_every=20)
+    b = hb.Ensemble(130, tab, outputs=outs, tracking_date=1760, track_every=20)
+    S = np.linspace(2.0, 5.0, 130)
+    for e in (a, b):
+        e.setvar("S", S)
+    a.run()
+    got = b.run_stream(outs, segments=5)
+    ref = a.fetchvars(np.arange(1746, 2301, dtype=np.float64))
+    for v in outs:
+        assert np.array_equal(got[v], ref[v].T), v
+    assert list(a.tracking_years()) == list(range(1760, 2301, 20))
+    for y in (1760, 2000, 2300):
+        fa, ka = a.fetch_tracking(y)
+        fb, kb = b.fetch_tracking(y)
+        assert np.array_equal(fa, fb) and np.array_equal(ka, kb), y
+    b.reset(1900)                     # re-derives the state of 1900, maps included
+    b.run()
+    fb, kb = b.fetch_tracking(2300)
+    fa, ka = a.fetch_tracking(2300)
+    assert np.array_equal(fa, fb) and np.array_equal(ka, kb)
+    a.close()
+    b.close()
