@@ -750,7 +750,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         }
 
         /* --- TemperatureComponent::run: temperature_component.cpp:417-557 (tstep = r > 0) --- */
-        double tas, heatflux, tland_new, sst_new;
+        double tas, heatflux, tland_new, sst_new, hf_mixed_out, hf_int_out;
         {
           const double dt = 1.0, bsi = DC_BSI, cal = DC_CAL, cas = DC_CAS, flnd = DC_FLND,
                        fso = DC_FSO;
@@ -806,6 +806,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           STATE(SI_HEAT_MIXED) = STATE(SI_HEAT_MIXED) + hf_mixed * (C.powtoheat * dt);
           STATE(SI_HEAT_INTERIOR) = STATE(SI_HEAT_INTERIOR) + hf_int * (fso * C.powtoheat * dt);
           heatflux = hf_mixed + fso * hf_int;
+          hf_mixed_out = hf_mixed; hf_int_out = hf_int;
           tland_new = TL;
           sst_new = TS;
           STATE(SI_TLAND) = TL;
@@ -857,6 +858,12 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_RF_CH4, rf_ch4);
         EMIT(OUT_RF_N2O, rf_n2o);
         EMIT(OUT_RH_CH4, mb.S[SI_RH_CH4 * HX_TILE]);
+        EMIT(OUT_NPP, mb.S[SI_X_NPP * HX_TILE]);
+        EMIT(OUT_RH, mb.S[SI_X_RH * HX_TILE]);
+        EMIT(OUT_GMST, DC_FLND * tland_new + (1.0 - DC_FLND) * sst_new);
+        EMIT(OUT_OCEAN_TAS, DC_BSI * sst_new);
+        EMIT(OUT_FLUX_MIXED, hf_mixed_out);
+        EMIT(OUT_FLUX_INTERIOR, hf_int_out);
         EMIT(OUT_TIMESTEPS, (double)mb.timesteps);
         }
 #undef EMIT

@@ -87,6 +87,7 @@ enum {
   /* per-year scratch (slowparameval results, emissions, annual sums) parked between phases */
   SI_X_CO2FERT, SI_X_TFD, SI_X_TFS, SI_X_FNEWTHAW, SI_X_NPPLUC, SI_X_FFI, SI_X_DACCS, SI_X_NBP,
   SI_X_FLUXSUM,
+  SI_X_NPP, SI_X_RH, /* final_npp / final_rh of the year's last stash (outputs NPP, RH) */
   SI_X_C_CO2, /* this year's CO2 constraint (NaN = none), read by the year's last stash */
   SI_X_C_NBP0, SI_X_C_NBP1, /* NBP constraints of year y-1 and y: round(t) picks one */
   SI_COUNT
@@ -111,7 +112,8 @@ enum {
   OUT_SST, OUT_PERMAFROST_C, OUT_CH4, OUT_N2O, OUT_O3, OUT_LAND_TAS, OUT_VEG_C, OUT_DETRITUS_C,
   OUT_SOIL_C, OUT_THAWEDP_C, OUT_EARTH_C, OUT_NBP, OUT_OCEAN_UPTAKE, OUT_LL_PH, OUT_PCO2_HL,
   OUT_PCO2_LL, OUT_CARBON_HL, OUT_CARBON_LL, OUT_CARBON_IO, OUT_CARBON_DO, OUT_RF_CH4,
-  OUT_RF_N2O, OUT_RH_CH4, OUT_TIMESTEPS,
+  OUT_RF_N2O, OUT_RH_CH4, OUT_NPP, OUT_RH, OUT_GMST, OUT_OCEAN_TAS, OUT_FLUX_MIXED,
+  OUT_FLUX_INTERIOR, OUT_TIMESTEPS,
   OUT_COUNT
 };
 

@@ -37,7 +37,8 @@ OUTPUT_VARIABLES = ["CO2_concentration", "global_tas", "RF_tot", "RF_CO2", "heat
                     "N2O_concentration", "O3_concentration", "land_tas", "veg_c", "detritus_c",
                     "soil_c", "thawedp_c", "earth_c", "NBP", "ocean_uptake", "LL_pH", "HL_PCO2",
                     "LL_PCO2", "HL_ocean_c", "LL_ocean_c", "IO_ocean_c", "DO_ocean_c", "RF_CH4",
-                    "RF_N2O", "rh_ch4", "ocean_timesteps"]
+                    "RF_N2O", "rh_ch4", "NPP", "RH", "gmst", "ocean_tas", "heatflux_mixed",
+                    "heatflux_interior", "ocean_timesteps"]
 MEMBER_STATUS = {0: "ok", 1: "negative flux/pool", 2: "mass not conserved",
                  3: "solver retries exhausted", 4: "no [H+] root", 5: "yearfraction out of bounds",
                  6: "CO2 SARF condition", 7: "ODE stepper", 8: "spin-up did not converge",
@@ -63,7 +64,9 @@ VARIABLE_UNITS = {
     "soil_c": "Pg C", "thawedp_c": "Pg C", "earth_c": "Pg C", "NBP": "Pg C/yr",
     "ocean_uptake": "Pg C/yr", "LL_pH": "pH", "HL_PCO2": "uatm", "LL_PCO2": "uatm",
     "HL_ocean_c": "Pg C", "LL_ocean_c": "Pg C", "IO_ocean_c": "Pg C", "DO_ocean_c": "Pg C",
-    "RF_CH4": "W/m2", "RF_N2O": "W/m2", "rh_ch4": "Pg C/yr", "ocean_timesteps": "(unitless)"}
+    "RF_CH4": "W/m2", "RF_N2O": "W/m2", "rh_ch4": "Pg C/yr", "ocean_timesteps": "(unitless)",
+    "NPP": "Pg C/yr", "RH": "Pg C/yr", "gmst": "degC", "ocean_tas": "degC",
+    "heatflux_mixed": "W/m2", "heatflux_interior": "W/m2"}
 VARIABLE_COMPONENT = {
     "CO2_concentration": "simpleNbox", "atmos_co2": "simpleNbox", "veg_c": "simpleNbox",
     "detritus_c": "simpleNbox", "soil_c": "simpleNbox", "permafrost_c": "simpleNbox",
@@ -73,7 +76,9 @@ VARIABLE_COMPONENT = {
     "RF_CH4": "forcing", "RF_N2O": "forcing", "ocean_c": "ocean", "ocean_uptake": "ocean",
     "HL_pH": "ocean", "LL_pH": "ocean", "HL_PCO2": "ocean", "LL_PCO2": "ocean",
     "HL_ocean_c": "ocean", "LL_ocean_c": "ocean", "IO_ocean_c": "ocean", "DO_ocean_c": "ocean",
-    "ocean_timesteps": "ocean", "CH4_concentration": "CH4", "N2O_concentration": "N2O",
+    "ocean_timesteps": "ocean", "NPP": "simpleNbox", "RH": "simpleNbox", "gmst": "temperature",
+    "ocean_tas": "temperature", "heatflux_mixed": "temperature",
+    "heatflux_interior": "temperature", "CH4_concentration": "CH4", "N2O_concentration": "N2O",
     "O3_concentration": "ozone"}
 
 

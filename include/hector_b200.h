@@ -139,7 +139,8 @@ int hx_get_param(hx_handle h, const char *name, double *per_member_out, int32_t 
  * heatflux, ocean_c, HL_pH, atmos_co2, sst, permafrost_c, CH4_concentration,
  * N2O_concentration, O3_concentration, land_tas, veg_c, detritus_c, soil_c, thawedp_c, earth_c,
  * NBP, ocean_uptake, LL_pH, HL_PCO2, LL_PCO2, HL_ocean_c, LL_ocean_c, IO_ocean_c, DO_ocean_c,
- * RF_CH4, RF_N2O, rh_ch4, ocean_timesteps).  Default: CO2_concentration, global_tas.
+ * RF_CH4, RF_N2O, rh_ch4, NPP, RH, gmst, ocean_tas, heatflux_mixed, heatflux_interior,
+ * ocean_timesteps).  Default: CO2_concentration, global_tas.
  * Must be called before hx_prepare. */
 int hx_select_outputs(hx_handle h, int32_t n, const char *const *names);
 

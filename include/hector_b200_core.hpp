@@ -160,7 +160,9 @@ inline unit_types units_of(const std::string &v) {
       {"IO_ocean_c", U_PGC}, {"DO_ocean_c", U_PGC}, {"NBP", U_PGC_YR}, {"ocean_uptake", U_PGC_YR},
       {"rh_ch4", U_PGC_YR}, {"HL_pH", U_PH}, {"LL_pH", U_PH}, {"HL_PCO2", U_UATM},
       {"LL_PCO2", U_UATM}, {"CH4_concentration", U_PPBV_CH4}, {"N2O_concentration", U_PPBV_N2O},
-      {"O3_concentration", U_DU_O3}, {"ocean_timesteps", U_UNITLESS},
+      {"O3_concentration", U_DU_O3}, {"ocean_timesteps", U_UNITLESS}, {"NPP", U_PGC_YR},
+      {"RH", U_PGC_YR}, {"gmst", U_DEGC}, {"ocean_tas", U_DEGC}, {"heatflux_mixed", U_W_M2},
+      {"heatflux_interior", U_W_M2},
       /* parameters */
       {"S", U_DEGC}, {"diff", U_CM2_S}, {"qco2", U_W_M2}, {"beta", U_UNITLESS},
       {"q10_rh", U_UNITLESS}, {"f_nppv", U_UNITLESS}, {"f_nppd", U_UNITLESS},
@@ -401,7 +403,8 @@ class EnsembleCore {
         "atmos_co2", "sst", "permafrost_c", "CH4_concentration", "N2O_concentration",
         "O3_concentration", "land_tas", "veg_c", "detritus_c", "soil_c", "thawedp_c", "earth_c",
         "NBP", "ocean_uptake", "LL_pH", "HL_PCO2", "LL_PCO2", "HL_ocean_c", "LL_ocean_c",
-        "IO_ocean_c", "DO_ocean_c", "RF_CH4", "RF_N2O", "rh_ch4", "ocean_timesteps"};
+        "IO_ocean_c", "DO_ocean_c", "RF_CH4", "RF_N2O", "rh_ch4", "NPP", "RH", "gmst",
+        "ocean_tas", "heatflux_mixed", "heatflux_interior", "ocean_timesteps"};
     chk(hx_select_outputs(h_, (int32_t)(sizeof all / sizeof all[0]), all));
     outputs_selected_ = true;
   }

@@ -88,7 +88,7 @@ typedef struct {
   double tempferts_last_year; /* tempferts_tv[t] */
   int have_tempferts_last;
   double current_luc_e, current_luc_u, current_ffi_e, current_daccs_u;
-  double RH_ch4, nbp;
+  double RH_ch4, nbp, final_npp, final_rh;
   double snbox_ODEstartdate;
   double *Tland_record; /* [nrow], index = year - start; first key is start+1 */
   int has_been_run_before;
@@ -1036,8 +1036,10 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
     double rh_fsa_adj = FP(m, snbox_rh_fsa(m) * rh_nbp_constraint_adjust);
     double rh_ftpa_co2_adj = FP(m, snbox_rh_ftpa_co2(m) * rh_nbp_constraint_adjust);
     double rh_ftpa_ch4_adj = FP(m, snbox_rh_ftpa_ch4(m) * rh_nbp_constraint_adjust);
-    /* final_rh = rh_fda_adj + rh_fsa_adj + rh_ftpa_co2_adj + rh_ftpa_ch4_adj */
-    FP(m, FP(m, FP(m, rh_fda_adj + rh_fsa_adj) + rh_ftpa_co2_adj) + rh_ftpa_ch4_adj);
+    /* final_npp = npp_biome (:429); final_rh = rh_fda_adj + rh_fsa_adj + rh_ftpa_co2_adj +
+     * rh_ftpa_ch4_adj (:446-447) */
+    m->final_npp = npp_biome;
+    m->final_rh = FP(m, FP(m, FP(m, rh_fda_adj + rh_fsa_adj) + rh_ftpa_co2_adj) + rh_ftpa_ch4_adj);
 
     double rh_fda_flux = FP(m, FP(m, rh_fda_adj) * yf);
     double rh_fsa_flux = FP(m, FP(m, rh_fsa_adj) * yf);
@@ -1947,6 +1949,12 @@ int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints
       OUT(HO_OUT_RF_CH4, rf_ch4_rel);
       OUT(HO_OUT_RF_N2O, rf_n2o_rel);
       OUT(HO_OUT_RH_CH4, m->RH_ch4);
+      OUT(HO_OUT_NPP, m->final_npp);
+      OUT(HO_OUT_RH, m->final_rh);
+      OUT(HO_OUT_GMST, dc_flnd * m->temp_landair[r] + (1.0 - dc_flnd) * m->temp_sst[r]);
+      OUT(HO_OUT_OCEAN_TAS, dc_bsi * m->temp_sst[r]);
+      OUT(HO_OUT_FLUX_MIXED, m->heatflux_mixed[r]);
+      OUT(HO_OUT_FLUX_INTERIOR, m->heatflux_interior[r]);
       OUT(HO_OUT_TIMESTEPS, (double)m->timesteps);
 #undef OUT
     }

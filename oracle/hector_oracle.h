@@ -66,6 +66,12 @@ enum {
   HO_OUT_RF_CH4,
   HO_OUT_RF_N2O,
   HO_OUT_RH_CH4,       /* end-of-year annual permafrost CH4 flux (what CH4 reads next year) */
+  HO_OUT_NPP,          /* final_npp: NPP of the year's last stash, Pg C/yr (simpleNbox.cpp:684-686) */
+  HO_OUT_RH,           /* final_rh: detritus + soil + thawed-permafrost CO2 and CH4 respiration */
+  HO_OUT_GMST,         /* gmst: flnd T_land + (1 - flnd) SST (temperature_component.cpp:506-507) */
+  HO_OUT_OCEAN_TAS,    /* ocean_tas: bsi SST (:716-717) */
+  HO_OUT_FLUX_MIXED,   /* heatflux_mixed */
+  HO_OUT_FLUX_INTERIOR,/* heatflux_interior */
   HO_OUT_TIMESTEPS,    /* ocean sub-steps (stashes) in the year */
   HO_NOUT
 };

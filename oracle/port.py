@@ -15,8 +15,8 @@ OUT_NAMES = ["CO2_concentration", "global_tas", "RF_tot", "RF_CO2", "heatflux", 
              "atmos_co2", "sst", "permafrost_c", "CH4_concentration", "N2O_concentration",
              "O3_concentration", "land_tas", "veg_c", "detritus_c", "soil_c", "thawedp_c",
              "earth_c", "NBP", "ocean_uptake", "LL_pH", "HL_PCO2", "LL_PCO2", "HL_ocean_c",
-             "LL_ocean_c", "IO_ocean_c", "DO_ocean_c", "RF_CH4", "RF_N2O", "rh_ch4",
-             "ocean_timesteps"]
+             "LL_ocean_c", "IO_ocean_c", "DO_ocean_c", "RF_CH4", "RF_N2O", "rh_ch4", "NPP", "RH",
+             "gmst", "ocean_tas", "heatflux_mixed", "heatflux_interior", "ocean_timesteps"]
 NOUT = len(OUT_NAMES)
 STATUS = {0: "OK", 1: "NEGATIVE", 2: "MASS", 3: "RETRIES", 4: "NOROOT", 5: "YEARFRACTION",
           6: "CO2SARF", 7: "STEPPER", 8: "TRACKING"}

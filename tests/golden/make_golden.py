@@ -14,6 +14,8 @@ what travels to the GPU box.
                       fractions + key masks of the 11 tracked pools at selected years (read at
                       full precision through oracle/ref_driver.cpp), and the reference's own
                       6-digit getTrackingData() CSV for one short run.
+  ref_outputs_extra.npz  NPP, RH, gmst, ocean_tas, heatflux_mixed, heatflux_interior of three runs
+                      of the UNMODIFIED reference (outputs added after ref_runs.npz was frozen).
   ref_constraints.npz known answers of the UNMODIFIED reference under user constraints (CO2, NBP,
                       tas, RF_tot, CH4, N2O, halocarbon concentrations), incl. two expected
                       failures.
@@ -333,8 +335,35 @@ def make_constraints():
                         fail_year=np.array(fails))
 
 
+EXTRA_VARS = ["NPP", "RH", "gmst", "ocean_tas", "heatflux_mixed", "heatflux_interior"]
+EXTRA_CASES = [("default_ssp245", "ssp245", {}),
+               ("pert_ssp585", "ssp585", dict(S=4.2, q10_rh=2.0, beta=0.4, diff=1.8)),
+               ("corner_lo_ssp119", "ssp119", dict(S=1.5, q10_rh=1.0, beta=0.1, diff=0.3))]
+
+
+def make_extra_outputs():
+    """ref_outputs_extra.npz: outputs added after ref_runs.npz was frozen (NPP, RH, gmst,
+    ocean_tas, heatflux_mixed, heatflux_interior), from the UNMODIFIED reference."""
+    from oracle import ref
+    names, scns, pnames, pvals, vals = [], [], [], [], []
+    for name, scn, params in EXTRA_CASES:
+        ok, err, o, _ = ref.run_member(os.path.join(REF, "inst/input/hector_%s.ini" % scn), params,
+                                       EXTRA_VARS)
+        assert ok, err
+        names.append(name); scns.append(scn); pnames.append(",".join(params))
+        pvals.append(np.array(list(params.values()) + [np.nan] * (8 - len(params))))
+        vals.append(o[:len(EXTRA_VARS)])
+        print(name, "ok")
+    np.savez_compressed(os.path.join(OUT, "ref_outputs_extra.npz"), names=np.array(names),
+                        scenarios=np.array(scns), param_names=np.array(pnames),
+                        param_values=np.array(pvals), variables=np.array(EXTRA_VARS),
+                        values=np.array(vals))
+
+
 if __name__ == "__main__":
-    if "tracking" in sys.argv[1:]:
+    if "extra" in sys.argv[1:]:
+        make_extra_outputs()
+    elif "tracking" in sys.argv[1:]:
         make_tracking()
     elif "constraints" in sys.argv[1:]:
         make_constraints()
@@ -342,3 +371,4 @@ if __name__ == "__main__":
         main()
         make_tracking()
         make_constraints()
+        make_extra_outputs()

@@ -350,3 +350,17 @@ def test_reset_to_a_date_inside_the_run():
     ens.run(1800)
     assert ens.current_date == 1800
     ens.close()
+
+
+@pytest.mark.parametrize("case", util.ref_outputs_extra(), ids=lambda c: c["name"])
+def test_extra_outputs_vs_reference_golden(case):
+    import hector_b200 as hb
+    variables = list(case["values"])
+    ens = hb.Ensemble(2, util.scenarios()[case["scenario"]], outputs=variables)
+    for k, v in case["params"].items():
+        ens.setvar(k, v)
+    ens.run()
+    got = ens.fetchvars(_years())
+    for v in variables:
+        assert util.parity_err(got[v][0], case["values"][v], v) < TOL, v
+    ens.close()

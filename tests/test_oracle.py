@@ -207,3 +207,13 @@ def test_constraints_against_reference(case):
         x = out[port.OUT_NAMES.index(v)]
         assert np.allclose(x[:n], ref[:n], rtol=1e-12, atol=1e-13), (v, np.abs(x[:n] - ref[:n]).max())
         assert np.isnan(ref[n:]).all()
+
+
+@pytest.mark.parametrize("case", util.ref_outputs_extra(), ids=lambda c: c["name"])
+def test_extra_outputs_against_reference(case):
+    """NPP, RH (final_npp / final_rh of the year's last stash), gmst, ocean_tas and the two heat
+    flux components: bit-identical to the unmodified reference"""
+    st, fy, out, cnt, sp = port.run_member(util.scenarios()[case["scenario"]], **case["params"])
+    assert st == 0
+    for v, ref in case["values"].items():
+        assert np.array_equal(out[port.OUT_NAMES.index(v)], ref), v

@@ -62,6 +62,19 @@ def ref_tracking_csv():
     return str(np.load(os.path.join(GOLDEN, "ref_tracking.npz"))["csv_1750_1755"])
 
 
+def ref_outputs_extra():
+    z = np.load(os.path.join(GOLDEN, "ref_outputs_extra.npz"))
+    variables = [str(v) for v in z["variables"]]
+    cases = []
+    for i, name in enumerate(z["names"]):
+        pn = str(z["param_names"][i])
+        keys = pn.split(",") if pn else []
+        cases.append(dict(name=str(name), scenario=str(z["scenarios"][i]),
+                          params={k: float(z["param_values"][i][j]) for j, k in enumerate(keys)},
+                          values=dict(zip(variables, z["values"][i]))))
+    return cases
+
+
 def ref_constraints():
     """constraint known answers of the unmodified reference (tests/golden/make_golden.py)"""
     z = np.load(os.path.join(GOLDEN, "ref_constraints.npz"))
@@ -82,7 +95,8 @@ def ref_constraints():
 # or are differences of large pools); CO2 / Tgav floors are SURVEY.md section 8(d)'s
 FLOOR = {"global_tas": 0.01, "CO2_concentration": 1.0, "sst": 0.01, "land_tas": 0.01,
          "heatflux": 0.1, "RF_tot": 0.01, "RF_CO2": 0.01, "RF_CH4": 0.01, "RF_N2O": 0.01,
-         "NBP": 1.0, "ocean_uptake": 1.0, "thawedp_c": 1.0, "rh_ch4": 1e-3}
+         "NBP": 1.0, "ocean_uptake": 1.0, "thawedp_c": 1.0, "rh_ch4": 1e-3, "gmst": 0.01,
+         "ocean_tas": 0.01, "heatflux_mixed": 0.1, "heatflux_interior": 0.1}
 
 
 def parity_err(x, ref, var):
