@@ -1067,8 +1067,8 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
    * 230-register build wins (17.0 vs 20.5 ms at 1 024 members).  The tracking build is bound by
    * its map traffic, not by occupancy, and spills badly at 168 registers. */
   if (d.T)
-    return d.constrained ? launch_run_t<true, true, 2>(d, C, r0, r1, st)
-                         : launch_run_t<true, false, 2>(d, C, r0, r1, st);
+    return d.constrained ? launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st)
+                         : launch_run_t<true, false, HX_TRACK_CTAS>(d, C, r0, r1, st);
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -11,6 +11,9 @@
 #ifndef HX_CONV_UNROLL
 #define HX_CONV_UNROLL 8 /* history rows per trip of the slab prepass of the DOECLIM convolution */
 #endif
+#ifndef HX_TRACK_CTAS
+#define HX_TRACK_CTAS 2 /* resident CTAs per SM of the record-only (tracking) run kernel */
+#endif
 #ifndef HX_YEAR_SYNC
 #define HX_YEAR_SYNC 1 /* one CTA barrier per simulated year: the warps share instruction fetches */
 #endif
