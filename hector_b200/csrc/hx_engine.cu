@@ -239,7 +239,9 @@ struct Engine {
    *   dN2O = (E + E_nat)/UC_N2O - N2O/tau
    * HalocarbonComponent::run (halocarbon_component.cpp:181-229): exponential decay + emissions,
    *   RF = rho Ha (1 + delta) */
-  void gas_series(int s, std::vector<double> &n2o, std::vector<double> &halo_rf) const {
+  void gas_series(int s, std::vector<double> &n2o, std::vector<double> &halo_rf,
+                  std::vector<double> *halo_conc = nullptr) const {
+    if (halo_conc) halo_conc->assign((size_t)nrow * HX_NHALO, 0.0);
     const double *R = raw[s].data();
     auto rawv = [&](int series, int r) { return R[(size_t)series * nrow + r]; };
     double N0 = pscalar[PI_N0];
@@ -271,11 +273,23 @@ struct Engine {
         const double expfac = std::exp(-alpha);
         Ha = Ha * expfac + concDeltaEmiss * tau * (1.0 - expfac);
         if (cha[r] == cha[r]) Ha = cha[r]; /* halocarbon_component.cpp:189-192 */
+        if (halo_conc) (*halo_conc)[(size_t)r * HX_NHALO + g] = Ha;
         const double rf_unadjusted = halo_rho[g] * Ha;
         halo_rf[(size_t)r * HX_NHALO + g] = rf_unadjusted + halo_delta[g] * rf_unadjusted;
       }
     }
   }
+
+  /* Outputs that need no kernel: the forcing of every agent other than CO2 / CH4 / N2O, the
+   * halocarbon concentrations and forcings.  They are functions of the scenario series, of
+   * per-member parameters and (two of them) of recorded outputs, evaluated at fetch time with the
+   * expressions of ForcingComponent::run (forcing_component.cpp:410-489), relative to the base
+   * year like every forcing the reference reports (:507-524); before the base year they are 0.
+   *   RF_BC RF_OC RF_SO2 RF_NH3 RF_aci RF_vol RF_albedo RF_misc RF_O3_trop RF_H2O_strat
+   *   RF_<gas> (absolute, as the halocarbon component reports it), Fadj<gas> (relative),
+   *   <gas>_concentration
+   * Returns 1 if `name` is one of them (rc holds the result code), 0 otherwise. */
+  int fetch_derived(const char *name, const double *dates, int n_dates, double *out, int &rc);
 
   void free_device() {
     void *ptrs[] = {d_P, d_S, d_S_snap, d_D, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
@@ -441,6 +455,120 @@ struct Engine {
 } // namespace
 
 struct hx_engine : Engine {};
+
+int Engine::fetch_derived(const char *name, const double *dates, int n_dates, double *out, int &rc) {
+  const std::string nm(name);
+  enum Kind { K_NONE, K_BC, K_OC, K_SO2, K_NH3, K_ACI, K_VOL, K_ALBEDO, K_MISC, K_O3, K_H2O,
+              K_HALO_RF, K_HALO_ADJ, K_HALO_CONC };
+  Kind kind = K_NONE;
+  int gas = -1;
+  static const struct { const char *n; Kind k; } simple[] = {
+      {"RF_BC", K_BC}, {"RF_OC", K_OC}, {"RF_SO2", K_SO2}, {"RF_NH3", K_NH3}, {"RF_aci", K_ACI},
+      {"RF_vol", K_VOL}, {"RF_albedo", K_ALBEDO}, {"RF_misc", K_MISC}, {"RF_O3_trop", K_O3},
+      {"RF_H2O_strat", K_H2O}};
+  for (const auto &e : simple)
+    if (nm == e.n) kind = e.k;
+  for (int g = 0; g < HX_NHALO && kind == K_NONE; ++g) {
+    const std::string gname(hx::kHaloNames[g]);
+    if (nm == "RF_" + gname) { kind = K_HALO_RF; gas = g; }
+    else if (nm == "Fadj" + gname) { kind = K_HALO_ADJ; gas = g; }
+    else if (nm == gname + "_concentration") { kind = K_HALO_CONC; gas = g; }
+  }
+  if (kind == K_NONE) return 0;
+  rc = HX_OK;
+  const int base = C.baseyear - cfg.start_year; /* base-year row */
+  std::vector<int> rows(n_dates);
+  for (int k = 0; k < n_dates; ++k) {
+    rows[k] = (int)dates[k] - cfg.start_year;
+    if (rows[k] < 1 || rows[k] > cur_row) {
+      rc = fail(HX_ERR_ARG, "date outside (start_year, current date]");
+      return 1;
+    }
+  }
+  /* per-member parameters and statuses */
+  auto param = [&](int pi, std::vector<double> &v) {
+    v.resize(M);
+    return hx_get_param(static_cast<hx_engine *>(this), hx::kParams[pi].name, v.data(), M);
+  };
+  std::vector<int32_t> st(M), fy(M);
+  rc = hx_member_status(static_cast<hx_engine *>(this), st.data(), fy.data(), M);
+  if (rc) return 1;
+  /* recorded outputs some agents are functions of (at the requested dates and the base year) */
+  std::vector<double> rec, rec_base;
+  auto need_output = [&](const char *var) {
+    std::vector<double> d2(dates, dates + n_dates);
+    rec.resize((size_t)M * n_dates);
+    rec_base.assign(M, 0.0);
+    int r2 = hx_fetch(static_cast<hx_engine *>(this), var, d2.data(), n_dates, rec.data());
+    if (r2 == HX_OK && base >= 1 && base <= cur_row) {
+      const double by = C.baseyear;
+      r2 = hx_fetch(static_cast<hx_engine *>(this), var, &by, 1, rec_base.data());
+    }
+    return r2;
+  };
+  std::vector<double> aero, vol, rho, M0v;
+  if (kind == K_BC || kind == K_OC || kind == K_SO2 || kind == K_NH3 || kind == K_ACI) {
+    if ((rc = param(PI_AERO, aero))) return 1;
+    const int pi = kind == K_BC ? PI_RHO_BC : kind == K_OC ? PI_RHO_OC : kind == K_SO2 ? PI_RHO_SO2 : PI_RHO_NH3;
+    if (kind != K_ACI && (rc = param(pi, rho))) return 1;
+  }
+  if (kind == K_VOL && (rc = param(PI_VOL, vol))) return 1;
+  if (kind == K_O3 && (rc = need_output("O3_concentration"))) return 1;
+  if (kind == K_H2O) {
+    if ((rc = need_output("CH4_concentration")) || (rc = param(PI_M0, M0v))) return 1;
+  }
+  /* per-scenario series */
+  std::vector<std::vector<double>> hrf(nscen), hconc(nscen);
+  if (kind == K_HALO_RF || kind == K_HALO_ADJ || kind == K_HALO_CONC) {
+    std::vector<double> n2o;
+    for (int s = 0; s < nscen; ++s) gas_series(s, n2o, hrf[s], &hconc[s]);
+  }
+  const double aci_beta = 2.279759, s_BCOC = 111.05064063,
+               s_SO2 = (260.34644166 * 1000) * (32.065 / 64.066);
+  const double nan = std::nan("");
+  for (int i = 0; i < M; ++i) {
+    const int s = member_scen[i];
+    const double *R = raw[s].data();
+    auto rawv = [&](int series, int r) { return R[(size_t)series * nrow + r]; };
+    /* absolute forcing of the agent in row r */
+    auto absolute = [&](int r, int k) -> double {
+      switch (kind) {
+        case K_BC: return aero[i] * rho[i] * rawv(RAW_BC, r);
+        case K_OC: return aero[i] * rho[i] * rawv(RAW_OC, r);
+        case K_SO2: return aero[i] * rho[i] * rawv(RAW_SO2, r);
+        case K_NH3: return aero[i] * rho[i] * rawv(RAW_NH3, r);
+        case K_ACI:
+          return aero[i] * (-1 * aci_beta *
+                            std::log(1 + (rawv(RAW_SO2, r) / s_SO2) +
+                                     ((rawv(RAW_BC, r) + rawv(RAW_OC, r)) / s_BCOC)));
+        case K_VOL: return vol[i] * rawv(RAW_SV, r);
+        case K_ALBEDO: return rawv(RAW_ALBEDO, r);
+        case K_MISC: return rawv(RAW_MISC, r);
+        case K_O3: return 0.042 * (k < 0 ? rec_base[i] : rec[(size_t)i * n_dates + k]);
+        case K_H2O: {
+          const double c0 = con(s, CN_CH4)[0];
+          const double M0 = (c0 == c0) ? c0 : M0v[i]; /* ch4_component.cpp:141-146 */
+          const double Ma = k < 0 ? rec_base[i] : rec[(size_t)i * n_dates + k];
+          return 0.0485 * ((Ma - M0) / (1831 - M0));
+        }
+        case K_HALO_RF: case K_HALO_ADJ: return hrf[s][(size_t)r * HX_NHALO + gas];
+        case K_HALO_CONC: return hconc[s][(size_t)r * HX_NHALO + gas];
+        default: return nan;
+      }
+    };
+    const bool relative = !(kind == K_HALO_RF || kind == K_HALO_CONC);
+    for (int k = 0; k < n_dates; ++k) {
+      const int r = rows[k];
+      double v;
+      if (st[i] > 0 && fy[i] <= cfg.start_year + r) v = nan; /* the member stopped before */
+      else if (!relative) v = absolute(r, k);
+      else if (r < base) v = 0.0; /* forcings are reported from the base year on */
+      else v = absolute(r, k) - absolute(base, -1);
+      out[(size_t)i * n_dates + k] = v;
+    }
+  }
+  return 1;
+}
 
 using hx::kParams;
 
@@ -1144,6 +1272,10 @@ double hx_current_date(hx_handle h) { return h ? h->cfg.start_year + h->cur_row 
 int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates, double *out) {
   if (!h || !name || !dates || !out || n_dates <= 0) return HX_ERR_ARG;
   if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_fetch before hx_prepare");
+  {
+    int rc = HX_OK;
+    if (h->fetch_derived(name, dates, n_dates, out, rc)) return rc;
+  }
   const int id = Engine::find_out(name);
   if (id < 0) return h->fail(HX_ERR_ARG, std::string("unknown output variable: ") + name);
   const int slot = h->d.out_slot[id];

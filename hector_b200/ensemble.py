@@ -82,6 +82,25 @@ VARIABLE_COMPONENT = {
     "O3_concentration": "ozone"}
 
 
+# Outputs that need no kernel: hx_fetch derives them from the scenario series, per-member
+# parameters and recorded outputs (RF_O3_trop needs O3_concentration, RF_H2O_strat needs
+# CH4_concentration among the selected outputs)
+DERIVED_VARIABLES = (["RF_BC", "RF_OC", "RF_SO2", "RF_NH3", "RF_aci", "RF_vol", "RF_albedo",
+                      "RF_misc", "RF_O3_trop", "RF_H2O_strat"]
+                     + ["RF_%s" % h for h in HALOS] + ["Fadj%s" % h for h in HALOS]
+                     + ["%s_concentration" % h for h in HALOS])
+
+
+def variable_units(v):
+    if v in VARIABLE_UNITS:
+        return VARIABLE_UNITS[v]
+    if v.startswith("RF_") or v.startswith("Fadj"):
+        return "W/m2"
+    if v.endswith("_concentration"):
+        return "pptv"
+    return "(unitless)"
+
+
 def load_scenario_tables(path):
     """{scenario: table[nrow, len(RAW_SERIES)]} from an .npz written by
     tests/golden/make_golden.py (columns in RAW_SERIES order)."""
@@ -299,7 +318,7 @@ class Ensemble:
             frames.append(pd.DataFrame({
                 "scenario": scenario, "member": np.repeat(members, dates.size),
                 "year": np.tile(dates.astype(int), members.size), "variable": v,
-                "value": x.reshape(-1), "units": VARIABLE_UNITS.get(v, "(unitless)")}))
+                "value": x.reshape(-1), "units": variable_units(v)}))
         return pd.concat(frames, ignore_index=True)
 
     def write_outputstream(self, path, member=0, run_name="hector_b200", dates=None,

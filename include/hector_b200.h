@@ -166,7 +166,13 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
                   double *const *outs, int32_t segments);
 
 /* out[member][date] (row-major, n_members x n_dates) on the host; dates before/at
- * start_year or beyond the current date are an error, as in the reference */
+ * start_year or beyond the current date are an error, as in the reference.
+ * Besides the recorded variables, hx_fetch answers for the outputs that need no kernel -- it
+ * derives them from the scenario series, per-member parameters and recorded outputs with
+ * ForcingComponent::run's expressions (forcing_component.cpp:410-524): RF_BC, RF_OC, RF_SO2,
+ * RF_NH3, RF_aci, RF_vol, RF_albedo, RF_misc, RF_O3_trop (needs O3_concentration recorded),
+ * RF_H2O_strat (needs CH4_concentration recorded), and per halocarbon RF_<gas> (absolute),
+ * Fadj<gas> (relative to the base year) and <gas>_concentration. */
 int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates, double *out);
 /* device-resident view: pointer to the [year][member_stride] block of `name` (year index 0 =
  * start_year+1); valid until hx_destroy.  For NCCL gathers / zero-copy consumers. */

@@ -185,6 +185,11 @@ inline unit_types units_of(const std::string &v) {
   const std::string suffix = "_constrain"; /* <gas>_constrain: halocarbon concentrations */
   if (v.size() > suffix.size() && v.compare(v.size() - suffix.size(), suffix.size(), suffix) == 0)
     return U_PPTV;
+  /* outputs derived at fetch time: per-agent forcings, halocarbon forcings and concentrations */
+  if (v.compare(0, 3, "RF_") == 0 || v.compare(0, 4, "Fadj") == 0) return U_W_M2;
+  const std::string csuffix = "_concentration";
+  if (v.size() > csuffix.size() && v.compare(v.size() - csuffix.size(), csuffix.size(), csuffix) == 0)
+    return U_PPTV;
   return U_UNDEFINED;
 }
 inline const char *member_failure(int status) { /* the reference's exception text */

@@ -335,9 +335,14 @@ def make_constraints():
                         fail_year=np.array(fails))
 
 
-EXTRA_VARS = ["NPP", "RH", "gmst", "ocean_tas", "heatflux_mixed", "heatflux_interior"]
+EXTRA_VARS = ["NPP", "RH", "gmst", "ocean_tas", "heatflux_mixed", "heatflux_interior",
+              # forcing agents and halocarbons the engine derives at fetch time
+              "RF_BC", "RF_OC", "RF_SO2", "RF_NH3", "RF_aci", "RF_vol", "RF_albedo", "RF_misc",
+              "RF_O3_trop", "RF_H2O_strat", "RF_CF4", "FadjCF4", "RF_CFC11", "FadjCFC11",
+              "RF_CH3Br", "FadjHFC134a", "CF4_concentration", "CFC12_concentration"]
 EXTRA_CASES = [("default_ssp245", "ssp245", {}),
                ("pert_ssp585", "ssp585", dict(S=4.2, q10_rh=2.0, beta=0.4, diff=1.8)),
+               ("aero_vol_ssp370", "ssp370", dict(aero_scalar=1.4, vol_scalar=0.85, S=3.7)),
                ("corner_lo_ssp119", "ssp119", dict(S=1.5, q10_rh=1.0, beta=0.1, diff=0.3))]
 
 

@@ -356,11 +356,25 @@ def test_reset_to_a_date_inside_the_run():
 def test_extra_outputs_vs_reference_golden(case):
     import hector_b200 as hb
     variables = list(case["values"])
-    ens = hb.Ensemble(2, util.scenarios()[case["scenario"]], outputs=variables)
+    recorded = [v for v in variables if v in hb.OUTPUT_VARIABLES]
+    derived = [v for v in variables if v in hb.DERIVED_VARIABLES]
+    assert len(recorded) + len(derived) == len(variables)
+    ens = hb.Ensemble(2, util.scenarios()[case["scenario"]],
+                      outputs=recorded + ["O3_concentration", "CH4_concentration"])
     for k, v in case["params"].items():
         ens.setvar(k, v)
     ens.run()
-    got = ens.fetchvars(_years())
+    got = ens.fetchvars(_years(), variables)
     for v in variables:
-        assert util.parity_err(got[v][0], case["values"][v], v) < TOL, v
+        floor = 1e-3 if v in derived and not v.endswith("_concentration") else util.FLOOR.get(v, 1e-3)
+        err = float(np.max(np.abs(got[v][0] - case["values"][v]) /
+                           np.maximum(np.abs(case["values"][v]), floor)))
+        assert err < TOL, (v, err)
+    # derived outputs are refused when the output they are a function of was not recorded
+    bare = hb.Ensemble(1, util.scenarios()[case["scenario"]])
+    bare.run(1760)
+    assert bare.fetch("RF_BC", [1755.0]).shape == (1, 1)
+    with pytest.raises(hb.HxError):
+        bare.fetch("RF_O3_trop", [1755.0])
+    bare.close()
     ens.close()
