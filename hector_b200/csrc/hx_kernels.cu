@@ -79,8 +79,6 @@ __device__ __forceinline__ void fence_proxy_async() {
 struct Bases {
   const double *P;
   double *S, *D, *ker, *sst, *tland, *conv;
-  double *T;     /* carbon-tracking maps (null when tracking is off) */
-  uint32_t *TK;
 };
 __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, int m) {
   const size_t tile = (size_t)(m / HX_BLOCK), ln = (size_t)(m % HX_BLOCK);
@@ -92,8 +90,6 @@ __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, in
   b.conv = d.conv + tile * (size_t)HX_SLAB_YEARS * HX_BLOCK + ln;
   b.sst = d.sst_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
   b.tland = d.tland_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
-  b.T = d.T ? d.T + tile * (size_t)(TS_COUNT * HX_NSRC) * HX_BLOCK + ln : nullptr;
-  b.TK = d.TK ? d.TK + tile * (size_t)TS_COUNT * HX_BLOCK + ln : nullptr;
   return b;
 }
 #define PAR(i) __ldg(BS.P + (i) * HX_BLOCK)

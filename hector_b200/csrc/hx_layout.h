@@ -125,13 +125,13 @@ enum {
  * (+ source "untracked").  Per member the maps live in a CTA-tiled array
  * T[tile][TS_COUNT * HX_NSRC][128] (+ masks K[tile][TS_COUNT][128]): the 11 pools, the ocean's
  * year-start copy of the atmosphere (ocean_component.hpp:78,106), the stash-start copies
- * that fluxes made by flux_from_fluxpool() carry, and the four CarbonAdditions maps. */
+ * that fluxes made by flux_from_fluxpool() carry (scratch), and the four CarbonAdditions maps. */
 #define HX_NPOOL 11
 #define HX_NSRC 12
 enum {
   TS_ATMOS = 0, TS_EARTH, TS_VEG, TS_DET, TS_SOIL, TS_PERM, TS_THAWED, TS_HL, TS_LL, TS_IO, TS_DO,
   TS_ATM_CPOOL,
-  TS_ATM0, TS_EARTH0, TS_DET0, TS_SOIL0, TS_PERM0, TS_OA,
+  TS_ATM0, TS_PERM0, TS_OA, /* scratch of one stash: live in the replay kernel's registers only */
   TS_ADD_HL, TS_ADD_LL, TS_ADD_IO, TS_ADD_DO,
   TS_COUNT
 };
