@@ -113,6 +113,7 @@ struct Engine {
   /* user constraints, [scen][CN_COUNT * nrow] series-major, NaN = no entry for that year */
   std::vector<std::vector<double>> cons;
   bool tables_dirty = false;                 /* a series changed after hx_prepare */
+  bool tables_constrained = false;           /* some scenario carries a CO2/NBP/CH4/RF_tot/tas constraint */
   std::vector<int32_t> member_scen;          /* API order */
   double pscalar[PI_COUNT];
   std::vector<double> pvec[PI_COUNT];        /* per-member overrides (API order), host copy */
@@ -358,7 +359,7 @@ struct Engine {
     build_tables(tab, any);
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaMemcpy(d_scen, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
-    d.constrained = any ? 1 : 0;
+    tables_constrained = any;
     tables_dirty = false;
     return HX_OK;
   }
@@ -427,6 +428,10 @@ struct Engine {
       int rc = upload_tables();
       if (rc) return rc;
     }
+    /* a land-ocean warming ratio is served by the constraint builds of the run kernel */
+    bool lo_active = pscalar[PI_LO_RATIO] != 0.0 || pvec_on_device_only[PI_LO_RATIO];
+    for (double v : pvec[PI_LO_RATIO]) lo_active = lo_active || v != 0.0;
+    d.constrained = (tables_constrained || lo_active) ? 1 : 0;
     CUDA_TRY(cudaMemcpyAsync(d_status, d_status_snap, (size_t)Mpad * sizeof(int32_t),
                              cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(hx::launch_setup(d, C, stream));
@@ -986,7 +991,8 @@ int hx_prepare(hx_handle h) {
   d.T = h->d_T; d.TK = h->d_TK; d.TO = h->d_TO; d.TOK = h->d_TOK; d.REC = h->d_REC; d.YCNT = h->d_YCNT;
   h->rec_elems = block_scen.size() * hx::track_record_bytes_per_cta() / sizeof(double);
   h->ycnt_bytes = block_scen.size() * hx::track_ycnt_bytes_per_tile();
-  d.constrained = any_constraint ? 1 : 0;
+  h->tables_constrained = any_constraint;
+  d.constrained = any_constraint ? 1 : 0; /* refined in run_setup_and_spinup */
   for (int i = 0; i < OUT_COUNT; ++i) d.out_slot[i] = -1;
   for (int s = 0; s < nsel; ++s) d.out_slot[h->out_sel[s]] = s;
   d.out_minimal = 1;

@@ -13,7 +13,7 @@
  *     only one, else linear interpolation with flat extrapolation
  *                        (inst/include/tseries.hpp:317-334, src/h_interpolator.cpp:109-125);
  *     ffi/daccs/luc series do not extrapolate (src/simpleNbox.cpp:49-56) and must cover the run.
- * Constraint inputs, biomes and spinup_chem=1 are reported as unsupported rather than ignored.
+ * Biomes and spinup_chem=1 are reported as unsupported rather than ignored.
  */
 #include <sys/stat.h>
 
@@ -343,7 +343,7 @@ bool read_ini(const std::string &path, IniInputs &out) {
       out.scalars[pname] = v;
       continue;
     }
-    if (name.find("constrain") != std::string::npos || name == "lo_warming_ratio") {
+    if (name.find("constrain") != std::string::npos) {
       out.error = "[" + section + "] " + name + ": not supported by the ensemble engine";
       out.unsupported = true;
       return false;

@@ -273,6 +273,7 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   STATE(SI_BASE_TOT) = 0.0; STATE(SI_BASE_CO2) = 0.0; STATE(SI_BASE_CH4) = 0.0;
   STATE(SI_BASE_N2O) = 0.0;
   STATE(SI_TLAND_WSUM) = 0.0; STATE(SI_TLAND_WCOMP) = 0.0; STATE(SI_DPAST_RAW) = 0.0;
+  STATE(SI_TLAND_C) = 0.0; STATE(SI_SST_C) = 0.0;
   BS.sst[0] = 0.0;   /* row 0: temp_sst[0] = 0 */
   BS.tland[0] = 0.0;
   d.fail_year[m] = 0;
@@ -630,7 +631,9 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         mb.S[SI_X_FLUXSUM * HX_TILE] = 0.0;
         mb.timesteps = 0;
         {
-          const double sst = STATE(SI_SST);
+          /* getData(sst): DOECLIM's, or the lo_warming_ratio one (temperature_component.cpp:
+           * 612-622) */
+          const double sst = CONSTR ? STATE(SI_SST_C) : STATE(SI_SST);
           const ChemG g = chem_constants2(C, sst, ck.base + ck.tid, ck.stride);
           mb.gHL = g.gHL; mb.gLL = g.gLL;
           const Csys2Out o = csys_solve2(ck.base + ck.tid, ck.stride, C.bor, mb.bHL, mb.bLL,
@@ -644,7 +647,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 
         /* --- SimpleNbox::run + slowparameval: simpleNbox-runtime.cpp:206-227, 945-1072 --- */
         {
-          const double tland = STATE(SI_TLAND);
+          const double tland = CONSTR ? STATE(SI_TLAND_C) : STATE(SI_TLAND); /* getData(land_tas) */
           const double wf = LP_WF(p);
           BS.tland[(size_t)r * Hs] = tland; /* Tland_record[y] = land tas of year y-1 */
           if (TRACK) {
@@ -746,7 +749,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         }
 
         /* --- TemperatureComponent::run: temperature_component.cpp:417-557 (tstep = r > 0) --- */
-        double tas, heatflux, tland_new, sst_new, hf_mixed_out, hf_int_out;
+        double tas, heatflux, tland_new, sst_new, hf_mixed_out, hf_int_out, ocean_tas_out, gmst_out;
         {
           const double dt = 1.0, bsi = DC_BSI, cal = DC_CAL, cas = DC_CAS, flnd = DC_FLND,
                        fso = DC_FSO;
@@ -809,6 +812,22 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           STATE(SI_SST) = TS;
           STATE(SI_RF_PREV) = rf_tot;
           BS.sst[(size_t)r * Hs] = TS;
+          ocean_tas_out = bsi * TS;
+          gmst_out = DC_FLND * TL + (1.0 - DC_FLND) * TS; /* always DOECLIM's own (:741-742) */
+          if (CONSTR) {
+            /* user-provided land-ocean warming ratio (:722-739): the land, ocean-air and sea-
+             * surface temperatures other components and callers see are re-derived from the
+             * global mean; DOECLIM's own state (above) is untouched */
+            const double lo = PAR(PI_LO_RATIO);
+            if (lo != 0.0) {
+              const double oa = tas / ((lo * flnd) + (1 - flnd));
+              tland_new = oa * lo;
+              sst_new = oa / bsi;
+              ocean_tas_out = oa;
+            }
+            STATE(SI_TLAND_C) = tland_new;
+            STATE(SI_SST_C) = sst_new;
+          }
         }
         ++years_done;
 
@@ -856,8 +875,8 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_RH_CH4, mb.S[SI_RH_CH4 * HX_TILE]);
         EMIT(OUT_NPP, mb.S[SI_X_NPP * HX_TILE]);
         EMIT(OUT_RH, mb.S[SI_X_RH * HX_TILE]);
-        EMIT(OUT_GMST, DC_FLND * tland_new + (1.0 - DC_FLND) * sst_new);
-        EMIT(OUT_OCEAN_TAS, DC_BSI * sst_new);
+        EMIT(OUT_GMST, gmst_out);
+        EMIT(OUT_OCEAN_TAS, ocean_tas_out);
         EMIT(OUT_FLUX_MIXED, hf_mixed_out);
         EMIT(OUT_FLUX_INTERIOR, hf_int_out);
         EMIT(OUT_TIMESTEPS, (double)mb.timesteps);

@@ -69,6 +69,7 @@ enum {
   PI_RHO_BC, PI_RHO_OC, PI_RHO_SO2, PI_RHO_NH3,
   PI_M0, PI_TSOIL, PI_TSTRAT, PI_UC_CH4, PI_TOH0, PI_CNOX, PI_CCO, PI_CNMVOC, PI_CCH4, PI_PO3,
   PI_N0,
+  PI_LO_RATIO, /* [temperature] lo_warming_ratio, 0 = off */
   PI_COUNT
 };
 
@@ -87,6 +88,8 @@ enum {
   /* per-year scratch (slowparameval results, emissions, annual sums) parked between phases */
   SI_X_CO2FERT, SI_X_TFD, SI_X_TFS, SI_X_FNEWTHAW, SI_X_NPPLUC, SI_X_FFI, SI_X_DACCS, SI_X_NBP,
   SI_X_FLUXSUM,
+  SI_TLAND_C, SI_SST_C, /* land / sea-surface temperature as the carbon cycle sees them: DOECLIM's
+                           own, or re-derived from tas with lo_warming_ratio (constraint builds) */
   SI_X_NPP, SI_X_RH, /* final_npp / final_rh of the year's last stash (outputs NPP, RH) */
   SI_X_C_CO2, /* this year's CO2 constraint (NaN = none), read by the year's last stash */
   SI_X_C_NBP0, SI_X_C_NBP1, /* NBP constraints of year y-1 and y: round(t) picks one */

@@ -41,7 +41,8 @@ static const ParamInfo kParams[PI_COUNT] = {
     {"M0", 731.41}, {"Tsoil", 120}, {"Tstrat", 150}, {"UC_CH4", 2.78},
     {"TOH0", 9.6}, {"CNOX", 8.4e-3}, {"CCO", -1.575e-4}, {"CNMVOC", -4.725e-4}, {"CCH4", -0.32},
     {"PO3", 30.0},
-    {"N0", 273.87}};
+    {"N0", 273.87},
+    {"lo_warming_ratio", 0.0}};
 
 /* parameters that influence the spin-up / alkalinity equilibration; if all of them are
  * scalars the spin-up is computed once and broadcast */

@@ -31,7 +31,7 @@ PARAMETERS = ["S", "diff", "qco2", "beta", "q10_rh", "f_nppv", "f_nppd", "f_litt
               "preind_surface_c", "preind_interdeep_c", "eps_abs", "eps_rel", "dt", "eps_spinup",
               "aero_scalar", "vol_scalar", "delta_co2", "delta_ch4", "delta_n2o", "rho_bc",
               "rho_oc", "rho_so2", "rho_nh3", "M0", "Tsoil", "Tstrat", "UC_CH4", "TOH0", "CNOX",
-              "CCO", "CNMVOC", "CCH4", "PO3", "N0"]
+              "CCO", "CNMVOC", "CCH4", "PO3", "N0", "lo_warming_ratio"]
 OUTPUT_VARIABLES = ["CO2_concentration", "global_tas", "RF_tot", "RF_CO2", "heatflux", "ocean_c",
                     "HL_pH", "atmos_co2", "sst", "permafrost_c", "CH4_concentration",
                     "N2O_concentration", "O3_concentration", "land_tas", "veg_c", "detritus_c",

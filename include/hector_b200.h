@@ -126,8 +126,8 @@ int hx_set_member_scenario(hx_handle h, const int32_t *scenario_of_member, int32
  * npp_flux0, C0, veg_c, detritus_c, soil_c, permafrost_c, warmingfactor, rh_ch4_frac, pf_mu,
  * pf_sigma, fpf_static, tt, tu, twi, tid, preind_surface_c, preind_interdeep_c, eps_abs,
  * eps_rel, dt, eps_spinup, aero_scalar, vol_scalar, delta_co2, delta_ch4, delta_n2o, rho_bc,
- * rho_oc, rho_so2, rho_nh3, M0, Tsoil, Tstrat, UC_CH4, TOH0, CNOX, CCO, CNMVOC, CCH4, PO3, N0
- * per member or scalar; baseyear, max_spinup, UC_N2O, TN2O0 and the halocarbon
+ * rho_oc, rho_so2, rho_nh3, M0, Tsoil, Tstrat, UC_CH4, TOH0, CNOX, CCO, CNMVOC, CCH4, PO3, N0,
+ * lo_warming_ratio per member or scalar; baseyear, max_spinup, UC_N2O, TN2O0 and the halocarbon
  * tau/rho/delta/H0/molarMass (<gas>.tau ...) scalar only).  Defaults = inst/input/hector_ssp245.ini. */
 int hx_set_param_scalar(hx_handle h, const char *name, double value);
 int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_t n);

@@ -175,7 +175,7 @@ inline unit_types units_of(const std::string &v) {
       {"rho_oc", U_W_M2_TG}, {"rho_so2", U_W_M2_GG}, {"rho_nh3", U_W_M2_TG}, {"M0", U_PPBV_CH4},
       {"N0", U_PPBV_N2O}, {"Tsoil", U_YRS}, {"Tstrat", U_YRS}, {"TOH0", U_YRS},
       {"UC_CH4", U_TG_PPBV}, {"CNOX", U_UNITLESS}, {"CCO", U_UNITLESS}, {"CNMVOC", U_UNITLESS},
-      {"CCH4", U_UNITLESS},
+      {"CCH4", U_UNITLESS}, {"lo_warming_ratio", U_UNITLESS},
       /* user constraints (component_data.hpp:46, 263, 273, 379-381) and [core] trackingDate */
       {"CO2_constrain", U_PPMV_CO2}, {"tas_constrain", U_DEGC}, {"RF_tot_constrain", U_W_M2},
       {"CH4_constrain", U_PPBV_CH4}, {"N2O_constrain", U_PPBV_N2O}, {"NBP_constrain", U_PGC_YR},

@@ -129,7 +129,7 @@ typedef struct {
       *heat_interior, *forcing;
   double A[4], B[4], Cc[4], IB[4];
   double taucfl, taukls, taucfs, tauksl, taudif, powtoheat;
-  double tas, tas_land, sst, heatflux;
+  double tas, tas_land, sst, heatflux, tas_ocean;
 } member_t;
 
 static void fail_member(member_t *m, int code) {
@@ -1559,6 +1559,18 @@ static void doeclim_run(member_t *m, int tstep, double rf_tot) {
   m->tas = m->temp[tstep];
   m->tas_land = temp_landair[tstep];
   m->sst = temp_sst[tstep];
+  m->tas_ocean = bsi * temp_sst[tstep];
+  /* user-provided land-ocean warming ratio (:722-739): what getData(land_tas / ocean_tas / sst)
+   * hands to the other components and to callers (:586-622); DOECLIM's own arrays stay */
+  if (m->p->lo_warming_ratio != 0) {
+    const double r = m->p->lo_warming_ratio;
+    const double temp_oceanair_constrain = m->temp[tstep] / ((r * flnd) + (1 - flnd));
+    const double temp_landair_constrain = temp_oceanair_constrain * r;
+    const double temp_sst_constrain = temp_oceanair_constrain / bsi;
+    m->tas_land = temp_landair_constrain;
+    m->sst = temp_sst_constrain;
+    m->tas_ocean = temp_oceanair_constrain;
+  }
 }
 
 /* ---------------------------------------------------------------------------------- */
@@ -1952,7 +1964,7 @@ int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints
       OUT(HO_OUT_NPP, m->final_npp);
       OUT(HO_OUT_RH, m->final_rh);
       OUT(HO_OUT_GMST, dc_flnd * m->temp_landair[r] + (1.0 - dc_flnd) * m->temp_sst[r]);
-      OUT(HO_OUT_OCEAN_TAS, dc_bsi * m->temp_sst[r]);
+      OUT(HO_OUT_OCEAN_TAS, m->tas_ocean);
       OUT(HO_OUT_FLUX_MIXED, m->heatflux_mixed[r]);
       OUT(HO_OUT_FLUX_INTERIOR, m->heatflux_interior[r]);
       OUT(HO_OUT_TIMESTEPS, (double)m->timesteps);

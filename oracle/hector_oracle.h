@@ -114,6 +114,10 @@ typedef struct {
   /* 26 x [<gas>_halocarbon] */
   double halo_tau[HO_NHALO], halo_rho[HO_NHALO], halo_delta[HO_NHALO], halo_H0[HO_NHALO],
       halo_molarMass[HO_NHALO];
+  /* [temperature] lo_warming_ratio: 0 = off; otherwise land / ocean-air / sea-surface
+   * temperatures as other components and callers see them are re-derived from global tas with
+   * this land-ocean warming ratio (temperature_component.cpp:586-622, 722-739) */
+  double lo_warming_ratio;
 } ho_params;
 
 /* User constraints: dense per-model-year series [nrow] (row = year - start_year), NaN = no

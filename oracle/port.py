@@ -41,6 +41,7 @@ class Params(C.Structure):
             "N0", "UC_N2O", "TN2O0")]
         + [(n, C.c_double * NHALO) for n in (
             "halo_tau", "halo_rho", "halo_delta", "halo_H0", "halo_molarMass")]
+        + [("lo_warming_ratio", C.c_double)]
     )
 
 

@@ -18,6 +18,7 @@ _lib = None
 # variable -> owning component for ini-style overrides (ref_setdata), cf. inst/input/*.ini
 PARAM_COMPONENT = {
     "S": "temperature", "diff": "temperature", "qco2": "temperature",
+    "lo_warming_ratio": "temperature",
     "beta": "simpleNbox", "q10_rh": "simpleNbox", "f_nppv": "simpleNbox", "f_nppd": "simpleNbox",
     "f_litterd": "simpleNbox", "npp_flux0": "simpleNbox", "C0": "simpleNbox",
     "aero_scalar": "forcing", "vol_scalar": "forcing",

@@ -125,8 +125,8 @@ int main(int argc, char **argv) {
     tc.setData("core", "trackingDate", message_data(unitval(1990, U_UNITLESS)));
     for (int y = 2000; y <= 2010; ++y) /* dated entries accumulate, one setData per year */
       tc.setData("CH4", "CH4_constrain", message_data((double)y, unitval(1800.0, U_PPBV_CH4)));
-    EXPECT(throws([&] { /* lo_warming_ratio: not an input of this engine */
-      tc.setData("temperature", "lo_warming_ratio", message_data(unitval(1.6, U_UNITLESS)));
+    EXPECT(throws([&] { /* lo_warming_ratio is unitless (temperature_component.cpp:266-269) */
+      tc.setData("temperature", "lo_warming_ratio", message_data(unitval(1.6, U_DEGC)));
     }));
     EXPECT(throws([&] {
       tc.setData("CH4", "CH4_constrain", message_data(2000.0, unitval(1800.0, U_PGC)));

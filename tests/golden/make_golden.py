@@ -336,6 +336,9 @@ def make_constraints():
 
 
 EXTRA_VARS = ["NPP", "RH", "gmst", "ocean_tas", "heatflux_mixed", "heatflux_interior",
+              # what a land-ocean warming ratio moves (the lo_ratio_* cases)
+              "CO2_concentration", "global_tas", "land_tas", "sst", "veg_c", "soil_c", "HL_pH",
+              "heatflux", "permafrost_c",
               # forcing agents and halocarbons the engine derives at fetch time
               "RF_BC", "RF_OC", "RF_SO2", "RF_NH3", "RF_aci", "RF_vol", "RF_albedo", "RF_misc",
               "RF_O3_trop", "RF_H2O_strat", "RF_CF4", "FadjCF4", "RF_CFC11", "FadjCFC11",
@@ -343,7 +346,11 @@ EXTRA_VARS = ["NPP", "RH", "gmst", "ocean_tas", "heatflux_mixed", "heatflux_inte
 EXTRA_CASES = [("default_ssp245", "ssp245", {}),
                ("pert_ssp585", "ssp585", dict(S=4.2, q10_rh=2.0, beta=0.4, diff=1.8)),
                ("aero_vol_ssp370", "ssp370", dict(aero_scalar=1.4, vol_scalar=0.85, S=3.7)),
-               ("corner_lo_ssp119", "ssp119", dict(S=1.5, q10_rh=1.0, beta=0.1, diff=0.3))]
+               ("corner_lo_ssp119", "ssp119", dict(S=1.5, q10_rh=1.0, beta=0.1, diff=0.3)),
+               # user-provided land-ocean warming ratio (temperature_component.cpp:586-622, 722-739)
+               ("lo_ratio_ssp245", "ssp245", dict(lo_warming_ratio=1.6)),
+               ("lo_ratio_ssp585", "ssp585", dict(lo_warming_ratio=1.3, S=4.0, q10_rh=2.2)),
+               ("lo_ratio_low_ssp126", "ssp126", dict(lo_warming_ratio=0.9, beta=0.2, diff=2.5))]
 
 
 def make_extra_outputs():

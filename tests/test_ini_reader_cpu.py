@@ -66,7 +66,10 @@ def test_unsupported_inputs_are_reported(tmp_path):
     bad3 = tmp_path / "lo.ini"
     bad3.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
         "[temperature]", "[temperature]\nlo_warming_ratio=1.6"))
-    assert L.hx_ini_read(str(bad3).encode(), None, None, None, 0) == -4
+    assert L.hx_ini_read(str(bad3).encode(), None, None, None, 0) == 0  # an input since r1
+    out = C.c_double()
+    assert L.hx_ini_scalar(str(bad3).encode(), b"lo_warming_ratio", C.byref(out)) == 0
+    assert out.value == 1.6
     bad2 = tmp_path / "unknown.ini"
     bad2.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
         "[temperature]", "[temperature]\nnot_a_variable=1"))
