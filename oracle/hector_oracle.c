@@ -19,6 +19,7 @@
 #include <float.h>
 #include <math.h>
 #include <setjmp.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -70,6 +71,15 @@ typedef struct {
   csys_t chem;
 } box_t;
 
+/* one biome's pools, slow parameters and recorded fluxes (simpleNbox.hpp:236-290) */
+typedef struct {
+  ho_biome par;
+  double veg_c, detritus_c, soil_c, permafrost_c, thawed_permafrost_c;
+  double co2fert, tempfertd, tempferts, f_frozen, f_new_thaw;
+  double tempferts_last_year; /* tempferts_tv[t] */
+  double RH_ch4, final_npp, final_rh;
+} bio_t;
+
 typedef struct {
   const ho_params *p;
   const double *raw; /* [nrow][HO_NRAW] */
@@ -82,13 +92,14 @@ typedef struct {
   int in_spinup;
 
   /* simpleNbox state (simpleNbox.hpp) */
-  double atmos_c, veg_c, detritus_c, soil_c, permafrost_c, thawed_permafrost_c, earth_c;
+  double atmos_c, earth_c;
+  int nb;                    /* biome_list.size() */
+  bio_t bio[HO_MAX_BIOMES];  /* biome_list order */
+  int border[HO_MAX_BIOMES]; /* std::map (name) order, for sum_map */
   double masstot, cum_luc_va, end_of_spinup_vegc, cumulative_pf_ch4, npp_luc_adjust;
-  double co2fert, tempfertd, tempferts, f_frozen, f_new_thaw;
-  double tempferts_last_year; /* tempferts_tv[t] */
   int have_tempferts_last;
   double current_luc_e, current_luc_u, current_ffi_e, current_daccs_u;
-  double RH_ch4, nbp, final_npp, final_rh;
+  double nbp;
   double snbox_ODEstartdate;
   double *Tland_record; /* [nrow], index = year - start; first key is start+1 */
   int has_been_run_before;
@@ -742,33 +753,42 @@ static double snbox_CO2_conc(member_t *m) { /* simpleNbox.cpp:414-420 */
   return FP(m, m->atmos_c * PGC_TO_PPMVCO2);
 }
 
-static double snbox_npp(member_t *m) { /* simpleNbox-runtime.cpp:622-635 */
-  double npp = FP(m, m->p->npp_flux0);
-  npp = FP(m, npp * m->co2fert);
+/* sum_map over one per-biome field, in std::map (biome name) order: simpleNbox.cpp:428-438 */
+#define SUM_MAP(m, field) sum_map_((m), offsetof(bio_t, field))
+static double sum_map_(member_t *m, size_t off) {
+  double sum = 0.0;
+  for (int k = 0; k < m->nb; ++k)
+    sum = FP(m, sum + *(const double *)((const char *)&m->bio[m->border[k]] + off));
+  return sum;
+}
+
+static double snbox_npp(member_t *m, const bio_t *b) { /* simpleNbox-runtime.cpp:622-635 */
+  double npp = FP(m, b->par.npp_flux0);
+  npp = FP(m, npp * b->co2fert);
   npp = FP(m, npp * m->npp_luc_adjust);
   return npp;
 }
-static double snbox_rh_fda(member_t *m) { /* :653-665 */
-  double dflux = FP(m, m->detritus_c * 0.25);
-  return FP(m, dflux * m->tempfertd);
+static double snbox_rh_fda(member_t *m, const bio_t *b) { /* :653-665 */
+  double dflux = FP(m, b->detritus_c * 0.25);
+  return FP(m, dflux * b->tempfertd);
 }
-static double snbox_rh_fsa(member_t *m) { /* :671-683 */
-  double soilflux = FP(m, m->soil_c * 0.02);
-  return FP(m, soilflux * m->tempferts);
+static double snbox_rh_fsa(member_t *m, const bio_t *b) { /* :671-683 */
+  double soilflux = FP(m, b->soil_c * 0.02);
+  return FP(m, soilflux * b->tempferts);
 }
-static double snbox_rh_ftpa_co2(member_t *m) { /* :689-701 */
-  double tpfc = FP(m, m->thawed_permafrost_c * (1 - m->p->fpf_static));
+static double snbox_rh_ftpa_co2(member_t *m, const bio_t *b) { /* :689-701 */
+  double tpfc = FP(m, b->thawed_permafrost_c * (1 - b->par.fpf_static));
   double tpflux = FP(m, tpfc * 0.02);
-  double r = FP(m, tpflux * m->tempferts);
-  return FP(m, r * (1.0 - m->p->rh_ch4_frac));
+  double r = FP(m, tpflux * b->tempferts);
+  return FP(m, r * (1.0 - b->par.rh_ch4_frac));
 }
-static double snbox_rh_ftpa_ch4(member_t *m) { /* :707-711 */
-  double r = FP(m, snbox_rh_ftpa_co2(m) / (1.0 - m->p->rh_ch4_frac));
-  return FP(m, r * m->p->rh_ch4_frac);
+static double snbox_rh_ftpa_ch4(member_t *m, const bio_t *b) { /* :707-711 */
+  double r = FP(m, snbox_rh_ftpa_co2(m, b) / (1.0 - b->par.rh_ch4_frac));
+  return FP(m, r * b->par.rh_ch4_frac);
 }
-static double snbox_rh(member_t *m) { /* :717-721 */
-  double r = FP(m, snbox_rh_fda(m) + snbox_rh_fsa(m));
-  return FP(m, r + snbox_rh_ftpa_co2(m));
+static double snbox_rh(member_t *m, const bio_t *b) { /* :717-721 */
+  double r = FP(m, snbox_rh_fda(m, b) + snbox_rh_fsa(m, b));
+  return FP(m, r + snbox_rh_ftpa_co2(m, b));
 }
 
 /* tseries::exists(year) && get(year) for a constraint series stored densely per model year
@@ -783,14 +803,14 @@ static int cn_get(const member_t *m, const double *series, int year, double *v) 
 }
 
 /* :744-772 */
-static void snbox_compute_pf_thaw_refreeze(member_t *m, double rh_co2, double rh_ch4, double *x,
+static void snbox_compute_pf_thaw_refreeze(const bio_t *b, double rh_co2, double rh_ch4, double *x,
                                            double *y, double *z) {
-  double biome_c_thaw = m->permafrost_c * m->f_new_thaw;
+  double biome_c_thaw = b->permafrost_c * b->f_new_thaw;
   double pf_refreeze_tp = 0.0, pf_refreeze_soil = 0.0;
   if (biome_c_thaw < 0) {
     const double pf_refreeze = -biome_c_thaw;
     biome_c_thaw = 0.0;
-    const double thawed_remaining = m->thawed_permafrost_c - rh_co2 - rh_ch4;
+    const double thawed_remaining = b->thawed_permafrost_c - rh_co2 - rh_ch4;
     pf_refreeze_tp = pf_refreeze < thawed_remaining ? pf_refreeze : thawed_remaining; /* std::min */
   }
   *x = biome_c_thaw; *y = pf_refreeze_tp; *z = pf_refreeze_soil;
@@ -798,18 +818,18 @@ static void snbox_compute_pf_thaw_refreeze(member_t *m, double rh_co2, double rh
 
 static void snbox_getCValues(member_t *m, double t, double c[]) { /* :247-258 */
   c[C_ATMOS] = m->atmos_c;
-  c[C_VEG] = FP(m, 0.0 + m->veg_c);          /* sum_map, simpleNbox.cpp:428-438 */
-  c[C_DET] = FP(m, 0.0 + m->detritus_c);
-  c[C_SOIL] = FP(m, 0.0 + m->soil_c);
-  c[C_PERMAFROST] = FP(m, 0.0 + m->permafrost_c);
-  c[C_THAWEDP] = FP(m, 0.0 + m->thawed_permafrost_c);
+  c[C_VEG] = SUM_MAP(m, veg_c);
+  c[C_DET] = SUM_MAP(m, detritus_c);
+  c[C_SOIL] = SUM_MAP(m, soil_c);
+  c[C_PERMAFROST] = SUM_MAP(m, permafrost_c);
+  c[C_THAWEDP] = SUM_MAP(m, thawed_permafrost_c);
   c[C_OCEAN] = ocean_totalcpool(m);          /* ocean_component.cpp:587-591 */
   m->ocean_ODEstartdate = t;
   c[C_EARTH] = m->earth_c;
   m->snbox_ODEstartdate = t;
 }
 
-/* :781-934 (single "global" biome, no NBP constraint) */
+/* :781-934 */
 static int snbox_calcderivs(member_t *m, double t, const double c[], double dcdt[]) {
   m->cnt.rhs_evals++;
   const int omodel_err = ocean_calcderivs(m, t, c, dcdt);
@@ -818,23 +838,33 @@ static int snbox_calcderivs(member_t *m, double t, const double c[], double dcdt
   if (ao_exchange >= 0.0) ocean_uptake = FP(m, ao_exchange);
   else ocean_release = FP(m, -ao_exchange);
 
-  const ho_params *p = m->p;
-  double npp_biome = snbox_npp(m);
-  double npp_current = FP(m, 0.0 + npp_biome);
-  double npp_fav = FP(m, 0.0 + FP(m, npp_biome * p->f_nppv));
-  double npp_fad = FP(m, 0.0 + FP(m, npp_biome * p->f_nppd));
-  double npp_fas = FP(m, 0.0 + FP(m, npp_biome * (1 - p->f_nppv - p->f_nppd)));
-  double rh_fda_current = FP(m, 0.0 + snbox_rh_fda(m));
-  double rh_fsa_current = FP(m, 0.0 + snbox_rh_fsa(m));
-  double rh_ftpa_co2_current = FP(m, 0.0 + snbox_rh_ftpa_co2(m));
-  double rh_ftpa_ch4_current = FP(m, 0.0 + snbox_rh_ftpa_ch4(m));
+  double npp_current = 0.0, npp_fav = 0.0, npp_fad = 0.0, npp_fas = 0.0;
+  double rh_fda_current = 0.0, rh_fsa_current = 0.0, rh_ftpa_co2_current = 0.0,
+         rh_ftpa_ch4_current = 0.0;
+  for (int ib = 0; ib < m->nb; ++ib) { /* biome_list order :809-821 */
+    const bio_t *b = &m->bio[ib];
+    const double npp_biome = snbox_npp(m, b);
+    npp_current = FP(m, npp_current + npp_biome);
+    npp_fav = FP(m, npp_fav + FP(m, npp_biome * b->par.f_nppv));
+    npp_fad = FP(m, npp_fad + FP(m, npp_biome * b->par.f_nppd));
+    npp_fas = FP(m, npp_fas + FP(m, npp_biome * (1 - b->par.f_nppv - b->par.f_nppd)));
+    rh_fda_current = FP(m, rh_fda_current + snbox_rh_fda(m, b));
+    rh_fsa_current = FP(m, rh_fsa_current + snbox_rh_fsa(m, b));
+    rh_ftpa_co2_current = FP(m, rh_ftpa_co2_current + snbox_rh_ftpa_co2(m, b));
+    rh_ftpa_ch4_current = FP(m, rh_ftpa_ch4_current + snbox_rh_ftpa_ch4(m, b));
+  }
   double rh_current = FP(m, FP(m, rh_fda_current + rh_fsa_current) + rh_ftpa_co2_current);
 
-  double v = FP(m, m->veg_c * 0.035);
-  double litter_flux = FP(m, 0.0 + v);
-  double litter_fvd = FP(m, 0.0 + FP(m, v * p->f_litterd));
-  double litter_fvs = FP(m, 0.0 + FP(m, v * (1 - p->f_litterd)));
-  double detsoil_flux = FP(m, 0.0 + FP(m, m->detritus_c * 0.6));
+  double litter_flux = 0.0, litter_fvd = 0.0, litter_fvs = 0.0, detsoil_flux = 0.0;
+  for (int ib = 0; ib < m->nb; ++ib) { /* :826-839 */
+    const bio_t *b = &m->bio[ib];
+    const double v = FP(m, b->veg_c * 0.035);
+    litter_flux = FP(m, litter_flux + v);
+    litter_fvd = FP(m, litter_fvd + FP(m, v * b->par.f_litterd));
+    litter_fvs = FP(m, litter_fvs + FP(m, v * (1 - b->par.f_litterd)));
+  }
+  for (int ib = 0; ib < m->nb; ++ib)
+    detsoil_flux = FP(m, detsoil_flux + FP(m, m->bio[ib].detritus_c * 0.6));
 
   const double total = c[C_VEG] + c[C_DET] + c[C_SOIL];
   double luc_fva = FP(m, FP(m, m->current_luc_e * c[C_VEG]) / total);
@@ -845,11 +875,15 @@ static int snbox_calcderivs(member_t *m, double t, const double c[], double dcdt
 
   double pf_thaw_c = 0.0, pf_refreeze_tp = 0.0, pf_refreeze_soil = 0.0;
   if (!m->in_spinup) {
-    double x, y, z;
-    snbox_compute_pf_thaw_refreeze(m, snbox_rh_ftpa_co2(m), snbox_rh_ftpa_ch4(m), &x, &y, &z);
-    pf_thaw_c = FP(m, 0.0 + FP(m, x));
-    pf_refreeze_tp = FP(m, 0.0 + FP(m, y));
-    pf_refreeze_soil = FP(m, 0.0 + FP(m, z));
+    for (int ib = 0; ib < m->nb; ++ib) {
+      const bio_t *b = &m->bio[ib];
+      double x, y, z;
+      snbox_compute_pf_thaw_refreeze(b, snbox_rh_ftpa_co2(m, b), snbox_rh_ftpa_ch4(m, b), &x, &y,
+                                     &z);
+      pf_thaw_c = FP(m, pf_thaw_c + FP(m, x));
+      pf_refreeze_tp = FP(m, pf_refreeze_tp + FP(m, y));
+      pf_refreeze_soil = FP(m, pf_refreeze_soil + FP(m, z));
+    }
   }
 
   /* NBP constraint :871-898: NPP and RH (and their parts) are scaled so that their net
@@ -910,27 +944,33 @@ static void snbox_slowparameval(member_t *m, double t, double Tland) {
   }
   m->npp_luc_adjust = (m->end_of_spinup_vegc - m->cum_luc_va) / m->end_of_spinup_vegc;
 
-  if (m->in_spinup) m->co2fert = 1.0;
-  else m->co2fert = 1 + p->beta * log(snbox_CO2_conc(m) / p->C0); /* :614-616 */
+  for (int ib = 0; ib < m->nb; ++ib) {
+    bio_t *b = &m->bio[ib];
+    if (m->in_spinup) b->co2fert = 1.0;
+    else b->co2fert = 1 + b->par.beta * log(snbox_CO2_conc(m) / p->C0); /* :614-616 */
+  }
 
-  double tfs_last = 0.0;
-  if (t > p->start_year && m->have_tempferts_last) tfs_last = m->tempferts_last_year;
-
-  if (m->in_spinup) {
-    m->tempfertd = 1.0;
-    m->tempferts = 1.0;
-    m->f_frozen = 1.0;
-    m->f_new_thaw = 0.0;
-  } else {
-    double wf = p->warmingfactor;
+  for (int ib = 0; ib < m->nb; ++ib) {
+    bio_t *b = &m->bio[ib];
+    double tfs_last = 0.0;
+    if (t > p->start_year && m->have_tempferts_last) tfs_last = b->tempferts_last_year;
+    if (m->in_spinup) {
+      b->tempfertd = 1.0;
+      b->tempferts = 1.0;
+      b->f_frozen = 1.0;
+      b->f_new_thaw = 0.0;
+      continue;
+    }
+    double wf = b->par.warmingfactor;
     const double Tland_biome = Tland * wf;
-    m->tempfertd = pow(p->q10_rh, (Tland_biome / 10.0));
-    m->f_new_thaw = 0.0;
-    if (m->permafrost_c) {
+    b->tempfertd = pow(b->par.q10_rh, (Tland_biome / 10.0));
+    b->f_new_thaw = 0.0;
+    if (b->permafrost_c) {
       double f_frozen_current = 1.0;
-      if (Tland_biome > 0) f_frozen_current = 1 - lognormal_cdf(p->pf_mu, p->pf_sigma, Tland_biome);
-      m->f_new_thaw = m->f_frozen - f_frozen_current;
-      m->f_frozen = f_frozen_current;
+      if (Tland_biome > 0)
+        f_frozen_current = 1 - lognormal_cdf(b->par.pf_mu, b->par.pf_sigma, Tland_biome);
+      b->f_new_thaw = b->f_frozen - f_frozen_current;
+      b->f_frozen = f_frozen_current;
     }
     double Tland_rm = 0.0;
     if (t > p->start_year + 0) {
@@ -942,12 +982,12 @@ static void snbox_slowparameval(member_t *m, double t, double Tland) {
       }
       Tland_rm /= 200;
     }
-    m->tempferts = pow(p->q10_rh, (Tland_rm / 10.0));
-    if (m->tempferts < tfs_last) m->tempferts = tfs_last;
+    b->tempferts = pow(b->par.q10_rh, (Tland_rm / 10.0));
+    if (b->tempferts < tfs_last) b->tempferts = tfs_last;
   }
 }
 
-/* :270-609 (single biome; no NBP / CO2 constraint) */
+/* :270-609 */
 static void snbox_stashCValues(member_t *m, double t, const double c[]) {
   const ho_params *p = m->p;
   const double yf = (t - m->snbox_ODEstartdate);
@@ -972,9 +1012,10 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
   double ao_flux = FP(m, m->box[LL].ao_flux + m->box[HL].ao_flux);
 
   double luc_e_untracked = m->current_luc_e, luc_u_untracked = m->current_luc_u;
-  double npp_total = FP(m, 0.0 + snbox_npp(m)); /* sum_npp */
-  double rh_total = FP(m, 0.0 + snbox_rh(m));   /* sum_rh */
-  const double permafrost_total = FP(m, 0.0 + m->permafrost_c);
+  double npp_total = 0.0, rh_total = 0.0; /* sum_npp, sum_rh: biome_list order */
+  for (int ib = 0; ib < m->nb; ++ib) npp_total = FP(m, npp_total + snbox_npp(m, &m->bio[ib]));
+  for (int ib = 0; ib < m->nb; ++ib) rh_total = FP(m, rh_total + snbox_rh(m, &m->bio[ib]));
+  const double permafrost_total = SUM_MAP(m, permafrost_c);
 
   double alf = npp_total - rh_total - luc_e_untracked + luc_u_untracked;
   double npp_rh_total = FP(m, npp_total + rh_total);
@@ -1014,13 +1055,15 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
   const double luc_e = luc_e_untracked, luc_u = luc_u_untracked;
   m->cum_luc_va = m->cum_luc_va + ((luc_e - luc_u) * c[C_VEG] / total);
 
-  {
-    const double wt = FP(m, snbox_npp(m) + snbox_rh(m)) / npp_rh_total;
-    const double wt_pf = permafrost_total > 0 ? m->permafrost_c / permafrost_total : 0;
+  for (int ib = 0; ib < m->nb; ++ib) { /* :399-531, biome_list order */
+    bio_t *b = &m->bio[ib];
+    const ho_biome *p = &b->par;
+    const double wt = FP(m, snbox_npp(m, b) + snbox_rh(m, b)) / npp_rh_total;
+    const double wt_pf = permafrost_total > 0 ? b->permafrost_c / permafrost_total : 0;
 
-    const double veg_frac = m->veg_c / total;
-    const double det_frac = m->detritus_c / total;
-    const double soil_frac = m->soil_c / total;
+    const double veg_frac = b->veg_c / total;
+    const double det_frac = b->detritus_c / total;
+    const double soil_frac = b->soil_c / total;
     double luc_fva_biome_flux = FP(m, FP(m, FP(m, luc_e_untracked * veg_frac)) * yf);
     double luc_fda_biome_flux = FP(m, FP(m, FP(m, luc_e_untracked * det_frac)) * yf);
     double luc_fsa_biome_flux = FP(m, FP(m, FP(m, luc_e_untracked * soil_frac)) * yf);
@@ -1032,20 +1075,20 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
     double npp_fas_biome_flux =
         FP(m, FP(m, FP(m, npp_biome * (1 - p->f_nppv - p->f_nppd))) * yf);
 
-    double rh_fda_adj = FP(m, snbox_rh_fda(m) * rh_nbp_constraint_adjust);
-    double rh_fsa_adj = FP(m, snbox_rh_fsa(m) * rh_nbp_constraint_adjust);
-    double rh_ftpa_co2_adj = FP(m, snbox_rh_ftpa_co2(m) * rh_nbp_constraint_adjust);
-    double rh_ftpa_ch4_adj = FP(m, snbox_rh_ftpa_ch4(m) * rh_nbp_constraint_adjust);
+    double rh_fda_adj = FP(m, snbox_rh_fda(m, b) * rh_nbp_constraint_adjust);
+    double rh_fsa_adj = FP(m, snbox_rh_fsa(m, b) * rh_nbp_constraint_adjust);
+    double rh_ftpa_co2_adj = FP(m, snbox_rh_ftpa_co2(m, b) * rh_nbp_constraint_adjust);
+    double rh_ftpa_ch4_adj = FP(m, snbox_rh_ftpa_ch4(m, b) * rh_nbp_constraint_adjust);
     /* final_npp = npp_biome (:429); final_rh = rh_fda_adj + rh_fsa_adj + rh_ftpa_co2_adj +
      * rh_ftpa_ch4_adj (:446-447) */
-    m->final_npp = npp_biome;
-    m->final_rh = FP(m, FP(m, FP(m, rh_fda_adj + rh_fsa_adj) + rh_ftpa_co2_adj) + rh_ftpa_ch4_adj);
+    b->final_npp = npp_biome;
+    b->final_rh = FP(m, FP(m, FP(m, rh_fda_adj + rh_fsa_adj) + rh_ftpa_co2_adj) + rh_ftpa_ch4_adj);
 
     double rh_fda_flux = FP(m, FP(m, rh_fda_adj) * yf);
     double rh_fsa_flux = FP(m, FP(m, rh_fsa_adj) * yf);
     double rh_fpa_co2_flux = FP(m, FP(m, rh_ftpa_co2_adj) * yf);
     double rh_fpa_ch4_flux = FP(m, FP(m, rh_ftpa_ch4_adj) * yf);
-    m->RH_ch4 = rh_fpa_ch4_flux;
+    b->RH_ch4 = rh_fpa_ch4_flux;
 
     /* luc fluxes :458-462 */
     if (T) tm_add(m, m->atmos_c, &m->tm[TP_ATMOS], luc_fva_biome_flux, &veg_0);
@@ -1056,22 +1099,22 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
     if (T) tm_add(m, a, &m->tm[TP_ATMOS], luc_fsa_biome_flux, &soil_0);
     a = FP(m, a + luc_fsa_biome_flux);
     m->atmos_c = a;
-    if (T) tm_add(m, m->veg_c, &m->tm[TP_VEG], luc_fav_biome_flux, &atm_0);
-    double vg = FP(m, m->veg_c + luc_fav_biome_flux);
+    if (T) tm_add(m, b->veg_c, &m->tm[TP_VEG], luc_fav_biome_flux, &atm_0);
+    double vg = FP(m, b->veg_c + luc_fav_biome_flux);
     vg = FP(m, vg - luc_fva_biome_flux);
-    m->veg_c = vg;
-    FP(m, m->detritus_c - luc_fda_biome_flux); /* :461, no effect except the throw */
-    m->soil_c = FP(m, m->soil_c - luc_fsa_biome_flux);
+    b->veg_c = vg;
+    FP(m, b->detritus_c - luc_fda_biome_flux); /* :461, no effect except the throw */
+    b->soil_c = FP(m, b->soil_c - luc_fsa_biome_flux);
 
     /* npp fluxes :465-469 */
     if (T) {
-      tm_add(m, m->veg_c, &m->tm[TP_VEG], npp_fav_biome_flux, &atm_0);
-      tm_add(m, m->detritus_c, &m->tm[TP_DET], npp_fad_biome_flux, &atm_0);
-      tm_add(m, m->soil_c, &m->tm[TP_SOIL], npp_fas_biome_flux, &atm_0);
+      tm_add(m, b->veg_c, &m->tm[TP_VEG], npp_fav_biome_flux, &atm_0);
+      tm_add(m, b->detritus_c, &m->tm[TP_DET], npp_fad_biome_flux, &atm_0);
+      tm_add(m, b->soil_c, &m->tm[TP_SOIL], npp_fas_biome_flux, &atm_0);
     }
-    m->veg_c = FP(m, m->veg_c + npp_fav_biome_flux);
-    m->detritus_c = FP(m, m->detritus_c + npp_fad_biome_flux);
-    m->soil_c = FP(m, m->soil_c + npp_fas_biome_flux);
+    b->veg_c = FP(m, b->veg_c + npp_fav_biome_flux);
+    b->detritus_c = FP(m, b->detritus_c + npp_fad_biome_flux);
+    b->soil_c = FP(m, b->soil_c + npp_fas_biome_flux);
     a = FP(m, m->atmos_c - npp_fav_biome_flux);
     a = FP(m, a - npp_fad_biome_flux);
     a = FP(m, a - npp_fas_biome_flux);
@@ -1085,59 +1128,59 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
     if (T) tm_add(m, a, &m->tm[TP_ATMOS], rh_fpa_co2_flux, &thawed_0);
     a = FP(m, a + rh_fpa_co2_flux);
     m->atmos_c = a;
-    m->detritus_c = FP(m, m->detritus_c - rh_fda_flux);
-    m->soil_c = FP(m, m->soil_c - rh_fsa_flux);
-    double tp = FP(m, m->thawed_permafrost_c - rh_fpa_co2_flux);
+    b->detritus_c = FP(m, b->detritus_c - rh_fda_flux);
+    b->soil_c = FP(m, b->soil_c - rh_fsa_flux);
+    double tp = FP(m, b->thawed_permafrost_c - rh_fpa_co2_flux);
     tp = FP(m, tp - rh_fpa_ch4_flux);
-    m->thawed_permafrost_c = tp;
+    b->thawed_permafrost_c = tp;
     m->cumulative_pf_ch4 += rh_fpa_ch4_flux;
 
     if (!m->in_spinup) { /* :484-503 */
       double x, y, z;
-      snbox_compute_pf_thaw_refreeze(m, rh_ftpa_co2_adj, rh_ftpa_ch4_adj, &x, &y, &z);
+      snbox_compute_pf_thaw_refreeze(b, rh_ftpa_co2_adj, rh_ftpa_ch4_adj, &x, &y, &z);
       double pf_thaw = FP(m, FP(m, FP(m, x)) * yf);
       double pf_refreeze_tp = FP(m, FP(m, FP(m, y)) * yf);
       double pf_refreeze_soil = FP(m, FP(m, FP(m, z)) * yf);
       /* pf_thaw carries permafrost's map, pf_refreeze_tp thawed permafrost's, pf_refreeze_soil
        * the soil's map as of now (after the luc and npp additions above) */
       const tmap_t soil_now = m->tm[TP_SOIL];
-      double pc = FP(m, m->permafrost_c - pf_thaw);
+      double pc = FP(m, b->permafrost_c - pf_thaw);
       if (T) tm_add(m, pc, &m->tm[TP_PERMAFROST], pf_refreeze_tp, &thawed_0);
       pc = FP(m, pc + pf_refreeze_tp);
       if (T) tm_add(m, pc, &m->tm[TP_PERMAFROST], pf_refreeze_soil, &soil_now);
       pc = FP(m, pc + pf_refreeze_soil);
-      m->permafrost_c = pc;
-      if (T) tm_add(m, m->thawed_permafrost_c, &m->tm[TP_THAWEDP], pf_thaw, &perm_0);
-      tp = FP(m, m->thawed_permafrost_c + pf_thaw);
+      b->permafrost_c = pc;
+      if (T) tm_add(m, b->thawed_permafrost_c, &m->tm[TP_THAWEDP], pf_thaw, &perm_0);
+      tp = FP(m, b->thawed_permafrost_c + pf_thaw);
       tp = FP(m, tp - pf_refreeze_tp);
-      m->thawed_permafrost_c = tp;
-      m->soil_c = FP(m, m->soil_c - pf_refreeze_soil);
+      b->thawed_permafrost_c = tp;
+      b->soil_c = FP(m, b->soil_c - pf_refreeze_soil);
     }
 
     /* litter :506-511 */
-    double litter_flux = FP(m, m->veg_c * (0.035 * yf));
+    double litter_flux = FP(m, b->veg_c * (0.035 * yf));
     double litter_fvd_flux = FP(m, litter_flux * p->f_litterd);
     double litter_fvs_flux = FP(m, litter_flux * (1 - p->f_litterd));
     if (T) {
-      tm_add(m, m->detritus_c, &m->tm[TP_DET], litter_fvd_flux, &m->tm[TP_VEG]);
-      tm_add(m, m->soil_c, &m->tm[TP_SOIL], litter_fvs_flux, &m->tm[TP_VEG]);
+      tm_add(m, b->detritus_c, &m->tm[TP_DET], litter_fvd_flux, &m->tm[TP_VEG]);
+      tm_add(m, b->soil_c, &m->tm[TP_SOIL], litter_fvs_flux, &m->tm[TP_VEG]);
     }
-    m->detritus_c = FP(m, m->detritus_c + litter_fvd_flux);
-    m->soil_c = FP(m, m->soil_c + litter_fvs_flux);
-    m->veg_c = FP(m, m->veg_c - litter_flux);
+    b->detritus_c = FP(m, b->detritus_c + litter_fvd_flux);
+    b->soil_c = FP(m, b->soil_c + litter_fvs_flux);
+    b->veg_c = FP(m, b->veg_c - litter_flux);
 
     /* detritus -> soil :514-521 */
-    double detsoil_flux = FP(m, m->detritus_c * (0.6 * yf));
-    if (T) tm_add(m, m->soil_c, &m->tm[TP_SOIL], detsoil_flux, &m->tm[TP_DET]);
-    m->soil_c = FP(m, m->soil_c + detsoil_flux);
-    m->detritus_c = FP(m, m->detritus_c - detsoil_flux);
+    double detsoil_flux = FP(m, b->detritus_c * (0.6 * yf));
+    if (T) tm_add(m, b->soil_c, &m->tm[TP_SOIL], detsoil_flux, &m->tm[TP_DET]);
+    b->soil_c = FP(m, b->soil_c + detsoil_flux);
+    b->detritus_c = FP(m, b->detritus_c - detsoil_flux);
 
     /* adjust to solver values (no sign check) :524-530 */
-    m->veg_c = newveg * wt;
-    m->detritus_c = newdet * wt;
-    m->soil_c = newsoil * wt;
-    m->permafrost_c = newpermafrost * wt_pf;
-    m->thawed_permafrost_c = newthawedpf * wt_pf;
+    b->veg_c = newveg * wt;
+    b->detritus_c = newdet * wt;
+    b->soil_c = newsoil * wt;
+    b->permafrost_c = newpermafrost * wt_pf;
+    b->thawed_permafrost_c = newthawedpf * wt_pf;
   }
 
   /* :534-541 */
@@ -1186,16 +1229,19 @@ static void snbox_stashCValues(member_t *m, double t, const double c[]) {
 
 /* record_state: simpleNbox.cpp:789-840 (only the part with side effects on the model) */
 static void snbox_record_state(member_t *m) {
-  if (!m->in_spinup) {
-    (void)snbox_npp(m);
-    (void)snbox_rh_fda(m);
-    (void)snbox_rh_fsa(m);
-    (void)snbox_rh_ftpa_co2(m);
-    m->RH_ch4 = snbox_rh_ftpa_ch4(m);
-  } else {
-    m->RH_ch4 = 0.0;
+  for (int ib = 0; ib < m->nb; ++ib) {
+    bio_t *b = &m->bio[ib];
+    if (!m->in_spinup) {
+      (void)snbox_npp(m, b);
+      (void)snbox_rh_fda(m, b);
+      (void)snbox_rh_fsa(m, b);
+      (void)snbox_rh_ftpa_co2(m, b);
+      b->RH_ch4 = snbox_rh_ftpa_ch4(m, b);
+    } else {
+      b->RH_ch4 = 0.0;
+    }
+    b->tempferts_last_year = b->tempferts;
   }
-  m->tempferts_last_year = m->tempferts;
   m->have_tempferts_last = 1;
 }
 
@@ -1783,17 +1829,37 @@ int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints
   m->tau_oh = p->TOH0;
   ocean_prepareToRun(m);
   /* SimpleNbox: simpleNbox.cpp:45-81, simpleNbox-runtime.cpp:61-197 */
-  m->veg_c = FP(m, p->veg_c);
-  m->detritus_c = FP(m, p->detritus_c);
-  m->soil_c = FP(m, p->soil_c);
-  m->permafrost_c = FP(m, p->permafrost_c);
-  m->thawed_permafrost_c = 0.0;
+  m->nb = p->n_biomes > 1 ? p->n_biomes : 1;
+  if (m->nb > HO_MAX_BIOMES || (m->nb > 1 && tracking_date < 9999)) { /* not restated */
+    status = HO_ERR_UNSUPPORTED;
+    goto done;
+  }
+  for (int ib = 0; ib < m->nb; ++ib) {
+    bio_t *b = &m->bio[ib];
+    if (p->n_biomes > 1) {
+      b->par = p->biome[ib];
+      m->border[ib] = p->biome_order[ib];
+    } else { /* the "global" biome of the scalar fields */
+      ho_biome g = {p->veg_c, p->detritus_c, p->soil_c, p->permafrost_c, p->npp_flux0, p->beta,
+                    p->q10_rh, p->warmingfactor, p->f_nppv, p->f_nppd, p->f_litterd,
+                    p->rh_ch4_frac, p->pf_mu, p->pf_sigma, p->fpf_static};
+      b->par = g;
+      m->border[ib] = ib;
+    }
+    b->veg_c = FP(m, b->par.veg_c);
+    b->detritus_c = FP(m, b->par.detritus_c);
+    b->soil_c = FP(m, b->par.soil_c);
+    b->permafrost_c = FP(m, b->par.permafrost_c);
+    b->thawed_permafrost_c = 0.0;
+    b->co2fert = b->tempfertd = b->tempferts = b->f_frozen = 1.0;
+    b->f_new_thaw = 0.0;
+    b->RH_ch4 = 0.0;
+    b->final_npp = b->final_rh = 0.0;
+  }
   m->earth_c = 5500;
   m->cum_luc_va = 0.0;
   m->npp_luc_adjust = 1.0;
-  m->co2fert = m->tempfertd = m->tempferts = m->f_frozen = 1.0;
-  m->f_new_thaw = 0.0;
-  m->end_of_spinup_vegc = m->veg_c;
+  m->end_of_spinup_vegc = SUM_MAP(m, veg_c);
   m->cumulative_pf_ch4 = 0.0;
   m->has_been_run_before = 0;
   m->atmos_c = FP(m, p->C0 * PPMVCO2_TO_PGC);
@@ -1801,7 +1867,6 @@ int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints
   m->atmosphere_cpool = m->tm[TP_ATMOS];            /* simpleNbox-runtime.cpp:195 */
   m->atmosphere_cpool_tracking = 0;
   m->masstot = 0.0;
-  m->RH_ch4 = 0.0;
   m->t = p->start_year; /* solver prepareToRun, carbon-cycle-solver.cpp:126 */
   m->dt = p->dt;
   doeclim_prepareToRun(m);
@@ -1835,9 +1900,9 @@ int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints
   }
   m->have_tempferts_last = 0; /* tempferts_tv[t] is only consulted for t > startDate */
   if (spin) {
-    spin->atmos = m->atmos_c; spin->veg = m->veg_c; spin->det = m->detritus_c;
-    spin->soil = m->soil_c; spin->permafrost = m->permafrost_c;
-    spin->thawed = m->thawed_permafrost_c; spin->earth = m->earth_c;
+    spin->atmos = m->atmos_c; spin->veg = SUM_MAP(m, veg_c); spin->det = SUM_MAP(m, detritus_c);
+    spin->soil = SUM_MAP(m, soil_c); spin->permafrost = SUM_MAP(m, permafrost_c);
+    spin->thawed = SUM_MAP(m, thawed_permafrost_c); spin->earth = m->earth_c;
     for (int i = 0; i < 4; ++i) spin->ocean[i] = m->box[i].carbon;
     spin->spinup_steps = (int)m->cnt.spinup_steps;
     spin->alk_HL = spin->alk_LL = 0;
@@ -1872,7 +1937,7 @@ int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints
     } else {
       const double current_ch4em = row[HO_RAW_CH4_E];
       const double current_toh = m->tau_oh;
-      const double rh_ch4 = m->RH_ch4 * (1000.0 * 16.04 / 12.01);
+      const double rh_ch4 = SUM_MAP(m, RH_ch4) * (1000.0 * 16.04 / 12.01);
       const double ch4n = row[HO_RAW_CH4N];
       const double emisTocon = (current_ch4em + rh_ch4 + ch4n) / p->UC_CH4;
       const double previous_ch4 = m->CH4[r - 1];
@@ -1894,7 +1959,7 @@ int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints
     }
     /* SimpleNbox::run: simpleNbox-runtime.cpp:206-227 */
     if (!m->has_been_run_before) {
-      m->end_of_spinup_vegc = FP(m, 0.0 + m->veg_c);
+      m->end_of_spinup_vegc = SUM_MAP(m, veg_c);
       m->has_been_run_before = 1;
     }
     /* tracking start (:215-220), then tell the ocean what the atmosphere is made of (:225) */
@@ -1939,15 +2004,15 @@ int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints
       OUT(HO_OUT_HL_PH, m->box[HL].chem.pH);
       OUT(HO_OUT_ATMOS_C, m->atmos_c);
       OUT(HO_OUT_SST, m->sst);
-      OUT(HO_OUT_PERMAFROST_C, m->permafrost_c);
+      OUT(HO_OUT_PERMAFROST_C, SUM_MAP(m, permafrost_c));
       OUT(HO_OUT_CH4, m->CH4[r]);
       OUT(HO_OUT_N2O, m->N2O[r]);
       OUT(HO_OUT_O3, m->O3[r]);
       OUT(HO_OUT_LAND_TAS, m->tas_land);
-      OUT(HO_OUT_VEG_C, m->veg_c);
-      OUT(HO_OUT_DETRITUS_C, m->detritus_c);
-      OUT(HO_OUT_SOIL_C, m->soil_c);
-      OUT(HO_OUT_THAWEDP_C, m->thawed_permafrost_c);
+      OUT(HO_OUT_VEG_C, SUM_MAP(m, veg_c));
+      OUT(HO_OUT_DETRITUS_C, SUM_MAP(m, detritus_c));
+      OUT(HO_OUT_SOIL_C, SUM_MAP(m, soil_c));
+      OUT(HO_OUT_THAWEDP_C, SUM_MAP(m, thawed_permafrost_c));
       OUT(HO_OUT_EARTH_C, m->earth_c);
       OUT(HO_OUT_NBP, m->nbp);
       OUT(HO_OUT_OCEAN_UPTAKE, m->annualflux_sum);
@@ -1960,9 +2025,9 @@ int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints
       OUT(HO_OUT_CARBON_DO, m->box[DO].carbon);
       OUT(HO_OUT_RF_CH4, rf_ch4_rel);
       OUT(HO_OUT_RF_N2O, rf_n2o_rel);
-      OUT(HO_OUT_RH_CH4, m->RH_ch4);
-      OUT(HO_OUT_NPP, m->final_npp);
-      OUT(HO_OUT_RH, m->final_rh);
+      OUT(HO_OUT_RH_CH4, SUM_MAP(m, RH_ch4));
+      OUT(HO_OUT_NPP, SUM_MAP(m, final_npp));
+      OUT(HO_OUT_RH, SUM_MAP(m, final_rh));
       OUT(HO_OUT_GMST, dc_flnd * m->temp_landair[r] + (1.0 - dc_flnd) * m->temp_sst[r]);
       OUT(HO_OUT_OCEAN_TAS, m->tas_ocean);
       OUT(HO_OUT_FLUX_MIXED, m->heatflux_mixed[r]);

@@ -86,8 +86,17 @@ enum {
   HO_ERR_YEARFRACTION = 5, /* simpleNbox-runtime.cpp:275, ocean_component.cpp:665 */
   HO_ERR_CO2SARF = 6,      /* forcing_component.cpp:353 */
   HO_ERR_STEPPER = 7,      /* odeint: 500 failed step-size searches */
-  HO_ERR_TRACKING = 8      /* fluxpool.hpp:105-112 source fractions out of range / tracking mismatch */
+  HO_ERR_TRACKING = 8,     /* fluxpool.hpp:105-112 source fractions out of range / tracking mismatch */
+  HO_ERR_UNSUPPORTED = 9   /* an input combination this restatement does not cover (biomes + tracking) */
 };
+
+#define HO_MAX_BIOMES 4
+/* what the reference keeps per biome (simpleNbox.hpp:236-290) */
+typedef struct {
+  double veg_c, detritus_c, soil_c, permafrost_c;
+  double npp_flux0, beta, q10_rh, warmingfactor, f_nppv, f_nppd, f_litterd;
+  double rh_ch4_frac, pf_mu, pf_sigma, fpf_static;
+} ho_biome;
 
 typedef struct {
   /* [core] */
@@ -118,6 +127,14 @@ typedef struct {
    * temperatures as other components and callers see them are re-derived from global tas with
    * this land-ocean warming ratio (temperature_component.cpp:586-622, 722-739) */
   double lo_warming_ratio;
+  /* biomes (simpleNbox.cpp:201-236): n_biomes <= 1 = the single "global" biome described by the
+   * scalar [simpleNbox] fields above; otherwise biome[0..n_biomes) in biome_list (creation)
+   * order replace them.  biome_order lists the same indices sorted by biome NAME: the
+   * reference keeps pools in std::map<string, ...>, so sum_map() adds in that order
+   * (simpleNbox.cpp:428-438) while the per-biome loops run in creation order. */
+  int n_biomes;
+  int biome_order[HO_MAX_BIOMES];
+  ho_biome biome[HO_MAX_BIOMES];
 } ho_params;
 
 /* User constraints: dense per-model-year series [nrow] (row = year - start_year), NaN = no

@@ -25,6 +25,18 @@ TRACK_POOLS = ["atmos_co2", "earth_c", "veg_c", "detritus_c", "soil_c", "permafr
 TRACK_SOURCES = TRACK_POOLS + ["untracked"]
 
 
+MAX_BIOMES = 4
+BIOME_FIELDS = ("veg_c", "detritus_c", "soil_c", "permafrost_c", "npp_flux0", "beta", "q10_rh",
+                "warmingfactor", "f_nppv", "f_nppd", "f_litterd", "rh_ch4_frac", "pf_mu",
+                "pf_sigma", "fpf_static")
+BIOME_DEFAULTS = dict(warmingfactor=1.0, rh_ch4_frac=0.023, pf_mu=1.67, pf_sigma=0.986,
+                      fpf_static=0.74)  # simpleNbox-runtime.cpp:109-143
+
+
+class Biome(C.Structure):
+    _fields_ = [(n, C.c_double) for n in BIOME_FIELDS]
+
+
 class Params(C.Structure):
     _fields_ = (
         [(n, C.c_int) for n in ("start_year", "end_year", "do_spinup", "max_spinup")]
@@ -41,8 +53,26 @@ class Params(C.Structure):
             "N0", "UC_N2O", "TN2O0")]
         + [(n, C.c_double * NHALO) for n in (
             "halo_tau", "halo_rho", "halo_delta", "halo_H0", "halo_molarMass")]
-        + [("lo_warming_ratio", C.c_double)]
+        + [("lo_warming_ratio", C.c_double), ("n_biomes", C.c_int),
+           ("biome_order", C.c_int * MAX_BIOMES), ("biome", Biome * MAX_BIOMES)]
     )
+
+    def set_biomes(self, biomes):
+        """biomes: {name: {field: value}} in creation (biome_list) order; every pool and
+        parameter the reference insists on (simpleNbox-runtime.cpp:66-101) must be given, the
+        rest default like its prepareToRun does (:102-143)"""
+        names = list(biomes)
+        assert 2 <= len(names) <= MAX_BIOMES
+        self.n_biomes = len(names)
+        for k, i in enumerate(sorted(range(len(names)), key=lambda i: names[i])):
+            self.biome_order[k] = i
+        for i, n in enumerate(names):
+            vals = dict(BIOME_DEFAULTS)
+            vals.update(biomes[n])
+            assert set(vals) == set(BIOME_FIELDS), (n, set(BIOME_FIELDS) ^ set(vals))
+            for f, v in vals.items():
+                setattr(self.biome[i], f, float(v))
+        return self
 
 
 class Counters(C.Structure):

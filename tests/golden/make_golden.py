@@ -372,8 +372,107 @@ def make_extra_outputs():
                         values=np.array(vals))
 
 
+BIOME_VARS = ["CO2_concentration", "global_tas", "veg_c", "detritus_c", "soil_c", "permafrost_c",
+              "thawedp_c", "NPP", "RH", "NBP", "CH4_concentration", "RF_tot", "HL_pH", "ocean_c",
+              "land_tas", "atmos_co2", "earth_c"]
+BIOME_GLOBAL_KEYS = ["npp_flux0", "veg_c", "detritus_c", "soil_c", "permafrost_c", "f_nppv", "f_nppd",
+                     "f_litterd", "beta", "q10_rh"]
+
+
+def _split(fracs, **over):
+    """biomes that split the default global pools and NPP by `fracs` (like R/biome.R split_biome
+    does), with per-biome overrides"""
+    glob = dict(npp_flux0=56.2, veg_c=550.0, detritus_c=55.0, soil_c=917.0, permafrost_c=865.0,
+                f_nppv=0.35, f_nppd=0.60, f_litterd=0.98, beta=0.65, q10_rh=1.2)
+    out = {}
+    for name, fr in fracs.items():
+        b = dict(glob)
+        for k in ("npp_flux0", "veg_c", "detritus_c", "soil_c", "permafrost_c"):
+            b[k] = glob[k] * fr
+        b.update(over.get(name, {}))
+        out[name] = b
+    return out
+
+
+# name -> (scenario, {biome: {field: value}} in creation order, {other parameter: value})
+BIOME_CASES = {
+    "two_ssp245": ("ssp245", _split(
+        {"boreal": 0.3, "tropical": 0.7},
+        boreal=dict(beta=0.5, q10_rh=2.2, warmingfactor=1.8, permafrost_c=865.0, f_nppv=0.30),
+        tropical=dict(beta=0.7, q10_rh=1.6, warmingfactor=0.9, permafrost_c=0.0, f_litterd=0.95)), {}),
+    # creation order differs from the name order the reference's std::map sums in
+    "three_ssp585": ("ssp585", _split(
+        {"tundra": 0.2, "amazon": 0.45, "midlat": 0.35},
+        tundra=dict(q10_rh=2.6, warmingfactor=2.1, permafrost_c=700.0, pf_mu=1.9, fpf_static=0.6,
+                    rh_ch4_frac=0.05),
+        amazon=dict(beta=0.8, warmingfactor=0.8, permafrost_c=0.0, f_nppd=0.55),
+        midlat=dict(beta=0.4, q10_rh=1.9, permafrost_c=165.0, pf_sigma=1.1)), dict(S=3.9, diff=1.6)),
+    "even_ssp126": ("ssp126", _split({"north": 0.5, "south": 0.5}), dict(q10_rh_all=1.8)),
+    "four_ssp370": ("ssp370", _split(
+        {"d": 0.1, "c": 0.2, "b": 0.3, "a": 0.4},
+        d=dict(warmingfactor=1.6, q10_rh=1.9), c=dict(beta=0.3), b=dict(f_nppv=0.4, f_nppd=0.5),
+        a=dict(permafrost_c=0.0)), dict(lo_warming_ratio=1.5)),
+    # the smallest biome's detritus pool goes negative: "Flux and pool values may not be negative"
+    "four_fail_ssp370": ("ssp370", _split(
+        {"d": 0.1, "c": 0.2, "b": 0.3, "a": 0.4},
+        d=dict(warmingfactor=2.5, q10_rh=3.0), c=dict(beta=0.1), b=dict(f_nppv=0.5, f_nppd=0.4),
+        a=dict(permafrost_c=0.0)), dict(lo_warming_ratio=1.5)),
+}
+
+
+def biome_ini(scn, biomes, path):
+    """the shipped ini with the global [simpleNbox] pool / parameter lines replaced by
+    <biome>.<name>= lines (simpleNbox.cpp:201-236)"""
+    src = os.path.join(REF, "inst/input/hector_%s.ini" % scn)
+    lines = []
+    for line in open(src).read().splitlines():
+        key = line.split("=")[0].strip()
+        if key in BIOME_GLOBAL_KEYS:
+            continue
+        lines.append(line.replace("csv:tables/", "csv:%s/inst/input/tables/" % REF))
+        if line.strip() == "[simpleNbox]":
+            for b, vals in biomes.items():
+                for k, v in vals.items():
+                    lines.append("%s.%s=%r" % (b, k, float(v)))
+    open(path, "w").write("\n".join(lines) + "\n")
+
+
+def make_biomes():
+    """ref_biomes.npz: multi-biome runs of the UNMODIFIED reference (biome-split pools,
+    simpleNbox-runtime.cpp:399-531)"""
+    import tempfile
+    from oracle import ref
+    tmp = tempfile.mkdtemp()
+    names, vals, fails = [], [], []
+    for name, (scn, biomes, params) in BIOME_CASES.items():
+        params = dict(params)
+        q10_all = params.pop("q10_rh_all", None)
+        if q10_all is not None:
+            for b in biomes.values():
+                b["q10_rh"] = q10_all
+        ini = os.path.join(tmp, name + ".ini")
+        biome_ini(scn, biomes, ini)
+        ok, err, o, _ = ref.run_member(ini, params, BIOME_VARS)
+        # a failing run leaves NaN from the failing year on (the driver steps year by year)
+        fail = 0 if ok else 1746 + int(np.argmax(np.isnan(o[0])))
+        if not ok:
+            o[:, fail - 1746:] = np.nan
+        names.append(name); vals.append(o); fails.append(fail)
+        print(name, "ok" if ok else "fails in %d: %s" % (fail, err[:80]))
+    import json
+    spec = {n: dict(scenario=c[0], biomes=c[1], params={k: v for k, v in c[2].items()
+                                                         if k != "q10_rh_all"})
+            for n, c in BIOME_CASES.items()}
+    np.savez_compressed(os.path.join(OUT, "ref_biomes.npz"), names=np.array(names),
+                        variables=np.array(BIOME_VARS + ["ocean_timesteps"]),
+                        values=np.array(vals), fail_year=np.array(fails),
+                        spec=np.array(json.dumps(spec)))
+
+
 if __name__ == "__main__":
-    if "extra" in sys.argv[1:]:
+    if "biomes" in sys.argv[1:]:
+        make_biomes()
+    elif "extra" in sys.argv[1:]:
         make_extra_outputs()
     elif "tracking" in sys.argv[1:]:
         make_tracking()
@@ -384,3 +483,4 @@ if __name__ == "__main__":
         make_tracking()
         make_constraints()
         make_extra_outputs()
+        make_biomes()

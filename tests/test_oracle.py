@@ -219,3 +219,30 @@ def test_extra_outputs_against_reference(case):
         if v not in port.OUT_NAMES:
             continue  # per-agent forcings: the engine derives them at fetch time, checked there
         assert np.array_equal(out[port.OUT_NAMES.index(v)], ref), v
+
+
+@pytest.mark.parametrize("case", util.ref_biomes(), ids=lambda c: c["name"])
+def test_biomes_against_reference(case):
+    """biome-split pools (simpleNbox-runtime.cpp:399-531, per-biome slow parameters :965-1062):
+    two, three (creation order != name order) and four biomes, one of them failing in the
+    reference with a negative pool -- bit-identical up to the failing year, same year, same reason"""
+    p = port.default_params()
+    p.set_biomes(case["biomes"])
+    st, fy, out, cnt, sp = port.run_member(util.scenarios()[case["scenario"]], params=p,
+                                           **case["params"])
+    n = 555
+    if case["fail_year"]:
+        assert (st, fy) == (1, case["fail_year"])  # HO_ERR_NEGATIVE
+        n = case["fail_year"] - 1746
+    else:
+        assert st == 0
+    for v, ref in case["values"].items():
+        if v in port.OUT_NAMES:
+            assert np.array_equal(out[port.OUT_NAMES.index(v)][:n], ref[:n]), v
+
+
+def test_biomes_with_tracking_are_refused():
+    p = port.default_params()
+    p.set_biomes(util.ref_biomes()[0]["biomes"])
+    st = port.run_member_tracked(util.scenarios()["ssp245"], 1750, params=p)[0]
+    assert st == 9  # HO_ERR_UNSUPPORTED

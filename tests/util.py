@@ -115,3 +115,18 @@ def lhs(M, seed=20241017):
         u = (rng.permutation(M) + rng.random(M)) / M
         cols.append(lo[j] + u * (hi[j] - lo[j]))
     return np.stack(cols, axis=1)
+
+
+def ref_biomes():
+    """multi-biome known answers of the unmodified reference (tests/golden/make_golden.py biomes)"""
+    import json
+    z = np.load(os.path.join(GOLDEN, "ref_biomes.npz"))
+    spec = json.loads(str(z["spec"]))
+    variables = [str(v) for v in z["variables"]]
+    cases = []
+    for i, name in enumerate(z["names"]):
+        sp = spec[str(name)]
+        cases.append(dict(name=str(name), scenario=sp["scenario"], biomes=sp["biomes"],
+                          params=sp["params"], fail_year=int(z["fail_year"][i]),
+                          values=dict(zip(variables, z["values"][i]))))
+    return cases
