@@ -16,7 +16,7 @@ EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "h
            "hx_set_param", "hx_set_param_device", "hx_get_param", "hx_select_outputs",
            "hx_prepare", "hx_run", "hx_run_stream", "hx_reset", "hx_reset_date", "hx_synchronize", "hx_fetch", "hx_output_device",
            "hx_ipc_export", "hx_ipc_open", "hx_ipc_pull", "hx_ipc_wait", "hx_ipc_close",
-           "hx_event_record", "hx_event_synchronize", "hx_member_status", "hx_set_tracking", "hx_fetch_tracking", "hx_tracking_years", "hx_counters", "hx_current_date", "hx_last_run_ms",
+           "hx_event_record", "hx_event_synchronize", "hx_member_status", "hx_set_tracking", "hx_set_biomes", "hx_biome_count", "hx_fetch_tracking", "hx_tracking_years", "hx_counters", "hx_current_date", "hx_last_run_ms",
            "hx_spinup_state", "hx_version"]
 
 
@@ -83,6 +83,8 @@ def lib():
     L.hx_event_record.argtypes = [vp, C.c_int32]
     L.hx_event_synchronize.argtypes = [vp, C.c_int32]
     L.hx_set_tracking.argtypes = [vp, C.c_int32, C.c_int32]
+    L.hx_set_biomes.argtypes = [vp, C.c_int32, C.POINTER(C.c_char_p)]
+    L.hx_biome_count.argtypes = [vp]
     L.hx_fetch_tracking.argtypes = [vp, C.c_double, dp, C.POINTER(C.c_uint32)]
     L.hx_tracking_years.argtypes = [vp, ip, C.c_int32]
     L.hx_member_status.argtypes = [vp, ip, ip, C.c_int32]

@@ -160,6 +160,56 @@ struct Engine {
     return code;
   }
 
+  /* biomes: hx_set_biomes */
+  int n_biomes = 1;
+  std::vector<std::string> biome_names;
+  double bscalar[HX_MAX_BIOMES][BP_COUNT];
+  std::vector<double> bvec[HX_MAX_BIOMES][BP_COUNT];
+  double *d_BP = nullptr, *d_BF = nullptr, *d_BF_snap = nullptr;
+  /* "<biome>.<name>" -> (biome, BP_* field); false if it is not one */
+  bool find_biome_param(const char *name, int &ib, int &f) const {
+    const char *dot = strchr(name, '.');
+    if (!dot || n_biomes <= 1) return false;
+    const std::string biome(name, dot - name);
+    for (ib = 0; ib < n_biomes; ++ib)
+      if (biome_names[ib] == biome) break;
+    if (ib == n_biomes) return false;
+    for (f = 0; f < BP_COUNT; ++f)
+      if (!strcmp(hx::kBiomeParams[f].name, dot + 1)) return true;
+    return false;
+  }
+  /* the global land inputs that per-biome values replace (simpleNbox.cpp:201-227) */
+  static bool is_biome_replaced(int pi) {
+    static const int k[] = {PI_VEG_C0, PI_DET_C0, PI_SOIL_C0, PI_PERMAFROST_C0, PI_NPP_FLUX0, PI_BETA,
+                            PI_Q10, PI_WARMINGFACTOR, PI_F_NPPV, PI_F_NPPD, PI_F_LITTERD,
+                            PI_RH_CH4_FRAC, PI_PF_MU, PI_PF_SIGMA, PI_FPF_STATIC};
+    for (int v : k)
+      if (v == pi) return true;
+    return false;
+  }
+  int upload_biomes() {
+    const int nf = n_biomes * BP_COUNT;
+    for (int ib = 0; ib < n_biomes; ++ib)
+      for (int f = 0; f < BP_COUNT; ++f) {
+        const int idx = ib * BP_COUNT + f;
+        k_fill_field<<<(Mpad + 255) / 256, 256, 0, stream>>>(d_BP, idx, nf, bscalar[ib][f], Mpad);
+        CUDA_TRY(cudaGetLastError());
+        if (bvec[ib][f].empty()) continue;
+        int rc = ensure_pinned((size_t)M * sizeof(double));
+        if (rc) return rc;
+        rc = ensure_stage((size_t)M * sizeof(double));
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        memcpy(h_pinned, bvec[ib][f].data(), (size_t)M * sizeof(double));
+        CUDA_TRY(cudaMemcpyAsync(d_stage, h_pinned, (size_t)M * sizeof(double),
+                                 cudaMemcpyHostToDevice, stream));
+        k_scatter_field<<<(M + 255) / 256, 256, 0, stream>>>(d_BP, idx, nf, d_stage, d_dev_of_api, M);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(stream));
+      }
+    return HX_OK;
+  }
+
   int find_param(const char *name) const {
     for (int i = 0; i < PI_COUNT; ++i)
       if (!strcmp(hx::kParams[i].name, name)) return i;
@@ -293,7 +343,7 @@ struct Engine {
   int fetch_derived(const char *name, const double *dates, int n_dates, double *out, int &rc);
 
   void free_device() {
-    void *ptrs[] = {d_P, d_S, d_S_snap, d_D, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
+    void *ptrs[] = {d_BP, d_BF, d_BF_snap, d_P, d_S, d_S_snap, d_D, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
                     d_block_scen, d_status, d_status_snap, d_status_post, d_fail_year, d_spinup_steps, d_yidx,
                     d_counters, d_dev_of_api, d_sched, d_T, d_TO, d_TK, d_TOK, d_REC, d_YCNT};
     for (void *p : ptrs)
@@ -305,6 +355,7 @@ struct Engine {
     d_T = d_TO = d_REC = nullptr;
     d_YCNT = nullptr;
     d_TK = d_TOK = nullptr;
+    d_BP = d_BF = d_BF_snap = nullptr;
     d_dev_of_api = nullptr;
     stage_bytes = 0;
     yidx_cap = 0;
@@ -365,6 +416,7 @@ struct Engine {
   }
 
   bool spinup_shared() const {
+    if (n_biomes > 1) return false; /* the broadcast covers the member-level state only */
     for (int pi : hx::kSpinupParams)
       if (!pvec[pi].empty() || pvec_on_device_only[pi]) return false;
     return true;
@@ -449,6 +501,9 @@ struct Engine {
     if (d_T) CUDA_TRY(hx::launch_track_init(d, stream));
     CUDA_TRY(cudaMemcpyAsync(d_S_snap, d_S, (size_t)SI_COUNT * Mpad * sizeof(double),
                              cudaMemcpyDeviceToDevice, stream));
+    if (d_BF)
+      CUDA_TRY(cudaMemcpyAsync(d_BF_snap, d_BF, (size_t)n_biomes * BF_COUNT * Mpad * sizeof(double),
+                               cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(d_status_post, d_status, (size_t)Mpad * sizeof(int32_t),
                              cudaMemcpyDeviceToDevice, stream));
     cur_row = 0;
@@ -752,9 +807,55 @@ static int set_special_scalar(hx_engine *h, const char *name, double v) {
   return 0;
 }
 
+int hx_set_biomes(hx_handle h, int32_t n_biomes, const char *const *names) {
+  if (!h) return HX_ERR_ARG;
+  if (h->prepared) return h->fail(HX_ERR_STATE, "hx_set_biomes must be called before hx_prepare");
+  if (n_biomes <= 1 && !names) { /* back to the single global biome */
+    h->n_biomes = 1;
+    h->biome_names.clear();
+    return HX_OK;
+  }
+  if (n_biomes < 2 || n_biomes > HX_MAX_BIOMES || !names)
+    return h->fail(HX_ERR_ARG, "hx_set_biomes: 2 .. " + std::to_string(HX_MAX_BIOMES) + " named biomes");
+  std::vector<std::string> nm;
+  for (int i = 0; i < n_biomes; ++i) {
+    if (!names[i] || !*names[i] || strchr(names[i], '.') || !strcmp(names[i], "global"))
+      return h->fail(HX_ERR_ARG, "hx_set_biomes: bad biome name (empty, dotted or 'global')");
+    for (const std::string &o : nm)
+      if (o == names[i]) return h->fail(HX_ERR_ARG, std::string("biome listed twice: ") + names[i]);
+    nm.push_back(names[i]);
+  }
+  h->n_biomes = n_biomes;
+  h->biome_names = nm;
+  for (int ib = 0; ib < HX_MAX_BIOMES; ++ib)
+    for (int f = 0; f < BP_COUNT; ++f) {
+      h->bscalar[ib][f] = hx::kBiomeParams[f].dflt;
+      h->bvec[ib][f].clear();
+    }
+  return HX_OK;
+}
+
+int hx_biome_count(hx_handle h) { return h ? h->n_biomes : HX_ERR_ARG; }
+
+/* "<biome>.<name>" inputs: scalar (per_member null) or one value per member */
+static int set_biome_param(hx_handle h, int ib, int f, double value, const double *per_member) {
+  if (h->prepared)
+    return h->fail(HX_ERR_STATE, "per-biome inputs must be set before hx_prepare");
+  if (per_member) h->bvec[ib][f].assign(per_member, per_member + h->M);
+  else { h->bscalar[ib][f] = value; h->bvec[ib][f].clear(); }
+  return HX_OK;
+}
+
 int hx_set_param_scalar(hx_handle h, const char *name, double value) {
   if (!h || !name) return HX_ERR_ARG;
+  {
+    int ib, f;
+    if (h->find_biome_param(name, ib, f)) return set_biome_param(h, ib, f, value, nullptr);
+  }
   const int pi = h->find_param(name);
+  if (pi >= 0 && h->n_biomes > 1 && Engine::is_biome_replaced(pi))
+    return h->fail(HX_ERR_ARG, std::string(name) + ": cannot have both global and biome-specific "
+                                                   "data (simpleNbox-runtime.cpp:66-69)");
   if (pi < 0) {
     if (h->prepared) return h->fail(HX_ERR_STATE, std::string(name) + " must be set before hx_prepare");
     if (set_special_scalar(h, name, value)) return HX_OK;
@@ -776,7 +877,17 @@ int hx_set_param_scalar(hx_handle h, const char *name, double value) {
 
 int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_t n) {
   if (!h || !name || !per_member) return HX_ERR_ARG;
+  {
+    int ib, f;
+    if (h->find_biome_param(name, ib, f)) {
+      if (n != h->M) return h->fail(HX_ERR_ARG, "hx_set_param: n != n_members");
+      return set_biome_param(h, ib, f, 0.0, per_member);
+    }
+  }
   const int pi = h->find_param(name);
+  if (pi >= 0 && h->n_biomes > 1 && Engine::is_biome_replaced(pi))
+    return h->fail(HX_ERR_ARG, std::string(name) + ": cannot have both global and biome-specific "
+                                                   "data (simpleNbox-runtime.cpp:66-69)");
   if (pi < 0) return h->fail(HX_ERR_ARG, std::string("unknown per-member parameter: ") + name);
   if (pi == PI_N0) return h->fail(HX_ERR_UNSUPPORTED, "N0 is scalar only (host N2O series)");
   if (n != h->M) return h->fail(HX_ERR_ARG, "hx_set_param: n != n_members");
@@ -926,6 +1037,22 @@ int hx_prepare(hx_handle h) {
   C.track_every = h->track_every;
   C.track_nrec = (int)h->track_years.size();
 
+  /* biomes: every biome needs its pools and parameters (simpleNbox-runtime.cpp:66-101) */
+  const int nb = h->n_biomes;
+  C.n_biomes = nb;
+  for (int i = 0; i < HX_MAX_BIOMES; ++i) C.biome_order[i] = i;
+  if (nb > 1) {
+    if (tracking)
+      return fail(HX_ERR_UNSUPPORTED, "carbon tracking with more than one biome is not implemented");
+    for (int ib = 0; ib < nb; ++ib)
+      for (int f = 0; f < BP_COUNT; ++f)
+        if (h->bvec[ib][f].empty() && std::isnan(h->bscalar[ib][f]))
+          return fail(HX_ERR_ARG, ("no " + std::string(hx::kBiomeParams[f].name) + " data for biome " +
+                                   h->biome_names[ib]).c_str());
+    std::sort(C.biome_order, C.biome_order + nb,
+              [&](int a, int b) { return h->biome_names[a] < h->biome_names[b]; });
+  }
+
   /* device scenario tables */
   std::vector<double> tab;
   bool any_constraint = false;
@@ -953,6 +1080,10 @@ int hx_prepare(hx_handle h) {
       cudaMalloc(&h->d_counters, HX_NCOUNTERS * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMalloc(&h->d_sched, (block_scen.size() + 1) * sizeof(unsigned)) != cudaSuccess ||
       cudaMalloc(&h->d_dev_of_api, (size_t)M * sizeof(int32_t)) != cudaSuccess ||
+      (nb > 1 &&
+       (cudaMalloc(&h->d_BP, (size_t)nb * BP_COUNT * Mp * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_BF, (size_t)nb * BF_COUNT * Mp * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_BF_snap, (size_t)nb * BF_COUNT * Mp * sizeof(double)) != cudaSuccess)) ||
       (tracking &&
        (cudaMalloc(&h->d_T, (size_t)TS_COUNT * HX_NSRC * Mp * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_TK, (size_t)TS_COUNT * Mp * sizeof(uint32_t)) != cudaSuccess ||
@@ -980,6 +1111,7 @@ int hx_prepare(hx_handle h) {
   cudaMemsetAsync(h->d_conv, 0, (size_t)HX_SLAB_YEARS * Mp * sizeof(double), st);
   cudaMemsetAsync(h->d_sst, 0, (size_t)nrow * Mp * sizeof(double), st);
   cudaMemsetAsync(h->d_tland, 0, (size_t)nrow * Mp * sizeof(double), st);
+  if (h->d_BF) cudaMemsetAsync(h->d_BF, 0, (size_t)nb * BF_COUNT * Mp * sizeof(double), st);
   if (cudaStreamSynchronize(st) != cudaSuccess)
     return fail(HX_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
 
@@ -989,6 +1121,7 @@ int hx_prepare(hx_handle h) {
   d.block_scen = h->d_block_scen; d.status = h->d_status; d.fail_year = h->d_fail_year;
   d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters; d.sched = h->d_sched;
   d.T = h->d_T; d.TK = h->d_TK; d.TO = h->d_TO; d.TOK = h->d_TOK; d.REC = h->d_REC; d.YCNT = h->d_YCNT;
+  d.BP = h->d_BP; d.BF = h->d_BF;
   h->rec_elems = block_scen.size() * hx::track_record_bytes_per_cta() / sizeof(double);
   h->ycnt_bytes = block_scen.size() * hx::track_ycnt_bytes_per_tile();
   h->tables_constrained = any_constraint;
@@ -1002,6 +1135,10 @@ int hx_prepare(hx_handle h) {
   h->prepared = true; /* upload_param / set_param paths need the buffers */
   for (int pi = 0; pi < PI_COUNT; ++pi) {
     int rc = h->upload_param(pi);
+    if (rc) { h->prepared = false; return rc; }
+  }
+  if (h->d_BP) {
+    int rc = h->upload_biomes();
     if (rc) { h->prepared = false; return rc; }
   }
   int rc = h->run_setup_and_spinup();
@@ -1024,6 +1161,10 @@ int hx_reset(hx_handle h) {
   }
   cudaError_t e = cudaMemcpyAsync(h->d_S, h->d_S_snap, (size_t)SI_COUNT * h->Mpad * sizeof(double),
                                   cudaMemcpyDeviceToDevice, h->stream);
+  if (e == cudaSuccess && h->d_BF)
+    e = cudaMemcpyAsync(h->d_BF, h->d_BF_snap,
+                        (size_t)h->n_biomes * BF_COUNT * h->Mpad * sizeof(double),
+                        cudaMemcpyDeviceToDevice, h->stream);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(h->d_status, h->d_status_post, (size_t)h->Mpad * sizeof(int32_t),
                         cudaMemcpyDeviceToDevice, h->stream);

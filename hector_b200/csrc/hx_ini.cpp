@@ -17,6 +17,8 @@
  */
 #include <sys/stat.h>
 
+#include <algorithm>
+
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -228,9 +230,28 @@ bool read_ini(const std::string &path, IniInputs &out) {
       name = name.substr(0, lb);
     }
     if (name.find('.') != std::string::npos && section == "simpleNbox") {
-      out.error = "biome-specific input '" + name + "' is not supported by the ensemble engine";
-      out.unsupported = true;
-      return false;
+      /* <biome>.<name>: a biome-specific pool or parameter (simpleNbox.cpp:201-236) */
+      const size_t dot = name.find('.');
+      const std::string biome = name.substr(0, dot), var = name.substr(dot + 1);
+      bool known = false;
+      for (int f = 0; f < BP_COUNT; ++f) known = known || var == kBiomeParams[f].name;
+      double v;
+      if (!known) {
+        out.error = "Unknown variable name while parsing simpleNbox: " + name;
+        return false;
+      }
+      if (!std::isnan(date) || !parse_number(value, v)) {
+        out.error = "[simpleNbox] " + name + ": expected a scalar, got: " + value;
+        return false;
+      }
+      if (biome == "global") {
+        name = var; /* the default biome spelled out */
+      } else {
+        if (std::find(out.biomes.begin(), out.biomes.end(), biome) == out.biomes.end())
+          out.biomes.push_back(biome);
+        out.biome_scalars.push_back(std::make_pair(name, v));
+        continue;
+      }
     }
 
     /* ---- [core] ---- */
@@ -351,6 +372,21 @@ bool read_ini(const std::string &path, IniInputs &out) {
     out.error = "Unknown variable name while parsing " + section + ": " + name;
     return false;
   }
+  if (!out.biomes.empty()) {
+    /* simpleNbox-runtime.cpp:66-69 */
+    for (int f = 0; f < BP_COUNT; ++f)
+      if (out.scalars.count(kBiomeParams[f].name)) {
+        out.error = "Cannot have both global and biome-specific data! (" +
+                    std::string(kBiomeParams[f].name) + ")";
+        return false;
+      }
+    if (out.biomes.size() < 2 || out.biomes.size() > HX_MAX_BIOMES) {
+      out.error = "the ensemble engine runs the global biome or 2 .. " +
+                  std::to_string(HX_MAX_BIOMES) + " named biomes";
+      out.unsupported = true;
+      return false;
+    }
+  }
   if (out.end_year <= out.start_year) {
     out.error = "[core] startDate/endDate missing or inconsistent";
     return false;
@@ -430,6 +466,16 @@ extern "C" int hx_create_from_ini(const char *const *ini_paths, int32_t n_inis, 
   if (in[0].tracking_date < 9999) {
     rc = hx_set_tracking(h, (int32_t)in[0].tracking_date, 1);
     if (rc) return bail(rc);
+  }
+  if (!in[0].biomes.empty()) {
+    std::vector<const char *> names;
+    for (const std::string &b : in[0].biomes) names.push_back(b.c_str());
+    rc = hx_set_biomes(h, (int32_t)names.size(), names.data());
+    if (rc) return bail(rc);
+    for (const std::pair<std::string, double> &kv : in[0].biome_scalars) {
+      rc = hx_set_param_scalar(h, kv.first.c_str(), kv.second);
+      if (rc) return bail(rc);
+    }
   }
   for (std::map<std::string, double>::const_iterator it = in[0].scalars.begin();
        it != in[0].scalars.end(); ++it) {

@@ -14,6 +14,10 @@ struct IniInputs {
   std::map<std::string, double> scalars;   /* engine parameter name -> value */
   std::vector<std::vector<double>> series; /* [RAW_COUNT][nrow] dense per-year values */
   std::map<int, std::vector<double>> constraints; /* CN_* -> [nrow], NaN = no entry */
+  /* <biome>.<name> entries of [simpleNbox] (simpleNbox.cpp:201-236): the biomes in the order
+   * they first appear, and their values */
+  std::vector<std::string> biomes;
+  std::vector<std::pair<std::string, double>> biome_scalars; /* "<biome>.<name>" -> value */
   std::string error;
   bool unsupported = false;
 };

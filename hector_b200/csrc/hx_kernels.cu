@@ -79,6 +79,8 @@ __device__ __forceinline__ void fence_proxy_async() {
 struct Bases {
   const double *P;
   double *S, *D, *ker, *sst, *tland, *conv;
+  const double *BP; /* per-biome parameters / state of this member (null: single biome) */
+  double *BF;
 };
 __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, int m) {
   const size_t tile = (size_t)(m / HX_BLOCK), ln = (size_t)(m % HX_BLOCK);
@@ -90,6 +92,8 @@ __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, in
   b.conv = d.conv + tile * (size_t)HX_SLAB_YEARS * HX_BLOCK + ln;
   b.sst = d.sst_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
   b.tland = d.tland_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
+  b.BP = d.BP ? d.BP + tile * (size_t)C.n_biomes * BP_COUNT * HX_BLOCK + ln : nullptr;
+  b.BF = d.BF ? d.BF + tile * (size_t)C.n_biomes * BF_COUNT * HX_BLOCK + ln : nullptr;
   return b;
 }
 #define PAR(i) __ldg(BS.P + (i) * HX_BLOCK)
@@ -114,6 +118,7 @@ __device__ __forceinline__ void load_member(const Bases &BS, Member &mb) {
   mb.status = 0; mb.neg = false; mb.timesteps = 0;
   mb.pco2HL = mb.pco2LL = 0.0; mb.gHL = mb.gLL = 0.0; mb.luc_e = mb.luc_u = 0.0;
   mb.REC = nullptr; mb.rec_n = 0; mb.trk = false; mb.trk_bad = false;
+  mb.BIOP = BS.BP; mb.BIOF = BS.BF;
 }
 
 __device__ __forceinline__ void store_member(const Bases &BS, const Member &mb) {
@@ -274,6 +279,26 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   STATE(SI_BASE_N2O) = 0.0;
   STATE(SI_TLAND_WSUM) = 0.0; STATE(SI_TLAND_WCOMP) = 0.0; STATE(SI_DPAST_RAW) = 0.0;
   STATE(SI_TLAND_C) = 0.0; STATE(SI_SST_C) = 0.0;
+  if (BS.BF) {
+    /* biome-split pools: each biome starts from its own initial pools, the member-level state
+     * holds their sums (sum_map order); simpleNbox.cpp:281-301, simpleNbox-runtime.cpp:79, 145 */
+    double sv = 0.0, sd = 0.0, ss = 0.0, sp = 0.0;
+    for (int k = 0; k < C.n_biomes; ++k) {
+      const int ib = C.biome_order[k];
+      const double *bp = BS.BP + (size_t)ib * BP_COUNT * HX_BLOCK;
+      double *bf = BS.BF + (size_t)ib * BF_COUNT * HX_BLOCK;
+      for (int f = 0; f < BF_COUNT; ++f) bf[f * HX_BLOCK] = 0.0;
+      sv += (bf[BF_VEG * HX_BLOCK] = __ldg(bp + BP_VEG_C0 * HX_BLOCK));
+      sd += (bf[BF_DET * HX_BLOCK] = __ldg(bp + BP_DET_C0 * HX_BLOCK));
+      ss += (bf[BF_SOIL * HX_BLOCK] = __ldg(bp + BP_SOIL_C0 * HX_BLOCK));
+      sp += (bf[BF_PERMAFROST * HX_BLOCK] = __ldg(bp + BP_PERMAFROST_C0 * HX_BLOCK));
+      bf[BF_TEMPFERTS * HX_BLOCK] = 1.0; bf[BF_F_FROZEN * HX_BLOCK] = 1.0;
+      bf[BF_X_CO2FERT * HX_BLOCK] = 1.0; bf[BF_X_TFD * HX_BLOCK] = 1.0;
+      bf[BF_X_TFS * HX_BLOCK] = 1.0;
+    }
+    STATE(SI_VEG) = sv; STATE(SI_DET) = sd; STATE(SI_SOIL) = ss; STATE(SI_PERMAFROST) = sp;
+    STATE(SI_EOS_VEGC) = sv;
+  }
   BS.sst[0] = 0.0;   /* row 0: temp_sst[0] = 0 */
   BS.tland[0] = 0.0;
   d.fail_year[m] = 0;
@@ -357,6 +382,7 @@ __device__ __noinline__ void chem_equilibrate(EqBox &b, Work &w) {
 /* Core::run_spinup (core.cpp:394-420) + CarbonCycleSolver::run_spinup
  * (carbon-cycle-solver.cpp:313-370); then the first-year chemistry switch-on of
  * OceanComponent::run (ocean_component.cpp:392-400). */
+template <bool BIOMES>
 __global__ void __launch_bounds__(HX_BLOCK)
 hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int m_offset,
                  int only_member) {
@@ -377,6 +403,12 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
   if (!(C.flags & HX_FLAG_NO_SPINUP)) {
     mb.S[SI_X_CO2FERT * HX_TILE] = 1.0; mb.S[SI_X_TFD * HX_TILE] = 1.0; mb.S[SI_X_TFS * HX_TILE] = 1.0; mb.S[SI_X_FNEWTHAW * HX_TILE] = 0.0; mb.S[SI_F_FROZEN * HX_TILE] = 1.0;
     mb.luc_e = mb.luc_u = mb.S[SI_X_FFI * HX_TILE] = mb.S[SI_X_DACCS * HX_TILE] = 0.0;
+    if (BIOMES)
+      for (int ib = 0; ib < C.n_biomes; ++ib) { /* no perturbation in spin-up (:968, 993-997) */
+        const Biome b = biome_of(mb, ib);
+        b.f(BF_X_CO2FERT) = 1.0; b.f(BF_X_TFD) = 1.0; b.f(BF_X_TFS) = 1.0;
+        b.f(BF_X_FNEWTHAW) = 0.0; b.f(BF_F_FROZEN) = 1.0;
+      }
     bool spunup = false;
     int step = 0;
     while (!spunup && ++step < C.max_spinup) {
@@ -384,7 +416,7 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
       mb.S[SI_X_NPPLUC * HX_TILE] = (mb.S[SI_EOS_VEGC * HX_TILE] - mb.S[SI_CUM_LUC_VA * HX_TILE]) / mb.S[SI_EOS_VEGC * HX_TILE];
       const double o0 = mb.atmos, o1 = mb.veg, o2 = mb.det, o3 = mb.soil, o4 = mb.perm,
                    o5 = mb.thawed, o6 = total_ocean(mb), o7 = mb.earth;
-      solver_year<true, false, false>(mb, C, p, ck, &rk[0][threadIdx.x], HX_BLOCK, (double)(step - 1), (double)step, true, w);
+      solver_year<true, false, false, BIOMES>(mb, C, p, ck, &rk[0][threadIdx.x], HX_BLOCK, (double)(step - 1), (double)step, true, w);
       if (mb.status) break;
       double mx = fabs(mb.atmos - o0);
       mx = fmax(mx, fabs(mb.veg - o1)); mx = fmax(mx, fabs(mb.det - o2));
@@ -396,6 +428,11 @@ hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxCons
     steps = step;
     mb.S[SI_RH_CH4 * HX_TILE] = 0.0;           /* record_state in spin-up: simpleNbox.cpp:809-814 */
     mb.S[SI_TEMPFERTS * HX_TILE] = 1.0;
+    if (BIOMES)
+      for (int ib = 0; ib < C.n_biomes; ++ib) {
+        const Biome b = biome_of(mb, ib);
+        b.f(BF_RH_CH4) = 0.0; b.f(BF_TEMPFERTS) = 1.0;
+      }
   }
   mb.S[SI_EOS_VEGC * HX_TILE] = mb.veg;        /* SimpleNbox::run first call: simpleNbox-runtime.cpp:209-213 */
   if (mb.status == 0) {
@@ -488,7 +525,7 @@ __device__ __forceinline__ void conv_prepass(const double *__restrict__ sst,
 /* ======================================================================================== */
 /* the yearly coupled step, rows r0+1 .. r1 (row = year - start_year).  TRACK = carbon tracking
  * compiled in (a second instantiation: the plain kernel carries none of its code). */
-template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT>
+template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES>
 __global__ void __launch_bounds__(HX_BLOCK, MINCTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   /* dynamic shared memory (> 48 KB): scenario slabs | row 0 | chemistry constants | RK stages */
@@ -648,7 +685,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         /* --- SimpleNbox::run + slowparameval: simpleNbox-runtime.cpp:206-227, 945-1072 --- */
         {
           const double tland = CONSTR ? STATE(SI_TLAND_C) : STATE(SI_TLAND); /* getData(land_tas) */
-          const double wf = LP_WF(p);
+          const double wf = BIOMES ? 1.0 : LP_WF(p); /* biomes weight the window mean themselves */
           BS.tland[(size_t)r * Hs] = tland; /* Tland_record[y] = land tas of year y-1 */
           if (TRACK) {
             /* tracking starts in year tracking_date (simpleNbox-runtime.cpp:215-220,
@@ -685,18 +722,28 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
             window = (wsum + wcomp) / 200;
             STATE(SI_TLAND_WSUM) = wsum; STATE(SI_TLAND_WCOMP) = wcomp;
           }
-          slow_params(mb, p, tland, r == 1, window);
+          if (BIOMES) slow_params_biomes(mb, C, p, tland, r == 1, window);
+          else slow_params(mb, p, tland, r == 1, window);
         }
 
         /* --- CarbonCycleSolver::run --- */
-        solver_year<false, TRACK, CONSTR>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
+        solver_year<false, TRACK, CONSTR, BIOMES>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
         if (mb.status) {
           d.status[m] = mb.status;
           d.fail_year[m] = y;
           break;
         }
         /* record_state: simpleNbox.cpp:789-840 */
-        {
+        if (BIOMES) {
+          for (int ib = 0; ib < C.n_biomes; ++ib) {
+            const Biome b = biome_of(mb, ib);
+            double npp, rh_fda, rh_fsa, rh_co2, rh_ch4v;
+            biome_fluxes(mb, b, npp, rh_fda, rh_fsa, rh_co2, rh_ch4v);
+            b.f(BF_RH_CH4) = rh_ch4v;
+            b.f(BF_TEMPFERTS) = b.f(BF_X_TFS);
+          }
+          mb.S[SI_RH_CH4 * HX_TILE] = biome_sum(mb, C, BF_RH_CH4);
+        } else {
           double npp, rh_fda, rh_fsa, rh_co2, rh_ch4v;
           land_fluxes<false>(mb, p, npp, rh_fda, rh_fsa, rh_co2, rh_ch4v);
           mb.S[SI_RH_CH4 * HX_TILE] = rh_ch4v;
@@ -1040,18 +1087,19 @@ cudaError_t launch_setup(const HxDev &d, const HxConst &C, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_spinup(const HxDev &d, const HxConst &C, cudaStream_t st) {
-  hx_spinup_kernel<<<d.Mpad / HX_BLOCK, HX_BLOCK, 0, st>>>(d, C, 0, -1);
+  if (d.BF) hx_spinup_kernel<true><<<d.Mpad / HX_BLOCK, HX_BLOCK, 0, st>>>(d, C, 0, -1);
+  else hx_spinup_kernel<false><<<d.Mpad / HX_BLOCK, HX_BLOCK, 0, st>>>(d, C, 0, -1);
   return cudaGetLastError();
 }
 cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cudaStream_t st) {
-  hx_spinup_kernel<<<1, HX_BLOCK, 0, st>>>(d, C, member - member % HX_BLOCK, member);
+  hx_spinup_kernel<false><<<1, HX_BLOCK, 0, st>>>(d, C, member - member % HX_BLOCK, member);
   return cudaGetLastError();
 }
-template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT = true>
+template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT = true, bool BIOMES = false>
 static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT>,
+    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
@@ -1062,7 +1110,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES>,
                                                                   HX_BLOCK, HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
     resident = sms * (per_sm > 0 ? per_sm : 1);
@@ -1072,7 +1120,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   const int grid = ntiles < resident ? ntiles : resident;
   cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
+  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
@@ -1081,6 +1129,8 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
    * every tile is resident anyway at 2 CTAs per SM the run is pure latency and the spill-free
    * 230-register build wins (17.0 vs 20.5 ms at 1 024 members).  The tracking build is bound by
    * its map traffic, not by occupancy, and spills badly at 168 registers. */
+  /* biome-split pools: one general build (constraints and every output; no tracking) */
+  if (d.BF) return launch_run_t<false, true, 2, true, true>(d, C, r0, r1, st);
   if (d.T)
     return d.constrained ? launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st)
                          : launch_run_t<true, false, HX_TRACK_CTAS>(d, C, r0, r1, st);

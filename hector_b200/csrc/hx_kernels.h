@@ -48,6 +48,9 @@ struct HxDev {
                                being run (hx_model.cuh, "Carbon tracking") */
   unsigned char *YCNT;      /* [tile][HX_SLAB_YEARS][128] stashes recorded up to each year's end */
   double *TO;               /* [track_nrec][HX_NPOOL * HX_NSRC][Mpad] recorded fractions */
+  /* biomes (null with the single global biome) */
+  const double *BP;         /* [tile][n_biomes * BP_COUNT][128] per-biome parameters */
+  double *BF;               /* [tile][n_biomes * BF_COUNT][128] per-biome pools and factors */
   uint32_t *TOK;            /* [track_nrec][HX_NPOOL][Mpad] recorded key masks */
 };
 

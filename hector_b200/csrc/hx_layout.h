@@ -140,6 +140,27 @@ enum {
 };
 #define HX_SRC_UNTRACKED 11
 
+/* Biomes (simpleNbox.cpp:201-236): with more than one, the land pools, their parameters and the
+ * yearly land factors exist once per biome.  Per-biome arrays are tiled like P and S:
+ * [tile][biome * COUNT + field][HX_TILE].  The per-member state keeps the across-biome sums
+ * (SI_VEG .. SI_THAWED, SI_RH_CH4, SI_X_NPP, SI_X_RH), which is all the other components see. */
+#define HX_MAX_BIOMES 4
+enum { /* per-biome parameters, the order of the oracle's ho_biome */
+  BP_VEG_C0 = 0, BP_DET_C0, BP_SOIL_C0, BP_PERMAFROST_C0, BP_NPP_FLUX0, BP_BETA, BP_Q10_RH,
+  BP_WARMINGFACTOR, BP_F_NPPV, BP_F_NPPD, BP_F_LITTERD, BP_RH_CH4_FRAC, BP_PF_MU, BP_PF_SIGMA,
+  BP_FPF_STATIC,
+  BP_COUNT
+};
+enum { /* per-biome state */
+  BF_VEG = 0, BF_DET, BF_SOIL, BF_PERMAFROST, BF_THAWED,
+  BF_TEMPFERTS, /* tempferts_tv of last year (sticky soil Q10 factor) */
+  BF_F_FROZEN,
+  BF_X_CO2FERT, BF_X_TFD, BF_X_TFS, BF_X_FNEWTHAW, /* this year's slow parameters */
+  BF_X_NPP, BF_X_RH,                               /* final_npp / final_rh of the last stash */
+  BF_RH_CH4,
+  BF_COUNT
+};
+
 /* ---- engine-wide constants handed to every kernel ---- */
 struct HxConst {
   int32_t start_year, end_year, nrow; /* nrow = end - start + 1 */
@@ -159,6 +180,10 @@ struct HxConst {
   double powtoheat;
   /* odeint default_step_adjuster growth at the error floor: 0.9 * pow(pow(5,-5), -1/5) */
   double rk_grow_max;
+  /* biomes: count (1 = the single "global" biome of the scalar parameters) and, for sum_map
+   * (simpleNbox.cpp:428-438, a std::map walk), the biome indices sorted by name */
+  int32_t n_biomes;
+  int32_t biome_order[HX_MAX_BIOMES];
 };
 
 /* status words live next to the state */

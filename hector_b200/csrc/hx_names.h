@@ -3,6 +3,8 @@
 #ifndef HX_NAMES_H
 #define HX_NAMES_H
 
+#include <cmath>
+
 #include "hx_layout.h"
 
 namespace hx {
@@ -43,6 +45,15 @@ static const ParamInfo kParams[PI_COUNT] = {
     {"PO3", 30.0},
     {"N0", 273.87},
     {"lo_warming_ratio", 0.0}};
+
+/* BP_* order: the per-biome inputs, named as the reference names them after the "<biome>."
+ * prefix (simpleNbox.cpp:281-396); NaN = must be given (simpleNbox-runtime.cpp:66-101), a number
+ * = the default prepareToRun fills in (:102-143) */
+static const ParamInfo kBiomeParams[BP_COUNT] = {
+    {"veg_c", NAN}, {"detritus_c", NAN}, {"soil_c", NAN}, {"permafrost_c", NAN},
+    {"npp_flux0", NAN}, {"beta", NAN}, {"q10_rh", NAN}, {"warmingfactor", 1.0},
+    {"f_nppv", NAN}, {"f_nppd", NAN}, {"f_litterd", NAN}, {"rh_ch4_frac", 0.023},
+    {"pf_mu", 1.67}, {"pf_sigma", 0.986}, {"fpf_static", 0.74}};
 
 /* parameters that influence the spin-up / alkalinity equilibration; if all of them are
  * scalars the spin-up is computed once and broadcast */

@@ -85,6 +85,11 @@ VARIABLE_COMPONENT = {
 # Outputs that need no kernel: hx_fetch derives them from the scenario series, per-member
 # parameters and recorded outputs (RF_O3_trop needs O3_concentration, RF_H2O_strat needs
 # CH4_concentration among the selected outputs)
+# per-biome inputs, set as "<biome>.<name>" once biomes are defined (simpleNbox.cpp:281-396)
+BIOME_PARAMETERS = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "npp_flux0", "beta", "q10_rh",
+                    "warmingfactor", "f_nppv", "f_nppd", "f_litterd", "rh_ch4_frac", "pf_mu",
+                    "pf_sigma", "fpf_static"]
+
 DERIVED_VARIABLES = (["RF_BC", "RF_OC", "RF_SO2", "RF_NH3", "RF_aci", "RF_vol", "RF_albedo",
                       "RF_misc", "RF_O3_trop", "RF_H2O_strat"]
                      + ["RF_%s" % h for h in HALOS] + ["Fadj%s" % h for h in HALOS]
@@ -119,11 +124,13 @@ def _dp(a):
 class Ensemble:
     def __init__(self, n_members, scenarios, member_scenario=None, start_year=1745, end_year=2300,
                  device=0, outputs=("CO2_concentration", "global_tas"), cold_newton=False,
-                 spinup=True, stream=None, tracking_date=None, track_every=1):
+                 spinup=True, stream=None, tracking_date=None, track_every=1, biomes=None):
         """scenarios: one table [nrow, 44] (RAW_SERIES columns), or a list of them;
         member_scenario: int array [n_members] of indices into that list;
         tracking_date: [core] trackingDate -- carbon tracking from that year on, recorded every
-        `track_every` years and in the end year (0: end year only)."""
+        `track_every` years and in the end year (0: end year only);
+        biomes: names of 2..4 biomes, in creation order, that replace the global one -- their
+        pools and parameters are then set as "<biome>.<name>" (BIOME_PARAMETERS) before prepare."""
         self.L = _capi.lib()
         if isinstance(scenarios, np.ndarray):
             scenarios = [scenarios]
@@ -156,7 +163,16 @@ class Ensemble:
         self._chk(self.L.hx_select_outputs(self.h, len(self.outputs), arr))
         if tracking_date is not None:
             self._chk(self.L.hx_set_tracking(self.h, int(tracking_date), int(track_every)))
+        self.biomes = list(biomes) if biomes else []
+        if self.biomes:
+            arr = (C.c_char_p * len(self.biomes))(*[b.encode() for b in self.biomes])
+            self._chk(self.L.hx_set_biomes(self.h, len(self.biomes), arr))
         self.prepared = False
+
+    def set_biome(self, biome, **values):
+        """<biome>.<name> inputs (scalars or per-member arrays), like setvar("boreal.beta", ...)"""
+        for k, v in values.items():
+            self.setvar("%s.%s" % (biome, k), v)
 
     @classmethod
     def from_ini(cls, ini_paths, n_members, member_scenario=None, device=0,

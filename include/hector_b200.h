@@ -198,6 +198,20 @@ int hx_fetch_tracking(hx_handle h, double date, double *frac, uint32_t *mask);
  * error; at most `cap` are written */
 int hx_tracking_years(hx_handle h, int32_t *years, int32_t cap);
 
+/* Biomes (simpleNbox.cpp:201-236, biome-split pools simpleNbox-runtime.cpp:399-531).  Replaces the
+ * single "global" biome by 2 .. HX_MAX_BIOMES named ones, in creation (biome_list) order; call
+ * before hx_prepare.  Afterwards the land inputs exist per biome and are set through
+ * hx_set_param_scalar / hx_set_param under the reference's names "<biome>.<name>", name in
+ *   veg_c detritus_c soil_c permafrost_c npp_flux0 beta q10_rh f_nppv f_nppd f_litterd   (required)
+ *   warmingfactor rh_ch4_frac pf_mu pf_sigma fpf_static                       (default like the reference)
+ * also before hx_prepare; the global spellings are then refused ("cannot have both global and
+ * biome-specific data").  Outputs stay the across-biome totals the reference reports for the
+ * global datum.  Not combined with carbon tracking (HX_ERR_UNSUPPORTED at hx_prepare).
+ * n_biomes <= 1 with names == NULL returns to the global biome. */
+#define HX_MAX_BIOMES 4
+int hx_set_biomes(hx_handle h, int32_t n_biomes, const char *const *names);
+int hx_biome_count(hx_handle h);
+
 /* Exchange of recorded outputs between the GPUs of one node WITHOUT kernels: every rank exports
  * its output block through CUDA IPC (64-byte handle; pass the handles around with any host-side
  * collective), opens its peers' blocks, and pulls finished year ranges with copy-engine

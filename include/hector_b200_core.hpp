@@ -182,6 +182,11 @@ inline unit_types units_of(const std::string &v) {
       {"trackingDate", U_UNITLESS}};
   for (const VarUnit &e : tab)
     if (v == e.name) return e.units;
+  /* <biome>.<name> (core.cpp:718-727): the units of <name>; "<gas>.tau" etc. are not in `tab` */
+  const size_t dot = v.find('.');
+  if (dot != std::string::npos)
+    for (const VarUnit &e : tab)
+      if (v.compare(dot + 1, std::string::npos, e.name) == 0) return e.units;
   const std::string suffix = "_constrain"; /* <gas>_constrain: halocarbon concentrations */
   if (v.size() > suffix.size() && v.compare(v.size() - suffix.size(), suffix.size(), suffix) == 0)
     return U_PPTV;
@@ -239,6 +244,21 @@ class EnsembleCore {
   void setMemberScenario(const std::vector<int32_t> &scenario_of_member) {
     need();
     chk(hx_set_member_scenario(h_, scenario_of_member.data(), (int32_t)scenario_of_member.size()));
+  }
+
+  /* Biomes: the reference grows biome_list as "<biome>.<name>" data arrive (simpleNbox.cpp:
+   * 229-236); here the list is declared once, in creation order, before any such setData
+   * (an ini file with <biome>.<name> lines declares it by itself).  getBiomeList: core.cpp:
+   * 560-563. */
+  void setBiomes(const std::vector<std::string> &names) {
+    need();
+    std::vector<const char *> p;
+    for (const std::string &s : names) p.push_back(s.c_str());
+    chk(hx_set_biomes(h_, (int32_t)p.size(), p.data()));
+    biomes_ = names;
+  }
+  std::vector<std::string> getBiomeList() const {
+    return biomes_.empty() ? std::vector<std::string>(1, "global") : biomes_;
   }
 
   /* Core::setData (core.cpp:219-268): the component name only routes in the reference */
@@ -420,6 +440,7 @@ class EnsembleCore {
   int n_, device_;
   unsigned flags_;
   bool prepared_ = false, outputs_selected_ = false;
+  std::vector<std::string> biomes_;
   double start_ = message_data::undefined(), end_ = message_data::undefined();
 };
 

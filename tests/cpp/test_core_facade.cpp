@@ -146,6 +146,38 @@ int main(int argc, char **argv) {
     std::printf("TRACK_CH4_2020=%.17g\n", (double)tc.sendMessage(M_GETDATA, "CH4_concentration", message_data(2020.0)));
   }
 
+  /* ---- biomes (tests/testthat/test_biome.R territory): two biomes that split the global
+   * pools 0.3 / 0.7, with their own beta, Q10 and warming factor -- the two_ssp245 case of
+   * tests/golden/ref_biomes.npz ---- */
+  {
+    Core bc(Logger::SEVERE, false, false);
+    bc.init();
+    INIToCoreReader(&bc).parse(ini);
+    EXPECT(bc.getBiomeList().size() == 1 && bc.getBiomeList()[0] == "global");
+    bc.setBiomes({"boreal", "tropical"});
+    EXPECT(bc.getBiomeList().size() == 2 && bc.getBiomeList()[1] == "tropical");
+    const struct { const char *name; double boreal, tropical; unit_types u; } in[] = {
+        {"npp_flux0", 56.2 * 0.3, 56.2 * 0.7, U_PGC_YR}, {"veg_c", 550.0 * 0.3, 550.0 * 0.7, U_PGC},
+        {"detritus_c", 55.0 * 0.3, 55.0 * 0.7, U_PGC},   {"soil_c", 917.0 * 0.3, 917.0 * 0.7, U_PGC},
+        {"permafrost_c", 865.0, 0.0, U_PGC},             {"f_nppv", 0.30, 0.35, U_UNITLESS},
+        {"f_nppd", 0.60, 0.60, U_UNITLESS},              {"f_litterd", 0.98, 0.95, U_UNITLESS},
+        {"beta", 0.5, 0.7, U_UNITLESS},                  {"q10_rh", 2.2, 1.6, U_UNITLESS},
+        {"warmingfactor", 1.8, 0.9, U_UNITLESS}};
+    for (const auto &e : in) {
+      bc.setData("simpleNbox", std::string("boreal.") + e.name, message_data(unitval(e.boreal, e.u)));
+      bc.setData("simpleNbox", std::string("tropical.") + e.name, message_data(unitval(e.tropical, e.u)));
+    }
+    EXPECT(throws([&] { /* units are those of the plain name */
+      bc.setData("simpleNbox", "boreal.veg_c", message_data(unitval(1.0, U_DEGC)));
+    }));
+    EXPECT(throws([&] { /* global and biome-specific data do not mix */
+      bc.setData("simpleNbox", "beta", message_data(unitval(0.5, U_UNITLESS)));
+    }));
+    bc.run();
+    std::printf("BIOME_CO2_2300=%.17g\n", (double)bc.sendMessage(M_GETDATA, "CO2_concentration", message_data(2300.0)));
+    std::printf("BIOME_VEG_2100=%.17g\n", (double)bc.sendMessage(M_GETDATA, "veg_c", message_data(2100.0)));
+  }
+
   /* ---- the batch face: 4 members, per-member S ---- */
   EnsembleCore ens(4);
   INIToCoreReader(&ens).parse(ini);

@@ -94,6 +94,11 @@ def test_facade_matches_oracle(exe):
     assert int(kv["TRACK_ROWS"]) > 31 * 11
     st, _, out = port.run_member_constrained(raw, {"CH4_constrain": {y: 1800.0 for y in range(2000, 2011)}})
     close("TRACK_CH4_2020", out[port.OUT_NAMES.index("CH4_concentration")][yr(2020)])
+    # biomes: the two_ssp245 run of the unmodified reference
+    bio = util.ref_biomes()[0]
+    assert bio["name"] == "two_ssp245"
+    close("BIOME_CO2_2300", bio["values"]["CO2_concentration"][yr(2300)])
+    close("BIOME_VEG_2100", bio["values"]["veg_c"][yr(2100)])
     # beta = 50: the oracle and the engine must agree on whether the reference aborts
     st, _, _, _, _ = port.run_member(raw, beta=50.0)
     assert (st != 0) == (kv["BETA50_FAILED"] == "1")

@@ -1,0 +1,135 @@
+"""Biome-split pools on the GPU (simpleNbox-runtime.cpp:399-531, 965-1062)
+against the committed multi-biome runs of the unmodified reference (ref_biomes.npz) and, for a
+perturbed ensemble, against the oracle."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+YEARS = np.arange(1746, 2301, dtype=np.float64)
+
+
+def _ensemble(hb, case, n, outputs):
+    ens = hb.Ensemble(n, util.scenarios()[case["scenario"]], outputs=outputs,
+                      biomes=list(case["biomes"]))
+    for b, vals in case["biomes"].items():
+        ens.set_biome(b, **vals)
+    for k, v in case["params"].items():
+        ens.setvar(k, v)
+    return ens
+
+
+@pytest.mark.parametrize("case", util.ref_biomes(), ids=lambda c: c["name"])
+def test_biomes_vs_reference_golden(case):
+    import hector_b200 as hb
+    variables = [v for v in case["values"] if v in hb.OUTPUT_VARIABLES]
+    assert {"CO2_concentration", "global_tas", "veg_c", "NPP", "RH", "ocean_timesteps"} <= set(variables)
+    ens = _ensemble(hb, case, 3, variables)
+    ens.run()
+    st, fy = ens.status()
+    n = 555
+    if case["fail_year"]:
+        assert (st == 1).all() and (fy == case["fail_year"]).all()  # HX_MEMBER_NEGATIVE
+        n = case["fail_year"] - 1746
+    else:
+        assert (st == 0).all()
+    got = ens.fetchvars(YEARS[:n], variables)
+    for v in variables:
+        ref = case["values"][v][:n]
+        if v == "ocean_timesteps":
+            assert np.array_equal(got[v][0], ref)
+            continue
+        err = float(np.max(np.abs(got[v][0] - ref) / np.maximum(np.abs(ref), util.FLOOR.get(v, 1e-3))))
+        assert err < TOL, (v, err)
+        assert np.array_equal(got[v][0], got[v][2])  # members are independent and identical
+    ens.close()
+
+
+def test_biome_ensemble_vs_oracle():
+    """per-member biome parameters (boreal.beta, tropical.q10_rh, boreal.warmingfactor) together
+    with a member-level one (S), an NBP constraint and lo_warming_ratio"""
+    import hector_b200 as hb
+    from oracle import port
+    case = util.ref_biomes()[0]
+    M = 6
+    rng = np.random.default_rng(7)
+    beta = rng.uniform(0.2, 0.8, M); q10 = rng.uniform(1.2, 2.6, M); wf = rng.uniform(0.8, 2.2, M)
+    S = rng.uniform(2.0, 4.5, M)
+    variables = ["CO2_concentration", "global_tas", "veg_c", "soil_c", "permafrost_c", "NBP",
+                 "ocean_timesteps"]
+    ens = _ensemble(hb, case, M, variables)
+    ens.setvar("boreal.beta", beta); ens.setvar("tropical.q10_rh", q10)
+    ens.setvar("boreal.warmingfactor", wf); ens.setvar("S", S)
+    ens.setvar("lo_warming_ratio", 1.4)
+    spec = {"NBP_constrain": {y: 0.4 for y in range(1990, 2011)}}
+    ens.setvar_series("NBP_constrain", list(spec["NBP_constrain"]), list(spec["NBP_constrain"].values()))
+    ens.run()
+    assert (ens.status()[0] == 0).all()
+    got = ens.fetchvars(YEARS, variables)
+    for i in range(M):
+        p = port.default_params()
+        biomes = {b: dict(v) for b, v in case["biomes"].items()}
+        biomes["boreal"]["beta"] = beta[i]; biomes["tropical"]["q10_rh"] = q10[i]
+        biomes["boreal"]["warmingfactor"] = wf[i]
+        p.set_biomes(biomes)
+        st, fy, out = port.run_member_constrained(util.scenarios()[case["scenario"]], spec, params=p,
+                                                  S=S[i], lo_warming_ratio=1.4)
+        assert st == 0
+        for v in variables:
+            ref = out[port.OUT_NAMES.index(v)]
+            if v == "ocean_timesteps":
+                assert np.array_equal(got[v][i], ref)
+                continue
+            err = float(np.max(np.abs(got[v][i] - ref) / np.maximum(np.abs(ref), util.FLOOR.get(v, 1e-3))))
+            assert err < TOL, (i, v, err)
+    # reset + rerun reproduces the run bit for bit (per-biome state is part of the snapshot)
+    ens.reset()
+    ens.run()
+    again = ens.fetchvars(YEARS, variables)
+    for v in variables:
+        assert np.array_equal(again[v], got[v])
+    ens.close()
+
+
+def test_biome_input_errors():
+    import hector_b200 as hb
+    tab = util.scenarios()["ssp245"]
+    with pytest.raises(hb.HxError):  # 'global' cannot be a biome next to others
+        hb.Ensemble(1, tab, biomes=["global", "boreal"])
+    ens = hb.Ensemble(1, tab, biomes=["boreal", "tropical"])
+    with pytest.raises(hb.HxError):  # global and biome-specific data do not mix
+        ens.setvar("beta", 0.5)
+    with pytest.raises(hb.HxError):  # unknown biome
+        ens.setvar("tundra.beta", 0.5)
+    ens.set_biome("boreal", veg_c=100.0)
+    with pytest.raises(hb.HxError) as e:  # incomplete biome data
+        ens.prepare()
+    assert "data for biome" in str(e.value)
+    ens.close()
+    with pytest.raises(hb.HxError):  # tracking + biomes: reported, not ignored
+        e2 = hb.Ensemble(1, tab, biomes=["a", "b"], tracking_date=1800)
+        case = util.ref_biomes()[2]
+        for b, vals in zip(["a", "b"], case["biomes"].values()):
+            e2.set_biome(b, **vals)
+        e2.prepare()
+
+
+def test_biomes_from_ini(tmp_path):
+    """newcore(ini) with <biome>.<name> lines: the library's ini reader defines the biomes"""
+    import hector_b200 as hb
+    from tests.test_ini_reader_cpu import biome_ini
+    case = util.ref_biomes()[1]  # three biomes, creation order != name order
+    variables = ["CO2_concentration", "global_tas", "soil_c", "permafrost_c"]
+    ens = hb.Ensemble.from_ini(biome_ini(tmp_path, case), 2, outputs=variables)
+    for k, v in case["params"].items():
+        ens.setvar(k, v)
+    ens.run()
+    assert (ens.status()[0] == 0).all()
+    got = ens.fetchvars(YEARS, variables)
+    for v in variables:
+        ref = case["values"][v]
+        err = float(np.max(np.abs(got[v][0] - ref) / np.maximum(np.abs(ref), util.FLOOR.get(v, 1e-3))))
+        assert err < TOL, (v, err)
+    ens.close()

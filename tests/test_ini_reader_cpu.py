@@ -58,11 +58,20 @@ def test_unsupported_inputs_are_reported(tmp_path):
     L = need_lib()
     src = open(os.path.join(input_dir(), "hector_ssp245.ini")).read()
     d = input_dir()
-    bad = tmp_path / "biome.ini"
+    bad = tmp_path / "biome.ini"  # global and biome-specific data: simpleNbox-runtime.cpp:66-69
     bad.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
         "[simpleNbox]", "[simpleNbox]\nboreal.veg_c=100"))
-    assert L.hx_ini_read(str(bad).encode(), None, None, None, 0) == -4
-    assert b"biome" in L.hx_last_error(None)
+    assert L.hx_ini_read(str(bad).encode(), None, None, None, 0) == -1
+    assert b"both global and biome-specific" in L.hx_last_error(None)
+    bad4 = tmp_path / "biome_unknown.ini"
+    bad4.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
+        "[simpleNbox]", "[simpleNbox]\nboreal.not_a_pool=100"))
+    assert L.hx_ini_read(str(bad4).encode(), None, None, None, 0) == -1
+    assert b"Unknown variable" in L.hx_last_error(None)
+    chem = tmp_path / "spinup_chem.ini"
+    chem.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
+        "[ocean]", "[ocean]\nspinup_chem=1"))
+    assert L.hx_ini_read(str(chem).encode(), None, None, None, 0) == -4
     bad3 = tmp_path / "lo.ini"
     bad3.write_text(src.replace("csv:tables/", "csv:%s/tables/" % d).replace(
         "[temperature]", "[temperature]\nlo_warming_ratio=1.6"))
@@ -93,4 +102,31 @@ def test_constraint_inputs_are_read(tmp_path):
     L = need_lib()
     y0, y1 = C.c_int32(), C.c_int32()
     assert L.hx_ini_read(constrained_ini(tmp_path).encode(), C.byref(y0), C.byref(y1), None, 0) == 0
+    assert (y0.value, y1.value) == (1745, 2300)
+
+
+def biome_ini(tmp_path, case):
+    """the shipped ini of the case's scenario with the global land inputs replaced by
+    <biome>.<name> lines -- what tests/golden/make_golden.py fed the reference"""
+    d = input_dir()
+    drop = {"npp_flux0", "veg_c", "detritus_c", "soil_c", "permafrost_c", "f_nppv", "f_nppd",
+            "f_litterd", "beta", "q10_rh"}
+    lines = []
+    for line in open(os.path.join(d, "hector_%s.ini" % case["scenario"])).read().splitlines():
+        if line.split("=")[0].strip() in drop:
+            continue
+        lines.append(line.replace("csv:tables/", "csv:%s/tables/" % d))
+        if line.strip() == "[simpleNbox]":
+            for b, vals in case["biomes"].items():
+                lines += ["%s.%s=%r" % (b, k, float(v)) for k, v in vals.items()]
+    p = tmp_path / (case["name"] + ".ini")
+    p.write_text("\n".join(lines) + "\n")
+    return str(p)
+
+
+def test_biome_ini_parses(tmp_path):
+    L = need_lib()
+    y0, y1 = C.c_int32(), C.c_int32()
+    ini = biome_ini(tmp_path, util.ref_biomes()[1])
+    assert L.hx_ini_read(ini.encode(), C.byref(y0), C.byref(y1), None, 0) == 0, L.hx_last_error(None)
     assert (y0.value, y1.value) == (1745, 2300)
