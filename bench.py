@@ -395,8 +395,8 @@ def main():
             for j, nme in enumerate(PARAMS):
                 e.setvar(nme, pinned_in[j].numpy())      # host -> device
             e.reset()                                    # set-up + spin-up (parameters changed)
-            # run + device -> host of every year of both variables; the copies of a finished
-            # run segment overlap the next segment's computation (hx_run_stream)
+            # run + device -> host of every year of both variables; a slab's rows are copied
+            # while the kernel computes the later slabs (hx_run_stream)
             e.run_stream(e2e_vars, outs=e2e_outs, segments=args.e2e_segments)
 
         e2e_ms, _ = timed(ens, step_e2e, max(2, args.steps // 2), 1, False)
@@ -405,7 +405,8 @@ def main():
                "h2d_bytes_per_step": int(4 * M * 8), "d2h_bytes_per_step": int(2 * M * YEARS * 8),
                "ms_per_step": e2e_ms,
                "includes": "4 parameter vectors H2D, set-up + spin-up, run, CO2+Tgav x 555 yr D2H "
-                           "(hx_run_stream: %d run segments, copies overlapped)" % args.e2e_segments}
+                           "(hx_run_stream: one launch of the persistent run kernel, every "
+                           "16-year slab's rows copied out as the kernel reports it complete)"}
 
     # ---- BASELINE.json configs[1]: the 1 024-member ensemble on one GPU ----
     small = None

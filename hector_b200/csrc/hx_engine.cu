@@ -475,6 +475,59 @@ struct Engine {
     return cudaSuccess;
   }
 
+  /* hx_run_stream, untracked: see there.  slab_done lives in mapped pinned memory; the kernel
+   * bumps slab_done[s] once per tile that finished slab s (after a system-scope fence), this
+   * thread polls it and queues the slab's device-to-host copies on the copy stream. */
+  unsigned *h_slab_done = nullptr, *d_slab_done = nullptr;
+  int slab_done_cap = 0;
+  int run_streamed(int r0, int r1, int n_vars, const int *slot, double *const *outs) {
+    const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
+    if (nslab > slab_done_cap) {
+      if (h_slab_done) cudaFreeHost(h_slab_done);
+      h_slab_done = nullptr;
+      slab_done_cap = 0;
+      CUDA_TRY(cudaHostAlloc((void **)&h_slab_done, (size_t)nslab * sizeof(unsigned), cudaHostAllocMapped));
+      CUDA_TRY(cudaHostGetDevicePointer((void **)&d_slab_done, h_slab_done, 0));
+      slab_done_cap = nslab;
+    }
+    memset(h_slab_done, 0, (size_t)nslab * sizeof(unsigned));
+    CUDA_TRY(cudaMemsetAsync(d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), stream));
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    HxDev ds = d;
+    ds.slab_done = d_slab_done;
+    CUDA_TRY(hx::launch_run(ds, C, r0, r1, stream));
+    CUDA_TRY(cudaEventRecord(ev1, stream));
+    const unsigned ntiles = 1u; /* the flag is raised once, by the slab's last tile */
+    volatile unsigned *done = h_slab_done;
+    bool kernel_over = false;
+    for (int s = 0; s < nslab; ++s) {
+      unsigned spins = 0;
+      while (done[s] < ntiles && !kernel_over) {
+        if ((++spins & 0xfffu) == 0) {
+          /* the kernel may have stopped without finishing (a launch or device error) */
+          const cudaError_t q = cudaStreamQuery(stream);
+          if (q == cudaSuccess) kernel_over = true;
+          else if (q != cudaErrorNotReady) return fail(HX_ERR_CUDA, std::string("run kernel: ") + cudaGetErrorString(q));
+        }
+      }
+      if (done[s] < ntiles)
+        return fail(HX_ERR_CUDA, "hx_run_stream: the run kernel ended without completing every slab");
+      const int ra = r0 + s * HX_SLAB_YEARS, rb = std::min(r1, ra + HX_SLAB_YEARS);
+      for (int v = 0; v < n_vars; ++v) {
+        const double *src = d_out + ((size_t)slot[v] * (nrow - 1) + ra) * Mpad;
+        double *dst = outs[v] + (size_t)(ra - r0) * M;
+        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)M * sizeof(double), src, (size_t)Mpad * sizeof(double),
+                                   (size_t)M * sizeof(double), (size_t)(rb - ra),
+                                   cudaMemcpyDeviceToHost, copy_stream));
+      }
+    }
+    CUDA_TRY(cudaEventRecord(ev_copy, copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(stream, ev_copy, 0));
+    CUDA_TRY(cudaStreamSynchronize(copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return HX_OK;
+  }
+
   int run_setup_and_spinup() {
     if (tables_dirty) {
       int rc = upload_tables();
@@ -711,6 +764,7 @@ int hx_destroy(hx_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->free_device();
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->h_slab_done) cudaFreeHost(h->h_slab_done);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   hx_ipc_close(h);
@@ -1078,7 +1132,7 @@ int hx_prepare(hx_handle h) {
       cudaMalloc(&h->d_fail_year, Mp * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc(&h->d_spinup_steps, Mp * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc(&h->d_counters, HX_NCOUNTERS * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMalloc(&h->d_sched, (block_scen.size() + 1) * sizeof(unsigned)) != cudaSuccess ||
+      cudaMalloc(&h->d_sched, (block_scen.size() + 1 + nrow / HX_SLAB_YEARS + 2) * sizeof(unsigned)) != cudaSuccess ||
       cudaMalloc(&h->d_dev_of_api, (size_t)M * sizeof(int32_t)) != cudaSuccess ||
       (nb > 1 &&
        (cudaMalloc(&h->d_BP, (size_t)nb * BP_COUNT * Mp * sizeof(double)) != cudaSuccess ||
@@ -1128,6 +1182,8 @@ int hx_prepare(hx_handle h) {
   d.constrained = any_constraint ? 1 : 0; /* refined in run_setup_and_spinup */
   for (int i = 0; i < OUT_COUNT; ++i) d.out_slot[i] = -1;
   for (int s = 0; s < nsel; ++s) d.out_slot[h->out_sel[s]] = s;
+  d.n_out = nsel;
+  d.slab_done = nullptr;
   d.out_minimal = 1;
   for (int s = 0; s < nsel; ++s)
     if (h->out_sel[s] != OUT_CO2 && h->out_sel[s] != OUT_TAS) d.out_minimal = 0;
@@ -1252,17 +1308,30 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
     if (rc) return rc;
   }
   if (segments < 1) segments = 1;
+  if (segments > 1 && !h->d_T) {
+    /* ONE launch of the persistent run kernel; the slabs' output rows are copied out as the
+     * kernel reports them complete (no per-segment launch tails, only the last slab's copy is
+     * exposed).  Tracked runs keep the segmented form: their slabs are separate launches. */
+    int rc = h->run_streamed(r0, r1, n_vars, slot.data(), outs);
+    if (rc != HX_OK) return rc;
+    h->cur_row = r1;
+    return HX_OK;
+  }
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
   if (segments > nslab) segments = nslab;
   cudaStream_t st = h->stream;
   const int ny = r1 - r0; /* columns... rows of the caller's [year][member] blocks */
   cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st);
   cudaEventRecord(h->ev0, st);
+  /* Segment lengths halve: a segment's device-to-host copy hides behind the next segment's
+   * computation (the copy engine is ~3x faster than the run per year), so only the LAST
+   * segment's copy is exposed -- keep that one short instead of splitting evenly. */
   int ra = r0;
+  int slabs_left = nslab;
   for (int sg = 0; sg < segments; ++sg) {
-    const int rb = (sg == segments - 1)
-                       ? r1
-                       : r0 + (int)(((long long)nslab * (sg + 1)) / segments) * HX_SLAB_YEARS;
+    const int take = (sg == segments - 1) ? slabs_left : (slabs_left + 1) / 2;
+    slabs_left -= take;
+    const int rb = (sg == segments - 1 || slabs_left == 0) ? r1 : ra + take * HX_SLAB_YEARS;
     if (rb <= ra) continue;
     cudaError_t e = h->launch_rows(ra, rb);
     if (e == cudaSuccess && !h->out_sel.empty())

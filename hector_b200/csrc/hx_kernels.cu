@@ -525,6 +525,13 @@ __device__ __forceinline__ void conv_prepass(const double *__restrict__ sst,
 /* ======================================================================================== */
 /* the yearly coupled step, rows r0+1 .. r1 (row = year - start_year).  TRACK = carbon tracking
  * compiled in (a second instantiation: the plain kernel carries none of its code). */
+/* failed members report NaN from the failing year on (the reference stops producing output) */
+__device__ __noinline__ void nan_fill_rows(const HxDev &d, int nyears, int m, int first, int last) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int s = 0; s < d.n_out; ++s)
+    for (int yi = first; yi < last; ++yi) d.out[((size_t)s * nyears + yi) * d.Mpad + m] = nan;
+}
+
 template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES>
 __global__ void __launch_bounds__(HX_BLOCK, MINCTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
@@ -956,12 +963,27 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
       if (mb.status == 0) store_member(BS, mb);
       else ++failed;
     }
+    if (d.slab_done) {
+      /* streaming run: the slab's output rows leave for the host as soon as every tile has
+       * finished it, so a failed member's NaNs are written here, not by a pass after the run */
+      const int stn = d.status[m];
+      if (stn > 0) nan_fill_rows(d, C.nrow - 1, m, max(d.fail_year[m] - C.start_year - 1, base), rend);
+    }
     /* publish the tile's state: make this CTA's global stores visible, then release */
     __threadfence();
     __syncthreads(); /* also: everyone is done with slab[0] / row0 before they are refilled */
     if (tid == 0) {
       const unsigned done = (unsigned)s + 1u;
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + tile), "r"(done) : "memory");
+      if (d.slab_done) {
+        /* the last tile to finish slab s raises the host's flag: a plain store into mapped
+         * memory after a system-scope fence (the tiles are counted in device memory) */
+        unsigned *slab_count = d.sched + 1 + ntiles;
+        if (atomicAdd(slab_count + s, 1u) == (unsigned)ntiles - 1u) {
+          __threadfence_system();
+          *(volatile unsigned *)(d.slab_done + s) = 1u;
+        }
+      }
     }
   }
   flush_work(d, w, years_done, failed);
@@ -1118,7 +1140,8 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   /* persistent CTAs: never more than can be co-resident (an item may wait on another CTA) */
   const int ntiles = d.Mpad / HX_BLOCK;
   const int grid = ntiles < resident ? ntiles : resident;
-  cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1) * sizeof(unsigned), st);
+  const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
+  cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1 + nslab) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
   hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
   return cudaGetLastError();

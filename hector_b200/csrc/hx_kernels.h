@@ -37,10 +37,15 @@ struct HxDev {
   int32_t *fail_year;       /* [Mpad] */
   int32_t *spinup_steps;    /* [Mpad] */
   unsigned long long *counters; /* [HX_NCOUNTERS] */
-  unsigned *sched;              /* [1 + Mpad / HX_BLOCK]: work-queue ticket, per-tile progress */
+  unsigned *sched;              /* [1 + tiles + slabs]: work-queue ticket, per-tile progress, tiles done per slab */
   int32_t out_slot[OUT_COUNT];  /* output id -> slot in `out`, -1 = not recorded */
   int32_t constrained;      /* some scenario carries a CO2 / CH4 / RF_tot / tas constraint */
   int32_t out_minimal;      /* only CO2_concentration and/or global_tas are recorded */
+  int32_t n_out;            /* recorded outputs (slots of `out`) */
+  /* hx_run_stream: [slabs of the launch] in mapped host memory, set to 1 when every tile has
+   * finished the slab -- the host copies a slab's output rows out while later slabs still run
+   * (null: off) */
+  unsigned *slab_done;
   /* carbon tracking (null unless a tracking date was set) */
   double *T;                /* [tile][TS_COUNT * HX_NSRC][128] source fractions */
   uint32_t *TK;             /* [tile][TS_COUNT][128] key masks */

@@ -155,8 +155,12 @@ int hx_reset(hx_handle h);                   /* back to the post-spin-up state a
 int hx_reset_date(hx_handle h, double date);
 int hx_synchronize(hx_handle h);
 /* hx_run + fetch of every year of the segment in one call, with the device-to-host copies
- * overlapped with the computation (the run is cut into `segments` launches; each finished
- * segment streams out over the copy engine while the next one computes).  outs[v] receives
+ * overlapped with the computation.  segments > 1: ONE launch of the persistent run kernel; the
+ * kernel raises a flag in mapped host memory when every tile has finished a 16-year slab, and
+ * the calling thread queues that slab's rows on the copy engine while later slabs compute, so
+ * only the last slab's copy is exposed (a failed member's NaNs are written by the kernel).
+ * Carbon-tracking runs are cut into `segments` launches of halving length instead (their slabs
+ * are separate launches already); segments = 1 runs, then copies.  outs[v] receives
  * names[v] YEAR-major: outs[v][(year - first_year) * n_members + member], first_year = the date
  * before the call + 1 -- the long format R's fetchvars returns (R/messages.R:46-88), and the
  * device layout, so no transpose stands between the kernel and the copy.  Use pinned host
