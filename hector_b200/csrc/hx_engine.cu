@@ -260,9 +260,18 @@ struct Engine {
     return out;
   }
 
-  static int find_out(const char *name) {
+  /* output id of a name: OUT_* or, with biomes, "<biome>.<name>" -> OUT_COUNT + ... */
+  int find_out(const char *name) const {
     for (int i = 0; i < OUT_COUNT; ++i)
       if (!strcmp(hx::kOutNames[i], name)) return i;
+    const char *dot = name ? strchr(name, '.') : nullptr;
+    if (dot && n_biomes > 1) {
+      const std::string biome(name, dot - name);
+      for (int ib = 0; ib < n_biomes; ++ib)
+        if (biome_names[ib] == biome)
+          for (int k = 0; k < BO_COUNT; ++k)
+            if (!strcmp(hx::kBiomeOutNames[k], dot + 1)) return OUT_COUNT + ib * BO_COUNT + k;
+    }
     return -1;
   }
 
@@ -881,6 +890,10 @@ int hx_set_biomes(hx_handle h, int32_t n_biomes, const char *const *names) {
   }
   h->n_biomes = n_biomes;
   h->biome_names = nm;
+  /* per-biome outputs selected under an earlier biome list no longer mean anything */
+  h->out_sel.erase(std::remove_if(h->out_sel.begin(), h->out_sel.end(),
+                                  [](int id) { return id >= OUT_COUNT; }),
+                   h->out_sel.end());
   for (int ib = 0; ib < HX_MAX_BIOMES; ++ib)
     for (int f = 0; f < BP_COUNT; ++f) {
       h->bscalar[ib][f] = hx::kBiomeParams[f].dflt;
@@ -1001,7 +1014,7 @@ int hx_select_outputs(hx_handle h, int32_t n, const char *const *names) {
   if (h->prepared) return h->fail(HX_ERR_STATE, "outputs must be selected before hx_prepare");
   std::vector<int> sel;
   for (int i = 0; i < n; ++i) {
-    const int id = Engine::find_out(names[i]);
+    const int id = h->find_out(names[i]);
     if (id < 0) return h->fail(HX_ERR_ARG, std::string("unknown output variable: ") + names[i]);
     if (std::find(sel.begin(), sel.end(), id) == sel.end()) sel.push_back(id);
   }
@@ -1180,7 +1193,7 @@ int hx_prepare(hx_handle h) {
   h->ycnt_bytes = block_scen.size() * hx::track_ycnt_bytes_per_tile();
   h->tables_constrained = any_constraint;
   d.constrained = any_constraint ? 1 : 0; /* refined in run_setup_and_spinup */
-  for (int i = 0; i < OUT_COUNT; ++i) d.out_slot[i] = -1;
+  for (int i = 0; i < HX_OUT_IDS; ++i) d.out_slot[i] = -1;
   for (int s = 0; s < nsel; ++s) d.out_slot[h->out_sel[s]] = s;
   d.n_out = nsel;
   d.slab_done = nullptr;
@@ -1293,7 +1306,7 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
   if (r1 <= r0) return HX_OK;
   std::vector<int> slot(n_vars);
   for (int v = 0; v < n_vars; ++v) {
-    const int id = Engine::find_out(names[v]);
+    const int id = h->find_out(names[v]);
     if (id < 0 || h->d.out_slot[id] < 0)
       return h->fail(HX_ERR_ARG, std::string("output not recorded: ") + (names[v] ? names[v] : "?"));
     if (!outs[v]) return HX_ERR_ARG;
@@ -1419,7 +1432,7 @@ int hx_ipc_close(hx_handle h) {
 int hx_ipc_pull(hx_handle h, const char *name, int32_t year_a, int32_t year_b, double *dst_dev) {
   if (!h || !name || !dst_dev) return HX_ERR_ARG;
   if (h->peer_out.empty()) return h->fail(HX_ERR_STATE, "hx_ipc_pull before hx_ipc_open");
-  const int id = Engine::find_out(name);
+  const int id = h->find_out(name);
   if (id < 0 || h->d.out_slot[id] < 0) return h->fail(HX_ERR_ARG, std::string("output not recorded: ") + name);
   const int ra = year_a - h->cfg.start_year - 1, rb = year_b - h->cfg.start_year; /* rows [ra, rb) */
   if (ra < 0 || rb > h->nrow - 1 || rb <= ra) return h->fail(HX_ERR_ARG, "hx_ipc_pull: bad year range");
@@ -1492,7 +1505,7 @@ int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates
     int rc = HX_OK;
     if (h->fetch_derived(name, dates, n_dates, out, rc)) return rc;
   }
-  const int id = Engine::find_out(name);
+  const int id = h->find_out(name);
   if (id < 0) return h->fail(HX_ERR_ARG, std::string("unknown output variable: ") + name);
   const int slot = h->d.out_slot[id];
   if (slot < 0) return h->fail(HX_ERR_ARG, std::string(name) + " was not selected with hx_select_outputs");
@@ -1612,7 +1625,7 @@ int hx_output_device(hx_handle h, const char *name, const double **dev_ptr, int6
                      int32_t *n_years) {
   if (!h || !name || !dev_ptr) return HX_ERR_ARG;
   if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_output_device before hx_prepare");
-  const int id = Engine::find_out(name);
+  const int id = h->find_out(name);
   if (id < 0 || h->d.out_slot[id] < 0) return h->fail(HX_ERR_ARG, std::string("output not recorded: ") + name);
   *dev_ptr = h->d_out + (size_t)h->d.out_slot[id] * (h->nrow - 1) * h->Mpad;
   if (member_stride) *member_stride = h->Mpad;

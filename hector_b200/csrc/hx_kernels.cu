@@ -935,6 +935,15 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_FLUX_INTERIOR, hf_int_out);
         EMIT(OUT_TIMESTEPS, (double)mb.timesteps);
         }
+        if (BIOMES) { /* <biome>.<name>: the biome's own pools and final NPP / RH */
+          const int bf[BO_COUNT] = {BF_VEG, BF_DET, BF_SOIL, BF_PERMAFROST, BF_THAWED, BF_X_NPP, BF_X_RH};
+          for (int ib = 0; ib < C.n_biomes; ++ib)
+            for (int k = 0; k < BO_COUNT; ++k) {
+              const int slot_ = d.out_slot[OUT_COUNT + ib * BO_COUNT + k];
+              if (slot_ >= 0)
+                d.out[((size_t)slot_ * nyears_total + yi) * Mp + m] = biome_of(mb, ib).f(bf[k]);
+            }
+        }
 #undef EMIT
         }
       }

@@ -38,7 +38,8 @@ struct HxDev {
   int32_t *spinup_steps;    /* [Mpad] */
   unsigned long long *counters; /* [HX_NCOUNTERS] */
   unsigned *sched;              /* [1 + tiles + slabs]: work-queue ticket, per-tile progress, tiles done per slab */
-  int32_t out_slot[OUT_COUNT];  /* output id -> slot in `out`, -1 = not recorded */
+  int32_t out_slot[HX_OUT_IDS]; /* output id -> slot in `out`, -1 = not recorded; ids from
+                                   OUT_COUNT on are the per-biome outputs */
   int32_t constrained;      /* some scenario carries a CO2 / CH4 / RF_tot / tas constraint */
   int32_t out_minimal;      /* only CO2_concentration and/or global_tas are recorded */
   int32_t n_out;            /* recorded outputs (slots of `out`) */

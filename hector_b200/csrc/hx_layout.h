@@ -160,6 +160,10 @@ enum { /* per-biome state */
   BF_RH_CH4,
   BF_COUNT
 };
+/* per-biome outputs "<biome>.<name>" (getData with a biome prefix, simpleNbox.cpp:533-697):
+ * output id OUT_COUNT + biome * BO_COUNT + k */
+enum { BO_VEG = 0, BO_DET, BO_SOIL, BO_PERMAFROST, BO_THAWED, BO_NPP, BO_RH, BO_COUNT };
+#define HX_OUT_IDS (OUT_COUNT + HX_MAX_BIOMES * BO_COUNT)
 
 /* ---- engine-wide constants handed to every kernel ---- */
 struct HxConst {

@@ -55,6 +55,10 @@ static const ParamInfo kBiomeParams[BP_COUNT] = {
     {"f_nppv", NAN}, {"f_nppd", NAN}, {"f_litterd", NAN}, {"rh_ch4_frac", 0.023},
     {"pf_mu", 1.67}, {"pf_sigma", 0.986}, {"fpf_static", 0.74}};
 
+/* BO_* order: per-biome outputs and the BF_* field each one reports */
+static const char *const kBiomeOutNames[BO_COUNT] = {"veg_c", "detritus_c", "soil_c",
+                                                     "permafrost_c", "thawedp_c", "NPP", "RH"};
+
 /* parameters that influence the spin-up / alkalinity equilibration; if all of them are
  * scalars the spin-up is computed once and broadcast */
 static const int kSpinupParams[] = {

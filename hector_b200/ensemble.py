@@ -90,6 +90,9 @@ BIOME_PARAMETERS = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "npp_flux0"
                     "warmingfactor", "f_nppv", "f_nppd", "f_litterd", "rh_ch4_frac", "pf_mu",
                     "pf_sigma", "fpf_static"]
 
+# per-biome outputs, selected and fetched as "<biome>.<name>" (simpleNbox.cpp:533-697)
+BIOME_OUTPUTS = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c", "NPP", "RH"]
+
 DERIVED_VARIABLES = (["RF_BC", "RF_OC", "RF_SO2", "RF_NH3", "RF_aci", "RF_vol", "RF_albedo",
                       "RF_misc", "RF_O3_trop", "RF_H2O_strat"]
                      + ["RF_%s" % h for h in HALOS] + ["Fadj%s" % h for h in HALOS]
@@ -99,6 +102,8 @@ DERIVED_VARIABLES = (["RF_BC", "RF_OC", "RF_SO2", "RF_NH3", "RF_aci", "RF_vol", 
 def variable_units(v):
     if v in VARIABLE_UNITS:
         return VARIABLE_UNITS[v]
+    if "." in v and v.split(".", 1)[1] in BIOME_OUTPUTS:  # <biome>.<name>
+        return VARIABLE_UNITS[v.split(".", 1)[1]]
     if v.startswith("RF_") or v.startswith("Fadj"):
         return "W/m2"
     if v.endswith("_concentration"):
@@ -158,15 +163,15 @@ class Ensemble:
             ms = np.ascontiguousarray(member_scenario, dtype=np.int32)
             self._chk(self.L.hx_set_member_scenario(
                 self.h, ms.ctypes.data_as(C.POINTER(C.c_int32)), len(ms)))
+        self.biomes = list(biomes) if biomes else []
+        if self.biomes:  # before the outputs: "<biome>.<name>" outputs name a known biome
+            arr = (C.c_char_p * len(self.biomes))(*[b.encode() for b in self.biomes])
+            self._chk(self.L.hx_set_biomes(self.h, len(self.biomes), arr))
         self.outputs = list(outputs)
         arr = (C.c_char_p * len(self.outputs))(*[s.encode() for s in self.outputs])
         self._chk(self.L.hx_select_outputs(self.h, len(self.outputs), arr))
         if tracking_date is not None:
             self._chk(self.L.hx_set_tracking(self.h, int(tracking_date), int(track_every)))
-        self.biomes = list(biomes) if biomes else []
-        if self.biomes:
-            arr = (C.c_char_p * len(self.biomes))(*[b.encode() for b in self.biomes])
-            self._chk(self.L.hx_set_biomes(self.h, len(self.biomes), arr))
         self.prepared = False
 
     def set_biome(self, biome, **values):

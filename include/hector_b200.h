@@ -209,8 +209,10 @@ int hx_tracking_years(hx_handle h, int32_t *years, int32_t cap);
  *   veg_c detritus_c soil_c permafrost_c npp_flux0 beta q10_rh f_nppv f_nppd f_litterd   (required)
  *   warmingfactor rh_ch4_frac pf_mu pf_sigma fpf_static                       (default like the reference)
  * also before hx_prepare; the global spellings are then refused ("cannot have both global and
- * biome-specific data").  Outputs stay the across-biome totals the reference reports for the
- * global datum.  Not combined with carbon tracking (HX_ERR_UNSUPPORTED at hx_prepare).
+ * biome-specific data").  The plain output names stay the across-biome totals the reference
+ * reports for the global datum; "<biome>.<name>", name in veg_c detritus_c soil_c permafrost_c
+ * thawedp_c NPP RH, selects and fetches one biome's own (hx_select_outputs after hx_set_biomes).
+ * Not combined with carbon tracking (HX_ERR_UNSUPPORTED at hx_prepare).
  * n_biomes <= 1 with names == NULL returns to the global biome. */
 #define HX_MAX_BIOMES 4
 int hx_set_biomes(hx_handle h, int32_t n_biomes, const char *const *names);

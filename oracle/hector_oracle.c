@@ -1778,6 +1778,18 @@ int ho_run_member(const ho_params *p, const double *raw, int run_to, double *out
                           NULL, NULL);
 }
 
+/* per-biome outputs of the next run on this thread (ho_run_member_biomes) */
+static __thread double *g_bio_out = NULL;
+
+int ho_run_member_biomes(const ho_params *p, const double *raw, const ho_constraints *cn, int run_to,
+                         double *out, int nyears_cap, int *fail_year, double *bio_out) {
+  g_bio_out = bio_out;
+  const int st = ho_run_member_ex(p, raw, cn, run_to, out, nyears_cap, fail_year, NULL, NULL, 9999,
+                                  NULL, NULL);
+  g_bio_out = NULL;
+  return st;
+}
+
 int ho_run_member_tracked(const ho_params *p, const double *raw, int run_to, double *out,
                           int nyears_cap, int *fail_year, ho_counters *counters,
                           ho_spinup_state *spin, int tracking_date, double *track_frac,
@@ -1995,6 +2007,14 @@ int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints
     if (out && r - 1 < nyears_cap) {
       const int i = r - 1;
 #define OUT(k, v) out[(size_t)(k) * nyears_cap + i] = (v)
+      if (g_bio_out) /* getData("<biome>.<name>"), simpleNbox.cpp:533-697 */
+        for (int ib = 0; ib < m->nb; ++ib) {
+          const bio_t *b = &m->bio[ib];
+          const double v[HO_NBIOME_OUT] = {b->veg_c, b->detritus_c, b->soil_c, b->permafrost_c,
+                                           b->thawed_permafrost_c, b->final_npp, b->final_rh};
+          for (int k = 0; k < HO_NBIOME_OUT; ++k)
+            g_bio_out[((size_t)ib * HO_NBIOME_OUT + k) * nyears_cap + i] = v[k];
+        }
       OUT(HO_OUT_CO2, CO2_conc);
       OUT(HO_OUT_TAS, m->tas);
       OUT(HO_OUT_RF_TOT, rf_tot_rel);

@@ -192,6 +192,12 @@ int ho_run_member_ex(const ho_params *p, const double *raw, const ho_constraints
                      double *out, int nyears_cap, int *fail_year, ho_counters *counters,
                      ho_spinup_state *spin, int tracking_date, double *track_frac,
                      uint32_t *track_mask);
+/* a run that also reports every biome's own pools and final fluxes:
+ * bio_out[biome][k][nyears_cap], k = veg_c detritus_c soil_c permafrost_c thawedp_c NPP RH
+ * (what getData("<biome>.<name>", date) returns, simpleNbox.cpp:533-697) */
+#define HO_NBIOME_OUT 7
+int ho_run_member_biomes(const ho_params *p, const double *raw, const ho_constraints *cn, int run_to,
+                         double *out, int nyears_cap, int *fail_year, double *bio_out);
 double ho_gas_series_constrained(const ho_params *p, const double *raw, const ho_constraints *cn,
                                  double *n2o, double *halo_rf);
 

@@ -246,6 +246,28 @@ def run_member_constrained(raw, spec, params=None, run_to=-1, tracking_date=None
     return st, fy.value, out, frac, mask
 
 
+BIOME_OUT_NAMES = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c", "NPP", "RH"]
+
+
+def run_member_biomes(raw, params, spec=None, run_to=-1, **over):
+    """a multi-biome run (params.set_biomes) -> (status, fail_year, out, bio_out[nb, 7, nyears]);
+    bio_out[b, k] = BIOME_OUT_NAMES[k] of biome b in creation order"""
+    p = params
+    for k, v in over.items():
+        setattr(p, k, v)
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    nrow = p.end_year - p.start_year + 1
+    cn, keep = make_constraints(nrow, p.start_year, spec or {})
+    ny = (p.end_year if run_to < 0 else run_to) - p.start_year
+    out = np.empty((NOUT, ny))
+    bio = np.full((max(p.n_biomes, 1), len(BIOME_OUT_NAMES), ny), np.nan)
+    fy = C.c_int(0)
+    f = lib().ho_run_member_biomes
+    f.restype = C.c_int
+    st = f(C.byref(p), _dp(raw), C.byref(cn), run_to, _dp(out), ny, C.byref(fy), _dp(bio))
+    return st, fy.value, out, bio
+
+
 def run_member_tracked(raw, tracking_date, params=None, run_to=-1, **over):
     """run_member with carbon tracking from `tracking_date`:
     -> (status, fail_year, out, frac[nyears, 11, 12] (NaN before tracking), mask[nyears, 11])"""

@@ -156,6 +156,8 @@ int main(int argc, char **argv) {
     EXPECT(bc.getBiomeList().size() == 1 && bc.getBiomeList()[0] == "global");
     bc.setBiomes({"boreal", "tropical"});
     EXPECT(bc.getBiomeList().size() == 2 && bc.getBiomeList()[1] == "tropical");
+    bc.selectOutputs({"CO2_concentration", "veg_c", "boreal.veg_c", "tropical.veg_c"});
+    EXPECT(throws([&] { bc.selectOutputs({"tundra.veg_c"}); })); /* not a biome */
     const struct { const char *name; double boreal, tropical; unit_types u; } in[] = {
         {"npp_flux0", 56.2 * 0.3, 56.2 * 0.7, U_PGC_YR}, {"veg_c", 550.0 * 0.3, 550.0 * 0.7, U_PGC},
         {"detritus_c", 55.0 * 0.3, 55.0 * 0.7, U_PGC},   {"soil_c", 917.0 * 0.3, 917.0 * 0.7, U_PGC},
@@ -176,6 +178,12 @@ int main(int argc, char **argv) {
     bc.run();
     std::printf("BIOME_CO2_2300=%.17g\n", (double)bc.sendMessage(M_GETDATA, "CO2_concentration", message_data(2300.0)));
     std::printf("BIOME_VEG_2100=%.17g\n", (double)bc.sendMessage(M_GETDATA, "veg_c", message_data(2100.0)));
+    const unitval bv = bc.sendMessage(M_GETDATA, "boreal.veg_c", message_data(2100.0));
+    EXPECT(bv.units() == U_PGC);
+    std::printf("BIOME_BOREAL_VEG_2100=%.17g\n", (double)bv);
+    const double tv = bc.sendMessage(M_GETDATA, "tropical.veg_c", message_data(2100.0));
+    const double gv = bc.sendMessage(M_GETDATA, "veg_c", message_data(2100.0));
+    EXPECT(std::fabs((double)bv + tv - gv) < 1e-9);
   }
 
   /* ---- the batch face: 4 members, per-member S ---- */

@@ -375,6 +375,7 @@ def make_extra_outputs():
 BIOME_VARS = ["CO2_concentration", "global_tas", "veg_c", "detritus_c", "soil_c", "permafrost_c",
               "thawedp_c", "NPP", "RH", "NBP", "CH4_concentration", "RF_tot", "HL_pH", "ocean_c",
               "land_tas", "atmos_co2", "earth_c"]
+BIOME_OWN_VARS = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c", "NPP", "RH"]
 BIOME_GLOBAL_KEYS = ["npp_flux0", "veg_c", "detritus_c", "soil_c", "permafrost_c", "f_nppv", "f_nppd",
                      "f_litterd", "beta", "q10_rh"]
 
@@ -443,7 +444,7 @@ def make_biomes():
     import tempfile
     from oracle import ref
     tmp = tempfile.mkdtemp()
-    names, vals, fails = [], [], []
+    names, vals, fails, owns = [], [], [], []
     for name, (scn, biomes, params) in BIOME_CASES.items():
         params = dict(params)
         q10_all = params.pop("q10_rh_all", None)
@@ -452,12 +453,17 @@ def make_biomes():
                 b["q10_rh"] = q10_all
         ini = os.path.join(tmp, name + ".ini")
         biome_ini(scn, biomes, ini)
-        ok, err, o, _ = ref.run_member(ini, params, BIOME_VARS)
+        # the global datum (sums over biomes), then every biome's own "<biome>.<name>"
+        per_biome = ["%s.%s" % (b, v) for b in biomes for v in BIOME_OWN_VARS]
+        ok, err, o, _ = ref.run_member(ini, params, BIOME_VARS + per_biome)
         # a failing run leaves NaN from the failing year on (the driver steps year by year)
         fail = 0 if ok else 1746 + int(np.argmax(np.isnan(o[0])))
         if not ok:
             o[:, fail - 1746:] = np.nan
-        names.append(name); vals.append(o); fails.append(fail)
+        own = np.full((4, len(BIOME_OWN_VARS), 555), np.nan)
+        own[:len(biomes)] = o[len(BIOME_VARS):-1].reshape(len(biomes), len(BIOME_OWN_VARS), 555)
+        o = np.vstack([o[:len(BIOME_VARS)], o[-1:]])
+        names.append(name); vals.append(o); fails.append(fail); owns.append(own)
         print(name, "ok" if ok else "fails in %d: %s" % (fail, err[:80]))
     import json
     spec = {n: dict(scenario=c[0], biomes=c[1], params={k: v for k, v in c[2].items()
@@ -466,6 +472,7 @@ def make_biomes():
     np.savez_compressed(os.path.join(OUT, "ref_biomes.npz"), names=np.array(names),
                         variables=np.array(BIOME_VARS + ["ocean_timesteps"]),
                         values=np.array(vals), fail_year=np.array(fails),
+                        biome_variables=np.array(BIOME_OWN_VARS), biome_values=np.array(owns),
                         spec=np.array(json.dumps(spec)))
 
 

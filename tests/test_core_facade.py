@@ -99,6 +99,7 @@ def test_facade_matches_oracle(exe):
     assert bio["name"] == "two_ssp245"
     close("BIOME_CO2_2300", bio["values"]["CO2_concentration"][yr(2300)])
     close("BIOME_VEG_2100", bio["values"]["veg_c"][yr(2100)])
+    close("BIOME_BOREAL_VEG_2100", bio["biome_values"]["boreal.veg_c"][yr(2100)])
     # beta = 50: the oracle and the engine must agree on whether the reference aborts
     st, _, _, _, _ = port.run_member(raw, beta=50.0)
     assert (st != 0) == (kv["BETA50_FAILED"] == "1")

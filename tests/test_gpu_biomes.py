@@ -26,6 +26,9 @@ def test_biomes_vs_reference_golden(case):
     import hector_b200 as hb
     variables = [v for v in case["values"] if v in hb.OUTPUT_VARIABLES]
     assert {"CO2_concentration", "global_tas", "veg_c", "NPP", "RH", "ocean_timesteps"} <= set(variables)
+    own = list(case["biome_values"])          # "<biome>.<name>" for every biome
+    assert len(own) == len(case["biomes"]) * len(hb.BIOME_OUTPUTS)
+    variables = variables + own
     ens = _ensemble(hb, case, 3, variables)
     ens.run()
     st, fy = ens.status()
@@ -37,7 +40,7 @@ def test_biomes_vs_reference_golden(case):
         assert (st == 0).all()
     got = ens.fetchvars(YEARS[:n], variables)
     for v in variables:
-        ref = case["values"][v][:n]
+        ref = (case["values"][v] if v in case["values"] else case["biome_values"][v])[:n]
         if v == "ocean_timesteps":
             assert np.array_equal(got[v][0], ref)
             continue

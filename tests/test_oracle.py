@@ -228,8 +228,8 @@ def test_biomes_against_reference(case):
     reference with a negative pool -- bit-identical up to the failing year, same year, same reason"""
     p = port.default_params()
     p.set_biomes(case["biomes"])
-    st, fy, out, cnt, sp = port.run_member(util.scenarios()[case["scenario"]], params=p,
-                                           **case["params"])
+    st, fy, out, bio = port.run_member_biomes(util.scenarios()[case["scenario"]], p,
+                                              **case["params"])
     n = 555
     if case["fail_year"]:
         assert (st, fy) == (1, case["fail_year"])  # HO_ERR_NEGATIVE
@@ -239,6 +239,10 @@ def test_biomes_against_reference(case):
     for v, ref in case["values"].items():
         if v in port.OUT_NAMES:
             assert np.array_equal(out[port.OUT_NAMES.index(v)][:n], ref[:n]), v
+    # every biome's own pools and final fluxes: getData("<biome>.<name>", date)
+    for ib, b in enumerate(case["biomes"]):
+        for k, v in enumerate(port.BIOME_OUT_NAMES):
+            assert np.array_equal(bio[ib, k][:n], case["biome_values"]["%s.%s" % (b, v)][:n]), (b, v)
 
 
 def test_biomes_with_tracking_are_refused():

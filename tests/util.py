@@ -126,7 +126,9 @@ def ref_biomes():
     cases = []
     for i, name in enumerate(z["names"]):
         sp = spec[str(name)]
+        own = {"%s.%s" % (b, str(v)): z["biome_values"][i][ib][k]
+               for ib, b in enumerate(sp["biomes"]) for k, v in enumerate(z["biome_variables"])}
         cases.append(dict(name=str(name), scenario=sp["scenario"], biomes=sp["biomes"],
                           params=sp["params"], fail_year=int(z["fail_year"][i]),
-                          values=dict(zip(variables, z["values"][i]))))
+                          values=dict(zip(variables, z["values"][i])), biome_values=own))
     return cases
