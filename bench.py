@@ -213,6 +213,8 @@ def main():
                     help="also time an ensemble over all 8 SSP scenarios interleaved (0 = skip)")
     ap.add_argument("--tracked-members", type=int, default=65536,
                     help="also time a carbon-tracking ensemble to 2500 (0 = skip)")
+    ap.add_argument("--biome-members", type=int, default=65536,
+                    help="also time a three-biome ensemble (0 = skip)")
     ap.add_argument("--e2e-segments", type=int, default=4)
     ap.add_argument("--exchange", default="auto", choices=["auto", "ipc", "nccl"],
                     help="N > 1: how the trajectories are exchanged: peer-memory pulls overlapped "
@@ -469,6 +471,35 @@ def main():
                            "carbon tracking from 1750 (11 pools x 12 sources per member)"}
         et.close()
 
+    # ---- biome-split land pools: three biomes, per-member biome parameters ----
+    biome = None
+    if args.biome_members and rank == 0 and world == 1:
+        mb_ = args.biome_members
+        glob = dict(npp_flux0=56.2, veg_c=550.0, detritus_c=55.0, soil_c=917.0, permafrost_c=865.0)
+        fracs = {"tundra": 0.2, "amazon": 0.45, "midlat": 0.35}
+        eb = hb.Ensemble(mb_, scenario_table(), device=local_rank, biomes=list(fracs),
+                         outputs=["CO2_concentration", "global_tas"], stream=stream.cuda_stream)
+        Xb = lhs(mb_)
+        for b, fr in fracs.items():
+            eb.set_biome(b, f_nppv=0.35, f_nppd=0.60, f_litterd=0.98,
+                         **{k: v * fr for k, v in glob.items()})
+            eb.setvar(b + ".q10_rh", np.ascontiguousarray(Xb[:, 1]))
+            eb.setvar(b + ".beta", np.ascontiguousarray(Xb[:, 2]))
+        eb.setvar("tundra.warmingfactor", 2.0)
+        eb.setvar("S", np.ascontiguousarray(Xb[:, 0]))
+        eb.setvar("diff", np.ascontiguousarray(Xb[:, 3]))
+        eb.prepare()
+        eb.synchronize()
+        bi_ms, _ = timed(eb, lambda e: (e.reset(), e.run()), max(2, args.steps // 2), 3, False)
+        bi_ms /= max(2, args.steps // 2)
+        stb, _ = eb.status()
+        biome = {"members": mb_, "biomes": 3, "value": mb_ * YEARS / (bi_ms * 1e-3), "unit": UNIT,
+                 "ms_per_step": bi_ms, "failed_members": int((stb != 0).sum()),
+                 "note": "the headline ensemble with the land split into three biomes (pools and "
+                         "NPP 0.2 / 0.45 / 0.35, per-member beta and q10_rh in every biome, "
+                         "tundra warming factor 2): the BIOMES instantiation of the run kernel"}
+        eb.close()
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -521,6 +552,7 @@ def main():
                                   "newton_calls")},
         "failed_members": failed, "small_ensemble": small, "multi_scenario_ensemble": multi,
         "tracked_ensemble": tracked,
+        "biome_ensemble": biome,
         "exchange": None if world == 1 else
         ("peer memory (CUDA IPC pulls, %d run segments)" % len(exchange.segments)
          if exchange is not None else "NCCL all-gather (%d run segments)" % len(seg_rows)),

@@ -158,6 +158,9 @@ enum { /* per-biome state */
   BF_X_CO2FERT, BF_X_TFD, BF_X_TFS, BF_X_FNEWTHAW, /* this year's slow parameters */
   BF_X_NPP, BF_X_RH,                               /* final_npp / final_rh of the last stash */
   BF_RH_CH4,
+  /* the biome's fluxes of the current sub-step (constant between two stashes): computed once
+   * with the sub-step constants, read again by the stash that ends the sub-step */
+  BF_S_NPP, BF_S_RH_FDA, BF_S_RH_FSA, BF_S_RH_CO2, BF_S_RH_CH4,
   BF_COUNT
 };
 /* per-biome outputs "<biome>.<name>" (getData with a biome prefix, simpleNbox.cpp:533-697):
