@@ -421,6 +421,14 @@ BIOME_CASES = {
 }
 
 
+# user constraints on top of biomes: {case: {constraint: {year: value}}}
+BIOME_CONSTRAINTS = {
+    "two_nbp_co2_ssp245": {"NBP_constrain": {y: 0.4 + 0.02 * (y - 1990) for y in range(1990, 2011)},
+                           "CO2_constrain": {y: 470.0 + 2.0 * (y - 2050) for y in range(2050, 2061)}},
+}
+BIOME_CASES["two_nbp_co2_ssp245"] = BIOME_CASES["two_ssp245"]
+
+
 def biome_ini(scn, biomes, path):
     """the shipped ini with the global [simpleNbox] pool / parameter lines replaced by
     <biome>.<name>= lines (simpleNbox.cpp:201-236)"""
@@ -436,6 +444,30 @@ def biome_ini(scn, biomes, path):
                 for k, v in vals.items():
                     lines.append("%s.%s=%r" % (b, k, float(v)))
     open(path, "w").write("\n".join(lines) + "\n")
+
+
+def _run_constrained(ref, ini, params, constraints, variables):
+    """like ref.run_member, with dated constraint entries set before prepareToRun"""
+    c = ref.RefCore(ini)
+    for k, v in params.items():
+        c.setdata(ref.PARAM_COMPONENT[k], k, v)
+    for var, d in constraints.items():
+        for y, v in d.items():
+            c.setvar(var, float(v), CONSTRAINT_UNITS[var], float(y))
+    c.prepare()
+    o = np.full((len(variables) + 1, 555), np.nan)
+    ok, err = True, ""
+    for y in range(1746, 2301):
+        try:
+            c.run(y)
+        except ref.RefError as e:
+            ok, err = False, str(e)
+            break
+        for k, v in enumerate(variables):
+            o[k, y - 1746] = c.fetch(v, y)
+        o[-1, y - 1746] = c.fetch_component("ocean", "ocean_timesteps")
+    c.close()
+    return ok, err, o
 
 
 def make_biomes():
@@ -455,7 +487,11 @@ def make_biomes():
         biome_ini(scn, biomes, ini)
         # the global datum (sums over biomes), then every biome's own "<biome>.<name>"
         per_biome = ["%s.%s" % (b, v) for b in biomes for v in BIOME_OWN_VARS]
-        ok, err, o, _ = ref.run_member(ini, params, BIOME_VARS + per_biome)
+        if name in BIOME_CONSTRAINTS:
+            ok, err, o = _run_constrained(ref, ini, params, BIOME_CONSTRAINTS[name],
+                                          BIOME_VARS + per_biome)
+        else:
+            ok, err, o, _ = ref.run_member(ini, params, BIOME_VARS + per_biome)
         # a failing run leaves NaN from the failing year on (the driver steps year by year)
         fail = 0 if ok else 1746 + int(np.argmax(np.isnan(o[0])))
         if not ok:
@@ -467,7 +503,9 @@ def make_biomes():
         print(name, "ok" if ok else "fails in %d: %s" % (fail, err[:80]))
     import json
     spec = {n: dict(scenario=c[0], biomes=c[1], params={k: v for k, v in c[2].items()
-                                                         if k != "q10_rh_all"})
+                                                         if k != "q10_rh_all"},
+                    constraints={k: {str(y): v for y, v in d.items()}
+                                 for k, d in BIOME_CONSTRAINTS.get(n, {}).items()})
             for n, c in BIOME_CASES.items()}
     np.savez_compressed(os.path.join(OUT, "ref_biomes.npz"), names=np.array(names),
                         variables=np.array(BIOME_VARS + ["ocean_timesteps"]),

@@ -18,6 +18,8 @@ def _ensemble(hb, case, n, outputs):
         ens.set_biome(b, **vals)
     for k, v in case["params"].items():
         ens.setvar(k, v)
+    for name, d in case.get("constraints", {}).items():  # NBP / CO2 constraints on top of biomes
+        ens.setvar_series(name, sorted(d), [d[y] for y in sorted(d)])
     return ens
 
 

@@ -229,7 +229,7 @@ def test_biomes_against_reference(case):
     p = port.default_params()
     p.set_biomes(case["biomes"])
     st, fy, out, bio = port.run_member_biomes(util.scenarios()[case["scenario"]], p,
-                                              **case["params"])
+                                              spec=case["constraints"], **case["params"])
     n = 555
     if case["fail_year"]:
         assert (st, fy) == (1, case["fail_year"])  # HO_ERR_NEGATIVE

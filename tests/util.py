@@ -130,5 +130,7 @@ def ref_biomes():
                for ib, b in enumerate(sp["biomes"]) for k, v in enumerate(z["biome_variables"])}
         cases.append(dict(name=str(name), scenario=sp["scenario"], biomes=sp["biomes"],
                           params=sp["params"], fail_year=int(z["fail_year"][i]),
+                          constraints={k: {int(y): v for y, v in d.items()}
+                                       for k, d in sp.get("constraints", {}).items()},
                           values=dict(zip(variables, z["values"][i])), biome_values=own))
     return cases
