@@ -114,6 +114,7 @@ struct Engine {
   std::vector<std::vector<double>> cons;
   bool tables_dirty = false;                 /* a series changed after hx_prepare */
   bool tables_constrained = false;           /* some scenario carries a CO2/NBP/CH4/RF_tot/tas constraint */
+  bool tables_nbp = false;                   /* ... an NBP constraint */
   std::vector<int32_t> member_scen;          /* API order */
   double pscalar[PI_COUNT];
   std::vector<double> pvec[PI_COUNT];        /* per-member overrides (API order), host copy */
@@ -392,9 +393,10 @@ struct Engine {
   }
 
   /* device scenario tables [scen][row][SC_STRIDE]: raw series, host gas series, constraints */
-  void build_tables(std::vector<double> &tab, bool &any_constraint) const {
+  void build_tables(std::vector<double> &tab, bool &any_constraint, bool &any_nbp) const {
     tab.assign((size_t)nscen * nrow * SC_STRIDE, 0.0);
     any_constraint = false;
+    any_nbp = false;
     for (int s = 0; s < nscen; ++s) {
       std::vector<double> n2o, hrf;
       gas_series(s, n2o, hrf);
@@ -410,16 +412,18 @@ struct Engine {
         row[SC_C_RFTOT] = rftot[r]; row[SC_C_TAS] = tas[r]; row[SC_C_NBP] = cnbp[r];
         for (int c = SC_C_CO2; c <= SC_C_NBP; ++c)
           if (row[c] == row[c]) any_constraint = true;
+        if (row[SC_C_NBP] == row[SC_C_NBP]) any_nbp = true;
       }
     }
   }
   int upload_tables() {
     std::vector<double> tab;
-    bool any = false;
-    build_tables(tab, any);
+    bool any = false, nbp = false;
+    build_tables(tab, any, nbp);
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaMemcpy(d_scen, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     tables_constrained = any;
+    tables_nbp = nbp;
     tables_dirty = false;
     return HX_OK;
   }
@@ -545,7 +549,7 @@ struct Engine {
     /* a land-ocean warming ratio is served by the constraint builds of the run kernel */
     bool lo_active = pscalar[PI_LO_RATIO] != 0.0 || pvec_on_device_only[PI_LO_RATIO];
     for (double v : pvec[PI_LO_RATIO]) lo_active = lo_active || v != 0.0;
-    d.constrained = (tables_constrained || lo_active) ? 1 : 0;
+    d.constrained = tables_nbp ? 2 : (tables_constrained || lo_active) ? 1 : 0;
     CUDA_TRY(cudaMemcpyAsync(d_status, d_status_snap, (size_t)Mpad * sizeof(int32_t),
                              cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(hx::launch_setup(d, C, stream));
@@ -1122,8 +1126,8 @@ int hx_prepare(hx_handle h) {
 
   /* device scenario tables */
   std::vector<double> tab;
-  bool any_constraint = false;
-  h->build_tables(tab, any_constraint);
+  bool any_constraint = false, any_nbp = false;
+  h->build_tables(tab, any_constraint, any_nbp);
 
   const size_t Mp = Mpad;
   const int nsel = (int)h->out_sel.size();
@@ -1192,7 +1196,8 @@ int hx_prepare(hx_handle h) {
   h->rec_elems = block_scen.size() * hx::track_record_bytes_per_cta() / sizeof(double);
   h->ycnt_bytes = block_scen.size() * hx::track_ycnt_bytes_per_tile();
   h->tables_constrained = any_constraint;
-  d.constrained = any_constraint ? 1 : 0; /* refined in run_setup_and_spinup */
+  h->tables_nbp = any_nbp;
+  d.constrained = any_nbp ? 2 : any_constraint ? 1 : 0; /* refined in run_setup_and_spinup */
   for (int i = 0; i < HX_OUT_IDS; ++i) d.out_slot[i] = -1;
   for (int s = 0; s < nsel; ++s) d.out_slot[h->out_sel[s]] = s;
   d.n_out = nsel;

@@ -532,7 +532,7 @@ __device__ __noinline__ void nan_fill_rows(const HxDev &d, int nyears, int m, in
     for (int yi = first; yi < last; ++yi) d.out[((size_t)s * nyears + yi) * d.Mpad + m] = nan;
 }
 
-template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES>
+template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES, bool NBP>
 __global__ void __launch_bounds__(HX_BLOCK, MINCTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   /* dynamic shared memory (> 48 KB): scenario slabs | row 0 | chemistry constants | RK stages */
@@ -734,7 +734,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         }
 
         /* --- CarbonCycleSolver::run --- */
-        solver_year<false, TRACK, CONSTR, BIOMES>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
+        solver_year<false, TRACK, CONSTR, BIOMES, NBP>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
         if (mb.status) {
           d.status[m] = mb.status;
           d.fail_year[m] = y;
@@ -1126,11 +1126,12 @@ cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cuda
   hx_spinup_kernel<false><<<1, HX_BLOCK, 0, st>>>(d, C, member - member % HX_BLOCK, member);
   return cudaGetLastError();
 }
-template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT = true, bool BIOMES = false>
+template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT = true, bool BIOMES = false,
+          bool NBP = CONSTR>
 static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES>,
+    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
@@ -1141,7 +1142,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP>,
                                                                   HX_BLOCK, HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
     resident = sms * (per_sm > 0 ? per_sm : 1);
@@ -1152,7 +1153,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
   cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1 + nslab) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
+  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
@@ -1161,8 +1162,11 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
    * every tile is resident anyway at 2 CTAs per SM the run is pure latency and the spill-free
    * 230-register build wins (17.0 vs 20.5 ms at 1 024 members).  The tracking build is bound by
    * its map traffic, not by occupancy, and spills badly at 168 registers. */
-  /* biome-split pools: one general build (constraints and every output; no tracking) */
-  if (d.BF) return launch_run_t<false, true, 2, true, true>(d, C, r0, r1, st);
+  /* biome-split pools: general builds (constraints and every output; no tracking), with and
+   * without the NBP machinery */
+  if (d.BF)
+    return d.constrained > 1 ? launch_run_t<false, true, 2, true, true, true>(d, C, r0, r1, st)
+                             : launch_run_t<false, true, 2, true, true, false>(d, C, r0, r1, st);
   if (d.T)
     return d.constrained ? launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st)
                          : launch_run_t<true, false, HX_TRACK_CTAS>(d, C, r0, r1, st);
@@ -1170,9 +1174,12 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const bool small = d.Mpad / HX_BLOCK <= 2 * sms;
-  if (d.constrained)
+  if (d.constrained > 1) /* an NBP constraint somewhere */
     return small ? launch_run_t<false, true, 2>(d, C, r0, r1, st)
                  : launch_run_t<false, true, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
+  if (d.constrained)     /* the other constraints, lo_warming_ratio: no NBP machinery */
+    return small ? launch_run_t<false, true, 2, true, false, false>(d, C, r0, r1, st)
+                 : launch_run_t<false, true, HX_RUN_MIN_CTAS, true, false, false>(d, C, r0, r1, st);
   if (d.out_minimal)
     return small ? launch_run_t<false, false, 2, false>(d, C, r0, r1, st)
                  : launch_run_t<false, false, HX_RUN_MIN_CTAS, false>(d, C, r0, r1, st);

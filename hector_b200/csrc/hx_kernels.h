@@ -40,7 +40,8 @@ struct HxDev {
   unsigned *sched;              /* [1 + tiles + slabs]: work-queue ticket, per-tile progress, tiles done per slab */
   int32_t out_slot[HX_OUT_IDS]; /* output id -> slot in `out`, -1 = not recorded; ids from
                                    OUT_COUNT on are the per-biome outputs */
-  int32_t constrained;      /* some scenario carries a CO2 / CH4 / RF_tot / tas constraint */
+  int32_t constrained;      /* 0 none; 1 some scenario carries a CO2 / CH4 / RF_tot / tas
+                               constraint or a member a lo_warming_ratio; 2 an NBP constraint */
   int32_t out_minimal;      /* only CO2_concentration and/or global_tas are recorded */
   int32_t n_out;            /* recorded outputs (slots of `out`) */
   /* hx_run_stream: [slabs of the launch] in mapped host memory, set to 1 when every tile has
