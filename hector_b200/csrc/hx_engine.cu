@@ -993,6 +993,15 @@ int hx_set_param_device(hx_handle h, const char *name, const double *dev, int32_
 
 int hx_get_param(hx_handle h, const char *name, double *out, int32_t n) {
   if (!h || !name || !out) return HX_ERR_ARG;
+  {
+    int ib, f;
+    if (h->find_biome_param(name, ib, f)) { /* "<biome>.<name>": host copies (set before prepare) */
+      if (n != h->M) return h->fail(HX_ERR_ARG, "hx_get_param: n != n_members");
+      for (int i = 0; i < n; ++i)
+        out[i] = h->bvec[ib][f].empty() ? h->bscalar[ib][f] : h->bvec[ib][f][i];
+      return HX_OK;
+    }
+  }
   const int pi = h->find_param(name);
   if (pi < 0) return h->fail(HX_ERR_ARG, std::string("unknown parameter: ") + name);
   if (n != h->M) return h->fail(HX_ERR_ARG, "hx_get_param: n != n_members");

@@ -109,6 +109,7 @@ def test_biome_input_errors():
     with pytest.raises(hb.HxError):  # unknown biome
         ens.setvar("tundra.beta", 0.5)
     ens.set_biome("boreal", veg_c=100.0)
+    assert ens.getvar("boreal.veg_c")[0] == 100.0 and ens.getvar("tropical.pf_mu")[0] == 1.67
     with pytest.raises(hb.HxError) as e:  # incomplete biome data
         ens.prepare()
     assert "data for biome" in str(e.value)
