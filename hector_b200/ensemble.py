@@ -174,6 +174,41 @@ class Ensemble:
             self._chk(self.L.hx_set_tracking(self.h, int(tracking_date), int(track_every)))
         self.prepared = False
 
+    def split_biome(self, new_biomes, fveg_c=None, fdetritus_c=None, fsoil_c=None,
+                    fpermafrost_c=None, fnpp_flux0=None, **params):
+        """R split_biome(core, "global", new_biomes, ...) (R/biome.R:61-131): the global biome's
+        pools and initial NPP are distributed over `new_biomes` by the given fractions (default:
+        evenly; the others default to fveg_c), every other parameter is inherited unless given
+        in `params` (one value, or one per new biome).  Call before prepare()."""
+        n = len(new_biomes)
+        fveg_c = [1.0 / n] * n if fveg_c is None else list(fveg_c)
+        fr = {"veg_c": fveg_c,
+              "detritus_c": fveg_c if fdetritus_c is None else list(fdetritus_c),
+              "soil_c": fveg_c if fsoil_c is None else list(fsoil_c),
+              "permafrost_c": fveg_c if fpermafrost_c is None else list(fpermafrost_c),
+              "npp_flux0": fveg_c if fnpp_flux0 is None else list(fnpp_flux0)}
+        for k, f in fr.items():
+            if len(f) != n or abs(sum(f) - 1.0) > 1e-12 or min(f) < 0 or \
+                    (k != "permafrost_c" and min(f) <= 0):
+                raise HxError("split_biome: the %s fractions must be positive and sum to 1" % k)
+        unknown = set(params) - set(BIOME_PARAMETERS)
+        if unknown:
+            raise HxError("split_biome: not a biome parameter: %s" % sorted(unknown))
+        cur = {k: self.getvar(k) for k in BIOME_PARAMETERS}  # the global biome's, per member
+        arr = (C.c_char_p * n)(*[b.encode() for b in new_biomes])
+        self._chk(self.L.hx_set_biomes(self.h, n, arr))
+        self.biomes = list(new_biomes)
+        for i, b in enumerate(new_biomes):
+            for k in BIOME_PARAMETERS:
+                if k in fr:
+                    v = cur[k] * fr[k][i]
+                elif k in params:
+                    p = params[k]
+                    v = np.full(self.n_members, float(p[i] if np.ndim(p) else p))
+                else:
+                    v = cur[k]
+                self.setvar("%s.%s" % (b, k), v)
+
     def set_biome(self, biome, **values):
         """<biome>.<name> inputs (scalars or per-member arrays), like setvar("boreal.beta", ...)"""
         for k, v in values.items():

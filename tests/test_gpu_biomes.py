@@ -98,6 +98,25 @@ def test_biome_ensemble_vs_oracle():
     ens.close()
 
 
+def test_split_biome_like_r():
+    """split_biome (R/biome.R:61-131): the even_ssp126 fixture was built as an even split of the
+    global biome with q10_rh = 1.8 in both halves"""
+    import hector_b200 as hb
+    case = [c for c in util.ref_biomes() if c["name"] == "even_ssp126"][0]
+    ens = hb.Ensemble(2, util.scenarios()["ssp126"], outputs=["CO2_concentration", "global_tas"])
+    ens.split_biome(["north", "south"], q10_rh=1.8)
+    assert ens.getvar("north.veg_c")[0] == 275.0 and ens.getvar("south.beta")[1] == 0.65
+    ens.run()
+    got = ens.fetchvars(YEARS, ["CO2_concentration", "global_tas"])
+    for v in got:
+        ref = case["values"][v]
+        err = float(np.max(np.abs(got[v][0] - ref) / np.maximum(np.abs(ref), util.FLOOR.get(v, 1e-3))))
+        assert err < TOL, (v, err)
+    with pytest.raises(hb.HxError):
+        hb.Ensemble(1, util.scenarios()["ssp126"]).split_biome(["a", "b"], fveg_c=[0.5, 0.6])
+    ens.close()
+
+
 def test_biome_input_errors():
     import hector_b200 as hb
     tab = util.scenarios()["ssp245"]
