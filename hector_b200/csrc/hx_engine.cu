@@ -150,6 +150,8 @@ struct Engine {
 
   cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_seg = nullptr, ev_copy = nullptr;
+  cudaStream_t setup_stream = nullptr; /* DOECLIM set-up beside the shared spin-up */
+  cudaEvent_t ev_setup_a = nullptr, ev_setup_b = nullptr;
   /* multi-GPU exchange over peer memory: peers' output blocks opened through CUDA IPC */
   std::vector<double *> peer_out;
   std::vector<cudaStream_t> peer_stream; /* one per peer: the pulls spread over the copy engines */
@@ -552,16 +554,29 @@ struct Engine {
     d.constrained = tables_nbp ? 2 : (tables_constrained || lo_active) ? 1 : 0;
     CUDA_TRY(cudaMemcpyAsync(d_status, d_status_snap, (size_t)Mpad * sizeof(int32_t),
                              cudaMemcpyDeviceToDevice, stream));
-    CUDA_TRY(hx::launch_setup(d, C, stream));
     if (spinup_shared() && M > 1) {
       /* E-7: nothing that shapes the spin-up or the alkalinity equilibration varies across
        * members, so one member's spin-up serves the ensemble: run it on one thread and
-       * broadcast the state rows it touches (SI_ATMOS .. SI_SOLVER_DT) */
+       * broadcast the state rows it touches (SI_ATMOS .. SI_SOLVER_DT).  That single thread is
+       * pure latency (2.2 ms), so the members' DOECLIM set-up (1.0 ms, reads and writes nothing
+       * the spin-up touches) runs beside it on a second stream. */
+      if (!setup_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&setup_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_setup_a, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_setup_b, cudaEventDisableTiming));
+      }
+      CUDA_TRY(hx::launch_setup(d, C, stream, 1));
+      CUDA_TRY(cudaEventRecord(ev_setup_a, stream));
+      CUDA_TRY(cudaStreamWaitEvent(setup_stream, ev_setup_a, 0));
+      CUDA_TRY(hx::launch_setup(d, C, setup_stream, 2));
+      CUDA_TRY(cudaEventRecord(ev_setup_b, setup_stream));
       CUDA_TRY(hx::launch_spinup_one(d, C, first_active, stream));
       k_broadcast_state<<<(Mpad + 255) / 256, 256, 0, stream>>>(
           d_S, d_spinup_steps, d_status, d_fail_year, first_active, SI_SOLVER_DT + 1, (size_t)Mpad);
       CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamWaitEvent(stream, ev_setup_b, 0));
     } else {
+      CUDA_TRY(hx::launch_setup(d, C, stream));
       CUDA_TRY(hx::launch_spinup(d, C, stream));
     }
     if (d_T) CUDA_TRY(hx::launch_track_init(d, stream));
@@ -790,6 +805,9 @@ int hx_destroy(hx_handle h) {
     if (e) cudaEventDestroy(e);
   if (h->ev_seg) cudaEventDestroy(h->ev_seg);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->ev_setup_a) cudaEventDestroy(h->ev_setup_a);
+  if (h->ev_setup_b) cudaEventDestroy(h->ev_setup_b);
+  if (h->setup_stream) cudaStreamDestroy(h->setup_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

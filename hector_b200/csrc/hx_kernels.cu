@@ -149,13 +149,23 @@ __device__ __forceinline__ void flush_work(const HxDev &d, const Work &w, unsign
 /* set-up: OceanComponent::prepareToRun (ocean_component.cpp:202-319),
  * TemperatureComponent::prepareToRun (temperature_component.cpp:196-413),
  * SimpleNbox::prepareToRun (simpleNbox-runtime.cpp:61-197) and the CH4/solver initial values. */
+__device__ __forceinline__ void setup_doeclim(const Bases &BS, const HxConst &C);
+__device__ __forceinline__ void setup_state(const HxDev &d, const HxConst &C, const Bases &BS, int m);
+
+/* phase bit 1: ocean rates, initial pools and state -- all the spin-up needs; bit 2: the DOECLIM
+ * matrices and lag kernel (the expensive part: nrow kernel entries per member), which the
+ * engine runs next to the spin-up on a second stream */
 __global__ void __launch_bounds__(HX_BLOCK)
-hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C) {
+hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int phase) {
   const int m = blockIdx.x * HX_BLOCK + threadIdx.x;
   if (m >= d.Mpad) return;
   if (d.status[m] < 0) return; /* padding lane */
   const Bases BS = make_bases(d, C, m);
 
+  if (phase & 2) {
+    setup_doeclim(BS, C);
+    if (!(phase & 1)) return;
+  }
   /* ocean exchange rates (fraction of the box per year), ocean_component.cpp:262-284 */
   const double spy = C.spy_ocean;
   const double tt = PAR(PI_TT), tu = PAR(PI_TU), twi = PAR(PI_TWI), tid = PAR(PI_TID);
@@ -171,8 +181,11 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   DER(DI_K_LL_HL) = LL_HL; DER(DI_K_LL_IO) = LL_IOex; DER(DI_K_HL_DO) = HL_DO;
   DER(DI_K_IO_LL) = IO_LL + IO_LLex; DER(DI_K_IO_HL) = IO_HL; DER(DI_K_IO_DO) = IO_DOex;
   DER(DI_K_DO_IO) = DO_IO + DO_IOex;
+  setup_state(d, C, BS, m);
+}
 
-  /* DOECLIM, temperature_component.cpp:248-412 */
+/* DOECLIM, temperature_component.cpp:248-412 */
+__device__ __forceinline__ void setup_doeclim(const Bases &BS, const HxConst &C) {
   const double dt = 1.0, ak = DC_AK, bk = DC_BK, csw = DC_CSW, rlam = DC_RLAM, bsi = DC_BSI,
                cal = DC_CAL, cas = DC_CAS, flnd = DC_FLND, fso = DC_FSO;
   const double S = PAR(PI_S), diff = PAR(PI_DIFF), qco2 = PAR(PI_QCO2);
@@ -247,8 +260,10 @@ hx_setup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   DER(DI_INV_UC_CH4) = 1.0 / PAR(PI_UC_CH4);
   DER(DI_INV_TSOIL) = 1.0 / PAR(PI_TSOIL);
   DER(DI_INV_TSTRAT) = 1.0 / PAR(PI_TSTRAT);
+}
 
-  /* initial pools: ocean_component.cpp:224-260, simpleNbox.cpp:45-81, simpleNbox-runtime.cpp:172 */
+/* initial pools: ocean_component.cpp:224-260, simpleNbox.cpp:45-81, simpleNbox-runtime.cpp:172 */
+__device__ __forceinline__ void setup_state(const HxDev &d, const HxConst &C, const Bases &BS, int m) {
   const double LL_vol_frac = C.vol_LL / (C.vol_LL + C.vol_HL);
   const double HL_vol_frac = 1 - LL_vol_frac;
   const double I_vol_frac = C.vol_IO / (C.vol_IO + C.vol_DO);
@@ -1113,8 +1128,8 @@ __global__ void hx_nan_fill_kernel(const __grid_constant__ HxDev d, int start_ye
 }
 
 /* ---- host-callable launchers ---- */
-cudaError_t launch_setup(const HxDev &d, const HxConst &C, cudaStream_t st) {
-  hx_setup_kernel<<<d.Mpad / HX_BLOCK, HX_BLOCK, 0, st>>>(d, C);
+cudaError_t launch_setup(const HxDev &d, const HxConst &C, cudaStream_t st, int phase) {
+  hx_setup_kernel<<<d.Mpad / HX_BLOCK, HX_BLOCK, 0, st>>>(d, C, phase);
   return cudaGetLastError();
 }
 cudaError_t launch_spinup(const HxDev &d, const HxConst &C, cudaStream_t st) {

@@ -62,7 +62,9 @@ struct HxDev {
 };
 
 namespace hx {
-cudaError_t launch_setup(const HxDev &d, const HxConst &C, cudaStream_t st);
+/* phase: 1 = ocean rates + initial state (what the spin-up reads), 2 = DOECLIM matrices and lag
+ * kernel, 3 = both */
+cudaError_t launch_setup(const HxDev &d, const HxConst &C, cudaStream_t st, int phase = 3);
 cudaError_t launch_spinup(const HxDev &d, const HxConst &C, cudaStream_t st);
 cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cudaStream_t st);
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st);
