@@ -208,3 +208,35 @@ def test_constraints_from_ini_file(tmp_path):
     assert np.allclose(ya["global_tas"][1][yrs - 1746], [tas[y] for y in yrs], rtol=0, atol=1e-15)
     a.close()
     b.close()
+
+
+def test_lo_warming_ratio_with_tas_and_co2_constraints_vs_oracle():
+    """a land-ocean warming ratio on top of a tas and a CO2 constraint (the oracle is bit-identical
+    to the reference for this combination): per-member ratios, the light constraint build"""
+    from oracle import port
+    import hector_b200 as hb
+    tab = util.scenarios()["ssp245"]
+    spec = {"tas_constrain": {y: 0.5 + 0.01 * (y - 1950) for y in range(1950, 2021)},
+            "CO2_constrain": {y: 400.0 for y in range(2030, 2036)}}
+    M = 5
+    ratio = np.array([0.0, 1.2, 1.7, 0.9, 1.45])   # member 0: ratio off
+    S = np.array([3.0, 2.2, 4.1, 3.6, 2.9])
+    outs = ["CO2_concentration", "global_tas", "land_tas", "sst", "ocean_tas", "gmst", "veg_c",
+            "heatflux", "ocean_timesteps"]
+    ens = hb.Ensemble(M, tab, outputs=outs)
+    ens.setvar("lo_warming_ratio", ratio)
+    ens.setvar("S", S)
+    _apply(ens, spec)
+    ens.run()
+    assert (ens.status()[0] == 0).all()
+    got = ens.fetchvars(YEARS)
+    for i in range(M):
+        ost, _, out = port.run_member_constrained(tab, spec, S=S[i], lo_warming_ratio=ratio[i])
+        assert ost == 0
+        for v in outs:
+            ref = out[port.OUT_NAMES.index(v)]
+            if v == "ocean_timesteps":
+                assert np.array_equal(got[v][i], ref), i
+            else:
+                assert util.parity_err(got[v][i], ref, v) < TOL, (i, v)
+    ens.close()
