@@ -490,9 +490,10 @@ struct Engine {
     return cudaSuccess;
   }
 
-  /* hx_run_stream, untracked: see there.  slab_done lives in mapped pinned memory; the kernel
-   * bumps slab_done[s] once per tile that finished slab s (after a system-scope fence), this
-   * thread polls it and queues the slab's device-to-host copies on the copy stream. */
+  /* hx_run_stream, untracked: see there.  slab_done lives in mapped pinned memory; the last
+   * tile to finish slab s sets slab_done[s] (tiles are counted in device memory; the store
+   * follows a system-scope fence), this thread polls it and queues the slab's device-to-host
+   * copies on the copy stream. */
   unsigned *h_slab_done = nullptr, *d_slab_done = nullptr;
   int slab_done_cap = 0;
   int run_streamed(int r0, int r1, int n_vars, const int *slot, double *const *outs) {
@@ -512,12 +513,11 @@ struct Engine {
     ds.slab_done = d_slab_done;
     CUDA_TRY(hx::launch_run(ds, C, r0, r1, stream));
     CUDA_TRY(cudaEventRecord(ev1, stream));
-    const unsigned ntiles = 1u; /* the flag is raised once, by the slab's last tile */
-    volatile unsigned *done = h_slab_done;
+    volatile unsigned *done = h_slab_done; /* done[s] becomes 1: raised by slab s's last tile */
     bool kernel_over = false;
     for (int s = 0; s < nslab; ++s) {
       unsigned spins = 0;
-      while (done[s] < ntiles && !kernel_over) {
+      while (done[s] == 0u && !kernel_over) {
         if ((++spins & 0xfffu) == 0) {
           /* the kernel may have stopped without finishing (a launch or device error) */
           const cudaError_t q = cudaStreamQuery(stream);
@@ -525,7 +525,7 @@ struct Engine {
           else if (q != cudaErrorNotReady) return fail(HX_ERR_CUDA, std::string("run kernel: ") + cudaGetErrorString(q));
         }
       }
-      if (done[s] < ntiles)
+      if (done[s] == 0u)
         return fail(HX_ERR_CUDA, "hx_run_stream: the run kernel ended without completing every slab");
       const int ra = r0 + s * HX_SLAB_YEARS, rb = std::min(r1, ra + HX_SLAB_YEARS);
       for (int v = 0; v < n_vars; ++v) {
