@@ -1,6 +1,12 @@
 """GPU: every per-member parameter perturbed at once (one random draw per member) against the
-oracle, all 38 outputs.  Written at the end of round 1 without GPU time left to run it: run it
-first thing next round and, once green, move it into tests/test_gpu_parity.py.
+oracle, all 38 outputs.  Written at the very end of round 1; its one run (12 members, seed 5,
+seconds of GPU time left) got through the status, failing-year and per-year sub-step-count
+checks of all members and then tripped the blanket 1e-10 assertion over ALL outputs -- the line
+naming the variable was cut off and there was no budget to rerun.  Secondary diagnostics of
+strongly perturbed members are only held to 5e-8 elsewhere (conditioning of
+the high-latitude box), so the script now reports contract variables (CO2, Tgav: 1e-10) and
+secondary ones (5e-8) separately and prints everything before asserting.  Run it first thing
+next round; once understood and green, move it into tests/test_gpu_parity.py.
 
 usage (under gpurun): python tools/gpu_all_params_vs_oracle.py [members] [seed]"""
 import os, sys
@@ -54,7 +60,10 @@ for name, v in vals.items():
 ens.run()
 st, fy = ens.status()
 got = ens.fetchvars(np.arange(1746, 2301, dtype=np.float64), outs)
+CONTRACT = ("CO2_concentration", "global_tas")
 worst = ("", -1, 0.0)
+worst2 = ("", -1, 0.0)
+per_var = {}
 for i in range(M):
     kw = {RANGES[n][0]: float(vals[n][i]) for n in vals}
     ost, ofy, out, _, _ = port.run_member(util.scenarios()["ssp370"], **kw)
@@ -66,8 +75,15 @@ for i in range(M):
             assert np.array_equal(got[v][i][:n], ref), (i, v)
             continue
         e = util.parity_err(got[v][i][:n], ref, v)
-        if e > worst[2]:
+        per_var[v] = max(per_var.get(v, 0.0), e)
+        if v in CONTRACT and e > worst[2]:
             worst = (v, i, e)
-print("members", M, "failed", int((st != 0).sum()), "worst", worst)
-assert worst[2] < 1e-10
+        if v not in CONTRACT and e > worst2[2]:
+            worst2 = (v, i, e)
+print("members", M, "failed", int((st != 0).sum()))
+for v, e in sorted(per_var.items(), key=lambda kv: -kv[1])[:12]:
+    print("  %-20s %.3g" % (v, e))
+print("worst contract variable", worst, "worst secondary", worst2, flush=True)
+assert worst[2] < 1e-10, worst
+assert worst2[2] < 5e-8, worst2
 print("OK")
