@@ -514,8 +514,57 @@ def make_biomes():
                         spec=np.array(json.dumps(spec)))
 
 
+ALLPARAM_VARS = ["CO2_concentration", "global_tas", "RF_tot", "HL_pH", "CH4_concentration",
+                 "N2O_concentration", "O3_concentration", "veg_c", "soil_c", "permafrost_c",
+                 "ocean_c", "heatflux"]
+
+
+def make_allparams():
+    """ref_allparams.npz: every scalar parameter (and tau / rho / delta of four halocarbons)
+    perturbed at once, three random draws on three SSPs, from the UNMODIFIED reference.  The
+    draws are those of tools/sweep_params_vs_ref.py (same table of ranges, seed 4)."""
+    import json
+    from oracle import ref, port
+    tool = os.path.join(os.path.dirname(os.path.dirname(OUT)), "tools", "sweep_params_vs_ref.py")
+    src = open(tool).read().split("SCN = [")[0]   # the table of ranges only
+    ns = {"__file__": tool}
+    argv, sys.argv = sys.argv, [tool]
+    exec(compile(src, tool, "exec"), ns)
+    sys.argv = argv
+    P = ns["P"]
+    rng = np.random.default_rng(4)
+    d = port.default_params()
+    names, scns, specs, vals = [], [], [], []
+    for case, scn in enumerate(["ssp119", "ssp370", "ssp585"]):
+        over_ref, over_or, halo = {}, {}, {}
+        for name, (comp, field, lo, hi) in P.items():
+            v = float(getattr(d, field)) * rng.uniform(lo, hi)
+            over_ref[(comp, name)] = v
+            over_or[field] = v
+        for g in rng.choice(len(port.HALOS), 4, replace=False):
+            gas = port.HALOS[int(g)]
+            for fld, ini in (("halo_tau", "tau"), ("halo_rho", "rho_" + gas),
+                             ("halo_delta", "delta_" + gas)):
+                cur = getattr(d, fld)[int(g)]
+                v = float(cur * rng.uniform(0.7, 1.3)) if cur != 0 else float(rng.uniform(-0.1, 0.1))
+                halo["%s[%d]" % (fld, int(g))] = v
+                over_ref[(gas + "_halocarbon", ini)] = v
+        ok, err, o, _ = ref.run_member(os.path.join(REF, "inst/input/hector_%s.ini" % scn),
+                                       over_ref, ALLPARAM_VARS)
+        assert ok, err
+        names.append("allparams_%d_%s" % (case, scn)); scns.append(scn)
+        specs.append(dict(params=over_or, halo=halo)); vals.append(o)
+        print(names[-1], "ok")
+    np.savez_compressed(os.path.join(OUT, "ref_allparams.npz"), names=np.array(names),
+                        scenarios=np.array(scns), spec=np.array(json.dumps(specs)),
+                        variables=np.array(ALLPARAM_VARS + ["ocean_timesteps"]),
+                        values=np.array(vals))
+
+
 if __name__ == "__main__":
-    if "biomes" in sys.argv[1:]:
+    if "allparams" in sys.argv[1:]:
+        make_allparams()
+    elif "biomes" in sys.argv[1:]:
         make_biomes()
     elif "extra" in sys.argv[1:]:
         make_extra_outputs()
@@ -529,3 +578,4 @@ if __name__ == "__main__":
         make_constraints()
         make_extra_outputs()
         make_biomes()
+        make_allparams()

@@ -250,3 +250,19 @@ def test_biomes_with_tracking_are_refused():
     p.set_biomes(util.ref_biomes()[0]["biomes"])
     st = port.run_member_tracked(util.scenarios()["ssp245"], 1750, params=p)[0]
     assert st == 9  # HO_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("case", util.ref_allparams(), ids=lambda c: c["name"])
+def test_all_parameters_at_once_against_reference(case):
+    """all 52 scalar parameters (temperature, land, ocean, solver, forcing, CH4 / OH / O3 / N2O)
+    and tau / rho / delta of four halocarbons perturbed in one run: every input is wired the way
+    the reference wires it -- bit-identical on 12 variables and the sub-step counts"""
+    p = port.default_params()
+    for key, v in case["halo"].items():
+        fld, idx = key[:-1].split("[")
+        getattr(p, fld)[int(idx)] = v
+    st, fy, out, cnt, sp = port.run_member(util.scenarios()[case["scenario"]], params=p,
+                                           **case["params"])
+    assert st == 0
+    for v, ref in case["values"].items():
+        assert np.array_equal(out[port.OUT_NAMES.index(v)], ref), v

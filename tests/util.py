@@ -134,3 +134,14 @@ def ref_biomes():
                                        for k, d in sp.get("constraints", {}).items()},
                           values=dict(zip(variables, z["values"][i])), biome_values=own))
     return cases
+
+
+def ref_allparams():
+    """every scalar parameter perturbed at once (tests/golden/make_golden.py allparams)"""
+    import json
+    z = np.load(os.path.join(GOLDEN, "ref_allparams.npz"))
+    spec = json.loads(str(z["spec"]))
+    variables = [str(v) for v in z["variables"]]
+    return [dict(name=str(n), scenario=str(z["scenarios"][i]), params=spec[i]["params"],
+                 halo=spec[i]["halo"], values=dict(zip(variables, z["values"][i])))
+            for i, n in enumerate(z["names"])]
