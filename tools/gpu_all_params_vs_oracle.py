@@ -8,7 +8,8 @@ the high-latitude box), so the script now reports contract variables (CO2, Tgav:
 secondary ones (5e-8) separately and prints everything before asserting.  A CPU experiment on
 the same 12 members supports the conditioning reading -- moving ONE input (diff) by one ulp moves
 the oracle's own ocean_uptake by up to 2.2e-11 and RF_tot by 8e-12 of their floors, with
-identical sub-step counts -- but does not prove it.  Run this first thing next round; once
+identical sub-step counts, and the oracle built with -ffp-contract=fast differs from itself by up
+to 5.1e-11 (ocean_uptake), 3.7e-11 (RF_tot), 2.9e-11 (global_tas) -- but does not prove it.  Run this first thing next round; once
 understood and green, move it into tests/test_gpu_parity.py.
 
 usage (under gpurun): python tools/gpu_all_params_vs_oracle.py [members] [seed]"""
