@@ -167,12 +167,17 @@ class Ensemble:
         if self.biomes:  # before the outputs: "<biome>.<name>" outputs name a known biome
             arr = (C.c_char_p * len(self.biomes))(*[b.encode() for b in self.biomes])
             self._chk(self.L.hx_set_biomes(self.h, len(self.biomes), arr))
-        self.outputs = list(outputs)
-        arr = (C.c_char_p * len(self.outputs))(*[s.encode() for s in self.outputs])
-        self._chk(self.L.hx_select_outputs(self.h, len(self.outputs), arr))
+        self.select_outputs(outputs)
         if tracking_date is not None:
             self._chk(self.L.hx_set_tracking(self.h, int(tracking_date), int(track_every)))
         self.prepared = False
+
+    def select_outputs(self, outputs):
+        """which variables the run records (before prepare): OUTPUT_VARIABLES names and, once
+        biomes are defined, "<biome>.<name>" with name in BIOME_OUTPUTS"""
+        self.outputs = list(outputs)
+        arr = (C.c_char_p * len(self.outputs))(*[s.encode() for s in self.outputs])
+        self._chk(self.L.hx_select_outputs(self.h, len(self.outputs), arr))
 
     def split_biome(self, new_biomes, fveg_c=None, fdetritus_c=None, fsoil_c=None,
                     fpermafrost_c=None, fnpp_flux0=None, **params):
@@ -198,6 +203,7 @@ class Ensemble:
         arr = (C.c_char_p * n)(*[b.encode() for b in new_biomes])
         self._chk(self.L.hx_set_biomes(self.h, n, arr))
         self.biomes = list(new_biomes)
+        self.select_outputs(self.outputs)  # a new biome list drops per-biome selections
         for i, b in enumerate(new_biomes):
             for k in BIOME_PARAMETERS:
                 if k in fr:
