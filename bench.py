@@ -192,6 +192,75 @@ def workload_config(args):
 
 
 # ------------------------------------------------------------------------------------------
+def roofline_of(kernel, members, years, kernel_ms, hbm_peak, peaks_measured, fp64_peak,
+                traffic_file, counts_file):
+    """The three fractions of one run-kernel launch:
+      frac       SURVEY.md 8(d)'s ALGORITHMIC bytes (5 048 B per member-year of a year-stepped SoA
+                 model) / live kernel time, against the measured HBM copy bandwidth -- how fast
+                 the model is advanced, NOT how busy HBM is;
+      dram_frac  real DRAM traffic of the launch (ncu dram__bytes_read + write, profiles/) /
+                 live kernel time, against the same bandwidth -- how busy HBM really is;
+      fp64       executed FP64 flops (ncu smsp__sass_thread_inst_executed_op_{dfma x2, dmul,
+                 dadd}, per member-year, profiles/) / live kernel time, against the DFMA peak
+                 measured on this GPU right now (hx_measure_fp64_peak)."""
+    achieved = members * years * B_ALG / (kernel_ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+         "frac": achieved / hbm_peak, "traffic": None,
+         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks_measured
+         else "B200_PROFILING.md fallback (of fallback)",
+         "kernel": kernel, "kernel_ms": kernel_ms,
+         "algorithmic_bytes_per_member_year": B_ALG,
+         "binds": "FP64 issue/latency at low occupancy, not HBM: see dram_frac and fp64"}
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))
+        # the capture's ensemble may differ in size from this run's: scale per member-year
+        traffic = t["dram_bytes_per_launch"] * (members * years) / float(
+            t.get("member_years", 65536 * 555))
+        r["traffic"] = traffic
+        r["dram_gbs"] = traffic / (kernel_ms * 1e-3) / 1e9
+        r["dram_frac"] = r["dram_gbs"] / hbm_peak
+        r["traffic_source"] = t.get("source")
+    except Exception:
+        pass
+    try:
+        c = json.load(open(os.path.join(ROOT, "profiles", counts_file)))
+        flops = (2.0 * c["dfma_per_member_year"] + c["dmul_per_member_year"]
+                 + c["dadd_per_member_year"]) * members * years
+        tf = flops / (kernel_ms * 1e-3) / 1e12
+        r["fp64"] = {"achieved_tflops": tf, "peak": fp64_peak,
+                     "frac": tf / fp64_peak if fp64_peak else None, "unit": "TFLOP/s",
+                     "flops_per_member_year": flops / (members * years),
+                     "peak_source": "hx_measure_fp64_peak on this GPU, this run (dependent-FMA "
+                                    "chains, all SMs, CUDA events)",
+                     "counts_source": c.get("source")}
+    except Exception:
+        pass
+    return r
+
+
+def parity_spot(ens, X, n=8, seed=7):
+    """Outside the timed region: CO2 / Tgav of n random members of the ensemble just run against
+    the CPU oracle (the checker; SURVEY.md 8(d) parity metric).  A regression that kept every
+    member's status at 0 would otherwise still print a throughput."""
+    from oracle import port
+    table = scenario_table()
+    pick = sorted(np.random.default_rng(seed).choice(X.shape[0], n, replace=False).tolist())
+    years = np.arange(1746, 2301, dtype=np.float64)
+    co2 = ens.fetch("CO2_concentration", years)
+    tas = ens.fetch("global_tas", years)
+    e_co2 = e_tas = 0.0
+    for i in pick:
+        st, _, out, _, _ = port.run_member(table, S=X[i, 0], q10_rh=X[i, 1], beta=X[i, 2],
+                                           diff=X[i, 3])
+        if st != 0:
+            continue
+        e_co2 = max(e_co2, float(np.max(np.abs(co2[i] - out[0]) / np.maximum(np.abs(out[0]), 1.0))))
+        e_tas = max(e_tas, float(np.max(np.abs(tas[i] - out[1]) / np.maximum(np.abs(out[1]), 0.01))))
+    return {"members": pick, "CO2_concentration": e_co2, "global_tas": e_tas, "tolerance": 1e-10,
+            "ok": bool(e_co2 <= 1e-10 and e_tas <= 1e-10),
+            "metric": "max_t |x - oracle| / max(|oracle|, floor), floor 1 ppm / 0.01 degC"}
+
+
 class CudaArrayView:
     """zero-copy view of an engine output block for torch (NCCL gathers)"""
 
@@ -384,6 +453,17 @@ def main():
     cnt = ens.counters()
     st, _ = ens.status()
     failed = int((st != 0).sum())
+    spot = None
+    fp64_peak = None
+    if rank == 0:
+        try:
+            spot = parity_spot(ens, X)
+        except Exception as ex:  # the checker is optional for the measurement
+            spot = {"ok": None, "error": repr(ex)}
+        import ctypes as C
+        tf = C.c_double()
+        if hb._capi.lib().hx_measure_fp64_peak(local_rank, C.byref(tf), None) == 0:
+            fp64_peak = tf.value
 
     # ---- end to end through the public API with host buffers ----
     e2e = None
@@ -417,7 +497,8 @@ def main():
         es = make_engine(ms_, lhs(ms_))
         sm_ms, sm_k = timed(es, lambda e: (e.reset(), e.run()), args.steps, 3, True)
         small = {"members": ms_, "value": ms_ * YEARS / (sm_ms / args.steps * 1e-3), "unit": UNIT,
-                 "ms_per_step": sm_ms / args.steps, "note": "BASELINE.json configs[1]; fills "
+                 "ms_per_step": sm_ms / args.steps, "kernel_ms": sm_k,
+                 "note": "BASELINE.json configs[1]; fills "
                  "%d of 148 SMs' worth of CTAs" % ((ms_ + 127) // 128)}
         es.close()
 
@@ -511,20 +592,12 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = M * YEARS * B_ALG / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))[
-            "dram_bytes_per_launch"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks
-                else "B200_PROFILING.md fallback (of fallback)",
-                "kernel": "hx_run_kernel", "kernel_ms": kernel_ms,
-                "algorithmic_bytes_per_member_year": B_ALG,
-                "note": "FP64 issue/latency binds before HBM on this path (SURVEY.md 8(d))"}
+    roofline = roofline_of("hx_run_kernel", M, YEARS, kernel_ms, peak, bool(peaks), fp64_peak,
+                           "latest_traffic.json", "latest_fp64_counts.json")
+    if small is not None:
+        small["roofline"] = roofline_of("hx_run_kernel (1 024 members)", small["members"], YEARS,
+                                        small["kernel_ms"], peak, bool(peaks), fp64_peak,
+                                        "latest_traffic_small.json", "latest_fp64_counts.json")
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -550,7 +623,7 @@ def main():
         "work_per_member_year": {k: cnt[k] / max(1, cnt["member_years"]) for k in
                                  ("rhs_evals", "rk_steps", "stashes", "newton_iterations",
                                   "newton_calls")},
-        "failed_members": failed, "small_ensemble": small, "multi_scenario_ensemble": multi,
+        "failed_members": failed, "parity_spot": spot, "small_ensemble": small, "multi_scenario_ensemble": multi,
         "tracked_ensemble": tracked,
         "biome_ensemble": biome,
         "exchange": None if world == 1 else

@@ -17,7 +17,7 @@ EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "h
            "hx_prepare", "hx_run", "hx_run_stream", "hx_reset", "hx_reset_date", "hx_synchronize", "hx_fetch", "hx_output_device",
            "hx_ipc_export", "hx_ipc_open", "hx_ipc_pull", "hx_ipc_wait", "hx_ipc_close",
            "hx_event_record", "hx_event_synchronize", "hx_member_status", "hx_set_tracking", "hx_set_biomes", "hx_biome_count", "hx_fetch_tracking", "hx_tracking_years", "hx_counters", "hx_current_date", "hx_last_run_ms",
-           "hx_spinup_state", "hx_version"]
+           "hx_spinup_state", "hx_measure_fp64_peak", "hx_measure_hbm_copy", "hx_version"]
 
 
 class HxError(RuntimeError):
@@ -94,5 +94,7 @@ def lib():
     L.hx_last_run_ms.argtypes = [vp]
     L.hx_last_run_ms.restype = C.c_double
     L.hx_spinup_state.argtypes = [vp, C.c_int32, dp]
+    L.hx_measure_fp64_peak.argtypes = [C.c_int32, dp, dp]
+    L.hx_measure_hbm_copy.argtypes = [C.c_int32, dp]
     _LIB = L
     return L

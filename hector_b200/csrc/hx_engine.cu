@@ -144,6 +144,7 @@ struct Engine {
   double *d_T = nullptr, *d_TO = nullptr, *d_REC = nullptr;
   unsigned char *d_YCNT = nullptr;
   uint32_t *d_TK = nullptr, *d_TOK = nullptr;
+  int32_t *d_trk_fail = nullptr; /* [Mpad] year in which the replay saw a bad mix (0: none) */
   size_t stage_bytes = 0, yidx_cap = 0;
   double *h_pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -357,7 +358,7 @@ struct Engine {
   void free_device() {
     void *ptrs[] = {d_BP, d_BF, d_BF_snap, d_P, d_S, d_S_snap, d_D, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
                     d_block_scen, d_status, d_status_snap, d_status_post, d_fail_year, d_spinup_steps, d_yidx,
-                    d_counters, d_dev_of_api, d_sched, d_T, d_TO, d_TK, d_TOK, d_REC, d_YCNT};
+                    d_counters, d_dev_of_api, d_sched, d_T, d_TO, d_TK, d_TOK, d_REC, d_YCNT, d_trk_fail};
     for (void *p : ptrs)
       if (p) cudaFree(p);
     d_P = d_S = d_S_snap = d_D = d_ker = d_conv = d_sst = d_tland = d_out = d_scen = d_stage = nullptr;
@@ -367,6 +368,7 @@ struct Engine {
     d_T = d_TO = d_REC = nullptr;
     d_YCNT = nullptr;
     d_TK = d_TOK = nullptr;
+    d_trk_fail = nullptr;
     d_BP = d_BF = d_BF_snap = nullptr;
     d_dev_of_api = nullptr;
     stage_bytes = 0;
@@ -481,12 +483,15 @@ struct Engine {
       if (e != cudaSuccess) return e;
       ra = re;
     }
-    /* whatever follows on the engine's stream sees the maps and statuses of every replay */
+    /* whatever follows on the engine's stream sees the maps of every replay; the replays
+     * report a bad mix through a word of their own (the run kernel of the next slab reads and
+     * writes the status words meanwhile), folded into the status here, in stream order */
     for (int b = 0; b < 2; ++b)
       if (used[b]) {
         cudaError_t e = cudaStreamWaitEvent(stream, ev_rec_free[b], 0);
         if (e != cudaSuccess) return e;
       }
+    if (used[0] || used[1]) return hx::launch_track_merge(d, stream);
     return cudaSuccess;
   }
 
@@ -580,6 +585,7 @@ struct Engine {
       CUDA_TRY(hx::launch_spinup(d, C, stream));
     }
     if (d_T) CUDA_TRY(hx::launch_track_init(d, stream));
+    if (d_trk_fail) CUDA_TRY(cudaMemsetAsync(d_trk_fail, 0, (size_t)Mpad * sizeof(int32_t), stream));
     CUDA_TRY(cudaMemcpyAsync(d_S_snap, d_S, (size_t)SI_COUNT * Mpad * sizeof(double),
                              cudaMemcpyDeviceToDevice, stream));
     if (d_BF)
@@ -1188,30 +1194,39 @@ int hx_prepare(hx_handle h) {
         cudaMalloc(&h->d_TO, h->track_years.size() * HX_NPOOL * HX_NSRC * Mp * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_TOK, h->track_years.size() * HX_NPOOL * Mp * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&h->d_REC, 2 * block_scen.size() * hx::track_record_bytes_per_cta()) != cudaSuccess ||
-        cudaMalloc(&h->d_YCNT, 2 * block_scen.size() * hx::track_ycnt_bytes_per_tile()) != cudaSuccess))) {
+        cudaMalloc(&h->d_YCNT, 2 * block_scen.size() * hx::track_ycnt_bytes_per_tile()) != cudaSuccess ||
+        cudaMalloc(&h->d_trk_fail, Mp * sizeof(int32_t)) != cudaSuccess))) {
     cudaError_t e = cudaGetLastError();
     h->free_device();
     return fail(HX_ERR_CUDA, (std::string("device allocation failed: ") + cudaGetErrorString(e)).c_str());
   }
   cudaStream_t st = h->stream;
-  cudaMemcpyAsync(h->d_scen, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(h->d_block_scen, block_scen.data(), block_scen.size() * sizeof(int32_t),
-                  cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(h->d_status_snap, status.data(), Mp * sizeof(int32_t), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(h->d_dev_of_api, h->dev_of_api.data(), (size_t)M * sizeof(int32_t),
-                  cudaMemcpyHostToDevice, st);
-  cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st);
-  cudaMemsetAsync(h->d_fail_year, 0, Mp * sizeof(int32_t), st);
-  cudaMemsetAsync(h->d_spinup_steps, 0, Mp * sizeof(int32_t), st);
-  cudaMemsetAsync(h->d_S, 0, SI_COUNT * Mp * sizeof(double), st);
-  cudaMemsetAsync(h->d_D, 0, DI_COUNT * Mp * sizeof(double), st);
-  cudaMemsetAsync(h->d_ker, 0, (size_t)HX_KER_ROWS(nrow) * Mp * sizeof(double), st);
-  cudaMemsetAsync(h->d_conv, 0, (size_t)HX_SLAB_YEARS * Mp * sizeof(double), st);
-  cudaMemsetAsync(h->d_sst, 0, (size_t)nrow * Mp * sizeof(double), st);
-  cudaMemsetAsync(h->d_tland, 0, (size_t)nrow * Mp * sizeof(double), st);
-  if (h->d_BF) cudaMemsetAsync(h->d_BF, 0, (size_t)nb * BF_COUNT * Mp * sizeof(double), st);
-  if (cudaStreamSynchronize(st) != cudaSuccess)
-    return fail(HX_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+  {
+    cudaError_t e = cudaMemcpyAsync(h->d_scen, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+    auto also = [&e](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    also(cudaMemcpyAsync(h->d_block_scen, block_scen.data(), block_scen.size() * sizeof(int32_t),
+                         cudaMemcpyHostToDevice, st));
+    also(cudaMemcpyAsync(h->d_status_snap, status.data(), Mp * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    also(cudaMemcpyAsync(h->d_dev_of_api, h->dev_of_api.data(), (size_t)M * sizeof(int32_t),
+                         cudaMemcpyHostToDevice, st));
+    also(cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st));
+    also(cudaMemsetAsync(h->d_fail_year, 0, Mp * sizeof(int32_t), st));
+    also(cudaMemsetAsync(h->d_spinup_steps, 0, Mp * sizeof(int32_t), st));
+    also(cudaMemsetAsync(h->d_S, 0, SI_COUNT * Mp * sizeof(double), st));
+    also(cudaMemsetAsync(h->d_D, 0, DI_COUNT * Mp * sizeof(double), st));
+    also(cudaMemsetAsync(h->d_ker, 0, (size_t)HX_KER_ROWS(nrow) * Mp * sizeof(double), st));
+    also(cudaMemsetAsync(h->d_conv, 0, (size_t)HX_SLAB_YEARS * Mp * sizeof(double), st));
+    also(cudaMemsetAsync(h->d_sst, 0, (size_t)nrow * Mp * sizeof(double), st));
+    also(cudaMemsetAsync(h->d_tland, 0, (size_t)nrow * Mp * sizeof(double), st));
+    if (h->d_BF) also(cudaMemsetAsync(h->d_BF, 0, (size_t)nb * BF_COUNT * Mp * sizeof(double), st));
+    if (h->d_trk_fail) also(cudaMemsetAsync(h->d_trk_fail, 0, Mp * sizeof(int32_t), st));
+    /* the host vectors above must outlive the copies */
+    also(cudaStreamSynchronize(st));
+    if (e != cudaSuccess) {
+      h->free_device();
+      return fail(HX_ERR_CUDA, (std::string("hx_prepare uploads: ") + cudaGetErrorString(e)).c_str());
+    }
+  }
 
   HxDev &d = h->d;
   d.Mpad = Mpad; d.P = h->d_P; d.S = h->d_S; d.D = h->d_D; d.ker = h->d_ker; d.conv = h->d_conv;
@@ -1219,7 +1234,7 @@ int hx_prepare(hx_handle h) {
   d.block_scen = h->d_block_scen; d.status = h->d_status; d.fail_year = h->d_fail_year;
   d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters; d.sched = h->d_sched;
   d.T = h->d_T; d.TK = h->d_TK; d.TO = h->d_TO; d.TOK = h->d_TOK; d.REC = h->d_REC; d.YCNT = h->d_YCNT;
-  d.BP = h->d_BP; d.BF = h->d_BF;
+  d.BP = h->d_BP; d.BF = h->d_BF; d.trk_fail = h->d_trk_fail;
   h->rec_elems = block_scen.size() * hx::track_record_bytes_per_cta() / sizeof(double);
   h->ycnt_bytes = block_scen.size() * hx::track_ycnt_bytes_per_tile();
   h->tables_constrained = any_constraint;
@@ -1270,6 +1285,8 @@ int hx_reset(hx_handle h) {
     e = cudaMemcpyAsync(h->d_status, h->d_status_post, (size_t)h->Mpad * sizeof(int32_t),
                         cudaMemcpyDeviceToDevice, h->stream);
   if (e == cudaSuccess && h->d_T) e = hx::launch_track_init(h->d, h->stream);
+  if (e == cudaSuccess && h->d_trk_fail)
+    e = cudaMemsetAsync(h->d_trk_fail, 0, (size_t)h->Mpad * sizeof(int32_t), h->stream);
   if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
   h->cur_row = 0;
   return HX_OK;
@@ -1297,6 +1314,12 @@ int hx_run(hx_handle h, double run_to_date) {
   if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_run before hx_prepare");
   cudaSetDevice(h->cfg.device);
   if (h->params_dirty) {
+    /* The reference would carry the old state on with the new values; the engine holds no
+     * history to do that from, and silently restarting from start_year would also overrun a
+     * caller's buffer sized from hx_current_date.  Mid-run changes need an explicit reset. */
+    if (h->cur_row > 0)
+      return h->fail(HX_ERR_STATE, "parameters or inputs changed since the run began: call "
+                                   "hx_reset (or hx_reset_date) before running on");
     int rc = h->run_setup_and_spinup();
     if (rc) return rc;
   }
@@ -1305,15 +1328,17 @@ int hx_run(hx_handle h, double run_to_date) {
   const int r1 = to - h->cfg.start_year;
   if (r1 <= h->cur_row) return HX_OK; /* "Requested run-to date <= current date. Models not run." */
   cudaStream_t st = h->stream;
-  cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st);
-  cudaEventRecord(h->ev0, st);
-  cudaError_t e = h->launch_rows(h->cur_row, r1);
+  cudaError_t e = cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st);
+  if (e == cudaSuccess) e = cudaEventRecord(h->ev0, st);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_run: ") + cudaGetErrorString(e));
+  e = h->launch_rows(h->cur_row, r1);
   if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("run kernel launch: ") + cudaGetErrorString(e));
   if (!h->out_sel.empty()) {
     e = hx::launch_nan_fill(h->d, h->C, (int)h->out_sel.size(), h->cur_row, r1, st);
     if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("nan fill launch: ") + cudaGetErrorString(e));
   }
-  cudaEventRecord(h->ev1, st);
+  e = cudaEventRecord(h->ev1, st);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_run: ") + cudaGetErrorString(e));
   h->cur_row = r1;
   return HX_OK;
 }
@@ -1329,6 +1354,12 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
   if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_run_stream before hx_prepare");
   cudaSetDevice(h->cfg.device);
   if (h->params_dirty) {
+    /* The reference would carry the old state on with the new values; the engine holds no
+     * history to do that from, and silently restarting from start_year would also overrun a
+     * caller's buffer sized from hx_current_date.  Mid-run changes need an explicit reset. */
+    if (h->cur_row > 0)
+      return h->fail(HX_ERR_STATE, "parameters or inputs changed since the run began: call "
+                                   "hx_reset (or hx_reset_date) before running on");
     int rc = h->run_setup_and_spinup();
     if (rc) return rc;
   }
@@ -1366,8 +1397,11 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
   if (segments > nslab) segments = nslab;
   cudaStream_t st = h->stream;
   const int ny = r1 - r0; /* columns... rows of the caller's [year][member] blocks */
-  cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st);
-  cudaEventRecord(h->ev0, st);
+  {
+    cudaError_t e0 = cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st);
+    if (e0 == cudaSuccess) e0 = cudaEventRecord(h->ev0, st);
+    if (e0 != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_run_stream: ") + cudaGetErrorString(e0));
+  }
   /* Segment lengths halve: a segment's device-to-host copy hides behind the next segment's
    * computation (the copy engine is ~3x faster than the run per year), so only the LAST
    * segment's copy is exposed -- keep that one short instead of splitting evenly. */
@@ -1382,8 +1416,9 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
     if (e == cudaSuccess && !h->out_sel.empty())
       e = hx::launch_nan_fill(h->d, h->C, (int)h->out_sel.size(), ra, rb, st);
     if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("run segment: ") + cudaGetErrorString(e));
-    cudaEventRecord(h->ev_seg, st);
-    cudaStreamWaitEvent(h->copy_stream, h->ev_seg, 0);
+    e = cudaEventRecord(h->ev_seg, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->copy_stream, h->ev_seg, 0);
+    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_run_stream: ") + cudaGetErrorString(e));
     for (int v = 0; v < n_vars; ++v) {
       /* years ra+1 .. rb are output rows ra .. rb-1 of the variable's [year][Mpad] block */
       const double *src = h->d_out + ((size_t)slot[v] * (h->nrow - 1) + ra) * h->Mpad;
@@ -1396,12 +1431,12 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
     ra = rb;
   }
   (void)ny;
-  cudaEventRecord(h->ev1, st);
+  cudaError_t e = cudaEventRecord(h->ev1, st);
   /* the caller's stream must see the copies as done */
-  cudaEventRecord(h->ev_copy, h->copy_stream);
-  cudaStreamWaitEvent(st, h->ev_copy, 0);
+  if (e == cudaSuccess) e = cudaEventRecord(h->ev_copy, h->copy_stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->ev_copy, 0);
   h->cur_row = r1;
-  cudaError_t e = cudaStreamSynchronize(h->copy_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->copy_stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_run_stream: ") + cudaGetErrorString(e));
   return HX_OK;
@@ -1559,12 +1594,14 @@ int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates
     h->yidx_cap = n_dates;
   }
   cudaStream_t st = h->stream;
-  cudaMemcpyAsync(h->d_yidx, yidx.data(), (size_t)n_dates * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  cudaError_t e = cudaMemcpyAsync(h->d_yidx, yidx.data(), (size_t)n_dates * sizeof(int32_t),
+                                  cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_fetch: ") + cudaGetErrorString(e));
   const double *src = h->d_out + (size_t)slot * (h->nrow - 1) * h->Mpad;
   dim3 grid((h->M + 31) / 32, (n_dates + 31) / 32), block(32, 8);
   k_fetch_transpose<<<grid, block, 0, st>>>(h->d_stage, src, h->d_yidx, h->d_dev_of_api, n_dates,
                                            h->M, (size_t)h->Mpad);
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(out, h->d_stage, (size_t)h->M * n_dates * sizeof(double),
                         cudaMemcpyDeviceToHost, st);
@@ -1621,14 +1658,15 @@ int hx_fetch_tracking(hx_handle h, double date, double *frac, uint32_t *mask) {
         return h->fail(HX_ERR_CUDA, "cudaMalloc yidx");
       h->yidx_cap = nq;
     }
-    cudaMemcpyAsync(h->d_yidx, yidx.data(), (size_t)nq * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    e = cudaMemcpyAsync(h->d_yidx, yidx.data(), (size_t)nq * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_fetch_tracking: ") + cudaGetErrorString(e));
     dim3 grid((h->M + 31) / 32, (nq + 31) / 32), block(32, 8);
     k_fetch_transpose<<<grid, block, 0, st>>>(sf, h->d_TO + (size_t)rec * nq * h->Mpad, h->d_yidx,
                                              h->d_dev_of_api, nq, h->M, (size_t)h->Mpad);
     k_fetch_masks<<<(h->M * HX_NPOOL + 255) / 256, 256, 0, st>>>(
         sm, h->d_TOK + (size_t)rec * HX_NPOOL * h->Mpad, h->d_dev_of_api, HX_NPOOL, h->M,
         (size_t)h->Mpad);
-    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
   } else if (y == cur) {
     /* not a recorded year, but the live maps are this year's */
     k_gather_track<<<(h->M * nq + 255) / 256, 256, 0, st>>>(sf, sm, h->d_T, h->d_TK,
@@ -1670,8 +1708,8 @@ int hx_member_status(hx_handle h, int32_t *status, int32_t *fail_year, int32_t n
   if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_member_status before hx_prepare");
   cudaSetDevice(h->cfg.device);
   std::vector<int32_t> st(h->Mpad), fy(h->Mpad);
-  cudaStreamSynchronize(h->stream);
-  cudaError_t e = cudaMemcpy(st.data(), h->d_status, (size_t)h->Mpad * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(st.data(), h->d_status, (size_t)h->Mpad * sizeof(int32_t), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess)
     e = cudaMemcpy(fy.data(), h->d_fail_year, (size_t)h->Mpad * sizeof(int32_t), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
@@ -1687,8 +1725,8 @@ int hx_counters(hx_handle h, uint64_t *out, int32_t n) {
   if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_counters before hx_prepare");
   cudaSetDevice(h->cfg.device);
   unsigned long long tmp[HX_NCOUNTERS];
-  cudaStreamSynchronize(h->stream);
-  cudaError_t e = cudaMemcpy(tmp, h->d_counters, sizeof tmp, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(tmp, h->d_counters, sizeof tmp, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
   for (int i = 0; i < n && i < HX_NCOUNTERS; ++i) out[i] = tmp[i];
   return HX_OK;
@@ -1708,7 +1746,8 @@ int hx_spinup_state(hx_handle h, int32_t member, double *out14) {
     if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
   }
   int32_t steps = 0;
-  cudaMemcpy(&steps, h->d_spinup_steps + dm, sizeof steps, cudaMemcpyDeviceToHost);
+  if (cudaMemcpy(&steps, h->d_spinup_steps + dm, sizeof steps, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return h->fail(HX_ERR_CUDA, "hx_spinup_state: copy failed");
   out14[13] = steps;
   return HX_OK;
 }

@@ -19,6 +19,8 @@
 
 namespace hx {
 
+#define HX_MAX_DEVICES 64 /* device ordinals with cached launch parameters */
+
 /* run-kernel dynamic shared memory map (bytes) */
 #define HX_SMEM_SLAB_BYTES ((HX_SLAB_YEARS + 1) * SC_STRIDE * 8)
 #define HX_SMEM_ROW0 HX_SMEM_SLAB_BYTES
@@ -1107,9 +1109,21 @@ hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
                                             C.start_year + r0 + 1, s * HX_TRK_NS,
                                             (s + 1) * HX_TRK_NS, C.tracking_date, C.track_every, C.track_nrec,
                                     C.end_year, d.TO + m, d.TOK + m, (size_t)d.Mpad);
-  if (s * HX_TRK_NS < HX_NSRC && !good && d.status[m] == 0) {
+  /* a bad mix is reported through the replay's own word: the status words belong to the run
+   * kernel, which may already be computing the next slab on the other stream.  Replays of one
+   * engine run in order, so the first failing slab's year sticks; the lanes of a member that
+   * disagree all store the same value. */
+  if (s * HX_TRK_NS < HX_NSRC && !good && d.trk_fail[m] == 0) d.trk_fail[m] = C.start_year + r0 + 1;
+}
+
+__global__ void hx_track_merge_kernel(const __grid_constant__ HxDev d) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= d.Mpad) return;
+  const int y = d.trk_fail[m];
+  if (y == 0 || d.status[m] < 0) return;
+  if (d.status[m] == 0 || d.fail_year[m] > y) {
     d.status[m] = HX_MEMBER_TRACKING;
-    d.fail_year[m] = C.start_year + r0 + 1;
+    d.fail_year[m] = y;
   }
 }
 
@@ -1144,24 +1158,26 @@ cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cuda
 template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT = true, bool BIOMES = false,
           bool NBP = CONSTR>
 static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  /* the function attribute and the occupancy are per device (context): one cache slot per
+   * device ordinal, so that engines on several GPUs can live in one process */
+  static int resident_of[HX_MAX_DEVICES] = {};
+  int dev = 0;
+  cudaError_t e0 = cudaGetDevice(&dev);
+  if (e0 != cudaSuccess) return e0;
+  if (dev < 0 || dev >= HX_MAX_DEVICES) return cudaErrorInvalidDevice;
+  if (!resident_of[dev]) {
     cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  static int resident = 0;
-  if (!resident) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
+    int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP>,
-                                                                  HX_BLOCK, HX_SMEM_RUN_BYTES);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP>,
+                                                      HX_BLOCK, HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
-    resident = sms * (per_sm > 0 ? per_sm : 1);
+    resident_of[dev] = sms * (per_sm > 0 ? per_sm : 1);
   }
+  const int resident = resident_of[dev];
   /* persistent CTAs: never more than can be co-resident (an item may wait on another CTA) */
   const int ntiles = d.Mpad / HX_BLOCK;
   const int grid = ntiles < resident ? ntiles : resident;
@@ -1209,6 +1225,10 @@ int track_slab_years() { return HX_SLAB_YEARS; }
 cudaError_t launch_track(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
   const long long threads = (long long)d.Mpad * HX_TRK_LANES;
   hx_track_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(d, C, r0, r1);
+  return cudaGetLastError();
+}
+cudaError_t launch_track_merge(const HxDev &d, cudaStream_t st) {
+  hx_track_merge_kernel<<<(d.Mpad + 255) / 256, 256, 0, st>>>(d);
   return cudaGetLastError();
 }
 cudaError_t launch_track_init(const HxDev &d, cudaStream_t st) {

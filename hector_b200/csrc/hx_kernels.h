@@ -59,6 +59,8 @@ struct HxDev {
   const double *BP;         /* [tile][n_biomes * BP_COUNT][128] per-biome parameters */
   double *BF;               /* [tile][n_biomes * BF_COUNT][128] per-biome pools and factors */
   uint32_t *TOK;            /* [track_nrec][HX_NPOOL][Mpad] recorded key masks */
+  int32_t *trk_fail;        /* [Mpad] first year whose replay saw a bad mix, 0 = none: written by
+                               the replay kernel only, folded into status by hx_track_merge */
 };
 
 namespace hx {
@@ -74,6 +76,8 @@ size_t track_ycnt_bytes_per_tile();
 int track_slab_years();
 /* replay the records of rows r0+1 .. r1 (one slab, as just run) into the source maps */
 cudaError_t launch_track(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st);
+/* fold the replays' failure words into status / fail_year (earliest failing year wins) */
+cudaError_t launch_track_merge(const HxDev &d, cudaStream_t st);
 cudaError_t launch_nan_fill(const HxDev &d, const HxConst &C, int nsel, int yr0, int yr1,
                             cudaStream_t st);
 }

@@ -93,6 +93,11 @@ enum {
   SI_X_NPP, SI_X_RH, /* final_npp / final_rh of the year's last stash (outputs NPP, RH) */
   SI_X_C_CO2, /* this year's CO2 constraint (NaN = none), read by the year's last stash */
   SI_X_C_NBP0, SI_X_C_NBP1, /* NBP constraints of year y-1 and y: round(t) picks one */
+  /* the solver's own thawed-permafrost and ocean totals after the last sub-step: a sub-step that
+   * follows a stash without a retry continues from them, not from the pools (the stash zeroes a
+   * thawed pool below 1e-10 and the four boxes sum to the solver's total only to the last ulps;
+   * carbon-cycle-solver.cpp:232, 279) */
+  SI_X_SOLVER_TPF, SI_X_SOLVER_OCEAN,
   SI_COUNT
 };
 

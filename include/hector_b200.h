@@ -145,7 +145,13 @@ int hx_get_param(hx_handle h, const char *name, double *per_member_out, int32_t 
 int hx_select_outputs(hx_handle h, int32_t n, const char *const *names);
 
 int hx_prepare(hx_handle h);
-int hx_run(hx_handle h, double run_to_date); /* < 0: run to end_year; resumes where it left off */
+/* Core::run(runtodate) (core.cpp:448-509).  < 0: run to end_year; resumes where it left off.
+ * After a parameter or input change (hx_set_param*, hx_set_scenario_series) the next run starts
+ * over from start_year with a fresh set-up and spin-up, like R's setvar + reset + run; when the
+ * change is made in the MIDDLE of a run (current date > start_year) hx_run and hx_run_stream
+ * refuse with HX_ERR_STATE until hx_reset / hx_reset_date is called -- the reference would carry
+ * the old state on with the new values, which needs a state history the engine does not keep. */
+int hx_run(hx_handle h, double run_to_date);
 int hx_reset(hx_handle h);                   /* back to the post-spin-up state at start_year */
 /* Core::reset(resetdate) (core.cpp:511-549): date <= start_year is hx_reset; a date inside the
  * run restores the state of that year so that hx_run continues from it.  The engine keeps no
@@ -245,6 +251,14 @@ double hx_last_run_ms(hx_handle h);
 /* post-spin-up snapshot of member m: atmos, veg, det, soil, permafrost, thawed, earth,
  * HL, LL, IO, DO, alk_HL, alk_LL, spinup_steps (14 doubles; alk valid after the first year) */
 int hx_spinup_state(hx_handle h, int32_t member, double *out14);
+
+/* ---- diagnostics: the denominators of the roofline bench.py reports ("FP64
+ * peak is not in MEASURED_PEAKS.json; the builder must microbenchmark it").  No reference
+ * counterpart.  hx_measure_fp64_peak: dependent-FMA chains on every SM, best of three launches,
+ * TFLOP/s (2 flops per FMA) and FMAs per clock per SM at the nominal SM clock;
+ * hx_measure_hbm_copy: device-to-device copy of 1 GiB, read + write GB/s. ---- */
+int hx_measure_fp64_peak(int32_t device, double *tflops, double *fma_per_clk_per_sm);
+int hx_measure_hbm_copy(int32_t device, double *gbs);
 
 const char *hx_version(void);
 

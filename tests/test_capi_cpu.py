@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_symbols():
     txt = open(os.path.join(ROOT, "include", "hector_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(hx_[a-z_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(hx_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_and_binding_agree():

@@ -15,8 +15,10 @@ CONTRACT = ("CO2_concentration", "global_tas")
 # Secondary diagnostics of the extreme-corner members (S = 6, q10 = 3.5 ...): the high-latitude
 # surface box there amplifies any 1-ulp difference (libm, FMA) by ~1.25x per year for decades
 # (measured: HL_PCO2 reaches 7.5e-9 by 2230 with identical sub-step counts, with either Newton
-# start), so only the contract variables are held to 1e-10 for those members.
-TOL_SECONDARY_CORNER = 5e-8
+# start; ocean_uptake 5.2e-8 of its 1 Pg C/yr floor), so only the contract variables are held to
+# 1e-10 for those members and the amplified diagnostics to a bound above what any last-ulp
+# variation of the arithmetic was seen to reach.
+TOL_SECONDARY_CORNER = 2e-7
 
 
 def _engine(n, scen="ssp245", outputs=None, **kw):
@@ -213,6 +215,45 @@ def test_error_behaviour():
     x = ens.fetch("CO2_concentration", [1800.0])      # engine still usable after errors
     assert x.shape == (2, 1) and x[0, 0] > 277
     ens.close()
+
+
+def test_parameter_change_inside_a_run_needs_a_reset():
+    """a setvar in the middle of a run used to restart silently from start_year and
+    overrun run_stream's buffers (sized from the current date); it is refused until reset()"""
+    import hector_b200 as hb
+    ens = _engine(4, outputs=["CO2_concentration"])
+    ens.run(1900)
+    before = ens.fetch("CO2_concentration", [1900.0])
+    ens.setvar("S", 4.0)
+    with pytest.raises(hb.HxError):
+        ens.run(2000)
+    with pytest.raises(hb.HxError):
+        ens.run_stream(["CO2_concentration"], to_date=2000)
+    assert ens.current_date == 1900                     # nothing ran, nothing was overwritten
+    assert np.array_equal(ens.fetch("CO2_concentration", [1900.0]), before)
+    ens.reset()
+    got = ens.run_stream(["CO2_concentration"], to_date=2000)
+    assert got["CO2_concentration"].shape == (255, 4) and ens.current_date == 2000
+    ens.close()
+
+
+def test_two_engines_in_one_process():
+    """two live engines (a second device when the box has one): the launch parameters the
+    kernels cache are per device"""
+    import torch
+    import hector_b200 as hb
+    dev2 = 1 if torch.cuda.device_count() > 1 else 0
+    a = hb.Ensemble(130, util.scenarios()["ssp245"], device=0)
+    b = hb.Ensemble(130, util.scenarios()["ssp245"], device=dev2)
+    S = np.linspace(2.0, 5.0, 130)
+    for e in (a, b):
+        e.setvar("S", S)
+    a.run(); b.run()
+    ga, gb = a.fetchvars(_years()), b.fetchvars(_years())
+    for v in ga:
+        assert np.array_equal(ga[v], gb[v]), v
+    a.close()
+    b.close()
 
 
 def test_engine_from_ini_equals_engine_from_tables():

@@ -1,0 +1,187 @@
+"""GPU parity at the sizes and shapes bench.py measures (VERDICT r01 "weak" #2): the 65 536-member
+headline ensemble, all eight SSP scenarios interleaved, the tracked SSP5-8.5 run to 2500 with the
+six Monte-Carlo parameters, and every per-member parameter perturbed at once -- each against the
+CPU oracle (oracle/hector_oracle.c, bit-identical to the unmodified reference) on a seeded sample.
+
+Tolerance: 1e-10 on CO2 and Tgav with SURVEY.md section 8(d)'s metric
+(max_t |x - ref| / max(|ref|, floor), floor_tas = 0.01 degC), sub-step counts and failure
+verdicts exactly; the reference's own regression test uses the same 1e-10
+(tests/testthat/test_old-new.R:8-36)."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+# All 38 outputs under the all-parameter draw are held to the same 1e-10.  Round 1 closed with
+# this probe tripping that bound on thawedp_c (1.37e-10 Pg C): not conditioning but a real
+# divergence -- a sub-step that follows a stash without a retry continues from the SOLVER's pool
+# vector (carbon-cycle-solver.cpp:232, 279), the kernel re-read the pools, and the stash had just
+# zeroed a thawed pool below 1e-10 (simpleNbox-runtime.cpp:337-340); fixed in solver_year.  What
+# remains is the conditioning the oracle shows against itself (tools/conditioning_probe.py:
+# rebuilt with FMA contraction it moves by up to 4.4e-11 on ocean_uptake, 4.0e-11 on RF_tot and
+# 3.7e-11 on global_tas for the worst members of this draw).
+TOL_SECONDARY = 1e-10
+SSPS = ["ssp119", "ssp126", "ssp245", "ssp370", "ssp434", "ssp460", "ssp534-over", "ssp585"]
+PARAMS4 = ["S", "q10_rh", "beta", "diff"]
+PARAMS6 = PARAMS4 + ["aero_scalar", "vol_scalar"]
+
+
+def _years(a=1746, b=2300):
+    return np.arange(a, b + 1, dtype=np.float64)
+
+
+def _check(got, i, out, what):
+    e1 = util.parity_err(got["CO2_concentration"][i], out[0], "CO2_concentration")
+    e2 = util.parity_err(got["global_tas"][i], out[1], "global_tas")
+    assert e1 < TOL and e2 < TOL, (what, i, e1, e2)
+    assert np.array_equal(got["ocean_timesteps"][i], out[-1]), (what, i, "sub-step counts")
+    return e1, e2
+
+
+def test_headline_65536_members_sampled_vs_oracle():
+    """BASELINE.json configs[2] / bench.py's headline workload at full size: 256 random members
+    of the 65 536-member Latin hypercube against the oracle, plus whole-ensemble properties."""
+    from oracle import port
+    import hector_b200 as hb
+    M = 65536
+    X = util.lhs(M)
+    outs = ["CO2_concentration", "global_tas", "ocean_timesteps"]
+    ens = hb.Ensemble(M, util.scenarios()["ssp245"], outputs=outs)
+    for j, n in enumerate(PARAMS4):
+        ens.setvar(n, X[:, j])
+    ens.run()
+    st, _ = ens.status()
+    got = ens.fetchvars(_years(), outs)
+    assert int((st != 0).sum()) == 0
+    assert np.isfinite(got["CO2_concentration"]).all() and np.isfinite(got["global_tas"]).all()
+    # Tgav is exactly 0 until the base year for every member (forcing_component.cpp:309-311)
+    assert np.all(got["global_tas"][:, :4] == 0.0)
+    raw = util.scenarios()["ssp245"]
+    pick = np.random.default_rng(2).choice(M, 256, replace=False)
+    worst = [0.0, 0.0]
+    for i in pick:
+        ost, _, out, _, _ = port.run_member(raw, S=X[i, 0], q10_rh=X[i, 1], beta=X[i, 2],
+                                            diff=X[i, 3])
+        assert ost == 0
+        e = _check(got, i, out, "headline")
+        worst = [max(a, b) for a, b in zip(worst, e)]
+    print("headline sample: worst CO2 %.3g  Tgav %.3g" % tuple(worst))
+    # a second run of the same engine is bit-identical (determinism at size)
+    ens.reset()
+    ens.run()
+    again = ens.fetch("CO2_concentration", _years())
+    assert np.array_equal(again, got["CO2_concentration"])
+    ens.close()
+
+
+def test_eight_ssps_interleaved_vs_oracle():
+    """BASELINE.json configs[3] shape: member i runs scenario i mod 8 in API order; every member
+    of a 512-member ensemble (64 per scenario) against the oracle."""
+    from oracle import port
+    import hector_b200 as hb
+    tabs = util.scenarios()
+    M = 512
+    ms = np.arange(M) % 8
+    X = util.lhs(M, seed=31)
+    outs = ["CO2_concentration", "global_tas", "ocean_timesteps"]
+    ens = hb.Ensemble(M, [tabs[n] for n in SSPS], member_scenario=ms, outputs=outs)
+    for j, n in enumerate(PARAMS4):
+        ens.setvar(n, X[:, j])
+    ens.run()
+    st, fy = ens.status()
+    got = ens.fetchvars(_years(), outs)
+    worst = {}
+    for i in range(M):
+        ost, ofy, out, _, _ = port.run_member(tabs[SSPS[ms[i]]], S=X[i, 0], q10_rh=X[i, 1],
+                                              beta=X[i, 2], diff=X[i, 3])
+        assert (ost != 0) == (st[i] != 0), (i, ost, st[i])
+        if ost:
+            assert ofy == fy[i]
+            continue
+        e = _check(got, i, out, SSPS[ms[i]])
+        w = worst.setdefault(SSPS[ms[i]], [0.0, 0.0])
+        w[0], w[1] = max(w[0], e[0]), max(w[1], e[1])
+    print("per scenario worst (CO2, Tgav):", {k: ("%.2g" % a, "%.2g" % b) for k, (a, b) in worst.items()})
+    ens.close()
+
+
+def test_tracked_2500_six_parameters_vs_oracle():
+    """BASELINE.json configs[4] shape: SSP5-8.5 with every series held at its 2300 value to 2500,
+    carbon tracking from 1750, Monte-Carlo over six parameters (seed 20241018): trajectories,
+    sub-step counts and the source maps of the recorded years against the oracle."""
+    from oracle import port
+    import hector_b200 as hb
+    raw = util.scenarios()["ssp585"]
+    ext = np.vstack([raw, np.repeat(raw[-1:], 200, axis=0)])
+    M = 96
+    rng = np.random.Generator(np.random.PCG64(20241018))
+    lo = np.array([2.0, 1.0, 0.2, 0.5, 0.5, 0.8])
+    hi = np.array([5.0, 2.6, 0.9, 2.5, 1.5, 1.2])
+    X = lo + rng.random((M, 6)) * (hi - lo)
+    outs = ["CO2_concentration", "global_tas", "ocean_timesteps"]
+    ens = hb.Ensemble(M, ext, end_year=2500, outputs=outs, tracking_date=1750, track_every=50)
+    for j, n in enumerate(PARAMS6):
+        ens.setvar(n, X[:, j])
+    ens.run()
+    st, _ = ens.status()
+    got = ens.fetchvars(_years(1746, 2500), outs)
+    rec_years = list(range(1750, 2501, 50))
+    maps = {y: ens.fetch_tracking(y) for y in rec_years}
+    for i in range(0, M, 8):
+        p = port.default_params(end_year=2500, **{n: X[i, j] for j, n in enumerate(PARAMS6)})
+        ost, _, out, frac, mask = port.run_member_tracked(ext, 1750, p)
+        assert ost == 0 and st[i] == 0
+        _check(got, i, out, "tracked-2500")
+        for y in rec_years:
+            f, k = maps[y]
+            assert np.array_equal(k[i], mask[y - 1746]), (i, y)
+            assert np.abs(f[i] - frac[y - 1746]).max() < 1e-12, (i, y)
+    # holding the series leaves 2300 where the 2300 run ends
+    short = hb.Ensemble(M, raw, outputs=outs)
+    for j, n in enumerate(PARAMS6):
+        short.setvar(n, X[:, j])
+    short.run()
+    g2 = short.fetchvars(_years(), outs)
+    for v in outs:
+        assert np.array_equal(g2[v], got[v][:, :555]), v
+    short.close()
+    ens.close()
+
+
+def test_all_parameters_at_once_vs_oracle():
+    """every per-member parameter of the engine perturbed at once (one draw per member, SSP3-7.0),
+    all 38 outputs: the probe that closed round 1 with an unexplained assertion
+    (tools/gpu_all_params_vs_oracle.py, 64 members, seed 5)."""
+    from oracle import port
+    import hector_b200 as hb
+    M = 64
+    vals = util.allparams_draw(M, 5, port.default_params())
+    assert set(hb.PARAMETERS) - set(vals) == {"N0"}
+    outs = list(hb.OUTPUT_VARIABLES)
+    scen = util.scenarios()["ssp370"]
+    ens = hb.Ensemble(M, scen, outputs=outs)
+    for n, v in vals.items():
+        ens.setvar(n, v)
+    ens.run()
+    st, fy = ens.status()
+    got = ens.fetchvars(_years(), outs)
+    worst = {}
+    for i in range(M):
+        kw = {util.ALLPARAM_RANGES[n][0]: float(vals[n][i]) for n in vals}
+        ost, ofy, out, _, _ = port.run_member(scen, **kw)
+        assert (ost != 0) == (st[i] != 0) and (ost == 0 or ofy == fy[i]), (i, ost, ofy, st[i])
+        n = 555 if not ost else ofy - 1746
+        for v in outs:
+            ref = out[port.OUT_NAMES.index(v)][:n]
+            if v == "ocean_timesteps":
+                assert np.array_equal(got[v][i][:n], ref), (i, v)
+            else:
+                worst[v] = max(worst.get(v, 0.0), util.parity_err(got[v][i][:n], ref, v))
+    print({k: "%.2g" % e for k, e in sorted(worst.items(), key=lambda kv: -kv[1])[:8]})
+    assert worst["CO2_concentration"] < TOL and worst["global_tas"] < TOL, worst
+    bad = {k: e for k, e in worst.items() if e > TOL_SECONDARY}
+    assert not bad, bad
+    ens.close()

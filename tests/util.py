@@ -145,3 +145,44 @@ def ref_allparams():
     return [dict(name=str(n), scenario=str(z["scenarios"][i]), params=spec[i]["params"],
                  halo=spec[i]["halo"], values=dict(zip(variables, z["values"][i])))
             for i, n in enumerate(z["names"])]
+
+
+# engine parameter name -> (oracle field, lo factor, hi factor): the all-parameter draw of
+# tools/gpu_all_params_vs_oracle.py / tests/test_gpu_parity.py::test_all_parameters_at_once.
+# N0 and the host-side gas constants are per-scenario in the sweep and stay at their defaults.
+ALLPARAM_RANGES = {
+    "S": ("S", 0.6, 1.6), "diff": ("diff", 0.5, 2.2), "qco2": ("qco2", 0.9, 1.1),
+    "beta": ("beta", 0.3, 1.4), "q10_rh": ("q10_rh", 0.9, 2.0), "f_nppv": ("f_nppv", 0.8, 1.1),
+    "f_nppd": ("f_nppd", 0.8, 1.0), "f_litterd": ("f_litterd", 0.9, 1.0),
+    "npp_flux0": ("npp_flux0", 0.85, 1.15), "C0": ("C0", 0.97, 1.03), "veg_c": ("veg_c", 0.8, 1.2),
+    "detritus_c": ("detritus_c", 0.8, 1.2), "soil_c": ("soil_c", 0.8, 1.2),
+    "permafrost_c": ("permafrost_c", 0.5, 1.3), "warmingfactor": ("warmingfactor", 0.8, 1.6),
+    "rh_ch4_frac": ("rh_ch4_frac", 0.5, 2.0), "pf_mu": ("pf_mu", 0.85, 1.2),
+    "pf_sigma": ("pf_sigma", 0.8, 1.2), "fpf_static": ("fpf_static", 0.7, 1.2),
+    "tt": ("tt", 0.8, 1.2), "tu": ("tu", 0.8, 1.2), "twi": ("twi", 0.8, 1.2), "tid": ("tid", 0.8, 1.2),
+    "preind_surface_c": ("preind_C_surface", 0.95, 1.05),
+    "preind_interdeep_c": ("preind_C_ID", 0.95, 1.05),
+    "eps_abs": ("eps_abs", 0.5, 2.0), "eps_rel": ("eps_rel", 0.5, 2.0), "dt": ("dt", 0.6, 1.6),
+    "eps_spinup": ("eps_spinup", 0.5, 2.0),
+    "aero_scalar": ("aero_scalar", 0.5, 1.5), "vol_scalar": ("vol_scalar", 0.8, 1.2),
+    "delta_co2": ("delta_co2", 0.5, 1.5), "delta_ch4": ("delta_ch4", 0.5, 1.5),
+    "delta_n2o": ("delta_n2o", 0.5, 1.5), "rho_bc": ("rho_bc", 0.5, 1.5), "rho_oc": ("rho_oc", 0.5, 1.5),
+    "rho_so2": ("rho_so2", 0.5, 1.5), "rho_nh3": ("rho_nh3", 0.5, 1.5),
+    "M0": ("M0", 0.97, 1.03), "Tsoil": ("Tsoil", 0.8, 1.2), "Tstrat": ("Tstrat", 0.8, 1.2),
+    "UC_CH4": ("UC_CH4", 0.95, 1.05), "TOH0": ("TOH0", 0.85, 1.15), "CNOX": ("CNOX", 0.7, 1.3),
+    "CCO": ("CCO", 0.7, 1.3), "CNMVOC": ("CNMVOC", 0.7, 1.3), "CCH4": ("CCH4", 0.8, 1.2),
+    "PO3": ("PO3", 0.9, 1.1), "lo_warming_ratio": ("lo_warming_ratio", 0.0, 0.0),
+}
+
+
+def allparams_draw(M, seed, defaults):
+    """every per-member parameter perturbed at once: {engine name: values[M]}; `defaults` is
+    the oracle's default parameter block (oracle.port.default_params())"""
+    rng = np.random.default_rng(seed)
+    vals = {}
+    for name, (field, lo, hi) in ALLPARAM_RANGES.items():
+        if name == "lo_warming_ratio":
+            vals[name] = np.where(rng.random(M) < 0.3, rng.uniform(0.9, 1.8, M), 0.0)
+        else:
+            vals[name] = float(getattr(defaults, field)) * rng.uniform(lo, hi, M)
+    return vals
