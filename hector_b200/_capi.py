@@ -11,12 +11,12 @@ COUNTER_NAMES = ["rhs_evals", "rk_steps", "rk_rejected", "stashes", "newton_iter
 HX_FLAG_COLD_NEWTON = 1
 HX_FLAG_NO_SPINUP = 2
 
-EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "hx_destroy", "hx_last_error", "hx_set_stream", "hx_set_scenario_series",
+EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "hx_ini_string", "hx_destroy", "hx_last_error", "hx_set_stream", "hx_set_scenario_series",
            "hx_set_scenario_table", "hx_set_member_scenario", "hx_set_param_scalar",
            "hx_set_param", "hx_set_param_device", "hx_get_param", "hx_select_outputs",
            "hx_prepare", "hx_run", "hx_run_stream", "hx_reset", "hx_reset_date", "hx_synchronize", "hx_fetch", "hx_output_device",
            "hx_ipc_export", "hx_ipc_open", "hx_ipc_pull", "hx_ipc_wait", "hx_ipc_close",
-           "hx_event_record", "hx_event_synchronize", "hx_member_status", "hx_set_tracking", "hx_set_biomes", "hx_biome_count", "hx_fetch_tracking", "hx_tracking_years", "hx_counters", "hx_current_date", "hx_last_run_ms",
+           "hx_xchg_create", "hx_xchg_open", "hx_run_exchange", "hx_xchg_block", "hx_xchg_close", "hx_event_record", "hx_event_synchronize", "hx_member_status", "hx_set_tracking", "hx_set_biomes", "hx_biome_count", "hx_biome_name", "hx_tracking_date", "hx_fetch_tracking", "hx_tracking_years", "hx_counters", "hx_current_date", "hx_last_run_ms",
            "hx_spinup_state", "hx_measure_fp64_peak", "hx_measure_hbm_copy", "hx_version"]
 
 
@@ -80,6 +80,11 @@ def lib():
     L.hx_ipc_pull.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32, vp]
     L.hx_ipc_wait.argtypes = [vp]
     L.hx_ipc_close.argtypes = [vp]
+    L.hx_xchg_create.argtypes = [vp, C.c_int32, C.c_int32, vp, C.POINTER(C.c_int64)]
+    L.hx_xchg_open.argtypes = [vp, C.c_int32, vp]
+    L.hx_run_exchange.argtypes = [vp, C.c_double]
+    L.hx_xchg_block.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64)]
+    L.hx_xchg_close.argtypes = [vp]
     L.hx_event_record.argtypes = [vp, C.c_int32]
     L.hx_event_synchronize.argtypes = [vp, C.c_int32]
     L.hx_set_tracking.argtypes = [vp, C.c_int32, C.c_int32]

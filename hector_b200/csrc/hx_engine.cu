@@ -158,6 +158,13 @@ struct Engine {
   std::vector<cudaStream_t> peer_stream; /* one per peer: the pulls spread over the copy engines */
   int peer_self = -1;
   cudaEvent_t ev_user[16] = {};
+  /* push exchange (hx_xchg_*): this rank's gather block [peers][n_out][nyears][Mpad], the peers'
+   * blocks opened through CUDA IPC, one copy stream per peer */
+  double *d_gather = nullptr;
+  size_t gather_elems_per_rank = 0;
+  std::vector<double *> peer_gather;
+  std::vector<cudaStream_t> push_stream;
+  int xchg_self = -1;
 
   int fail(int code, const std::string &msg) {
     err = msg;
@@ -548,6 +555,58 @@ struct Engine {
     return HX_OK;
   }
 
+  /* hx_run_exchange: like run_streamed, but a finished slab's rows go to every peer's gather
+   * block (and to this rank's own) instead of to the host: device-to-device copies on the copy
+   * engines, over NVLink for the peers, one stream per destination so that they spread over the
+   * engines, while the kernel computes the later slabs. */
+  int run_pushed(int r0, int r1) {
+    const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
+    if (nslab > slab_done_cap) {
+      if (h_slab_done) cudaFreeHost(h_slab_done);
+      h_slab_done = nullptr;
+      slab_done_cap = 0;
+      CUDA_TRY(cudaHostAlloc((void **)&h_slab_done, (size_t)nslab * sizeof(unsigned), cudaHostAllocMapped));
+      CUDA_TRY(cudaHostGetDevicePointer((void **)&d_slab_done, h_slab_done, 0));
+      slab_done_cap = nslab;
+    }
+    memset(h_slab_done, 0, (size_t)nslab * sizeof(unsigned));
+    CUDA_TRY(cudaMemsetAsync(d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), stream));
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    HxDev ds = d;
+    ds.slab_done = d_slab_done;
+    CUDA_TRY(hx::launch_run(ds, C, r0, r1, stream));
+    CUDA_TRY(cudaEventRecord(ev1, stream));
+    volatile unsigned *done = h_slab_done;
+    const int n = (int)peer_gather.size(), nsel = (int)out_sel.size();
+    const size_t ny = (size_t)(nrow - 1);
+    bool kernel_over = false;
+    for (int s = 0; s < nslab; ++s) {
+      unsigned spins = 0;
+      while (done[s] == 0u && !kernel_over) {
+        if ((++spins & 0xfffu) == 0) {
+          const cudaError_t q = cudaStreamQuery(stream);
+          if (q == cudaSuccess) kernel_over = true;
+          else if (q != cudaErrorNotReady) return fail(HX_ERR_CUDA, std::string("run kernel: ") + cudaGetErrorString(q));
+        }
+      }
+      if (done[s] == 0u)
+        return fail(HX_ERR_CUDA, "hx_run_exchange: the run kernel ended without completing every slab");
+      const int ra = r0 + s * HX_SLAB_YEARS, rb = std::min(r1, ra + HX_SLAB_YEARS);
+      for (int k = 0; k < n; ++k) {
+        const int p = (xchg_self + 1 + k) % n; /* every rank starts with a different peer */
+        for (int v = 0; v < nsel; ++v) {
+          const double *src = d_out + ((size_t)v * ny + ra) * Mpad;
+          double *dst = peer_gather[p] + (size_t)xchg_self * gather_elems_per_rank + ((size_t)v * ny + ra) * Mpad;
+          CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)(rb - ra) * Mpad * sizeof(double), cudaMemcpyDefault,
+                                   push_stream[p]));
+        }
+      }
+    }
+    for (cudaStream_t ps : push_stream) CUDA_TRY(cudaStreamSynchronize(ps));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return HX_OK;
+  }
+
   int run_setup_and_spinup() {
     if (tables_dirty) {
       int rc = upload_tables();
@@ -802,6 +861,7 @@ int hx_destroy(hx_handle h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   hx_ipc_close(h);
+  hx_xchg_close(h);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_rec_full[i]) cudaEventDestroy(h->ev_rec_full[i]);
     if (h->ev_rec_free[i]) cudaEventDestroy(h->ev_rec_free[i]);
@@ -843,11 +903,21 @@ int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, i
   }
   const int si = Engine::find_raw(name);
   if (si < 0) return h->fail(HX_ERR_ARG, std::string("unknown scenario series: ") + name);
-  if (year0 > h->cfg.start_year || year0 + n - 1 < h->cfg.end_year)
-    return h->fail(HX_ERR_ARG, std::string("series does not cover start..end: ") + name);
   double *dst = h->raw[scenario_id].data() + (size_t)si * h->nrow;
-  for (int r = 0; r < h->nrow; ++r) dst[r] = values[h->cfg.start_year - year0 + r];
-  h->raw_set[scenario_id][si] = 1;
+  if (year0 > h->cfg.start_year || year0 + n - 1 < h->cfg.end_year) {
+    /* a few years of a series that is already there: R's setvar(core, dates, var, values)
+     * (R/messages.R:107-140 -> Core::sendMessage(SETDATA, var, message_data(date, value)));
+     * a series must have been given in full once (the ini / csv reader does that) */
+    if (!h->raw_set[scenario_id][si])
+      return h->fail(HX_ERR_ARG, std::string("series does not cover start..end: ") + name);
+    for (int k = 0; k < n; ++k) {
+      const int r = year0 + k - h->cfg.start_year;
+      if (r >= 0 && r < h->nrow && values[k] == values[k]) dst[r] = values[k];
+    }
+  } else {
+    for (int r = 0; r < h->nrow; ++r) dst[r] = values[h->cfg.start_year - year0 + r];
+    h->raw_set[scenario_id][si] = 1;
+  }
   if (h->prepared) { h->tables_dirty = true; h->params_dirty = true; } /* R: setvar + reset */
   return HX_OK;
 }
@@ -932,12 +1002,26 @@ int hx_set_biomes(hx_handle h, int32_t n_biomes, const char *const *names) {
 
 int hx_biome_count(hx_handle h) { return h ? h->n_biomes : HX_ERR_ARG; }
 
+int hx_biome_name(hx_handle h, int32_t i, char *buf, int32_t cap) {
+  if (!h || !buf || cap < 1) return HX_ERR_ARG;
+  const std::string nm = h->n_biomes <= 1 ? (i == 0 ? "global" : "") : (i >= 0 && i < h->n_biomes ? h->biome_names[i] : "");
+  if (nm.empty()) return h->fail(HX_ERR_ARG, "hx_biome_name: index out of range");
+  snprintf(buf, (size_t)cap, "%s", nm.c_str());
+  return HX_OK;
+}
+
+int hx_tracking_date(hx_handle h) { return h ? h->tracking_date : HX_ERR_ARG; }
+
 /* "<biome>.<name>" inputs: scalar (per_member null) or one value per member */
 static int set_biome_param(hx_handle h, int ib, int f, double value, const double *per_member) {
-  if (h->prepared)
-    return h->fail(HX_ERR_STATE, "per-biome inputs must be set before hx_prepare");
   if (per_member) h->bvec[ib][f].assign(per_member, per_member + h->M);
   else { h->bscalar[ib][f] = value; h->bvec[ib][f].clear(); }
+  if (h->prepared) { /* like a global parameter: takes effect at the next reset / run */
+    cudaSetDevice(h->cfg.device);
+    int rc = h->upload_biomes();
+    if (rc) return rc;
+    h->params_dirty = true;
+  }
   return HX_OK;
 }
 
@@ -1524,6 +1608,102 @@ int hx_ipc_wait(hx_handle h) {
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_ipc_wait: ") + cudaGetErrorString(e));
   }
+  return HX_OK;
+}
+
+/* ---- push exchange: every rank's finished slabs are written into every peer's gather block ---- */
+int hx_xchg_close(hx_handle h) {
+  if (!h) return HX_OK;
+  for (size_t p = 0; p < h->peer_gather.size(); ++p)
+    if ((int)p != h->xchg_self && h->peer_gather[p]) cudaIpcCloseMemHandle(h->peer_gather[p]);
+  for (cudaStream_t s : h->push_stream)
+    if (s) cudaStreamDestroy(s);
+  h->push_stream.clear();
+  h->peer_gather.clear();
+  if (h->d_gather) cudaFree(h->d_gather);
+  h->d_gather = nullptr;
+  h->xchg_self = -1;
+  return HX_OK;
+}
+
+int hx_xchg_create(hx_handle h, int32_t n_peers, int32_t self_index, void *handle64, int64_t *bytes) {
+  if (!h || n_peers < 1 || self_index < 0 || self_index >= n_peers || !handle64) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_xchg_create before hx_prepare");
+  if (h->out_sel.empty()) return h->fail(HX_ERR_STATE, "hx_xchg_create: no outputs are recorded");
+  cudaSetDevice(h->cfg.device);
+  hx_xchg_close(h);
+  h->gather_elems_per_rank = h->out_sel.size() * (size_t)(h->nrow - 1) * h->Mpad;
+  const size_t total = (size_t)n_peers * h->gather_elems_per_rank * sizeof(double);
+  cudaError_t e = cudaMalloc(&h->d_gather, total);
+  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_xchg_create: ") + cudaGetErrorString(e));
+  cudaIpcMemHandle_t mh;
+  e = cudaIpcGetMemHandle(&mh, h->d_gather);
+  if (e != cudaSuccess) {
+    hx_xchg_close(h);
+    return h->fail(HX_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  memcpy(handle64, &mh, 64);
+  if (bytes) *bytes = (int64_t)total;
+  h->xchg_self = self_index;
+  h->peer_gather.assign(n_peers, nullptr);
+  h->peer_gather[self_index] = h->d_gather;
+  return HX_OK;
+}
+
+int hx_xchg_open(hx_handle h, int32_t n_peers, const void *handles) {
+  if (!h || !handles) return HX_ERR_ARG;
+  if (h->xchg_self < 0 || n_peers != (int)h->peer_gather.size())
+    return h->fail(HX_ERR_STATE, "hx_xchg_open: call hx_xchg_create with the same n_peers first");
+  cudaSetDevice(h->cfg.device);
+  for (int p = 0; p < n_peers; ++p) {
+    if (p == h->xchg_self) continue;
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, (const char *)handles + (size_t)p * 64, 64);
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      hx_xchg_close(h);
+      return h->fail(HX_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    }
+    h->peer_gather[p] = (double *)ptr;
+  }
+  h->push_stream.assign(n_peers, nullptr);
+  for (int p = 0; p < n_peers; ++p)
+    if (cudaStreamCreateWithFlags(&h->push_stream[p], cudaStreamNonBlocking) != cudaSuccess) {
+      hx_xchg_close(h);
+      return h->fail(HX_ERR_CUDA, "hx_xchg_open: could not create the copy streams");
+    }
+  return HX_OK;
+}
+
+int hx_xchg_block(hx_handle h, const double **dev_ptr, int64_t *elems_per_rank) {
+  if (!h || !dev_ptr) return HX_ERR_ARG;
+  if (!h->d_gather) return h->fail(HX_ERR_STATE, "hx_xchg_block before hx_xchg_create");
+  *dev_ptr = h->d_gather;
+  if (elems_per_rank) *elems_per_rank = (int64_t)h->gather_elems_per_rank;
+  return HX_OK;
+}
+
+int hx_run_exchange(hx_handle h, double run_to_date) {
+  if (!h) return HX_ERR_ARG;
+  if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_run_exchange before hx_prepare");
+  if (h->push_stream.empty()) return h->fail(HX_ERR_STATE, "hx_run_exchange before hx_xchg_open");
+  if (h->d_T) return h->fail(HX_ERR_UNSUPPORTED, "hx_run_exchange with carbon tracking: use hx_run, then a gather");
+  cudaSetDevice(h->cfg.device);
+  if (h->params_dirty) {
+    if (h->cur_row > 0)
+      return h->fail(HX_ERR_STATE, "parameters or inputs changed since the run began: call "
+                                   "hx_reset (or hx_reset_date) before running on");
+    int rc = h->run_setup_and_spinup();
+    if (rc) return rc;
+  }
+  const int to = run_to_date < 0 ? h->cfg.end_year : (int)run_to_date;
+  if (to > h->cfg.end_year) return h->fail(HX_ERR_ARG, "run_to_date beyond end_year");
+  const int r0 = h->cur_row, r1 = to - h->cfg.start_year;
+  if (r1 <= r0) return HX_OK;
+  int rc = h->run_pushed(r0, r1);
+  if (rc != HX_OK) return rc;
+  h->cur_row = r1;
   return HX_OK;
 }
 

@@ -529,8 +529,22 @@ extern "C" int hx_ini_scalar(const char *ini_path, const char *name, double *out
     hx_set_create_error((std::string(ini_path) + ": " + in.error).c_str());
     return in.unsupported ? HX_ERR_UNSUPPORTED : HX_ERR_ARG;
   }
+  if (!strcmp(name, "trackingDate")) { *out = in.tracking_date; return HX_OK; }
+  if (!strcmp(name, "do_spinup")) { *out = in.do_spinup ? 1.0 : 0.0; return HX_OK; }
   std::map<std::string, double>::const_iterator it = in.scalars.find(name);
   if (it == in.scalars.end()) return HX_ERR_ARG;
   *out = it->second;
+  return HX_OK;
+}
+
+extern "C" int hx_ini_string(const char *ini_path, const char *name, char *buf, int32_t cap) {
+  if (!ini_path || !name || !buf || cap < 1) return HX_ERR_ARG;
+  hx::IniInputs in;
+  if (!hx::read_ini(ini_path, in)) {
+    hx_set_create_error((std::string(ini_path) + ": " + in.error).c_str());
+    return in.unsupported ? HX_ERR_UNSUPPORTED : HX_ERR_ARG;
+  }
+  if (strcmp(name, "run_name")) return HX_ERR_ARG; /* [core] run_name is the one string input */
+  snprintf(buf, (size_t)cap, "%s", in.run_name.c_str());
   return HX_OK;
 }

@@ -19,6 +19,16 @@
 
 namespace hx {
 
+/* The DOECLIM convolution accumulates with fused multiply-adds.  HX_NO_FMA (together with nvcc
+ * --fmad=false) gives a build whose arithmetic rounds like the reference's x86-64 build, product
+ * and sum separately -- a debugging discriminator for parity work (tools/README.md), not a
+ * product configuration. */
+#ifdef HX_NO_FMA
+#define HX_CONV_FMA(a, b, c) __dadd_rn(__dmul_rn((a), (b)), (c))
+#else
+#define HX_CONV_FMA(a, b, c) fma((a), (b), (c))
+#endif
+
 #define HX_MAX_DEVICES 64 /* device ordinals with cached launch parameters */
 
 /* run-kernel dynamic shared memory map (bytes) */
@@ -525,7 +535,7 @@ __device__ __forceinline__ void conv_prepass(const double *__restrict__ sst,
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int j = 0; j < B; ++j) acc[j] = fma(s[u], V[j + (U - 1) - u], acc[j]);
+        for (int j = 0; j < B; ++j) acc[j] = HX_CONV_FMA(s[u], V[j + (U - 1) - u], acc[j]);
 #pragma unroll
       for (int p = B + U - 2; p >= U; --p) V[p] = V[p - U];
 #pragma unroll
@@ -839,14 +849,14 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
            * one term sst[t-1] K(1): it is last year's unscaled sum plus one FMA.  DPAST2 takes
            * the rows i < n_pre from the slab prepass and adds its last rows here, oldest first
            * like the reference. */
-          const double hint = fma(sst, BS.ker[Hs], STATE(SI_DPAST_RAW));
+          const double hint = HX_CONV_FMA(sst, BS.ker[Hs], STATE(SI_DPAST_RAW));
           double DPAST2 = BS.conv[(size_t)(r - base - 1) * Hs];
           {
             const double *ps = BS.sst + (size_t)n_pre * Hs;          /* sst[i], i ascending */
             const double *pk = BS.ker + (size_t)(r - n_pre + 1) * Hs; /* K(r - i + 1), descending */
 #pragma unroll 4
             for (int i = n_pre; i < r; ++i) {
-              DPAST2 = fma(*ps, *pk, DPAST2);
+              DPAST2 = HX_CONV_FMA(*ps, *pk, DPAST2);
               ps += Hs;
               pk -= Hs;
             }

@@ -465,6 +465,28 @@ class Ensemble:
     def ipc_wait(self):
         self._chk(self.L.hx_ipc_wait(self.h))
 
+    # -- push exchange: finished slabs go to every peer's gather block while the run computes --
+    def xchg_create(self, n_peers, self_index):
+        """-> 64-byte CUDA IPC handle of this rank's gather block"""
+        buf = C.create_string_buffer(64)
+        self._chk(self.L.hx_xchg_create(self.h, int(n_peers), int(self_index), buf, None))
+        return buf.raw
+
+    def xchg_open(self, handles):
+        self._chk(self.L.hx_xchg_open(self.h, len(handles), b"".join(handles)))
+
+    def run_exchange(self, to_date=-1):
+        if not self.prepared:
+            self.prepare()
+        self._chk(self.L.hx_run_exchange(self.h, float(to_date)))
+
+    def xchg_block(self):
+        """(device pointer, elements per rank slot) of the gather block"""
+        p = C.c_void_p()
+        n = C.c_int64()
+        self._chk(self.L.hx_xchg_block(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
     def event_record(self, idx):
         self._chk(self.L.hx_event_record(self.h, int(idx)))
 

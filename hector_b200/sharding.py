@@ -2,7 +2,10 @@
 exchange of the job is an all-gather of the per-member summary outputs.
 
   gather_summary   torch.distributed all-gather (NCCL on GPUs, gloo in the CPU tests)
-  PeerExchange     the same result over peer memory: every rank opens its peers' output blocks
+  PushExchange     the same result over peer memory, one kernel launch per rank: a rank's finished
+                   16-year slabs are copied into every peer's gather block by the copy engines
+                   while its kernel computes the later slabs (hx_xchg_* / hx_run_exchange)
+  PeerExchange     the round-1 form: pulls of whole run segments: every rank opens its peers' output blocks
                    through CUDA IPC and pulls finished run segments with copy-engine transfers
                    over NVLink while its own kernel computes the next segment.  A collective
                    kernel cannot do that: it finds no room next to the persistent run kernel.
@@ -101,3 +104,54 @@ class PeerExchange:
         # nobody may overwrite its outputs (the next reset / run) while a peer still reads them
         dist.barrier(group=self.group)
         return self.blocks
+
+
+class _DevView:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+class PushExchange:
+    """Every rank (one engine each, same outputs / years / padded member count) ends up with every
+    rank's recorded outputs: self.block is a device tensor [world, n_outputs, n_years, stride]
+    (outputs in the engine's selection order), rank k's at index k.
+
+        ex = PushExchange(ens, group)
+        ens.reset(); block = ex.run()
+
+    ONE launch of the persistent run kernel per rank; each finished slab is pushed to all peers
+    over NVLink while later slabs compute; a host barrier on `group` (gloo: an NCCL barrier is a
+    kernel and would queue behind work on the device) completes the exchange."""
+
+    def __init__(self, ens, group):
+        self.ens, self.group = ens, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        try:
+            mine, err = ens.xchg_create(self.world, self.rank), None
+        except Exception as ex:
+            mine, err = None, ex
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=group)
+        if err is None and all(h is not None for h in handles):
+            try:
+                ens.xchg_open(handles)
+            except Exception as ex:
+                err = ex
+        elif err is None:
+            err = RuntimeError("a peer could not create its gather block")
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            raise err if err is not None else RuntimeError("a peer could not open the blocks")
+        _, stride, ny = ens.output_device(ens.outputs[0])
+        ptr, per_rank = ens.xchg_block()
+        n_out = per_rank // (ny * stride)
+        self.n_years, self.stride, self.n_out = ny, stride, n_out
+        self.block = torch.as_tensor(_DevView(ptr, (self.world, n_out, ny, stride)), device="cuda")
+
+    def run(self, to_date=-1):
+        dist.barrier(group=self.group)      # nobody still reads the blocks this run overwrites
+        self.ens.run_exchange(to_date)
+        dist.barrier(group=self.group)      # everybody's pushes have landed
+        return self.block

@@ -90,6 +90,8 @@ int hx_create_from_ini(const char *const *ini_paths, int32_t n_inis, int32_t n_m
 int hx_ini_read(const char *ini_path, int32_t *start_year, int32_t *end_year, double *table,
                 int32_t table_rows);
 int hx_ini_scalar(const char *ini_path, const char *name, double *out);
+/* the one string input of an ini file: [core] run_name (Core::getRun_name, core.hpp:88) */
+int hx_ini_string(const char *ini_path, const char *name, char *buf, int32_t cap);
 int hx_destroy(hx_handle h); /* idempotent on NULL */
 const char *hx_last_error(hx_handle h); /* h may be NULL: error of the last failed hx_create */
 
@@ -97,8 +99,10 @@ const char *hx_last_error(hx_handle h); /* h may be NULL: error of the last fail
  * selects the engine's own stream. */
 int hx_set_stream(hx_handle h, void *cuda_stream);
 
-/* Raw scenario series, one value per integer year year0 .. year0+n-1 (must cover
- * start_year..end_year).  Names are the reference's input names: ffi_emissions, daccs_uptake,
+/* Raw scenario series, one value per integer year year0 .. year0+n-1.  The first call for a
+ * series must cover start_year..end_year; later calls may overwrite any sub-range of years (R's
+ * setvar(core, dates, var, values) editing a few years of an emission series; NaN entries are
+ * skipped).  Names are the reference's input names: ffi_emissions, daccs_uptake,
  * luc_emissions, luc_uptake, CH4_emissions, CH4N, NOX_emissions, CO_emissions,
  * NMVOC_emissions, BC_emissions, OC_emissions, SO2_emissions, NH3_emissions, SV, RF_albedo,
  * RF_misc, N2O_emissions, N2O_natural_emissions, <gas>_emissions for the 26 halocarbons.
@@ -200,6 +204,8 @@ int hx_output_device(hx_handle h, const char *name, const double **dev_ptr,
 #define HX_TRACK_NPOOL 11
 #define HX_TRACK_NSRC 12
 int hx_set_tracking(hx_handle h, int32_t tracking_date, int32_t record_every);
+/* Core::getTrackingDate (core.hpp:85): 9999 = tracking off */
+int hx_tracking_date(hx_handle h);
 /* frac[member][pool][source] (n_members x 11 x 12) and, if mask != NULL, mask[member][pool] whose
  * bit s says that source s is a key of the pool's map (the rows the reference's tracking CSV
  * prints; a key can carry fraction 0).  `date` must be a recorded year or the current date. */
@@ -214,7 +220,8 @@ int hx_tracking_years(hx_handle h, int32_t *years, int32_t cap);
  * hx_set_param_scalar / hx_set_param under the reference's names "<biome>.<name>", name in
  *   veg_c detritus_c soil_c permafrost_c npp_flux0 beta q10_rh f_nppv f_nppd f_litterd   (required)
  *   warmingfactor rh_ch4_frac pf_mu pf_sigma fpf_static                       (default like the reference)
- * also before hx_prepare; the global spellings are then refused ("cannot have both global and
+ * (after hx_prepare they take effect at the next reset / run, like every parameter); the global
+ * spellings are then refused ("cannot have both global and
  * biome-specific data").  The plain output names stay the across-biome totals the reference
  * reports for the global datum; "<biome>.<name>", name in veg_c detritus_c soil_c permafrost_c
  * thawedp_c NPP RH, selects and fetches one biome's own (hx_select_outputs after hx_set_biomes).
@@ -223,6 +230,9 @@ int hx_tracking_years(hx_handle h, int32_t *years, int32_t cap);
 #define HX_MAX_BIOMES 4
 int hx_set_biomes(hx_handle h, int32_t n_biomes, const char *const *names);
 int hx_biome_count(hx_handle h);
+/* name of biome i in creation order ("global" when there is only the global one):
+ * Core::getBiomeList (core.cpp:560-563) */
+int hx_biome_name(hx_handle h, int32_t i, char *buf, int32_t cap);
 
 /* Exchange of recorded outputs between the GPUs of one node WITHOUT kernels: every rank exports
  * its output block through CUDA IPC (64-byte handle; pass the handles around with any host-side
@@ -239,6 +249,31 @@ int hx_ipc_open(hx_handle h, int32_t n_peers, const void *handles, int32_t self_
 int hx_ipc_pull(hx_handle h, const char *name, int32_t year_a, int32_t year_b, double *dst_dev);
 int hx_ipc_wait(hx_handle h);  /* all pulls issued so far have landed */
 int hx_ipc_close(hx_handle h);
+/* ---- the job's one exchange, PUSHED while the run kernel computes (members
+ * shard over the GPUs of a node; afterwards every GPU holds every member's recorded outputs).
+ * No reference counterpart: the reference is single-process.  One process per GPU, all engines
+ * with the same outputs, years and padded member count:
+ *   hx_xchg_create   allocates this rank's gather block [n_peers][n_out][n_years][stride] (stride
+ *                    and n_years as hx_output_device reports them) and returns its CUDA IPC handle;
+ *   (the caller exchanges the 64-byte handles between the ranks -- MPI_Allgather, a torch.
+ *    distributed all_gather_object, a file: any transport)
+ *   hx_xchg_open     opens the peers' blocks (handles[n_peers][64], own slot ignored);
+ *   hx_run_exchange  hx_run as ONE launch of the persistent kernel; each 16-year slab, once every
+ *                    tile has finished it (flag in mapped host memory), is copied into slot
+ *                    `self_index` of EVERY rank's block by the copy engines, over NVLink for the
+ *                    peers, while the kernel computes the later slabs; returns when the kernel and
+ *                    this rank's copies are complete.  A barrier across the ranks (the caller's:
+ *                    MPI_Barrier, gloo ...) then makes every block complete; another one must
+ *                    precede the next run, which overwrites the blocks.
+ *   hx_xchg_block    device pointer of this rank's block, elements per rank slot.
+ * Only the last slab's copy and one host barrier stay exposed; no collective kernel has to find
+ * room next to the run kernel.  Untracked runs only. ---- */
+int hx_xchg_create(hx_handle h, int32_t n_peers, int32_t self_index, void *handle64, int64_t *bytes);
+int hx_xchg_open(hx_handle h, int32_t n_peers, const void *handles);
+int hx_run_exchange(hx_handle h, double run_to_date);
+int hx_xchg_block(hx_handle h, const double **dev_ptr, int64_t *elems_per_rank);
+int hx_xchg_close(hx_handle h);
+
 /* markers on the engine's stream (idx 0..15): record after a launch, wait for it on the host */
 int hx_event_record(hx_handle h, int32_t idx);
 int hx_event_synchronize(hx_handle h, int32_t idx);

@@ -32,27 +32,23 @@
 #include <cmath>
 #include <cstring>
 #include <exception>
+#include <fstream>
+#include <iostream>
 #include <limits>
+#include <map>
 #include <sstream>
 #include <string>
 #include <vector>
 
 #include "hector_b200.h"
 
-namespace hector_b200 {
-
-#define HXB_M_GETDATA "getData"
-#define HXB_M_SETDATA "setData"
-#ifndef M_GETDATA
-#define M_GETDATA HXB_M_GETDATA
-#define M_SETDATA HXB_M_SETDATA
-#endif
-
-/* ---- h_exception (h_exception.hpp:26-102): message + where it was raised ---- */
+/* ---- h_exception (h_exception.hpp:26-102): message + where it was raised.  Like the reference's
+ * it lives in the GLOBAL namespace: the R glue catches it unqualified (rcpp_hector.cpp:56). ---- */
+#ifndef HECTOR_B200_H_EXCEPTION
+#define HECTOR_B200_H_EXCEPTION
 class h_exception : public std::exception {
   std::string msg_, func_, file_;
   int line_;
-  mutable std::string full_;
 
  public:
   h_exception(const std::string &msg, const std::string &func, const std::string &file, int line)
@@ -66,7 +62,20 @@ class h_exception : public std::exception {
               << "\nline:\t" << e.line_ << "\n";
   }
 };
-#define HXB_THROW(m) throw ::hector_b200::h_exception((m), __func__, __FILE__, __LINE__)
+#endif
+
+namespace hector_b200 {
+
+using ::h_exception;
+
+#define HXB_M_GETDATA "getData"
+#define HXB_M_SETDATA "setData"
+#ifndef M_GETDATA
+#define M_GETDATA HXB_M_GETDATA
+#define M_SETDATA HXB_M_SETDATA
+#endif
+
+#define HXB_THROW(m) throw ::h_exception((m), __func__, __FILE__, __LINE__)
 
 /* ---- units (unitval.hpp:68-130): the ones variables of this path carry ---- */
 enum unit_types {
@@ -129,7 +138,7 @@ struct message_data {
     }
     if (strict && r.units() != expected)
       HXB_THROW("Units: " + r.unitsName() + " do not match expected: " + unitval::unitsName(expected));
-    r.expecting_unit(expected);
+    if (expected != U_UNDEFINED) r.expecting_unit(expected); /* no opinion: keep the caller's */
     return r;
   }
   double date;
@@ -139,8 +148,38 @@ struct message_data {
   bool isVal;
 };
 
-struct Logger { /* log levels only: the engine does not log (logger.hpp:47-54) */
+/* Logger (logger.hpp:35-118): levels, H_LOG's shouldWrite / write pair, close.  The engine itself
+ * does not log; this serves callers that write to the core's global log (src/main.cpp:43-113). */
+class Logger {
+ public:
   enum LogLevel { DEBUG, NOTICE, WARNING, SEVERE };
+  Logger() : min_(WARNING), screen_(false) {}
+  void open(const std::string & /*logName*/, bool echoToScreen, bool /*echoToFile*/, LogLevel minLogLevel) {
+    min_ = minLogLevel;
+    screen_ = echoToScreen;
+  }
+  bool shouldWrite(const LogLevel writeLevel) const { return screen_ && writeLevel >= min_; }
+  std::ostream &write(const LogLevel writeLevel, const std::string &functionInfo) {
+    static const char *const names[] = {"DEBUG", "NOTICE", "WARNING", "SEVERE"};
+    return std::clog << names[(int)writeLevel] << ":" << functionInfo << ": ";
+  }
+  void close() { std::clog.flush(); }
+
+ private:
+  LogLevel min_;
+  bool screen_;
+};
+
+class Core;
+/* AVisitor (avisitor.hpp:44-88): what Core::addVisitor takes.  Only visit(Core*) is ever called
+ * here -- the components behind the engine are not objects a visitor could be handed. */
+class AVisitor {
+ public:
+  virtual ~AVisitor() {}
+  virtual bool shouldVisit(const bool in_spinup, const double date) = 0;
+  virtual void reset(const double /*reset_date*/) {}
+  virtual void outputTrackingData(std::ostream & /*tracking_out*/) const {}
+  virtual void visit(Core * /*core*/) {}
 };
 
 namespace detail {
@@ -179,7 +218,10 @@ inline unit_types units_of(const std::string &v) {
       /* user constraints (component_data.hpp:46, 263, 273, 379-381) and [core] trackingDate */
       {"CO2_constrain", U_PPMV_CO2}, {"tas_constrain", U_DEGC}, {"RF_tot_constrain", U_W_M2},
       {"CH4_constrain", U_PPBV_CH4}, {"N2O_constrain", U_PPBV_N2O}, {"NBP_constrain", U_PGC_YR},
-      {"trackingDate", U_UNITLESS}};
+      {"trackingDate", U_UNITLESS},
+      /* emission series (component_data.hpp; unit checks of each component's setData) */
+      {"ffi_emissions", U_PGC_YR}, {"daccs_uptake", U_PGC_YR}, {"luc_emissions", U_PGC_YR},
+      {"luc_uptake", U_PGC_YR}};
   for (const VarUnit &e : tab)
     if (v == e.name) return e.units;
   /* <biome>.<name> (core.cpp:718-727): the units of <name>; "<gas>.tau" etc. are not in `tab` */
@@ -216,7 +258,7 @@ inline const char *member_failure(int status) { /* the reference's exception tex
 /* ---- M members behind Hector's message surface ---- */
 class EnsembleCore {
  public:
-  /* all 32 recorded variables unless `outputs` names a subset (fewer outputs = less HBM traffic) */
+  /* all recorded variables unless selectOutputs names a subset (fewer outputs = less HBM traffic) */
   explicit EnsembleCore(int n_members = 1, int device = 0, unsigned flags = 0)
       : n_(n_members), device_(device), flags_(flags) {}
   EnsembleCore(const EnsembleCore &) = delete;
@@ -224,41 +266,90 @@ class EnsembleCore {
   virtual ~EnsembleCore() { shutDown(); }
 
   void init() {} /* components are created with the engine (core.cpp:90-196) */
+  Logger &getGlobalLogger() { return glog_; }
 
   /* INIToCoreReader::parse: one ini file per scenario */
   void parse(const std::vector<std::string> &ini_files) {
     shutDown();
-    std::vector<const char *> p;
-    for (const std::string &s : ini_files) p.push_back(s.c_str());
-    if (hx_create_from_ini(p.data(), (int32_t)p.size(), n_, device_, flags_, &h_) != HX_OK)
-      HXB_THROW(std::string(hx_last_error(nullptr)));
-    prepared_ = false;
+    ini_files_ = ini_files;
+    journal_.clear();
+    biomes_.clear();
+    biomes_edited_ = false;
+    open_engine();
+    /* biomes an ini file declares ("<biome>.<name>" lines, simpleNbox.cpp:229-236): remember the
+     * list and their values, so that a later createBiome / renameBiome can rebuild the engine */
+    const int nb = hx_biome_count(h_);
+    if (nb > 1) {
+      for (int i = 0; i < nb; ++i) {
+        char buf[256];
+        chk(hx_biome_name(h_, i, buf, (int32_t)sizeof buf));
+        biomes_.push_back(buf);
+      }
+      for (const std::string &b : biomes_) capture_biome(b + ".", b + ".");
+    }
   }
   void selectOutputs(const std::vector<std::string> &names) {
     need();
-    std::vector<const char *> p;
-    for (const std::string &s : names) p.push_back(s.c_str());
-    chk(hx_select_outputs(h_, (int32_t)p.size(), p.data()));
-    outputs_selected_ = true;
+    apply_outputs(names);
+    outputs_ = names;
   }
   void setMemberScenario(const std::vector<int32_t> &scenario_of_member) {
     need();
     chk(hx_set_member_scenario(h_, scenario_of_member.data(), (int32_t)scenario_of_member.size()));
+    member_scenario_ = scenario_of_member;
   }
 
-  /* Biomes: the reference grows biome_list as "<biome>.<name>" data arrive (simpleNbox.cpp:
-   * 229-236); here the list is declared once, in creation order, before any such setData
-   * (an ini file with <biome>.<name> lines declares it by itself).  getBiomeList: core.cpp:
-   * 560-563. */
-  void setBiomes(const std::vector<std::string> &names) {
-    need();
-    std::vector<const char *> p;
-    for (const std::string &s : names) p.push_back(s.c_str());
-    chk(hx_set_biomes(h_, (int32_t)p.size(), p.data()));
-    biomes_ = names;
-  }
+  /* ---- biomes (core.cpp:560-599 -> simpleNbox.cpp:864-1100) ----
+   * The engine fixes its biome list when it is prepared, so an edit rebuilds it: the ini files
+   * are read again, the new list is declared and every setData / sendMessage(SETDATA) made so
+   * far is replayed; it is prepared again (set-up + spin-up) when next needed.  A core whose only
+   * biome has been renamed keeps running the global code path under the new name. */
   std::vector<std::string> getBiomeList() const {
     return biomes_.empty() ? std::vector<std::string>(1, "global") : biomes_;
+  }
+  void setBiomes(const std::vector<std::string> &names) { /* declare the whole list at once */
+    need();
+    for (const std::string &b : names)
+      if (b.empty() || b.find('.') != std::string::npos) HXB_THROW("bad biome name '" + b + "'");
+    rebuild(names);
+  }
+  void createBiome(const std::string &biome) {
+    need();
+    if (has_biome(biome)) HXB_THROW("Assertion failed: Biome '" + biome + "' is already in `biome_list`.");
+    if (biomes_.empty())
+      HXB_THROW("Assertion failed: If one of the biomes is 'global', you cannot add other biomes.");
+    std::vector<std::string> nl = biomes_;
+    nl.push_back(biome);
+    /* new pools and initial NPP are zero (simpleNbox.cpp:873-900); parameters stay unset */
+    static const char *const zeroed[] = {"veg_c", "detritus_c", "soil_c", "permafrost_c", "npp_flux0"};
+    for (const char *p : zeroed) journal_.push_back(SetCall::scalar(biome + "." + p, 0.0));
+    rebuild(nl);
+  }
+  void deleteBiome(const std::string &biome) {
+    need();
+    if (!has_biome(biome)) HXB_THROW("Assertion failed: Biome '" + biome + "' not found in `biome_list`.");
+    if (getBiomeList().size() == 1) HXB_THROW("cannot delete the only biome");
+    std::vector<std::string> nl;
+    for (const std::string &b : biomes_)
+      if (b != biome) nl.push_back(b);
+    drop_journal_prefix(biome + ".");
+    rebuild(nl);
+  }
+  void renameBiome(const std::string &oldname, const std::string &newname) {
+    need();
+    if (!has_biome(oldname)) HXB_THROW("Assertion failed: Biome '" + oldname + "' not found in `biome_list`.");
+    if (has_biome(newname)) HXB_THROW("Assertion failed: Biome '" + newname + "' already exists in `biome_list`.");
+    if (newname.empty() || newname.find('.') != std::string::npos) HXB_THROW("bad biome name '" + newname + "'");
+    std::vector<std::string> nl = getBiomeList();
+    for (std::string &b : nl)
+      if (b == oldname) b = newname;
+    /* the old biome's pools and parameters, as they stand, become the new one's */
+    const std::string from = engine_prefix(oldname);
+    drop_journal_prefix(oldname + ".");
+    if (from.empty()) drop_global_land_params();
+    capture_biome(from, newname + ".");
+    if (nl.size() == 1 && nl[0] == "global") nl.clear();
+    rebuild(nl);
   }
 
   /* Core::setData (core.cpp:219-268): the component name only routes in the reference */
@@ -267,36 +358,33 @@ class EnsembleCore {
     need();
     const unit_types want = detail::units_of(varName);
     const unitval v = data.getUnitval(want);
-    if (varName == "trackingDate") { /* [core] trackingDate, core.cpp:228-235 */
-      chk(hx_set_tracking(h_, (int32_t)(double)v, 1));
-    } else if (data.date != message_data::undefined()) {
-      /* a dated input: one entry of a user constraint (emission series come from the ini) */
-      const double d = v;
-      chk(hx_set_scenario_series(h_, 0, varName.c_str(), (int32_t)data.date, 1, &d));
-    } else {
-      chk(hx_set_param_scalar(h_, varName.c_str(), (double)v));
-    }
+    SetCall c = varName == "trackingDate"                    ? SetCall::tracking((double)v)
+                : data.date != message_data::undefined()     ? SetCall::dated(varName, data.date, (double)v)
+                                                             : SetCall::scalar(varName, (double)v);
+    apply(c);
+    journal_.push_back(c);
   }
   /* R setvar for a whole ensemble: one value per member */
   void setMembers(const std::string &varName, const std::vector<double> &per_member,
                   unit_types units = U_UNDEFINED) {
     need();
     check_units(varName, units);
-    chk(hx_set_param(h_, varName.c_str(), per_member.data(), (int32_t)per_member.size()));
+    SetCall c = SetCall::members(varName, per_member);
+    apply(c);
+    journal_.push_back(c);
   }
 
   void prepareToRun() {
     need();
-    if (!outputs_selected_) select_all();
-    chk(hx_prepare(h_));
-    prepared_ = true;
+    ensure_prepared();
   }
   /* Core::run (core.cpp:448-509).  throw_on_failure mirrors the single-core behaviour: the first
    * failed member's exception is re-thrown; batch callers pass false and read memberStatus(). */
   void run(double runtodate = -1.0, bool throw_on_failure = true) {
     need();
-    if (!prepared_) prepareToRun();
+    ensure_prepared();
     if (runtodate >= 0 && runtodate > getEndDate()) HXB_THROW("Run-to date is after end date.");
+    const double from = hx_current_date(h_);
     chk(hx_run(h_, runtodate));
     chk(hx_synchronize(h_));
     if (throw_on_failure) {
@@ -309,23 +397,33 @@ class EnsembleCore {
           HXB_THROW(os.str());
         }
     }
+    after_run(from, hx_current_date(h_));
   }
   /* Core::reset (core.cpp:511-549): to (or before) the start date -- parameters changed since
    * the last spin-up trigger a new one --, or to a year inside the run already made */
   void reset(double resetdate) {
     need();
-    if (!prepared_) return;
-    chk(hx_reset_date(h_, resetdate));
+    if (prepared_) chk(hx_reset_date(h_, resetdate)); /* an engine not yet prepared is at the start */
+    after_reset(resetdate);
   }
   void shutDown() {
     if (h_) hx_destroy(h_);
     h_ = nullptr;
-    prepared_ = outputs_selected_ = false;
+    prepared_ = false;
   }
 
-  double getStartDate() const { return h_ ? start_of(h_) : message_data::undefined(); }
+  double getStartDate() const { return h_ ? start_ : message_data::undefined(); }
   double getEndDate() const { return end_; }
   double getCurrentDate() const { return h_ ? hx_current_date(h_) : message_data::undefined(); }
+  /* Core::getTrackingDate (core.hpp:85): 9999 when tracking is off (core.cpp:60) */
+  double getTrackingDate() const { return h_ ? (double)hx_tracking_date(h_) : 9999.0; }
+  /* [core] run_name of the (first) ini file (core.hpp:88) */
+  std::string getRun_name() const {
+    char buf[512] = "";
+    if (!ini_files_.empty()) hx_ini_string(ini_files_[0].c_str(), "run_name", buf, (int32_t)sizeof buf);
+    return buf;
+  }
+  bool outputEnabled(const std::string & /*componentName*/) const { return true; }
   int members() const { return n_; }
   hx_handle handle() const { return h_; }
 
@@ -337,14 +435,22 @@ class EnsembleCore {
     if (message == HXB_M_SETDATA) {
       const unit_types want = detail::units_of(datum);
       const unitval v = info.getUnitval(want, /*strict*/ want != U_UNDEFINED);
-      if (n_ == 1) {
-        chk(hx_set_param_scalar(h_, datum.c_str(), (double)v));
+      SetCall c;
+      if (info.date != message_data::undefined()) {
+        /* a dated input: one year of an emission series or of a user constraint -- R's
+         * setvar(core, dates, var, values, unit) arrives here once per date */
+        c = SetCall::dated(datum, info.date, (double)v);
+      } else if (n_ == 1) {
+        c = SetCall::scalar(datum, (double)v);
       } else {
+        if (member < 0 || member >= n_) HXB_THROW("member index out of range");
         std::vector<double> cur(n_);
-        chk(hx_get_param(h_, datum.c_str(), cur.data(), n_));
-        cur.at(member) = (double)v;
-        chk(hx_set_param(h_, datum.c_str(), cur.data(), n_));
+        chk(hx_get_param(h_, engine_name(datum).c_str(), cur.data(), n_));
+        cur[member] = (double)v;
+        c = SetCall::members(datum, cur);
       }
+      apply(c);
+      journal_.push_back(c);
       return v;
     }
     HXB_THROW("Unknown message: " + message);
@@ -353,13 +459,16 @@ class EnsembleCore {
     need();
     if (member < 0 || member >= n_) HXB_THROW("member index out of range");
     const unit_types u = detail::units_of(varName);
-    if (date == message_data::undefined()) { /* a parameter */
-      std::vector<double> cur(n_);
-      chk(hx_get_param(h_, varName.c_str(), cur.data(), n_));
-      return unitval(cur[member], u);
-    }
+    const std::string name = engine_name(varName);
     std::vector<double> col(n_);
-    chk(hx_fetch(h_, varName.c_str(), &date, 1, col.data()));
+    if (date == message_data::undefined()) {
+      /* a parameter -- or, for a variable, its value at the current date (the reference's
+       * undated getData; misc/main-api.cpp:136-138) */
+      if (hx_get_param(h_, name.c_str(), col.data(), n_) == HX_OK) return unitval(col[member], u);
+      date = getCurrentDate();
+    }
+    ensure_prepared();
+    chk(hx_fetch(h_, name.c_str(), &date, 1, col.data()));
     return unitval(col[member], u);
   }
   /* Core::getTrackingData (core.cpp:199-209): the CSVFluxPoolVisitor's text for one member,
@@ -369,48 +478,169 @@ class EnsembleCore {
   std::string getTrackingData(int member = 0) {
     need();
     if (member < 0 || member >= n_) HXB_THROW("member index out of range");
+    const int ny = prepared_ ? hx_tracking_years(h_, nullptr, 0) : 0;
+    if (ny <= 0) return std::string();
+    std::vector<int32_t> years(ny);
+    hx_tracking_years(h_, years.data(), ny);
+    std::ostringstream os;
+    os << "year,component,pool_name,pool_value,pool_units,source_name,source_fraction\n";
+    for (int32_t y : years) {
+      if (y > getCurrentDate()) break;
+      trackingRows(os, y, member);
+    }
+    return os.str();
+  }
+  /* the tracking rows of one recorded year (or of the current date) */
+  void trackingRows(std::ostream &os, int year, int member = 0) {
     static const char *const pools[HX_TRACK_NPOOL] = {"atmos_co2", "earth_c", "veg_c", "detritus_c",
                                                       "soil_c", "permafrost_c", "thawedp_c", "HL",
                                                       "LL", "intermediate", "deep"};
     static const char *const pool_var[HX_TRACK_NPOOL] = {
         "atmos_co2", "earth_c", "veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c",
         "HL_ocean_c", "LL_ocean_c", "IO_ocean_c", "DO_ocean_c"};
-    const int ny = prepared_ ? hx_tracking_years(h_, nullptr, 0) : 0;
-    if (ny <= 0) return std::string();
-    std::vector<int32_t> years(ny);
-    hx_tracking_years(h_, years.data(), ny);
     std::vector<double> frac((size_t)n_ * HX_TRACK_NPOOL * HX_TRACK_NSRC), col(n_);
     std::vector<uint32_t> mask((size_t)n_ * HX_TRACK_NPOOL);
-    std::ostringstream os;
-    os << "year,component,pool_name,pool_value,pool_units,source_name,source_fraction\n";
-    for (int32_t y : years) {
-      if (y > getCurrentDate()) break;
-      chk(hx_fetch_tracking(h_, (double)y, frac.data(), mask.data()));
-      for (int k = 0; k < HX_TRACK_NPOOL; ++k) {
-        const double date = y;
-        chk(hx_fetch(h_, pool_var[k], &date, 1, col.data()));
-        for (int s = 0; s < HX_TRACK_NSRC; ++s)
-          if (mask[(size_t)member * HX_TRACK_NPOOL + k] >> s & 1u)
-            os << y << "," << (k < 7 ? "simpleNbox" : "ocean") << "," << pools[k] << ","
-               << col[member] << ",Pg C," << (s < HX_TRACK_NPOOL ? pools[s] : "untracked") << ","
-               << frac[((size_t)member * HX_TRACK_NPOOL + k) * HX_TRACK_NSRC + s] << "\n";
-      }
+    chk(hx_fetch_tracking(h_, (double)year, frac.data(), mask.data()));
+    for (int k = 0; k < HX_TRACK_NPOOL; ++k) {
+      const double date = year;
+      chk(hx_fetch(h_, pool_var[k], &date, 1, col.data()));
+      for (int s = 0; s < HX_TRACK_NSRC; ++s)
+        if (mask[(size_t)member * HX_TRACK_NPOOL + k] >> s & 1u)
+          os << year << "," << (k < 7 ? "simpleNbox" : "ocean") << "," << pools[k] << ","
+             << col[member] << ",Pg C," << (s < HX_TRACK_NPOOL ? pools[s] : "untracked") << ","
+             << frac[((size_t)member * HX_TRACK_NPOOL + k) * HX_TRACK_NSRC + s] << "\n";
     }
-    return os.str();
   }
   /* R fetchvars for the whole ensemble: out[member][date] */
   void fetch(const std::string &varName, const std::vector<double> &dates, double *out) {
     need();
-    chk(hx_fetch(h_, varName.c_str(), dates.data(), (int32_t)dates.size(), out));
+    ensure_prepared();
+    chk(hx_fetch(h_, engine_name(varName).c_str(), dates.data(), (int32_t)dates.size(), out));
   }
   void memberStatus(std::vector<int32_t> &status, std::vector<int32_t> &fail_year) {
     need();
+    ensure_prepared();
     status.resize(n_);
     fail_year.resize(n_);
     chk(hx_member_status(h_, status.data(), fail_year.data(), n_));
   }
+  /* is `var` among the recorded outputs (the visitors print what is there) */
+  bool isRecorded(const std::string &var) const {
+    if (outputs_.empty()) return true; /* everything */
+    for (const std::string &o : outputs_)
+      if (o == var) return true;
+    return false;
+  }
 
  protected:
+  /* one setData / sendMessage(SETDATA) / setMembers, kept so that an engine rebuilt for a new
+   * biome list can be brought back to the same inputs */
+  struct SetCall {
+    enum Kind { SCALAR, DATED, MEMBERS, TRACKING } kind = SCALAR;
+    std::string name;
+    double date = 0.0, value = 0.0;
+    std::vector<double> per_member;
+    static SetCall scalar(const std::string &n, double v) { SetCall c; c.kind = SCALAR; c.name = n; c.value = v; return c; }
+    static SetCall dated(const std::string &n, double d, double v) { SetCall c; c.kind = DATED; c.name = n; c.date = d; c.value = v; return c; }
+    static SetCall members(const std::string &n, const std::vector<double> &v) { SetCall c; c.kind = MEMBERS; c.name = n; c.per_member = v; return c; }
+    static SetCall tracking(double v) { SetCall c; c.kind = TRACKING; c.value = v; return c; }
+  };
+  void apply(const SetCall &c) {
+    const std::string name = engine_name(c.name);
+    switch (c.kind) {
+      case SetCall::TRACKING: chk(hx_set_tracking(h_, (int32_t)c.value, 1)); break; /* core.cpp:228-235 */
+      case SetCall::DATED: chk(hx_set_scenario_series(h_, 0, name.c_str(), (int32_t)c.date, 1, &c.value)); break;
+      case SetCall::MEMBERS: chk(hx_set_param(h_, name.c_str(), c.per_member.data(), (int32_t)c.per_member.size())); break;
+      default: chk(hx_set_param_scalar(h_, name.c_str(), c.value));
+    }
+  }
+  void open_engine() {
+    std::vector<const char *> p;
+    for (const std::string &f : ini_files_) p.push_back(f.c_str());
+    if (hx_create_from_ini(p.data(), (int32_t)p.size(), n_, device_, flags_, &h_) != HX_OK)
+      HXB_THROW(std::string(hx_last_error(nullptr)));
+    prepared_ = false;
+    if (!member_scenario_.empty())
+      chk(hx_set_member_scenario(h_, member_scenario_.data(), (int32_t)member_scenario_.size()));
+    if (biomes_edited_) {
+      if (biomes_.size() > 1) {
+        std::vector<const char *> b;
+        for (const std::string &s : biomes_) b.push_back(s.c_str());
+        chk(hx_set_biomes(h_, (int32_t)b.size(), b.data()));
+      } else {
+        chk(hx_set_biomes(h_, 1, nullptr)); /* one biome, whatever its name: the global code path */
+      }
+    }
+    for (const SetCall &c : journal_) apply(c);
+    if (!outputs_.empty()) apply_outputs(outputs_);
+  }
+  void rebuild(const std::vector<std::string> &new_list) {
+    if (h_) hx_destroy(h_);
+    h_ = nullptr;
+    biomes_ = new_list;
+    biomes_edited_ = true;
+    /* per-biome outputs of biomes that no longer exist cannot be selected any more */
+    std::vector<std::string> keep;
+    for (const std::string &o : outputs_) {
+      const size_t dot = o.find('.');
+      if (dot == std::string::npos || has_biome(o.substr(0, dot))) keep.push_back(o);
+    }
+    outputs_ = keep;
+    open_engine();
+  }
+  void ensure_prepared() {
+    if (prepared_) return;
+    if (outputs_.empty()) select_all();
+    chk(hx_prepare(h_));
+    prepared_ = true;
+  }
+  bool has_biome(const std::string &b) const {
+    for (const std::string &x : getBiomeList())
+      if (x == b) return true;
+    return false;
+  }
+  /* how the engine spells the inputs of biome `b`: "<b>." with several biomes, "" for the only one */
+  std::string engine_prefix(const std::string &b) const { return biomes_.size() > 1 ? b + "." : std::string(); }
+  /* "<biome>.<name>" of a core with ONE (renamed) biome is the engine's plain <name> */
+  std::string engine_name(const std::string &name) const {
+    if (biomes_.size() == 1 && name.compare(0, biomes_[0].size() + 1, biomes_[0] + ".") == 0)
+      return name.substr(biomes_[0].size() + 1);
+    return name;
+  }
+  /* journal the 15 per-biome inputs as the engine holds them under `from_prefix`, renamed */
+  void capture_biome(const std::string &from_prefix, const std::string &to_prefix) {
+    static const char *const names[] = {"veg_c", "detritus_c", "soil_c", "permafrost_c", "npp_flux0",
+                                        "beta", "q10_rh", "warmingfactor", "f_nppv", "f_nppd",
+                                        "f_litterd", "rh_ch4_frac", "pf_mu", "pf_sigma", "fpf_static"};
+    std::vector<double> cur(n_);
+    for (const char *p : names) {
+      chk(hx_get_param(h_, (from_prefix + p).c_str(), cur.data(), n_));
+      bool same = true, unset = false;
+      for (int i = 0; i < n_; ++i) { same = same && cur[i] == cur[0]; unset = unset || cur[i] != cur[i]; }
+      if (unset) continue; /* a created biome's parameter that was never given */
+      journal_.push_back(same ? SetCall::scalar(to_prefix + p, cur[0]) : SetCall::members(to_prefix + p, cur));
+    }
+  }
+  void drop_journal_prefix(const std::string &prefix) {
+    std::vector<SetCall> keep;
+    for (const SetCall &c : journal_)
+      if (c.name.compare(0, prefix.size(), prefix) != 0) keep.push_back(c);
+    journal_.swap(keep);
+  }
+  void drop_global_land_params() { /* they live on under the biome's name */
+    static const char *const names[] = {"veg_c", "detritus_c", "soil_c", "permafrost_c", "npp_flux0",
+                                        "beta", "q10_rh", "warmingfactor", "f_nppv", "f_nppd",
+                                        "f_litterd", "rh_ch4_frac", "pf_mu", "pf_sigma", "fpf_static"};
+    std::vector<SetCall> keep;
+    for (const SetCall &c : journal_) {
+      bool land = false;
+      for (const char *p : names) land = land || c.name == p;
+      if (!land) keep.push_back(c);
+    }
+    journal_.swap(keep);
+  }
+  virtual void after_run(double /*from*/, double /*to*/) {}
+  virtual void after_reset(double /*date*/) {}
   void need() const {
     if (!h_) HXB_THROW("no input has been parsed yet (INIToCoreReader::parse)");
   }
@@ -422,6 +652,13 @@ class EnsembleCore {
     if (given != U_UNDEFINED && want != U_UNDEFINED && given != want)
       HXB_THROW("Units: " + unitval::unitsName(given) + " do not match expected: " + unitval::unitsName(want));
   }
+  void apply_outputs(const std::vector<std::string> &names) {
+    std::vector<std::string> en;
+    for (const std::string &s : names) en.push_back(engine_name(s));
+    std::vector<const char *> p;
+    for (const std::string &s : en) p.push_back(s.c_str());
+    chk(hx_select_outputs(h_, (int32_t)p.size(), p.data()));
+  }
   void select_all() {
     static const char *const all[] = {
         "CO2_concentration", "global_tas", "RF_tot", "RF_CO2", "heatflux", "ocean_c", "HL_pH",
@@ -430,29 +667,47 @@ class EnsembleCore {
         "NBP", "ocean_uptake", "LL_pH", "HL_PCO2", "LL_PCO2", "HL_ocean_c", "LL_ocean_c",
         "IO_ocean_c", "DO_ocean_c", "RF_CH4", "RF_N2O", "rh_ch4", "NPP", "RH", "gmst",
         "ocean_tas", "heatflux_mixed", "heatflux_interior", "ocean_timesteps"};
-    chk(hx_select_outputs(h_, (int32_t)(sizeof all / sizeof all[0]), all));
-    outputs_selected_ = true;
+    std::vector<std::string> names(all, all + sizeof all / sizeof all[0]);
+    if (biomes_.size() > 1) { /* "<biome>.<name>": every biome's own pools and fluxes */
+      static const char *const own[] = {"veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c", "NPP", "RH"};
+      for (const std::string &b : biomes_)
+        for (const char *v : own) names.push_back(b + "." + v);
+    }
+    std::vector<const char *> p;
+    for (const std::string &n : names) p.push_back(n.c_str());
+    chk(hx_select_outputs(h_, (int32_t)p.size(), p.data()));
   }
-  double start_of(hx_handle) const { return start_; }
 
   friend class INIToCoreReader;
   hx_handle h_ = nullptr;
   int n_, device_;
   unsigned flags_;
-  bool prepared_ = false, outputs_selected_ = false;
-  std::vector<std::string> biomes_;
+  bool prepared_ = false, biomes_edited_ = false;
+  std::vector<std::string> ini_files_, biomes_, outputs_;
+  std::vector<int32_t> member_scenario_;
+  std::vector<SetCall> journal_;
+  Logger glog_;
   double start_ = message_data::undefined(), end_ = message_data::undefined();
 };
 
 /* ---- the single-member face, with the reference's registry (core.cpp:813-857) ---- */
 class Core : public EnsembleCore {
  public:
-  Core(Logger::LogLevel = Logger::DEBUG, bool /*echotoscreen*/ = true, bool /*echotofile*/ = true)
-      : EnsembleCore(1) {}
+  Core(Logger::LogLevel loglvl = Logger::DEBUG, bool echotoscreen = true, bool echotofile = true)
+      : EnsembleCore(1) {
+    glog_.open("hector", echotoscreen, echotofile, loglvl);
+  }
   static double undefinedIndex() { return message_data::undefined(); }
+  /* Core::addVisitor (core.cpp:429-436): visitors stay the caller's.  After every run() they are
+   * shown each year just computed, oldest first: shouldVisit(false, year), then visit(this) --
+   * what the reference does at the end of every time step (core.cpp:497-503); the spin-up is
+   * not shown. */
+  void addVisitor(AVisitor *visitor) { visitors_.push_back(visitor); }
+  /* the year a visitor is being shown (getCurrentDate() is already the end of the run) */
+  double visitDate() const { return visit_date_; }
   static int mkcore(bool /*logtofile*/ = false, Logger::LogLevel lvl = Logger::NOTICE,
-                    bool /*logtoscrn*/ = false) {
-    registry().push_back(new Core(lvl, false, false));
+                    bool logtoscrn = false) {
+    registry().push_back(new Core(lvl, logtoscrn, false));
     return (int)registry().size() - 1;
   }
   static Core *getcore(std::vector<Core *>::size_type idx) {
@@ -465,7 +720,22 @@ class Core : public EnsembleCore {
     }
   }
 
+ protected:
+  void after_run(double from, double to) override {
+    if (visitors_.empty()) return;
+    for (double y = from + 1; y <= to; y += 1.0) {
+      visit_date_ = y;
+      for (AVisitor *v : visitors_)
+        if (v->shouldVisit(false, y)) v->visit(this);
+    }
+  }
+  void after_reset(double date) override {
+    for (AVisitor *v : visitors_) v->reset(date);
+  }
+
  private:
+  std::vector<AVisitor *> visitors_;
+  double visit_date_ = 0.0;
   static std::vector<Core *> &registry() {
     static std::vector<Core *> r;
     return r;

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 import hector_b200 as hb
-from hector_b200.sharding import PeerExchange, shard_range
+from hector_b200.sharding import PeerExchange, PushExchange, shard_range
 from tests import util
 
 dist.init_process_group("gloo")
@@ -34,10 +34,19 @@ ens = hb.Ensemble(M, util.scenarios()["ssp245"], device=dev, outputs=variables)
 for j, n in enumerate(["S", "q10_rh", "beta", "diff"]):
     ens.setvar(n, X[:, j])
 ens.prepare()
-ex = PeerExchange(ens, variables, dist.group.WORLD, segments=3)
-for rep in range(2):                       # twice: buffers and events are reused
-    ens.reset()
-    blocks = ex.run()
+MODE = %(mode)r
+if MODE == "pull":
+    ex = PeerExchange(ens, variables, dist.group.WORLD, segments=3)
+    for rep in range(2):                       # twice: buffers and events are reused
+        ens.reset()
+        blocks = ex.run()
+else:
+    ex = PushExchange(ens, dist.group.WORLD)
+    for rep in range(2):
+        ens.reset()
+        blk = ex.run()                         # [world, n_out, years, stride]
+    torch.cuda.synchronize()
+    blocks = {v: blk[:, k] for k, v in enumerate(variables)}
 years = np.arange(1746, 2301, dtype=np.float64)
 mine = {v: ens.fetch(v, years) for v in variables}           # [M, years]
 out = {}
@@ -61,10 +70,13 @@ def _free_port():
     return p
 
 
-def test_two_process_peer_exchange(tmp_path):
+@pytest.mark.parametrize("mode", ["pull", "push"])
+def test_two_process_peer_exchange(tmp_path, mode):
+    """pull: PeerExchange (run segments pulled by the receivers); push: PushExchange (one launch,
+    every finished slab written into the peers' gather blocks: hx_xchg_* / hx_run_exchange)"""
     out = str(tmp_path / "rank%d.npz")
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % {"root": ROOT, "out": out})
+    script.write_text(WORKER % {"root": ROOT, "out": out, "mode": mode})
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()))
     procs = []
     for rank in range(2):
