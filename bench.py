@@ -269,6 +269,213 @@ class CudaArrayView:
                                          "version": 2, "strides": None}
 
 
+SSPS = ["ssp119", "ssp126", "ssp245", "ssp370", "ssp434", "ssp460", "ssp534-over", "ssp585"]
+
+
+def run_config4(total, rank, world, local_rank, stream, dist, gloo, timed, args):
+    """BASELINE.json configs[3]: `total` members, all 8 SSP scenarios interleaved in API order
+    (member i runs scenario i mod 8), sharded as SURVEY.md 8(e) says: members sorted by scenario,
+    the sorted list cut into `world` contiguous ranges.  Exchange: pushed over peer memory when
+    available (hx_run_exchange), else one NCCL all-gather.  Afterwards rank 0 un-permutes a random
+    subset of API members out of the gathered block and compares it with (a) a single-GPU run of
+    exactly those members and (b) the CPU oracle."""
+    import torch
+    import hector_b200 as hb
+    from hector_b200.sharding import scenario_sorted_shards, PushExchange
+    ms = np.arange(total) % 8
+    X = lhs(total)
+    order, bounds = scenario_sorted_shards(ms, world)
+    lo, hi = bounds[rank]
+    if any(b - a != hi - lo for a, b in bounds):
+        raise SystemExit("bench.py --config4-members: not divisible by the number of ranks")
+    mine = order[lo:hi]
+    scen_ids = sorted(set(ms[mine].tolist()))
+    for sid in scen_ids:
+        if int((ms[mine] == sid).sum()) % 128:
+            raise SystemExit("bench.py --config4-members: per-rank scenario groups must be whole "
+                             "128-member tiles")
+    remap = {sid: k for k, sid in enumerate(scen_ids)}
+    ens = hb.Ensemble(len(mine), [scenario_table(SSPS[sid]) for sid in scen_ids],
+                      member_scenario=np.array([remap[int(x)] for x in ms[mine]], dtype=np.int32),
+                      device=local_rank, outputs=E2E_VARS, stream=stream.cuda_stream)
+    for j, nme in enumerate(PARAMS):
+        ens.setvar(nme, np.ascontiguousarray(X[mine, j]))
+    ens.prepare()
+    ens.synchronize()
+    _, stride, ny = ens.output_device(E2E_VARS[0])
+    assert stride == len(mine)
+    push = None
+    gathered = None
+    if world > 1:
+        ok = 1
+        try:
+            if gloo is None:
+                raise RuntimeError("no gloo group")
+            push = PushExchange(ens, gloo)
+        except Exception as ex:
+            sys.stderr.write("bench.py config4: push exchange unavailable (%r), NCCL all-gather\n" % (ex,))
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            push = None
+            gathered = torch.empty((world, 2, ny, stride), dtype=torch.float64, device="cuda")
+    views = []
+    for v in E2E_VARS:
+        ptr, _, _ = ens.output_device(v)
+        views.append(torch.as_tensor(CudaArrayView(ptr, (ny, stride)), device="cuda"))
+
+    def step(e):
+        e.reset()
+        if world == 1:
+            e.run()
+        elif push is not None:
+            push.run()
+        else:
+            e.run()
+            mineblk = torch.stack(views)                       # [2, ny, stride]
+            dist.all_gather_into_tensor(gathered.reshape(-1), mineblk.reshape(-1))
+
+    nsteps = max(2, args.steps // 2)
+    ms_total, _ = timed(ens, step, nsteps, 2, False)
+    ms_step = ms_total / nsteps
+    st, _ = ens.status()
+    failed = torch.tensor([int((st != 0).sum())], dtype=torch.int64, device="cuda")
+    if dist:
+        dist.all_reduce(failed)
+    res = None
+    if rank == 0:
+        block = (push.block if push is not None else gathered) if world > 1 else torch.stack(views)[None]
+        inv = np.argsort(order)
+        pick = np.sort(np.random.default_rng(4).choice(total, 64, replace=False))
+        pos = inv[pick]
+        rk, col = pos // stride, pos % stride
+        got = block[torch.as_tensor(rk, device="cuda"), :, :, torch.as_tensor(col, device="cuda")]
+        got = got.cpu().numpy()                                # [64, 2, ny]
+        # (a) the same members on one GPU, in API order
+        one = hb.Ensemble(64, [scenario_table(n) for n in SSPS], member_scenario=ms[pick].astype(np.int32),
+                          device=local_rank, outputs=E2E_VARS)
+        for j, nme in enumerate(PARAMS):
+            one.setvar(nme, np.ascontiguousarray(X[pick, j]))
+        one.run()
+        years = np.arange(1746, 2301, dtype=np.float64)
+        ref = np.stack([one.fetch(v, years) for v in E2E_VARS], axis=1)   # [64, 2, ny]
+        one.close()
+        same = bool(np.array_equal(got, ref))
+        maxrel = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 0.01)))
+        # (b) the oracle on eight of them (one per scenario)
+        from oracle import port
+        e_co2 = e_tas = 0.0
+        for k in range(8):
+            i = int(np.nonzero(ms[pick] == k)[0][0]) if (ms[pick] == k).any() else k
+            stt, _, out, _, _ = port.run_member(scenario_table(SSPS[int(ms[pick][i])]), S=X[pick[i], 0],
+                                                q10_rh=X[pick[i], 1], beta=X[pick[i], 2], diff=X[pick[i], 3])
+            e_co2 = max(e_co2, float(np.max(np.abs(got[i, 0] - out[0]) / np.maximum(np.abs(out[0]), 1.0))))
+            e_tas = max(e_tas, float(np.max(np.abs(got[i, 1] - out[1]) / np.maximum(np.abs(out[1]), 0.01))))
+        res = {"members": total, "members_per_gpu": len(mine), "scenarios": 8,
+               "scenarios_on_rank0": [SSPS[s_] for s_ in scen_ids],
+               "value": total * YEARS / (ms_step * 1e-3), "unit": UNIT, "ms_per_step": ms_step,
+               "failed_members": int(failed.item()),
+               "exchange": "none (1 GPU)" if world == 1 else ("peer memory, pushed" if push is not None
+                                                                else "NCCL all-gather"),
+               "gathered_bytes_per_gpu": int(world * 2 * ny * stride * 8),
+               "unpermute_check": {"api_members": 64, "bit_identical_to_single_gpu_run": same,
+                                   "max_rel_diff": maxrel},
+               "parity_spot": {"members": 8, "CO2_concentration": e_co2, "global_tas": e_tas,
+                               "ok": bool(e_co2 <= 1e-10 and e_tas <= 1e-10)},
+               "note": "BASELINE.json configs[3]: member i runs scenario i mod 8 (API order); "
+                       "members sorted by scenario and cut into contiguous per-GPU ranges "
+                       "(SURVEY.md 8(e)); every GPU ends with all members' CO2 + Tgav"}
+    if dist:
+        dist.barrier()
+    ens.close()
+    return res
+
+
+def run_config5(total, rank, world, local_rank, stream, dist, timed, args):
+    """BASELINE.json configs[4]: `total` members, SSP5-8.5 with every series held at its 2300 value
+    to 2500, carbon tracking from 1750 (maps recorded in 2500), Monte-Carlo over (S, q10_rh, beta,
+    diff, aero_scalar, vol_scalar), seed 20241018; contiguous shards; ONE NCCL all-gather of the
+    CO2 + Tgav trajectories after the run, and an all-reduced summary of the tracked maps."""
+    import torch
+    import hector_b200 as hb
+    from hector_b200.sharding import shard_range
+    raw = scenario_table("ssp585")
+    ext = np.vstack([raw, np.repeat(raw[-1:], 200, axis=0)])
+    rng = np.random.Generator(np.random.PCG64(20241018))
+    lo6 = np.array([2.0, 1.0, 0.2, 0.5, 0.5, 0.8]); hi6 = np.array([5.0, 2.6, 0.9, 2.5, 1.5, 1.2])
+    X6 = lo6 + rng.random((total, 6)) * (hi6 - lo6)
+    a, b = shard_range(total, rank, world)
+    if (b - a) * world != total or (b - a) % 128:
+        raise SystemExit("bench.py --config5-members: shards must be equal and whole tiles")
+    free0 = torch.cuda.mem_get_info()[0]
+    ens = hb.Ensemble(b - a, ext, end_year=2500, device=local_rank, outputs=E2E_VARS,
+                      tracking_date=1750, track_every=0, stream=stream.cuda_stream)
+    names6 = PARAMS + ["aero_scalar", "vol_scalar"]
+    for j, nme in enumerate(names6):
+        ens.setvar(nme, np.ascontiguousarray(X6[a:b, j]))
+    ens.prepare()
+    ens.synchronize()
+    engine_bytes = free0 - torch.cuda.mem_get_info()[0]
+    _, stride, ny = ens.output_device(E2E_VARS[0])
+    views = []
+    for v in E2E_VARS:
+        ptr, _, _ = ens.output_device(v)
+        views.append(torch.as_tensor(CudaArrayView(ptr, (ny, stride)), device="cuda"))
+    gathered = torch.empty((world, 2, ny, stride), dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def step(e):
+        e.reset()
+        e.run()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.reshape(-1), torch.stack(views).reshape(-1))
+
+    nsteps = max(2, args.steps // 2)
+    ms_total, _ = timed(ens, step, nsteps, 1, False)
+    ms_step = ms_total / nsteps
+    st, _ = ens.status()
+    frac, _ = ens.fetch_tracking(2500)                       # [members, 11 pools, 12 sources]
+    ok = st == 0
+    sums = torch.tensor(np.concatenate([frac[ok, 0, :].sum(axis=0), [ok.sum(), (~ok).sum()]]),
+                        dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(sums)
+    sums = sums.cpu().numpy()
+    res = None
+    if rank == 0:
+        from oracle import port
+        # parity of this rank's first member against the oracle (trajectory and tracked maps)
+        p = port.default_params(end_year=2500, **{n: X6[a, j] for j, n in enumerate(names6)})
+        stt, _, out, ofrac, _ = port.run_member_tracked(ext, 1750, p)
+        years = np.arange(1746, 2501, dtype=np.float64)
+        mine0 = (gathered[0, :, :, 0] if world > 1 else torch.stack(views)[:, :, 0]).cpu().numpy()
+        e_co2 = float(np.max(np.abs(mine0[0] - out[0]) / np.maximum(np.abs(out[0]), 1.0)))
+        e_tas = float(np.max(np.abs(mine0[1] - out[1]) / np.maximum(np.abs(out[1]), 0.01)))
+        e_map = float(np.abs(frac[0] - ofrac[2500 - 1746]).max())
+        res = {"members": total, "members_per_gpu": b - a, "years": 755,
+               "value": total * 755 / (ms_step * 1e-3), "unit": UNIT, "ms_per_step": ms_step,
+               "failed_members": int(sums[-1]),
+               "engine_device_memory_gb": engine_bytes / 1e9,
+               "gathered_bytes_per_gpu": int(world * 2 * ny * stride * 8),
+               "exchange": "none (1 GPU)" if world == 1 else "one NCCL all-gather of CO2 + Tgav "
+                           "(755 years, every member) after the run",
+               "tracking_summary": {"pool": "atmos_co2", "year": 2500,
+                                    "sources": ["atmos_co2", "earth_c", "veg_c", "detritus_c", "soil_c",
+                                                "permafrost_c", "thawedp_c", "HL", "LL", "intermediate",
+                                                "deep", "untracked"],
+                                    "ensemble_mean_fraction": (sums[:12] / max(sums[12], 1.0)).tolist()},
+               "parity_spot": {"member": int(a), "CO2_concentration": e_co2, "global_tas": e_tas,
+                               "tracked_fractions_abs": e_map,
+                               "ok": bool(e_co2 <= 1e-10 and e_tas <= 1e-10 and e_map <= 1e-12)},
+               "note": "BASELINE.json configs[4]: Monte-Carlo over six parameters, SSP5-8.5 "
+                       "1745->2500 (series held at their 2300 values), carbon tracking from 1750 "
+                       "(11 pools x 12 sources per member), contiguous member shards"}
+    if dist:
+        dist.barrier()
+    ens.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -285,10 +492,17 @@ def main():
     ap.add_argument("--biome-members", type=int, default=65536,
                     help="also time a three-biome ensemble (0 = skip)")
     ap.add_argument("--e2e-segments", type=int, default=4)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "ipc", "nccl"],
-                    help="N > 1: how the trajectories are exchanged: peer-memory pulls overlapped "
-                         "with the run, or one NCCL all-gather after it.  auto = ipc from 4 GPUs "
-                         "on (measured: N = 2 38.3 vs 38.0 ms, N = 8 40.9 vs 43.0 ms)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "push", "ipc", "nccl"],
+                    help="N > 1: how the trajectories are exchanged.  push (auto): ONE launch per "
+                         "rank, every finished 16-year slab copied into the peers' gather blocks "
+                         "over NVLink while the kernel runs (hx_run_exchange); ipc: round 1's "
+                         "pulls of 4 run segments; nccl: one all-gather after the run")
+    ap.add_argument("--config4-members", type=int, default=-1,
+                    help="BASELINE.json configs[3] leg: total members over all ranks, 8 SSPs "
+                         "interleaved (default 262 144 at 8 GPUs, else skipped; 0 = skip)")
+    ap.add_argument("--config5-members", type=int, default=-1,
+                    help="BASELINE.json configs[4] leg: total members, SSP5-8.5 to 2500 with carbon "
+                         "tracking (default 1 048 576 at 8 GPUs, else skipped; 0 = skip)")
     ap.add_argument("--exchange-segments", type=int, default=4)
     ap.add_argument("--gather-segments", type=int, default=1,
                     help="N > 1: run segments per step, each followed by its share of the "
@@ -315,6 +529,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
     torch.cuda.set_device(local_rank)
+    from hector_b200.sharding import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local_rank)   # before any pinned host buffer exists
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -364,12 +580,17 @@ def main():
     peer_all = None
     gloo = None
     exchange = None
-    if world > 1 and (args.exchange == "ipc" or (args.exchange == "auto" and world >= 4)):
-        from hector_b200.sharding import PeerExchange
+    push = None
+    want = args.exchange if args.exchange != "auto" else "push"
+    if world > 1 and want in ("push", "ipc"):
+        from hector_b200.sharding import PeerExchange, PushExchange
         gloo = dist.new_group(backend="gloo")
         ok = 1
         try:
-            exchange = PeerExchange(ens, E2E_VARS, gloo, segments=args.exchange_segments)
+            if want == "push":
+                push = PushExchange(ens, gloo)
+            else:
+                exchange = PeerExchange(ens, E2E_VARS, gloo, segments=args.exchange_segments)
         except Exception as ex:  # e.g. CUDA IPC not permitted in this container
             sys.stderr.write("bench.py: peer-memory exchange unavailable on rank %d (%r); "
                              "using the NCCL all-gather\n" % (rank, ex))
@@ -377,13 +598,17 @@ def main():
         flag = torch.tensor([ok], dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=gloo)   # all ranks or none
         if int(flag.item()) == 1:
-            peer_all = [exchange.blocks[v] for v in E2E_VARS]
+            peer_all = ([push.block[:, k] for k in range(len(E2E_VARS))] if push is not None
+                        else [exchange.blocks[v] for v in E2E_VARS])
         else:
-            exchange = None
+            exchange = push = None
 
     def step_ipc(e):
         e.reset()
-        exchange.run()
+        if push is not None:
+            push.run()
+        else:
+            exchange.run()
 
     def step_device(e, do_gather=True):
         if world > 1 and do_gather and peer_all is not None:
@@ -433,10 +658,10 @@ def main():
         # one-off check of the exchange against NCCL's all-gather of the same blocks
         step_ipc(ens)
         for t, g in zip(views, peer_all):
-            ref = torch.empty_like(g)
+            ref = torch.empty(g.shape, dtype=g.dtype, device=g.device)
             dist.all_gather_into_tensor(ref.reshape(-1), t.reshape(-1))
             torch.cuda.synchronize()
-            if not torch.equal(torch.nan_to_num(ref), torch.nan_to_num(g)):
+            if not torch.equal(torch.nan_to_num(ref), torch.nan_to_num(g.contiguous())):
                 raise SystemExit("bench.py: peer-memory exchange differs from the NCCL all-gather")
         dist.barrier(group=gloo)
 
@@ -486,6 +711,9 @@ def main():
         e2e = {"value": world * M * YEARS / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(4 * M * 8), "d2h_bytes_per_step": int(2 * M * YEARS * 8),
                "ms_per_step": e2e_ms,
+               "delivers": "every rank's own members to that rank's pinned host buffers (no cross-"
+                           "rank exchange on this path: the host side of a sharded job reads its "
+                           "shard)" if world > 1 else "all members to the caller's host buffers",
                "includes": "4 parameter vectors H2D, set-up + spin-up, run, CO2+Tgav x 555 yr D2H "
                            "(hx_run_stream: one launch of the persistent run kernel, every "
                            "16-year slab's rows copied out as the kernel reports it complete)"}
@@ -581,6 +809,15 @@ def main():
                          "tundra warming factor 2): the BIOMES instantiation of the run kernel"}
         eb.close()
 
+    # ---- BASELINE.json configs[3] and configs[4] AT SIZE, sharded over all ranks ----
+    config4 = config5 = None
+    n4 = args.config4_members if args.config4_members >= 0 else (262144 if world == 8 else 0)
+    n5 = args.config5_members if args.config5_members >= 0 else (1048576 if world == 8 else 0)
+    if n4:
+        config4 = run_config4(n4, rank, world, local_rank, stream, dist, gloo, timed, args)
+    if n5:
+        config5 = run_config5(n5, rank, world, local_rank, stream, dist, timed, args)
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -616,7 +853,7 @@ def main():
         # per step: one run kernel + one NaN-fill kernel per run segment (1 segment at N = 1,
         # --exchange-segments / --gather-segments of them at N > 1); restores and exchanges
         # are copies, not kernels
-        "gpu_launches": 2 * args.steps * (1 if world == 1 else
+        "gpu_launches": 2 * args.steps * (1 if (world == 1 or push is not None) else
                                           (len(exchange.segments) if exchange is not None
                                            else len(seg_rows))),
         "roofline": roofline, "cpu_baseline": cpu,
@@ -627,8 +864,12 @@ def main():
         "tracked_ensemble": tracked,
         "biome_ensemble": biome,
         "exchange": None if world == 1 else
-        ("peer memory (CUDA IPC pulls, %d run segments)" % len(exchange.segments)
+        ("peer memory, pushed: one launch per rank, each finished 16-year slab copied into every "
+         "peer's gather block over NVLink while the kernel computes (hx_run_exchange), one host "
+         "barrier" if push is not None else
+         "peer memory (CUDA IPC pulls, %d run segments)" % len(exchange.segments)
          if exchange is not None else "NCCL all-gather (%d run segments)" % len(seg_rows)),
+        "numa": numa, "config4": config4, "config5": config5,
     }
     print(json.dumps(line))
     ens.close()

@@ -10,6 +10,10 @@ exchange of the job is an all-gather of the per-member summary outputs (SURVEY.m
                    over NVLink while its own kernel computes the next segment.  A collective
                    kernel cannot do that: it finds no room next to the persistent run kernel.
 """
+import os
+import subprocess
+
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -155,3 +159,53 @@ class PushExchange:
         self.ens.run_exchange(to_date)
         dist.barrier(group=self.group)      # everybody's pushes have landed
         return self.block
+
+
+def scenario_sorted_shards(member_scenario, world):
+    """members are sorted by scenario (stable: API order inside a
+    scenario) and the sorted list is cut into `world` contiguous balanced ranges, so that a GPU
+    holds few scenarios' tables and whole tiles of one scenario.
+    -> (order, bounds): order[p] = API index of the member at sorted position p; bounds[r] =
+    [lo, hi) of rank r's sorted positions.  inverse: np.argsort(order)."""
+    ms = np.asarray(member_scenario)
+    order = np.argsort(ms, kind="stable")
+    return order, [shard_range(len(order), r, world) for r in range(world)]
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates
+    pinned host buffers (first touch then places them on that node): eight ranks streaming
+    582 MB each per step into NUMA-remote memory is what made the 8-GPU end-to-end step 37 %
+    slower than the 1-GPU one in round 1.  -> dict describing what was done (for the bench line)."""
+    try:
+        bus = None
+        try:
+            p = torch.cuda.get_device_properties(device_index)
+            bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        except Exception:
+            out = subprocess.run(["nvidia-smi", "-i", str(device_index), "--query-gpu=pci.bus_id",
+                                  "--format=csv,noheader"], capture_output=True, text=True).stdout
+            bus = out.strip().lower()
+            if len(bus.split(":")[0]) == 8:      # nvidia-smi prints an 8-digit domain
+                bus = bus[4:]
+        base = "/sys/bus/pci/devices/" + bus
+        node = int(open(base + "/numa_node").read())
+        cpus = _parse_cpulist(open(base + "/local_cpulist").read())
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if node < 0 or not use or use == allowed:
+            return {"numa_node": node, "bound": False, "cpus": len(allowed)}
+        os.sched_setaffinity(0, use)
+        return {"numa_node": node, "bound": True, "cpus": len(use)}
+    except Exception as ex:  # binding is an optimisation, never a requirement
+        return {"bound": False, "error": repr(ex)}

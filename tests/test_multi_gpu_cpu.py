@@ -81,3 +81,27 @@ def test_two_rank_gather_matches_single_process(tmp_path):
     for i in (0, 2, 3, 5):
         st, _, o, _, _ = port.run_member(raw, S=X[i, 0], q10_rh=X[i, 1], beta=X[i, 2], diff=X[i, 3])
         assert np.array_equal(full[0, :, i], o[0]) and np.array_equal(full[1, :, i], o[1])
+
+
+def test_scenario_sorted_shards_unpermute():
+    """BASELINE.json configs[3] partition: members interleaved over 8 scenarios in
+    API order are sorted by scenario and cut into contiguous per-rank ranges; the gathered
+    [rank][column] block is un-permuted back to API order through the inverse of the sort."""
+    from hector_b200.sharding import scenario_sorted_shards
+    M = 8 * 24
+    ms = np.arange(M) % 8
+    payload = np.arange(M) * 10.0 + ms            # something that identifies the API member
+    for world in (1, 2, 4, 8):
+        order, bounds = scenario_sorted_shards(ms, world)
+        assert sorted(order.tolist()) == list(range(M))
+        per = M // world
+        gathered = np.empty((world, per))
+        for r, (lo, hi) in enumerate(bounds):
+            mine = order[lo:hi]
+            assert hi - lo == per
+            assert (np.diff(ms[mine]) >= 0).all()              # scenario-sorted inside the shard
+            assert len(set(ms[mine].tolist())) == max(1, 8 // world)
+            gathered[r] = payload[mine]
+        inv = np.argsort(order)
+        back = gathered[inv // per, inv % per]
+        assert np.array_equal(back, payload)
