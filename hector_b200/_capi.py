@@ -10,6 +10,8 @@ COUNTER_NAMES = ["rhs_evals", "rk_steps", "rk_rejected", "stashes", "newton_iter
                  "newton_calls", "failed_members", "member_years"]
 HX_FLAG_COLD_NEWTON = 1
 HX_FLAG_NO_SPINUP = 2
+HX_FLAG_EXACT_ATTEMPTS = 4
+HX_FLAG_KEEP_ORDER = 8
 
 EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "hx_ini_string", "hx_destroy", "hx_last_error", "hx_set_stream", "hx_set_scenario_series",
            "hx_set_scenario_table", "hx_set_member_scenario", "hx_set_param_scalar",

@@ -51,14 +51,17 @@ __global__ void k_gather_field(double *dst, const double *A, int f, int nfields,
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = A[HX_TILED(f, dev_of_api[i], nfields)];
 }
-/* out[m_api][k] = src[yidx[k]][dev_of_api[m_api]]  (tile transpose through shared memory) */
+/* out[m_api][k] = src[yidx[k]][col(m_api)]  (tile transpose through shared memory); col = the
+ * member itself for blocks kept in API order (the recorded outputs), dev_of_api[m] for blocks in
+ * device order (the tracking maps) */
 __global__ void k_fetch_transpose(double *out, const double *src, const int32_t *yidx,
                                   const int32_t *dev_of_api, int n_dates, int M, size_t Mpad) {
   __shared__ double tile[32][33];
   const int m0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int k = k0 + j, m = m0 + threadIdx.x;
-    if (k < n_dates && m < M) tile[j][threadIdx.x] = src[(size_t)yidx[k] * Mpad + dev_of_api[m]];
+    if (k < n_dates && m < M)
+      tile[j][threadIdx.x] = src[(size_t)yidx[k] * Mpad + (dev_of_api ? dev_of_api[m] : m)];
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -105,6 +108,10 @@ struct Engine {
   int M = 0, Mpad = 0, nrow = 0, nscen = 0;
   bool prepared = false, params_dirty = false;
   int cur_row = 0;
+  /* earliest table row changed since the last set-up (dated series edits; 0 for parameters):
+   * the state of every year before it is unaffected, which is what lets hx_reset_date serve R's
+   * setvar(core, dates, ...) + reset(core, min(dates) - 1) */
+  int dirty_from_row = 0x7fffffff;
   double last_run_ms = 0.0;
 
   /* host-side inputs */
@@ -129,8 +136,7 @@ struct Engine {
 
   /* permutation API <-> device */
   std::vector<int32_t> dev_of_api;
-  int32_t *d_dev_of_api = nullptr;
-  bool identity_perm = true;
+  int32_t *d_dev_of_api = nullptr, *d_api_of_dev = nullptr;
 
   /* device buffers */
   double *d_P = nullptr, *d_S = nullptr, *d_S_snap = nullptr, *d_D = nullptr, *d_ker = nullptr, *d_conv = nullptr,
@@ -365,7 +371,7 @@ struct Engine {
   void free_device() {
     void *ptrs[] = {d_BP, d_BF, d_BF_snap, d_P, d_S, d_S_snap, d_D, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
                     d_block_scen, d_status, d_status_snap, d_status_post, d_fail_year, d_spinup_steps, d_yidx,
-                    d_counters, d_dev_of_api, d_sched, d_T, d_TO, d_TK, d_TOK, d_REC, d_YCNT, d_trk_fail};
+                    d_counters, d_dev_of_api, d_api_of_dev, d_sched, d_T, d_TO, d_TK, d_TOK, d_REC, d_YCNT, d_trk_fail};
     for (void *p : ptrs)
       if (p) cudaFree(p);
     d_P = d_S = d_S_snap = d_D = d_ker = d_conv = d_sst = d_tland = d_out = d_scen = d_stage = nullptr;
@@ -377,7 +383,7 @@ struct Engine {
     d_TK = d_TOK = nullptr;
     d_trk_fail = nullptr;
     d_BP = d_BF = d_BF_snap = nullptr;
-    d_dev_of_api = nullptr;
+    d_dev_of_api = d_api_of_dev = nullptr;
     stage_bytes = 0;
     yidx_cap = 0;
   }
@@ -654,6 +660,7 @@ struct Engine {
                              cudaMemcpyDeviceToDevice, stream));
     cur_row = 0;
     params_dirty = false;
+    dirty_from_row = 0x7fffffff;
     return HX_OK;
   }
 };
@@ -898,7 +905,10 @@ int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, i
       const int r = year0 + k - h->cfg.start_year;
       if (r >= 0 && r < h->nrow) dst[r] = values[k];
     }
-    if (h->prepared) { h->tables_dirty = true; h->params_dirty = true; }
+    if (h->prepared) {
+      h->tables_dirty = true; h->params_dirty = true;
+      h->dirty_from_row = std::min(h->dirty_from_row, std::max(0, year0 - h->cfg.start_year));
+    }
     return HX_OK;
   }
   const int si = Engine::find_raw(name);
@@ -918,7 +928,10 @@ int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, i
     for (int r = 0; r < h->nrow; ++r) dst[r] = values[h->cfg.start_year - year0 + r];
     h->raw_set[scenario_id][si] = 1;
   }
-  if (h->prepared) { h->tables_dirty = true; h->params_dirty = true; } /* R: setvar + reset */
+  if (h->prepared) { /* R: setvar + reset */
+    h->tables_dirty = true; h->params_dirty = true;
+    h->dirty_from_row = std::min(h->dirty_from_row, std::max(0, year0 - h->cfg.start_year));
+  }
   return HX_OK;
 }
 
@@ -1021,6 +1034,7 @@ static int set_biome_param(hx_handle h, int ib, int f, double value, const doubl
     int rc = h->upload_biomes();
     if (rc) return rc;
     h->params_dirty = true;
+    h->dirty_from_row = 0;
   }
   return HX_OK;
 }
@@ -1050,6 +1064,7 @@ int hx_set_param_scalar(hx_handle h, const char *name, double value) {
     int rc = h->upload_param(pi);
     if (rc) return rc;
     h->params_dirty = true;
+    h->dirty_from_row = 0;
   }
   return HX_OK;
 }
@@ -1077,6 +1092,7 @@ int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_
     int rc = h->upload_param(pi);
     if (rc) return rc;
     h->params_dirty = true;
+    h->dirty_from_row = 0;
   }
   return HX_OK;
 }
@@ -1096,6 +1112,7 @@ int hx_set_param_device(hx_handle h, const char *name, const double *dev, int32_
   h->pvec[pi].clear();
   h->pvec_on_device_only[pi] = true;
   h->params_dirty = true;
+  h->dirty_from_row = 0;
   return HX_OK;
 }
 
@@ -1169,12 +1186,50 @@ int hx_prepare(hx_handle h) {
     Mpad += nb * HX_BLOCK;
   }
   h->Mpad = Mpad;
+  /* Inside a scenario the members are laid out so that the 32 members of a warp -- and the 128
+   * of a tile -- behave alike.  Members differ in how many ODE sub-steps a year takes (1 to 4,
+   * following the ocean's reduced-time-step machine) and a warp pays for its slowest lane: in
+   * caller order an LHS ensemble keeps 26.6 of 32 lanes busy (ncu, round 1).  How a member
+   * behaves is a smooth function of its parameters, so the members are sorted into a k-d tree
+   * over the per-member parameters that vary (median splits, cycling through the parameters,
+   * down to leaves of one warp): neighbours in every parameter share a warp.  Outputs stay in
+   * API order (api_of_dev), so nothing outside the engine sees the permutation. */
   h->dev_of_api.resize(M);
-  std::vector<int> fillp(seg_start);
-  h->identity_perm = true;
-  for (int i = 0; i < M; ++i) {
-    h->dev_of_api[i] = fillp[h->member_scen[i]]++;
-    if (h->dev_of_api[i] != i) h->identity_perm = false;
+  std::vector<int32_t> api_of_dev(Mpad, -1);
+  {
+    std::vector<std::vector<int>> of_scen(h->nscen);
+    for (int i = 0; i < M; ++i) of_scen[h->member_scen[i]].push_back(i);
+    std::vector<int> dims;
+    static const int first_dims[] = {PI_BETA, PI_S, PI_DIFF, PI_Q10};
+    for (int pi : first_dims)
+      if (!h->pvec[pi].empty()) dims.push_back(pi);
+    for (int pi = 0; pi < PI_COUNT; ++pi)
+      if (!h->pvec[pi].empty() && std::find(dims.begin(), dims.end(), pi) == dims.end()) dims.push_back(pi);
+    for (int s = 0; s < h->nscen; ++s) {
+      std::vector<int> &ix = of_scen[s];
+      if (!dims.empty() && !(h->cfg.flags & HX_FLAG_KEEP_ORDER)) {
+        /* iterative k-d ordering: (lo, hi, depth) ranges split at the median of one parameter */
+        struct Range { int lo, hi, depth; };
+        std::vector<Range> todo(1, Range{0, (int)ix.size(), 0});
+        while (!todo.empty()) {
+          const Range r = todo.back();
+          todo.pop_back();
+          if (r.hi - r.lo <= 32) continue;
+          const std::vector<double> &v = h->pvec[dims[r.depth % dims.size()]];
+          /* split at a multiple of 32 so that leaves are whole warps */
+          int mid = r.lo + ((r.hi - r.lo) / 2 + 31) / 32 * 32;
+          if (mid >= r.hi) mid = r.lo + (r.hi - r.lo) / 2;
+          std::nth_element(ix.begin() + r.lo, ix.begin() + mid, ix.begin() + r.hi,
+                           [&](int a, int b) { return v[a] < v[b] || (v[a] == v[b] && a < b); });
+          todo.push_back(Range{r.lo, mid, r.depth + 1});
+          todo.push_back(Range{mid, r.hi, r.depth + 1});
+        }
+      }
+      for (size_t k = 0; k < ix.size(); ++k) {
+        h->dev_of_api[ix[k]] = seg_start[s] + (int)k;
+        api_of_dev[seg_start[s] + (int)k] = ix[k];
+      }
+    }
   }
   std::vector<int32_t> status(Mpad, -1);
   for (int i = 0; i < M; ++i) status[h->dev_of_api[i]] = 0;
@@ -1229,6 +1284,8 @@ int hx_prepare(hx_handle h) {
   const int nb = h->n_biomes;
   C.n_biomes = nb;
   for (int i = 0; i < HX_MAX_BIOMES; ++i) C.biome_order[i] = i;
+  if ((h->cfg.flags & HX_FLAG_EXACT_ATTEMPTS) && (tracking || nb > 1))
+    return fail(HX_ERR_UNSUPPORTED, "HX_FLAG_EXACT_ATTEMPTS is available for plain and constraint runs only");
   if (nb > 1) {
     if (tracking)
       return fail(HX_ERR_UNSUPPORTED, "carbon tracking with more than one biome is not implemented");
@@ -1266,8 +1323,9 @@ int hx_prepare(hx_handle h) {
       cudaMalloc(&h->d_fail_year, Mp * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc(&h->d_spinup_steps, Mp * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc(&h->d_counters, HX_NCOUNTERS * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMalloc(&h->d_sched, (block_scen.size() + 1 + nrow / HX_SLAB_YEARS + 2) * sizeof(unsigned)) != cudaSuccess ||
+      cudaMalloc(&h->d_sched, (2 * block_scen.size() + 1 + nrow / HX_SLAB_YEARS + 2) * sizeof(unsigned)) != cudaSuccess ||
       cudaMalloc(&h->d_dev_of_api, (size_t)M * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&h->d_api_of_dev, Mp * sizeof(int32_t)) != cudaSuccess ||
       (nb > 1 &&
        (cudaMalloc(&h->d_BP, (size_t)nb * BP_COUNT * Mp * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_BF, (size_t)nb * BF_COUNT * Mp * sizeof(double)) != cudaSuccess ||
@@ -1293,6 +1351,8 @@ int hx_prepare(hx_handle h) {
     also(cudaMemcpyAsync(h->d_status_snap, status.data(), Mp * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     also(cudaMemcpyAsync(h->d_dev_of_api, h->dev_of_api.data(), (size_t)M * sizeof(int32_t),
                          cudaMemcpyHostToDevice, st));
+    also(cudaMemcpyAsync(h->d_api_of_dev, api_of_dev.data(), Mp * sizeof(int32_t),
+                         cudaMemcpyHostToDevice, st));
     also(cudaMemsetAsync(h->d_counters, 0, HX_NCOUNTERS * sizeof(unsigned long long), st));
     also(cudaMemsetAsync(h->d_fail_year, 0, Mp * sizeof(int32_t), st));
     also(cudaMemsetAsync(h->d_spinup_steps, 0, Mp * sizeof(int32_t), st));
@@ -1315,6 +1375,7 @@ int hx_prepare(hx_handle h) {
   HxDev &d = h->d;
   d.Mpad = Mpad; d.P = h->d_P; d.S = h->d_S; d.D = h->d_D; d.ker = h->d_ker; d.conv = h->d_conv;
   d.sst_hist = h->d_sst; d.tland_hist = h->d_tland; d.out = h->d_out; d.scen = h->d_scen;
+  d.api_of_dev = h->d_api_of_dev;
   d.block_scen = h->d_block_scen; d.status = h->d_status; d.fail_year = h->d_fail_year;
   d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters; d.sched = h->d_sched;
   d.T = h->d_T; d.TK = h->d_TK; d.TO = h->d_TO; d.TOK = h->d_TOK; d.REC = h->d_REC; d.YCNT = h->d_YCNT;
@@ -1383,11 +1444,16 @@ int hx_reset_date(hx_handle h, double date) {
   if (y <= h->cfg.start_year) return hx_reset(h);
   if (y > h->cfg.start_year + h->cur_row)
     return h->fail(HX_ERR_ARG, "reset date is after the current date"); /* core.cpp:520-523 */
-  if (h->params_dirty)
+  /* The run is deterministic (bit-reproducible), so the state at `date` is re-derived by running
+   * to it again.  After an input change that is still exact as long as the change only touches
+   * years after `date` -- R's setvar(core, dates, var, ...) followed by the reset to
+   * min(dates) - 1 it asks for (R/messages.R:107-140): the years up to `date` see the inputs
+   * they saw before.  A change that reaches further back (any undated parameter) would need
+   * the recorded state of the OLD run, which the engine does not keep. */
+  if (h->params_dirty && y - h->cfg.start_year >= h->dirty_from_row)
     return h->fail(HX_ERR_UNSUPPORTED,
-                   "reset to a date inside the run after parameters or inputs changed: the "
-                   "engine keeps no per-year state history; reset to the start date instead");
-  /* the run is deterministic (bit-reproducible), so the state at `date` is re-derived */
+                   "reset to a date inside the run after a change that also affects earlier "
+                   "years: the engine keeps no per-year state history; reset to the start date");
   int rc = hx_reset(h);
   if (rc) return rc;
   return hx_run(h, (double)y);
@@ -1459,10 +1525,6 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
     if (!outs[v]) return HX_ERR_ARG;
     slot[v] = h->d.out_slot[id];
   }
-  if (!h->identity_perm)
-    return h->fail(HX_ERR_UNSUPPORTED,
-                   "hx_run_stream needs members in API order on the device (one scenario, or "
-                   "members grouped by scenario); use hx_run + hx_fetch");
   {
     int rc = ensure_copy_stream(h);
     if (rc) return rc;
@@ -1779,8 +1841,8 @@ int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates
   if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_fetch: ") + cudaGetErrorString(e));
   const double *src = h->d_out + (size_t)slot * (h->nrow - 1) * h->Mpad;
   dim3 grid((h->M + 31) / 32, (n_dates + 31) / 32), block(32, 8);
-  k_fetch_transpose<<<grid, block, 0, st>>>(h->d_stage, src, h->d_yidx, h->d_dev_of_api, n_dates,
-                                           h->M, (size_t)h->Mpad);
+  k_fetch_transpose<<<grid, block, 0, st>>>(h->d_stage, src, h->d_yidx, nullptr, n_dates, h->M,
+                                           (size_t)h->Mpad);
   e = cudaGetLastError();
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(out, h->d_stage, (size_t)h->M * n_dates * sizeof(double),

@@ -553,13 +553,13 @@ __device__ __forceinline__ void conv_prepass(const double *__restrict__ sst,
 /* the yearly coupled step, rows r0+1 .. r1 (row = year - start_year).  TRACK = carbon tracking
  * compiled in (a second instantiation: the plain kernel carries none of its code). */
 /* failed members report NaN from the failing year on (the reference stops producing output) */
-__device__ __noinline__ void nan_fill_rows(const HxDev &d, int nyears, int m, int first, int last) {
+__device__ __noinline__ void nan_fill_rows(const HxDev &d, int nyears, int col, int first, int last) {
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   for (int s = 0; s < d.n_out; ++s)
-    for (int yi = first; yi < last; ++yi) d.out[((size_t)s * nyears + yi) * d.Mpad + m] = nan;
+    for (int yi = first; yi < last; ++yi) d.out[((size_t)s * nyears + yi) * d.Mpad + col] = nan;
 }
 
-template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES, bool NBP>
+template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES, bool NBP, bool EXACT>
 __global__ void __launch_bounds__(HX_BLOCK, MINCTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   /* dynamic shared memory (> 48 KB): scenario slabs | row 0 | chemistry constants | RK stages */
@@ -570,7 +570,6 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
   double (*chemk)[HX_BLOCK] = reinterpret_cast<double (*)[HX_BLOCK]>(hx_smem + HX_SMEM_CHEMK);
   double (*rk)[HX_BLOCK] = reinterpret_cast<double (*)[HX_BLOCK]>(hx_smem + HX_SMEM_RK);
   __shared__ __align__(8) uint64_t bars[1];
-  __shared__ unsigned s_ticket;
   const int tid = threadIdx.x;
   const int nyears_total = C.nrow - 1;
   const bool cold = (C.flags & HX_FLAG_COLD_NEWTON) != 0;
@@ -587,27 +586,72 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
   }
   __syncthreads();
 
-  /* Persistent CTAs over a work queue of (tile, slab) items, slab-major: item t covers the
-   * HX_SLAB_YEARS years of slab t / ntiles for the 128 members of tile t % ntiles.  A tile's
-   * slabs are sequentially dependent (state in S), so an item waits until the tile's previous
-   * slab has been published; with slab-major tickets that predecessor was handed out ntiles
-   * tickets earlier.  All tiles therefore advance together and every SM stays full until the
-   * last slab -- a static one-CTA-per-tile grid needs ceil(tiles / resident CTAs) full rounds
-   * (2 rounds for 512 tiles on 296 resident CTAs; 1.73 here). */
+  /* Persistent CTAs over the work items (tile, slab): the HX_SLAB_YEARS years of one slab for the
+   * 128 members of one tile.  A tile's slabs are sequentially dependent (state in S), its slabs
+   * may run on different CTAs.  A free CTA claims the LEAST ADVANCED tile that nobody is working
+   * on: its first warp scans the tiles' progress words (a warp-wide minimum by shuffles), lane 0
+   * takes the tile with a compare-and-swap on its busy word.  All tiles therefore advance
+   * together, slab-major -- what the streaming output wants -- and no CTA ever waits for a
+   * particular tile: with members sorted so that the members of a tile behave alike, tiles differ
+   * in cost by up to 1.5x and a fixed ticket order left the CTA that drew a slow tile's next slab
+   * spinning until the previous one was published.  (A static one-CTA-per-tile grid needs
+   * ceil(tiles / resident CTAs) full rounds: 2 for 512 tiles on 444 resident CTAs.) */
   const int ntiles = d.Mpad / HX_BLOCK;
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
-  const unsigned total_items = (unsigned)ntiles * (unsigned)nslab;
-  unsigned *ticket = d.sched;
-  unsigned *progress = d.sched + 1; /* [ntiles]: slabs of this launch already published */
-  unsigned item_no = 0;             /* items this CTA has processed: mbarrier phase */
+  unsigned *progress = d.sched + 1;            /* [ntiles]: slabs of this launch already published */
+  unsigned *busy = d.sched + 1 + ntiles + nslab; /* [ntiles]: 1 while a CTA works on the tile */
+  unsigned item_no = 0;                        /* items this CTA has processed: mbarrier phase */
+  __shared__ int s_tile, s_slab;
+  /* equal progress: prefer the tiles after this CTA's own offset, so that CTAs starting together
+   * do not all reach for the same tile */
+  const unsigned my_off = (unsigned)(((unsigned long long)blockIdx.x * (unsigned)ntiles) / gridDim.x);
 
   for (;;) {
-    if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+    if (tid < 32) {
+      int got_tile = -1, got_slab = 0;
+      for (;;) {
+        unsigned best = 0xffffffffu;
+        int remaining = 0;
+        for (int t = tid; t < ntiles; t += 32) {
+          unsigned pr, bz;
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(pr) : "l"(progress + t) : "memory");
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bz) : "l"(busy + t) : "memory");
+          if (pr < (unsigned)nslab) {
+            remaining = 1;
+            const unsigned rot = ((unsigned)t + (unsigned)ntiles - my_off) % (unsigned)ntiles;
+            if (!bz) best = min(best, (pr << 20) | rot); /* up to 2^20 tiles, 4095 slabs */
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+          remaining |= __shfl_xor_sync(0xffffffffu, remaining, o);
+        }
+        if (best == 0xffffffffu) {
+          if (!remaining) break;      /* every tile has finished the launch */
+          __nanosleep(400);           /* all unfinished tiles are being worked on */
+          continue;
+        }
+        const int t = (int)(((best & 0xfffffu) + my_off) % (unsigned)ntiles);
+        int ok = 0;
+        unsigned seen = 0;
+        if (tid == 0) {
+          if (atomicCAS(busy + t, 0u, 1u) == 0u) {
+            /* acquire: the tile's state as its previous slab left it (also drops stale L1 lines) */
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + t) : "memory");
+            if (seen == (best >> 20)) ok = 1;
+            else asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(busy + t), "r"(0u) : "memory");
+          }
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) { got_tile = t; got_slab = (int)(best >> 20); break; }
+      }
+      if (tid == 0) { s_tile = got_tile; s_slab = got_slab; }
+    }
     __syncthreads();
-    const unsigned t = s_ticket;
-    if (t >= total_items) break;
-    const int tile = (int)(t % (unsigned)ntiles);
-    const int s = (int)(t / (unsigned)ntiles);
+    const int tile = s_tile;
+    if (tile < 0) break;
+    const int s = s_slab;
     const int m = tile * HX_BLOCK + tid;
     const double *table = d.scen + (size_t)d.block_scen[tile] * C.nrow * SC_STRIDE;
     /* slab s covers table rows base .. base+HX_SLAB_YEARS (one overlap row for the y-1
@@ -621,18 +665,16 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
       fence_proxy_async();
       mbar_arrive_expect_tx(&bars[0], bytes);
       bulk_g2s(slab[0], table + (size_t)base * SC_STRIDE, bytes, &bars[0]);
-      /* wait for the tile's previous slab (acquire: also drops stale L1 lines of its state) */
-      unsigned seen;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + tile) : "memory");
-        if (seen < (unsigned)s) __nanosleep(200);
-      } while (seen < (unsigned)s);
     }
     for (int i = tid; i < SC_STRIDE; i += HX_BLOCK) row0[i] = table[i];
     __syncthreads();
     __threadfence(); /* every thread orders its state loads after the acquire above */
 
     const bool lane_ok = (d.status[m] == 0);
+    /* the output block is in API member order (what callers, copies and exchanges see); the
+     * engine orders members internally (by scenario, then so that the members of a warp behave
+     * alike), so a member's column is looked up once per work item.  -1: padding lane. */
+    const int mo = d.api_of_dev[m];
     const Bases BS = make_bases(d, C, m);
     /* history rows [0, n_pre) of the DOECLIM convolution, for all years of the slab at once */
     const int n_pre = ((base + 1) / HX_CONV_UNROLL) * HX_CONV_UNROLL;
@@ -761,7 +803,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         }
 
         /* --- CarbonCycleSolver::run --- */
-        solver_year<false, TRACK, CONSTR, BIOMES, NBP>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
+        solver_year<false, TRACK, CONSTR, BIOMES, NBP, NBP || EXACT>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
         if (mb.status) {
           d.status[m] = mb.status;
           d.fail_year[m] = y;
@@ -919,7 +961,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 #define EMIT(id, val)                                                              \
   do {                                                                             \
     const int slot_ = d.out_slot[id];                                              \
-    if (slot_ >= 0) d.out[((size_t)slot_ * nyears_total + yi) * Mp + m] = (val);   \
+    if (slot_ >= 0) d.out[((size_t)slot_ * nyears_total + yi) * Mp + mo] = (val);  \
   } while (0)
         EMIT(OUT_CO2, CO2_conc);
         EMIT(OUT_TAS, tas);
@@ -968,7 +1010,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
             for (int k = 0; k < BO_COUNT; ++k) {
               const int slot_ = d.out_slot[OUT_COUNT + ib * BO_COUNT + k];
               if (slot_ >= 0)
-                d.out[((size_t)slot_ * nyears_total + yi) * Mp + m] = biome_of(mb, ib).f(bf[k]);
+                d.out[((size_t)slot_ * nyears_total + yi) * Mp + mo] = biome_of(mb, ib).f(bf[k]);
             }
         }
 #undef EMIT
@@ -1003,7 +1045,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
       /* streaming run: the slab's output rows leave for the host as soon as every tile has
        * finished it, so a failed member's NaNs are written here, not by a pass after the run */
       const int stn = d.status[m];
-      if (stn > 0) nan_fill_rows(d, C.nrow - 1, m, max(d.fail_year[m] - C.start_year - 1, base), rend);
+      if (stn > 0) nan_fill_rows(d, C.nrow - 1, mo, max(d.fail_year[m] - C.start_year - 1, base), rend);
     }
     /* publish the tile's state: make this CTA's global stores visible, then release */
     __threadfence();
@@ -1011,6 +1053,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     if (tid == 0) {
       const unsigned done = (unsigned)s + 1u;
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + tile), "r"(done) : "memory");
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(busy + tile), "r"(0u) : "memory");
       if (d.slab_done) {
         /* the last tile to finish slab s raises the host's flag: a plain store into mapped
          * memory after a system-scope fence (the tiles are counted in device memory) */
@@ -1147,8 +1190,9 @@ __global__ void hx_nan_fill_kernel(const __grid_constant__ HxDev d, int start_ye
   int first = d.fail_year[m] - start_year - 1; /* output index of the failing year */
   if (first < yr0) first = yr0;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  const int col = d.api_of_dev[m];
   for (int s = 0; s < nsel; ++s)
-    for (int yi = first; yi < yr1; ++yi) d.out[((size_t)s * nyears + yi) * d.Mpad + m] = nan;
+    for (int yi = first; yi < yr1; ++yi) d.out[((size_t)s * nyears + yi) * d.Mpad + col] = nan;
 }
 
 /* ---- host-callable launchers ---- */
@@ -1166,7 +1210,7 @@ cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cuda
   return cudaGetLastError();
 }
 template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT = true, bool BIOMES = false,
-          bool NBP = CONSTR>
+          bool NBP = CONSTR, bool EXACT = false>
 static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
   /* the function attribute and the occupancy are per device (context): one cache slot per
    * device ordinal, so that engines on several GPUs can live in one process */
@@ -1176,13 +1220,13 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   if (e0 != cudaSuccess) return e0;
   if (dev < 0 || dev >= HX_MAX_DEVICES) return cudaErrorInvalidDevice;
   if (!resident_of[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP>,
+    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP>,
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT>,
                                                       HX_BLOCK, HX_SMEM_RUN_BYTES);
     if (e != cudaSuccess) return e;
     resident_of[dev] = sms * (per_sm > 0 ? per_sm : 1);
@@ -1192,9 +1236,9 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   const int ntiles = d.Mpad / HX_BLOCK;
   const int grid = ntiles < resident ? ntiles : resident;
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
-  cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1 + nslab) * sizeof(unsigned), st);
+  cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(2 * ntiles + 1 + nslab) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
+  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
@@ -1211,6 +1255,11 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
   if (d.T)
     return d.constrained ? launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st)
                          : launch_run_t<true, false, HX_TRACK_CTAS>(d, C, r0, r1, st);
+  if (C.flags & HX_FLAG_EXACT_ATTEMPTS) { /* the builds that execute abandoned ODE attempts */
+    if (d.constrained > 1) return launch_run_t<false, true, 2>(d, C, r0, r1, st); /* NBP: always exact */
+    return d.constrained ? launch_run_t<false, true, 2, true, false, false, true>(d, C, r0, r1, st)
+                         : launch_run_t<false, false, 2, true, false, false, true>(d, C, r0, r1, st);
+  }
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

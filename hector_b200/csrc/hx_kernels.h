@@ -30,14 +30,15 @@ struct HxDev {
   double *conv;             /* [HX_SLAB_YEARS][Mpad] per-slab partial convolution sums */
   double *sst_hist;         /* [nrow][Mpad] */
   double *tland_hist;       /* [nrow][Mpad] */
-  double *out;              /* [nsel][nrow-1][Mpad] */
+  double *out;              /* [nsel][nrow-1][Mpad], columns in API member order */
+  const int32_t *api_of_dev; /* [Mpad] API index (= output column) of each device member, -1 = padding */
   const double *scen;       /* [n_scen][nrow][SC_STRIDE] */
   const int32_t *block_scen; /* [Mpad / HX_BLOCK] scenario of each CTA */
   int32_t *status;          /* [Mpad]; -1 = padding lane */
   int32_t *fail_year;       /* [Mpad] */
   int32_t *spinup_steps;    /* [Mpad] */
   unsigned long long *counters; /* [HX_NCOUNTERS] */
-  unsigned *sched;              /* [1 + tiles + slabs]: work-queue ticket, per-tile progress, tiles done per slab */
+  unsigned *sched;              /* [1 + tiles + slabs + tiles]: (unused), per-tile progress, tiles done per slab, per-tile busy */
   int32_t out_slot[HX_OUT_IDS]; /* output id -> slot in `out`, -1 = not recorded; ids from
                                    OUT_COUNT on are the per-biome outputs */
   int32_t constrained;      /* 0 none; 1 some scenario carries a CO2 / CH4 / RF_tot / tas

@@ -42,7 +42,8 @@ OUTPUT_VARIABLES = ["CO2_concentration", "global_tas", "RF_tot", "RF_CO2", "heat
 MEMBER_STATUS = {0: "ok", 1: "negative flux/pool", 2: "mass not conserved",
                  3: "solver retries exhausted", 4: "no [H+] root", 5: "yearfraction out of bounds",
                  6: "CO2 SARF condition", 7: "ODE stepper", 8: "spin-up did not converge",
-                 9: "tracking fractions out of range"}
+                 9: "tracking fractions out of range",
+                 10: "needs exact_attempts=True (a skipped ODE attempt could have gone negative)"}
 # carbon tracking: tracked pools (fluxpool names) and the possible source names
 TRACK_POOLS = ["atmos_co2", "earth_c", "veg_c", "detritus_c", "soil_c", "permafrost_c",
                "thawedp_c", "HL", "LL", "intermediate", "deep"]
@@ -129,11 +130,15 @@ def _dp(a):
 class Ensemble:
     def __init__(self, n_members, scenarios, member_scenario=None, start_year=1745, end_year=2300,
                  device=0, outputs=("CO2_concentration", "global_tas"), cold_newton=False,
-                 spinup=True, stream=None, tracking_date=None, track_every=1, biomes=None):
+                 spinup=True, stream=None, tracking_date=None, track_every=1, biomes=None,
+                 exact_attempts=False, keep_order=False):
         """scenarios: one table [nrow, 44] (RAW_SERIES columns), or a list of them;
         member_scenario: int array [n_members] of indices into that list;
         tracking_date: [core] trackingDate -- carbon tracking from that year on, recorded every
         `track_every` years and in the end year (0: end year only);
+        exact_attempts: execute the ODE attempts the reference abandons whenever one could raise
+        its negativity exception (HX_FLAG_EXACT_ATTEMPTS; without it such a member stops with
+        status 10); keep_order: no internal re-ordering of the members (HX_FLAG_KEEP_ORDER);
         biomes: names of 2..4 biomes, in creation order, that replace the global one -- their
         pools and parameters are then set as "<biome>.<name>" (BIOME_PARAMETERS) before prepare."""
         self.L = _capi.lib()
@@ -142,7 +147,9 @@ class Ensemble:
         self.n_members = int(n_members)
         self.start_year, self.end_year = int(start_year), int(end_year)
         flags = (_capi.HX_FLAG_COLD_NEWTON if cold_newton else 0) | \
-                (0 if spinup else _capi.HX_FLAG_NO_SPINUP)
+                (0 if spinup else _capi.HX_FLAG_NO_SPINUP) | \
+                (_capi.HX_FLAG_EXACT_ATTEMPTS if exact_attempts else 0) | \
+                (_capi.HX_FLAG_KEEP_ORDER if keep_order else 0)
         cfg = _capi.HxConfig(self.n_members, len(scenarios), self.start_year, self.end_year,
                              int(device), flags)
         self.h = C.c_void_p()

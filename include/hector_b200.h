@@ -50,12 +50,22 @@ typedef struct hx_engine *hx_handle;
 #define HX_MEMBER_CO2SARF 6      /* forcing_component.cpp:353 */
 #define HX_MEMBER_STEPPER 7      /* odeint: 500 failed step-size searches */
 #define HX_MEMBER_SPINUP 8       /* spin-up did not converge within max_spinup (reference only logs) */
+#define HX_MEMBER_NEEDS_EXACT 10  /* not a reference failure: an ODE attempt the reference abandons
+                                    (and the engine skips) could have raised its negativity
+                                    exception for this member; re-run with HX_FLAG_EXACT_ATTEMPTS */
 #define HX_MEMBER_TRACKING 9     /* "fractions must be 0-1" / "pool_map must sum to ~1.0" fluxpool.hpp:105-112 */
 
 /* hx_config.flags */
 #define HX_FLAG_COLD_NEWTON 1u   /* start every [H+] solve from the Fujiwara bound like the
                                     reference (ocean_csys.cpp:141-153) instead of last root */
 #define HX_FLAG_NO_SPINUP 2u     /* do_spinup = 0 */
+#define HX_FLAG_EXACT_ATTEMPTS 4u /* execute the ODE attempts the reference abandons whenever one of
+                                    their stage states could go negative (slower build of the run
+                                    kernel; without it such a member stops with
+                                    HX_MEMBER_NEEDS_EXACT).  Plain and constraint runs only. */
+#define HX_FLAG_KEEP_ORDER 8u    /* keep members in caller order on the device (default: members of a
+                                    scenario are re-ordered so that the members of a warp behave
+                                    alike; outputs are in caller order either way) */
 
 typedef struct {
   int32_t n_members;   /* ensemble members owned by this engine (this GPU's shard) */
@@ -160,8 +170,11 @@ int hx_reset(hx_handle h);                   /* back to the post-spin-up state a
 /* Core::reset(resetdate) (core.cpp:511-549): date <= start_year is hx_reset; a date inside the
  * run restores the state of that year so that hx_run continues from it.  The engine keeps no
  * per-year state history (the reference keeps one tvector per state variable); it re-derives the
- * state by re-running to `date`, which is exact because runs are bit-reproducible -- and is
- * therefore refused (HX_ERR_UNSUPPORTED) if parameters or inputs changed since the last run. */
+ * state by re-running to `date`, which is exact because runs are bit-reproducible.  After input
+ * changes it stays exact -- and is allowed -- when every change made since the last run concerns
+ * years after `date` only: the dated hx_set_scenario_series edits of R's setvar(core, dates, ...)
+ * followed by reset(core, min(dates) - 1).  After a change that reaches back to `date` or
+ * earlier (any parameter) it is refused with HX_ERR_UNSUPPORTED: reset to the start instead. */
 int hx_reset_date(hx_handle h, double date);
 int hx_synchronize(hx_handle h);
 /* hx_run + fetch of every year of the segment in one call, with the device-to-host copies

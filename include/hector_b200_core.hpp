@@ -250,6 +250,9 @@ inline const char *member_failure(int status) { /* the reference's exception tex
     case HX_MEMBER_STEPPER: return "Max number of iterations exceeded in odeint";
     case HX_MEMBER_SPINUP: return "spin-up did not converge";
     case HX_MEMBER_TRACKING: return "fractions must be 0-1";
+    case HX_MEMBER_NEEDS_EXACT:
+      return "an ODE attempt the engine skips could have raised 'Flux and pool values may not be "
+             "negative'; re-run with HX_FLAG_EXACT_ATTEMPTS";
     default: return "model failure";
   }
 }

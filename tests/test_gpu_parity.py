@@ -393,6 +393,38 @@ def test_reset_to_a_date_inside_the_run():
     ens.close()
 
 
+def test_dated_setvar_then_reset_to_the_year_before():
+    """R: setvar(core, 2050:2060, FFI_EMISSIONS(), 0) marks the core for a reset to 2049
+    (R/messages.R:123-134) and run() performs it: the state of 2049 is that of the old run, the
+    new emissions act from 2050 on"""
+    import hector_b200 as hb
+    from oracle import port
+    raw = util.scenarios()["ssp245"]
+    ens = _engine(3, outputs=["CO2_concentration", "global_tas"])
+    S = np.array([2.5, 3.0, 4.0])
+    ens.setvar("S", S)
+    ens.run(2100)
+    old = ens.fetchvars(_years(1746, 2100))
+    yrs = np.arange(2050, 2061)
+    ens.setvar_series("ffi_emissions", yrs, np.zeros(yrs.size))
+    with pytest.raises(hb.HxError):
+        ens.reset(2055)                        # the change reaches back before 2055
+    ens.reset(2049)
+    assert ens.current_date == 2049
+    ens.run(2100)
+    new = ens.fetchvars(_years(1746, 2100))
+    edited = raw.copy()
+    edited[2050 - 1745:2061 - 1745, 0] = 0.0
+    for v in old:
+        assert np.array_equal(old[v][:, :2050 - 1746], new[v][:, :2050 - 1746]), v   # the past is the past
+    assert not np.array_equal(old["CO2_concentration"][:, 2052 - 1746:], new["CO2_concentration"][:, 2052 - 1746:])
+    for i in range(3):
+        st, _, out, _, _ = port.run_member(edited, S=S[i])
+        assert util.parity_err(new["CO2_concentration"][i], out[0][:355], "CO2_concentration") < TOL
+        assert util.parity_err(new["global_tas"][i], out[1][:355], "global_tas") < TOL
+    ens.close()
+
+
 @pytest.mark.parametrize("case", util.ref_outputs_extra(), ids=lambda c: c["name"])
 def test_extra_outputs_vs_reference_golden(case):
     import hector_b200 as hb
