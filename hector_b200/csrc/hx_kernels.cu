@@ -598,8 +598,8 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
    * ceil(tiles / resident CTAs) full rounds: 2 for 512 tiles on 444 resident CTAs.) */
   const int ntiles = d.Mpad / HX_BLOCK;
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
-  unsigned *progress = d.sched + 1;            /* [ntiles]: slabs of this launch already published */
-  unsigned *busy = d.sched + 1 + ntiles + nslab; /* [ntiles]: 1 while a CTA works on the tile */
+  /* one word per tile: (slabs of this launch already published << 1) | busy */
+  unsigned *state = d.sched + 1;
   unsigned item_no = 0;                        /* items this CTA has processed: mbarrier phase */
   __shared__ int s_tile, s_slab;
   /* equal progress: prefer the tiles after this CTA's own offset, so that CTAs starting together
@@ -612,14 +612,19 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
       for (;;) {
         unsigned best = 0xffffffffu;
         int remaining = 0;
-        for (int t = tid; t < ntiles; t += 32) {
-          unsigned pr, bz;
-          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(pr) : "l"(progress + t) : "memory");
-          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bz) : "l"(busy + t) : "memory");
-          if (pr < (unsigned)nslab) {
-            remaining = 1;
-            const unsigned rot = ((unsigned)t + (unsigned)ntiles - my_off) % (unsigned)ntiles;
-            if (!bz) best = min(best, (pr << 20) | rot); /* up to 2^20 tiles, 4095 slabs */
+        /* L2-coherent loads (ld.global.cg), four in flight per lane */
+        for (int t0 = tid; t0 < ntiles; t0 += 128) {
+          unsigned v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = (t0 + 32 * u < ntiles) ? __ldcg(state + t0 + 32 * u) : 0xffffffffu;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const unsigned pr = v[u] >> 1;
+            if (v[u] != 0xffffffffu && pr < (unsigned)nslab) {
+              remaining = 1;
+              const unsigned rot = ((unsigned)(t0 + 32 * u) + (unsigned)ntiles - my_off) % (unsigned)ntiles;
+              if (!(v[u] & 1u)) best = min(best, (pr << 20) | rot); /* up to 2^20 tiles, 2047 slabs */
+            }
           }
         }
 #pragma unroll
@@ -633,15 +638,13 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           continue;
         }
         const int t = (int)(((best & 0xfffffu) + my_off) % (unsigned)ntiles);
+        const unsigned want = (best >> 20) << 1;
         int ok = 0;
-        unsigned seen = 0;
-        if (tid == 0) {
-          if (atomicCAS(busy + t, 0u, 1u) == 0u) {
-            /* acquire: the tile's state as its previous slab left it (also drops stale L1 lines) */
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + t) : "memory");
-            if (seen == (best >> 20)) ok = 1;
-            else asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(busy + t), "r"(0u) : "memory");
-          }
+        if (tid == 0 && atomicCAS(state + t, want, want | 1u) == want) {
+          /* acquire: the tile's state as its previous slab left it (also drops stale L1 lines) */
+          unsigned seen;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(state + t) : "memory");
+          ok = 1;
         }
         ok = __shfl_sync(0xffffffffu, ok, 0);
         if (ok) { got_tile = t; got_slab = (int)(best >> 20); break; }
@@ -1052,8 +1055,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     __syncthreads(); /* also: everyone is done with slab[0] / row0 before they are refilled */
     if (tid == 0) {
       const unsigned done = (unsigned)s + 1u;
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + tile), "r"(done) : "memory");
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(busy + tile), "r"(0u) : "memory");
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(state + tile), "r"(done << 1) : "memory");
       if (d.slab_done) {
         /* the last tile to finish slab s raises the host's flag: a plain store into mapped
          * memory after a system-scope fence (the tiles are counted in device memory) */
@@ -1236,7 +1238,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   const int ntiles = d.Mpad / HX_BLOCK;
   const int grid = ntiles < resident ? ntiles : resident;
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
-  cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(2 * ntiles + 1 + nslab) * sizeof(unsigned), st);
+  cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1 + nslab) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
   hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
   return cudaGetLastError();

@@ -38,7 +38,7 @@ struct HxDev {
   int32_t *fail_year;       /* [Mpad] */
   int32_t *spinup_steps;    /* [Mpad] */
   unsigned long long *counters; /* [HX_NCOUNTERS] */
-  unsigned *sched;              /* [1 + tiles + slabs + tiles]: (unused), per-tile progress, tiles done per slab, per-tile busy */
+  unsigned *sched;              /* [1 + tiles + slabs]: (unused), per-tile (progress << 1 | busy), tiles done per slab */
   int32_t out_slot[HX_OUT_IDS]; /* output id -> slot in `out`, -1 = not recorded; ids from
                                    OUT_COUNT on are the per-biome outputs */
   int32_t constrained;      /* 0 none; 1 some scenario carries a CO2 / CH4 / RF_tot / tas
