@@ -37,6 +37,17 @@ namespace hx {
 #define HX_SMEM_CHEMK (HX_SMEM_ROW0 + SC_STRIDE * 8)
 #define HX_SMEM_RK (HX_SMEM_CHEMK + 10 * HX_BLOCK * 8)
 #define HX_SMEM_RUN_BYTES (HX_SMEM_RK + HX_RK_SLOTS * HX_BLOCK * 8)
+/* builds with two resident CTAs per SM have room for the tile's whole state block S next to
+ * that (2 x 111 KB of the SM's 228 KB): the year loop then reads and writes its state in shared
+ * memory, and HBM / L2 see it once per 16-year work item */
+#ifndef HX_SMEM_STATE
+#define HX_SMEM_STATE 1
+#endif
+#define HX_SMEM_STATE_BYTES (SI_COUNT * HX_BLOCK * 8)
+template <int MINCTAS>
+__host__ __device__ constexpr bool smem_state() { return HX_SMEM_STATE && MINCTAS == 2; }
+template <int MINCTAS>
+__host__ __device__ constexpr size_t run_smem_bytes() { return HX_SMEM_RUN_BYTES + (smem_state<MINCTAS>() ? HX_SMEM_STATE_BYTES : 0); }
 
 /* ---- small PTX wrappers: mbarrier + bulk async copy (TMA engine, UBLKCP in SASS) ---- */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -678,7 +689,14 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
      * engine orders members internally (by scenario, then so that the members of a warp behave
      * alike), so a member's column is looked up once per work item.  -1: padding lane. */
     const int mo = d.api_of_dev[m];
-    const Bases BS = make_bases(d, C, m);
+    Bases BS = make_bases(d, C, m);
+    double *const gS = BS.S;
+    if (smem_state<MINCTAS>()) {
+      double *smS = reinterpret_cast<double *>(hx_smem + HX_SMEM_RUN_BYTES) + tid;
+#pragma unroll 8
+      for (int i = 0; i < SI_COUNT; ++i) smS[i * HX_BLOCK] = gS[i * HX_BLOCK];
+      BS.S = smS;
+    }
     /* history rows [0, n_pre) of the DOECLIM convolution, for all years of the slab at once */
     const int n_pre = ((base + 1) / HX_CONV_UNROLL) * HX_CONV_UNROLL;
     conv_prepass<HX_SLAB_YEARS, HX_CONV_UNROLL>(BS.sst, BS.ker, base, n_pre, BS.conv);
@@ -1050,6 +1068,10 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
       const int stn = d.status[m];
       if (stn > 0) nan_fill_rows(d, C.nrow - 1, mo, max(d.fail_year[m] - C.start_year - 1, base), rend);
     }
+    if (smem_state<MINCTAS>()) { /* the state block goes back to global memory */
+#pragma unroll 8
+      for (int i = 0; i < SI_COUNT; ++i) gS[i * HX_BLOCK] = BS.S[i * HX_BLOCK];
+    }
     /* publish the tile's state: make this CTA's global stores visible, then release */
     __threadfence();
     __syncthreads(); /* also: everyone is done with slab[0] / row0 before they are refilled */
@@ -1224,12 +1246,12 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   if (!resident_of[dev]) {
     cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         HX_SMEM_RUN_BYTES);
+                                         (int)run_smem_bytes<MINCTAS>());
     if (e != cudaSuccess) return e;
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT>,
-                                                      HX_BLOCK, HX_SMEM_RUN_BYTES);
+                                                      HX_BLOCK, run_smem_bytes<MINCTAS>());
     if (e != cudaSuccess) return e;
     resident_of[dev] = sms * (per_sm > 0 ? per_sm : 1);
   }
@@ -1240,7 +1262,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
   cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1 + nslab) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT><<<grid, HX_BLOCK, HX_SMEM_RUN_BYTES, st>>>(d, C, r0, r1);
+  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT><<<grid, HX_BLOCK, run_smem_bytes<MINCTAS>(), st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {

@@ -18,7 +18,10 @@
 #define HX_YEAR_SYNC 1 /* one CTA barrier per simulated year: the warps share instruction fetches */
 #endif
 #ifndef HX_RUN_MIN_CTAS
-#define HX_RUN_MIN_CTAS 3 /* resident CTAs per SM the run kernel is compiled for (168 registers: a few spills, but 12 instead of 8 warps per SM hide more FP64 latency; measured 39.3 vs 40.8 ms) */
+#define HX_RUN_MIN_CTAS 2 /* resident CTAs per SM the run kernel is compiled for.  2: 246 registers, no
+                             spills, and room in shared memory for the tile's whole state block
+                             (31.6 ms at 65 536 members); 3: 168 registers with spills, state in
+                             global memory / L1 (32.5 ms); 2 without the state block: 32.7 ms */
 #endif
 
 struct HxDev {
