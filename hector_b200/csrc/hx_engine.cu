@@ -112,6 +112,17 @@ struct Engine {
    * the state of every year before it is unaffected, which is what lets hx_reset_date serve R's
    * setvar(core, dates, ...) + reset(core, min(dates) - 1) */
   int dirty_from_row = 0x7fffffff;
+  /* something the spin-up or the initial state depends on changed since the post-spin-up
+   * snapshot was taken (kSpinupParams, M0, biome inputs, any series): otherwise a reset after a
+   * parameter change restores the snapshot and only redoes the DOECLIM set-up (E-7: the spin-up
+   * is computed once per distinct spin-up parameter set) */
+  bool spinup_dirty = true;
+  static bool affects_spinup(int pi) {
+    if (pi == PI_M0) return true; /* initial CH4 */
+    for (int k : hx::kSpinupParams)
+      if (k == pi) return true;
+    return false;
+  }
   double last_run_ms = 0.0;
 
   /* host-side inputs */
@@ -614,6 +625,7 @@ struct Engine {
   }
 
   int run_setup_and_spinup() {
+    const bool tables_changed = tables_dirty; /* a CH4 constraint in the first row sets the initial CH4 */
     if (tables_dirty) {
       int rc = upload_tables();
       if (rc) return rc;
@@ -622,6 +634,23 @@ struct Engine {
     bool lo_active = pscalar[PI_LO_RATIO] != 0.0 || pvec_on_device_only[PI_LO_RATIO];
     for (double v : pvec[PI_LO_RATIO]) lo_active = lo_active || v != 0.0;
     d.constrained = tables_nbp ? 2 : (tables_constrained || lo_active) ? 1 : 0;
+    if (!spinup_dirty && !tables_changed) {
+      /* nothing the spin-up depends on changed: the post-spin-up snapshot still stands */
+      CUDA_TRY(cudaMemcpyAsync(d_S, d_S_snap, (size_t)SI_COUNT * Mpad * sizeof(double),
+                               cudaMemcpyDeviceToDevice, stream));
+      if (d_BF)
+        CUDA_TRY(cudaMemcpyAsync(d_BF, d_BF_snap, (size_t)n_biomes * BF_COUNT * Mpad * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, stream));
+      CUDA_TRY(cudaMemcpyAsync(d_status, d_status_post, (size_t)Mpad * sizeof(int32_t),
+                               cudaMemcpyDeviceToDevice, stream));
+      CUDA_TRY(hx::launch_setup(d, C, stream, 2)); /* DOECLIM matrices, lag kernel, derived constants */
+      if (d_T) CUDA_TRY(hx::launch_track_init(d, stream));
+      if (d_trk_fail) CUDA_TRY(cudaMemsetAsync(d_trk_fail, 0, (size_t)Mpad * sizeof(int32_t), stream));
+      cur_row = 0;
+      params_dirty = false;
+      dirty_from_row = 0x7fffffff;
+      return HX_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(d_status, d_status_snap, (size_t)Mpad * sizeof(int32_t),
                              cudaMemcpyDeviceToDevice, stream));
     if (spinup_shared() && M > 1) {
@@ -661,6 +690,7 @@ struct Engine {
     cur_row = 0;
     params_dirty = false;
     dirty_from_row = 0x7fffffff;
+    spinup_dirty = false;
     return HX_OK;
   }
 };
@@ -1035,6 +1065,7 @@ static int set_biome_param(hx_handle h, int ib, int f, double value, const doubl
     if (rc) return rc;
     h->params_dirty = true;
     h->dirty_from_row = 0;
+    h->spinup_dirty = true;
   }
   return HX_OK;
 }
@@ -1065,6 +1096,7 @@ int hx_set_param_scalar(hx_handle h, const char *name, double value) {
     if (rc) return rc;
     h->params_dirty = true;
     h->dirty_from_row = 0;
+    if (Engine::affects_spinup(pi)) h->spinup_dirty = true;
   }
   return HX_OK;
 }
@@ -1093,6 +1125,7 @@ int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_
     if (rc) return rc;
     h->params_dirty = true;
     h->dirty_from_row = 0;
+    if (Engine::affects_spinup(pi)) h->spinup_dirty = true;
   }
   return HX_OK;
 }
@@ -1113,6 +1146,7 @@ int hx_set_param_device(hx_handle h, const char *name, const double *dev, int32_
   h->pvec_on_device_only[pi] = true;
   h->params_dirty = true;
   h->dirty_from_row = 0;
+  if (Engine::affects_spinup(pi)) h->spinup_dirty = true;
   return HX_OK;
 }
 

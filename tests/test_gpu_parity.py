@@ -217,6 +217,48 @@ def test_error_behaviour():
     ens.close()
 
 
+def test_reset_after_parameter_change_equals_a_fresh_engine():
+    """setvar -> reset -> run.  A change that the spin-up does not depend on (S, diff, q10_rh,
+    beta, forcing scalars) restores the post-spin-up snapshot and only redoes the DOECLIM set-up;
+    one that it does depend on (f_nppv, M0 ...) re-runs set-up and spin-up.  Either way the result
+    is what a fresh engine with those values produces, bit for bit."""
+    M = 200
+    X = util.lhs(M, seed=9)
+    names = ["S", "q10_rh", "beta", "diff"]
+
+    def fresh(**extra):
+        e = _engine(M, outputs=["CO2_concentration", "global_tas"])
+        for j, n in enumerate(names):
+            e.setvar(n, X[:, j])
+        for k, v in extra.items():
+            e.setvar(k, v)
+        e.run()
+        g = e.fetchvars(_years())
+        e.close()
+        return g
+
+    ens = _engine(M, outputs=["CO2_concentration", "global_tas"])
+    for j, n in enumerate(names):
+        ens.setvar(n, X[:, j])
+    ens.run()
+    steps = [dict(S=X[::-1, 0].copy(), aero_scalar=1.2),        # snapshot path
+             dict(f_nppv=np.linspace(0.3, 0.4, M)),             # spin-up parameter: full path
+             dict(diff=X[::-1, 3].copy()),                      # snapshot path again, after a full one
+             dict(M0=700.0)]                                    # initial CH4: full path
+    applied = {}
+    for change in steps:
+        for k, v in change.items():
+            ens.setvar(k, v)
+        applied.update(change)
+        ens.reset()
+        ens.run()
+        got = ens.fetchvars(_years())
+        ref = fresh(**applied)
+        for v in got:
+            assert np.array_equal(got[v], ref[v], equal_nan=True), (list(change), v)
+    ens.close()
+
+
 def test_parameter_change_inside_a_run_needs_a_reset():
     """a setvar in the middle of a run used to restart silently from start_year and
     overrun run_stream's buffers (sized from the current date); it is refused until reset()"""
