@@ -188,6 +188,76 @@ struct Engine {
     return code;
   }
 
+  /* per-member N2O / halocarbon parameters (the GAS build): values given per member, by GP_* id;
+   * scalars stay in UC_N2O / TN2O0 / halo_* above */
+  std::vector<double> gvec[GP_COUNT];
+  double *d_GP = nullptr, *d_GF = nullptr, *d_GF_snap = nullptr, *d_scen_gas = nullptr;
+  bool gas_per_member() const {
+    if (!pvec[PI_N0].empty()) return true;
+    for (const std::vector<double> &v : gvec)
+      if (!v.empty()) return true;
+    return false;
+  }
+  double gas_scalar(int gp) const {
+    if (gp == GP_UC_N2O) return UC_N2O;
+    if (gp == GP_TN2O0) return TN2O0;
+    const int g = (gp - GP_HALO0) / 5, f = (gp - GP_HALO0) % 5;
+    const double *tab[5] = {halo_tau, halo_rho, halo_delta, halo_H0, halo_mm};
+    return tab[f][g];
+  }
+  /* "UC_N2O", "TN2O0", "<gas>.tau|rho|delta|H0|molarMass" -> GP_* id, or -1 */
+  static int find_gas_param(const char *name) {
+    if (!strcmp(name, "UC_N2O")) return GP_UC_N2O;
+    if (!strcmp(name, "TN2O0")) return GP_TN2O0;
+    const char *dot = strchr(name, '.');
+    if (!dot) return -1;
+    const std::string gas(name, dot - name), field(dot + 1);
+    static const char *const fields[5] = {"tau", "rho", "delta", "H0", "molarMass"};
+    for (int g = 0; g < HX_NHALO; ++g)
+      if (gas == hx::kHaloNames[g])
+        for (int f = 0; f < 5; ++f)
+          if (field == fields[f]) return GP_HALO0 + 5 * g + f;
+    return -1;
+  }
+  double gas_value(int gp, int member) const { return gvec[gp].empty() ? gas_scalar(gp) : gvec[gp][member]; }
+  int upload_gas() {
+    for (int gp = 0; gp < GP_COUNT; ++gp) {
+      k_fill_field<<<(Mpad + 255) / 256, 256, 0, stream>>>(d_GP, gp, GP_COUNT, gas_scalar(gp), Mpad);
+      CUDA_TRY(cudaGetLastError());
+      if (gvec[gp].empty()) continue;
+      int rc = ensure_pinned((size_t)M * sizeof(double));
+      if (rc) return rc;
+      rc = ensure_stage((size_t)M * sizeof(double));
+      if (rc) return rc;
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      memcpy(h_pinned, gvec[gp].data(), (size_t)M * sizeof(double));
+      CUDA_TRY(cudaMemcpyAsync(d_stage, h_pinned, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, stream));
+      k_scatter_field<<<(M + 255) / 256, 256, 0, stream>>>(d_GP, gp, GP_COUNT, d_stage, d_dev_of_api, M);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return HX_OK;
+  }
+  /* one member's halocarbon series with its own parameters (the derived outputs of the GAS
+   * build): concentration and adjusted forcing per row, halocarbon_component.cpp:181-229 */
+  void halo_series_member(int s, int g, int member, std::vector<double> &conc, std::vector<double> &rf) const {
+    const double tau = gas_value(GP_HALO0 + 5 * g + 0, member), rho = gas_value(GP_HALO0 + 5 * g + 1, member),
+                 delta = gas_value(GP_HALO0 + 5 * g + 2, member), mm = gas_value(GP_HALO0 + 5 * g + 4, member);
+    double Ha = gas_value(GP_HALO0 + 5 * g + 3, member);
+    const double *E = raw[s].data() + (size_t)(RAW_HALO0 + g) * nrow;
+    conc.assign(nrow, 0.0);
+    rf.assign(nrow, 0.0);
+    const double expfac = std::exp(-(1 / tau));
+    for (int r = 1; r < nrow; ++r) {
+      const double emissMol = E[r] / mm * 1.0;
+      const double concDeltaEmiss = emissMol / (0.1 * 1.8);
+      Ha = Ha * expfac + concDeltaEmiss * tau * (1.0 - expfac);
+      conc[r] = Ha;
+      const double rf_unadjusted = rho * Ha;
+      rf[r] = rf_unadjusted + delta * rf_unadjusted;
+    }
+  }
+
   /* biomes: hx_set_biomes */
   int n_biomes = 1;
   std::vector<std::string> biome_names;
@@ -380,7 +450,7 @@ struct Engine {
   int fetch_derived(const char *name, const double *dates, int n_dates, double *out, int &rc);
 
   void free_device() {
-    void *ptrs[] = {d_BP, d_BF, d_BF_snap, d_P, d_S, d_S_snap, d_D, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
+    void *ptrs[] = {d_GP, d_GF, d_GF_snap, d_scen_gas, d_BP, d_BF, d_BF_snap, d_P, d_S, d_S_snap, d_D, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
                     d_block_scen, d_status, d_status_snap, d_status_post, d_fail_year, d_spinup_steps, d_yidx,
                     d_counters, d_dev_of_api, d_api_of_dev, d_sched, d_T, d_TO, d_TK, d_TOK, d_REC, d_YCNT, d_trk_fail};
     for (void *p : ptrs)
@@ -394,6 +464,7 @@ struct Engine {
     d_TK = d_TOK = nullptr;
     d_trk_fail = nullptr;
     d_BP = d_BF = d_BF_snap = nullptr;
+    d_GP = d_GF = d_GF_snap = d_scen_gas = nullptr;
     d_dev_of_api = d_api_of_dev = nullptr;
     stage_bytes = 0;
     yidx_cap = 0;
@@ -641,6 +712,9 @@ struct Engine {
       if (d_BF)
         CUDA_TRY(cudaMemcpyAsync(d_BF, d_BF_snap, (size_t)n_biomes * BF_COUNT * Mpad * sizeof(double),
                                  cudaMemcpyDeviceToDevice, stream));
+      if (d_GF)
+        CUDA_TRY(cudaMemcpyAsync(d_GF, d_GF_snap, (size_t)GF_COUNT * Mpad * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, stream));
       CUDA_TRY(cudaMemcpyAsync(d_status, d_status_post, (size_t)Mpad * sizeof(int32_t),
                                cudaMemcpyDeviceToDevice, stream));
       CUDA_TRY(hx::launch_setup(d, C, stream, 2)); /* DOECLIM matrices, lag kernel, derived constants */
@@ -684,6 +758,9 @@ struct Engine {
                              cudaMemcpyDeviceToDevice, stream));
     if (d_BF)
       CUDA_TRY(cudaMemcpyAsync(d_BF_snap, d_BF, (size_t)n_biomes * BF_COUNT * Mpad * sizeof(double),
+                               cudaMemcpyDeviceToDevice, stream));
+    if (d_GF)
+      CUDA_TRY(cudaMemcpyAsync(d_GF_snap, d_GF, (size_t)GF_COUNT * Mpad * sizeof(double),
                                cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(d_status_post, d_status, (size_t)Mpad * sizeof(int32_t),
                              cudaMemcpyDeviceToDevice, stream));
@@ -769,10 +846,12 @@ int Engine::fetch_derived(const char *name, const double *dates, int n_dates, do
   const double aci_beta = 2.279759, s_BCOC = 111.05064063,
                s_SO2 = (260.34644166 * 1000) * (32.065 / 64.066);
   const double nan = std::nan("");
+  std::vector<double> m_conc, m_rf; /* GAS build: this member's own halocarbon series */
   for (int i = 0; i < M; ++i) {
     const int s = member_scen[i];
     const double *R = raw[s].data();
     auto rawv = [&](int series, int r) { return R[(size_t)series * nrow + r]; };
+    if (d_GP && gas >= 0) halo_series_member(s, gas, i, m_conc, m_rf);
     /* absolute forcing of the agent in row r */
     auto absolute = [&](int r, int k) -> double {
       switch (kind) {
@@ -794,8 +873,9 @@ int Engine::fetch_derived(const char *name, const double *dates, int n_dates, do
           const double Ma = k < 0 ? rec_base[i] : rec[(size_t)i * n_dates + k];
           return 0.0485 * ((Ma - M0) / (1831 - M0));
         }
-        case K_HALO_RF: case K_HALO_ADJ: return hrf[s][(size_t)r * HX_NHALO + gas];
-        case K_HALO_CONC: return hconc[s][(size_t)r * HX_NHALO + gas];
+        case K_HALO_RF: case K_HALO_ADJ:
+          return d_GP ? m_rf[r] : hrf[s][(size_t)r * HX_NHALO + gas];
+        case K_HALO_CONC: return d_GP ? m_conc[r] : hconc[s][(size_t)r * HX_NHALO + gas];
         default: return nan;
       }
     };
@@ -929,6 +1009,9 @@ int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, i
   if (scenario_id < 0 || scenario_id >= h->nscen) return h->fail(HX_ERR_ARG, "bad scenario id");
   const int ci = Engine::find_constraint(name);
   if (ci >= 0) {
+    if (h->prepared && h->d_GP)
+      return h->fail(HX_ERR_UNSUPPORTED, "constraints cannot be added to a run with per-member N2O / "
+                                         "halocarbon parameters");
     /* a constraint series may cover any part of the run; NaN = no entry for that year */
     double *dst = h->cons[scenario_id].data() + (size_t)ci * h->nrow;
     for (int k = 0; k < n; ++k) { /* entries outside [year0, year0 + n) are kept */
@@ -943,6 +1026,10 @@ int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, i
   }
   const int si = Engine::find_raw(name);
   if (si < 0) return h->fail(HX_ERR_ARG, std::string("unknown scenario series: ") + name);
+  if (h->prepared && h->d_GP && (si == RAW_N2O_E || si == RAW_N2O_NAT || si >= RAW_HALO0))
+    return h->fail(HX_ERR_UNSUPPORTED, "with per-member N2O / halocarbon parameters the gas emission "
+                                       "series are fixed at hx_prepare");
+
   double *dst = h->raw[scenario_id].data() + (size_t)si * h->nrow;
   if (year0 > h->cfg.start_year || year0 + n - 1 < h->cfg.end_year) {
     /* a few years of a series that is already there: R's setvar(core, dates, var, values)
@@ -989,6 +1076,10 @@ int hx_set_member_scenario(hx_handle h, const int32_t *scen, int32_t n) {
 }
 
 static int set_special_scalar(hx_engine *h, const char *name, double v) {
+  {
+    const int gp = Engine::find_gas_param(name);
+    if (gp >= 0) h->gvec[gp].clear();
+  }
   if (!strcmp(name, "trackingDate")) { h->tracking_date = (int)v; return 1; }
   if (!strcmp(name, "baseyear")) { h->baseyear = v; return 1; }
   if (!strcmp(name, "max_spinup")) { h->max_spinup = (int)v; return 1; }
@@ -1114,8 +1205,18 @@ int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_
   if (pi >= 0 && h->n_biomes > 1 && Engine::is_biome_replaced(pi))
     return h->fail(HX_ERR_ARG, std::string(name) + ": cannot have both global and biome-specific "
                                                    "data (simpleNbox-runtime.cpp:66-69)");
-  if (pi < 0) return h->fail(HX_ERR_ARG, std::string("unknown per-member parameter: ") + name);
-  if (pi == PI_N0) return h->fail(HX_ERR_UNSUPPORTED, "N0 is scalar only (host N2O series)");
+  if (pi < 0) {
+    /* N2O / halocarbon parameters per member: the run then carries the 27 gas recurrences on
+     * the device (n2o_component.cpp:98-116, halocarbon_component.cpp:127-136) */
+    const int gp = Engine::find_gas_param(name);
+    if (gp < 0) return h->fail(HX_ERR_ARG, std::string("unknown per-member parameter: ") + name);
+    if (h->prepared) return h->fail(HX_ERR_STATE, std::string(name) + " per member must be set before hx_prepare");
+    if (n != h->M) return h->fail(HX_ERR_ARG, "hx_set_param: n != n_members");
+    h->gvec[gp].assign(per_member, per_member + n);
+    return HX_OK;
+  }
+  if (pi == PI_N0 && h->prepared)
+    return h->fail(HX_ERR_STATE, "N0 per member must be set before hx_prepare");
   if (n != h->M) return h->fail(HX_ERR_ARG, "hx_set_param: n != n_members");
   h->pvec[pi].assign(per_member, per_member + n);
   h->pvec_on_device_only[pi] = false;
@@ -1162,7 +1263,13 @@ int hx_get_param(hx_handle h, const char *name, double *out, int32_t n) {
     }
   }
   const int pi = h->find_param(name);
-  if (pi < 0) return h->fail(HX_ERR_ARG, std::string("unknown parameter: ") + name);
+  if (pi < 0) {
+    const int gp = Engine::find_gas_param(name);
+    if (gp < 0) return h->fail(HX_ERR_ARG, std::string("unknown parameter: ") + name);
+    if (n != h->M) return h->fail(HX_ERR_ARG, "hx_get_param: n != n_members");
+    for (int i = 0; i < n; ++i) out[i] = h->gas_value(gp, i);
+    return HX_OK;
+  }
   if (n != h->M) return h->fail(HX_ERR_ARG, "hx_get_param: n != n_members");
   if (h->pvec_on_device_only[pi]) {
     cudaSetDevice(h->cfg.device);
@@ -1336,6 +1443,33 @@ int hx_prepare(hx_handle h) {
   std::vector<double> tab;
   bool any_constraint = false, any_nbp = false;
   h->build_tables(tab, any_constraint, any_nbp);
+  const bool gas = h->gas_per_member();
+  std::vector<double> gas_tab;
+  if (gas) {
+    bool gas_constraint = false;
+    for (int sc = 0; sc < h->nscen; ++sc)
+      for (int series = CN_N2O; series < CN_COUNT; series = (series == CN_N2O ? CN_HALO0 : series + 1)) {
+        const double *c = h->con(sc, series);
+        for (int r = 0; r < nrow; ++r) gas_constraint = gas_constraint || c[r] == c[r];
+      }
+    bool lo_active = h->pscalar[PI_LO_RATIO] != 0.0;
+    for (double v : h->pvec[PI_LO_RATIO]) lo_active = lo_active || v != 0.0;
+    if (tracking || nb > 1 || any_constraint || gas_constraint || lo_active ||
+        (h->cfg.flags & HX_FLAG_EXACT_ATTEMPTS))
+      return fail(HX_ERR_UNSUPPORTED, "per-member N2O / halocarbon parameters are available for plain "
+                                      "runs only (no tracking, biomes, constraints, lo_warming_ratio, "
+                                      "exact attempts)");
+    gas_tab.assign((size_t)h->nscen * nrow * HX_GAS_COLS, 0.0);
+    for (int sc = 0; sc < h->nscen; ++sc) {
+      const double *R = h->raw[sc].data();
+      for (int r = 0; r < nrow; ++r) {
+        double *row = gas_tab.data() + ((size_t)sc * nrow + r) * HX_GAS_COLS;
+        row[0] = R[(size_t)RAW_N2O_E * nrow + r];
+        row[1] = R[(size_t)RAW_N2O_NAT * nrow + r];
+        for (int g = 0; g < HX_NHALO; ++g) row[2 + g] = R[(size_t)(RAW_HALO0 + g) * nrow + r];
+      }
+    }
+  }
 
   const size_t Mp = Mpad;
   const int nsel = (int)h->out_sel.size();
@@ -1360,6 +1494,11 @@ int hx_prepare(hx_handle h) {
       cudaMalloc(&h->d_sched, (2 * block_scen.size() + 1 + nrow / HX_SLAB_YEARS + 2) * sizeof(unsigned)) != cudaSuccess ||
       cudaMalloc(&h->d_dev_of_api, (size_t)M * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc(&h->d_api_of_dev, Mp * sizeof(int32_t)) != cudaSuccess ||
+      (gas &&
+       (cudaMalloc(&h->d_GP, (size_t)GP_COUNT * Mp * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_GF, (size_t)GF_COUNT * Mp * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_GF_snap, (size_t)GF_COUNT * Mp * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&h->d_scen_gas, gas_tab.size() * sizeof(double)) != cudaSuccess)) ||
       (nb > 1 &&
        (cudaMalloc(&h->d_BP, (size_t)nb * BP_COUNT * Mp * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_BF, (size_t)nb * BF_COUNT * Mp * sizeof(double)) != cudaSuccess ||
@@ -1397,6 +1536,10 @@ int hx_prepare(hx_handle h) {
     also(cudaMemsetAsync(h->d_sst, 0, (size_t)nrow * Mp * sizeof(double), st));
     also(cudaMemsetAsync(h->d_tland, 0, (size_t)nrow * Mp * sizeof(double), st));
     if (h->d_BF) also(cudaMemsetAsync(h->d_BF, 0, (size_t)nb * BF_COUNT * Mp * sizeof(double), st));
+    if (gas) {
+      also(cudaMemsetAsync(h->d_GF, 0, (size_t)GF_COUNT * Mp * sizeof(double), st));
+      also(cudaMemcpyAsync(h->d_scen_gas, gas_tab.data(), gas_tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     if (h->d_trk_fail) also(cudaMemsetAsync(h->d_trk_fail, 0, Mp * sizeof(int32_t), st));
     /* the host vectors above must outlive the copies */
     also(cudaStreamSynchronize(st));
@@ -1414,6 +1557,7 @@ int hx_prepare(hx_handle h) {
   d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters; d.sched = h->d_sched;
   d.T = h->d_T; d.TK = h->d_TK; d.TO = h->d_TO; d.TOK = h->d_TOK; d.REC = h->d_REC; d.YCNT = h->d_YCNT;
   d.BP = h->d_BP; d.BF = h->d_BF; d.trk_fail = h->d_trk_fail;
+  d.GP = h->d_GP; d.GF = h->d_GF; d.scen_gas = h->d_scen_gas;
   h->rec_elems = block_scen.size() * hx::track_record_bytes_per_cta() / sizeof(double);
   h->ycnt_bytes = block_scen.size() * hx::track_ycnt_bytes_per_tile();
   h->tables_constrained = any_constraint;
@@ -1434,6 +1578,10 @@ int hx_prepare(hx_handle h) {
   }
   if (h->d_BP) {
     int rc = h->upload_biomes();
+    if (rc) { h->prepared = false; return rc; }
+  }
+  if (h->d_GP) {
+    int rc = h->upload_gas();
     if (rc) { h->prepared = false; return rc; }
   }
   int rc = h->run_setup_and_spinup();
@@ -1459,6 +1607,9 @@ int hx_reset(hx_handle h) {
   if (e == cudaSuccess && h->d_BF)
     e = cudaMemcpyAsync(h->d_BF, h->d_BF_snap,
                         (size_t)h->n_biomes * BF_COUNT * h->Mpad * sizeof(double),
+                        cudaMemcpyDeviceToDevice, h->stream);
+  if (e == cudaSuccess && h->d_GF)
+    e = cudaMemcpyAsync(h->d_GF, h->d_GF_snap, (size_t)GF_COUNT * h->Mpad * sizeof(double),
                         cudaMemcpyDeviceToDevice, h->stream);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(h->d_status, h->d_status_post, (size_t)h->Mpad * sizeof(int32_t),

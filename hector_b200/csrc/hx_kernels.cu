@@ -104,6 +104,8 @@ struct Bases {
   double *S, *D, *ker, *sst, *tland, *conv;
   const double *BP; /* per-biome parameters / state of this member (null: single biome) */
   double *BF;
+  const double *GP; /* per-member N2O / halocarbon parameters and state (null: host series) */
+  double *GF;
 };
 __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, int m) {
   const size_t tile = (size_t)(m / HX_BLOCK), ln = (size_t)(m % HX_BLOCK);
@@ -117,6 +119,8 @@ __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, in
   b.tland = d.tland_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
   b.BP = d.BP ? d.BP + tile * (size_t)C.n_biomes * BP_COUNT * HX_BLOCK + ln : nullptr;
   b.BF = d.BF ? d.BF + tile * (size_t)C.n_biomes * BF_COUNT * HX_BLOCK + ln : nullptr;
+  b.GP = d.GP ? d.GP + tile * (size_t)GP_COUNT * HX_BLOCK + ln : nullptr;
+  b.GF = d.GF ? d.GF + tile * (size_t)GF_COUNT * HX_BLOCK + ln : nullptr;
   return b;
 }
 #define PAR(i) __ldg(BS.P + (i) * HX_BLOCK)
@@ -336,6 +340,17 @@ __device__ __forceinline__ void setup_state(const HxDev &d, const HxConst &C, co
     }
     STATE(SI_VEG) = sv; STATE(SI_DET) = sd; STATE(SI_SOIL) = ss; STATE(SI_PERMAFROST) = sp;
     STATE(SI_EOS_VEGC) = sv;
+  }
+  if (BS.GF) {
+    /* N2OComponent / HalocarbonComponent::prepareToRun: N2O starts at N0 (n2o_component.cpp:
+     * 141-146), every halocarbon at H0 (halocarbon_component.cpp:160-166); exp(-1 / tau) once */
+    BS.GF[GF_N2O * HX_BLOCK] = PAR(PI_N0);
+    for (int g = 0; g < HX_NHALO; ++g) {
+      const double tau = __ldg(BS.GP + (GP_HALO0 + 5 * g + 0) * HX_BLOCK);
+      BS.GF[(GF_HA0 + g) * HX_BLOCK] = __ldg(BS.GP + (GP_HALO0 + 5 * g + 3) * HX_BLOCK);
+      BS.GF[(GF_EXPFAC0 + g) * HX_BLOCK] = hx_exp(-(1 / tau));
+      BS.GF[(GF_RF0 + g) * HX_BLOCK] = 0.0;
+    }
   }
   BS.sst[0] = 0.0;   /* row 0: temp_sst[0] = 0 */
   BS.tland[0] = 0.0;
@@ -570,7 +585,7 @@ __device__ __noinline__ void nan_fill_rows(const HxDev &d, int nyears, int col, 
     for (int yi = first; yi < last; ++yi) d.out[((size_t)s * nyears + yi) * d.Mpad + col] = nan;
 }
 
-template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES, bool NBP, bool EXACT>
+template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES, bool NBP, bool EXACT, bool GAS>
 __global__ void __launch_bounds__(HX_BLOCK, MINCTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   /* dynamic shared memory (> 48 KB): scenario slabs | row 0 | chemistry constants | RK stages */
@@ -761,6 +776,33 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           STATE(SI_CH4) = ch4_new;
         }
 
+        /* --- N2OComponent::run (n2o_component.cpp:150-191) and the 26 HalocarbonComponent::run
+         * (halocarbon_component.cpp:181-229) with this member's own parameters --- */
+        double n2o_conc = sc[SC_N2O];
+        if (GAS) {
+          const double *gt = d.scen_gas + ((size_t)d.block_scen[tile] * C.nrow + r) * HX_GAS_COLS;
+          const double N0 = PAR(PI_N0);
+          const double previous_n2o = BS.GF[GF_N2O * HX_BLOCK];
+          const double tau_n2o = __ldg(BS.GP + GP_TN2O0 * HX_BLOCK) * hx_pow(previous_n2o / N0, -0.05);
+          const double current_n2oem = __ldg(gt + 0) + __ldg(gt + 1);
+          const double dN2O = current_n2oem / __ldg(BS.GP + GP_UC_N2O * HX_BLOCK) - previous_n2o / tau_n2o;
+          n2o_conc = previous_n2o + dN2O;
+          BS.GF[GF_N2O * HX_BLOCK] = n2o_conc;
+#pragma unroll 2
+          for (int g = 0; g < HX_NHALO; ++g) {
+            const double *gp = BS.GP + (GP_HALO0 + 5 * g) * HX_BLOCK;
+            const double tau = __ldg(gp), rho = __ldg(gp + HX_BLOCK), delta = __ldg(gp + 2 * HX_BLOCK),
+                         mm = __ldg(gp + 4 * HX_BLOCK);
+            const double expfac = BS.GF[(GF_EXPFAC0 + g) * HX_BLOCK];
+            const double emissMol = __ldg(gt + 2 + g) / mm * 1.0;
+            const double concDeltaEmiss = emissMol / (0.1 * 1.8);
+            const double Ha = BS.GF[(GF_HA0 + g) * HX_BLOCK] * expfac + concDeltaEmiss * tau * (1.0 - expfac);
+            BS.GF[(GF_HA0 + g) * HX_BLOCK] = Ha;
+            const double rf_unadjusted = rho * Ha;
+            BS.GF[(GF_RF0 + g) * HX_BLOCK] = rf_unadjusted + delta * rf_unadjusted;
+          }
+        }
+
         /* --- OceanComponent::run: ocean_component.cpp:356-407 --- */
         mb.S[SI_X_FLUXSUM * HX_TILE] = 0.0;
         mb.timesteps = 0;
@@ -865,7 +907,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           /* preindustrial CH4 / N2O as the CH4 and N2O components hold them after prepareToRun:
            * a start-date constraint replaces the parameter (ch4_component.cpp:141-146,
            * n2o_component.cpp:141-146; row 0 of the N2O series is N0 by construction) */
-          fp.C0 = LP_C0(p); fp.M0 = PAR(PI_M0); fp.N0 = row0[SC_N2O]; fp.aero = PAR(PI_AERO);
+          fp.C0 = LP_C0(p); fp.M0 = PAR(PI_M0); fp.N0 = GAS ? PAR(PI_N0) : row0[SC_N2O]; fp.aero = PAR(PI_AERO);
           if (CONSTR) {
             const double c0 = row0[SC_C_CH4];
             if (c0 == c0) fp.M0 = c0;
@@ -874,7 +916,10 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           fp.delta_n2o = PAR(PI_DELTA_N2O); fp.rho_bc = PAR(PI_RHO_BC); fp.rho_oc = PAR(PI_RHO_OC);
           fp.rho_so2 = PAR(PI_RHO_SO2); fp.rho_nh3 = PAR(PI_RHO_NH3);
           double fco2, fch4, fn2o;
-          double F = forcing_total(fp, sc, CO2_conc, ch4, o3, fco2, fch4, fn2o, mb.status);
+          double F = GAS ? forcing_total<HX_BLOCK>(fp, sc, n2o_conc, BS.GF + GF_RF0 * HX_BLOCK, CO2_conc, ch4,
+                                                   o3, fco2, fch4, fn2o, mb.status)
+                         : forcing_total<1>(fp, sc, n2o_conc, sc + SC_HALO0, CO2_conc, ch4, o3, fco2,
+                                            fch4, fn2o, mb.status);
           if (CONSTR) { /* user-supplied total forcing: forcing_component.cpp:498-505 */
             const double c = sc[SC_C_RFTOT];
             if (c == c) F = c;
@@ -997,7 +1042,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_SST, sst_new);
         EMIT(OUT_PERMAFROST_C, mb.perm);
         EMIT(OUT_CH4, ch4);
-        EMIT(OUT_N2O, sc[SC_N2O]);
+        EMIT(OUT_N2O, n2o_conc);
         EMIT(OUT_O3, o3);
         EMIT(OUT_LAND_TAS, tland_new);
         EMIT(OUT_VEG_C, mb.veg);
@@ -1234,7 +1279,7 @@ cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cuda
   return cudaGetLastError();
 }
 template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT = true, bool BIOMES = false,
-          bool NBP = CONSTR, bool EXACT = false>
+          bool NBP = CONSTR, bool EXACT = false, bool GAS = false>
 static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
   /* the function attribute and the occupancy are per device (context): one cache slot per
    * device ordinal, so that engines on several GPUs can live in one process */
@@ -1244,13 +1289,13 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   if (e0 != cudaSuccess) return e0;
   if (dev < 0 || dev >= HX_MAX_DEVICES) return cudaErrorInvalidDevice;
   if (!resident_of[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT>,
+    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)run_smem_bytes<MINCTAS>());
     if (e != cudaSuccess) return e;
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT>,
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS>,
                                                       HX_BLOCK, run_smem_bytes<MINCTAS>());
     if (e != cudaSuccess) return e;
     resident_of[dev] = sms * (per_sm > 0 ? per_sm : 1);
@@ -1262,7 +1307,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
   cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1 + nslab) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT><<<grid, HX_BLOCK, run_smem_bytes<MINCTAS>(), st>>>(d, C, r0, r1);
+  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS><<<grid, HX_BLOCK, run_smem_bytes<MINCTAS>(), st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
@@ -1279,6 +1324,8 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
   if (d.T)
     return d.constrained ? launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st)
                          : launch_run_t<true, false, HX_TRACK_CTAS>(d, C, r0, r1, st);
+  if (d.GP) /* per-member N2O / halocarbon parameters: the GAS build (plain runs, every output) */
+    return launch_run_t<false, false, 2, true, false, false, false, true>(d, C, r0, r1, st);
   if (C.flags & HX_FLAG_EXACT_ATTEMPTS) { /* the builds that execute abandoned ODE attempts */
     if (d.constrained > 1) return launch_run_t<false, true, 2>(d, C, r0, r1, st); /* NBP: always exact */
     return d.constrained ? launch_run_t<false, true, 2, true, false, false, true>(d, C, r0, r1, st)

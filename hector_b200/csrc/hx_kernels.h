@@ -63,6 +63,10 @@ struct HxDev {
   const double *BP;         /* [tile][n_biomes * BP_COUNT][128] per-biome parameters */
   double *BF;               /* [tile][n_biomes * BF_COUNT][128] per-biome pools and factors */
   uint32_t *TOK;            /* [track_nrec][HX_NPOOL][Mpad] recorded key masks */
+  /* per-member N2O / halocarbon parameters (null: host series per scenario, the default) */
+  const double *GP;         /* [tile][GP_COUNT][128] */
+  double *GF;               /* [tile][GF_COUNT][128] */
+  const double *scen_gas;   /* [n_scen][nrow][HX_GAS_COLS] emissions */
   int32_t *trk_fail;        /* [Mpad] first year whose replay saw a bad mix, 0 = none: written by
                                the replay kernel only, folded into status by hx_track_merge */
 };

@@ -173,6 +173,28 @@ enum { /* per-biome state */
 enum { BO_VEG = 0, BO_DET, BO_SOIL, BO_PERMAFROST, BO_THAWED, BO_NPP, BO_RH, BO_COUNT };
 #define HX_OUT_IDS (OUT_COUNT + HX_MAX_BIOMES * BO_COUNT)
 
+/* ---- per-member N2O / halocarbon parameters and state (the GAS build of the run kernel) ----
+ * By default the N2O concentration and the 26 halocarbon forcings are member-independent series
+ * computed on the host per scenario (E-5).  When one of their parameters is given per member
+ * (n2o_component.cpp:98-116: N0, UC_N2O, TN2O0; halocarbon_component.cpp:127-136: tau, rho, delta,
+ * H0, molarMass of a gas) the 27 recurrences run per member on the device: parameters
+ * GP[tile][GP_COUNT][128], state GF[tile][GF_COUNT][128], and the emissions come from a second
+ * scenario table [scenario][row][HX_GAS_COLS] (N2O_emissions, N2O_natural_emissions, 26 x
+ * <gas>_emissions). */
+enum {
+  GP_UC_N2O = 0, GP_TN2O0,
+  GP_HALO0, /* gas g: GP_HALO0 + 5 g + {0 tau, 1 rho, 2 delta, 3 H0, 4 molarMass} */
+  GP_COUNT = GP_HALO0 + 5 * HX_NHALO
+};
+enum {
+  GF_N2O = 0,                      /* N2O concentration of the last year */
+  GF_HA0 = 1,                      /* 26 halocarbon concentrations */
+  GF_EXPFAC0 = GF_HA0 + HX_NHALO,  /* 26 x exp(-1 / tau), set-up */
+  GF_RF0 = GF_EXPFAC0 + HX_NHALO,  /* 26 x this year's adjusted forcing rho Ha (1 + delta) */
+  GF_COUNT = GF_RF0 + HX_NHALO
+};
+#define HX_GAS_COLS (2 + HX_NHALO)
+
 /* ---- engine-wide constants handed to every kernel ---- */
 struct HxConst {
   int32_t start_year, end_year, nrow; /* nrow = end - start + 1 */

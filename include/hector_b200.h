@@ -141,8 +141,15 @@ int hx_set_member_scenario(hx_handle h, const int32_t *scenario_of_member, int32
  * pf_sigma, fpf_static, tt, tu, twi, tid, preind_surface_c, preind_interdeep_c, eps_abs,
  * eps_rel, dt, eps_spinup, aero_scalar, vol_scalar, delta_co2, delta_ch4, delta_n2o, rho_bc,
  * rho_oc, rho_so2, rho_nh3, M0, Tsoil, Tstrat, UC_CH4, TOH0, CNOX, CCO, CNMVOC, CCH4, PO3, N0,
- * lo_warming_ratio per member or scalar; baseyear, max_spinup, UC_N2O, TN2O0 and the halocarbon
- * tau/rho/delta/H0/molarMass (<gas>.tau ...) scalar only).  Defaults = inst/input/hector_ssp245.ini. */
+ * lo_warming_ratio per member or scalar; baseyear and max_spinup scalar only).  Defaults =
+ * inst/input/hector_ssp245.ini.
+ *
+ * The N2O and halocarbon parameters -- N0, UC_N2O, TN2O0 (n2o_component.cpp:98-116) and
+ * <gas>.tau / .rho / .delta / .H0 / .molarMass for the 26 halocarbons (halocarbon_component.cpp:
+ * 127-136) -- are scalars by default, and their 27 series are then computed once per scenario on
+ * the host.  Given per member (hx_set_param, before hx_prepare) they move the 27 recurrences
+ * into the run kernel (its GAS build): plain runs only -- with tracking, biomes, constraints,
+ * lo_warming_ratio or HX_FLAG_EXACT_ATTEMPTS hx_prepare returns HX_ERR_UNSUPPORTED. */
 int hx_set_param_scalar(hx_handle h, const char *name, double value);
 int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_t n);
 /* same, from a DEVICE pointer (no host round trip) */

@@ -22,6 +22,20 @@ def reference_present():
     return os.path.exists(os.path.join(REF, "src", "main.cpp"))
 
 
+def build_xchg():
+    """tests/cpp/test_xchg.cpp: the push exchange driven from C++ by two forked processes (needs
+    only this repo and the CUDA runtime headers) -> path"""
+    os.makedirs(OUT, exist_ok=True)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = os.path.join(OUT, "xchg_cpp")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-I",
+                    os.path.join(cuda, "include"), os.path.join(HERE, "test_xchg.cpp"), "-L", LIBDIR,
+                    "-lhector_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart",
+                    "-Wl,-rpath," + LIBDIR, "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", exe],
+                   check=True, capture_output=True, text=True)
+    return exe
+
+
 def build():
     """-> {name: path}; raises CalledProcessError with the compiler's output on failure"""
     os.makedirs(OUT, exist_ok=True)
@@ -38,4 +52,5 @@ def build():
 
 
 if __name__ == "__main__":
+    print(build_xchg())
     print(build())

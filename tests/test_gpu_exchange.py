@@ -90,3 +90,24 @@ def test_two_process_peer_exchange(tmp_path, mode):
         assert np.array_equal(r0[v][1].T, r1["mine_" + v])
         assert np.array_equal(r1[v][0].T, r0["mine_" + v])
         assert np.array_equal(r0[v], r1[v])
+
+
+def test_push_exchange_from_cpp():
+    """the same exchange without Python: tests/cpp/test_xchg.cpp forks two processes that use only
+    the C ABI (hx_xchg_create / hx_xchg_open / hx_run_exchange / hx_xchg_block) and a socketpair"""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cpp"))
+    import build_compat
+    exe = os.path.join(build_compat.OUT, "xchg_cpp")
+    if not os.path.exists(exe):
+        try:
+            exe = build_compat.build_xchg()
+        except Exception as ex:   # no compiler / CUDA headers on this box
+            pytest.skip("cannot build tests/cpp/test_xchg.cpp here: %r" % (ex,))
+    ini = None
+    for d in ("/root/reference/inst/input", os.path.join(ROOT, "oracle", "_ref", "input")):
+        if os.path.exists(os.path.join(d, "hector_ssp245.ini")):
+            ini = os.path.join(d, "hector_ssp245.ini")
+    if ini is None:
+        pytest.skip("reference input data not available")
+    r = subprocess.run([exe, ini], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "XCHG_OK" in r.stdout, r.stdout + r.stderr

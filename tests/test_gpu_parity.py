@@ -217,6 +217,66 @@ def test_error_behaviour():
     ens.close()
 
 
+def test_per_member_n2o_and_halocarbon_parameters():
+    """N0, UC_N2O, TN2O0 and the tau / rho / delta / H0 of halocarbons given PER MEMBER
+    (n2o_component.cpp:98-116, halocarbon_component.cpp:127-136): the run kernel's GAS build carries
+    the 27 gas recurrences on the device instead of reading the host's per-scenario series"""
+    from oracle import port
+    import hector_b200 as hb
+    M = 48
+    rng = np.random.default_rng(41)
+    raw = util.scenarios()["ssp370"]
+    d = port.default_params()
+    per = {"N0": d.N0 * rng.uniform(0.97, 1.03, M), "UC_N2O": d.UC_N2O * rng.uniform(0.9, 1.1, M),
+           "TN2O0": d.TN2O0 * rng.uniform(0.9, 1.1, M), "S": rng.uniform(2.0, 5.0, M)}
+    gases = ["CF4", "CFC11", "HFC134a", "SF6", "CH3Br"]
+    gidx = [port.HALOS.index(g) for g in gases]
+    for g, k in zip(gases, gidx):
+        per[g + ".tau"] = d.halo_tau[k] * rng.uniform(0.7, 1.4, M)
+        per[g + ".rho"] = d.halo_rho[k] * rng.uniform(0.8, 1.2, M)
+        per[g + ".delta"] = rng.uniform(-0.1, 0.2, M)
+        per[g + ".H0"] = d.halo_H0[k] * rng.uniform(0.5, 1.5, M) + rng.uniform(0.0, 0.01, M)
+    outs = ["CO2_concentration", "global_tas", "RF_tot", "N2O_concentration", "RF_N2O", "ocean_timesteps"]
+    ens = hb.Ensemble(M, raw, outputs=outs)
+    for k, v in per.items():
+        ens.setvar(k, v)
+    ens.run()
+    st, _ = ens.status()
+    assert (st == 0).all()
+    got = ens.fetchvars(_years(), outs)
+    derived = {v: ens.fetch(v, _years()) for v in ("RF_CF4", "CFC11_concentration", "FadjSF6")}
+    assert np.allclose(ens.getvar("CF4.tau"), per["CF4.tau"])
+    for i in range(0, M, 3):
+        p = port.default_params(N0=per["N0"][i], UC_N2O=per["UC_N2O"][i], TN2O0=per["TN2O0"][i], S=per["S"][i])
+        for g, k in zip(gases, gidx):
+            p.halo_tau[k] = per[g + ".tau"][i]
+            p.halo_rho[k] = per[g + ".rho"][i]
+            p.halo_delta[k] = per[g + ".delta"][i]
+            p.halo_H0[k] = per[g + ".H0"][i]
+        ost, _, out, _, _ = port.run_member(raw, params=p)
+        assert ost == 0
+        for v in outs:
+            ref = out[port.OUT_NAMES.index(v)]
+            if v == "ocean_timesteps":
+                assert np.array_equal(got[v][i], ref)
+            else:
+                assert util.parity_err(got[v][i], ref, v) < TOL, (i, v, util.parity_err(got[v][i], ref, v))
+        n2o, hrf = port.gas_series(raw, p)                      # absolute, per row (row 0 = start year)
+        k = port.HALOS.index("CF4")
+        assert np.max(np.abs(derived["RF_CF4"][i] - hrf[1:, k]) / np.maximum(np.abs(hrf[1:, k]), 1e-6)) < TOL
+        k = port.HALOS.index("SF6")
+        base = 1750 - 1745
+        rel = np.where(np.arange(1, 556) >= base, hrf[1:, k] - hrf[base, k], 0.0)
+        assert np.max(np.abs(derived["FadjSF6"][i] - rel)) < 1e-12
+    # what the GAS build cannot be combined with is refused, not ignored
+    bad = hb.Ensemble(4, raw, tracking_date=1800)
+    bad.setvar("CF4.tau", np.full(4, 40000.0))
+    with pytest.raises(hb.HxError):
+        bad.prepare()
+    bad.close()
+    ens.close()
+
+
 def test_reset_after_parameter_change_equals_a_fresh_engine():
     """setvar -> reset -> run.  A change that the spin-up does not depend on (S, diff, q10_rh,
     beta, forcing scalars) restores the post-spin-up snapshot and only redoes the DOECLIM set-up;
