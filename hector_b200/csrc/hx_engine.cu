@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -450,7 +451,7 @@ struct Engine {
   int fetch_derived(const char *name, const double *dates, int n_dates, double *out, int &rc);
 
   void free_device() {
-    void *ptrs[] = {d_GP, d_GF, d_GF_snap, d_scen_gas, d_BP, d_BF, d_BF_snap, d_P, d_S, d_S_snap, d_D, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
+    void *ptrs[] = {d_GP, d_GF, d_GF_snap, d_scen_gas, d_BP, d_BF, d_BF_snap, d_P, d_S, d_S_snap, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
                     d_block_scen, d_status, d_status_snap, d_status_post, d_fail_year, d_spinup_steps, d_yidx,
                     d_counters, d_dev_of_api, d_api_of_dev, d_sched, d_T, d_TO, d_TK, d_TOK, d_REC, d_YCNT, d_trk_fail};
     for (void *p : ptrs)
@@ -1474,10 +1475,12 @@ int hx_prepare(hx_handle h) {
   const size_t Mp = Mpad;
   const int nsel = (int)h->out_sel.size();
 
-  if (cudaMalloc(&h->d_P, PI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
+  /* parameters and derived constants share one allocation (tried: a persisting-L2 window over it
+   * against the slabs' history streams -- 31.59 vs 31.65 ms, not kept) */
+  if (cudaMalloc(&h->d_P, (size_t)(PI_COUNT + DI_COUNT) * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_S, SI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_S_snap, SI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&h->d_D, DI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
+      (h->d_D = h->d_P + (size_t)PI_COUNT * Mp) == nullptr ||
       cudaMalloc(&h->d_ker, (size_t)HX_KER_ROWS(nrow) * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_conv, (size_t)HX_SLAB_YEARS * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_sst, (size_t)nrow * Mp * sizeof(double)) != cudaSuccess ||
