@@ -19,7 +19,7 @@ EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "h
            "hx_prepare", "hx_run", "hx_run_stream", "hx_reset", "hx_reset_date", "hx_synchronize", "hx_fetch", "hx_output_device",
            "hx_ipc_export", "hx_ipc_open", "hx_ipc_pull", "hx_ipc_wait", "hx_ipc_close",
            "hx_xchg_create", "hx_xchg_open", "hx_run_exchange", "hx_xchg_block", "hx_xchg_close", "hx_event_record", "hx_event_synchronize", "hx_member_status", "hx_set_tracking", "hx_set_biomes", "hx_biome_count", "hx_biome_name", "hx_tracking_date", "hx_fetch_tracking", "hx_tracking_years", "hx_counters", "hx_current_date", "hx_last_run_ms",
-           "hx_spinup_state", "hx_measure_fp64_peak", "hx_measure_hbm_copy", "hx_version"]
+           "hx_spinup_state", "hx_measure_fp64_peak", "hx_measure_hbm_copy", "hx_diag_transcendentals", "hx_version"]
 
 
 class HxError(RuntimeError):
@@ -103,5 +103,7 @@ def lib():
     L.hx_spinup_state.argtypes = [vp, C.c_int32, dp]
     L.hx_measure_fp64_peak.argtypes = [C.c_int32, dp, dp]
     L.hx_measure_hbm_copy.argtypes = [C.c_int32, dp]
+    if hasattr(L, "hx_diag_transcendentals"):  # absent from older A/B builds (tools/gpu_ab.sh)
+        L.hx_diag_transcendentals.argtypes = [C.c_int32, C.c_int32, dp, dp, dp, C.c_int32]
     _LIB = L
     return L

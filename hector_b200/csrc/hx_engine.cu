@@ -507,6 +507,13 @@ struct Engine {
         double *row = tab.data() + ((size_t)s * nrow + r) * SC_STRIDE;
         for (int c = 0; c <= SC_MISC; ++c) row[c] = R[(size_t)c * nrow + r]; /* RAW_x == SC_x up to MISC */
         row[SC_N2O] = n2o[r];
+        row[SC_SQRT_N2O] = std::sqrt(n2o[r]);
+        {
+          const double aci_beta = 2.279759, s_BCOC = 111.05064063,
+                       s_SO2 = (260.34644166 * 1000) * (32.065 / 64.066);
+          const double E_BC = row[SC_BC], E_OC = row[SC_OC], E_SO2 = row[SC_SO2];
+          row[SC_ACI] = -1 * aci_beta * std::log(1 + (E_SO2 / s_SO2) + ((E_BC + E_OC) / s_BCOC));
+        }
         for (int g = 0; g < HX_NHALO; ++g) row[SC_HALO0 + g] = hrf[(size_t)r * HX_NHALO + g];
         row[SC_C_CO2] = cco2[r]; row[SC_C_CH4] = cch4[r];
         row[SC_C_RFTOT] = rftot[r]; row[SC_C_TAS] = tas[r]; row[SC_C_NBP] = cnbp[r];

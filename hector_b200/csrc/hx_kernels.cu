@@ -287,6 +287,8 @@ __device__ __forceinline__ void setup_doeclim(const Bases &BS, const HxConst &C)
   DER(DI_INV_UC_CH4) = 1.0 / PAR(PI_UC_CH4);
   DER(DI_INV_TSOIL) = 1.0 / PAR(PI_TSOIL);
   DER(DI_INV_TSTRAT) = 1.0 / PAR(PI_TSTRAT);
+  DER(DI_LOG_M0) = hx_log(PAR(PI_M0));
+  DER(DI_SQRT_M0) = sqrt(PAR(PI_M0));
 }
 
 /* initial pools: ocean_component.cpp:224-260, simpleNbox.cpp:45-81, simpleNbox-runtime.cpp:172 */
@@ -755,7 +757,10 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           const double previous_ch4 = STATE(SI_CH4);
           double toh = 0.0;
           if (previous_ch4 != M0) {
-            const double a = PAR(PI_CCH4) * ((1.0 * hx_log(previous_ch4)) - hx_log(M0));
+            /* log(previous_ch4) was taken last year for the ozone burden (below) and log(M0) by
+             * the set-up kernel: same function, same argument, same bits */
+            const double lprev = (r == 1) ? hx_log(previous_ch4) : STATE(SI_LOG_CH4);
+            const double a = PAR(PI_CCH4) * ((1.0 * lprev) - DER(DI_LOG_M0));
             const double b = PAR(PI_CNOX) * ((1.0 * sc[SC_NOX]) - row0[SC_NOX]);
             const double c = PAR(PI_CCO) * ((1.0 * sc[SC_CO]) - row0[SC_CO]);
             const double dd = PAR(PI_CNMVOC) * ((1.0 * sc[SC_NMVOC]) - row0[SC_NMVOC]);
@@ -861,8 +866,11 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
             window = (wsum + wcomp) / 200;
             STATE(SI_TLAND_WSUM) = wsum; STATE(SI_TLAND_WCOMP) = wcomp;
           }
-          if (BIOMES) slow_params_biomes(mb, C, p, tland, r == 1, window);
-          else slow_params(mb, p, tland, r == 1, window);
+          /* log(CO2 / C0) of the atmosphere at the start of the year: taken at the end of last
+           * year (below), where the forcing needs the same number */
+          const double lco2 = (r == 1) ? hx_log((mb.atmos * HX_PGC_TO_PPMVCO2) / LP_C0(p)) : STATE(SI_LOG_CO2R);
+          if (BIOMES) slow_params_biomes(mb, C, p, tland, r == 1, window, lco2);
+          else slow_params(mb, p, tland, r == 1, window, lco2);
         }
 
         /* --- CarbonCycleSolver::run --- */
@@ -899,7 +907,12 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 
         /* --- OzoneComponent::run (o3_component.cpp:126-146) + ForcingComponent::run --- */
         const double ch4 = STATE(SI_CH4);
-        const double o3 = (5 * hx_log(ch4)) + (0.125 * sc[SC_NOX]) + (0.0011 * sc[SC_CO]) +
+        /* the year's two remaining logarithms as one interleaved pair; both are needed again at
+         * the top of next year (OH lifetime, CO2 fertilisation) and travel in the state */
+        const HxPair lg = hx_log_x2(ch4, CO2_conc / LP_C0(p));
+        STATE(SI_LOG_CH4) = lg.a;
+        STATE(SI_LOG_CO2R) = lg.b;
+        const double o3 = (5 * lg.a) + (0.125 * sc[SC_NOX]) + (0.0011 * sc[SC_CO]) +
                           (0.0033 * sc[SC_NMVOC]);
         double rf_tot = 0.0, rf_co2 = 0.0, rf_ch4 = 0.0, rf_n2o = 0.0;
         if (y >= C.baseyear) {
@@ -908,9 +921,15 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
            * a start-date constraint replaces the parameter (ch4_component.cpp:141-146,
            * n2o_component.cpp:141-146; row 0 of the N2O series is N0 by construction) */
           fp.C0 = LP_C0(p); fp.M0 = PAR(PI_M0); fp.N0 = GAS ? PAR(PI_N0) : row0[SC_N2O]; fp.aero = PAR(PI_AERO);
+          /* square roots of member or scenario constants come from the set-up kernel / the
+           * scenario table (sqrt is correctly rounded everywhere: the same doubles) */
+          fp.sqM0 = DER(DI_SQRT_M0);
+          fp.sqN0 = GAS ? sqrt(fp.N0) : row0[SC_SQRT_N2O];
+          fp.sqNa = GAS ? sqrt(n2o_conc) : sc[SC_SQRT_N2O];
+          fp.ln_co2 = lg.b;
           if (CONSTR) {
             const double c0 = row0[SC_C_CH4];
-            if (c0 == c0) fp.M0 = c0;
+            if (c0 == c0) { fp.M0 = c0; fp.sqM0 = sqrt(c0); }
           }
           fp.vol = PAR(PI_VOL); fp.delta_co2 = PAR(PI_DELTA_CO2); fp.delta_ch4 = PAR(PI_DELTA_CH4);
           fp.delta_n2o = PAR(PI_DELTA_N2O); fp.rho_bc = PAR(PI_RHO_BC); fp.rho_oc = PAR(PI_RHO_OC);
@@ -1372,4 +1391,43 @@ cudaError_t launch_nan_fill(const HxDev &d, const HxConst &C, int nsel, int yr0,
   return cudaGetLastError();
 }
 
+/* diagnostics: the interleaved transcendentals (hx_exp_n / hx_log_n, hx_model.cuh) next to the
+ * library routines they restate, value by value (tests compare the two bit for bit) */
+__global__ void hx_transc_check_kernel(const double *x, double *fast, double *lib, int n, int which) {
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= n) return;
+  double a[4], y[4];
+  for (int k = 0; k < 4; ++k) a[k] = x[min(i0 + k, n - 1)];
+  if (which == 0) hx_exp_n<4, false>(a, y);
+  else if (which == 1) hx_exp_n<4, true>(a, y);
+  else hx_log_n<4>(a, y);
+  for (int k = 0; k < 4 && i0 + k < n; ++k) {
+    fast[i0 + k] = y[k];
+    lib[i0 + k] = which == 0 ? exp(a[k]) : which == 1 ? exp10(a[k]) : log(a[k]);
+  }
+}
+
 } // namespace hx
+
+extern "C" int hx_diag_transcendentals(int32_t device, int32_t which, const double *x, double *fast,
+                                       double *lib, int32_t n) {
+  if (!x || !fast || !lib || n <= 0 || which < 0 || which > 2) return HX_ERR_ARG;
+  int prev = 0;
+  if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) return HX_ERR_CUDA;
+  double *dx = nullptr, *df = nullptr, *dl = nullptr;
+  const size_t bytes = (size_t)n * sizeof(double);
+  cudaError_t e = cudaMalloc(&dx, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&df, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&dl, bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(dx, x, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const int threads = (n + 3) / 4;
+    hx::hx_transc_check_kernel<<<(threads + 127) / 128, 128>>>(dx, df, dl, n, which);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(fast, df, bytes, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(lib, dl, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(df); cudaFree(dl);
+  cudaSetDevice(prev);
+  return e == cudaSuccess ? HX_OK : HX_ERR_CUDA;
+}

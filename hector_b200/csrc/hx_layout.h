@@ -47,8 +47,12 @@ enum {
    * forcing [W/m2], global mean temperature [degC], net biome production [Pg C/yr]; N2O and halocarbon constraints are already
    * folded into SC_N2O / SC_HALO0.. on the host */
   SC_C_CO2 = SC_HALO0 + HX_NHALO, SC_C_CH4, SC_C_RFTOT, SC_C_TAS, SC_C_NBP,
-  SC_USED,                       /* 48 */
-  SC_STRIDE = 48                 /* 384 B per row: multiple of 16 B for cp.async.bulk */
+  /* member-independent pieces of the forcing, host-precomputed with the C library (the doubles
+   * the reference computes): -aci_beta log(1 + SO2 / s_SO2 + (BC + OC) / s_BCOC)
+   * (forcing_component.cpp:465-467) and sqrt(N2O concentration) */
+  SC_ACI, SC_SQRT_N2O,
+  SC_USED,                       /* 50 */
+  SC_STRIDE = 50                 /* 400 B per row: multiple of 16 B for cp.async.bulk */
 };
 
 /* ---- constraint series (what callers hand in), reference input names ---- */
@@ -98,6 +102,9 @@ enum {
    * thawed pool below 1e-10 and the four boxes sum to the solver's total only to the last ulps;
    * carbon-cycle-solver.cpp:232, 279) */
   SI_X_SOLVER_TPF, SI_X_SOLVER_OCEAN,
+  /* log(CH4) and log(CO2 / C0) as the year's end left them: the OH lifetime and the CO2
+   * fertilisation of the next year take the logarithms of the same numbers */
+  SI_LOG_CH4, SI_LOG_CO2R,
   SI_COUNT
 };
 
@@ -111,6 +118,7 @@ enum {
   DI_LNQ10,       /* log(q10_rh): pow(q10, x) is evaluated as exp(x * lnq10) */
   DI_QC1, DI_QC2, /* forcing-increment correction per unit dQ (temperature_component.cpp:471-475) */
   DI_INV_UC_CH4, DI_INV_TSOIL, DI_INV_TSTRAT, /* reciprocals of the CH4 constants */
+  DI_LOG_M0, DI_SQRT_M0,                      /* log and sqrt of the preindustrial CH4 */
   DI_COUNT
 };
 

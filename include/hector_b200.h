@@ -314,6 +314,10 @@ int hx_spinup_state(hx_handle h, int32_t member, double *out14);
  * hx_measure_hbm_copy: device-to-device copy of 1 GiB, read + write GB/s. ---- */
 int hx_measure_fp64_peak(int32_t device, double *tflops, double *fma_per_clk_per_sm);
 int hx_measure_hbm_copy(int32_t device, double *gbs);
+/* the run kernel's interleaved exp (which = 0) / exp10 (1) / log (2) next to the CUDA library's,
+ * for n host values: the two output arrays must be bit-identical (hx_model.cuh, hx_exp_n) */
+int hx_diag_transcendentals(int32_t device, int32_t which, const double *x, double *fast,
+                            double *lib, int32_t n);
 
 const char *hx_version(void);
 

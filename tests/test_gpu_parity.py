@@ -32,6 +32,42 @@ def _years(a=1746, b=2300):
     return np.arange(a, b + 1, dtype=np.float64)
 
 
+@pytest.mark.parametrize("which,name", [(0, "exp"), (1, "exp10"), (2, "log")])
+def test_vector_transcendentals(which, name):
+    """hx_exp_n / hx_log_n (interleaved chains, hx_model.cuh) against the CUDA library routine
+    they restate: bit-identical on the model's argument ranges and, through the fallback, on
+    everything else (huge, tiny, negative, zero, infinite, NaN)."""
+    import ctypes as C
+    from hector_b200 import _capi
+    rng = np.random.default_rng(which)
+    n = 1 << 20
+    if which == 2:
+        x = np.concatenate([rng.uniform(250.0, 330.0, n // 4), rng.uniform(2.5, 3.3, n // 4),
+                            10.0 ** rng.uniform(-300, 300, n // 4), rng.uniform(0.2, 20.0, n // 4 - 8),
+                            [0.0, -1.0, np.inf, np.nan, 5e-324, 1e-310, 1.0, 2.2250738585072014e-308]])
+    else:
+        lim = 720.0 if which == 0 else 312.0
+        x = np.concatenate([rng.uniform(-60.0, 10.0, n // 2), rng.uniform(-lim, lim, n // 4),
+                            rng.normal(0.0, 1e-3, n // 4 - 8),
+                            [0.0, -0.0, np.inf, -np.inf, np.nan, 1e300, -1e300, 708.5]])
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    fast = np.empty_like(x)
+    lib = np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    rc = _capi.lib().hx_diag_transcendentals(0, which, x.ctypes.data_as(dp), fast.ctypes.data_as(dp),
+                                             lib.ctypes.data_as(dp), x.size)
+    assert rc == 0
+    same = fast.view(np.uint64) == lib.view(np.uint64)
+    both_nan = np.isnan(fast) & np.isnan(lib)
+    bad = ~(same | both_nan)
+    assert not bad.any(), (name, x[bad][:5], fast[bad][:5], lib[bad][:5])
+    ref = {0: np.exp, 1: lambda v: np.power(10.0, v), 2: np.log}[which]
+    with np.errstate(all="ignore"):
+        r = ref(x)
+    ok = np.isfinite(r) & (np.abs(r) > 1e-300)  # not the subnormal results
+    assert np.max(np.abs(lib[ok] - r[ok]) / np.abs(r[ok])) < 1e-15
+
+
 def test_default_member_all_outputs_vs_oracle_and_golden():
     from oracle import port
     import hector_b200 as hb
