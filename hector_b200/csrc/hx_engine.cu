@@ -1401,6 +1401,8 @@ int hx_prepare(hx_handle h) {
     const double ocean_area = 3.6e14;
     C.vol_LL = ocean_area * part_low * thick_LL;
     C.vol_HL = ocean_area * part_high * thick_HL;
+    C.inv_vol_LL = 1.0 / C.vol_LL;
+    C.inv_vol_HL = 1.0 / C.vol_HL;
     C.vol_IO = ocean_area * thick_inter;
     C.vol_DO = ocean_area * thick_deep;
     C.As_HL = ocean_area * part_high;

@@ -818,7 +818,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           const ChemG g = chem_constants2(C, sst, ck.base + ck.tid, ck.stride);
           mb.gHL = g.gHL; mb.gLL = g.gLL;
           const Csys2Out o = csys_solve2(ck.base + ck.tid, ck.stride, C.bor, mb.bHL, mb.bLL,
-                                         STATE(SI_ALK_HL), STATE(SI_ALK_LL), C.vol_HL, C.vol_LL,
+                                         STATE(SI_ALK_HL), STATE(SI_ALK_LL), C.inv_vol_HL, C.inv_vol_LL,
                                          STATE(SI_H_HL), STATE(SI_H_LL), cold);
           mb.pco2HL = o.pco2[0]; mb.pco2LL = o.pco2[1];
           STATE(SI_H_HL) = o.h[0]; STATE(SI_H_LL) = o.h[1];
@@ -1400,10 +1400,15 @@ __global__ void hx_transc_check_kernel(const double *x, double *fast, double *li
   for (int k = 0; k < 4; ++k) a[k] = x[min(i0 + k, n - 1)];
   if (which == 0) hx_exp_n<4, false>(a, y);
   else if (which == 1) hx_exp_n<4, true>(a, y);
-  else hx_log_n<4>(a, y);
+  else if (which == 2) hx_log_n<4>(a, y);
+  else { /* hx_div: x holds (numerator, denominator) pairs, outputs in the numerator's slot */
+    y[0] = hx_div(a[0], a[1]); y[1] = 0.0;
+    y[2] = hx_div(a[2], a[3]); y[3] = 0.0;
+  }
   for (int k = 0; k < 4 && i0 + k < n; ++k) {
     fast[i0 + k] = y[k];
-    lib[i0 + k] = which == 0 ? exp(a[k]) : which == 1 ? exp10(a[k]) : log(a[k]);
+    lib[i0 + k] = which == 0 ? exp(a[k]) : which == 1 ? exp10(a[k]) : which == 2 ? log(a[k])
+                : (k & 1) ? 0.0 : a[k] / a[min(k + 1, 3)];
   }
 }
 
@@ -1411,7 +1416,7 @@ __global__ void hx_transc_check_kernel(const double *x, double *fast, double *li
 
 extern "C" int hx_diag_transcendentals(int32_t device, int32_t which, const double *x, double *fast,
                                        double *lib, int32_t n) {
-  if (!x || !fast || !lib || n <= 0 || which < 0 || which > 2) return HX_ERR_ARG;
+  if (!x || !fast || !lib || n <= 0 || which < 0 || which > 3) return HX_ERR_ARG;
   int prev = 0;
   if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) return HX_ERR_CUDA;
   double *dx = nullptr, *df = nullptr, *dl = nullptr;

@@ -217,6 +217,7 @@ struct HxConst {
   double S, sqrtS, S15, bor;
   /* geometry (ocean_component.cpp:207-303) */
   double vol_HL, vol_LL, vol_IO, vol_DO, As_HL, As_LL, U;
+  double inv_vol_HL, inv_vol_LL; /* 1 / volume of the surface boxes (convertToDIC) */
   double spy_ocean;
   /* DOECLIM (temperature_component.hpp:77-98) */
   double powtoheat;

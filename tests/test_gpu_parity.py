@@ -68,6 +68,39 @@ def test_vector_transcendentals(which, name):
     assert np.max(np.abs(lib[ok] - r[ok]) / np.abs(r[ok])) < 1e-15
 
 
+def test_early_test_division():
+    """hx_div (operand test first, then the compiler's own fast-path sequence) against the `/`
+    operator: bit-identical for ordinary operands and, through the fallback, for the rest."""
+    import ctypes as C
+    from hector_b200 import _capi
+    rng = np.random.default_rng(3)
+    n = 1 << 21
+    num = np.concatenate([rng.normal(0, 1, n // 8) * 10.0 ** rng.uniform(-12, 12, n // 8),
+                          rng.normal(0, 1, n // 8) * 10.0 ** rng.uniform(-300, 300, n // 8),
+                          rng.uniform(1e-9, 1e-7, n // 4 - 8),
+                          [0.0, -0.0, np.inf, np.nan, 1.0, 5e-324, 1e308, -1.0]])
+    den = np.concatenate([rng.normal(0, 1, n // 8) * 10.0 ** rng.uniform(-12, 12, n // 8),
+                          rng.normal(0, 1, n // 8) * 10.0 ** rng.uniform(-300, 300, n // 8),
+                          rng.uniform(1e-9, 1e-7, n // 4 - 8),
+                          [3.0, 2.0, 2.0, 1.0, 0.0, 3.0, 1e-308, np.inf]])
+    x = np.empty(2 * num.size)
+    x[0::2] = num
+    x[1::2] = den
+    fast = np.empty_like(x)
+    lib = np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    rc = _capi.lib().hx_diag_transcendentals(0, 3, x.ctypes.data_as(dp), fast.ctypes.data_as(dp),
+                                             lib.ctypes.data_as(dp), x.size)
+    assert rc == 0
+    q, ql = fast[0::2], lib[0::2]
+    bad = ~((q.view(np.uint64) == ql.view(np.uint64)) | (np.isnan(q) & np.isnan(ql)))
+    assert not bad.any(), (num[bad][:5], den[bad][:5], q[bad][:5], ql[bad][:5])
+    with np.errstate(all="ignore"):
+        r = num / den
+    same = (r.view(np.uint64) == ql.view(np.uint64)) | (np.isnan(r) & np.isnan(ql))
+    assert same.all()  # IEEE division either way
+
+
 def test_default_member_all_outputs_vs_oracle_and_golden():
     from oracle import port
     import hector_b200 as hb
