@@ -473,7 +473,7 @@ struct Engine {
 
   int upload_param(int pi) {
     if (pvec_on_device_only[pi]) return HX_OK; /* already resident (hx_set_param_device) */
-    k_fill_field<<<(Mpad + 255) / 256, 256, 0, stream>>>(d_P, pi, PI_COUNT, pscalar[pi], Mpad);
+    k_fill_field<<<(Mpad + 255) / 256, 256, 0, stream>>>(d_P, pi, PD_COUNT, pscalar[pi], Mpad);
     CUDA_TRY(cudaGetLastError());
     if (!pvec[pi].empty()) {
       int rc = ensure_pinned((size_t)M * sizeof(double));
@@ -485,7 +485,7 @@ struct Engine {
       memcpy(h_pinned, pvec[pi].data(), (size_t)M * sizeof(double));
       CUDA_TRY(cudaMemcpyAsync(d_stage, h_pinned, (size_t)M * sizeof(double),
                                cudaMemcpyHostToDevice, stream));
-      k_scatter_field<<<(M + 255) / 256, 256, 0, stream>>>(d_P, pi, PI_COUNT, d_stage, d_dev_of_api, M);
+      k_scatter_field<<<(M + 255) / 256, 256, 0, stream>>>(d_P, pi, PD_COUNT, d_stage, d_dev_of_api, M);
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaStreamSynchronize(stream));
     }
@@ -1246,7 +1246,7 @@ int hx_set_param_device(hx_handle h, const char *name, const double *dev, int32_
   if (pi < 0 || pi == PI_N0) return h->fail(HX_ERR_ARG, std::string("bad per-member parameter: ") + name);
   if (n != h->M) return h->fail(HX_ERR_ARG, "hx_set_param_device: n != n_members");
   cudaSetDevice(h->cfg.device);
-  k_scatter_field<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_P, pi, PI_COUNT, dev, h->d_dev_of_api, n);
+  k_scatter_field<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_P, pi, PD_COUNT, dev, h->d_dev_of_api, n);
   {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, cudaGetErrorString(e));
@@ -1282,7 +1282,7 @@ int hx_get_param(hx_handle h, const char *name, double *out, int32_t n) {
   if (h->pvec_on_device_only[pi]) {
     cudaSetDevice(h->cfg.device);
     if (h->ensure_stage((size_t)n * sizeof(double))) return HX_ERR_CUDA;
-    k_gather_field<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_stage, h->d_P, pi, PI_COUNT,
+    k_gather_field<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_stage, h->d_P, pi, PD_COUNT,
                                                           h->d_dev_of_api, n);
     cudaError_t e = cudaMemcpyAsync(out, h->d_stage, (size_t)n * sizeof(double),
                                     cudaMemcpyDeviceToHost, h->stream);
@@ -1484,12 +1484,13 @@ int hx_prepare(hx_handle h) {
   const size_t Mp = Mpad;
   const int nsel = (int)h->out_sel.size();
 
-  /* parameters and derived constants share one allocation (tried: a persisting-L2 window over it
-   * against the slabs' history streams -- 31.59 vs 31.65 ms, not kept) */
-  if (cudaMalloc(&h->d_P, (size_t)(PI_COUNT + DI_COUNT) * Mp * sizeof(double)) != cudaSuccess ||
+  /* parameters and derived constants are one tiled array, [tile][PI_COUNT | DI_COUNT][128]: one
+   * base pointer per thread serves both (tried: a persisting-L2 window over it against the slabs'
+   * history streams -- 31.59 vs 31.65 ms, not kept) */
+  if (cudaMalloc(&h->d_P, (size_t)PD_COUNT * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_S, SI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_S_snap, SI_COUNT * Mp * sizeof(double)) != cudaSuccess ||
-      (h->d_D = h->d_P + (size_t)PI_COUNT * Mp) == nullptr ||
+      (h->d_D = h->d_P + (size_t)PI_COUNT * HX_TILE) == nullptr || /* tile 0's derived constants */
       cudaMalloc(&h->d_ker, (size_t)HX_KER_ROWS(nrow) * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_conv, (size_t)HX_SLAB_YEARS * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_sst, (size_t)nrow * Mp * sizeof(double)) != cudaSuccess ||
@@ -1542,7 +1543,7 @@ int hx_prepare(hx_handle h) {
     also(cudaMemsetAsync(h->d_fail_year, 0, Mp * sizeof(int32_t), st));
     also(cudaMemsetAsync(h->d_spinup_steps, 0, Mp * sizeof(int32_t), st));
     also(cudaMemsetAsync(h->d_S, 0, SI_COUNT * Mp * sizeof(double), st));
-    also(cudaMemsetAsync(h->d_D, 0, DI_COUNT * Mp * sizeof(double), st));
+    also(cudaMemsetAsync(h->d_P, 0, (size_t)PD_COUNT * Mp * sizeof(double), st)); /* parameters follow below */
     also(cudaMemsetAsync(h->d_ker, 0, (size_t)HX_KER_ROWS(nrow) * Mp * sizeof(double), st));
     also(cudaMemsetAsync(h->d_conv, 0, (size_t)HX_SLAB_YEARS * Mp * sizeof(double), st));
     also(cudaMemsetAsync(h->d_sst, 0, (size_t)nrow * Mp * sizeof(double), st));

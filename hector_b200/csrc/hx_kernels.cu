@@ -110,9 +110,9 @@ struct Bases {
 __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, int m) {
   const size_t tile = (size_t)(m / HX_BLOCK), ln = (size_t)(m % HX_BLOCK);
   Bases b;
-  b.P = d.P + tile * PI_COUNT * HX_BLOCK + ln;
+  b.P = d.P + tile * PD_COUNT * HX_BLOCK + ln;
   b.S = d.S + tile * SI_COUNT * HX_BLOCK + ln;
-  b.D = d.D + tile * DI_COUNT * HX_BLOCK + ln;
+  b.D = const_cast<double *>(b.P) + PI_COUNT * HX_BLOCK; /* same tile block: a compile-time offset */
   b.ker = d.ker + tile * (size_t)HX_KER_ROWS(C.nrow) * HX_BLOCK + ln;
   b.conv = d.conv + tile * (size_t)HX_SLAB_YEARS * HX_BLOCK + ln;
   b.sst = d.sst_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
@@ -551,6 +551,19 @@ __device__ __forceinline__ void conv_prepass(const double *__restrict__ sst,
       sn[u] = 0.0; vn[u] = 0.0;
     }
     for (int i0 = 0; i0 < n_pre; i0 += U) {
+#if HX_CONV_L2_AHEAD
+      /* the rows of trip i0 + HX_CONV_L2_AHEAD U on their way from HBM to L2 now: the register
+       * prefetch below is one trip deep, enough for L2's latency but not for DRAM's */
+      if (i0 + HX_CONV_L2_AHEAD * U < n_pre) {
+        const double *fs = sst + (size_t)(i0 + HX_CONV_L2_AHEAD * U) * Hs;
+        const double *fk = pk - (size_t)(i0 + HX_CONV_L2_AHEAD * U) * Hs;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fs + (size_t)u * Hs));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fk + (size_t)u * Hs));
+        }
+      }
+#endif
       if (i0 + U < n_pre) {
         const double *ns = sst + (size_t)(i0 + U) * Hs;
         const double *nk = pk - (size_t)(i0 + U) * Hs;

@@ -14,6 +14,9 @@
 #ifndef HX_TRACK_CTAS
 #define HX_TRACK_CTAS 2 /* resident CTAs per SM of the record-only (tracking) run kernel */
 #endif
+#ifndef HX_CONV_L2_AHEAD
+#define HX_CONV_L2_AHEAD 3 /* trips ahead of the prepass whose history rows are prefetched into L2 (0 = off) */
+#endif
 #ifndef HX_YEAR_SYNC
 #define HX_YEAR_SYNC 1 /* one CTA barrier per simulated year: the warps share instruction fetches */
 #endif
@@ -26,9 +29,9 @@
 
 struct HxDev {
   int32_t Mpad;             /* padded member count, multiple of HX_BLOCK */
-  const double *P;          /* [PI_COUNT][Mpad] */
+  const double *P;          /* [tile][PI_COUNT | DI_COUNT][128]: parameters, then derived constants */
   double *S;                /* [SI_COUNT][Mpad] */
-  double *D;                /* [DI_COUNT][Mpad] */
+  double *D;                /* tile 0's derived constants inside P (kernels derive it from P) */
   double *ker;              /* [HX_KER_ROWS(nrow)][Mpad]  DOECLIM lag kernel K(j), zero padded */
   double *conv;             /* [HX_SLAB_YEARS][Mpad] per-slab partial convolution sums */
   double *sst_hist;         /* [nrow][Mpad] */

@@ -2,7 +2,7 @@
  *
  * Per-member data is structure-of-arrays, tiled by CTA ("CTA-tiled SoA"): the HX_TILE = 128
  * members of one CTA own a contiguous block
- *   params     P[tile][PI_COUNT][128]     state  S[tile][SI_COUNT][128]   derived D[tile][DI_COUNT][128]
+ *   params + derived constants  P[tile][PI_COUNT | DI_COUNT][128]     state  S[tile][SI_COUNT][128]
  *   histories  sst_hist / tland_hist [tile][nrow][128],  ker [tile][HX_KER_ROWS(nrow)][128]
  *   scratch    conv [tile][HX_SLAB_YEARS][128]   (per-slab partial convolution sums)
  * so (a) a warp touches 32 consecutive doubles (256 B) per access, (b) every field of a thread
@@ -121,6 +121,8 @@ enum {
   DI_LOG_M0, DI_SQRT_M0,                      /* log and sqrt of the preindustrial CH4 */
   DI_COUNT
 };
+/* parameters and derived constants live in ONE tiled array, [tile][PI_COUNT | DI_COUNT][128] */
+#define PD_COUNT (PI_COUNT + DI_COUNT)
 
 /* ---- recorded outputs ---- */
 enum {
