@@ -549,12 +549,16 @@ struct Engine {
    * the source maps before the next slab overwrites the record. */
   cudaStream_t track_stream = nullptr;
   cudaEvent_t ev_rec_full[2] = {nullptr, nullptr}, ev_rec_free[2] = {nullptr, nullptr};
-  size_t rec_elems = 0, ycnt_bytes = 0; /* size of one of the two record buffers */
+  size_t rec_elems = 0, ycnt_bytes = 0; /* size of ONE slab's record; a buffer holds rec_group of them */
+  int rec_group = 1;                    /* slabs per tracked launch of the run kernel */
 
   /* The record is double buffered and the replay runs on a stream of its own, so the run
-   * kernel of slab s+1 overlaps the replay of slab s (the replay's CTAs fill the SMs that the
-   * run kernel's last wave leaves idle, and vice versa).  Replays stay in order on their
-   * stream; a record buffer is rewritten only after its replay has finished. */
+   * kernel of one group of slabs overlaps the replay of the group before (the replay's CTAs
+   * fill the SMs that the run kernel's last wave leaves idle, and vice versa).  Replays stay in
+   * order on their stream; a record buffer is rewritten only after its replays have finished.
+   * A launch of the persistent run kernel covers rec_group slabs (as many as the device memory
+   * left for the record allows, up to 4): the claim scheduler keeps every SM busy across them,
+   * where one launch per slab ended in a partial wave each time. */
   cudaError_t launch_rows(int ra, int rb) {
     if (!d_T) return hx::launch_run(d, C, ra, rb, stream);
     if (!track_stream) {
@@ -568,18 +572,28 @@ struct Engine {
     const int slab = hx::track_slab_years();
     bool used[2] = {false, false};
     for (int i = 0; ra < rb; ++i) {
-      const int re = std::min(rb, ra + slab);
+      const int re = std::min(rb, ra + slab * rec_group);
       const int b = i & 1;
       HxDev db = d;
-      db.REC = d_REC + (size_t)b * rec_elems;
-      db.YCNT = d_YCNT + (size_t)b * ycnt_bytes;
+      db.REC = d_REC + (size_t)b * rec_group * rec_elems;
+      db.YCNT = d_YCNT + (size_t)b * rec_group * ycnt_bytes;
+      db.rec_slab_stride = rec_elems;
+      db.ycnt_slab_stride = ycnt_bytes;
       cudaError_t e = cudaSuccess;
       if (used[b]) e = cudaStreamWaitEvent(stream, ev_rec_free[b], 0);
       if (e == cudaSuccess) e = hx::launch_run(db, C, ra, re, stream);
       if (e == cudaSuccess && cfg.start_year + re >= C.tracking_date) {
         e = cudaEventRecord(ev_rec_full[b], stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(track_stream, ev_rec_full[b], 0);
-        if (e == cudaSuccess) e = hx::launch_track(db, C, ra, re, track_stream);
+        /* one replay per slab of the group, in order */
+        for (int g = 0, sa = ra; sa < re && e == cudaSuccess; ++g, sa += slab) {
+          const int se = std::min(re, sa + slab);
+          if (cfg.start_year + se < C.tracking_date) continue;
+          HxDev dg = db;
+          dg.REC = db.REC + (size_t)g * rec_elems;
+          dg.YCNT = db.YCNT + (size_t)g * ycnt_bytes;
+          e = hx::launch_track(dg, C, sa, se, track_stream);
+        }
         if (e == cudaSuccess) e = cudaEventRecord(ev_rec_free[b], track_stream);
         used[b] = true;
       }
@@ -1483,6 +1497,17 @@ int hx_prepare(hx_handle h) {
 
   const size_t Mp = Mpad;
   const int nsel = (int)h->out_sel.size();
+  if (tracking) {
+    /* slabs per tracked launch (launch_rows): up to 4, from the memory the device has free --
+     * two buffers of rec_group slab records, at most 45 % of it (HX_TRK_GROUP overrides) */
+    size_t free_b = 0, total_b = 0;
+    const size_t slab_b = block_scen.size() * hx::track_record_bytes_per_cta();
+    int g = 1;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && slab_b > 0)
+      g = (int)std::min<size_t>(4, std::max<size_t>(1, (size_t)(0.45 * (double)free_b) / (2 * slab_b)));
+    if (const char *ev = std::getenv("HX_TRK_GROUP")) g = std::max(1, std::min(64, std::atoi(ev)));
+    h->rec_group = g;
+  }
 
   /* parameters and derived constants are one tiled array, [tile][PI_COUNT | DI_COUNT][128]: one
    * base pointer per thread serves both (tried: a persisting-L2 window over it against the slabs'
@@ -1521,8 +1546,8 @@ int hx_prepare(hx_handle h) {
         cudaMalloc(&h->d_TK, (size_t)TS_COUNT * Mp * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&h->d_TO, h->track_years.size() * HX_NPOOL * HX_NSRC * Mp * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&h->d_TOK, h->track_years.size() * HX_NPOOL * Mp * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMalloc(&h->d_REC, 2 * block_scen.size() * hx::track_record_bytes_per_cta()) != cudaSuccess ||
-        cudaMalloc(&h->d_YCNT, 2 * block_scen.size() * hx::track_ycnt_bytes_per_tile()) != cudaSuccess ||
+        cudaMalloc(&h->d_REC, 2 * (size_t)h->rec_group * block_scen.size() * hx::track_record_bytes_per_cta()) != cudaSuccess ||
+        cudaMalloc(&h->d_YCNT, 2 * (size_t)h->rec_group * block_scen.size() * hx::track_ycnt_bytes_per_tile()) != cudaSuccess ||
         cudaMalloc(&h->d_trk_fail, Mp * sizeof(int32_t)) != cudaSuccess))) {
     cudaError_t e = cudaGetLastError();
     h->free_device();

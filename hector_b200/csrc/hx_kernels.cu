@@ -749,7 +749,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     if (TRACK) {
 #pragma unroll
       for (int j = 0; j < HX_SLAB_YEARS; ++j) ycnt[j] = 0;
-      mb.REC = d.REC + ((size_t)tile * HX_BLOCK + tid) * (HX_REC_STASH_MAX * HX_REC_N);
+      mb.REC = d.REC + (size_t)s * d.rec_slab_stride + ((size_t)tile * HX_BLOCK + tid) * (HX_REC_STASH_MAX * HX_REC_N);
       mb.rec_n = 0;
     }
     int r = base + 1;
@@ -1123,7 +1123,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     if (TRACK) {
       /* hand the slab's record to the replay kernel: years a stopped member never reached carry
        * the last count forward; a record that overflowed fails the member */
-      unsigned char *yc = d.YCNT + (size_t)tile * (HX_SLAB_YEARS * HX_BLOCK) + tid;
+      unsigned char *yc = d.YCNT + (size_t)s * d.ycnt_slab_stride + (size_t)tile * (HX_SLAB_YEARS * HX_BLOCK) + tid;
 #pragma unroll
       for (int j = 0; j < HX_SLAB_YEARS; ++j) {
         if (j > 0 && ycnt[j] < ycnt[j - 1]) ycnt[j] = ycnt[j - 1];

@@ -61,6 +61,9 @@ struct HxDev {
   double *REC;              /* [member][HX_REC_STASH_MAX][HX_REC_N] stash records of the slab
                                being run (hx_model.cuh, "Carbon tracking") */
   unsigned char *YCNT;      /* [tile][HX_SLAB_YEARS][128] stashes recorded up to each year's end */
+  /* a tracked launch may cover several slabs: slab s of the launch records into REC + s *
+   * rec_slab_stride (doubles) and YCNT + s * ycnt_slab_stride (bytes) */
+  size_t rec_slab_stride, ycnt_slab_stride;
   double *TO;               /* [track_nrec][HX_NPOOL * HX_NSRC][Mpad] recorded fractions */
   /* biomes (null with the single global biome) */
   const double *BP;         /* [tile][n_biomes * BP_COUNT][128] per-biome parameters */

@@ -1,6 +1,5 @@
 set -x
-for rep in 1 2; do
-for f in hector_b200/libhector_b200.so hector_b200/ab_pdonly.so hector_b200/ab_v16.so; do
-  echo "== small $f"; HECTOR_B200_LIB=$PWD/$f python tools/profile_run.py 1024 4 | grep "run ms" | tail -3 | tr '\n' ' '; echo
-done; done 2>&1 | tee -a gpurun_out/r02_ab_pd2.log
-bash tools/gpu_ab.sh 2>&1 | tee -a gpurun_out/r02_ab_pd2.log
+python -m pytest tests/test_gpu_tracking.py tests/test_gpu_parity_at_size.py -q -x 2>&1 | tail -4
+for g in 1 2 4 8; do
+  echo "== HX_TRK_GROUP=$g"; HX_TRK_GROUP=$g python tools/profile_tracked.py 65536 | tr '\n' ' '; echo
+done 2>&1 | tee gpurun_out/r02_ab_trk_group.log
