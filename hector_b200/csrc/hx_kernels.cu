@@ -1188,19 +1188,23 @@ __global__ void hx_track_init_kernel(const __grid_constant__ HxDev d) {
 }
 
 /* Replay of one slab's stash records into the members' source maps: one thread per (member,
- * source), 16 lanes per member (12 of them mixing) so that a member never straddles a warp.
- * The sixteen lanes stage the member's record through shared memory: while stash st is mixed,
+ * two sources), six lanes per member, five members per warp so that a member never straddles
+ * one.  The six lanes stage the member's record through shared memory: while stash st is mixed,
  * the (a, b) pairs of stash st+1 are already in flight as whole 128-byte lines. */
 #ifndef HX_TRK_NS
 #define HX_TRK_NS 2 /* sources per replay thread: 2-way ILP in every mix (150 vs 163 ms with 1) */
 #endif
-#define HX_TRK_LANES (16 / HX_TRK_NS)            /* lanes per member */
-#define HX_TRK_MEMBERS (128 / HX_TRK_LANES)      /* members per 128-thread CTA */
+/* lanes per member: the twelve sources at HX_TRK_NS per lane -- six lanes, five members per
+ * warp (two lanes of every warp idle; eight lanes per member with two of them mixing zeros kept
+ * members aligned to the warp but wasted a quarter of every instruction) */
+#define HX_TRK_LANES ((HX_NSRC + HX_TRK_NS - 1) / HX_TRK_NS)
+#define HX_TRK_PER_WARP (32 / HX_TRK_LANES)      /* members per warp */
+#define HX_TRK_MEMBERS (4 * HX_TRK_PER_WARP)     /* members per 128-thread CTA */
 struct StagedRecord {
   const double *rec;   /* the member's record, [stash][HX_REC_N] */
   double *sh;          /* this member's two staging buffers, [2][HX_REC_MIX * HX_REC_ROW] */
   int lane, nst;
-  unsigned mask;       /* the member's 16 lanes within the warp */
+  unsigned mask;       /* the member's lanes within the warp */
   double v[(HX_REC_N + HX_TRK_LANES - 1) / HX_TRK_LANES]; /* next stash in flight */
   int staged;          /* stash whose pairs are in v, -1: none */
   __device__ __forceinline__ void prefetch(int st) {
@@ -1240,10 +1244,12 @@ struct StagedRecord {
 __global__ void __launch_bounds__(128, HX_TRK_NS == 1 ? 5 : 3)
 hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   __shared__ double sh[HX_TRK_MEMBERS][2][HX_REC_MIX * HX_REC_ROW];
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m = gid / HX_TRK_LANES, s = gid % HX_TRK_LANES;
+  const int wl = threadIdx.x & 31, wm = wl / HX_TRK_LANES; /* lane and member within the warp */
+  if (wm >= HX_TRK_PER_WARP) return;                      /* the warp's spare lanes */
+  const int cm = (threadIdx.x >> 5) * HX_TRK_PER_WARP + wm; /* member within the CTA */
+  const int m = blockIdx.x * HX_TRK_MEMBERS + cm, s = wl % HX_TRK_LANES;
   if (m >= d.Mpad) return;
-  if (d.status[m] < 0) return; /* padding lane (all 16 lanes of the member leave together) */
+  if (d.status[m] < 0) return; /* padding member (all its lanes leave together) */
   const size_t tile = (size_t)(m / HX_BLOCK), ln = (size_t)(m % HX_BLOCK);
   double *T = d.T + tile * (size_t)(TS_COUNT * HX_NSRC) * HX_BLOCK + ln;
   uint32_t *TK = d.TK + tile * (size_t)TS_COUNT * HX_BLOCK + ln;
@@ -1251,14 +1257,11 @@ hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   const int nyears = r1 - r0;
   StagedRecord fetch;
   fetch.rec = d.REC + (size_t)m * (HX_REC_STASH_MAX * HX_REC_N);
-  fetch.sh = &sh[threadIdx.x / HX_TRK_LANES][0][0];
+  fetch.sh = &sh[cm][0][0];
   fetch.lane = s;
   fetch.nst = yc[(nyears - 1) * HX_BLOCK];
-  fetch.mask = ((HX_TRK_LANES == 16) ? 0xFFFFu : 0xFFu)
-               << ((threadIdx.x & 31) / HX_TRK_LANES * HX_TRK_LANES);
+  fetch.mask = ((1u << HX_TRK_LANES) - 1u) << (wm * HX_TRK_LANES);
   fetch.staged = -1;
-  /* the four idle lanes of a member help with the staging and mix a source that is written
-   * nowhere: source index 12 .. 15 is outside every map */
   const bool good = track_replay<HX_TRK_NS>(T, TK, fetch, yc, HX_BLOCK, nyears,
                                             C.start_year + r0 + 1, s * HX_TRK_NS,
                                             (s + 1) * HX_TRK_NS, C.tracking_date, C.track_every, C.track_nrec,
@@ -1385,8 +1388,7 @@ size_t track_record_bytes_per_cta() {
 size_t track_ycnt_bytes_per_tile() { return (size_t)HX_SLAB_YEARS * HX_BLOCK; }
 int track_slab_years() { return HX_SLAB_YEARS; }
 cudaError_t launch_track(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
-  const long long threads = (long long)d.Mpad * HX_TRK_LANES;
-  hx_track_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(d, C, r0, r1);
+  hx_track_kernel<<<(unsigned)((d.Mpad + HX_TRK_MEMBERS - 1) / HX_TRK_MEMBERS), 128, 0, st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_track_merge(const HxDev &d, cudaStream_t st) {
