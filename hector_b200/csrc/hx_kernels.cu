@@ -721,11 +721,24 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     const int mo = d.api_of_dev[m];
     Bases BS = make_bases(d, C, m);
     double *const gS = BS.S;
-    if (smem_state<MINCTAS>()) {
+    double *const gBF = BS.BF;
+    /* the block of shared memory behind the kernel's own arrays holds the tile's state S -- or,
+     * in the biome builds, the per-biome pools and factors BF (up to three biomes fit): the
+     * biome loops of every sub-step and stash read and write them far more often than S */
+    constexpr bool S_IN_SMEM = smem_state<MINCTAS>() && !BIOMES;
+    const bool bf_in_smem = smem_state<MINCTAS>() && BIOMES && C.n_biomes * BF_COUNT <= SI_COUNT;
+    if (S_IN_SMEM) {
       double *smS = reinterpret_cast<double *>(hx_smem + HX_SMEM_RUN_BYTES) + tid;
 #pragma unroll 8
       for (int i = 0; i < SI_COUNT; ++i) smS[i * HX_BLOCK] = gS[i * HX_BLOCK];
       BS.S = smS;
+    }
+    if (bf_in_smem) {
+      double *smB = reinterpret_cast<double *>(hx_smem + HX_SMEM_RUN_BYTES) + tid;
+      const int nf = C.n_biomes * BF_COUNT;
+#pragma unroll 4
+      for (int i = 0; i < nf; ++i) smB[i * HX_BLOCK] = gBF[i * HX_BLOCK];
+      BS.BF = smB;
     }
     /* history rows [0, n_pre) of the DOECLIM convolution, for all years of the slab at once */
     const int n_pre = ((base + 1) / HX_CONV_UNROLL) * HX_CONV_UNROLL;
@@ -1145,9 +1158,14 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
       const int stn = d.status[m];
       if (stn > 0) nan_fill_rows(d, C.nrow - 1, mo, max(d.fail_year[m] - C.start_year - 1, base), rend);
     }
-    if (smem_state<MINCTAS>()) { /* the state block goes back to global memory */
+    if (S_IN_SMEM) { /* the state block goes back to global memory */
 #pragma unroll 8
       for (int i = 0; i < SI_COUNT; ++i) gS[i * HX_BLOCK] = BS.S[i * HX_BLOCK];
+    }
+    if (bf_in_smem) {
+      const int nf = C.n_biomes * BF_COUNT;
+#pragma unroll 4
+      for (int i = 0; i < nf; ++i) gBF[i * HX_BLOCK] = BS.BF[i * HX_BLOCK];
     }
     /* publish the tile's state: make this CTA's global stores visible, then release */
     __threadfence();
@@ -1353,9 +1371,12 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
    * its map traffic, not by occupancy, and spills badly at 168 registers. */
   /* biome-split pools: general builds (constraints and every output; no tracking), with and
    * without the NBP machinery */
-  if (d.BF)
-    return d.constrained > 1 ? launch_run_t<false, true, 2, true, true, true>(d, C, r0, r1, st)
-                             : launch_run_t<false, true, 2, true, true, false>(d, C, r0, r1, st);
+  if (d.BF) {
+    if (d.constrained > 1) return launch_run_t<false, true, 2, true, true, true>(d, C, r0, r1, st);
+    if (d.constrained) return launch_run_t<false, true, 2, true, true, false>(d, C, r0, r1, st);
+    /* no constraint, no lo_warming_ratio: the biome loops without the constraint machinery */
+    return launch_run_t<false, false, 2, true, true, false>(d, C, r0, r1, st);
+  }
   if (d.T)
     return d.constrained ? launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st)
                          : launch_run_t<true, false, HX_TRACK_CTAS>(d, C, r0, r1, st);
