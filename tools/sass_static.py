@@ -40,3 +40,26 @@ for f, line in lines:
         st[f] += 1
 for k, v in st.most_common(top):
     print("%-28s %6d" % (k, v))
+
+# ---- instruction mix of the whole library and the lines that prove the bulk copy / mbarrier /
+# shuffle / compare-and-swap instructions of the chosen kernel (profiles/r02_sass_static_*.txt)
+sass = subprocess.run(["cuobjdump", "-sass", os.path.abspath(so)], capture_output=True, text=True).stdout
+mix = collections.Counter()
+proof = collections.Counter()
+inside = False
+for ln in sass.splitlines():
+    if "Function :" in ln:
+        inside = kname in ln
+        continue
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", ln)
+    if not m:
+        continue
+    mix[m.group(1)] += 1
+    if inside and re.search(r"UBLKCP|SYNCS|SHFL|ATOMG|ATOM\.|MEMBAR|BAR\.|CCTL\.E\.PF", ln):
+        proof[re.sub(r"/\*[0-9a-f]+\*/", "", ln).strip()] += 1
+print("\n==== instruction mix of the whole cubin (cuobjdump -sass %s | mnemonic counts)" % so)
+for k, v in mix.most_common(40):
+    print("%7d %s" % (v, k))
+print("\n==== lines proving TMA bulk copy / mbarrier / shuffles / CAS / L2 prefetch in %s" % kname)
+for k, v in proof.most_common(40):
+    print("%7d %s" % (v, k))
