@@ -752,7 +752,7 @@ struct Engine {
     if (spinup_shared() && M > 1) {
       /* E-7: nothing that shapes the spin-up or the alkalinity equilibration varies across
        * members, so one member's spin-up serves the ensemble: run it on one thread and
-       * broadcast the state rows it touches (SI_ATMOS .. SI_SOLVER_DT).  That single thread is
+       * broadcast the state rows it touches (the first SI_SPINUP_ROWS).  That single thread is
        * pure latency (2.2 ms), so the members' DOECLIM set-up (1.0 ms, reads and writes nothing
        * the spin-up touches) runs beside it on a second stream. */
       if (!setup_stream) {
@@ -767,7 +767,7 @@ struct Engine {
       CUDA_TRY(cudaEventRecord(ev_setup_b, setup_stream));
       CUDA_TRY(hx::launch_spinup_one(d, C, first_active, stream));
       k_broadcast_state<<<(Mpad + 255) / 256, 256, 0, stream>>>(
-          d_S, d_spinup_steps, d_status, d_fail_year, first_active, SI_SOLVER_DT + 1, (size_t)Mpad);
+          d_S, d_spinup_steps, d_status, d_fail_year, first_active, SI_SPINUP_ROWS, (size_t)Mpad);
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaStreamWaitEvent(stream, ev_setup_b, 0));
     } else {

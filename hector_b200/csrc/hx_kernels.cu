@@ -43,7 +43,7 @@ namespace hx {
 #ifndef HX_SMEM_STATE
 #define HX_SMEM_STATE 1
 #endif
-#define HX_SMEM_STATE_BYTES (SI_COUNT * HX_BLOCK * 8)
+#define HX_SMEM_STATE_BYTES ((HX_HOT_COUNT + SI_COUNT - SI_REG_COUNT) * HX_BLOCK * 8)
 template <int MINCTAS>
 __host__ __device__ constexpr bool smem_state() { return HX_SMEM_STATE && MINCTAS == 2; }
 template <int MINCTAS>
@@ -94,6 +94,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void year_barrier() {
   asm volatile("barrier.sync 1, %0;" ::"n"(HX_BLOCK) : "memory");
 }
+/* a read-only load the compiler leaves where it is written */
+__device__ __forceinline__ double ldg_pinned(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+/* the same for data this kernel writes itself (the histories): a coherent load */
+__device__ __forceinline__ double ld_pinned(const double *p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -101,6 +113,8 @@ __device__ __forceinline__ void fence_proxy_async() {
 /* CTA-tiled SoA accessors: one base pointer per array, compile-time field offsets */
 struct Bases {
   const double *P;
+  const double *H; /* the hot stretch of P | D: in the array itself or the run kernel's shared copy */
+  double *Sg;      /* the state in global memory (S may point into shared memory) */
   double *S, *D, *ker, *sst, *tland, *conv;
   const double *BP; /* per-biome parameters / state of this member (null: single biome) */
   double *BF;
@@ -113,6 +127,8 @@ __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, in
   b.P = d.P + tile * PD_COUNT * HX_BLOCK + ln;
   b.S = d.S + tile * SI_COUNT * HX_BLOCK + ln;
   b.D = const_cast<double *>(b.P) + PI_COUNT * HX_BLOCK; /* same tile block: a compile-time offset */
+  b.H = b.P + HX_HOT_FIRST * HX_BLOCK;
+  b.Sg = b.S;
   b.ker = d.ker + tile * (size_t)HX_KER_ROWS(C.nrow) * HX_BLOCK + ln;
   b.conv = d.conv + tile * (size_t)HX_SLAB_YEARS * HX_BLOCK + ln;
   b.sst = d.sst_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
@@ -129,19 +145,21 @@ __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, in
 
 __device__ __forceinline__ LandPar load_landpar(const Bases &BS) {
   LandPar p;
-  p.P = BS.P; p.D = BS.D;
+  p.P = BS.P; p.D = BS.D; p.H = BS.H;
   return p;
 }
 
 __device__ __forceinline__ void load_member(const Bases &BS, Member &mb) {
   mb.S = BS.S;
-  mb.atmos = STATE(SI_ATMOS); mb.veg = STATE(SI_VEG); mb.det = STATE(SI_DET);
-  mb.soil = STATE(SI_SOIL); mb.perm = STATE(SI_PERMAFROST); mb.thawed = STATE(SI_THAWED);
-  mb.earth = STATE(SI_EARTH);
-  mb.bHL = STATE(SI_BOX_HL); mb.bLL = STATE(SI_BOX_LL); mb.bIO = STATE(SI_BOX_IO);
-  mb.bDO = STATE(SI_BOX_DO);
-  mb.max_timestep = STATE(SI_MAX_TIMESTEP); mb.timeout = (int)STATE(SI_TIMEOUT);
-  mb.solver_dt = STATE(SI_SOLVER_DT);
+  /* the SI_REG_COUNT register-resident fields: straight from / to global memory */
+#define STATE_G(i) BS.Sg[(i) * HX_BLOCK]
+  mb.atmos = STATE_G(SI_ATMOS); mb.veg = STATE_G(SI_VEG); mb.det = STATE_G(SI_DET);
+  mb.soil = STATE_G(SI_SOIL); mb.perm = STATE_G(SI_PERMAFROST); mb.thawed = STATE_G(SI_THAWED);
+  mb.earth = STATE_G(SI_EARTH);
+  mb.bHL = STATE_G(SI_BOX_HL); mb.bLL = STATE_G(SI_BOX_LL); mb.bIO = STATE_G(SI_BOX_IO);
+  mb.bDO = STATE_G(SI_BOX_DO);
+  mb.max_timestep = STATE_G(SI_MAX_TIMESTEP); mb.timeout = (int)STATE_G(SI_TIMEOUT);
+  mb.solver_dt = STATE_G(SI_SOLVER_DT);
   mb.status = 0; mb.neg = false; mb.timesteps = 0;
   mb.pco2HL = mb.pco2LL = 0.0; mb.gHL = mb.gLL = 0.0; mb.luc_e = mb.luc_u = 0.0;
   mb.REC = nullptr; mb.rec_n = 0; mb.trk = false; mb.trk_bad = false;
@@ -149,13 +167,13 @@ __device__ __forceinline__ void load_member(const Bases &BS, Member &mb) {
 }
 
 __device__ __forceinline__ void store_member(const Bases &BS, const Member &mb) {
-  STATE(SI_ATMOS) = mb.atmos; STATE(SI_VEG) = mb.veg; STATE(SI_DET) = mb.det;
-  STATE(SI_SOIL) = mb.soil; STATE(SI_PERMAFROST) = mb.perm; STATE(SI_THAWED) = mb.thawed;
-  STATE(SI_EARTH) = mb.earth;
-  STATE(SI_BOX_HL) = mb.bHL; STATE(SI_BOX_LL) = mb.bLL; STATE(SI_BOX_IO) = mb.bIO;
-  STATE(SI_BOX_DO) = mb.bDO;
-  STATE(SI_MAX_TIMESTEP) = mb.max_timestep; STATE(SI_TIMEOUT) = (double)mb.timeout;
-  STATE(SI_SOLVER_DT) = mb.solver_dt;
+  STATE_G(SI_ATMOS) = mb.atmos; STATE_G(SI_VEG) = mb.veg; STATE_G(SI_DET) = mb.det;
+  STATE_G(SI_SOIL) = mb.soil; STATE_G(SI_PERMAFROST) = mb.perm; STATE_G(SI_THAWED) = mb.thawed;
+  STATE_G(SI_EARTH) = mb.earth;
+  STATE_G(SI_BOX_HL) = mb.bHL; STATE_G(SI_BOX_LL) = mb.bLL; STATE_G(SI_BOX_IO) = mb.bIO;
+  STATE_G(SI_BOX_DO) = mb.bDO;
+  STATE_G(SI_MAX_TIMESTEP) = mb.max_timestep; STATE_G(SI_TIMEOUT) = (double)mb.timeout;
+  STATE_G(SI_SOLVER_DT) = mb.solver_dt;
 }
 
 __device__ __forceinline__ void flush_work(const HxDev &d, const Work &w, unsigned years,
@@ -728,10 +746,18 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     constexpr bool S_IN_SMEM = smem_state<MINCTAS>() && !BIOMES;
     const bool bf_in_smem = smem_state<MINCTAS>() && BIOMES && C.n_biomes * BF_COUNT <= SI_COUNT;
     if (S_IN_SMEM) {
-      double *smS = reinterpret_cast<double *>(hx_smem + HX_SMEM_RUN_BYTES) + tid;
+      /* [the hot stretch of P | D][the state without its register-resident fields]: the block
+       * is as large as the whole state was, the fourteen fields that only load_member /
+       * store_member touch made room for the fourteen constants every sub-step and stash reads */
+      double *smH = reinterpret_cast<double *>(hx_smem + HX_SMEM_RUN_BYTES) + tid;
+      double *smS = smH + (HX_HOT_COUNT - SI_REG_COUNT) * HX_BLOCK; /* field i at smS[i * HX_BLOCK], i >= SI_REG_COUNT */
+      const double *gH = BS.H;
+#pragma unroll
+      for (int i = 0; i < HX_HOT_COUNT; ++i) smH[i * HX_BLOCK] = __ldg(gH + i * HX_BLOCK);
 #pragma unroll 8
-      for (int i = 0; i < SI_COUNT; ++i) smS[i * HX_BLOCK] = gS[i * HX_BLOCK];
+      for (int i = SI_REG_COUNT; i < SI_COUNT; ++i) smS[i * HX_BLOCK] = gS[i * HX_BLOCK];
       BS.S = smS;
+      BS.H = smH;
     }
     if (bf_in_smem) {
       double *smB = reinterpret_cast<double *>(hx_smem + HX_SMEM_RUN_BYTES) + tid;
@@ -769,6 +795,27 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     const bool entered = (mb.status == 0);
     if (entered) {
       for (; r <= rend; ++r) {
+#if HX_OH_AHEAD
+        /* the ten constants of the OH / CH4 block are the year's first reads from L2, and nothing
+         * else can run until they arrive: requested BEFORE the year barrier (volatile loads, so
+         * that they stay there), their latency passes while the warp waits for the others */
+        const double oh_m0 = ldg_pinned(BS.P + PI_M0 * HX_BLOCK), oh_cch4 = ldg_pinned(BS.P + PI_CCH4 * HX_BLOCK),
+                     oh_cnox = ldg_pinned(BS.P + PI_CNOX * HX_BLOCK), oh_cco = ldg_pinned(BS.P + PI_CCO * HX_BLOCK),
+                     oh_cnmvoc = ldg_pinned(BS.P + PI_CNMVOC * HX_BLOCK), oh_toh0 = ldg_pinned(BS.P + PI_TOH0 * HX_BLOCK),
+                     oh_logm0 = ldg_pinned(BS.D + DI_LOG_M0 * HX_BLOCK), oh_iuc = ldg_pinned(BS.D + DI_INV_UC_CH4 * HX_BLOCK),
+                     oh_itsoil = ldg_pinned(BS.D + DI_INV_TSOIL * HX_BLOCK), oh_itstrat = ldg_pinned(BS.D + DI_INV_TSTRAT * HX_BLOCK);
+#else
+#define oh_m0 PAR(PI_M0)
+#define oh_cch4 PAR(PI_CCH4)
+#define oh_cnox PAR(PI_CNOX)
+#define oh_cco PAR(PI_CCO)
+#define oh_cnmvoc PAR(PI_CNMVOC)
+#define oh_toh0 PAR(PI_TOH0)
+#define oh_logm0 DER(DI_LOG_M0)
+#define oh_iuc DER(DI_INV_UC_CH4)
+#define oh_itsoil DER(DI_INV_TSOIL)
+#define oh_itstrat DER(DI_INV_TSTRAT)
+#endif
 #if HX_YEAR_SYNC
         year_barrier();
 #endif
@@ -779,24 +826,24 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 
         /* --- OH, CH4: oh_component.cpp:137-174, ch4_component.cpp:152-199 --- */
         {
-          const double M0 = PAR(PI_M0);
+          const double M0 = oh_m0;
           const double previous_ch4 = STATE(SI_CH4);
           double toh = 0.0;
           if (previous_ch4 != M0) {
             /* log(previous_ch4) was taken last year for the ozone burden (below) and log(M0) by
              * the set-up kernel: same function, same argument, same bits */
             const double lprev = (r == 1) ? hx_log(previous_ch4) : STATE(SI_LOG_CH4);
-            const double a = PAR(PI_CCH4) * ((1.0 * lprev) - DER(DI_LOG_M0));
-            const double b = PAR(PI_CNOX) * ((1.0 * sc[SC_NOX]) - row0[SC_NOX]);
-            const double c = PAR(PI_CCO) * ((1.0 * sc[SC_CO]) - row0[SC_CO]);
-            const double dd = PAR(PI_CNMVOC) * ((1.0 * sc[SC_NMVOC]) - row0[SC_NMVOC]);
+            const double a = oh_cch4 * ((1.0 * lprev) - oh_logm0);
+            const double b = oh_cnox * ((1.0 * sc[SC_NOX]) - row0[SC_NOX]);
+            const double c = oh_cco * ((1.0 * sc[SC_CO]) - row0[SC_CO]);
+            const double dd = oh_cnmvoc * ((1.0 * sc[SC_NMVOC]) - row0[SC_NMVOC]);
             toh = a + b + c + dd;
           }
-          const double tau_oh = PAR(PI_TOH0) * hx_exp(-toh);
+          const double tau_oh = oh_toh0 * hx_exp(-toh);
           const double rh_ch4_tg = mb.S[SI_RH_CH4 * HX_TILE] * (1000.0 * 16.04 / 12.01);
-          const double emisTocon = (sc[SC_CH4_E] + rh_ch4_tg + sc[SC_CH4N]) * DER(DI_INV_UC_CH4);
-          const double soil_sink = previous_ch4 * DER(DI_INV_TSOIL);
-          const double strat_sink = previous_ch4 * DER(DI_INV_TSTRAT);
+          const double emisTocon = (sc[SC_CH4_E] + rh_ch4_tg + sc[SC_CH4N]) * oh_iuc;
+          const double soil_sink = previous_ch4 * oh_itsoil;
+          const double strat_sink = previous_ch4 * oh_itstrat;
           const double oh_sink = previous_ch4 / tau_oh;
           const double dCH4 = emisTocon - soil_sink - strat_sink - oh_sink;
           double ch4_new = previous_ch4 + dCH4;
@@ -834,6 +881,19 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           }
         }
 
+        /* what slowparameval will read, requested ahead of the chemistry (see SlowPar) */
+        SlowPar sp = {0.0, 1.0, 0.0, 0.0, 0.0};
+        double th_in = 0.0, th_out = 0.0; /* land-temperature rows entering / leaving the window */
+#if HX_SLOW_AHEAD
+        if (!BIOMES) {
+          sp.beta = ldg_pinned(BS.P + PI_BETA * HX_BLOCK); sp.wf = ldg_pinned(BS.P + PI_WARMINGFACTOR * HX_BLOCK);
+          sp.lnq10 = ldg_pinned(BS.D + DI_LNQ10 * HX_BLOCK); sp.pf_mu = ldg_pinned(BS.P + PI_PF_MU * HX_BLOCK);
+          sp.pf_sigma = ldg_pinned(BS.P + PI_PF_SIGMA * HX_BLOCK);
+        }
+        if (r - 2 >= 1) th_in = ld_pinned(BS.tland + (size_t)(r - 2) * Hs);
+        if (r - 202 >= 1) th_out = ld_pinned(BS.tland + (size_t)(r - 202) * Hs);
+#endif
+
         /* --- OceanComponent::run: ocean_component.cpp:356-407 --- */
         mb.S[SI_X_FLUXSUM * HX_TILE] = 0.0;
         mb.timesteps = 0;
@@ -855,7 +915,15 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         /* --- SimpleNbox::run + slowparameval: simpleNbox-runtime.cpp:206-227, 945-1072 --- */
         {
           const double tland = CONSTR ? STATE(SI_TLAND_C) : STATE(SI_TLAND); /* getData(land_tas) */
-          const double wf = BIOMES ? 1.0 : LP_WF(p); /* biomes weight the window mean themselves */
+#if !HX_SLOW_AHEAD
+          if (!BIOMES) {
+            sp.beta = LP_BETA(p); sp.wf = LP_WF(p); sp.lnq10 = LP_LNQ10(p); sp.pf_mu = LP_PF_MU(p);
+            sp.pf_sigma = LP_PF_SIGMA(p);
+          }
+          if (r - 2 >= 1) th_in = BS.tland[(size_t)(r - 2) * Hs];
+          if (r - 202 >= 1) th_out = BS.tland[(size_t)(r - 202) * Hs];
+#endif
+          const double wf = sp.wf; /* 1 with biomes: they weight the window mean themselves */
           BS.tland[(size_t)r * Hs] = tland; /* Tland_record[y] = land tas of year y-1 */
           if (TRACK) {
             /* tracking starts in year tracking_date (simpleNbox-runtime.cpp:215-220,
@@ -878,11 +946,10 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
            * leaves per year instead of re-reading 200 history rows. */
           double window = 0.0;
           if (r >= 2) {
-            const double *th = BS.tland;
             double wsum = STATE(SI_TLAND_WSUM), wcomp = STATE(SI_TLAND_WCOMP);
             double add = 0.0, sub = 0.0;
-            if (r - 2 >= 1) add = th[(size_t)(r - 2) * Hs] * wf;
-            if (r - 202 >= 1) sub = -(th[(size_t)(r - 202) * Hs] * wf);
+            if (r - 2 >= 1) add = th_in * wf;
+            if (r - 202 >= 1) sub = -(th_out * wf);
             double t1 = wsum + add;
             wcomp += (fabs(wsum) >= fabs(add)) ? ((wsum - t1) + add) : ((add - t1) + wsum);
             wsum = t1;
@@ -896,7 +963,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
            * year (below), where the forcing needs the same number */
           const double lco2 = (r == 1) ? hx_log((mb.atmos * HX_PGC_TO_PPMVCO2) / LP_C0(p)) : STATE(SI_LOG_CO2R);
           if (BIOMES) slow_params_biomes(mb, C, p, tland, r == 1, window, lco2);
-          else slow_params(mb, p, tland, r == 1, window, lco2);
+          else slow_params(mb, sp, tland, r == 1, window, lco2);
         }
 
         /* --- CarbonCycleSolver::run --- */
@@ -935,7 +1002,48 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         const double ch4 = STATE(SI_CH4);
         /* the year's two remaining logarithms as one interleaved pair; both are needed again at
          * the top of next year (OH lifetime, CO2 fertilisation) and travel in the state */
-        const HxPair lg = hx_log_x2(ch4, CO2_conc / LP_C0(p));
+#if HX_FORC_AHEAD
+        /* the forcing's and DOECLIM's member constants, requested ahead of the logarithm pair and
+         * the forcing sum that hide their latency */
+        const double fa_c0 = ldg_pinned(BS.P + PI_C0 * HX_BLOCK), fa_m0 = ldg_pinned(BS.P + PI_M0 * HX_BLOCK),
+                     fa_aero = ldg_pinned(BS.P + PI_AERO * HX_BLOCK), fa_vol = ldg_pinned(BS.P + PI_VOL * HX_BLOCK),
+                     fa_dco2 = ldg_pinned(BS.P + PI_DELTA_CO2 * HX_BLOCK), fa_dch4 = ldg_pinned(BS.P + PI_DELTA_CH4 * HX_BLOCK),
+                     fa_dn2o = ldg_pinned(BS.P + PI_DELTA_N2O * HX_BLOCK), fa_rbc = ldg_pinned(BS.P + PI_RHO_BC * HX_BLOCK),
+                     fa_roc = ldg_pinned(BS.P + PI_RHO_OC * HX_BLOCK), fa_rso2 = ldg_pinned(BS.P + PI_RHO_SO2 * HX_BLOCK),
+                     fa_rnh3 = ldg_pinned(BS.P + PI_RHO_NH3 * HX_BLOCK), fa_sqm0 = ldg_pinned(BS.D + DI_SQRT_M0 * HX_BLOCK);
+        const double dc_qc1 = ldg_pinned(BS.D + DI_QC1 * HX_BLOCK), dc_qc2 = ldg_pinned(BS.D + DI_QC2 * HX_BLOCK),
+                     dc_a0 = ldg_pinned(BS.D + DI_A0 * HX_BLOCK), dc_a1 = ldg_pinned(BS.D + DI_A1 * HX_BLOCK),
+                     dc_a2 = ldg_pinned(BS.D + DI_A2 * HX_BLOCK), dc_a3 = ldg_pinned(BS.D + DI_A3 * HX_BLOCK),
+                     dc_ib0 = ldg_pinned(BS.D + DI_IB0 * HX_BLOCK), dc_ib1 = ldg_pinned(BS.D + DI_IB1 * HX_BLOCK),
+                     dc_ib2 = ldg_pinned(BS.D + DI_IB2 * HX_BLOCK), dc_ib3 = ldg_pinned(BS.D + DI_IB3 * HX_BLOCK),
+                     dc_sqdt = ldg_pinned(BS.D + DI_SQDT_TAUDIF * HX_BLOCK), dc_hfint = ldg_pinned(BS.D + DI_HF_INT * HX_BLOCK);
+#else
+#define fa_c0 LP_C0(p)
+#define fa_m0 PAR(PI_M0)
+#define fa_aero PAR(PI_AERO)
+#define fa_vol PAR(PI_VOL)
+#define fa_dco2 PAR(PI_DELTA_CO2)
+#define fa_dch4 PAR(PI_DELTA_CH4)
+#define fa_dn2o PAR(PI_DELTA_N2O)
+#define fa_rbc PAR(PI_RHO_BC)
+#define fa_roc PAR(PI_RHO_OC)
+#define fa_rso2 PAR(PI_RHO_SO2)
+#define fa_rnh3 PAR(PI_RHO_NH3)
+#define fa_sqm0 DER(DI_SQRT_M0)
+#define dc_qc1 DER(DI_QC1)
+#define dc_qc2 DER(DI_QC2)
+#define dc_a0 DER(DI_A0)
+#define dc_a1 DER(DI_A1)
+#define dc_a2 DER(DI_A2)
+#define dc_a3 DER(DI_A3)
+#define dc_ib0 DER(DI_IB0)
+#define dc_ib1 DER(DI_IB1)
+#define dc_ib2 DER(DI_IB2)
+#define dc_ib3 DER(DI_IB3)
+#define dc_sqdt DER(DI_SQDT_TAUDIF)
+#define dc_hfint DER(DI_HF_INT)
+#endif
+        const HxPair lg = hx_log_x2(ch4, CO2_conc / fa_c0);
         STATE(SI_LOG_CH4) = lg.a;
         STATE(SI_LOG_CO2R) = lg.b;
         const double o3 = (5 * lg.a) + (0.125 * sc[SC_NOX]) + (0.0011 * sc[SC_CO]) +
@@ -946,10 +1054,10 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           /* preindustrial CH4 / N2O as the CH4 and N2O components hold them after prepareToRun:
            * a start-date constraint replaces the parameter (ch4_component.cpp:141-146,
            * n2o_component.cpp:141-146; row 0 of the N2O series is N0 by construction) */
-          fp.C0 = LP_C0(p); fp.M0 = PAR(PI_M0); fp.N0 = GAS ? PAR(PI_N0) : row0[SC_N2O]; fp.aero = PAR(PI_AERO);
+          fp.C0 = fa_c0; fp.M0 = fa_m0; fp.N0 = GAS ? PAR(PI_N0) : row0[SC_N2O]; fp.aero = fa_aero;
           /* square roots of member or scenario constants come from the set-up kernel / the
            * scenario table (sqrt is correctly rounded everywhere: the same doubles) */
-          fp.sqM0 = DER(DI_SQRT_M0);
+          fp.sqM0 = fa_sqm0;
           fp.sqN0 = GAS ? sqrt(fp.N0) : row0[SC_SQRT_N2O];
           fp.sqNa = GAS ? sqrt(n2o_conc) : sc[SC_SQRT_N2O];
           fp.ln_co2 = lg.b;
@@ -957,9 +1065,9 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
             const double c0 = row0[SC_C_CH4];
             if (c0 == c0) { fp.M0 = c0; fp.sqM0 = sqrt(c0); }
           }
-          fp.vol = PAR(PI_VOL); fp.delta_co2 = PAR(PI_DELTA_CO2); fp.delta_ch4 = PAR(PI_DELTA_CH4);
-          fp.delta_n2o = PAR(PI_DELTA_N2O); fp.rho_bc = PAR(PI_RHO_BC); fp.rho_oc = PAR(PI_RHO_OC);
-          fp.rho_so2 = PAR(PI_RHO_SO2); fp.rho_nh3 = PAR(PI_RHO_NH3);
+          fp.vol = fa_vol; fp.delta_co2 = fa_dco2; fp.delta_ch4 = fa_dch4;
+          fp.delta_n2o = fa_dn2o; fp.rho_bc = fa_rbc; fp.rho_oc = fa_roc;
+          fp.rho_so2 = fa_rso2; fp.rho_nh3 = fa_rnh3;
           double fco2, fch4, fn2o;
           double F = GAS ? forcing_total<HX_BLOCK>(fp, sc, n2o_conc, BS.GF + GF_RF0 * HX_BLOCK, CO2_conc, ch4,
                                                    o3, fco2, fch4, fn2o, mb.status)
@@ -989,8 +1097,8 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
                        fso = DC_FSO;
           const double tland = STATE(SI_TLAND), sst = STATE(SI_SST), rf_prev = STATE(SI_RF_PREV);
           const double dQ = rf_tot - rf_prev;
-          const double QC1 = dQ * DER(DI_QC1);
-          const double QC2 = dQ * DER(DI_QC2);
+          const double QC1 = dQ * dc_qc1;
+          const double QC2 = dQ * dc_qc2;
           double DQ1 = 0.5 * dt / cal * (rf_tot + rf_prev);
           double DQ2 = 0.5 * dt / cas * (rf_tot + rf_prev);
           DQ1 = DQ1 + QC1;
@@ -1015,14 +1123,14 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
             }
           }
           STATE(SI_DPAST_RAW) = DPAST2;
-          DPAST2 = DPAST2 * fso * DER(DI_SQDT_TAUDIF);
+          DPAST2 = DPAST2 * fso * dc_sqdt;
           const double DPAST1 = 0.0;
-          const double DTEAUX1 = DER(DI_A0) * tland + DER(DI_A1) * sst;
-          const double DTEAUX2 = DER(DI_A2) * tland + DER(DI_A3) * sst;
-          double TL = DER(DI_IB0) * (DQ1 + DPAST1 + DTEAUX1) +
-                      DER(DI_IB1) * (DQ2 + DPAST2 + DTEAUX2);
-          double TS = DER(DI_IB2) * (DQ1 + DPAST1 + DTEAUX1) +
-                      DER(DI_IB3) * (DQ2 + DPAST2 + DTEAUX2);
+          const double DTEAUX1 = dc_a0 * tland + dc_a1 * sst;
+          const double DTEAUX2 = dc_a2 * tland + dc_a3 * sst;
+          double TL = dc_ib0 * (DQ1 + DPAST1 + DTEAUX1) +
+                      dc_ib1 * (DQ2 + DPAST2 + DTEAUX2);
+          double TS = dc_ib2 * (DQ1 + DPAST1 + DTEAUX1) +
+                      dc_ib3 * (DQ2 + DPAST2 + DTEAUX2);
           tas = flnd * TL + (1.0 - flnd) * bsi * TS;
           if (CONSTR) {
             /* user-supplied global temperature (:510-525): overwrite, then back-calculate the
@@ -1035,7 +1143,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
             }
           }
           const double hf_mixed = cas * (TS - sst);
-          const double hf_int = DER(DI_HF_INT) * (2.0 * TS - hint);
+          const double hf_int = dc_hfint * (2.0 * TS - hint);
           STATE(SI_HEAT_MIXED) = STATE(SI_HEAT_MIXED) + hf_mixed * (C.powtoheat * dt);
           STATE(SI_HEAT_INTERIOR) = STATE(SI_HEAT_INTERIOR) + hf_int * (fso * C.powtoheat * dt);
           heatflux = hf_mixed + fso * hf_int;
@@ -1160,7 +1268,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     }
     if (S_IN_SMEM) { /* the state block goes back to global memory */
 #pragma unroll 8
-      for (int i = 0; i < SI_COUNT; ++i) gS[i * HX_BLOCK] = BS.S[i * HX_BLOCK];
+      for (int i = SI_REG_COUNT; i < SI_COUNT; ++i) gS[i * HX_BLOCK] = BS.S[i * HX_BLOCK];
     }
     if (bf_in_smem) {
       const int nf = C.n_biomes * BF_COUNT;
@@ -1259,7 +1367,7 @@ struct StagedRecord {
   }
 };
 
-__global__ void __launch_bounds__(128, HX_TRK_NS == 1 ? 5 : 3)
+__global__ void __launch_bounds__(128, HX_TRK_NS == 1 ? 5 : HX_TRK_NS == 2 ? 3 : 2)
 hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   __shared__ double sh[HX_TRK_MEMBERS][2][HX_REC_MIX * HX_REC_ROW];
   const int wl = threadIdx.x & 31, wm = wl / HX_TRK_LANES; /* lane and member within the warp */

@@ -61,29 +61,42 @@ enum {
   CN_COUNT = CN_HALO0 + HX_NHALO
 };
 
-/* ---- per-member parameters ---- */
+/* ---- per-member parameters ----
+ * The last HX_HOT_PI of them and the first HX_HOT_DI derived constants (below) are contiguous in
+ * the tiled array P | D: the run kernel keeps that stretch -- what every sub-step and stash of
+ * the year reads -- in shared memory (HX_HOT_*). */
 enum {
   PI_S = 0, PI_DIFF, PI_QCO2,
-  PI_BETA, PI_Q10, PI_F_NPPV, PI_F_NPPD, PI_F_LITTERD, PI_NPP_FLUX0, PI_C0,
+  PI_BETA, PI_Q10, PI_C0,
   PI_VEG_C0, PI_DET_C0, PI_SOIL_C0, PI_PERMAFROST_C0,
-  PI_WARMINGFACTOR, PI_RH_CH4_FRAC, PI_PF_MU, PI_PF_SIGMA, PI_FPF_STATIC,
+  PI_WARMINGFACTOR, PI_PF_MU, PI_PF_SIGMA,
   PI_TT, PI_TU, PI_TWI, PI_TID, PI_PREIND_SURF, PI_PREIND_ID,
-  PI_EPS_ABS, PI_EPS_REL, PI_DT, PI_EPS_SPINUP,
+  PI_EPS_REL, PI_DT, PI_EPS_SPINUP,
   PI_AERO, PI_VOL, PI_DELTA_CO2, PI_DELTA_CH4, PI_DELTA_N2O,
   PI_RHO_BC, PI_RHO_OC, PI_RHO_SO2, PI_RHO_NH3,
   PI_M0, PI_TSOIL, PI_TSTRAT, PI_UC_CH4, PI_TOH0, PI_CNOX, PI_CCO, PI_CNMVOC, PI_CCH4, PI_PO3,
   PI_N0,
   PI_LO_RATIO, /* [temperature] lo_warming_ratio, 0 = off */
+  /* the hot stretch */
+  PI_EPS_ABS, PI_NPP_FLUX0, PI_F_NPPV, PI_F_NPPD, PI_F_LITTERD, PI_FPF_STATIC, PI_RH_CH4_FRAC,
   PI_COUNT
 };
+#define HX_HOT_PI 7
+#define HX_HOT_DI 7                       /* DI_K_LL_HL .. DI_K_DO_IO */
+#define HX_HOT_FIRST (PI_COUNT - HX_HOT_PI) /* first field of the stretch in P | D */
+#define HX_HOT_COUNT (HX_HOT_PI + HX_HOT_DI)
 
-/* ---- per-member dynamic state ---- */
+/* ---- per-member dynamic state ----
+ * The first SI_REG_COUNT fields live in registers while a work item runs (they are read once
+ * when it starts and written once when it ends), so the run kernel's shared-memory copy of the
+ * state leaves them out; the first SI_SPINUP_ROWS fields are what the spin-up touches. */
 enum {
   SI_ATMOS = 0, SI_VEG, SI_DET, SI_SOIL, SI_PERMAFROST, SI_THAWED, SI_EARTH,
   SI_BOX_HL, SI_BOX_LL, SI_BOX_IO, SI_BOX_DO,
+  SI_MAX_TIMESTEP, SI_TIMEOUT, SI_SOLVER_DT,
   SI_ALK_HL, SI_ALK_LL, SI_H_HL, SI_H_LL,        /* alkalinity, last [H+] root (warm start) */
   SI_TEMPFERTS, SI_F_FROZEN, SI_CUM_LUC_VA, SI_EOS_VEGC, SI_MASSTOT, SI_CUM_PF_CH4, SI_RH_CH4,
-  SI_MAX_TIMESTEP, SI_TIMEOUT, SI_LASTFLUX_ANN, SI_SOLVER_DT,
+  SI_LASTFLUX_ANN,
   SI_CH4, SI_TLAND, SI_SST, SI_HEAT_MIXED, SI_HEAT_INTERIOR, SI_RF_PREV,
   SI_BASE_TOT, SI_BASE_CO2, SI_BASE_CH4, SI_BASE_N2O,
   SI_TLAND_WSUM, SI_TLAND_WCOMP, /* 200-year land-temperature window: compensated running sum */
@@ -107,6 +120,8 @@ enum {
   SI_LOG_CH4, SI_LOG_CO2R,
   SI_COUNT
 };
+#define SI_REG_COUNT 14   /* SI_ATMOS .. SI_SOLVER_DT */
+#define SI_SPINUP_ROWS 26 /* SI_ATMOS .. SI_LASTFLUX_ANN */
 
 /* ---- per-member derived constants (set-up kernel) ---- */
 enum {
@@ -123,6 +138,7 @@ enum {
 };
 /* parameters and derived constants live in ONE tiled array, [tile][PI_COUNT | DI_COUNT][128] */
 #define PD_COUNT (PI_COUNT + DI_COUNT)
+#define PD_OF(di) (PI_COUNT + (di)) /* a derived constant's field index in that array */
 
 /* ---- recorded outputs ---- */
 enum {

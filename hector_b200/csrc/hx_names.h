@@ -28,14 +28,12 @@ struct ParamInfo {
 /* PI_* order */
 static const ParamInfo kParams[PI_COUNT] = {
     {"S", 3.0}, {"diff", 1.042}, {"qco2", 3.75},
-    {"beta", 0.65}, {"q10_rh", 1.2}, {"f_nppv", 0.35}, {"f_nppd", 0.60}, {"f_litterd", 0.98},
-    {"npp_flux0", 56.2}, {"C0", 277.15},
+    {"beta", 0.65}, {"q10_rh", 1.2}, {"C0", 277.15},
     {"veg_c", 550}, {"detritus_c", 55}, {"soil_c", 917}, {"permafrost_c", 865},
-    {"warmingfactor", 1.0}, {"rh_ch4_frac", 0.023}, {"pf_mu", 1.67}, {"pf_sigma", 0.986},
-    {"fpf_static", 0.74},
+    {"warmingfactor", 1.0}, {"pf_mu", 1.67}, {"pf_sigma", 0.986},
     {"tt", 72000000}, {"tu", 49000000}, {"twi", 12500000}, {"tid", 200000000},
     {"preind_surface_c", 900}, {"preind_interdeep_c", 37100},
-    {"eps_abs", 1.0e-6}, {"eps_rel", 1.0e-6}, {"dt", 0.25}, {"eps_spinup", 0.001},
+    {"eps_rel", 1.0e-6}, {"dt", 0.25}, {"eps_spinup", 0.001},
     {"aero_scalar", 1.0}, {"vol_scalar", 1.0}, {"delta_co2", 0.05}, {"delta_ch4", -.14},
     {"delta_n2o", 0.07},
     {"rho_bc", 0.06386286}, {"rho_oc", -0.006407143}, {"rho_so2", -7.469841e-06},
@@ -44,7 +42,9 @@ static const ParamInfo kParams[PI_COUNT] = {
     {"TOH0", 9.6}, {"CNOX", 8.4e-3}, {"CCO", -1.575e-4}, {"CNMVOC", -4.725e-4}, {"CCH4", -0.32},
     {"PO3", 30.0},
     {"N0", 273.87},
-    {"lo_warming_ratio", 0.0}};
+    {"lo_warming_ratio", 0.0},
+    {"eps_abs", 1.0e-6}, {"npp_flux0", 56.2}, {"f_nppv", 0.35}, {"f_nppd", 0.60},
+    {"f_litterd", 0.98}, {"fpf_static", 0.74}, {"rh_ch4_frac", 0.023}};
 
 /* BP_* order: the per-biome inputs, named as the reference names them after the "<biome>."
  * prefix (simpleNbox.cpp:281-396); NaN = must be given (simpleNbox-runtime.cpp:66-101), a number

@@ -1,5 +1,7 @@
 set -x
-python -m pytest tests/test_gpu_biomes.py -q -x 2>&1 | tail -3
-for f in hector_b200/libhector_b200.so hector_b200/ab_head.so; do
-echo "== $f"; HECTOR_B200_LIB=$PWD/$f python tools/profile_biomes.py 65536
-done 2>&1 | tee gpurun_out/r02_ab_biome_smem.log
+bash tools/gpu_ab.sh 2>&1 | tee gpurun_out/r02_ab_hot.log
+for rep in 1 2; do
+for f in hector_b200/libhector_b200.so hector_b200/ab_ohonly.so; do
+  echo "== small $f"; HECTOR_B200_LIB=$PWD/$f python tools/profile_run.py 1024 4 | grep "run ms" | tail -3 | tr '\n' ' '; echo
+done; done 2>&1 | tee -a gpurun_out/r02_ab_hot.log
+python -m pytest tests -m gpu -q -x > gpurun_out/r02_gputests_p.log 2>&1; tail -4 gpurun_out/r02_gputests_p.log
