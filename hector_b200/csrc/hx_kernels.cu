@@ -744,11 +744,11 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
      * in the biome builds, the per-biome pools and factors BF (up to three biomes fit): the
      * biome loops of every sub-step and stash read and write them far more often than S */
     constexpr bool S_IN_SMEM = smem_state<MINCTAS>() && !BIOMES;
-    const bool bf_in_smem = smem_state<MINCTAS>() && BIOMES && C.n_biomes * BF_COUNT <= SI_COUNT;
+    const bool bf_in_smem = smem_state<MINCTAS>() && BIOMES && C.n_biomes * BF_COUNT <= HX_HOT_COUNT + SI_COUNT - SI_REG_COUNT;
     if (S_IN_SMEM) {
       /* [the hot stretch of P | D][the state without its register-resident fields]: the block
        * is as large as the whole state was, the fourteen fields that only load_member /
-       * store_member touch made room for the fourteen constants every sub-step and stash reads */
+       * store_member touch made room for the constants every sub-step and stash reads */
       double *smH = reinterpret_cast<double *>(hx_smem + HX_SMEM_RUN_BYTES) + tid;
       double *smS = smH + (HX_HOT_COUNT - SI_REG_COUNT) * HX_BLOCK; /* field i at smS[i * HX_BLOCK], i >= SI_REG_COUNT */
       const double *gH = BS.H;

@@ -71,17 +71,17 @@ enum {
   PI_VEG_C0, PI_DET_C0, PI_SOIL_C0, PI_PERMAFROST_C0,
   PI_WARMINGFACTOR, PI_PF_MU, PI_PF_SIGMA,
   PI_TT, PI_TU, PI_TWI, PI_TID, PI_PREIND_SURF, PI_PREIND_ID,
-  PI_EPS_REL, PI_DT, PI_EPS_SPINUP,
+  PI_DT, PI_EPS_SPINUP,
   PI_AERO, PI_VOL, PI_DELTA_CO2, PI_DELTA_CH4, PI_DELTA_N2O,
   PI_RHO_BC, PI_RHO_OC, PI_RHO_SO2, PI_RHO_NH3,
   PI_M0, PI_TSOIL, PI_TSTRAT, PI_UC_CH4, PI_TOH0, PI_CNOX, PI_CCO, PI_CNMVOC, PI_CCH4, PI_PO3,
   PI_N0,
   PI_LO_RATIO, /* [temperature] lo_warming_ratio, 0 = off */
   /* the hot stretch */
-  PI_EPS_ABS, PI_NPP_FLUX0, PI_F_NPPV, PI_F_NPPD, PI_F_LITTERD, PI_FPF_STATIC, PI_RH_CH4_FRAC,
+  PI_EPS_REL, PI_EPS_ABS, PI_NPP_FLUX0, PI_F_NPPV, PI_F_NPPD, PI_F_LITTERD, PI_FPF_STATIC, PI_RH_CH4_FRAC,
   PI_COUNT
 };
-#define HX_HOT_PI 7
+#define HX_HOT_PI 8
 #define HX_HOT_DI 7                       /* DI_K_LL_HL .. DI_K_DO_IO */
 #define HX_HOT_FIRST (PI_COUNT - HX_HOT_PI) /* first field of the stretch in P | D */
 #define HX_HOT_COUNT (HX_HOT_PI + HX_HOT_DI)

@@ -33,7 +33,7 @@ static const ParamInfo kParams[PI_COUNT] = {
     {"warmingfactor", 1.0}, {"pf_mu", 1.67}, {"pf_sigma", 0.986},
     {"tt", 72000000}, {"tu", 49000000}, {"twi", 12500000}, {"tid", 200000000},
     {"preind_surface_c", 900}, {"preind_interdeep_c", 37100},
-    {"eps_rel", 1.0e-6}, {"dt", 0.25}, {"eps_spinup", 0.001},
+    {"dt", 0.25}, {"eps_spinup", 0.001},
     {"aero_scalar", 1.0}, {"vol_scalar", 1.0}, {"delta_co2", 0.05}, {"delta_ch4", -.14},
     {"delta_n2o", 0.07},
     {"rho_bc", 0.06386286}, {"rho_oc", -0.006407143}, {"rho_so2", -7.469841e-06},
@@ -43,7 +43,7 @@ static const ParamInfo kParams[PI_COUNT] = {
     {"PO3", 30.0},
     {"N0", 273.87},
     {"lo_warming_ratio", 0.0},
-    {"eps_abs", 1.0e-6}, {"npp_flux0", 56.2}, {"f_nppv", 0.35}, {"f_nppd", 0.60},
+    {"eps_rel", 1.0e-6}, {"eps_abs", 1.0e-6}, {"npp_flux0", 56.2}, {"f_nppv", 0.35}, {"f_nppd", 0.60},
     {"f_litterd", 0.98}, {"fpf_static", 0.74}, {"rh_ch4_frac", 0.023}};
 
 /* BP_* order: the per-biome inputs, named as the reference names them after the "<biome>."
