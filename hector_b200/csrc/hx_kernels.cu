@@ -793,17 +793,25 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     }
     int r = base + 1;
     const bool entered = (mb.status == 0);
+#define HX_OH_LOADS(T)                                                                              \
+  T oh_m0 = ldg_pinned(BS.P + PI_M0 * HX_BLOCK), oh_cch4 = ldg_pinned(BS.P + PI_CCH4 * HX_BLOCK),          \
+    oh_cnox = ldg_pinned(BS.P + PI_CNOX * HX_BLOCK), oh_cco = ldg_pinned(BS.P + PI_CCO * HX_BLOCK),        \
+    oh_cnmvoc = ldg_pinned(BS.P + PI_CNMVOC * HX_BLOCK), oh_toh0 = ldg_pinned(BS.P + PI_TOH0 * HX_BLOCK),  \
+    oh_logm0 = ldg_pinned(BS.D + DI_LOG_M0 * HX_BLOCK), oh_iuc = ldg_pinned(BS.D + DI_INV_UC_CH4 * HX_BLOCK), \
+    oh_itsoil = ldg_pinned(BS.D + DI_INV_TSOIL * HX_BLOCK), oh_itstrat = ldg_pinned(BS.D + DI_INV_TSTRAT * HX_BLOCK);
+#if HX_OH_AHEAD == 2
+    HX_OH_LOADS(double)
+#endif
     if (entered) {
       for (; r <= rend; ++r) {
-#if HX_OH_AHEAD
+#if HX_OH_AHEAD == 1
         /* the ten constants of the OH / CH4 block are the year's first reads from L2, and nothing
          * else can run until they arrive: requested BEFORE the year barrier (volatile loads, so
          * that they stay there), their latency passes while the warp waits for the others */
-        const double oh_m0 = ldg_pinned(BS.P + PI_M0 * HX_BLOCK), oh_cch4 = ldg_pinned(BS.P + PI_CCH4 * HX_BLOCK),
-                     oh_cnox = ldg_pinned(BS.P + PI_CNOX * HX_BLOCK), oh_cco = ldg_pinned(BS.P + PI_CCO * HX_BLOCK),
-                     oh_cnmvoc = ldg_pinned(BS.P + PI_CNMVOC * HX_BLOCK), oh_toh0 = ldg_pinned(BS.P + PI_TOH0 * HX_BLOCK),
-                     oh_logm0 = ldg_pinned(BS.D + DI_LOG_M0 * HX_BLOCK), oh_iuc = ldg_pinned(BS.D + DI_INV_UC_CH4 * HX_BLOCK),
-                     oh_itsoil = ldg_pinned(BS.D + DI_INV_TSOIL * HX_BLOCK), oh_itstrat = ldg_pinned(BS.D + DI_INV_TSTRAT * HX_BLOCK);
+        HX_OH_LOADS(const double)
+#elif HX_OH_AHEAD == 2
+        /* requested a phase earlier still: before the loop for its first year, after the solver
+         * for the next one (below) */
 #else
 #define oh_m0 PAR(PI_M0)
 #define oh_cch4 PAR(PI_CCH4)
@@ -881,18 +889,8 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           }
         }
 
-        /* what slowparameval will read, requested ahead of the chemistry (see SlowPar) */
         SlowPar sp = {0.0, 1.0, 0.0, 0.0, 0.0};
         double th_in = 0.0, th_out = 0.0; /* land-temperature rows entering / leaving the window */
-#if HX_SLOW_AHEAD
-        if (!BIOMES) {
-          sp.beta = ldg_pinned(BS.P + PI_BETA * HX_BLOCK); sp.wf = ldg_pinned(BS.P + PI_WARMINGFACTOR * HX_BLOCK);
-          sp.lnq10 = ldg_pinned(BS.D + DI_LNQ10 * HX_BLOCK); sp.pf_mu = ldg_pinned(BS.P + PI_PF_MU * HX_BLOCK);
-          sp.pf_sigma = ldg_pinned(BS.P + PI_PF_SIGMA * HX_BLOCK);
-        }
-        if (r - 2 >= 1) th_in = ld_pinned(BS.tland + (size_t)(r - 2) * Hs);
-        if (r - 202 >= 1) th_out = ld_pinned(BS.tland + (size_t)(r - 202) * Hs);
-#endif
 
         /* --- OceanComponent::run: ocean_component.cpp:356-407 --- */
         mb.S[SI_X_FLUXSUM * HX_TILE] = 0.0;
@@ -915,14 +913,14 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         /* --- SimpleNbox::run + slowparameval: simpleNbox-runtime.cpp:206-227, 945-1072 --- */
         {
           const double tland = CONSTR ? STATE(SI_TLAND_C) : STATE(SI_TLAND); /* getData(land_tas) */
-#if !HX_SLOW_AHEAD
+          /* (requesting these seven values ahead of the chemistry was tried: +0.8 % -- they stay
+           * live across its two calls) */
           if (!BIOMES) {
             sp.beta = LP_BETA(p); sp.wf = LP_WF(p); sp.lnq10 = LP_LNQ10(p); sp.pf_mu = LP_PF_MU(p);
             sp.pf_sigma = LP_PF_SIGMA(p);
           }
           if (r - 2 >= 1) th_in = BS.tland[(size_t)(r - 2) * Hs];
           if (r - 202 >= 1) th_out = BS.tland[(size_t)(r - 202) * Hs];
-#endif
           const double wf = sp.wf; /* 1 with biomes: they weight the window mean themselves */
           BS.tland[(size_t)r * Hs] = tland; /* Tland_record[y] = land tas of year y-1 */
           if (TRACK) {
@@ -973,6 +971,52 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           d.fail_year[m] = y;
           break;
         }
+#if HX_FORC_AHEAD
+        /* the forcing's and DOECLIM's member constants, requested as soon as the solver is done:
+         * record_state, the logarithm pair and the forcing sum hide their latency */
+        const double fa_c0 = ldg_pinned(BS.P + PI_C0 * HX_BLOCK), fa_m0 = ldg_pinned(BS.P + PI_M0 * HX_BLOCK),
+                     fa_aero = ldg_pinned(BS.P + PI_AERO * HX_BLOCK), fa_vol = ldg_pinned(BS.P + PI_VOL * HX_BLOCK),
+                     fa_dco2 = ldg_pinned(BS.P + PI_DELTA_CO2 * HX_BLOCK), fa_dch4 = ldg_pinned(BS.P + PI_DELTA_CH4 * HX_BLOCK),
+                     fa_dn2o = ldg_pinned(BS.P + PI_DELTA_N2O * HX_BLOCK), fa_rbc = ldg_pinned(BS.P + PI_RHO_BC * HX_BLOCK),
+                     fa_roc = ldg_pinned(BS.P + PI_RHO_OC * HX_BLOCK), fa_rso2 = ldg_pinned(BS.P + PI_RHO_SO2 * HX_BLOCK),
+                     fa_rnh3 = ldg_pinned(BS.P + PI_RHO_NH3 * HX_BLOCK), fa_sqm0 = ldg_pinned(BS.D + DI_SQRT_M0 * HX_BLOCK);
+        const double dc_qc1 = ldg_pinned(BS.D + DI_QC1 * HX_BLOCK), dc_qc2 = ldg_pinned(BS.D + DI_QC2 * HX_BLOCK),
+                     dc_a0 = ldg_pinned(BS.D + DI_A0 * HX_BLOCK), dc_a1 = ldg_pinned(BS.D + DI_A1 * HX_BLOCK),
+                     dc_a2 = ldg_pinned(BS.D + DI_A2 * HX_BLOCK), dc_a3 = ldg_pinned(BS.D + DI_A3 * HX_BLOCK),
+                     dc_ib0 = ldg_pinned(BS.D + DI_IB0 * HX_BLOCK), dc_ib1 = ldg_pinned(BS.D + DI_IB1 * HX_BLOCK),
+                     dc_ib2 = ldg_pinned(BS.D + DI_IB2 * HX_BLOCK), dc_ib3 = ldg_pinned(BS.D + DI_IB3 * HX_BLOCK),
+                     dc_sqdt = ldg_pinned(BS.D + DI_SQDT_TAUDIF * HX_BLOCK), dc_hfint = ldg_pinned(BS.D + DI_HF_INT * HX_BLOCK),
+                     dc_k1 = ldg_pinned(BS.ker + Hs); /* K(1): written by the set-up kernel, read-only here */
+#else
+#define fa_c0 LP_C0(p)
+#define fa_m0 PAR(PI_M0)
+#define fa_aero PAR(PI_AERO)
+#define fa_vol PAR(PI_VOL)
+#define fa_dco2 PAR(PI_DELTA_CO2)
+#define fa_dch4 PAR(PI_DELTA_CH4)
+#define fa_dn2o PAR(PI_DELTA_N2O)
+#define fa_rbc PAR(PI_RHO_BC)
+#define fa_roc PAR(PI_RHO_OC)
+#define fa_rso2 PAR(PI_RHO_SO2)
+#define fa_rnh3 PAR(PI_RHO_NH3)
+#define fa_sqm0 DER(DI_SQRT_M0)
+#define dc_qc1 DER(DI_QC1)
+#define dc_qc2 DER(DI_QC2)
+#define dc_a0 DER(DI_A0)
+#define dc_a1 DER(DI_A1)
+#define dc_a2 DER(DI_A2)
+#define dc_a3 DER(DI_A3)
+#define dc_ib0 DER(DI_IB0)
+#define dc_ib1 DER(DI_IB1)
+#define dc_ib2 DER(DI_IB2)
+#define dc_ib3 DER(DI_IB3)
+#define dc_sqdt DER(DI_SQDT_TAUDIF)
+#define dc_hfint DER(DI_HF_INT)
+#define dc_k1 BS.ker[Hs]
+#endif
+#if HX_OH_AHEAD == 2
+        HX_OH_LOADS() /* next year's */
+#endif
         /* record_state: simpleNbox.cpp:789-840 */
         if (BIOMES) {
           for (int ib = 0; ib < C.n_biomes; ++ib) {
@@ -1002,47 +1046,6 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         const double ch4 = STATE(SI_CH4);
         /* the year's two remaining logarithms as one interleaved pair; both are needed again at
          * the top of next year (OH lifetime, CO2 fertilisation) and travel in the state */
-#if HX_FORC_AHEAD
-        /* the forcing's and DOECLIM's member constants, requested ahead of the logarithm pair and
-         * the forcing sum that hide their latency */
-        const double fa_c0 = ldg_pinned(BS.P + PI_C0 * HX_BLOCK), fa_m0 = ldg_pinned(BS.P + PI_M0 * HX_BLOCK),
-                     fa_aero = ldg_pinned(BS.P + PI_AERO * HX_BLOCK), fa_vol = ldg_pinned(BS.P + PI_VOL * HX_BLOCK),
-                     fa_dco2 = ldg_pinned(BS.P + PI_DELTA_CO2 * HX_BLOCK), fa_dch4 = ldg_pinned(BS.P + PI_DELTA_CH4 * HX_BLOCK),
-                     fa_dn2o = ldg_pinned(BS.P + PI_DELTA_N2O * HX_BLOCK), fa_rbc = ldg_pinned(BS.P + PI_RHO_BC * HX_BLOCK),
-                     fa_roc = ldg_pinned(BS.P + PI_RHO_OC * HX_BLOCK), fa_rso2 = ldg_pinned(BS.P + PI_RHO_SO2 * HX_BLOCK),
-                     fa_rnh3 = ldg_pinned(BS.P + PI_RHO_NH3 * HX_BLOCK), fa_sqm0 = ldg_pinned(BS.D + DI_SQRT_M0 * HX_BLOCK);
-        const double dc_qc1 = ldg_pinned(BS.D + DI_QC1 * HX_BLOCK), dc_qc2 = ldg_pinned(BS.D + DI_QC2 * HX_BLOCK),
-                     dc_a0 = ldg_pinned(BS.D + DI_A0 * HX_BLOCK), dc_a1 = ldg_pinned(BS.D + DI_A1 * HX_BLOCK),
-                     dc_a2 = ldg_pinned(BS.D + DI_A2 * HX_BLOCK), dc_a3 = ldg_pinned(BS.D + DI_A3 * HX_BLOCK),
-                     dc_ib0 = ldg_pinned(BS.D + DI_IB0 * HX_BLOCK), dc_ib1 = ldg_pinned(BS.D + DI_IB1 * HX_BLOCK),
-                     dc_ib2 = ldg_pinned(BS.D + DI_IB2 * HX_BLOCK), dc_ib3 = ldg_pinned(BS.D + DI_IB3 * HX_BLOCK),
-                     dc_sqdt = ldg_pinned(BS.D + DI_SQDT_TAUDIF * HX_BLOCK), dc_hfint = ldg_pinned(BS.D + DI_HF_INT * HX_BLOCK);
-#else
-#define fa_c0 LP_C0(p)
-#define fa_m0 PAR(PI_M0)
-#define fa_aero PAR(PI_AERO)
-#define fa_vol PAR(PI_VOL)
-#define fa_dco2 PAR(PI_DELTA_CO2)
-#define fa_dch4 PAR(PI_DELTA_CH4)
-#define fa_dn2o PAR(PI_DELTA_N2O)
-#define fa_rbc PAR(PI_RHO_BC)
-#define fa_roc PAR(PI_RHO_OC)
-#define fa_rso2 PAR(PI_RHO_SO2)
-#define fa_rnh3 PAR(PI_RHO_NH3)
-#define fa_sqm0 DER(DI_SQRT_M0)
-#define dc_qc1 DER(DI_QC1)
-#define dc_qc2 DER(DI_QC2)
-#define dc_a0 DER(DI_A0)
-#define dc_a1 DER(DI_A1)
-#define dc_a2 DER(DI_A2)
-#define dc_a3 DER(DI_A3)
-#define dc_ib0 DER(DI_IB0)
-#define dc_ib1 DER(DI_IB1)
-#define dc_ib2 DER(DI_IB2)
-#define dc_ib3 DER(DI_IB3)
-#define dc_sqdt DER(DI_SQDT_TAUDIF)
-#define dc_hfint DER(DI_HF_INT)
-#endif
         const HxPair lg = hx_log_x2(ch4, CO2_conc / fa_c0);
         STATE(SI_LOG_CH4) = lg.a;
         STATE(SI_LOG_CO2R) = lg.b;
@@ -1110,7 +1113,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
            * one term sst[t-1] K(1): it is last year's unscaled sum plus one FMA.  DPAST2 takes
            * the rows i < n_pre from the slab prepass and adds its last rows here, oldest first
            * like the reference. */
-          const double hint = HX_CONV_FMA(sst, BS.ker[Hs], STATE(SI_DPAST_RAW));
+          const double hint = HX_CONV_FMA(sst, dc_k1, STATE(SI_DPAST_RAW));
           double DPAST2 = BS.conv[(size_t)(r - base - 1) * Hs];
           {
             const double *ps = BS.sst + (size_t)n_pre * Hs;          /* sst[i], i ascending */

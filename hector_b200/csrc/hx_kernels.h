@@ -18,13 +18,10 @@
 #define HX_CONV_L2_AHEAD 3 /* trips ahead of the prepass whose history rows are prefetched into L2 (0 = off) */
 #endif
 #ifndef HX_FORC_AHEAD
-#define HX_FORC_AHEAD 1 /* the forcing's and DOECLIM's constants are requested before the logarithm pair */
-#endif
-#ifndef HX_SLOW_AHEAD
-#define HX_SLOW_AHEAD 0 /* slowparameval's constants and window rows are requested before the chemistry */
+#define HX_FORC_AHEAD 1 /* the forcing's and DOECLIM's constants are requested as soon as the solver is done */
 #endif
 #ifndef HX_OH_AHEAD
-#define HX_OH_AHEAD 1 /* the OH / CH4 constants are requested before the year barrier */
+#define HX_OH_AHEAD 2 /* the OH / CH4 constants are requested ahead: 1 = before the year barrier, 2 = after the solver of the year before */
 #endif
 #ifndef HX_YEAR_SYNC
 #define HX_YEAR_SYNC 1 /* one CTA barrier per simulated year: the warps share instruction fetches */

@@ -67,9 +67,8 @@ enum {
  * the year reads -- in shared memory (HX_HOT_*). */
 enum {
   PI_S = 0, PI_DIFF, PI_QCO2,
-  PI_BETA, PI_Q10, PI_C0,
+  PI_Q10, PI_C0,
   PI_VEG_C0, PI_DET_C0, PI_SOIL_C0, PI_PERMAFROST_C0,
-  PI_WARMINGFACTOR, PI_PF_MU, PI_PF_SIGMA,
   PI_TT, PI_TU, PI_TWI, PI_TID, PI_PREIND_SURF, PI_PREIND_ID,
   PI_DT, PI_EPS_SPINUP,
   PI_AERO, PI_VOL, PI_DELTA_CO2, PI_DELTA_CH4, PI_DELTA_N2O,
@@ -78,11 +77,12 @@ enum {
   PI_N0,
   PI_LO_RATIO, /* [temperature] lo_warming_ratio, 0 = off */
   /* the hot stretch */
+  PI_BETA, PI_WARMINGFACTOR, PI_PF_MU, PI_PF_SIGMA, /* slowparameval, once a year */
   PI_EPS_REL, PI_EPS_ABS, PI_NPP_FLUX0, PI_F_NPPV, PI_F_NPPD, PI_F_LITTERD, PI_FPF_STATIC, PI_RH_CH4_FRAC,
   PI_COUNT
 };
-#define HX_HOT_PI 8
-#define HX_HOT_DI 7                       /* DI_K_LL_HL .. DI_K_DO_IO */
+#define HX_HOT_PI 12
+#define HX_HOT_DI 8                       /* DI_K_LL_HL .. DI_K_DO_IO, DI_LNQ10 */
 #define HX_HOT_FIRST (PI_COUNT - HX_HOT_PI) /* first field of the stretch in P | D */
 #define HX_HOT_COUNT (HX_HOT_PI + HX_HOT_DI)
 
@@ -126,11 +126,11 @@ enum {
 /* ---- per-member derived constants (set-up kernel) ---- */
 enum {
   DI_K_LL_HL = 0, DI_K_LL_IO, DI_K_HL_DO, DI_K_IO_LL, DI_K_IO_HL, DI_K_IO_DO, DI_K_DO_IO,
+  DI_LNQ10,       /* log(q10_rh): pow(q10, x) is evaluated as exp(x * lnq10) */
   DI_A0, DI_A1, DI_A2, DI_A3, DI_IB0, DI_IB1, DI_IB2, DI_IB3,
   DI_TAUCFL, DI_TAUKLS, DI_TAUCFS, DI_TAUKSL,
   DI_SQDT_TAUDIF, /* pow(dt/taudif, 0.5)            temperature_component.cpp:491 */
   DI_HF_INT,      /* cas*fso/pow(taudif*dt, 0.5)    temperature_component.cpp:539 */
-  DI_LNQ10,       /* log(q10_rh): pow(q10, x) is evaluated as exp(x * lnq10) */
   DI_QC1, DI_QC2, /* forcing-increment correction per unit dQ (temperature_component.cpp:471-475) */
   DI_INV_UC_CH4, DI_INV_TSOIL, DI_INV_TSTRAT, /* reciprocals of the CH4 constants */
   DI_LOG_M0, DI_SQRT_M0,                      /* log and sqrt of the preindustrial CH4 */

@@ -28,9 +28,8 @@ struct ParamInfo {
 /* PI_* order */
 static const ParamInfo kParams[PI_COUNT] = {
     {"S", 3.0}, {"diff", 1.042}, {"qco2", 3.75},
-    {"beta", 0.65}, {"q10_rh", 1.2}, {"C0", 277.15},
+    {"q10_rh", 1.2}, {"C0", 277.15},
     {"veg_c", 550}, {"detritus_c", 55}, {"soil_c", 917}, {"permafrost_c", 865},
-    {"warmingfactor", 1.0}, {"pf_mu", 1.67}, {"pf_sigma", 0.986},
     {"tt", 72000000}, {"tu", 49000000}, {"twi", 12500000}, {"tid", 200000000},
     {"preind_surface_c", 900}, {"preind_interdeep_c", 37100},
     {"dt", 0.25}, {"eps_spinup", 0.001},
@@ -43,6 +42,7 @@ static const ParamInfo kParams[PI_COUNT] = {
     {"PO3", 30.0},
     {"N0", 273.87},
     {"lo_warming_ratio", 0.0},
+    {"beta", 0.65}, {"warmingfactor", 1.0}, {"pf_mu", 1.67}, {"pf_sigma", 0.986},
     {"eps_rel", 1.0e-6}, {"eps_abs", 1.0e-6}, {"npp_flux0", 56.2}, {"f_nppv", 0.35}, {"f_nppd", 0.60},
     {"f_litterd", 0.98}, {"fpf_static", 0.74}, {"rh_ch4_frac", 0.023}};
 

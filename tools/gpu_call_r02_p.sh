@@ -1,4 +1,7 @@
 set -x
-bash tools/gpu_ab.sh 2>&1 | tee gpurun_out/r02_ab_epsrel.log
-ncu --set full --clock-control none --import-source on -k regex:hx_run_kernel -c 1 -o gpurun_out/r02_v18 python tools/profile_run.py 65536 1 > gpurun_out/ncu_v18.log 2>&1; tail -2 gpurun_out/ncu_v18.log
-python -m pytest tests/test_gpu_parity.py -q -x 2>&1 | tail -2
+bash tools/gpu_ab.sh 2>&1 | tee gpurun_out/r02_ab_v20.log
+for rep in 1 2; do
+for f in hector_b200/libhector_b200.so hector_b200/ab_head.so; do
+  echo "== small $f"; HECTOR_B200_LIB=$PWD/$f python tools/profile_run.py 1024 4 | grep "run ms" | tail -3 | tr '\n' ' '; echo
+done; done 2>&1 | tee -a gpurun_out/r02_ab_v20.log
+python -m pytest tests -m gpu -q -x > gpurun_out/r02_gputests_p.log 2>&1; tail -4 gpurun_out/r02_gputests_p.log
