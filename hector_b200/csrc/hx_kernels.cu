@@ -792,6 +792,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
       mb.rec_n = 0;
     }
     int r = base + 1;
+    int bars_done = 0; /* barriers this thread has arrived at in this work item */
     const bool entered = (mb.status == 0);
 #define HX_OH_LOADS(T)                                                                              \
   T oh_m0 = ldg_pinned(BS.P + PI_M0 * HX_BLOCK), oh_cch4 = ldg_pinned(BS.P + PI_CCH4 * HX_BLOCK),          \
@@ -825,7 +826,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 #define oh_itstrat DER(DI_INV_TSTRAT)
 #endif
 #if HX_YEAR_SYNC
-        year_barrier();
+        year_barrier(); ++bars_done;
 #endif
         {
         const double *sc = sl + (size_t)(r - base) * SC_STRIDE;     /* year y */
@@ -964,6 +965,9 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           else slow_params(mb, sp, tland, r == 1, window, lco2);
         }
 
+#if HX_YEAR_SYNC >= 2
+        year_barrier(); ++bars_done; /* the warps enter the solver together */
+#endif
         /* --- CarbonCycleSolver::run --- */
         solver_year<false, TRACK, CONSTR, BIOMES, NBP, NBP || EXACT>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
         if (mb.status) {
@@ -971,6 +975,9 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
           d.fail_year[m] = y;
           break;
         }
+#if HX_YEAR_SYNC >= 3
+        year_barrier(); ++bars_done; /* ... and leave it together */
+#endif
 #if HX_FORC_AHEAD
         /* the forcing's and DOECLIM's member constants, requested as soon as the solver is done:
          * record_state, the logarithm pair and the forcing sum hide their latency */
@@ -1242,7 +1249,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 #if HX_YEAR_SYNC
     /* r = the year a member stopped in (its barrier for that year is done), rend + 1 for a
      * member that ran the whole slab, base + 1 with no arrivals yet for a lane that never ran */
-    for (int q = entered ? r + 1 : r; q <= rend; ++q) year_barrier();
+    for (; bars_done < HX_YEAR_SYNC * (rend - base); ++bars_done) year_barrier();
 #endif
     if (TRACK) {
       /* hand the slab's record to the replay kernel: years a stopped member never reached carry

@@ -1,7 +1,6 @@
 set -x
-bash tools/gpu_ab.sh 2>&1 | tee gpurun_out/r02_ab_v20.log
+bash tools/gpu_ab.sh 2>&1 | tee gpurun_out/r02_ab_sync.log
 for rep in 1 2; do
-for f in hector_b200/libhector_b200.so hector_b200/ab_head.so; do
+for f in hector_b200/libhector_b200.so hector_b200/ab_sync2.so hector_b200/ab_sync3.so; do
   echo "== small $f"; HECTOR_B200_LIB=$PWD/$f python tools/profile_run.py 1024 4 | grep "run ms" | tail -3 | tr '\n' ' '; echo
-done; done 2>&1 | tee -a gpurun_out/r02_ab_v20.log
-python -m pytest tests -m gpu -q -x > gpurun_out/r02_gputests_p.log 2>&1; tail -4 gpurun_out/r02_gputests_p.log
+done; done 2>&1 | tee -a gpurun_out/r02_ab_sync.log
