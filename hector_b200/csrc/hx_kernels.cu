@@ -618,7 +618,9 @@ __device__ __noinline__ void nan_fill_rows(const HxDev &d, int nyears, int col, 
     for (int yi = first; yi < last; ++yi) d.out[((size_t)s * nyears + yi) * d.Mpad + col] = nan;
 }
 
-template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES, bool NBP, bool EXACT, bool GAS>
+/* LAT: the build for ensembles so small that every warp has a scheduler to itself (latency of one
+ * warp is all that counts; code size is not): see integrate<.., RKU> */
+template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES, bool NBP, bool EXACT, bool GAS, bool LAT>
 __global__ void __launch_bounds__(HX_BLOCK, MINCTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   /* dynamic shared memory (> 48 KB): scenario slabs | row 0 | chemistry constants | RK stages */
@@ -969,7 +971,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         year_barrier(); ++bars_done; /* the warps enter the solver together */
 #endif
         /* --- CarbonCycleSolver::run --- */
-        solver_year<false, TRACK, CONSTR, BIOMES, NBP, NBP || EXACT>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
+        solver_year<false, TRACK, CONSTR, BIOMES, NBP, NBP || EXACT, LAT>(mb, C, p, ck, &rk[0][tid], HX_BLOCK, (double)(y - 1), (double)y, cold, w);
         if (mb.status) {
           d.status[m] = mb.status;
           d.fail_year[m] = y;
@@ -1450,7 +1452,7 @@ cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cuda
   return cudaGetLastError();
 }
 template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT = true, bool BIOMES = false,
-          bool NBP = CONSTR, bool EXACT = false, bool GAS = false>
+          bool NBP = CONSTR, bool EXACT = false, bool GAS = false, bool LAT = false>
 static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
   /* the function attribute and the occupancy are per device (context): one cache slot per
    * device ordinal, so that engines on several GPUs can live in one process */
@@ -1460,13 +1462,13 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   if (e0 != cudaSuccess) return e0;
   if (dev < 0 || dev >= HX_MAX_DEVICES) return cudaErrorInvalidDevice;
   if (!resident_of[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS>,
+    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)run_smem_bytes<MINCTAS>());
     if (e != cudaSuccess) return e;
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS>,
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT>,
                                                       HX_BLOCK, run_smem_bytes<MINCTAS>());
     if (e != cudaSuccess) return e;
     resident_of[dev] = sms * (per_sm > 0 ? per_sm : 1);
@@ -1478,7 +1480,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
   cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1 + nslab) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS><<<grid, HX_BLOCK, run_smem_bytes<MINCTAS>(), st>>>(d, C, r0, r1);
+  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT><<<grid, HX_BLOCK, run_smem_bytes<MINCTAS>(), st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
@@ -1515,11 +1517,13 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
   if (d.constrained)     /* the other constraints, lo_warming_ratio: no NBP machinery */
     return small ? launch_run_t<false, true, 2, true, false, false>(d, C, r0, r1, st)
                  : launch_run_t<false, true, HX_RUN_MIN_CTAS, true, false, false>(d, C, r0, r1, st);
+  /* "small": at most one CTA per SM, i.e. every warp has a scheduler to itself -> the LAT build */
+  const bool lone = d.Mpad / HX_BLOCK <= sms;
   if (d.out_minimal)
-    return small ? launch_run_t<false, false, 2, false>(d, C, r0, r1, st)
-                 : launch_run_t<false, false, HX_RUN_MIN_CTAS, false>(d, C, r0, r1, st);
-  return small ? launch_run_t<false, false, 2>(d, C, r0, r1, st)
-               : launch_run_t<false, false, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
+    return lone ? launch_run_t<false, false, 2, false, false, false, false, false, true>(d, C, r0, r1, st)
+                : launch_run_t<false, false, HX_RUN_MIN_CTAS, false>(d, C, r0, r1, st);
+  return lone ? launch_run_t<false, false, 2, true, false, false, false, false, true>(d, C, r0, r1, st)
+              : launch_run_t<false, false, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
 }
 size_t track_record_bytes_per_cta() {
   return (size_t)HX_REC_STASH_MAX * HX_REC_N * HX_BLOCK * sizeof(double);

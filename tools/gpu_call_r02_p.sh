@@ -1,6 +1,3 @@
 set -x
-bash tools/gpu_ab.sh 2>&1 | tee gpurun_out/r02_ab_sync.log
-for rep in 1 2; do
-for f in hector_b200/libhector_b200.so hector_b200/ab_sync2.so hector_b200/ab_sync3.so; do
-  echo "== small $f"; HECTOR_B200_LIB=$PWD/$f python tools/profile_run.py 1024 4 | grep "run ms" | tail -3 | tr '\n' ' '; echo
-done; done 2>&1 | tee -a gpurun_out/r02_ab_sync.log
+for n in 1024 4096 16384; do echo "== members $n"; python tools/profile_run.py $n 4 | grep "run ms" | tail -2 | tr '\n' ' '; echo; done 2>&1 | tee gpurun_out/r02_small_sizes.log
+python -m pytest tests -m gpu -q -x > gpurun_out/r02_gputests_p.log 2>&1; tail -4 gpurun_out/r02_gputests_p.log
