@@ -46,8 +46,12 @@ namespace hx {
 #define HX_SMEM_STATE_BYTES ((HX_HOT_COUNT + SI_COUNT - SI_REG_COUNT) * HX_BLOCK * 8)
 template <int MINCTAS>
 __host__ __device__ constexpr bool smem_state() { return HX_SMEM_STATE && MINCTAS == 2; }
-template <int MINCTAS>
-__host__ __device__ constexpr size_t run_smem_bytes() { return HX_SMEM_RUN_BYTES + (smem_state<MINCTAS>() ? HX_SMEM_STATE_BYTES : 0); }
+/* the latency build (one CTA per SM at most) keeps ALL of P | D on chip, not just the hot stretch */
+#define HX_SMEM_LAT_BYTES ((PD_COUNT + SI_COUNT - SI_REG_COUNT) * HX_BLOCK * 8)
+template <int MINCTAS, bool LAT = false>
+__host__ __device__ constexpr size_t run_smem_bytes() {
+  return HX_SMEM_RUN_BYTES + (!smem_state<MINCTAS>() ? 0 : LAT ? HX_SMEM_LAT_BYTES : HX_SMEM_STATE_BYTES);
+}
 
 /* ---- small PTX wrappers: mbarrier + bulk async copy (TMA engine, UBLKCP in SASS) ---- */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -100,6 +104,9 @@ __device__ __forceinline__ double ldg_pinned(const double *p) {
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+/* a member constant requested ahead of its use: pinned where it is written when it comes from
+ * L2, an ordinary read when the constants are in shared memory */
+#define PAR_AHEAD(ptr) (BS.psm ? *(ptr) : ldg_pinned(ptr))
 /* the same for data this kernel writes itself (the histories): a coherent load */
 __device__ __forceinline__ double ld_pinned(const double *p) {
   double v;
@@ -115,6 +122,7 @@ struct Bases {
   const double *P;
   const double *H; /* the hot stretch of P | D: in the array itself or the run kernel's shared copy */
   double *Sg;      /* the state in global memory (S may point into shared memory) */
+  bool psm;        /* P and D point into shared memory (the latency build): plain loads only */
   double *S, *D, *ker, *sst, *tland, *conv;
   const double *BP; /* per-biome parameters / state of this member (null: single biome) */
   double *BF;
@@ -129,6 +137,7 @@ __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, in
   b.D = const_cast<double *>(b.P) + PI_COUNT * HX_BLOCK; /* same tile block: a compile-time offset */
   b.H = b.P + HX_HOT_FIRST * HX_BLOCK;
   b.Sg = b.S;
+  b.psm = false;
   b.ker = d.ker + tile * (size_t)HX_KER_ROWS(C.nrow) * HX_BLOCK + ln;
   b.conv = d.conv + tile * (size_t)HX_SLAB_YEARS * HX_BLOCK + ln;
   b.sst = d.sst_hist + tile * (size_t)C.nrow * HX_BLOCK + ln;
@@ -139,13 +148,13 @@ __device__ __forceinline__ Bases make_bases(const HxDev &d, const HxConst &C, in
   b.GF = d.GF ? d.GF + tile * (size_t)GF_COUNT * HX_BLOCK + ln : nullptr;
   return b;
 }
-#define PAR(i) __ldg(BS.P + (i) * HX_BLOCK)
+#define PAR(i) (BS.psm ? BS.P[(i) * HX_BLOCK] : __ldg(BS.P + (i) * HX_BLOCK))
 #define STATE(i) BS.S[(i) * HX_BLOCK]
 #define DER(i) BS.D[(i) * HX_BLOCK]
 
 __device__ __forceinline__ LandPar load_landpar(const Bases &BS) {
   LandPar p;
-  p.P = BS.P; p.D = BS.D; p.H = BS.H;
+  p.P = BS.P; p.D = BS.D; p.H = BS.H; p.psm = BS.psm;
   return p;
 }
 
@@ -752,14 +761,24 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
        * is as large as the whole state was, the fourteen fields that only load_member /
        * store_member touch made room for the constants every sub-step and stash reads */
       double *smH = reinterpret_cast<double *>(hx_smem + HX_SMEM_RUN_BYTES) + tid;
-      double *smS = smH + (HX_HOT_COUNT - SI_REG_COUNT) * HX_BLOCK; /* field i at smS[i * HX_BLOCK], i >= SI_REG_COUNT */
-      const double *gH = BS.H;
+      double *smS = smH + ((LAT ? PD_COUNT : HX_HOT_COUNT) - SI_REG_COUNT) * HX_BLOCK; /* field i at smS[i * HX_BLOCK], i >= SI_REG_COUNT */
+      if (LAT) { /* every parameter and derived constant: the year loop reads none of them from L2 */
+        const double *gP = BS.P;
+#pragma unroll 8
+        for (int i = 0; i < PD_COUNT; ++i) smH[i * HX_BLOCK] = __ldg(gP + i * HX_BLOCK);
+        BS.P = smH;
+        BS.D = smH + PI_COUNT * HX_BLOCK;
+        BS.H = smH + HX_HOT_FIRST * HX_BLOCK;
+        BS.psm = true;
+      } else {
+        const double *gH = BS.H;
 #pragma unroll
-      for (int i = 0; i < HX_HOT_COUNT; ++i) smH[i * HX_BLOCK] = __ldg(gH + i * HX_BLOCK);
+        for (int i = 0; i < HX_HOT_COUNT; ++i) smH[i * HX_BLOCK] = __ldg(gH + i * HX_BLOCK);
+        BS.H = smH;
+      }
 #pragma unroll 8
       for (int i = SI_REG_COUNT; i < SI_COUNT; ++i) smS[i * HX_BLOCK] = gS[i * HX_BLOCK];
       BS.S = smS;
-      BS.H = smH;
     }
     if (bf_in_smem) {
       double *smB = reinterpret_cast<double *>(hx_smem + HX_SMEM_RUN_BYTES) + tid;
@@ -797,11 +816,11 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     int bars_done = 0; /* barriers this thread has arrived at in this work item */
     const bool entered = (mb.status == 0);
 #define HX_OH_LOADS(T)                                                                              \
-  T oh_m0 = ldg_pinned(BS.P + PI_M0 * HX_BLOCK), oh_cch4 = ldg_pinned(BS.P + PI_CCH4 * HX_BLOCK),          \
-    oh_cnox = ldg_pinned(BS.P + PI_CNOX * HX_BLOCK), oh_cco = ldg_pinned(BS.P + PI_CCO * HX_BLOCK),        \
-    oh_cnmvoc = ldg_pinned(BS.P + PI_CNMVOC * HX_BLOCK), oh_toh0 = ldg_pinned(BS.P + PI_TOH0 * HX_BLOCK),  \
-    oh_logm0 = ldg_pinned(BS.D + DI_LOG_M0 * HX_BLOCK), oh_iuc = ldg_pinned(BS.D + DI_INV_UC_CH4 * HX_BLOCK), \
-    oh_itsoil = ldg_pinned(BS.D + DI_INV_TSOIL * HX_BLOCK), oh_itstrat = ldg_pinned(BS.D + DI_INV_TSTRAT * HX_BLOCK);
+  T oh_m0 = PAR_AHEAD(BS.P + PI_M0 * HX_BLOCK), oh_cch4 = PAR_AHEAD(BS.P + PI_CCH4 * HX_BLOCK),          \
+    oh_cnox = PAR_AHEAD(BS.P + PI_CNOX * HX_BLOCK), oh_cco = PAR_AHEAD(BS.P + PI_CCO * HX_BLOCK),        \
+    oh_cnmvoc = PAR_AHEAD(BS.P + PI_CNMVOC * HX_BLOCK), oh_toh0 = PAR_AHEAD(BS.P + PI_TOH0 * HX_BLOCK),  \
+    oh_logm0 = PAR_AHEAD(BS.D + DI_LOG_M0 * HX_BLOCK), oh_iuc = PAR_AHEAD(BS.D + DI_INV_UC_CH4 * HX_BLOCK), \
+    oh_itsoil = PAR_AHEAD(BS.D + DI_INV_TSOIL * HX_BLOCK), oh_itstrat = PAR_AHEAD(BS.D + DI_INV_TSTRAT * HX_BLOCK);
 #if HX_OH_AHEAD == 2
     HX_OH_LOADS(double)
 #endif
@@ -983,18 +1002,18 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 #if HX_FORC_AHEAD
         /* the forcing's and DOECLIM's member constants, requested as soon as the solver is done:
          * record_state, the logarithm pair and the forcing sum hide their latency */
-        const double fa_c0 = ldg_pinned(BS.P + PI_C0 * HX_BLOCK), fa_m0 = ldg_pinned(BS.P + PI_M0 * HX_BLOCK),
-                     fa_aero = ldg_pinned(BS.P + PI_AERO * HX_BLOCK), fa_vol = ldg_pinned(BS.P + PI_VOL * HX_BLOCK),
-                     fa_dco2 = ldg_pinned(BS.P + PI_DELTA_CO2 * HX_BLOCK), fa_dch4 = ldg_pinned(BS.P + PI_DELTA_CH4 * HX_BLOCK),
-                     fa_dn2o = ldg_pinned(BS.P + PI_DELTA_N2O * HX_BLOCK), fa_rbc = ldg_pinned(BS.P + PI_RHO_BC * HX_BLOCK),
-                     fa_roc = ldg_pinned(BS.P + PI_RHO_OC * HX_BLOCK), fa_rso2 = ldg_pinned(BS.P + PI_RHO_SO2 * HX_BLOCK),
-                     fa_rnh3 = ldg_pinned(BS.P + PI_RHO_NH3 * HX_BLOCK), fa_sqm0 = ldg_pinned(BS.D + DI_SQRT_M0 * HX_BLOCK);
-        const double dc_qc1 = ldg_pinned(BS.D + DI_QC1 * HX_BLOCK), dc_qc2 = ldg_pinned(BS.D + DI_QC2 * HX_BLOCK),
-                     dc_a0 = ldg_pinned(BS.D + DI_A0 * HX_BLOCK), dc_a1 = ldg_pinned(BS.D + DI_A1 * HX_BLOCK),
-                     dc_a2 = ldg_pinned(BS.D + DI_A2 * HX_BLOCK), dc_a3 = ldg_pinned(BS.D + DI_A3 * HX_BLOCK),
-                     dc_ib0 = ldg_pinned(BS.D + DI_IB0 * HX_BLOCK), dc_ib1 = ldg_pinned(BS.D + DI_IB1 * HX_BLOCK),
-                     dc_ib2 = ldg_pinned(BS.D + DI_IB2 * HX_BLOCK), dc_ib3 = ldg_pinned(BS.D + DI_IB3 * HX_BLOCK),
-                     dc_sqdt = ldg_pinned(BS.D + DI_SQDT_TAUDIF * HX_BLOCK), dc_hfint = ldg_pinned(BS.D + DI_HF_INT * HX_BLOCK),
+        const double fa_c0 = PAR_AHEAD(BS.P + PI_C0 * HX_BLOCK), fa_m0 = PAR_AHEAD(BS.P + PI_M0 * HX_BLOCK),
+                     fa_aero = PAR_AHEAD(BS.P + PI_AERO * HX_BLOCK), fa_vol = PAR_AHEAD(BS.P + PI_VOL * HX_BLOCK),
+                     fa_dco2 = PAR_AHEAD(BS.P + PI_DELTA_CO2 * HX_BLOCK), fa_dch4 = PAR_AHEAD(BS.P + PI_DELTA_CH4 * HX_BLOCK),
+                     fa_dn2o = PAR_AHEAD(BS.P + PI_DELTA_N2O * HX_BLOCK), fa_rbc = PAR_AHEAD(BS.P + PI_RHO_BC * HX_BLOCK),
+                     fa_roc = PAR_AHEAD(BS.P + PI_RHO_OC * HX_BLOCK), fa_rso2 = PAR_AHEAD(BS.P + PI_RHO_SO2 * HX_BLOCK),
+                     fa_rnh3 = PAR_AHEAD(BS.P + PI_RHO_NH3 * HX_BLOCK), fa_sqm0 = PAR_AHEAD(BS.D + DI_SQRT_M0 * HX_BLOCK);
+        const double dc_qc1 = PAR_AHEAD(BS.D + DI_QC1 * HX_BLOCK), dc_qc2 = PAR_AHEAD(BS.D + DI_QC2 * HX_BLOCK),
+                     dc_a0 = PAR_AHEAD(BS.D + DI_A0 * HX_BLOCK), dc_a1 = PAR_AHEAD(BS.D + DI_A1 * HX_BLOCK),
+                     dc_a2 = PAR_AHEAD(BS.D + DI_A2 * HX_BLOCK), dc_a3 = PAR_AHEAD(BS.D + DI_A3 * HX_BLOCK),
+                     dc_ib0 = PAR_AHEAD(BS.D + DI_IB0 * HX_BLOCK), dc_ib1 = PAR_AHEAD(BS.D + DI_IB1 * HX_BLOCK),
+                     dc_ib2 = PAR_AHEAD(BS.D + DI_IB2 * HX_BLOCK), dc_ib3 = PAR_AHEAD(BS.D + DI_IB3 * HX_BLOCK),
+                     dc_sqdt = PAR_AHEAD(BS.D + DI_SQDT_TAUDIF * HX_BLOCK), dc_hfint = PAR_AHEAD(BS.D + DI_HF_INT * HX_BLOCK),
                      dc_k1 = ldg_pinned(BS.ker + Hs); /* K(1): written by the set-up kernel, read-only here */
 #else
 #define fa_c0 LP_C0(p)
@@ -1464,12 +1483,12 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   if (!resident_of[dev]) {
     cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)run_smem_bytes<MINCTAS>());
+                                         (int)run_smem_bytes<MINCTAS, LAT>());
     if (e != cudaSuccess) return e;
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT>,
-                                                      HX_BLOCK, run_smem_bytes<MINCTAS>());
+                                                      HX_BLOCK, run_smem_bytes<MINCTAS, LAT>());
     if (e != cudaSuccess) return e;
     resident_of[dev] = sms * (per_sm > 0 ? per_sm : 1);
   }
@@ -1480,7 +1499,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
   cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1 + nslab) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT><<<grid, HX_BLOCK, run_smem_bytes<MINCTAS>(), st>>>(d, C, r0, r1);
+  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT><<<grid, HX_BLOCK, run_smem_bytes<MINCTAS, LAT>(), st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
