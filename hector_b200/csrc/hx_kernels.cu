@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "hx_kernels.h"
 #include "hx_model.cuh"
@@ -1537,7 +1538,9 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
     return small ? launch_run_t<false, true, 2, true, false, false>(d, C, r0, r1, st)
                  : launch_run_t<false, true, HX_RUN_MIN_CTAS, true, false, false>(d, C, r0, r1, st);
   /* "small": at most one CTA per SM, i.e. every warp has a scheduler to itself -> the LAT build */
-  const bool lone = d.Mpad / HX_BLOCK <= sms;
+  /* (HX_NO_LAT=1 keeps small ensembles on the general build: sanitizer runs of that build) */
+  static const bool no_lat = std::getenv("HX_NO_LAT") != nullptr;
+  const bool lone = !no_lat && d.Mpad / HX_BLOCK <= sms;
   if (d.out_minimal)
     return lone ? launch_run_t<false, false, 2, false, false, false, false, false, true>(d, C, r0, r1, st)
                 : launch_run_t<false, false, HX_RUN_MIN_CTAS, false>(d, C, r0, r1, st);
