@@ -210,7 +210,10 @@ def roofline_of(kernel, members, years, kernel_ms, hbm_peak, peaks_measured, fp6
          else "B200_PROFILING.md fallback (of fallback)",
          "kernel": kernel, "kernel_ms": kernel_ms,
          "algorithmic_bytes_per_member_year": B_ALG,
-         "binds": "FP64 issue/latency at low occupancy, not HBM: see dram_frac and fp64"}
+         "binds": "FP64 issue/latency at low occupancy, not HBM: see dram_frac and fp64",
+         "frac_note": "frac counts SURVEY 8(d)'s algorithmic bytes (a year-stepped model re-reading "
+                      "its DOECLIM history every year); the kernel reads the history once per 16 "
+                      "years and keeps the state on chip, so frac can exceed 1 while HBM is idle"}
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))
         # the capture's ensemble may differ in size from this run's: scale per member-year

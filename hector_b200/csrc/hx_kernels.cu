@@ -848,7 +848,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 #define oh_itstrat DER(DI_INV_TSTRAT)
 #endif
 #if HX_YEAR_SYNC
-        year_barrier(); ++bars_done;
+        if ((r - base - 1) % HX_YEAR_SYNC_EVERY == 0) { year_barrier(); ++bars_done; }
 #endif
         {
         const double *sc = sl + (size_t)(r - base) * SC_STRIDE;     /* year y */
@@ -1271,7 +1271,8 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 #if HX_YEAR_SYNC
     /* r = the year a member stopped in (its barrier for that year is done), rend + 1 for a
      * member that ran the whole slab, base + 1 with no arrivals yet for a lane that never ran */
-    for (; bars_done < HX_YEAR_SYNC * (rend - base); ++bars_done) year_barrier();
+    for (; bars_done < (HX_YEAR_SYNC - 1) * (rend - base) + (rend - base + HX_YEAR_SYNC_EVERY - 1) / HX_YEAR_SYNC_EVERY; ++bars_done)
+      year_barrier();
 #endif
     if (TRACK) {
       /* hand the slab's record to the replay kernel: years a stopped member never reached carry

@@ -23,6 +23,9 @@
 #ifndef HX_OH_AHEAD
 #define HX_OH_AHEAD 2 /* the OH / CH4 constants are requested ahead: 1 = before the year barrier, 2 = after the solver of the year before */
 #endif
+#ifndef HX_YEAR_SYNC_EVERY
+#define HX_YEAR_SYNC_EVERY 1 /* the top-of-year barrier every n-th year of a work item */
+#endif
 #ifndef HX_YEAR_SYNC
 #define HX_YEAR_SYNC 1 /* one CTA barrier per simulated year: the warps share instruction fetches */
 #endif
