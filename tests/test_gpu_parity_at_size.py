@@ -249,3 +249,60 @@ def test_extreme_members_failure_set_vs_oracle(exact):
     assert ties <= 4
     assert 300 < failed < 420, failed      # the draw is meant to sit on the edge
     ens.close()
+
+
+_BUILD_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+from tests import util
+import hector_b200 as hb
+M = {M}
+X = util.lhs(M)
+kw = dict(outputs={outs!r})
+kw.update({kw!r})
+ens = hb.Ensemble(M, util.scenarios()[{scen!r}], **kw)
+for j, n in enumerate(["S", "q10_rh", "beta", "diff"]):
+    ens.setvar(n, X[:, j])
+ens.run()
+got = ens.fetchvars(np.arange(1746, 2301, dtype=np.float64), {outs!r})
+res = {{k: v for k, v in got.items()}}
+if kw.get("tracking_date"):
+    frac, mask = ens.fetch_tracking(2300)
+    res["frac"] = frac; res["mask"] = mask
+np.savez({out!r}, **res)
+"""
+
+
+def _run_in_subprocess(tmp_path, tag, env, M, scen, outs, kw):
+    """One ensemble run in a fresh process (the build switches below are read once per process)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / (tag + ".npz"))
+    code = _BUILD_SCRIPT.format(root=root, M=M, outs=outs, kw=kw, scen=scen, out=out)
+    e = dict(os.environ)
+    e.update(env)
+    subprocess.run([sys.executable, "-c", code], check=True, env=e, timeout=600)
+    return np.load(out)
+
+
+def test_latency_build_is_bit_identical_to_the_general_build(tmp_path):
+    """Ensembles of at most one CTA per SM run the LAT instantiation of the run kernel
+    (straight-line Runge-Kutta stages, every constant in shared memory); HX_NO_LAT=1 keeps them
+    on the general build.  Same arithmetic in the same order: every output bit for bit."""
+    outs = ["CO2_concentration", "global_tas", "ocean_timesteps", "RF_tot", "ocean_c"]
+    a = _run_in_subprocess(tmp_path, "lat", {}, 1024, "ssp370", outs, {})
+    b = _run_in_subprocess(tmp_path, "general", {"HX_NO_LAT": "1"}, 1024, "ssp370", outs, {})
+    for k in outs:
+        assert np.array_equal(a[k].view(np.uint64), b[k].view(np.uint64)), k
+
+
+def test_tracked_record_groups_are_bit_identical(tmp_path):
+    """The record-only run kernel covers 1 or 4 slabs per launch (HX_TRK_GROUP): trajectories and
+    tracked source maps must not depend on it."""
+    outs = ["CO2_concentration", "global_tas"]
+    kw = dict(tracking_date=1750, track_every=0)
+    a = _run_in_subprocess(tmp_path, "g1", {"HX_TRK_GROUP": "1"}, 640, "ssp585", outs, kw)
+    b = _run_in_subprocess(tmp_path, "g4", {"HX_TRK_GROUP": "4"}, 640, "ssp585", outs, kw)
+    for k in outs + ["frac"]:
+        assert np.array_equal(a[k].view(np.uint64), b[k].view(np.uint64)), k
+    assert np.array_equal(a["mask"], b["mask"])
