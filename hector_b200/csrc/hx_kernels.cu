@@ -469,7 +469,7 @@ template <bool BIOMES>
 __global__ void __launch_bounds__(HX_BLOCK)
 hx_spinup_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int m_offset,
                  int only_member) {
-  __shared__ double rk[HX_RK_SLOTS][HX_BLOCK]; /* Runge-Kutta stage derivatives k1..k7 */
+  __shared__ __align__(16) double rk[HX_RK_SLOTS][HX_BLOCK]; /* Runge-Kutta stage derivatives k1..k7 */
   const int m = m_offset + blockIdx.x * HX_BLOCK + threadIdx.x;
   if (m >= d.Mpad) return;
   if (d.status[m] < 0) return;

@@ -1,22 +1,7 @@
 set -x
-nvidia-smi --query-gpu=memory.used,memory.total --format=csv
-python - <<'PY'
-import os, sys
-sys.path.insert(0, os.getcwd())
-import numpy as np, torch
-import hector_b200 as hb
-from bench import lhs, scenario_table, PARAMS
-M = 131072
-X = lhs(M)
-ens = hb.Ensemble(M, scenario_table("ssp585", end=2500) if 'end' in scenario_table.__code__.co_varnames else scenario_table("ssp585"), outputs=["CO2_concentration", "global_tas"], tracking_date=1750, track_every=0)
-for j, n in enumerate(PARAMS):
-    ens.setvar(n, np.ascontiguousarray(X[:, j]))
-ens.prepare()
-free, total = torch.cuda.mem_get_info()
-print("after prepare: used GB", (total - free) / 1e9)
-for _ in range(2):
-    ens.reset(); ens.run(); ens.synchronize()
-    print("run ms", ens.last_run_ms)
-st, fy = ens.status()
-print("failed", int((st != 0).sum()))
-PY
+bash tools/gpu_ab.sh 2>&1 | tee gpurun_out/r02_ab_lds128.log
+for rep in 1 2; do
+for f in hector_b200/libhector_b200.so hector_b200/ab_head.so; do
+  echo "== small $f"; HECTOR_B200_LIB=$PWD/$f python tools/profile_run.py 1024 4 | grep "run ms" | tail -3 | tr '\n' ' '; echo
+done; done 2>&1 | tee -a gpurun_out/r02_ab_lds128.log
+python -m pytest tests -m gpu -q -x > gpurun_out/r02_gputests_p.log 2>&1; tail -4 gpurun_out/r02_gputests_p.log
