@@ -1518,9 +1518,11 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
     /* no constraint, no lo_warming_ratio: the biome loops without the constraint machinery */
     return launch_run_t<false, false, 2, true, true, false>(d, C, r0, r1, st);
   }
-  if (d.T)
-    return d.constrained ? launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st)
+  if (d.T) { /* carbon tracking: the record-only builds */
+    if (d.constrained) return launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st);
+    return d.out_minimal ? launch_run_t<true, false, HX_TRACK_CTAS, false>(d, C, r0, r1, st)
                          : launch_run_t<true, false, HX_TRACK_CTAS>(d, C, r0, r1, st);
+  }
   if (d.GP) /* per-member N2O / halocarbon parameters: the GAS build (plain runs, every output) */
     return launch_run_t<false, false, 2, true, false, false, false, true>(d, C, r0, r1, st);
   if (C.flags & HX_FLAG_EXACT_ATTEMPTS) { /* the builds that execute abandoned ODE attempts */
