@@ -172,7 +172,7 @@ __device__ __forceinline__ void load_member(const Bases &BS, Member &mb) {
   mb.solver_dt = STATE_G(SI_SOLVER_DT);
   mb.status = 0; mb.neg = false; mb.timesteps = 0;
   mb.pco2HL = mb.pco2LL = 0.0; mb.gHL = mb.gLL = 0.0; mb.luc_e = mb.luc_u = 0.0;
-  mb.REC = nullptr; mb.rec_n = 0; mb.trk = false; mb.trk_bad = false;
+  mb.REC = nullptr; mb.rec_stride = 0; mb.rec_n = 0; mb.trk = false; mb.trk_bad = false;
   mb.BIOP = BS.BP; mb.BIOF = BS.BF;
 }
 
@@ -810,7 +810,12 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     if (TRACK) {
 #pragma unroll
       for (int j = 0; j < HX_SLAB_YEARS; ++j) ycnt[j] = 0;
+#if HX_REC_PAIR_MAJOR
+      mb.REC = d.REC + (size_t)s * d.rec_slab_stride + 2 * ((size_t)tile * HX_BLOCK + tid);
+      mb.rec_stride = (size_t)d.Mpad;
+#else
       mb.REC = d.REC + (size_t)s * d.rec_slab_stride + ((size_t)tile * HX_BLOCK + tid) * (HX_REC_STASH_MAX * HX_REC_N);
+#endif
       mb.rec_n = 0;
     }
     int r = base + 1;
@@ -1359,6 +1364,45 @@ __global__ void hx_track_init_kernel(const __grid_constant__ HxDev d) {
 #define HX_TRK_LANES ((HX_NSRC + HX_TRK_NS - 1) / HX_TRK_NS)
 #define HX_TRK_PER_WARP (32 / HX_TRK_LANES)      /* members per warp */
 #define HX_TRK_MEMBERS (4 * HX_TRK_PER_WARP)     /* members per 128-thread CTA */
+#if HX_REC_PAIR_MAJOR
+struct StagedRecord {
+  const double2 *rec;  /* the member's column of the slab's record, pair (stash, k) at rec[(stash * MIX + k) * stride] */
+  size_t stride;       /* members per row */
+  double *sh;          /* this member's two staging buffers, [2][HX_REC_MIX * HX_REC_ROW] */
+  int lane, nst;
+  unsigned mask;       /* the member's lanes within the warp */
+  double2 v[(HX_REC_MIX + HX_TRK_LANES - 1) / HX_TRK_LANES]; /* this lane's pairs of the next stash, in flight */
+  int staged;          /* stash whose pairs are in v, -1: none */
+  __device__ __forceinline__ void prefetch(int st) {
+    staged = st;
+    if (st >= nst) return;
+    const double2 *p = rec + (size_t)st * HX_REC_MIX * stride;
+#pragma unroll
+    for (int j = 0; j < (HX_REC_MIX + HX_TRK_LANES - 1) / HX_TRK_LANES; ++j) {
+      const int k = lane + HX_TRK_LANES * j;
+      v[j] = (k < HX_REC_MIX) ? __ldcs(p + (size_t)k * stride) : make_double2(0.0, 0.0);
+    }
+  }
+  /* rows (a, b, 1 / (a + b)) of stash st in shared memory; st advances by one per call */
+  __device__ __forceinline__ const double *stash(int st) {
+    double *buf = sh + (st & 1) * (HX_REC_MIX * HX_REC_ROW);
+    if (staged != st) prefetch(st);
+#pragma unroll
+    for (int j = 0; j < (HX_REC_MIX + HX_TRK_LANES - 1) / HX_TRK_LANES; ++j) {
+      const int k = lane + HX_TRK_LANES * j;
+      if (k < HX_REC_MIX) {
+        const double total = __dadd_rn(v[j].x, v[j].y);
+        buf[k * HX_REC_ROW] = v[j].x;
+        buf[k * HX_REC_ROW + 1] = v[j].y;
+        buf[k * HX_REC_ROW + 2] = (total != 0.0) ? 1.0 / total : 0.0;
+      }
+    }
+    prefetch(st + 1);
+    __syncwarp(mask);
+    return buf;
+  }
+};
+#else
 struct StagedRecord {
   const double *rec;   /* the member's record, [stash][HX_REC_N] */
   double *sh;          /* this member's two staging buffers, [2][HX_REC_MIX * HX_REC_ROW] */
@@ -1400,6 +1444,7 @@ struct StagedRecord {
   }
 };
 
+#endif
 __global__ void __launch_bounds__(128, HX_TRK_NS == 1 ? 5 : HX_TRK_NS == 2 ? 3 : 2)
 hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   __shared__ double sh[HX_TRK_MEMBERS][2][HX_REC_MIX * HX_REC_ROW];
@@ -1415,7 +1460,12 @@ hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   const unsigned char *yc = d.YCNT + tile * (size_t)(HX_SLAB_YEARS * HX_BLOCK) + ln;
   const int nyears = r1 - r0;
   StagedRecord fetch;
+#if HX_REC_PAIR_MAJOR
+  fetch.rec = reinterpret_cast<const double2 *>(d.REC) + m;
+  fetch.stride = (size_t)d.Mpad;
+#else
   fetch.rec = d.REC + (size_t)m * (HX_REC_STASH_MAX * HX_REC_N);
+#endif
   fetch.sh = &sh[cm][0][0];
   fetch.lane = s;
   fetch.nst = yc[(nyears - 1) * HX_BLOCK];

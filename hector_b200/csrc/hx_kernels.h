@@ -67,7 +67,7 @@ struct HxDev {
   /* carbon tracking (null unless a tracking date was set) */
   double *T;                /* [tile][TS_COUNT * HX_NSRC][128] source fractions */
   uint32_t *TK;             /* [tile][TS_COUNT][128] key masks */
-  double *REC;              /* [member][HX_REC_STASH_MAX][HX_REC_N] stash records of the slab
+  double *REC;              /* [HX_REC_STASH_MAX][HX_REC_MIX][member] (a, b) pairs: stash records of the slab
                                being run (hx_model.cuh, "Carbon tracking") */
   unsigned char *YCNT;      /* [tile][HX_SLAB_YEARS][128] stashes recorded up to each year's end */
   /* a tracked launch may cover several slabs: slab s of the launch records into REC + s *
