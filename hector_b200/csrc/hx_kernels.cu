@@ -810,12 +810,8 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     if (TRACK) {
 #pragma unroll
       for (int j = 0; j < HX_SLAB_YEARS; ++j) ycnt[j] = 0;
-#if HX_REC_PAIR_MAJOR
       mb.REC = d.REC + (size_t)s * d.rec_slab_stride + 2 * ((size_t)tile * HX_BLOCK + tid);
       mb.rec_stride = (size_t)d.Mpad;
-#else
-      mb.REC = d.REC + (size_t)s * d.rec_slab_stride + ((size_t)tile * HX_BLOCK + tid) * (HX_REC_STASH_MAX * HX_REC_N);
-#endif
       mb.rec_n = 0;
     }
     int r = base + 1;
@@ -1364,7 +1360,10 @@ __global__ void hx_track_init_kernel(const __grid_constant__ HxDev d) {
 #define HX_TRK_LANES ((HX_NSRC + HX_TRK_NS - 1) / HX_TRK_NS)
 #define HX_TRK_PER_WARP (32 / HX_TRK_LANES)      /* members per warp */
 #define HX_TRK_MEMBERS (4 * HX_TRK_PER_WARP)     /* members per 128-thread CTA */
-#if HX_REC_PAIR_MAJOR
+/* + 2: a member's two buffers start 300 words apart, so the five members of a warp read their
+ * rows (one address per member) from different banks */
+#define HX_TRK_SH_STRIDE (2 * HX_REC_MIX * HX_REC_ROW + 2) /* doubles of staging per member */
+#define HX_TRK_SH_BYTES (HX_TRK_MEMBERS * HX_TRK_SH_STRIDE * 8)
 struct StagedRecord {
   const double2 *rec;  /* the member's column of the slab's record, pair (stash, k) at rec[(stash * MIX + k) * stride] */
   size_t stride;       /* members per row */
@@ -1373,6 +1372,7 @@ struct StagedRecord {
   unsigned mask;       /* the member's lanes within the warp */
   double2 v[(HX_REC_MIX + HX_TRK_LANES - 1) / HX_TRK_LANES]; /* this lane's pairs of the next stash, in flight */
   int staged;          /* stash whose pairs are in v, -1: none */
+  bool slow;           /* the stash just staged needs the general mix (see stash()) */
   __device__ __forceinline__ void prefetch(int st) {
     staged = st;
     if (st >= nst) return;
@@ -1383,71 +1383,38 @@ struct StagedRecord {
       v[j] = (k < HX_REC_MIX) ? __ldcs(p + (size_t)k * stride) : make_double2(0.0, 0.0);
     }
   }
-  /* rows (a, b, 1 / (a + b)) of stash st in shared memory; st advances by one per call */
+  /* rows (v = b / (a + b), a + b) of stash st in shared memory; st advances by one per call.
+   * `slow` is set for the member's lanes when the stash holds anything the straight-line mix
+   * does not cover: a zero or NaN total other than thawed permafrost's (R_T0: empty until the
+   * first thaw, it keeps its test), or a dump into the deep ocean (a present R_DUMPx row) */
   __device__ __forceinline__ const double *stash(int st) {
     double *buf = sh + (st & 1) * (HX_REC_MIX * HX_REC_ROW);
     if (staged != st) prefetch(st);
+    bool odd = false;
 #pragma unroll
     for (int j = 0; j < (HX_REC_MIX + HX_TRK_LANES - 1) / HX_TRK_LANES; ++j) {
       const int k = lane + HX_TRK_LANES * j;
       if (k < HX_REC_MIX) {
         const double total = __dadd_rn(v[j].x, v[j].y);
-        buf[k * HX_REC_ROW] = v[j].x;
-        buf[k * HX_REC_ROW + 1] = v[j].y;
-        buf[k * HX_REC_ROW + 2] = (total != 0.0) ? 1.0 / total : 0.0;
+        /* v = b (1 / total), not b / total: the flux b is zero in a quarter of the rows, and a
+         * zero numerator sends the division through its slow path */
+        *reinterpret_cast<double2 *>(buf + k * HX_REC_ROW) =
+            make_double2((total != 0.0) ? __dmul_rn(v[j].y, 1.0 / total) : 0.0, total);
+        if (k == R_DUMP0 || k == R_DUMP1) odd = odd || (total == total);
+        else if (k != R_T0) odd = odd || !(fabs(total) > 0.0);
       }
     }
-    prefetch(st + 1);
-    __syncwarp(mask);
-    return buf;
-  }
-};
-#else
-struct StagedRecord {
-  const double *rec;   /* the member's record, [stash][HX_REC_N] */
-  double *sh;          /* this member's two staging buffers, [2][HX_REC_MIX * HX_REC_ROW] */
-  int lane, nst;
-  unsigned mask;       /* the member's lanes within the warp */
-  double v[(HX_REC_N + HX_TRK_LANES - 1) / HX_TRK_LANES]; /* next stash in flight */
-  int staged;          /* stash whose pairs are in v, -1: none */
-  __device__ __forceinline__ void prefetch(int st) {
-    staged = st;
-    if (st >= nst) return;
-    const double *p = rec + (size_t)st * HX_REC_N;
-#pragma unroll
-    for (int j = 0; j < (HX_REC_N + HX_TRK_LANES - 1) / HX_TRK_LANES; ++j) {
-      const int i = lane + HX_TRK_LANES * j;
-      v[j] = (i < HX_REC_N) ? __ldcs(p + i) : 0.0;
-    }
-  }
-  /* rows (a, b, 1 / (a + b)) of stash st in shared memory; st advances by one per call */
-  __device__ __forceinline__ const double *stash(int st) {
-    double *buf = sh + (st & 1) * (HX_REC_MIX * HX_REC_ROW);
-    if (staged != st) prefetch(st);
-#pragma unroll
-    for (int j = 0; j < (HX_REC_N + HX_TRK_LANES - 1) / HX_TRK_LANES; ++j) {
-      const int i = lane + HX_TRK_LANES * j; /* pair element i = 2 k + {0, 1} */
-      if (i < HX_REC_N) buf[(i >> 1) * HX_REC_ROW + (i & 1)] = v[j];
-    }
-    __syncwarp(mask);
-#pragma unroll
-    for (int j = 0; j < (HX_REC_MIX + HX_TRK_LANES - 1) / HX_TRK_LANES; ++j) {
-      const int kx = lane + HX_TRK_LANES * j;
-      if (kx < HX_REC_MIX) {
-        const double total = __dadd_rn(buf[kx * HX_REC_ROW], buf[kx * HX_REC_ROW + 1]);
-        buf[kx * HX_REC_ROW + 2] = (total != 0.0) ? 1.0 / total : 0.0;
-      }
-    }
+    slow = __any_sync(mask, odd);
     prefetch(st + 1);
     __syncwarp(mask);
     return buf;
   }
 };
 
-#endif
 __global__ void __launch_bounds__(128, HX_TRK_NS == 1 ? 5 : HX_TRK_NS == 2 ? 3 : 2)
 hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
-  __shared__ double sh[HX_TRK_MEMBERS][2][HX_REC_MIX * HX_REC_ROW];
+  extern __shared__ __align__(16) double sh_dyn[];
+  double (*sh)[HX_TRK_SH_STRIDE] = reinterpret_cast<double (*)[HX_TRK_SH_STRIDE]>(sh_dyn);
   const int wl = threadIdx.x & 31, wm = wl / HX_TRK_LANES; /* lane and member within the warp */
   if (wm >= HX_TRK_PER_WARP) return;                      /* the warp's spare lanes */
   const int cm = (threadIdx.x >> 5) * HX_TRK_PER_WARP + wm; /* member within the CTA */
@@ -1460,17 +1427,14 @@ hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   const unsigned char *yc = d.YCNT + tile * (size_t)(HX_SLAB_YEARS * HX_BLOCK) + ln;
   const int nyears = r1 - r0;
   StagedRecord fetch;
-#if HX_REC_PAIR_MAJOR
   fetch.rec = reinterpret_cast<const double2 *>(d.REC) + m;
   fetch.stride = (size_t)d.Mpad;
-#else
-  fetch.rec = d.REC + (size_t)m * (HX_REC_STASH_MAX * HX_REC_N);
-#endif
-  fetch.sh = &sh[cm][0][0];
+  fetch.sh = &sh[cm][0];
   fetch.lane = s;
   fetch.nst = yc[(nyears - 1) * HX_BLOCK];
   fetch.mask = ((1u << HX_TRK_LANES) - 1u) << (wm * HX_TRK_LANES);
   fetch.staged = -1;
+  fetch.slow = true;
   const bool good = track_replay<HX_TRK_NS>(T, TK, fetch, yc, HX_BLOCK, nyears,
                                             C.start_year + r0 + 1, s * HX_TRK_NS,
                                             (s + 1) * HX_TRK_NS, C.tracking_date, C.track_every, C.track_nrec,
@@ -1606,7 +1570,11 @@ size_t track_record_bytes_per_cta() {
 size_t track_ycnt_bytes_per_tile() { return (size_t)HX_SLAB_YEARS * HX_BLOCK; }
 int track_slab_years() { return HX_SLAB_YEARS; }
 cudaError_t launch_track(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
-  hx_track_kernel<<<(unsigned)((d.Mpad + HX_TRK_MEMBERS - 1) / HX_TRK_MEMBERS), 128, 0, st>>>(d, C, r0, r1);
+  if (HX_TRK_SH_BYTES > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(hx_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HX_TRK_SH_BYTES);
+    if (e != cudaSuccess) return e;
+  }
+  hx_track_kernel<<<(unsigned)((d.Mpad + HX_TRK_MEMBERS - 1) / HX_TRK_MEMBERS), 128, HX_TRK_SH_BYTES, st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_track_merge(const HxDev &d, cudaStream_t st) {
