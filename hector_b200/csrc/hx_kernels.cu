@@ -1364,48 +1364,74 @@ __global__ void hx_track_init_kernel(const __grid_constant__ HxDev d) {
  * rows (one address per member) from different banks */
 #define HX_TRK_SH_STRIDE (2 * HX_REC_MIX * HX_REC_ROW + 2) /* doubles of staging per member */
 #define HX_TRK_SH_BYTES (HX_TRK_MEMBERS * HX_TRK_SH_STRIDE * 8)
+/* 1 / t for an ordinary positive t (the caller has checked 1e-290 < t < 1e290): the hardware's
+ * 20-bit seed and one cubic Newton step, relative error about 2 ulp -- the weight v of a mix
+ * needs no more (tm_mix, hx_model.cuh), and the division operator's range test, its branch and
+ * its two further steps were a third of the staging code */
+__device__ __forceinline__ double rcp_ordinary(double t) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
+  double e = fma(-t, y, 1.0);
+  e = fma(e, e, e);
+  return fma(y, e, y);
+}
 struct StagedRecord {
-  const double2 *rec;  /* the member's column of the slab's record, pair (stash, k) at rec[(stash * MIX + k) * stride] */
+  const double2 *next; /* this lane's first pair of the stash to fetch next: the slab's record holds
+                          pair (stash, k) of the member at [(stash * HX_REC_MIX + k) * stride] */
   size_t stride;       /* members per row */
   double *sh;          /* this member's two staging buffers, [2][HX_REC_MIX * HX_REC_ROW] */
   int lane, nst;
   unsigned mask;       /* the member's lanes within the warp */
   double2 v[(HX_REC_MIX + HX_TRK_LANES - 1) / HX_TRK_LANES]; /* this lane's pairs of the next stash, in flight */
-  int staged;          /* stash whose pairs are in v, -1: none */
+  int staged;          /* stash whose pairs are in v */
   bool slow;           /* the stash just staged needs the general mix (see stash()) */
-  __device__ __forceinline__ void prefetch(int st) {
-    staged = st;
-    if (st >= nst) return;
-    const double2 *p = rec + (size_t)st * HX_REC_MIX * stride;
+  __device__ __forceinline__ void begin(const double2 *rec) {
+    next = rec + (size_t)lane * stride;
+    staged = -1;
+    slow = true;
+    prefetch();
+  }
+  __device__ __forceinline__ void prefetch() {
+    if (++staged >= nst) return;
+    const double2 *q = next;
+    const size_t step = (size_t)HX_TRK_LANES * stride;
 #pragma unroll
     for (int j = 0; j < (HX_REC_MIX + HX_TRK_LANES - 1) / HX_TRK_LANES; ++j) {
-      const int k = lane + HX_TRK_LANES * j;
-      v[j] = (k < HX_REC_MIX) ? __ldcs(p + (size_t)k * stride) : make_double2(0.0, 0.0);
+      v[j] = (lane + HX_TRK_LANES * j < HX_REC_MIX) ? __ldcs(q) : make_double2(0.0, 0.0);
+      q += step;
     }
+    next += (size_t)HX_REC_MIX * stride;
   }
   /* rows (v = b / (a + b), a + b) of stash st in shared memory; st advances by one per call.
    * `slow` is set for the member's lanes when the stash holds anything the straight-line mix
-   * does not cover: a zero or NaN total other than thawed permafrost's (R_T0: empty until the
-   * first thaw, it keeps its test), or a dump into the deep ocean (a present R_DUMPx row) */
+   * does not cover: a total that is not an ordinary positive number -- other than the two that
+   * are zero for decades and keep their test (R_T0, thawed permafrost before the first thaw;
+   * R_OA, the ocean -> air flux while both surface boxes take carbon up) --, or a dump into the
+   * deep ocean (a present R_DUMPx row) */
   __device__ __forceinline__ const double *stash(int st) {
     double *buf = sh + (st & 1) * (HX_REC_MIX * HX_REC_ROW);
-    if (staged != st) prefetch(st);
     bool odd = false;
 #pragma unroll
     for (int j = 0; j < (HX_REC_MIX + HX_TRK_LANES - 1) / HX_TRK_LANES; ++j) {
       const int k = lane + HX_TRK_LANES * j;
       if (k < HX_REC_MIX) {
         const double total = __dadd_rn(v[j].x, v[j].y);
-        /* v = b (1 / total), not b / total: the flux b is zero in a quarter of the rows, and a
-         * zero numerator sends the division through its slow path */
-        *reinterpret_cast<double2 *>(buf + k * HX_REC_ROW) =
-            make_double2((total != 0.0) ? __dmul_rn(v[j].y, 1.0 / total) : 0.0, total);
-        if (k == R_DUMP0 || k == R_DUMP1) odd = odd || (total == total);
-        else if (k != R_T0) odd = odd || !(fabs(total) > 0.0);
+        const bool dump = (k == R_DUMP0 || k == R_DUMP1); /* absent dumps carry a NaN flux */
+        double w;
+        if (__builtin_expect(total > 1e-290 && total < 1e290, 1)) {
+          w = __dmul_rn(v[j].y, rcp_ordinary(total));
+          odd = odd || dump;
+        } else {
+          /* b (1 / total), not b / total: a zero flux would send the division through its slow
+           * path */
+          w = (total != 0.0) ? __dmul_rn(v[j].y, 1.0 / total) : 0.0;
+          odd = odd || (dump ? (total == total) : !(total == 0.0 && (k == R_T0 || k == R_OA)));
+        }
+        *reinterpret_cast<double2 *>(buf + k * HX_REC_ROW) = make_double2(w, total);
       }
     }
     slow = __any_sync(mask, odd);
-    prefetch(st + 1);
+    prefetch();
     __syncwarp(mask);
     return buf;
   }
@@ -1427,14 +1453,12 @@ hx_track_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst
   const unsigned char *yc = d.YCNT + tile * (size_t)(HX_SLAB_YEARS * HX_BLOCK) + ln;
   const int nyears = r1 - r0;
   StagedRecord fetch;
-  fetch.rec = reinterpret_cast<const double2 *>(d.REC) + m;
   fetch.stride = (size_t)d.Mpad;
   fetch.sh = &sh[cm][0];
   fetch.lane = s;
   fetch.nst = yc[(nyears - 1) * HX_BLOCK];
   fetch.mask = ((1u << HX_TRK_LANES) - 1u) << (wm * HX_TRK_LANES);
-  fetch.staged = -1;
-  fetch.slow = true;
+  fetch.begin(reinterpret_cast<const double2 *>(d.REC) + m);
   const bool good = track_replay<HX_TRK_NS>(T, TK, fetch, yc, HX_BLOCK, nyears,
                                             C.start_year + r0 + 1, s * HX_TRK_NS,
                                             (s + 1) * HX_TRK_NS, C.tracking_date, C.track_every, C.track_nrec,
