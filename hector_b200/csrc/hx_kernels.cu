@@ -1424,7 +1424,7 @@ struct StagedRecord {
         } else {
           /* b (1 / total), not b / total: a zero flux would send the division through its slow
            * path */
-          w = (total != 0.0) ? __dmul_rn(v[j].y, 1.0 / total) : 0.0;
+          w = (total != 0.0 && total == total) ? __dmul_rn(v[j].y, 1.0 / total) : 0.0;
           odd = odd || (dump ? (total == total) : !(total == 0.0 && (k == R_T0 || k == R_OA)));
         }
         *reinterpret_cast<double2 *>(buf + k * HX_REC_ROW) = make_double2(w, total);
