@@ -1256,7 +1256,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_FLUX_INTERIOR, hf_int_out);
         EMIT(OUT_TIMESTEPS, (double)mb.timesteps);
         }
-        if (BIOMES) { /* <biome>.<name>: the biome's own pools and final NPP / RH */
+        if (BIOMES && ALLOUT) { /* <biome>.<name>: the biome's own pools and final NPP / RH */
           const int bf[BO_COUNT] = {BF_VEG, BF_DET, BF_SOIL, BF_PERMAFROST, BF_THAWED, BF_X_NPP, BF_X_RH};
           for (int ib = 0; ib < C.n_biomes; ++ib)
             for (int k = 0; k < BO_COUNT; ++k) {
@@ -1553,8 +1553,10 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
   if (d.BF) {
     if (d.constrained > 1) return launch_run_t<false, true, 2, true, true, true>(d, C, r0, r1, st);
     if (d.constrained) return launch_run_t<false, true, 2, true, true, false>(d, C, r0, r1, st);
-    /* no constraint, no lo_warming_ratio: the biome loops without the constraint machinery */
-    return launch_run_t<false, false, 2, true, true, false>(d, C, r0, r1, st);
+    /* no constraint, no lo_warming_ratio: the biome loops without the constraint machinery;
+     * CO2 / Tgav only: without the other outputs' code either */
+    return d.out_minimal ? launch_run_t<false, false, 2, false, true, false>(d, C, r0, r1, st)
+                         : launch_run_t<false, false, 2, true, true, false>(d, C, r0, r1, st);
   }
   if (d.T) { /* carbon tracking: the record-only builds */
     if (d.constrained) return launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st);
@@ -1575,9 +1577,13 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
   if (d.constrained > 1) /* an NBP constraint somewhere */
     return small ? launch_run_t<false, true, 2>(d, C, r0, r1, st)
                  : launch_run_t<false, true, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
-  if (d.constrained)     /* the other constraints, lo_warming_ratio: no NBP machinery */
+  if (d.constrained) {   /* the other constraints, lo_warming_ratio: no NBP machinery */
+    if (d.out_minimal)
+      return small ? launch_run_t<false, true, 2, false, false, false>(d, C, r0, r1, st)
+                   : launch_run_t<false, true, HX_RUN_MIN_CTAS, false, false, false>(d, C, r0, r1, st);
     return small ? launch_run_t<false, true, 2, true, false, false>(d, C, r0, r1, st)
                  : launch_run_t<false, true, HX_RUN_MIN_CTAS, true, false, false>(d, C, r0, r1, st);
+  }
   /* "small": at most one CTA per SM, i.e. every warp has a scheduler to itself -> the LAT build */
   /* (HX_NO_LAT=1 keeps small ensembles on the general build: sanitizer runs of that build) */
   static const bool no_lat = std::getenv("HX_NO_LAT") != nullptr;

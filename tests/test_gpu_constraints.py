@@ -240,3 +240,52 @@ def test_lo_warming_ratio_with_tas_and_co2_constraints_vs_oracle():
             else:
                 assert util.parity_err(got[v][i], ref, v) < TOL, (i, v)
     ens.close()
+
+
+def test_co2_tgav_only_builds_match_the_all_output_builds():
+    """constraint and biome runs that record only CO2 / Tgav take kernel builds without the other
+    outputs' code (like the plain runs): bit for bit what the all-output builds record"""
+    import hector_b200 as hb
+    tabs = util.scenarios()
+    M = 160
+    X = util.lhs(M, seed=11)
+    minimal = ["CO2_concentration", "global_tas"]
+
+    def run(outputs, make):
+        ens = make(outputs)
+        for j, n in enumerate(["S", "q10_rh", "beta", "diff"]):
+            if make is biomes and n in ("q10_rh", "beta"):  # biome-specific there
+                ens.setvar("boreal." + n, X[:, j])
+                ens.setvar("tropical." + n, X[::-1, j].copy())
+            else:
+                ens.setvar(n, X[:, j])
+        ens.run()
+        st, fy = ens.status()
+        got = ens.fetchvars(YEARS, minimal)
+        ens.close()
+        return st, fy, got
+
+    # constraints without NBP (the "combo" case holds one; drop it) + lo_warming_ratio
+    spec = {k: v for k, v in [c for c in util.ref_constraints() if c["name"] == "combo"][0]["spec"].items()
+            if k != "NBP_constrain"}
+    assert spec
+
+    def constrained(outputs):
+        ens = hb.Ensemble(M, tabs["ssp245"], outputs=outputs)
+        _apply(ens, spec)
+        ens.setvar("lo_warming_ratio", 1.6)
+        return ens
+
+    def biomes(outputs):
+        case = util.ref_biomes()[0]
+        ens = hb.Ensemble(M, tabs[case["scenario"]], outputs=outputs, biomes=list(case["biomes"]))
+        for b, vals in case["biomes"].items():
+            ens.set_biome(b, **vals)
+        return ens
+
+    for make in (constrained, biomes):
+        a = run(minimal, make)
+        b = run(minimal + ["RF_tot", "veg_c", "ocean_timesteps"], make)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        for v in minimal:
+            assert np.array_equal(a[2][v], b[2][v], equal_nan=True), (make.__name__, v)
