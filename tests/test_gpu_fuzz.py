@@ -152,3 +152,75 @@ def test_tracking_with_scenarios_constraints_and_all_parameters(seed, tdate):
     # same bound (observed 4e-12 and 1.1e-11; the default member's maps agree to 1e-14)
     assert wmap < TOL, wmap
     ens.close()
+
+
+GLOBAL_POOLS = dict(npp_flux0=56.2, veg_c=550.0, detritus_c=55.0, soil_c=917.0, permafrost_c=865.0)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_biome_configurations_with_constraints(seed):
+    """2-4 biomes in random creation order; per MEMBER: Dirichlet shares of the pools and of NPP,
+    all ten per-biome parameters, S, diff and sometimes a land-ocean ratio; sometimes a CO2 / NBP
+    / tas constraint on top -- totals, the per-biome outputs of every biome and the failing
+    year against the oracle (tools/sweep_biomes_vs_ref.py holds the oracle bit-identical to the
+    unmodified reference on draws of this kind)."""
+    from oracle import port
+    import hector_b200 as hb
+    rng = np.random.default_rng(seed)
+    nb = int(rng.integers(2, 5))
+    names = [str(n) for n in rng.permutation(["tundra", "boreal", "midlat", "amazon", "desert"])[:nb]]
+    scn = SSPS[int(rng.integers(8))]
+    raw = util.scenarios()[scn]
+    M = 12
+    shares = rng.dirichlet(np.ones(nb) * 3.0, M)        # [M, nb]
+    pfshare = rng.dirichlet(np.ones(nb), M)
+    pfshare[rng.random(M) < 0.4, int(rng.integers(nb))] = 0.0
+    pfshare /= pfshare.sum(axis=1, keepdims=True)
+    per = {b: dict(beta=rng.uniform(0.1, 0.9, M), q10_rh=rng.uniform(1.0, 2.8, M),
+                   warmingfactor=rng.uniform(0.6, 2.4, M), f_nppv=rng.uniform(0.25, 0.45, M),
+                   f_nppd=rng.uniform(0.4, 0.55, M), f_litterd=rng.uniform(0.9, 1.0, M),
+                   rh_ch4_frac=rng.uniform(0.0, 0.06, M), pf_mu=rng.uniform(1.2, 2.2, M),
+                   pf_sigma=rng.uniform(0.7, 1.3, M), fpf_static=rng.uniform(0.5, 0.9, M))
+           for b in names}
+    for ib, b in enumerate(names):
+        for k, g in GLOBAL_POOLS.items():
+            per[b][k] = g * (pfshare[:, ib] if k == "permafrost_c" else shares[:, ib])
+    S, diff = rng.uniform(1.8, 5.0, M), rng.uniform(0.5, 2.5, M)
+    lo = np.where(rng.random(M) < 0.3, rng.uniform(0.9, 1.8, M), 0.0)
+    spec = {}
+    if rng.random() < 0.7:
+        _, _, base, _, _ = port.run_member(raw)
+        spec = _random_spec(rng, base, port, ["NBP_constrain", "CO2_constrain", "tas_constrain"])
+    own = ["%s.%s" % (b, v) for b in names for v in port.BIOME_OUT_NAMES]
+    totals = ["CO2_concentration", "global_tas", "veg_c", "detritus_c", "soil_c", "permafrost_c",
+              "thawedp_c", "NBP", "NPP", "RH", "land_tas", "ocean_timesteps"]
+    ens = hb.Ensemble(M, raw, outputs=totals + own, biomes=names)
+    for b in names:
+        ens.set_biome(b, **per[b])
+    ens.setvar("S", S); ens.setvar("diff", diff); ens.setvar("lo_warming_ratio", lo)
+    for name, d in spec.items():
+        ens.setvar_series(name, sorted(d), [d[y] for y in sorted(d)])
+    ens.run()
+    st, fy = ens.status()
+    got = ens.fetchvars(YEARS, totals + own)
+    worst, nfail = {}, 0
+    for i in range(M):
+        p = port.default_params()
+        p.set_biomes({b: {k: float(v[i]) for k, v in per[b].items()} for b in names})
+        ost, ofy, out, bio = port.run_member_biomes(raw, p, spec, S=S[i], diff=diff[i],
+                                                    lo_warming_ratio=lo[i])
+        nfail += ost != 0
+        _compare(port, got, st, fy, i, ost, ofy, out, totals, worst, scn)
+        n = 555 if not ost else ofy - 1746
+        for ib, b in enumerate(names):
+            for k, v in enumerate(port.BIOME_OUT_NAMES):
+                # a biome's thawed pool and permafrost answer the temperature like the totals do
+                e = util.parity_err(got["%s.%s" % (b, v)][i][:n], bio[ib, k][:n], v) if n else 0.0
+                key = "biome." + v
+                worst[key] = max(worst.get(key, 0.0), e)
+    print(scn, names, "constraints", sorted(spec), "failed members", nfail,
+          {k: "%.2g" % e for k, e in sorted(worst.items(), key=lambda kv: -kv[1])[:6]})
+    bad = {k: e for k, e in worst.items() if e > TOL and k != "biome.thawedp_c"}
+    assert not bad, bad
+    assert worst["biome.thawedp_c"] < 10 * TOL, worst["biome.thawedp_c"]
+    ens.close()
