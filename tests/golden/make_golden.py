@@ -100,8 +100,8 @@ def tseries_get(series, t):
     return y0 + (t - x0) * (y1 - y0) / (x1 - x0)
 
 
-def scenario_table(scn):
-    ini_path = os.path.join(REF, "inst/input/hector_%s.ini" % scn)
+def scenario_table(scn, ini_path=None):
+    ini_path = ini_path or os.path.join(REF, "inst/input/hector_%s.ini" % scn)
     ini = parse_ini(ini_path)
     start, end = int(ini["core"]["startDate"]), int(ini["core"]["endDate"])
     tab = np.zeros((end - start + 1, len(RAW)))
@@ -561,8 +561,42 @@ def make_allparams():
                         values=np.array(vals))
 
 
+LUC_PULSE_INI = os.path.join(REF, "tests/testthat/input/luc_pulse.ini")
+# what luc_pulse.ini sets differently from the shipped scenario inis (oracle field: value)
+LUC_PULSE_PARAMS = dict(end_year=1850, beta=0.0, q10_rh=1.0, npp_flux0=55.9, permafrost_c=0.0,
+                        soil_c=1782.0, S=2.7, diff=2.4, rho_bc=0.0508, rho_oc=-.00621,
+                        rho_so2=-.00000724, rho_nh3=-.00208)
+
+
+def make_luc_pulse():
+    """ref_luc_pulse.npz: the reference's own LUC-pulse case (tests/testthat/test_pulse.R with
+    tests/testthat/input/luc_pulse.ini: no emissions, beta = 0, Q10 = 1, no permafrost, a run
+    that ends in 1850, one land-use pulse in 1800) run by the UNMODIFIED reference, with the
+    dense input table an independent reading of its csv yields."""
+    from oracle import ref
+    tab, ini = scenario_table(None, LUC_PULSE_INI)
+    for k, v in LUC_PULSE_PARAMS.items():   # the table above is what the ini says
+        sec = {"end_year": None, "S": "temperature", "diff": "temperature"}.get(k, "simpleNbox")
+        if k.startswith("rho_"):
+            sec = "forcing"
+        if sec:
+            assert float(ini[sec][k]) == v, (k, ini[sec][k], v)
+    ny = int(ini["core"]["endDate"]) - int(ini["core"]["startDate"])
+    variables = REF_VARS + ["luc_emissions", "NPP", "RH"]
+    ok, err, o, _ = ref.run_member(LUC_PULSE_INI, {}, variables, nyears=ny)
+    assert ok, err
+    assert not np.isnan(o).any()
+    np.savez_compressed(os.path.join(OUT, "ref_luc_pulse.npz"), table=tab,
+                        param_names=np.array(list(LUC_PULSE_PARAMS)),
+                        param_values=np.array(list(LUC_PULSE_PARAMS.values()), dtype=np.float64),
+                        variables=np.array(variables + ["ocean_timesteps"]), values=o)
+    print("luc_pulse: veg_c 1799 %.9f 1801 %.9f" % (o[variables.index("veg_c")][53], o[variables.index("veg_c")][55]))
+
+
 if __name__ == "__main__":
-    if "allparams" in sys.argv[1:]:
+    if "luc_pulse" in sys.argv[1:]:
+        make_luc_pulse()
+    elif "allparams" in sys.argv[1:]:
         make_allparams()
     elif "biomes" in sys.argv[1:]:
         make_biomes()
@@ -579,3 +613,4 @@ if __name__ == "__main__":
         make_extra_outputs()
         make_biomes()
         make_allparams()
+        make_luc_pulse()

@@ -622,3 +622,47 @@ def test_extra_outputs_vs_reference_golden(case):
         bare.fetch("RF_O3_trop", [1755.0])
     bare.close()
     ens.close()
+
+
+def test_luc_pulse_case_of_the_reference():
+    """tests/testthat/test_pulse.R: no emissions, beta = 0, Q10 = 1, no permafrost, a run that
+    ends in 1850 (one 16-year slab short of seven), one land-use pulse in 1800 -- against the
+    unmodified reference's run of input/luc_pulse.ini (tests/golden/ref_luc_pulse.npz), with the
+    reference test's own assertions, from tables and from the ini file itself"""
+    import os
+    import hector_b200 as hb
+    case = util.ref_luc_pulse()
+    outs = [v for v in case["values"] if v in hb.OUTPUT_VARIABLES]
+    years = _years(1746, 1850)
+    ens = hb.Ensemble(3, case["table"], end_year=1850, outputs=outs)
+    for k, v in case["params"].items():
+        if k != "end_year":
+            ens.setvar(k, v)
+    ens.run()
+    assert (ens.status()[0] == 0).all()
+    got = ens.fetchvars(years, outs)
+    worst = {}
+    for v in outs:
+        ref = case["values"][v]
+        assert np.array_equal(got[v][0], got[v][2])
+        if v == "ocean_timesteps":
+            assert np.array_equal(got[v][0], ref)
+        else:
+            worst[v] = util.parity_err(got[v][0], ref, v)
+    print({k: "%.2g" % e for k, e in sorted(worst.items(), key=lambda kv: -kv[1])[:5]})
+    assert max(worst.values()) < TOL, worst
+    assert (got["permafrost_c"] == 0).all() and (got["thawedp_c"] == 0).all()
+    veg = got["veg_c"][0]
+    assert (np.diff(veg[1750 - 1746:1800 - 1746]) < 1e-6).all()
+    assert (np.diff(veg[1801 - 1746:1851 - 1746]) < 1e-6).all()
+    from tests.test_ini_reader_cpu import INPUT_DIRS
+    ini = [os.path.join(d, "testthat", "luc_pulse.ini") for d in INPUT_DIRS]
+    ini = [p for p in ini if os.path.exists(p)]
+    if ini:
+        e2 = hb.Ensemble.from_ini(ini[0], 2, outputs=outs)
+        e2.run()
+        g2 = e2.fetchvars(years, outs)
+        for v in outs:
+            assert np.array_equal(g2[v][0], got[v][0]), v
+        e2.close()
+    ens.close()

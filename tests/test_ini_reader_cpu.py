@@ -130,3 +130,28 @@ def test_biome_ini_parses(tmp_path):
     ini = biome_ini(tmp_path, util.ref_biomes()[1])
     assert L.hx_ini_read(ini.encode(), C.byref(y0), C.byref(y1), None, 0) == 0, L.hx_last_error(None)
     assert (y0.value, y1.value) == (1745, 2300)
+
+
+def test_luc_pulse_ini_of_the_reference():
+    """tests/testthat/input/luc_pulse.ini: a run that ends in 1850, natural emissions given as
+    `CH4N[1750]=223` entries instead of csv columns, a csv with constraint columns nobody asks
+    for -- the table equals the independent reading in tests/golden/ref_luc_pulse.npz"""
+    L = need_lib()
+    ini = os.path.join(input_dir(), "testthat", "luc_pulse.ini")
+    if not os.path.exists(ini):
+        ini = "/root/reference/tests/testthat/input/luc_pulse.ini"
+    if not os.path.exists(ini):
+        pytest.skip("luc_pulse.ini not available")
+    case = util.ref_luc_pulse()
+    s, e = C.c_int32(), C.c_int32()
+    assert L.hx_ini_read(ini.encode(), C.byref(s), C.byref(e), None, 0) == 0, L.hx_last_error(None)
+    assert (s.value, e.value) == (1745, 1850)
+    tab = np.empty((106, 44))
+    assert L.hx_ini_read(ini.encode(), None, None, tab.ctypes.data_as(C.POINTER(C.c_double)), 106) == 0
+    assert np.array_equal(tab, case["table"])
+    for k, v in case["params"].items():
+        if k == "end_year":
+            continue
+        out = C.c_double()
+        assert L.hx_ini_scalar(ini.encode(), k.encode(), C.byref(out)) == 0, k
+        assert out.value == v, (k, out.value, v)

@@ -266,3 +266,22 @@ def test_all_parameters_at_once_against_reference(case):
     assert st == 0
     for v, ref in case["values"].items():
         assert np.array_equal(out[port.OUT_NAMES.index(v)], ref), v
+
+
+def test_luc_pulse_case_of_the_reference():
+    """tests/testthat/test_pulse.R on input/luc_pulse.ini -- no emissions, beta = 0, Q10 = 1, no
+    permafrost, end date 1850, one land-use pulse in 1800: the restatement is bit-identical to
+    the unmodified reference on every variable, and the reference test's own assertions hold"""
+    from oracle import port
+    case = util.ref_luc_pulse()
+    st, fy, out, _, _ = port.run_member(case["table"], port.default_params(**case["params"]))
+    assert st == 0 and out.shape[1] == 105
+    for v, ref in case["values"].items():
+        if v in port.OUT_NAMES:
+            assert np.array_equal(out[port.OUT_NAMES.index(v)], ref), v
+    veg = out[port.OUT_NAMES.index("veg_c")]
+    assert (np.diff(veg[1750 - 1746:1800 - 1746]) < 1e-6).all()   # flat after the spin-up
+    assert (np.diff(veg[1801 - 1746:1851 - 1746]) < 1e-6).all()   # and after the pulse
+    assert veg[1799 - 1746] - veg[1801 - 1746] > 2.0              # the pulse itself
+    luc_in = case["table"][1:, 2]                                  # luc_emissions, 1746..1850
+    assert np.array_equal(case["values"]["luc_emissions"], luc_in) and luc_in.sum() > 0

@@ -136,6 +136,17 @@ def ref_biomes():
     return cases
 
 
+def ref_luc_pulse():
+    """the reference's own LUC-pulse case (tests/testthat/test_pulse.R, input/luc_pulse.ini) as
+    the unmodified reference ran it: input table [106, 44], the parameters the ini sets, outputs
+    over 1746..1850 (tests/golden/make_golden.py luc_pulse)"""
+    z = np.load(os.path.join(GOLDEN, "ref_luc_pulse.npz"))
+    params = {str(n): float(v) for n, v in zip(z["param_names"], z["param_values"])}
+    params["end_year"] = int(params["end_year"])
+    variables = [str(v) for v in z["variables"]]
+    return dict(table=z["table"], params=params, values=dict(zip(variables, z["values"])))
+
+
 def ref_allparams():
     """every scalar parameter perturbed at once (tests/golden/make_golden.py allparams)"""
     import json
