@@ -593,9 +593,32 @@ def make_luc_pulse():
     print("luc_pulse: veg_c 1799 %.9f 1801 %.9f" % (o[variables.index("veg_c")][53], o[variables.index("veg_c")][55]))
 
 
+PICONTROL_PARAMS = dict(soil_c=1782.0, permafrost_c=0.0, rho_bc=0.0508, rho_oc=-.00621,
+                        rho_so2=-.00000724, rho_nh3=-.00208)
+
+
+def make_picontrol():
+    """ref_picontrol.npz: inst/input/hector_picontrol.ini (every series a single `name[1745]=v`
+    entry, a one-entry CO2 constraint in the start year, no permafrost) run by the UNMODIFIED
+    reference (tests/testthat/test_inis.R: every shipped ini makes a core)."""
+    from oracle import ref
+    path = os.path.join(REF, "inst/input/hector_picontrol.ini")
+    tab, ini = scenario_table(None, path)
+    assert ini["simpleNbox"]["CO2_constrain[1745]"] == "277.15"
+    ok, err, o, _ = ref.run_member(path, {}, REF_VARS)
+    assert ok, err
+    np.savez_compressed(os.path.join(OUT, "ref_picontrol.npz"), table=tab,
+                        param_names=np.array(list(PICONTROL_PARAMS)),
+                        param_values=np.array(list(PICONTROL_PARAMS.values()), dtype=np.float64),
+                        variables=np.array(REF_VARS + ["ocean_timesteps"]), values=o)
+    print("picontrol: CO2 2300 %.12f Tgav 2300 %.3e" % (o[0][-1], o[1][-1]))
+
+
 if __name__ == "__main__":
     if "luc_pulse" in sys.argv[1:]:
         make_luc_pulse()
+    elif "picontrol" in sys.argv[1:]:
+        make_picontrol()
     elif "allparams" in sys.argv[1:]:
         make_allparams()
     elif "biomes" in sys.argv[1:]:
@@ -614,3 +637,4 @@ if __name__ == "__main__":
         make_biomes()
         make_allparams()
         make_luc_pulse()
+        make_picontrol()

@@ -666,3 +666,40 @@ def test_luc_pulse_case_of_the_reference():
             assert np.array_equal(g2[v][0], got[v][0]), v
         e2.close()
     ens.close()
+
+
+def test_picontrol_ini_of_the_reference():
+    """inst/input/hector_picontrol.ini through the library's own reader (constant inputs, a
+    one-entry CO2 constraint in the start year, no permafrost) against the unmodified
+    reference's run (tests/golden/ref_picontrol.npz), and from tables"""
+    import os
+    import hector_b200 as hb
+    from tests.test_ini_reader_cpu import INPUT_DIRS
+    case = util.ref_picontrol()
+    outs = list(case["values"])
+    ens = hb.Ensemble(2, case["table"], outputs=outs)
+    for k, v in case["params"].items():
+        ens.setvar(k, v)
+    for name, d in case["constraints"].items():
+        ens.setvar_series(name, sorted(d), [d[y] for y in sorted(d)])
+    ens.run()
+    assert (ens.status()[0] == 0).all()
+    got = ens.fetchvars(_years(), outs)
+    worst = {}
+    for v in outs:
+        if v == "ocean_timesteps":
+            assert np.array_equal(got[v][0], case["values"][v])
+        else:
+            worst[v] = util.parity_err(got[v][0], case["values"][v], v)
+    print({k: "%.2g" % e for k, e in sorted(worst.items(), key=lambda kv: -kv[1])[:5]})
+    assert max(worst.values()) < TOL, worst
+    ini = [os.path.join(d, "hector_picontrol.ini") for d in INPUT_DIRS]
+    ini = [p for p in ini if os.path.exists(p)]
+    if ini:
+        e2 = hb.Ensemble.from_ini(ini[0], 2, outputs=outs)
+        e2.run()
+        g2 = e2.fetchvars(_years(), outs)
+        for v in outs:
+            assert np.array_equal(g2[v][0], got[v][0]), v
+        e2.close()
+    ens.close()

@@ -155,3 +155,13 @@ def test_luc_pulse_ini_of_the_reference():
         out = C.c_double()
         assert L.hx_ini_scalar(ini.encode(), k.encode(), C.byref(out)) == 0, k
         assert out.value == v, (k, out.value, v)
+
+
+def test_picontrol_ini_of_the_reference():
+    """every series of hector_picontrol.ini is a single `name[1745]=value` entry"""
+    L = need_lib()
+    ini = os.path.join(input_dir(), "hector_picontrol.ini").encode()
+    case = util.ref_picontrol()
+    tab = np.empty((556, 44))
+    assert L.hx_ini_read(ini, None, None, tab.ctypes.data_as(C.POINTER(C.c_double)), 556) == 0
+    assert np.array_equal(tab, case["table"])

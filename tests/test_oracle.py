@@ -285,3 +285,17 @@ def test_luc_pulse_case_of_the_reference():
     assert veg[1799 - 1746] - veg[1801 - 1746] > 2.0              # the pulse itself
     luc_in = case["table"][1:, 2]                                  # luc_emissions, 1746..1850
     assert np.array_equal(case["values"]["luc_emissions"], luc_in) and luc_in.sum() > 0
+
+
+def test_picontrol_ini_of_the_reference():
+    """inst/input/hector_picontrol.ini (tests/testthat/test_inis.R): constant inputs given as
+    single entries, a one-entry CO2 constraint in the start year (it never binds: the first
+    simulated year is 1746), no permafrost -- bit-identical to the unmodified reference"""
+    from oracle import port
+    case = util.ref_picontrol()
+    st, fy, out = port.run_member_constrained(case["table"], case["constraints"], **case["params"])
+    assert st == 0
+    for v, ref in case["values"].items():
+        assert np.array_equal(out[port.OUT_NAMES.index(v)], ref), v
+    co2 = case["values"]["CO2_concentration"]
+    assert np.abs(co2 - 277.15).max() < 0.01 and np.abs(case["values"]["global_tas"]).max() < 1e-3

@@ -147,6 +147,16 @@ def ref_luc_pulse():
     return dict(table=z["table"], params=params, values=dict(zip(variables, z["values"])))
 
 
+def ref_picontrol():
+    """inst/input/hector_picontrol.ini as the unmodified reference ran it (make_golden.py
+    picontrol): input table [556, 44], the parameters the ini sets, 31 variables x 555 years"""
+    z = np.load(os.path.join(GOLDEN, "ref_picontrol.npz"))
+    params = {str(n): float(v) for n, v in zip(z["param_names"], z["param_values"])}
+    variables = [str(v) for v in z["variables"]]
+    return dict(table=z["table"], params=params, values=dict(zip(variables, z["values"])),
+                constraints={"CO2_constrain": {1745: 277.15}})
+
+
 def ref_allparams():
     """every scalar parameter perturbed at once (tests/golden/make_golden.py allparams)"""
     import json
