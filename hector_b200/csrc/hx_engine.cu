@@ -392,6 +392,24 @@ struct Engine {
     stage_bytes = bytes;
     return HX_OK;
   }
+  /* field f of a CTA-tiled device array for every member, API order, on the host */
+  int gather_field_host(const double *A, int f, int nfields, double *out) {
+    int rc = ensure_stage((size_t)M * sizeof(double));
+    if (rc) return rc;
+    k_gather_field<<<(M + 255) / 256, 256, 0, stream>>>(d_stage, A, f, nfields, d_dev_of_api, M);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, d_stage, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return HX_OK;
+  }
+  /* parameter pi of every member, API order */
+  int param_values(int pi, double *out) {
+    if (pvec_on_device_only[pi]) return gather_field_host(d_P, pi, PD_COUNT, out);
+    for (int i = 0; i < M; ++i) out[i] = pvec[pi].empty() ? pscalar[pi] : pvec[pi][i];
+    return HX_OK;
+  }
+  int start_row(int id, std::vector<double> &row);
+  int fetch_rows(int slot, const std::vector<int32_t> &yidx, int n_dates, double *out);
   int ensure_pinned(size_t bytes) {
     if (bytes <= pinned_bytes) return HX_OK;
     if (h_pinned) cudaFreeHost(h_pinned);
@@ -2046,6 +2064,87 @@ double hx_last_run_ms(hx_handle h) {
 
 double hx_current_date(hx_handle h) { return h ? h->cfg.start_year + h->cur_row : -1.0; }
 
+} /* extern "C" */
+
+/* What the reference answers for the START date (R's fetchvars keeps dates >= startdate,
+ * R/messages.R:66; tests/testthat/test_parameters.R:46 asks for the CO2 concentration of 1745):
+ * every component records its state at the start date once the spin-up is done -- the pools as
+ * the spin-up left them (simpleNbox.cpp:640-662 through record_state, ocean_component.cpp
+ * getData), the preindustrial concentrations (C0, M0, N0, PO3), zero for temperatures, heat
+ * fluxes, forcings, pH / pCO2 and the ocean uptake, the spin-up's last NPP and RH; NBP has no
+ * entry there (the reference throws "Interpolation requested but not allowed").  Pinned by
+ * tests/golden/ref_startdate.npz. */
+int Engine::start_row(int id, std::vector<double> &row) {
+  row.assign((size_t)M, 0.0);
+  std::vector<double> tmp((size_t)M);
+  int rc = HX_OK;
+  auto state = [&](int f) { return gather_field_host(d_S_snap, f, SI_COUNT, row.data()); };
+  if (id >= OUT_COUNT) { /* <biome>.<name> */
+    static const int bf[BO_COUNT] = {BF_VEG, BF_DET, BF_SOIL, BF_PERMAFROST, BF_THAWED, BF_X_NPP, BF_X_RH};
+    const int ib = (id - OUT_COUNT) / BO_COUNT, k = (id - OUT_COUNT) % BO_COUNT;
+    rc = gather_field_host(d_BF_snap, ib * BF_COUNT + bf[k], n_biomes * BF_COUNT, row.data());
+  } else switch (id) {
+    case OUT_CO2: rc = param_values(PI_C0, row.data()); break;
+    case OUT_CH4: rc = param_values(PI_M0, row.data()); break;
+    case OUT_N2O: rc = param_values(PI_N0, row.data()); break;
+    case OUT_O3: rc = param_values(PI_PO3, row.data()); break;
+    case OUT_ATMOS_C: rc = state(SI_ATMOS); break;
+    case OUT_VEG_C: rc = state(SI_VEG); break;
+    case OUT_DETRITUS_C: rc = state(SI_DET); break;
+    case OUT_SOIL_C: rc = state(SI_SOIL); break;
+    case OUT_PERMAFROST_C: rc = state(SI_PERMAFROST); break;
+    case OUT_THAWEDP_C: rc = state(SI_THAWED); break;
+    case OUT_EARTH_C: rc = state(SI_EARTH); break;
+    case OUT_CARBON_HL: rc = state(SI_BOX_HL); break;
+    case OUT_CARBON_LL: rc = state(SI_BOX_LL); break;
+    case OUT_CARBON_IO: rc = state(SI_BOX_IO); break;
+    case OUT_CARBON_DO: rc = state(SI_BOX_DO); break;
+    case OUT_NPP: rc = state(SI_X_NPP); break;
+    case OUT_RH: rc = state(SI_X_RH); break;
+    case OUT_OCEAN_C: { /* the run kernel's order of summation */
+      static const int box[4] = {SI_BOX_DO, SI_BOX_IO, SI_BOX_LL, SI_BOX_HL};
+      for (int b = 0; b < 4 && rc == HX_OK; ++b) {
+        rc = gather_field_host(d_S_snap, box[b], SI_COUNT, tmp.data());
+        for (int i = 0; i < M; ++i) row[i] = b ? row[i] + tmp[i] : tmp[i];
+      }
+      break;
+    }
+    case OUT_NBP:
+      return fail(HX_ERR_ARG, "NBP has no value at the start date (the reference: Interpolation "
+                              "requested but not allowed)");
+    default: break; /* temperatures, heat fluxes, forcings, pH, pCO2, uptake, rh_ch4: 0 */
+  }
+  if (rc) return rc;
+  /* a member whose spin-up failed has no start state */
+  std::vector<int32_t> st((size_t)Mpad);
+  CUDA_TRY(cudaMemcpy(st.data(), d_status_snap, (size_t)Mpad * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < M; ++i)
+    if (st[dev_of_api[i]] > 0) row[i] = std::numeric_limits<double>::quiet_NaN();
+  return HX_OK;
+}
+
+/* out[member][k] = recorded output `slot` of year index yidx[k], API member order */
+int Engine::fetch_rows(int slot, const std::vector<int32_t> &yidx, int n_dates, double *out) {
+  int rc = ensure_stage((size_t)M * n_dates * sizeof(double));
+  if (rc) return rc;
+  if ((size_t)n_dates > yidx_cap) {
+    if (d_yidx) cudaFree(d_yidx);
+    d_yidx = nullptr;
+    yidx_cap = 0;
+    CUDA_TRY(cudaMalloc(&d_yidx, (size_t)n_dates * sizeof(int32_t)));
+    yidx_cap = n_dates;
+  }
+  CUDA_TRY(cudaMemcpyAsync(d_yidx, yidx.data(), (size_t)n_dates * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  const double *src = d_out + (size_t)slot * (nrow - 1) * Mpad;
+  dim3 grid((M + 31) / 32, (n_dates + 31) / 32), block(32, 8);
+  k_fetch_transpose<<<grid, block, 0, stream>>>(d_stage, src, d_yidx, nullptr, n_dates, M, (size_t)Mpad);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, d_stage, (size_t)M * n_dates * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return HX_OK;
+}
+
+extern "C" {
 int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates, double *out) {
   NvtxRange nvtx_("hx_fetch");
   if (!h || !name || !dates || !out || n_dates <= 0) return HX_ERR_ARG;
@@ -2060,35 +2159,27 @@ int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates
   if (slot < 0) return h->fail(HX_ERR_ARG, std::string(name) + " was not selected with hx_select_outputs");
   cudaSetDevice(h->cfg.device);
   std::vector<int32_t> yidx(n_dates);
+  bool want_start = false;
   for (int k = 0; k < n_dates; ++k) {
     const int r = (int)dates[k] - h->cfg.start_year;
-    if (r < 1 || r > h->cur_row)
-      return h->fail(HX_ERR_ARG, "date outside (start_year, current date]");
-    yidx[k] = r - 1;
+    if (r < 0 || r > h->cur_row)
+      return h->fail(HX_ERR_ARG, "date outside [start_year, current date]");
+    want_start = want_start || r == 0;
+    yidx[k] = r > 0 ? r - 1 : 0; /* the start date's column is filled in below */
   }
-  int rc = h->ensure_stage((size_t)h->M * n_dates * sizeof(double));
-  if (rc) return rc;
-  if ((size_t)n_dates > h->yidx_cap) {
-    if (h->d_yidx) cudaFree(h->d_yidx);
-    h->d_yidx = nullptr;
-    if (cudaMalloc(&h->d_yidx, (size_t)n_dates * sizeof(int32_t)) != cudaSuccess)
-      return h->fail(HX_ERR_CUDA, "cudaMalloc yidx");
-    h->yidx_cap = n_dates;
+  std::vector<double> row0;
+  if (want_start) {
+    const int rc0 = h->start_row(id, row0);
+    if (rc0) return rc0;
   }
-  cudaStream_t st = h->stream;
-  cudaError_t e = cudaMemcpyAsync(h->d_yidx, yidx.data(), (size_t)n_dates * sizeof(int32_t),
-                                  cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_fetch: ") + cudaGetErrorString(e));
-  const double *src = h->d_out + (size_t)slot * (h->nrow - 1) * h->Mpad;
-  dim3 grid((h->M + 31) / 32, (n_dates + 31) / 32), block(32, 8);
-  k_fetch_transpose<<<grid, block, 0, st>>>(h->d_stage, src, h->d_yidx, nullptr, n_dates, h->M,
-                                           (size_t)h->Mpad);
-  e = cudaGetLastError();
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(out, h->d_stage, (size_t)h->M * n_dates * sizeof(double),
-                        cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_fetch: ") + cudaGetErrorString(e));
+  if (h->cur_row > 0) { /* otherwise nothing but the start date can have been asked for */
+    const int rc = h->fetch_rows(slot, yidx, n_dates, out);
+    if (rc) return rc;
+  }
+  if (want_start)
+    for (int k = 0; k < n_dates; ++k)
+      if ((int)dates[k] == h->cfg.start_year)
+        for (int i = 0; i < h->M; ++i) out[(size_t)i * n_dates + k] = row0[i];
   return HX_OK;
 }
 

@@ -199,8 +199,13 @@ int hx_synchronize(hx_handle h);
 int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *const *names,
                   double *const *outs, int32_t segments);
 
-/* out[member][date] (row-major, n_members x n_dates) on the host; dates before/at
- * start_year or beyond the current date are an error, as in the reference.
+/* out[member][date] (row-major, n_members x n_dates) on the host; dates before start_year or
+ * beyond the current date are an error, as in the reference.  The START date itself is a valid
+ * date for the recorded variables, as it is there (R's fetchvars keeps dates >= startdate,
+ * R/messages.R:66): the pools as the spin-up left them, the preindustrial concentrations
+ * (C0, M0, N0, PO3), zero for temperatures, heat fluxes, forcings, pH / pCO2 and the ocean
+ * uptake, the spin-up's last NPP and RH; NBP has no entry there (HX_ERR_ARG; the reference
+ * throws).  The derived outputs below start in start_year + 1.
  * Besides the recorded variables, hx_fetch answers for the outputs that need no kernel -- it
  * derives them from the scenario series, per-member parameters and recorded outputs with
  * ForcingComponent::run's expressions (forcing_component.cpp:410-524): RF_BC, RF_OC, RF_SO2,

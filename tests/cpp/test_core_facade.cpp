@@ -79,7 +79,11 @@ int main(int argc, char **argv) {
   /* ---- errors: same places as the reference, and the core stays usable ---- */
   EXPECT(throws([&] { core->sendMessage(M_GETDATA, "no_such_variable", message_data(2000.0)); }));
   EXPECT(throws([&] { core->sendMessage(M_GETDATA, "global_tas", message_data(2301.0)); }));
-  EXPECT(throws([&] { core->sendMessage(M_GETDATA, "global_tas", message_data(1745.0)); }));
+  EXPECT(throws([&] { core->sendMessage(M_GETDATA, "global_tas", message_data(1744.0)); }));
+  /* the start date is a valid date, as in the reference (tests/testthat/test_parameters.R:46):
+   * the preindustrial concentration, a zero temperature */
+  EXPECT((double)core->sendMessage(M_GETDATA, "global_tas", message_data(1745.0)) == 0.0);
+  EXPECT((double)core->sendMessage(M_GETDATA, "CO2_concentration", message_data(1745.0)) == 277.15);
   EXPECT(throws([&] { core->sendMessage("noSuchMessage", "global_tas"); }));
   EXPECT(throws([&] { core->sendMessage(M_SETDATA, "S", message_data(unitval(3.0, U_PGC))); }));
   EXPECT(throws([&] { tas.value(U_PGC); }));

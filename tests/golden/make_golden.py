@@ -614,8 +614,53 @@ def make_picontrol():
     print("picontrol: CO2 2300 %.12f Tgav 2300 %.3e" % (o[0][-1], o[1][-1]))
 
 
+# (component, ini name, engine name, value) of the perturbed start-date case
+STARTDATE_PERTURBED = [("simpleNbox", "C0", "C0", 285.0), ("simpleNbox", "veg_c", "veg_c", 600.0),
+                       ("simpleNbox", "detritus_c", "detritus_c", 50.0),
+                       ("simpleNbox", "soil_c", "soil_c", 1000.0),
+                       ("simpleNbox", "permafrost_c", "permafrost_c", 700.0),
+                       ("simpleNbox", "npp_flux0", "npp_flux0", 50.0),
+                       ("simpleNbox", "beta", "beta", 0.4), ("simpleNbox", "q10_rh", "q10_rh", 2.0),
+                       ("ocean", "preind_surface_c", "preind_surface_c", 950.0),
+                       ("ocean", "preind_interdeep_c", "preind_interdeep_c", 36000.0),
+                       ("CH4", "M0", "M0", 700.0), ("N2O", "N0", "N0", 270.0),
+                       ("ozone", "PO3", "PO3", 28.0), ("temperature", "S", "S", 4.0)]
+
+
+def make_startdate():
+    """ref_startdate.npz: what the UNMODIFIED reference answers for the START date (R's
+    fetchvars keeps dates >= startdate, R/messages.R:66; tests/testthat/test_parameters.R:46
+    fetches the CO2 concentration of 1745): the post-spin-up pools, the preindustrial
+    concentrations, zeros for temperatures / forcings / fluxes, the spin-up's last NPP and RH --
+    and which variables have no entry there (NaN in the fixture: NBP).  Two cases: SSP2-4.5
+    defaults and a perturbed member; the core ran to 1760 before the fetch."""
+    from oracle import ref
+    names, vals = [], []
+    variables = REF_VARS + ["NPP", "RH", "gmst", "ocean_tas", "heatflux_mixed", "heatflux_interior"]
+    for case, over in (("default", []), ("perturbed", STARTDATE_PERTURBED)):
+        with ref.RefCore(os.path.join(REF, "inst/input/hector_ssp245.ini")) as core:
+            for comp, ini_name, _, v in over:
+                core.setdata(comp, ini_name, v)
+            core.prepare()
+            core.run(1760.0)
+            row = []
+            for v in variables:
+                try:
+                    row.append(core.fetch(v, 1745.0))
+                except ref.RefError:
+                    row.append(np.nan)
+            names.append(case); vals.append(row)
+            print(case, dict(zip(variables, row)))
+    np.savez_compressed(os.path.join(OUT, "ref_startdate.npz"), names=np.array(names),
+                        variables=np.array(variables), values=np.array(vals),
+                        perturbed_names=np.array([e for _, _, e, _ in STARTDATE_PERTURBED]),
+                        perturbed_values=np.array([v for _, _, _, v in STARTDATE_PERTURBED]))
+
+
 if __name__ == "__main__":
-    if "luc_pulse" in sys.argv[1:]:
+    if "startdate" in sys.argv[1:]:
+        make_startdate()
+    elif "luc_pulse" in sys.argv[1:]:
         make_luc_pulse()
     elif "picontrol" in sys.argv[1:]:
         make_picontrol()
@@ -638,3 +683,4 @@ if __name__ == "__main__":
         make_allparams()
         make_luc_pulse()
         make_picontrol()
+        make_startdate()

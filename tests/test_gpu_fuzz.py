@@ -218,6 +218,12 @@ def test_random_biome_configurations_with_constraints(seed):
                 e = util.parity_err(got["%s.%s" % (b, v)][i][:n], bio[ib, k][:n], v) if n else 0.0
                 key = "biome." + v
                 worst[key] = max(worst.get(key, 0.0), e)
+    # the start date (R's fetchvars keeps it): the biomes' post-spin-up pools add up to the totals
+    for v in ("veg_c", "soil_c", "permafrost_c"):
+        tot = ens.fetch(v, [1745.0])[:, 0]
+        parts = sum(ens.fetch("%s.%s" % (b, v), [1745.0])[:, 0] for b in names)
+        assert np.abs(tot - parts).max() <= 1e-12 * np.abs(tot).max(), v
+    assert np.abs(ens.fetch("permafrost_c", [1745.0])[:, 0] - GLOBAL_POOLS["permafrost_c"]).max() < 1e-9
     print(scn, names, "constraints", sorted(spec), "failed members", nfail,
           {k: "%.2g" % e for k, e in sorted(worst.items(), key=lambda kv: -kv[1])[:6]})
     bad = {k: e for k, e in worst.items() if e > TOL and k != "biome.thawedp_c"}

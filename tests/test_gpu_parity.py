@@ -703,3 +703,39 @@ def test_picontrol_ini_of_the_reference():
             assert np.array_equal(g2[v][0], got[v][0]), v
         e2.close()
     ens.close()
+
+
+def test_start_date_values_like_the_reference():
+    """fetchvars at the START date (R/messages.R:66 keeps dates >= startdate;
+    tests/testthat/test_parameters.R:40-68 "Initial CO2 concentration equals preindustrial"):
+    the post-spin-up pools, the preindustrial concentrations, zeros, the spin-up's last NPP / RH
+    against the unmodified reference (tests/golden/ref_startdate.npz), before and after the run,
+    alone and mixed with later dates; NBP has no entry there, as in the reference."""
+    import hector_b200 as hb
+    cases = util.ref_startdate()
+    outs = [v for v in cases[0]["values"] if v in hb.OUTPUT_VARIABLES]
+    ens = hb.Ensemble(2, util.scenarios()["ssp245"], outputs=outs)
+    for k, v in cases[1]["params"].items():
+        ens.setvar(k, np.array([ens.getvar(k)[0], v]))
+    ens.prepare()
+    before = {v: ens.fetch(v, [1745.0]) for v in outs if v != "NBP"}
+    with pytest.raises(hb.HxError):
+        ens.fetch("CO2_concentration", [1746.0])       # not run yet
+    ens.run(1760)
+    for v in outs:
+        if v == "NBP":
+            with pytest.raises(hb.HxError, match="start date"):
+                ens.fetch(v, [1745.0])
+            continue
+        got = ens.fetch(v, [1750.0, 1745.0, 1760.0])
+        later = ens.fetch(v, [1750.0, 1760.0])
+        assert np.array_equal(got[:, [0, 2]], later), v
+        assert np.array_equal(got[:, 1:2], before[v]), v
+        for i, case in enumerate(cases):
+            ref = case["values"][v]
+            assert abs(got[i, 1] - ref) <= 1e-10 * max(abs(ref), 1e-3), (case["name"], v, got[i, 1], ref)
+    # the reference's own test: the initial concentration IS the preindustrial parameter
+    assert np.array_equal(ens.fetch("CO2_concentration", [1745.0])[:, 0], ens.getvar("C0"))
+    with pytest.raises(hb.HxError):
+        ens.fetch("CO2_concentration", [1744.0])
+    ens.close()

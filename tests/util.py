@@ -157,6 +157,16 @@ def ref_picontrol():
                 constraints={"CO2_constrain": {1745: 277.15}})
 
 
+def ref_startdate():
+    """what the unmodified reference answers for the start date (make_golden.py startdate):
+    [{name, params {engine name: value}, values {variable: value or NaN = no entry}}]"""
+    z = np.load(os.path.join(GOLDEN, "ref_startdate.npz"))
+    variables = [str(v) for v in z["variables"]]
+    pert = {str(n): float(v) for n, v in zip(z["perturbed_names"], z["perturbed_values"])}
+    return [dict(name=str(n), params=pert if str(n) == "perturbed" else {},
+                 values=dict(zip(variables, z["values"][i]))) for i, n in enumerate(z["names"])]
+
+
 def ref_allparams():
     """every scalar parameter perturbed at once (tests/golden/make_golden.py allparams)"""
     import json
