@@ -2153,6 +2153,27 @@ int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates
     int rc = HX_OK;
     if (h->fetch_derived(name, dates, n_dates, out, rc)) return rc;
   }
+  {
+    /* an INPUT series read back -- getData of the component that owns it (simpleNbox.cpp:650-662
+     * ffi / daccs / luc, ch4_component.cpp, n2o_component.cpp, oh_component.cpp, bc / oc / so2 /
+     * nh3, halocarbon_component.cpp "<gas>_emissions"): tests/testthat/test_pulse.R fetches
+     * luc_emissions.  Any year of the run, start date included; a constraint series answers NaN
+     * (the reference's MISSING_FLOAT) where it has no entry. */
+    const int si = Engine::find_raw(name);
+    const int ci = si < 0 ? Engine::find_constraint(name) : -1;
+    if (si >= 0 || ci >= 0) {
+      for (int k = 0; k < n_dates; ++k) {
+        const int r = (int)dates[k] - h->cfg.start_year;
+        if (r < 0 || r >= h->nrow) return h->fail(HX_ERR_ARG, "date outside [start_year, end_year]");
+        for (int i = 0; i < h->M; ++i) {
+          const int sc = h->member_scen[i];
+          out[(size_t)i * n_dates + k] = si >= 0 ? h->raw[sc][(size_t)si * h->nrow + r]
+                                                 : h->cons[sc][(size_t)ci * h->nrow + r];
+        }
+      }
+      return HX_OK;
+    }
+  }
   const int id = h->find_out(name);
   if (id < 0) return h->fail(HX_ERR_ARG, std::string("unknown output variable: ") + name);
   const int slot = h->d.out_slot[id];

@@ -206,6 +206,9 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
  * (C0, M0, N0, PO3), zero for temperatures, heat fluxes, forcings, pH / pCO2 and the ocean
  * uptake, the spin-up's last NPP and RH; NBP has no entry there (HX_ERR_ARG; the reference
  * throws).  The derived outputs below start in start_year + 1.
+ * An INPUT series is read back under its own name (ffi_emissions, luc_emissions, CH4_emissions,
+ * <gas>_emissions, SV, RF_albedo ...; any year of the run) like the getData of the component
+ * that owns it; a constraint series (CO2_constrain ...) answers NaN where it has no entry.
  * Besides the recorded variables, hx_fetch answers for the outputs that need no kernel -- it
  * derives them from the scenario series, per-member parameters and recorded outputs with
  * ForcingComponent::run's expressions (forcing_component.cpp:410-524): RF_BC, RF_OC, RF_SO2,

@@ -655,6 +655,13 @@ def test_luc_pulse_case_of_the_reference():
     veg = got["veg_c"][0]
     assert (np.diff(veg[1750 - 1746:1800 - 1746]) < 1e-6).all()
     assert (np.diff(veg[1801 - 1746:1851 - 1746]) < 1e-6).all()
+    # "the LUC pulse itself should be equal to what's in the input file": inputs read back
+    luc = ens.fetch("luc_emissions", np.arange(1745.0, 1851.0))
+    assert np.array_equal(luc[1], case["table"][:, 2]) and luc.sum() > 0
+    assert np.array_equal(luc[0, 1:], case["values"]["luc_emissions"])
+    assert np.isnan(ens.fetch("CO2_constrain", [1800.0])).all()     # no entry: MISSING_FLOAT
+    with pytest.raises(hb.HxError):
+        ens.fetch("luc_emissions", [1851.0])
     from tests.test_ini_reader_cpu import INPUT_DIRS
     ini = [os.path.join(d, "testthat", "luc_pulse.ini") for d in INPUT_DIRS]
     ini = [p for p in ini if os.path.exists(p)]
