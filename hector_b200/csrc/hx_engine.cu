@@ -476,6 +476,7 @@ struct Engine {
    *   <gas>_concentration
    * Returns 1 if `name` is one of them (rc holds the result code), 0 otherwise. */
   int fetch_derived(const char *name, const double *dates, int n_dates, double *out, int &rc);
+  int fetch_functions(const char *name, const double *dates, int n_dates, double *out, int &rc);
 
   void free_device() {
     void *ptrs[] = {d_GP, d_GF, d_GF_snap, d_scen_gas, d_BP, d_BF, d_BF_snap, d_P, d_S, d_S_snap, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
@@ -939,6 +940,155 @@ int Engine::fetch_derived(const char *name, const double *dates, int n_dates, do
       out[(size_t)i * n_dates + k] = v;
     }
   }
+  return 1;
+}
+
+/* The rest of the reference's outputstream variables that are plain functions of recorded
+ * outputs, parameters and input series -- evaluated at fetch time with the reference's
+ * expressions, no kernel involved (returns 0 when `name` is none of them):
+ *   HL_sst, LL_sst   box temperature the year's chemistry ran at: last year's sst + 18 + deltaT
+ *                    (oceanbox.cpp:97-99; ocean_component.cpp record_state)
+ *   HL_DIC, LL_DIC   convertToDIC of the box's carbon (ocean_csys.cpp:403-408)
+ *   DIC, pH, PCO2    area-weighted surface means, part_low x LL + part_high x HL
+ *                    (ocean_component.cpp getData)
+ *   ML_ocean_c       LL + HL carbon
+ *   TAU_OH           OH lifetime (oh_component.cpp:137-174) from last year's CH4
+ *   f_frozen         frozen permafrost fraction (simpleNbox-runtime.cpp:1012-1024) from last
+ *                    year's land temperature; single biome only
+ * Each needs the outputs it is a function of to be recorded (hx_select_outputs).  Pinned by
+ * tests/golden/ref_outputs_more.npz.  Not served: HL_CO3 / LL_CO3 / CO3, HL_ocean_uptake /
+ * LL_ocean_uptake, rh_det, rh_soil (they would need state the run kernel does not keep). */
+int Engine::fetch_functions(const char *name, const double *dates, int n_dates, double *out, int &rc) {
+  enum Kind { F_NONE, F_SST_HL, F_SST_LL, F_DIC_HL, F_DIC_LL, F_DIC, F_PH, F_PCO2, F_ML, F_TAU_OH, F_FROZEN };
+  static const struct { const char *n; Kind k; } tab[] = {
+      {"HL_sst", F_SST_HL}, {"LL_sst", F_SST_LL}, {"HL_DIC", F_DIC_HL}, {"LL_DIC", F_DIC_LL},
+      {"DIC", F_DIC}, {"pH", F_PH}, {"PCO2", F_PCO2}, {"ML_ocean_c", F_ML}, {"TAU_OH", F_TAU_OH},
+      {"f_frozen", F_FROZEN}};
+  Kind kind = F_NONE;
+  for (const auto &e : tab)
+    if (!strcmp(name, e.n)) kind = e.k;
+  if (kind == F_NONE) return 0;
+  rc = HX_OK;
+  int rmax = 0;
+  for (int k = 0; k < n_dates; ++k) {
+    const int r = (int)dates[k] - cfg.start_year;
+    if (r < 1 || r > cur_row) {
+      rc = fail(HX_ERR_ARG, "date outside (start_year, current date]");
+      return 1;
+    }
+    rmax = std::max(rmax, r);
+  }
+  hx_engine *self = static_cast<hx_engine *>(this);
+  const size_t N = (size_t)M * n_dates;
+  /* a recorded output at the requested dates, `back` years earlier (the start date included) */
+  auto rec = [&](const char *var, int back, std::vector<double> &v) {
+    std::vector<double> d2(n_dates);
+    for (int k = 0; k < n_dates; ++k) d2[k] = dates[k] - back;
+    v.resize(N);
+    return hx_fetch(self, var, d2.data(), n_dates, v.data());
+  };
+  auto param = [&](int pi, std::vector<double> &v) {
+    v.resize(M);
+    return param_values(pi, v.data());
+  };
+  const double part_high = 0.15, part_low = 1 - part_high; /* ocean_component.hpp:89-90 */
+  auto to_dic = [](double carbon, double volume) { /* ocean_csys.cpp:403-408, umol/kg */
+    const double dic = ((carbon * 1e15) * (1.0 / 12.01) * (1.0 / 1027.0) * (1.0 / volume));
+    return dic * 1e6;
+  };
+  std::vector<double> a, b;
+  switch (kind) {
+    case F_SST_HL: case F_SST_LL: {
+      if ((rc = rec("sst", 1, a))) return 1;
+      const double deltaT = kind == F_SST_HL ? -16.4 : 2.9; /* ocean_component.cpp:291, 300 */
+      for (size_t q = 0; q < N; ++q) out[q] = a[q] + 18.0 + deltaT; /* MEAN_TOS_TEMP, oceanbox.hpp:35 */
+      break;
+    }
+    case F_DIC_HL: case F_DIC_LL: {
+      if ((rc = rec(kind == F_DIC_HL ? "HL_ocean_c" : "LL_ocean_c", 0, a))) return 1;
+      const double vol = kind == F_DIC_HL ? C.vol_HL : C.vol_LL;
+      for (size_t q = 0; q < N; ++q) out[q] = to_dic(a[q], vol);
+      break;
+    }
+    case F_DIC:
+      if ((rc = rec("LL_ocean_c", 0, a)) || (rc = rec("HL_ocean_c", 0, b))) return 1;
+      for (size_t q = 0; q < N; ++q)
+        out[q] = part_low * to_dic(a[q], C.vol_LL) + part_high * to_dic(b[q], C.vol_HL);
+      break;
+    case F_PH: case F_PCO2:
+      if ((rc = rec(kind == F_PH ? "LL_pH" : "LL_PCO2", 0, a)) ||
+          (rc = rec(kind == F_PH ? "HL_pH" : "HL_PCO2", 0, b)))
+        return 1;
+      for (size_t q = 0; q < N; ++q) out[q] = part_low * a[q] + part_high * b[q];
+      break;
+    case F_ML:
+      if ((rc = rec("LL_ocean_c", 0, a)) || (rc = rec("HL_ocean_c", 0, b))) return 1;
+      for (size_t q = 0; q < N; ++q) out[q] = a[q] + b[q];
+      break;
+    case F_TAU_OH: {
+      std::vector<double> M0, TOH0, CCH4, CNOX, CCO, CNMVOC;
+      if ((rc = rec("CH4_concentration", 1, a)) || (rc = param(PI_M0, M0)) || (rc = param(PI_TOH0, TOH0)) ||
+          (rc = param(PI_CCH4, CCH4)) || (rc = param(PI_CNOX, CNOX)) || (rc = param(PI_CCO, CCO)) ||
+          (rc = param(PI_CNMVOC, CNMVOC)))
+        return 1;
+      for (int i = 0; i < M; ++i) {
+        const double *R = raw[member_scen[i]].data();
+        for (int k = 0; k < n_dates; ++k) {
+          const int r = (int)dates[k] - cfg.start_year;
+          const double previous_ch4 = a[(size_t)i * n_dates + k];
+          double toh = 0.0;
+          if (previous_ch4 != M0[i]) {
+            const double ta = CCH4[i] * ((1.0 * std::log(previous_ch4)) - std::log(M0[i]));
+            const double tb = CNOX[i] * ((1.0 * R[(size_t)RAW_NOX * nrow + r]) - R[(size_t)RAW_NOX * nrow]);
+            const double tc = CCO[i] * ((1.0 * R[(size_t)RAW_CO * nrow + r]) - R[(size_t)RAW_CO * nrow]);
+            const double td = CNMVOC[i] * ((1.0 * R[(size_t)RAW_NMVOC * nrow + r]) - R[(size_t)RAW_NMVOC * nrow]);
+            toh = ta + tb + tc + td;
+          }
+          out[(size_t)i * n_dates + k] = TOH0[i] * std::exp(-toh);
+        }
+      }
+      break;
+    }
+    case F_FROZEN: {
+      if (n_biomes > 1) {
+        rc = fail(HX_ERR_UNSUPPORTED, "f_frozen with more than one biome is not derived");
+        return 1;
+      }
+      /* the fraction only moves while there is permafrost left, so walk every year up to the last
+       * one asked for */
+      std::vector<double> yrs(rmax), T, P, wf, mu, sigma;
+      for (int r = 0; r < rmax; ++r) yrs[r] = cfg.start_year + r;
+      T.resize((size_t)M * rmax); P.resize((size_t)M * rmax);
+      if ((rc = hx_fetch(self, "land_tas", yrs.data(), rmax, T.data())) ||
+          (rc = hx_fetch(self, "permafrost_c", yrs.data(), rmax, P.data())) ||
+          (rc = param(PI_WARMINGFACTOR, wf)) || (rc = param(PI_PF_MU, mu)) || (rc = param(PI_PF_SIGMA, sigma)))
+        return 1;
+      const double root_two = 1.41421356237309504880168872420969807856967187537694;
+      std::vector<double> f(rmax + 1);
+      for (int i = 0; i < M; ++i) {
+        f[0] = 1.0;
+        for (int r = 1; r <= rmax; ++r) { /* slowparameval of year r sees the year before */
+          const double Tb = T[(size_t)i * rmax + r - 1] * wf[i], perm = P[(size_t)i * rmax + r - 1];
+          f[r] = f[r - 1];
+          if (perm == perm && perm != 0.0) {
+            double cur = 1.0;
+            if (Tb > 0) cur = 1 - std::erfc(-((std::log(Tb) - mu[i]) / (sigma[i] * root_two))) / 2;
+            f[r] = cur;
+          } else if (!(perm == perm)) f[r] = perm;
+        }
+        for (int k = 0; k < n_dates; ++k) out[(size_t)i * n_dates + k] = f[(int)dates[k] - cfg.start_year];
+      }
+      break;
+    }
+    default: break;
+  }
+  /* a member that stopped reports nothing from its failing year on */
+  std::vector<int32_t> st(M), fy(M);
+  if ((rc = hx_member_status(self, st.data(), fy.data(), M))) return 1;
+  for (int i = 0; i < M; ++i)
+    if (st[i] > 0)
+      for (int k = 0; k < n_dates; ++k)
+        if (fy[i] <= (int)dates[k]) out[(size_t)i * n_dates + k] = std::nan("");
   return 1;
 }
 
@@ -2152,6 +2302,7 @@ int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates
   {
     int rc = HX_OK;
     if (h->fetch_derived(name, dates, n_dates, out, rc)) return rc;
+    if (h->fetch_functions(name, dates, n_dates, out, rc)) return rc;
   }
   {
     /* an INPUT series read back -- getData of the component that owns it (simpleNbox.cpp:650-662

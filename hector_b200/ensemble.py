@@ -67,8 +67,13 @@ VARIABLE_UNITS = {
     "HL_ocean_c": "Pg C", "LL_ocean_c": "Pg C", "IO_ocean_c": "Pg C", "DO_ocean_c": "Pg C",
     "RF_CH4": "W/m2", "RF_N2O": "W/m2", "rh_ch4": "Pg C/yr", "ocean_timesteps": "(unitless)",
     "NPP": "Pg C/yr", "RH": "Pg C/yr", "gmst": "degC", "ocean_tas": "degC",
-    "heatflux_mixed": "W/m2", "heatflux_interior": "W/m2"}
+    "heatflux_mixed": "W/m2", "heatflux_interior": "W/m2",
+    # functions of recorded outputs, evaluated at fetch time (FUNCTION_VARIABLES)
+    "HL_sst": "degC", "LL_sst": "degC", "HL_DIC": "umol/kg", "LL_DIC": "umol/kg", "DIC": "umol/kg",
+    "pH": "pH", "PCO2": "uatm", "ML_ocean_c": "Pg C", "TAU_OH": "Years", "f_frozen": "(unitless)"}
 VARIABLE_COMPONENT = {
+    "HL_sst": "ocean", "LL_sst": "ocean", "HL_DIC": "ocean", "LL_DIC": "ocean", "DIC": "ocean",
+    "pH": "ocean", "PCO2": "ocean", "ML_ocean_c": "ocean", "TAU_OH": "OH", "f_frozen": "simpleNbox",
     "CO2_concentration": "simpleNbox", "atmos_co2": "simpleNbox", "veg_c": "simpleNbox",
     "detritus_c": "simpleNbox", "soil_c": "simpleNbox", "permafrost_c": "simpleNbox",
     "thawedp_c": "simpleNbox", "earth_c": "simpleNbox", "NBP": "simpleNbox",
@@ -93,6 +98,16 @@ BIOME_PARAMETERS = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "npp_flux0"
 
 # per-biome outputs, selected and fetched as "<biome>.<name>" (simpleNbox.cpp:533-697)
 BIOME_OUTPUTS = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c", "NPP", "RH"]
+
+# The rest of the reference's outputstream variables that are plain functions of recorded outputs
+# (hx_fetch evaluates them on the host; each needs the outputs it depends on to be selected):
+# {variable: recorded outputs it needs}.  R's ALL_VARS() minus these and the lists above leaves
+# HL_CO3, LL_CO3, CO3, HL_ocean_uptake, LL_ocean_uptake, rh_det, rh_soil: not served.
+FUNCTION_VARIABLES = {
+    "HL_sst": ["sst"], "LL_sst": ["sst"], "HL_DIC": ["HL_ocean_c"], "LL_DIC": ["LL_ocean_c"],
+    "DIC": ["HL_ocean_c", "LL_ocean_c"], "pH": ["HL_pH", "LL_pH"], "PCO2": ["HL_PCO2", "LL_PCO2"],
+    "ML_ocean_c": ["HL_ocean_c", "LL_ocean_c"], "TAU_OH": ["CH4_concentration"],
+    "f_frozen": ["land_tas", "permafrost_c"]}
 
 DERIVED_VARIABLES = (["RF_BC", "RF_OC", "RF_SO2", "RF_NH3", "RF_aci", "RF_vol", "RF_albedo",
                       "RF_misc", "RF_O3_trop", "RF_H2O_strat"]

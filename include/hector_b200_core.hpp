@@ -80,7 +80,8 @@ using ::h_exception;
 /* ---- units (unitval.hpp:68-130): the ones variables of this path carry ---- */
 enum unit_types {
   U_UNITLESS, U_PPMV_CO2, U_PPBV_CH4, U_PPBV_N2O, U_DU_O3, U_TG_PPBV, U_DEGC, U_CM2_S, U_PGC,
-  U_PGC_YR, U_W_M2, U_W_M2_TG, U_W_M2_GG, U_M3_S, U_PH, U_UATM, U_YRS, U_PPTV, U_UNDEFINED
+  U_PGC_YR, U_W_M2, U_W_M2_TG, U_W_M2_GG, U_M3_S, U_PH, U_UATM, U_YRS, U_PPTV, U_UMOL_KG,
+  U_UNDEFINED
 };
 
 class unitval {
@@ -94,7 +95,7 @@ class unitval {
     static const char *const names[] = {"(unitless)", "ppmv CO2", "ppbv CH4", "ppbv N2O", "DU O3",
                                         "Tg/ppbv", "degC", "cm2/s", "Pg C", "Pg C/yr", "W/m2",
                                         "W/m2/Tg", "W/m2/Gg", "m3/s", "pH", "uatm", "Years",
-                                        "pptv", "(undefined)"};
+                                        "pptv", "umol/kg", "(undefined)"};
     return names[(int)u];
   }
   static unit_types parseUnitsName(const std::string &s) {
@@ -197,6 +198,10 @@ inline unit_types units_of(const std::string &v) {
       {"permafrost_c", U_PGC}, {"veg_c", U_PGC}, {"detritus_c", U_PGC}, {"soil_c", U_PGC},
       {"thawedp_c", U_PGC}, {"earth_c", U_PGC}, {"HL_ocean_c", U_PGC}, {"LL_ocean_c", U_PGC},
       {"IO_ocean_c", U_PGC}, {"DO_ocean_c", U_PGC}, {"NBP", U_PGC_YR}, {"ocean_uptake", U_PGC_YR},
+      /* functions of recorded outputs, evaluated by hx_fetch (include/hector_b200.h) */
+      {"HL_sst", U_DEGC}, {"LL_sst", U_DEGC}, {"HL_DIC", U_UMOL_KG}, {"LL_DIC", U_UMOL_KG},
+      {"DIC", U_UMOL_KG}, {"pH", U_PH}, {"PCO2", U_UATM}, {"ML_ocean_c", U_PGC}, {"TAU_OH", U_YRS},
+      {"f_frozen", U_UNITLESS},
       {"rh_ch4", U_PGC_YR}, {"HL_pH", U_PH}, {"LL_pH", U_PH}, {"HL_PCO2", U_UATM},
       {"LL_PCO2", U_UATM}, {"CH4_concentration", U_PPBV_CH4}, {"N2O_concentration", U_PPBV_N2O},
       {"O3_concentration", U_DU_O3}, {"ocean_timesteps", U_UNITLESS}, {"NPP", U_PGC_YR},

@@ -372,6 +372,35 @@ def make_extra_outputs():
                         values=np.array(vals))
 
 
+# the rest of R's ALL_VARS() (tests/testthat/test_set_get_data.R "Can fetch all variables"): what
+# the outputstream visitor prints beyond the variables above
+MORE_VARS = ["HL_sst", "LL_sst", "HL_DIC", "LL_DIC", "DIC", "pH", "PCO2", "ML_ocean_c", "TAU_OH",
+             "f_frozen", "HL_CO3", "LL_CO3", "CO3", "HL_ocean_uptake", "LL_ocean_uptake", "rh_det",
+             "rh_soil",
+             # what the engine derives them from
+             "sst", "land_tas", "permafrost_c", "HL_ocean_c", "LL_ocean_c", "HL_pH", "LL_pH",
+             "HL_PCO2", "LL_PCO2", "CH4_concentration"]
+
+
+def make_more_outputs():
+    """ref_outputs_more.npz: the remaining outputstream variables from the UNMODIFIED reference
+    (three of EXTRA_CASES)"""
+    from oracle import ref
+    names, scns, pnames, pvals, vals = [], [], [], [], []
+    for name, scn, params in [EXTRA_CASES[0], EXTRA_CASES[1], EXTRA_CASES[5]]:
+        ok, err, o, _ = ref.run_member(os.path.join(REF, "inst/input/hector_%s.ini" % scn), params,
+                                       MORE_VARS)
+        assert ok, err
+        names.append(name); scns.append(scn); pnames.append(",".join(params))
+        pvals.append(np.array(list(params.values()) + [np.nan] * (8 - len(params))))
+        vals.append(o[:len(MORE_VARS)])
+        print(name, "ok")
+    np.savez_compressed(os.path.join(OUT, "ref_outputs_more.npz"), names=np.array(names),
+                        scenarios=np.array(scns), param_names=np.array(pnames),
+                        param_values=np.array(pvals), variables=np.array(MORE_VARS),
+                        values=np.array(vals))
+
+
 BIOME_VARS = ["CO2_concentration", "global_tas", "veg_c", "detritus_c", "soil_c", "permafrost_c",
               "thawedp_c", "NPP", "RH", "NBP", "CH4_concentration", "RF_tot", "HL_pH", "ocean_c",
               "land_tas", "atmos_co2", "earth_c"]
@@ -658,7 +687,9 @@ def make_startdate():
 
 
 if __name__ == "__main__":
-    if "startdate" in sys.argv[1:]:
+    if "more" in sys.argv[1:]:
+        make_more_outputs()
+    elif "startdate" in sys.argv[1:]:
         make_startdate()
     elif "luc_pulse" in sys.argv[1:]:
         make_luc_pulse()
@@ -684,3 +715,4 @@ if __name__ == "__main__":
         make_luc_pulse()
         make_picontrol()
         make_startdate()
+        make_more_outputs()

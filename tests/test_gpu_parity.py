@@ -746,3 +746,31 @@ def test_start_date_values_like_the_reference():
     with pytest.raises(hb.HxError):
         ens.fetch("CO2_concentration", [1744.0])
     ens.close()
+
+
+@pytest.mark.parametrize("case", util.ref_outputs_more(), ids=lambda c: c["name"])
+def test_function_outputs_vs_reference_golden(case):
+    """the rest of R's ALL_VARS() (tests/testthat/test_set_get_data.R "Can fetch all variables"):
+    box temperatures, DIC, the surface means, the mixed-layer carbon, the OH lifetime and the
+    frozen fraction, evaluated at fetch time from recorded outputs, against the unmodified
+    reference (tests/golden/ref_outputs_more.npz; one case with a land-ocean warming ratio)"""
+    import hector_b200 as hb
+    need = sorted({v for deps in hb.FUNCTION_VARIABLES.values() for v in deps})
+    ens = hb.Ensemble(2, util.scenarios()[case["scenario"]], outputs=need)
+    for k, v in case["params"].items():
+        ens.setvar(k, v)
+    ens.run()
+    worst = {}
+    for v in hb.FUNCTION_VARIABLES:
+        got = ens.fetch(v, _years())
+        assert np.array_equal(got[0], got[1])
+        ref = case["values"][v]
+        worst[v] = float(np.max(np.abs(got[0] - ref) / np.maximum(np.abs(ref), 1e-3)))
+    print({k: "%.2g" % e for k, e in sorted(worst.items(), key=lambda kv: -kv[1])})
+    assert max(worst.values()) < TOL, worst
+    for v in ("HL_CO3", "rh_det", "HL_ocean_uptake"):      # documented as not served
+        with pytest.raises(hb.HxError):
+            ens.fetch(v, [2000.0])
+    with pytest.raises(hb.HxError):
+        ens.fetch("HL_sst", [1745.0])
+    ens.close()

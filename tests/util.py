@@ -62,8 +62,13 @@ def ref_tracking_csv():
     return str(np.load(os.path.join(GOLDEN, "ref_tracking.npz"))["csv_1750_1755"])
 
 
-def ref_outputs_extra():
-    z = np.load(os.path.join(GOLDEN, "ref_outputs_extra.npz"))
+def ref_outputs_more():
+    """the rest of R's ALL_VARS() from the unmodified reference (make_golden.py more)"""
+    return ref_outputs_extra("ref_outputs_more.npz")
+
+
+def ref_outputs_extra(fixture="ref_outputs_extra.npz"):
+    z = np.load(os.path.join(GOLDEN, fixture))
     variables = [str(v) for v in z["variables"]]
     cases = []
     for i, name in enumerate(z["names"]):
