@@ -774,3 +774,26 @@ def test_function_outputs_vs_reference_golden(case):
     with pytest.raises(hb.HxError):
         ens.fetch("HL_sst", [1745.0])
     ens.close()
+
+
+def test_set_and_get_every_emission_series():
+    """tests/testthat/test_set_get_data.R: setvar(core, 1800, <emissions>, random value), run to
+    1800, fetchvars(core, 1800, <emissions>) returns it -- for every emission series at once,
+    two scenarios with different values"""
+    import hector_b200 as hb
+    names = [n for n in hb.RAW_SERIES if n.endswith("_emissions")]
+    assert len(names) == 38, names          # the reference test lists 37 of them (no NH3)
+    tabs = util.scenarios()
+    ens = hb.Ensemble(4, [tabs["ssp245"], tabs["ssp126"]], member_scenario=[0, 1, 0, 1])
+    rng = np.random.default_rng(3)
+    vals = rng.exponential(5.0, (2, len(names)))
+    for sc in range(2):
+        for j, n in enumerate(names):
+            ens.setvar_series(n, [1800], [vals[sc, j]], scenario=sc)
+    ens.run(1800)
+    assert (ens.status()[0] == 0).all()
+    for j, n in enumerate(names):
+        got = ens.fetch(n, [1799.0, 1800.0])
+        assert np.array_equal(got[:, 1], vals[[0, 1, 0, 1], j]), n
+        assert np.array_equal(got[0, :1], tabs["ssp245"][1799 - 1745, hb.RAW_SERIES.index(n)][None]), n
+    ens.close()
