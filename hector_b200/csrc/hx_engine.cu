@@ -956,14 +956,16 @@ int Engine::fetch_derived(const char *name, const double *dates, int n_dates, do
  *   f_frozen         frozen permafrost fraction (simpleNbox-runtime.cpp:1012-1024) from last
  *                    year's land temperature; single biome only
  * Each needs the outputs it is a function of to be recorded (hx_select_outputs).  Pinned by
- * tests/golden/ref_outputs_more.npz.  Not served: HL_CO3 / LL_CO3 / CO3, HL_ocean_uptake /
- * LL_ocean_uptake, rh_det, rh_soil (they would need state the run kernel does not keep). */
+ *   HL_CO3, LL_CO3, CO3  carbonate of the year's last chemistry solve, from the recorded pCO2
+ *                    and pH of that solve and the box temperature
+ * tests/golden/ref_outputs_more.npz.  Not served: HL_ocean_uptake / LL_ocean_uptake, rh_det,
+ * rh_soil (they would need state the run kernel does not keep). */
 int Engine::fetch_functions(const char *name, const double *dates, int n_dates, double *out, int &rc) {
-  enum Kind { F_NONE, F_SST_HL, F_SST_LL, F_DIC_HL, F_DIC_LL, F_DIC, F_PH, F_PCO2, F_ML, F_TAU_OH, F_FROZEN };
+  enum Kind { F_NONE, F_SST_HL, F_SST_LL, F_DIC_HL, F_DIC_LL, F_DIC, F_PH, F_PCO2, F_ML, F_TAU_OH, F_FROZEN, F_CO3_HL, F_CO3_LL, F_CO3 };
   static const struct { const char *n; Kind k; } tab[] = {
       {"HL_sst", F_SST_HL}, {"LL_sst", F_SST_LL}, {"HL_DIC", F_DIC_HL}, {"LL_DIC", F_DIC_LL},
       {"DIC", F_DIC}, {"pH", F_PH}, {"PCO2", F_PCO2}, {"ML_ocean_c", F_ML}, {"TAU_OH", F_TAU_OH},
-      {"f_frozen", F_FROZEN}};
+      {"f_frozen", F_FROZEN}, {"HL_CO3", F_CO3_HL}, {"LL_CO3", F_CO3_LL}, {"CO3", F_CO3}};
   Kind kind = F_NONE;
   for (const auto &e : tab)
     if (!strcmp(name, e.n)) kind = e.k;
@@ -1025,6 +1027,35 @@ int Engine::fetch_functions(const char *name, const double *dates, int n_dates, 
       if ((rc = rec("LL_ocean_c", 0, a)) || (rc = rec("HL_ocean_c", 0, b))) return 1;
       for (size_t q = 0; q < N; ++q) out[q] = a[q] + b[q];
       break;
+    case F_CO3_HL: case F_CO3_LL: case F_CO3: {
+      /* carbonate of the year's last chemistry solve, from what that solve left on record:
+       * PCO2o = [CO2*] 1e6 / Kh and pH = -log10 h give [CO2*] and h; with K1, K2 at the box
+       * temperature DIC = [CO2*] (1 + K1/h + K1 K2/h^2) and CO3 = DIC / (1 + h/K2 + h^2/(K1 K2))
+       * (ocean_csys.cpp:166-366; Kh Weiss 1974, K1 / K2 Mehrbach refit) */
+      std::vector<double> sst, pco2[2], ph[2];
+      if ((rc = rec("sst", 1, sst))) return 1;
+      const bool need_hl = kind != F_CO3_LL, need_ll = kind != F_CO3_HL;
+      if (need_hl && ((rc = rec("HL_PCO2", 0, pco2[0])) || (rc = rec("HL_pH", 0, ph[0])))) return 1;
+      if (need_ll && ((rc = rec("LL_PCO2", 0, pco2[1])) || (rc = rec("LL_pH", 0, ph[1])))) return 1;
+      const double S = C.S;
+      auto co3 = [&](double Tc, double PCO2o, double pH) {
+        const double Tk = Tc + 273.15;
+        const double tmp = 9345.17 / Tk - 60.2409 + 23.3585 * std::log(Tk / 100);
+        const double Kh = std::exp(tmp + S * (0.023517 - 0.00023656 * Tk + 0.0047036e-4 * Tk * Tk));
+        const double K1 = std::pow(10, -(3633.86 / Tk - 61.2172 + 9.6777 * std::log(Tk) - 0.011555 * S + 0.0001152 * S * S));
+        const double K2 = std::pow(10.0, -(471.78 / Tk + 25.9290 - 3.16967 * std::log(Tk) - 0.01781 * S + 0.0001122 * S * S));
+        const double h = std::pow(10.0, -pH);
+        const double co2st = PCO2o * Kh / 1e6;
+        const double dic = co2st * (1.0 + K1 / h + K1 * K2 / h / h);
+        return dic / (1.0 + h / K2 + h * h / K1 / K2) * 1e6;
+      };
+      for (size_t q = 0; q < N; ++q) {
+        const double hl = need_hl ? co3(sst[q] + 18.0 + -16.4, pco2[0][q], ph[0][q]) : 0.0;
+        const double ll = need_ll ? co3(sst[q] + 18.0 + 2.9, pco2[1][q], ph[1][q]) : 0.0;
+        out[q] = kind == F_CO3_HL ? hl : kind == F_CO3_LL ? ll : part_low * ll + part_high * hl;
+      }
+      break;
+    }
     case F_TAU_OH: {
       std::vector<double> M0, TOH0, CCH4, CNOX, CCO, CNMVOC;
       if ((rc = rec("CH4_concentration", 1, a)) || (rc = param(PI_M0, M0)) || (rc = param(PI_TOH0, TOH0)) ||

@@ -70,10 +70,12 @@ VARIABLE_UNITS = {
     "heatflux_mixed": "W/m2", "heatflux_interior": "W/m2",
     # functions of recorded outputs, evaluated at fetch time (FUNCTION_VARIABLES)
     "HL_sst": "degC", "LL_sst": "degC", "HL_DIC": "umol/kg", "LL_DIC": "umol/kg", "DIC": "umol/kg",
-    "pH": "pH", "PCO2": "uatm", "ML_ocean_c": "Pg C", "TAU_OH": "Years", "f_frozen": "(unitless)"}
+    "pH": "pH", "PCO2": "uatm", "ML_ocean_c": "Pg C", "TAU_OH": "Years", "f_frozen": "(unitless)",
+    "HL_CO3": "umol/kg", "LL_CO3": "umol/kg", "CO3": "umol/kg"}
 VARIABLE_COMPONENT = {
     "HL_sst": "ocean", "LL_sst": "ocean", "HL_DIC": "ocean", "LL_DIC": "ocean", "DIC": "ocean",
     "pH": "ocean", "PCO2": "ocean", "ML_ocean_c": "ocean", "TAU_OH": "OH", "f_frozen": "simpleNbox",
+    "HL_CO3": "ocean", "LL_CO3": "ocean", "CO3": "ocean",
     "CO2_concentration": "simpleNbox", "atmos_co2": "simpleNbox", "veg_c": "simpleNbox",
     "detritus_c": "simpleNbox", "soil_c": "simpleNbox", "permafrost_c": "simpleNbox",
     "thawedp_c": "simpleNbox", "earth_c": "simpleNbox", "NBP": "simpleNbox",
@@ -102,12 +104,14 @@ BIOME_OUTPUTS = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c", "
 # The rest of the reference's outputstream variables that are plain functions of recorded outputs
 # (hx_fetch evaluates them on the host; each needs the outputs it depends on to be selected):
 # {variable: recorded outputs it needs}.  R's ALL_VARS() minus these and the lists above leaves
-# HL_CO3, LL_CO3, CO3, HL_ocean_uptake, LL_ocean_uptake, rh_det, rh_soil: not served.
+# HL_ocean_uptake, LL_ocean_uptake, rh_det, rh_soil: not served.
 FUNCTION_VARIABLES = {
     "HL_sst": ["sst"], "LL_sst": ["sst"], "HL_DIC": ["HL_ocean_c"], "LL_DIC": ["LL_ocean_c"],
     "DIC": ["HL_ocean_c", "LL_ocean_c"], "pH": ["HL_pH", "LL_pH"], "PCO2": ["HL_PCO2", "LL_PCO2"],
     "ML_ocean_c": ["HL_ocean_c", "LL_ocean_c"], "TAU_OH": ["CH4_concentration"],
-    "f_frozen": ["land_tas", "permafrost_c"]}
+    "f_frozen": ["land_tas", "permafrost_c"],
+    "HL_CO3": ["sst", "HL_PCO2", "HL_pH"], "LL_CO3": ["sst", "LL_PCO2", "LL_pH"],
+    "CO3": ["sst", "HL_PCO2", "HL_pH", "LL_PCO2", "LL_pH"]}
 
 DERIVED_VARIABLES = (["RF_BC", "RF_OC", "RF_SO2", "RF_NH3", "RF_aci", "RF_vol", "RF_albedo",
                       "RF_misc", "RF_O3_trop", "RF_H2O_strat"]

@@ -201,7 +201,7 @@ inline unit_types units_of(const std::string &v) {
       /* functions of recorded outputs, evaluated by hx_fetch (include/hector_b200.h) */
       {"HL_sst", U_DEGC}, {"LL_sst", U_DEGC}, {"HL_DIC", U_UMOL_KG}, {"LL_DIC", U_UMOL_KG},
       {"DIC", U_UMOL_KG}, {"pH", U_PH}, {"PCO2", U_UATM}, {"ML_ocean_c", U_PGC}, {"TAU_OH", U_YRS},
-      {"f_frozen", U_UNITLESS},
+      {"f_frozen", U_UNITLESS}, {"HL_CO3", U_UMOL_KG}, {"LL_CO3", U_UMOL_KG}, {"CO3", U_UMOL_KG},
       {"rh_ch4", U_PGC_YR}, {"HL_pH", U_PH}, {"LL_pH", U_PH}, {"HL_PCO2", U_UATM},
       {"LL_PCO2", U_UATM}, {"CH4_concentration", U_PPBV_CH4}, {"N2O_concentration", U_PPBV_N2O},
       {"O3_concentration", U_DU_O3}, {"ocean_timesteps", U_UNITLESS}, {"NPP", U_PGC_YR},

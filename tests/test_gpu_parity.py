@@ -768,7 +768,7 @@ def test_function_outputs_vs_reference_golden(case):
         worst[v] = float(np.max(np.abs(got[0] - ref) / np.maximum(np.abs(ref), 1e-3)))
     print({k: "%.2g" % e for k, e in sorted(worst.items(), key=lambda kv: -kv[1])})
     assert max(worst.values()) < TOL, worst
-    for v in ("HL_CO3", "rh_det", "HL_ocean_uptake"):      # documented as not served
+    for v in ("rh_det", "rh_soil", "HL_ocean_uptake"):      # documented as not served
         with pytest.raises(hb.HxError):
             ens.fetch(v, [2000.0])
     with pytest.raises(hb.HxError):
