@@ -161,7 +161,7 @@ struct Engine {
 
   /* device buffers */
   double *d_P = nullptr, *d_S = nullptr, *d_S_snap = nullptr, *d_D = nullptr, *d_ker = nullptr, *d_conv = nullptr,
-         *d_sst = nullptr, *d_tland = nullptr, *d_out = nullptr, *d_scen = nullptr,
+         *d_sst = nullptr, *d_tland = nullptr, *d_out = nullptr, *d_X = nullptr, *d_scen = nullptr,
          *d_stage = nullptr;
   int32_t *d_block_scen = nullptr, *d_status = nullptr, *d_status_snap = nullptr,
           *d_status_post = nullptr,
@@ -479,12 +479,12 @@ struct Engine {
   int fetch_functions(const char *name, const double *dates, int n_dates, double *out, int &rc);
 
   void free_device() {
-    void *ptrs[] = {d_GP, d_GF, d_GF_snap, d_scen_gas, d_BP, d_BF, d_BF_snap, d_P, d_S, d_S_snap, d_ker, d_conv, d_sst, d_tland, d_out, d_scen, d_stage,
+    void *ptrs[] = {d_GP, d_GF, d_GF_snap, d_scen_gas, d_BP, d_BF, d_BF_snap, d_P, d_S, d_S_snap, d_ker, d_conv, d_sst, d_tland, d_out, d_X, d_scen, d_stage,
                     d_block_scen, d_status, d_status_snap, d_status_post, d_fail_year, d_spinup_steps, d_yidx,
                     d_counters, d_dev_of_api, d_api_of_dev, d_sched, d_T, d_TO, d_TK, d_TOK, d_REC, d_YCNT, d_trk_fail};
     for (void *p : ptrs)
       if (p) cudaFree(p);
-    d_P = d_S = d_S_snap = d_D = d_ker = d_conv = d_sst = d_tland = d_out = d_scen = d_stage = nullptr;
+    d_P = d_S = d_S_snap = d_D = d_ker = d_conv = d_sst = d_tland = d_out = d_X = d_scen = d_stage = nullptr;
     d_block_scen = d_status = d_status_snap = d_status_post = d_fail_year = d_spinup_steps = d_yidx = nullptr;
     d_counters = nullptr;
     d_sched = nullptr;
@@ -958,8 +958,8 @@ int Engine::fetch_derived(const char *name, const double *dates, int n_dates, do
  * Each needs the outputs it is a function of to be recorded (hx_select_outputs).  Pinned by
  *   HL_CO3, LL_CO3, CO3  carbonate of the year's last chemistry solve, from the recorded pCO2
  *                    and pH of that solve and the box temperature
- * tests/golden/ref_outputs_more.npz.  Not served: HL_ocean_uptake / LL_ocean_uptake, rh_det,
- * rh_soil (they would need state the run kernel does not keep). */
+ * tests/golden/ref_outputs_more.npz.  (HL_ocean_uptake, LL_ocean_uptake, rh_det and rh_soil are
+ * recorded by the run kernel when selected: hx_layout.h, "scratch rows X".) */
 int Engine::fetch_functions(const char *name, const double *dates, int n_dates, double *out, int &rc) {
   enum Kind { F_NONE, F_SST_HL, F_SST_LL, F_DIC_HL, F_DIC_LL, F_DIC, F_PH, F_PCO2, F_ML, F_TAU_OH, F_FROZEN, F_CO3_HL, F_CO3_LL, F_CO3 };
   static const struct { const char *n; Kind k; } tab[] = {
@@ -1706,6 +1706,12 @@ int hx_prepare(hx_handle h) {
 
   const size_t Mp = Mpad;
   const int nsel = (int)h->out_sel.size();
+  /* the per-stash outputs (hx_layout.h, "scratch rows X") */
+  bool want_x = false;
+  for (int id : h->out_sel) want_x = want_x || (id >= OUT_UPTAKE_HL && id <= OUT_RH_SOIL);
+  if (want_x && nb > 1)
+    return fail(HX_ERR_UNSUPPORTED, "HL_ocean_uptake / LL_ocean_uptake / rh_det / rh_soil are not "
+                                    "recorded with more than one biome");
   if (tracking) {
     /* slabs per tracked launch (launch_rows): up to 4, from the memory the device has free --
      * two buffers of rec_group slab records, at most 45 % of it (HX_TRK_GROUP overrides) */
@@ -1730,6 +1736,7 @@ int hx_prepare(hx_handle h) {
       cudaMalloc(&h->d_sst, (size_t)nrow * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_tland, (size_t)nrow * Mp * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_out, std::max<size_t>(1, (size_t)nsel * (nrow - 1) * Mp) * sizeof(double)) != cudaSuccess ||
+      (want_x && cudaMalloc(&h->d_X, (size_t)XS_COUNT * Mp * sizeof(double)) != cudaSuccess) ||
       cudaMalloc(&h->d_scen, tab.size() * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_block_scen, block_scen.size() * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc(&h->d_status, Mp * sizeof(int32_t)) != cudaSuccess ||
@@ -1780,6 +1787,7 @@ int hx_prepare(hx_handle h) {
     also(cudaMemsetAsync(h->d_P, 0, (size_t)PD_COUNT * Mp * sizeof(double), st)); /* parameters follow below */
     also(cudaMemsetAsync(h->d_ker, 0, (size_t)HX_KER_ROWS(nrow) * Mp * sizeof(double), st));
     also(cudaMemsetAsync(h->d_conv, 0, (size_t)HX_SLAB_YEARS * Mp * sizeof(double), st));
+    if (h->d_X) also(cudaMemsetAsync(h->d_X, 0, (size_t)XS_COUNT * Mp * sizeof(double), st));
     also(cudaMemsetAsync(h->d_sst, 0, (size_t)nrow * Mp * sizeof(double), st));
     also(cudaMemsetAsync(h->d_tland, 0, (size_t)nrow * Mp * sizeof(double), st));
     if (h->d_BF) also(cudaMemsetAsync(h->d_BF, 0, (size_t)nb * BF_COUNT * Mp * sizeof(double), st));
@@ -1798,7 +1806,7 @@ int hx_prepare(hx_handle h) {
 
   HxDev &d = h->d;
   d.Mpad = Mpad; d.P = h->d_P; d.S = h->d_S; d.D = h->d_D; d.ker = h->d_ker; d.conv = h->d_conv;
-  d.sst_hist = h->d_sst; d.tland_hist = h->d_tland; d.out = h->d_out; d.scen = h->d_scen;
+  d.sst_hist = h->d_sst; d.tland_hist = h->d_tland; d.out = h->d_out; d.X = h->d_X; d.scen = h->d_scen;
   d.api_of_dev = h->d_api_of_dev;
   d.block_scen = h->d_block_scen; d.status = h->d_status; d.fail_year = h->d_fail_year;
   d.spinup_steps = h->d_spinup_steps; d.counters = h->d_counters; d.sched = h->d_sched;

@@ -172,7 +172,7 @@ __device__ __forceinline__ void load_member(const Bases &BS, Member &mb) {
   mb.solver_dt = STATE_G(SI_SOLVER_DT);
   mb.status = 0; mb.neg = false; mb.timesteps = 0;
   mb.pco2HL = mb.pco2LL = 0.0; mb.gHL = mb.gLL = 0.0; mb.luc_e = mb.luc_u = 0.0;
-  mb.REC = nullptr; mb.rec_stride = 0; mb.rec_n = 0; mb.trk = false; mb.trk_bad = false;
+  mb.X = nullptr; mb.REC = nullptr; mb.rec_stride = 0; mb.rec_n = 0; mb.trk = false; mb.trk_bad = false;
   mb.BIOP = BS.BP; mb.BIOF = BS.BF;
 }
 
@@ -795,6 +795,8 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
     Member mb;
     if (lane_ok) load_member(BS, mb);
     else mb.status = -1;
+    /* scratch rows of the per-stash outputs: only the all-output builds know them */
+    mb.X = (ALLOUT && d.X) ? d.X + (size_t)tile * XS_COUNT * HX_BLOCK + tid : nullptr;
     mbar_wait(&bars[0], item_no & 1u);
     ++item_no;
     const double *sl = slab[0];
@@ -918,6 +920,7 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
 
         /* --- OceanComponent::run: ocean_component.cpp:356-407 --- */
         mb.S[SI_X_FLUXSUM * HX_TILE] = 0.0;
+        if (ALLOUT && mb.X) { mb.X[XS_UPTAKE_HL * HX_TILE] = 0.0; mb.X[XS_UPTAKE_LL * HX_TILE] = 0.0; }
         mb.timesteps = 0;
         {
           /* getData(sst): DOECLIM's, or the lo_warming_ratio one (temperature_component.cpp:
@@ -1255,6 +1258,12 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
         EMIT(OUT_FLUX_MIXED, hf_mixed_out);
         EMIT(OUT_FLUX_INTERIOR, hf_int_out);
         EMIT(OUT_TIMESTEPS, (double)mb.timesteps);
+        if (mb.X) {
+          EMIT(OUT_UPTAKE_HL, mb.X[XS_UPTAKE_HL * HX_TILE]);
+          EMIT(OUT_UPTAKE_LL, mb.X[XS_UPTAKE_LL * HX_TILE]);
+          EMIT(OUT_RH_DET, mb.X[XS_RH_DET * HX_TILE]);
+          EMIT(OUT_RH_SOIL, mb.X[XS_RH_SOIL * HX_TILE]);
+        }
         }
         if (BIOMES && ALLOUT) { /* <biome>.<name>: the biome's own pools and final NPP / RH */
           const int bf[BO_COUNT] = {BF_VEG, BF_DET, BF_SOIL, BF_PERMAFROST, BF_THAWED, BF_X_NPP, BF_X_RH};

@@ -46,6 +46,7 @@ struct HxDev {
   double *sst_hist;         /* [nrow][Mpad] */
   double *tland_hist;       /* [nrow][Mpad] */
   double *out;              /* [nsel][nrow-1][Mpad], columns in API member order */
+  double *X;                /* [tile][XS_COUNT][128] scratch rows of the per-stash outputs, or null */
   const int32_t *api_of_dev; /* [Mpad] API index (= output column) of each device member, -1 = padding */
   const double *scen;       /* [n_scen][nrow][SC_STRIDE] */
   const int32_t *block_scen; /* [Mpad / HX_BLOCK] scenario of each CTA */

@@ -123,6 +123,13 @@ enum {
 #define SI_REG_COUNT 14   /* SI_ATMOS .. SI_SOLVER_DT */
 #define SI_SPINUP_ROWS 26 /* SI_ATMOS .. SI_LASTFLUX_ANN */
 
+/* ---- per-member scratch rows X[tile][XS_COUNT][128] in global memory (allocated only when one
+ * of OUT_UPTAKE_HL .. OUT_RH_SOIL is recorded): the per-box air-sea flux sums of the year
+ * (ocean_component.cpp:737-738) and the last stash's detritus / soil respiration
+ * (simpleNbox-runtime.cpp:445-446), written by the stashes, read by the year's output stage.  The
+ * shared-memory state block has no room for them and they are off the year's critical path. */
+enum { XS_UPTAKE_HL = 0, XS_UPTAKE_LL, XS_RH_DET, XS_RH_SOIL, XS_COUNT };
+
 /* ---- per-member derived constants (set-up kernel) ---- */
 enum {
   DI_K_LL_HL = 0, DI_K_LL_IO, DI_K_HL_DO, DI_K_IO_LL, DI_K_IO_HL, DI_K_IO_DO, DI_K_DO_IO,
@@ -148,6 +155,8 @@ enum {
   OUT_PCO2_LL, OUT_CARBON_HL, OUT_CARBON_LL, OUT_CARBON_IO, OUT_CARBON_DO, OUT_RF_CH4,
   OUT_RF_N2O, OUT_RH_CH4, OUT_NPP, OUT_RH, OUT_GMST, OUT_OCEAN_TAS, OUT_FLUX_MIXED,
   OUT_FLUX_INTERIOR, OUT_TIMESTEPS,
+  /* per-stash quantities the year loop parks in the scratch rows X (below) when asked for */
+  OUT_UPTAKE_HL, OUT_UPTAKE_LL, OUT_RH_DET, OUT_RH_SOIL,
   OUT_COUNT
 };
 

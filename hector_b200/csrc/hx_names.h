@@ -73,7 +73,8 @@ static const char *const kOutNames[OUT_COUNT] = {
     "O3_concentration", "land_tas", "veg_c", "detritus_c", "soil_c", "thawedp_c", "earth_c", "NBP",
     "ocean_uptake", "LL_pH", "HL_PCO2", "LL_PCO2", "HL_ocean_c", "LL_ocean_c", "IO_ocean_c",
     "DO_ocean_c", "RF_CH4", "RF_N2O", "rh_ch4", "NPP", "RH", "gmst", "ocean_tas",
-    "heatflux_mixed", "heatflux_interior", "ocean_timesteps"};
+    "heatflux_mixed", "heatflux_interior", "ocean_timesteps",
+    "HL_ocean_uptake", "LL_ocean_uptake", "rh_det", "rh_soil"};
 
 /* halocarbon defaults (26 x [<gas>_halocarbon] sections of hector_ssp245.ini) */
 static const double kHaloTau[HX_NHALO] = {50000.0, 10000.0, 228.0, 5.4, 17.0, 30.0, 14.0, 51.0,

@@ -71,11 +71,13 @@ VARIABLE_UNITS = {
     # functions of recorded outputs, evaluated at fetch time (FUNCTION_VARIABLES)
     "HL_sst": "degC", "LL_sst": "degC", "HL_DIC": "umol/kg", "LL_DIC": "umol/kg", "DIC": "umol/kg",
     "pH": "pH", "PCO2": "uatm", "ML_ocean_c": "Pg C", "TAU_OH": "Years", "f_frozen": "(unitless)",
-    "HL_CO3": "umol/kg", "LL_CO3": "umol/kg", "CO3": "umol/kg"}
+    "HL_CO3": "umol/kg", "LL_CO3": "umol/kg", "CO3": "umol/kg",
+    "HL_ocean_uptake": "Pg C/yr", "LL_ocean_uptake": "Pg C/yr", "rh_det": "Pg C/yr", "rh_soil": "Pg C/yr"}
 VARIABLE_COMPONENT = {
     "HL_sst": "ocean", "LL_sst": "ocean", "HL_DIC": "ocean", "LL_DIC": "ocean", "DIC": "ocean",
     "pH": "ocean", "PCO2": "ocean", "ML_ocean_c": "ocean", "TAU_OH": "OH", "f_frozen": "simpleNbox",
-    "HL_CO3": "ocean", "LL_CO3": "ocean", "CO3": "ocean",
+    "HL_CO3": "ocean", "LL_CO3": "ocean", "CO3": "ocean", "HL_ocean_uptake": "ocean",
+    "LL_ocean_uptake": "ocean", "rh_det": "simpleNbox", "rh_soil": "simpleNbox",
     "CO2_concentration": "simpleNbox", "atmos_co2": "simpleNbox", "veg_c": "simpleNbox",
     "detritus_c": "simpleNbox", "soil_c": "simpleNbox", "permafrost_c": "simpleNbox",
     "thawedp_c": "simpleNbox", "earth_c": "simpleNbox", "NBP": "simpleNbox",
@@ -101,10 +103,14 @@ BIOME_PARAMETERS = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "npp_flux0"
 # per-biome outputs, selected and fetched as "<biome>.<name>" (simpleNbox.cpp:533-697)
 BIOME_OUTPUTS = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c", "NPP", "RH"]
 
+# Per-stash quantities the run kernel records on request (scratch rows in global memory, the
+# all-output builds only; single biome): selected and fetched like OUTPUT_VARIABLES
+STASH_OUTPUTS = ["HL_ocean_uptake", "LL_ocean_uptake", "rh_det", "rh_soil"]
+
 # The rest of the reference's outputstream variables that are plain functions of recorded outputs
 # (hx_fetch evaluates them on the host; each needs the outputs it depends on to be selected):
-# {variable: recorded outputs it needs}.  R's ALL_VARS() minus these and the lists above leaves
-# HL_ocean_uptake, LL_ocean_uptake, rh_det, rh_soil: not served.
+# {variable: recorded outputs it needs}.  With OUTPUT_VARIABLES, STASH_OUTPUTS and
+# DERIVED_VARIABLES this is all of R's ALL_VARS().
 FUNCTION_VARIABLES = {
     "HL_sst": ["sst"], "LL_sst": ["sst"], "HL_DIC": ["HL_ocean_c"], "LL_DIC": ["LL_ocean_c"],
     "DIC": ["HL_ocean_c", "LL_ocean_c"], "pH": ["HL_pH", "LL_pH"], "PCO2": ["HL_PCO2", "LL_PCO2"],

@@ -201,6 +201,8 @@ inline unit_types units_of(const std::string &v) {
       /* functions of recorded outputs, evaluated by hx_fetch (include/hector_b200.h) */
       {"HL_sst", U_DEGC}, {"LL_sst", U_DEGC}, {"HL_DIC", U_UMOL_KG}, {"LL_DIC", U_UMOL_KG},
       {"DIC", U_UMOL_KG}, {"pH", U_PH}, {"PCO2", U_UATM}, {"ML_ocean_c", U_PGC}, {"TAU_OH", U_YRS},
+      {"HL_ocean_uptake", U_PGC_YR}, {"LL_ocean_uptake", U_PGC_YR}, {"rh_det", U_PGC_YR},
+      {"rh_soil", U_PGC_YR},
       {"f_frozen", U_UNITLESS}, {"HL_CO3", U_UMOL_KG}, {"LL_CO3", U_UMOL_KG}, {"CO3", U_UMOL_KG},
       {"rh_ch4", U_PGC_YR}, {"HL_pH", U_PH}, {"LL_pH", U_PH}, {"HL_PCO2", U_UATM},
       {"LL_PCO2", U_UATM}, {"CH4_concentration", U_PPBV_CH4}, {"N2O_concentration", U_PPBV_N2O},

@@ -768,9 +768,8 @@ def test_function_outputs_vs_reference_golden(case):
         worst[v] = float(np.max(np.abs(got[0] - ref) / np.maximum(np.abs(ref), 1e-3)))
     print({k: "%.2g" % e for k, e in sorted(worst.items(), key=lambda kv: -kv[1])})
     assert max(worst.values()) < TOL, worst
-    for v in ("rh_det", "rh_soil", "HL_ocean_uptake"):      # documented as not served
-        with pytest.raises(hb.HxError):
-            ens.fetch(v, [2000.0])
+    with pytest.raises(hb.HxError):                         # recorded on request only
+        ens.fetch("rh_det", [2000.0])
     with pytest.raises(hb.HxError):
         ens.fetch("HL_sst", [1745.0])
     ens.close()
@@ -797,3 +796,35 @@ def test_set_and_get_every_emission_series():
         assert np.array_equal(got[:, 1], vals[[0, 1, 0, 1], j]), n
         assert np.array_equal(got[0, :1], tabs["ssp245"][1799 - 1745, hb.RAW_SERIES.index(n)][None]), n
     ens.close()
+
+
+@pytest.mark.parametrize("case", util.ref_outputs_more(), ids=lambda c: c["name"])
+def test_stash_outputs_vs_reference_golden(case):
+    """HL_ocean_uptake, LL_ocean_uptake (the per-box air-sea flux sums of the year), rh_det and
+    rh_soil (the last stash's detritus / soil respiration): recorded by the all-output builds
+    when selected, against the unmodified reference; selecting them changes nothing else"""
+    import hector_b200 as hb
+    base = ["CO2_concentration", "global_tas", "ocean_uptake", "RH", "rh_ch4"]
+    ens = hb.Ensemble(3, util.scenarios()[case["scenario"]], outputs=base + hb.STASH_OUTPUTS)
+    plain = hb.Ensemble(3, util.scenarios()[case["scenario"]], outputs=base)
+    for e in (ens, plain):
+        for k, v in case["params"].items():
+            e.setvar(k, v)
+        e.run(2000)
+        e.run()             # the sums restart with every year, whatever the launch boundaries
+    got = ens.fetchvars(_years())
+    ref = plain.fetchvars(_years())
+    for v in base:
+        assert np.array_equal(got[v], ref[v]), v
+    worst = {}
+    for v in hb.STASH_OUTPUTS:
+        assert np.array_equal(got[v][0], got[v][2])
+        r = case["values"][v]
+        worst[v] = float(np.max(np.abs(got[v][0] - r) / np.maximum(np.abs(r), 1.0)))
+    print({k: "%.2g" % e for k, e in worst.items()})
+    assert max(worst.values()) < TOL, worst
+    # the two boxes add up to the total, the two respirations stay below it
+    tot = got["HL_ocean_uptake"] + got["LL_ocean_uptake"]
+    assert np.abs(tot - got["ocean_uptake"]).max() < 1e-12
+    assert (got["rh_det"] + got["rh_soil"] <= got["RH"] * (1 + 1e-15)).all()
+    ens.close(); plain.close()
