@@ -828,3 +828,67 @@ def test_stash_outputs_vs_reference_golden(case):
     assert np.abs(tot - got["ocean_uptake"]).max() < 1e-12
     assert (got["rh_det"] + got["rh_soil"] <= got["RH"] * (1 + 1e-15)).all()
     ens.close(); plain.close()
+
+
+def test_runscenario_like_the_reference_test():
+    """tests/testthat/test_hector.R "Running a single scenario returns proper outputs": every
+    year from the START date to the end date, the four default variables, their units"""
+    import hector_b200 as hb
+    vars4 = ["CO2_concentration", "RF_tot", "RF_CO2", "global_tas"]
+    ens = hb.Ensemble(1, util.scenarios()["ssp245"], outputs=vars4)
+    ens.run()
+    sce = ens.fetchvars_frame(np.arange(ens.start_year, ens.end_year + 1), vars4)
+    assert list(sce["year"].unique()) == list(range(1745, 2301))
+    assert list(sce["variable"].unique()) == vars4
+    assert list(sce["units"].unique()) == ["ppmv CO2", "W/m2", "degC"]
+    first = sce[sce["year"] == 1745].set_index("variable")["value"]
+    assert first["CO2_concentration"] == 277.15 and first["global_tas"] == 0.0 and first["RF_tot"] == 0.0
+    assert not sce["value"].isna().any()
+    ens.close()
+
+
+def test_ocean_and_atmosphere_like_the_reference_tests():
+    """tests/testthat/test_ocean.R and test_atmosphere.R as written: the boxes add up to the
+    ocean pool, the two surface fluxes to the uptake, high and low latitude differ in every
+    variable, each ocean parameter moves every ocean output; the 39 forcing agents add up to
+    RF_tot; global_tas is the area-weighted land / ocean mean and exceeds gmst"""
+    import hector_b200 as hb
+    boxes = ["HL_ocean_c", "LL_ocean_c", "IO_ocean_c", "DO_ocean_c"]
+    hl = ["HL_ocean_c", "HL_pH", "HL_ocean_uptake", "HL_PCO2", "HL_sst", "HL_CO3"]
+    ll = ["LL_ocean_c", "LL_pH", "LL_ocean_uptake", "LL_PCO2", "LL_sst", "LL_CO3"]
+    ocean_vars = ["ocean_uptake", "ocean_c", "HL_pH", "HL_PCO2", "HL_DIC", "HL_sst", "HL_CO3"]
+    recorded = ["ocean_c", "ocean_uptake", "sst", "HL_pH", "LL_pH", "HL_PCO2", "LL_PCO2", "RF_tot",
+                "RF_CO2", "RF_N2O", "RF_CH4", "O3_concentration", "CH4_concentration", "land_tas",
+                "ocean_tas", "global_tas", "gmst"] + boxes + hb.STASH_OUTPUTS
+    params = ["tt", "tu", "twi", "tid", "preind_surface_c", "preind_interdeep_c"]
+    M = 1 + len(params)
+    ens = hb.Ensemble(M, util.scenarios()["ssp245"], outputs=recorded)
+    for j, p in enumerate(params):          # member 0: defaults; member j + 1: parameter j x 1.1
+        v = np.full(M, ens.getvar(p)[0])
+        v[j + 1] *= 1.1
+        ens.setvar(p, v)
+    ens.run(2100)
+    t = np.arange(1850.0, 1901.0)
+    f = lambda v: ens.fetch(v, t)
+    assert np.allclose(f("ocean_c")[0], sum(f(b)[0] for b in boxes), rtol=1.5e-8, atol=0)
+    assert np.allclose(f("ocean_uptake")[0], f("HL_ocean_uptake")[0] + f("LL_ocean_uptake")[0], rtol=1.5e-8, atol=1e-12)
+    assert all(f(a)[0].mean() != f(b)[0].mean() for a, b in zip(hl, ll))
+    base = {v: f(v)[0].mean() for v in ocean_vars}
+    for j, p in enumerate(params):
+        for v in ocean_vars:
+            assert abs(f(v)[j + 1].mean() - base[v]) > 1e-10, (p, v)
+    with pytest.raises(hb.HxError):         # parameters take no dates
+        ens.fetch("tt", t)
+    # test_atmosphere.R
+    t = np.arange(1850.0, 2101.0)
+    agents = (["RF_albedo", "RF_CO2", "RF_N2O", "RF_H2O_strat", "RF_O3_trop", "RF_BC", "RF_OC", "RF_SO2",
+               "RF_vol", "RF_CH4", "RF_NH3", "RF_aci", "RF_misc"] + ["Fadj%s" % h for h in hb.ensemble.HALOS])
+    assert len(agents) == 39
+    total = ens.fetch("RF_tot", t)[0]
+    parts = sum(ens.fetch(a, t)[0] for a in agents)
+    assert np.allclose(total, parts, rtol=1e-8, atol=1e-12)
+    t = np.arange(2020.0, 2101.0)
+    land, ocean, tas, gmst = (ens.fetch(v, t)[0] for v in ("land_tas", "ocean_tas", "global_tas", "gmst"))
+    assert np.allclose(tas, 0.29 * land + ocean * (1 - 0.29), rtol=1e-5)
+    assert (tas > gmst).all()
+    ens.close()

@@ -3,7 +3,7 @@ synccheck): 300 members (two full tiles + a ragged one), 40 years unless told ot
 
   compute-sanitizer --tool memcheck  python tools/sanitize_driver.py plain
   compute-sanitizer --tool racecheck python tools/sanitize_driver.py tracked
-flavours: plain allout constrained nbp tracked biomes stream spinup (default: all)"""
+flavours: plain allout stashout constrained nbp tracked biomes stream spinup (default: all)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -12,7 +12,7 @@ from bench import lhs, scenario_table, PARAMS
 
 M = int(os.environ.get("HX_SAN_MEMBERS", "300"))
 TO = float(os.environ.get("HX_SAN_TO", "1785"))
-flavours = sys.argv[1:] or ["plain", "allout", "constrained", "nbp", "tracked", "biomes", "stream",
+flavours = sys.argv[1:] or ["plain", "allout", "stashout", "constrained", "nbp", "tracked", "biomes", "stream",
                             "spinup"]
 X = lhs(M)
 tab = scenario_table()
@@ -31,6 +31,8 @@ for fl in flavours:
     kw = dict(outputs=["CO2_concentration", "global_tas"])
     if fl in ("allout", "constrained", "nbp"):
         kw["outputs"] = hb.OUTPUT_VARIABLES
+    if fl == "stashout":   # + the per-stash outputs parked in the scratch rows X
+        kw["outputs"] = list(hb.OUTPUT_VARIABLES) + hb.STASH_OUTPUTS
     if fl == "tracked":
         kw.update(tracking_date=1750, track_every=10)
     if fl == "biomes":
