@@ -892,3 +892,49 @@ def test_ocean_and_atmosphere_like_the_reference_tests():
     assert np.allclose(tas, 0.29 * land + ocean * (1 - 0.29), rtol=1e-5)
     assert (tas > gmst).all()
     ens.close()
+
+
+def test_parameter_responses_like_the_reference_tests():
+    """tests/testthat/test_parameters.R: each member changes ONE parameter of the default run --
+    lower C0 -> lower CO2; lower ECS -> cooler; higher Q10 -> more CO2; lower diffusivity ->
+    warmer; lower aerosol scaling -> warmer; higher volcanic scaling -> larger |RF_vol| and other
+    temperatures; lower f_nppv / f_nppd / f_litterd -> different pools; higher beta -> more NPP;
+    a land-ocean ratio of 3 comes back out of land_tas / ocean_tas"""
+    import hector_b200 as hb
+    outs = ["CO2_concentration", "global_tas", "RF_tot", "veg_c", "detritus_c", "soil_c", "NPP",
+            "land_tas", "ocean_tas", "sst"]
+    cases = [("C0", 250.0 / 277.15), ("S", 0.5), ("q10_rh", 2.0), ("diff", 0.5), ("aero_scalar", 0.5),
+             ("vol_scalar", 2.0), ("f_nppv", 0.5), ("f_nppd", 0.5), ("f_litterd", 0.5), ("beta", 2.0)]
+    M = len(cases) + 2
+    ens = hb.Ensemble(M, util.scenarios()["ssp245"], outputs=outs)
+    for j, (p, fac) in enumerate(cases):
+        v = np.full(M, ens.getvar(p)[0])
+        v[j + 1] *= fac
+        ens.setvar(p, v)
+        assert ens.getvar(p)[j + 1] == v[j + 1] and ens.getvar(p)[0] == v[0]   # set and retrieved
+    lo = np.zeros(M); lo[M - 1] = 3.0
+    ens.setvar("lo_warming_ratio", lo)
+    ens.run(2100)
+    dates, tdates = np.arange(1750.0, 2101.0), np.arange(2000.0, 2101.0)
+    g = lambda v, t=tdates: ens.fetch(v, t)
+    k = {p: j + 1 for j, (p, _) in enumerate(cases)}
+    co2 = g("CO2_concentration", dates)
+    assert (co2[k["C0"]] < co2[0]).all()
+    tas = g("global_tas")
+    assert (tas[k["S"]] < tas[0]).all()
+    assert (g("CO2_concentration")[k["q10_rh"]] > g("CO2_concentration")[0]).all()
+    assert (tas[k["diff"]] > tas[0]).all()
+    assert (tas[k["aero_scalar"]] > tas[0]).all()
+    vol0, vol1 = ens.fetch("RF_vol", tdates)[0], ens.fetch("RF_vol", tdates)[k["vol_scalar"]]
+    assert (tas[k["vol_scalar"]] != tas[0]).all() and (np.abs(vol1) - np.abs(vol0) >= 0).all()
+    for p in ("f_nppv", "f_nppd", "f_litterd"):
+        for v in ("veg_c", "detritus_c", "soil_c"):
+            assert (np.abs(g(v)[k[p]] - g(v)[0]) > 0).all(), (p, v)
+    assert (g("NPP")[k["beta"]] > g("NPP")[0]).all()
+    # the land-ocean warming ratio, test_parameters.R:373-420
+    keep = np.floor(np.linspace(1850, 2100, 30))
+    ratio0 = ens.fetch("land_tas", keep)[0] / ens.fetch("ocean_tas", keep)[0]
+    assert len(np.unique(ratio0)) == len(ratio0)            # emergent: not constant
+    ratio3 = ens.fetch("land_tas", keep)[M - 1] / ens.fetch("ocean_tas", keep)[M - 1]
+    assert (np.abs(3.0 - ratio3) <= 1e-5).all()
+    ens.close()
