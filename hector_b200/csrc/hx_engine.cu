@@ -958,14 +958,18 @@ int Engine::fetch_derived(const char *name, const double *dates, int n_dates, do
  * Each needs the outputs it is a function of to be recorded (hx_select_outputs).  Pinned by
  *   HL_CO3, LL_CO3, CO3  carbonate of the year's last chemistry solve, from the recorded pCO2
  *                    and pH of that solve and the box temperature
+ *   HL_OmegaCa, LL_OmegaCa, HL_OmegaAr, LL_OmegaAr   calcite / aragonite saturation from it
  * tests/golden/ref_outputs_more.npz.  (HL_ocean_uptake, LL_ocean_uptake, rh_det and rh_soil are
  * recorded by the run kernel when selected: hx_layout.h, "scratch rows X".) */
 int Engine::fetch_functions(const char *name, const double *dates, int n_dates, double *out, int &rc) {
-  enum Kind { F_NONE, F_SST_HL, F_SST_LL, F_DIC_HL, F_DIC_LL, F_DIC, F_PH, F_PCO2, F_ML, F_TAU_OH, F_FROZEN, F_CO3_HL, F_CO3_LL, F_CO3 };
+  enum Kind { F_NONE, F_SST_HL, F_SST_LL, F_DIC_HL, F_DIC_LL, F_DIC, F_PH, F_PCO2, F_ML, F_TAU_OH, F_FROZEN, F_CO3_HL, F_CO3_LL, F_CO3,
+              F_OMEGACA_HL, F_OMEGACA_LL, F_OMEGAAR_HL, F_OMEGAAR_LL };
   static const struct { const char *n; Kind k; } tab[] = {
       {"HL_sst", F_SST_HL}, {"LL_sst", F_SST_LL}, {"HL_DIC", F_DIC_HL}, {"LL_DIC", F_DIC_LL},
       {"DIC", F_DIC}, {"pH", F_PH}, {"PCO2", F_PCO2}, {"ML_ocean_c", F_ML}, {"TAU_OH", F_TAU_OH},
-      {"f_frozen", F_FROZEN}, {"HL_CO3", F_CO3_HL}, {"LL_CO3", F_CO3_LL}, {"CO3", F_CO3}};
+      {"f_frozen", F_FROZEN}, {"HL_CO3", F_CO3_HL}, {"LL_CO3", F_CO3_LL}, {"CO3", F_CO3},
+      {"HL_OmegaCa", F_OMEGACA_HL}, {"LL_OmegaCa", F_OMEGACA_LL}, {"HL_OmegaAr", F_OMEGAAR_HL},
+      {"LL_OmegaAr", F_OMEGAAR_LL}};
   Kind kind = F_NONE;
   for (const auto &e : tab)
     if (!strcmp(name, e.n)) kind = e.k;
@@ -1027,17 +1031,39 @@ int Engine::fetch_functions(const char *name, const double *dates, int n_dates, 
       if ((rc = rec("LL_ocean_c", 0, a)) || (rc = rec("HL_ocean_c", 0, b))) return 1;
       for (size_t q = 0; q < N; ++q) out[q] = a[q] + b[q];
       break;
+    case F_OMEGACA_HL: case F_OMEGACA_LL: case F_OMEGAAR_HL: case F_OMEGAAR_LL:
     case F_CO3_HL: case F_CO3_LL: case F_CO3: {
       /* carbonate of the year's last chemistry solve, from what that solve left on record:
        * PCO2o = [CO2*] 1e6 / Kh and pH = -log10 h give [CO2*] and h; with K1, K2 at the box
        * temperature DIC = [CO2*] (1 + K1/h + K1 K2/h^2) and CO3 = DIC / (1 + h/K2 + h^2/(K1 K2))
        * (ocean_csys.cpp:166-366; Kh Weiss 1974, K1 / K2 Mehrbach refit) */
       std::vector<double> sst, pco2[2], ph[2];
+      const double S = C.S;
       if ((rc = rec("sst", 1, sst))) return 1;
-      const bool need_hl = kind != F_CO3_LL, need_ll = kind != F_CO3_HL;
+      const bool omega = kind >= F_OMEGACA_HL;
+      const bool need_hl = kind == F_CO3_HL || kind == F_CO3 || kind == F_OMEGACA_HL || kind == F_OMEGAAR_HL;
+      const bool need_ll = kind == F_CO3_LL || kind == F_CO3 || kind == F_OMEGACA_LL || kind == F_OMEGAAR_LL;
+      /* saturation states: [CO3] [Ca] / Ksp with calcite's or aragonite's solubility product
+       * (Mucci 1983; ocean_csys.cpp:300-318, 362-364) */
+      auto omega_of = [&](double Tc, double co3_umol) {
+        const double Tk = Tc + 273.15;
+        const bool ca = kind == F_OMEGACA_HL || kind == F_OMEGACA_LL;
+        double t1, t2, t3;
+        if (ca) {
+          t1 = -171.9065 - 0.077993 * Tk + 2839.319 / Tk + 71.595 * std::log10(Tk);
+          t2 = +(-0.77712 + 0.0028426 * Tk + 178.34 / Tk) * std::sqrt(S);
+          t3 = -0.07711 * S + 0.0041249 * std::pow(S, 1.5);
+        } else {
+          t1 = -171.945 - 0.077993 * Tk + 2903.293 / Tk + 71.595 * std::log10(Tk);
+          t2 = +(-0.068393 + 0.0017276 * Tk + 88.135 / Tk) * std::sqrt(S);
+          t3 = -0.10018 * S + 0.0059415 * std::pow(S, 1.5);
+        }
+        const double Ksp = std::pow(10.0, t1 + t2 + t3);
+        const double calcium = 0.02128 / 40.087 * (S / 1.80655);
+        return ((co3_umol / 1e6 * calcium) / Ksp);
+      };
       if (need_hl && ((rc = rec("HL_PCO2", 0, pco2[0])) || (rc = rec("HL_pH", 0, ph[0])))) return 1;
       if (need_ll && ((rc = rec("LL_PCO2", 0, pco2[1])) || (rc = rec("LL_pH", 0, ph[1])))) return 1;
-      const double S = C.S;
       auto co3 = [&](double Tc, double PCO2o, double pH) {
         const double Tk = Tc + 273.15;
         const double tmp = 9345.17 / Tk - 60.2409 + 23.3585 * std::log(Tk / 100);
@@ -1052,7 +1078,8 @@ int Engine::fetch_functions(const char *name, const double *dates, int n_dates, 
       for (size_t q = 0; q < N; ++q) {
         const double hl = need_hl ? co3(sst[q] + 18.0 + -16.4, pco2[0][q], ph[0][q]) : 0.0;
         const double ll = need_ll ? co3(sst[q] + 18.0 + 2.9, pco2[1][q], ph[1][q]) : 0.0;
-        out[q] = kind == F_CO3_HL ? hl : kind == F_CO3_LL ? ll : part_low * ll + part_high * hl;
+        if (omega) out[q] = need_hl ? omega_of(sst[q] + 18.0 + -16.4, hl) : omega_of(sst[q] + 18.0 + 2.9, ll);
+        else out[q] = kind == F_CO3_HL ? hl : kind == F_CO3_LL ? ll : part_low * ll + part_high * hl;
       }
       break;
     }
@@ -1491,6 +1518,11 @@ int hx_get_param(hx_handle h, const char *name, double *out, int32_t n) {
         out[i] = h->bvec[ib][f].empty() ? h->bscalar[ib][f] : h->bvec[ib][f][i];
       return HX_OK;
     }
+  }
+  if (!strcmp(name, "baseyear")) { /* forcing_component.cpp getData(D_RF_BASEYEAR) */
+    if (n != h->M) return h->fail(HX_ERR_ARG, "hx_get_param: n != n_members");
+    for (int i = 0; i < n; ++i) out[i] = h->baseyear == 0.0 ? h->cfg.start_year + 1 : h->baseyear;
+    return HX_OK;
   }
   const int pi = h->find_param(name);
   if (pi < 0) {

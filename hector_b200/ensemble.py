@@ -117,7 +117,10 @@ FUNCTION_VARIABLES = {
     "ML_ocean_c": ["HL_ocean_c", "LL_ocean_c"], "TAU_OH": ["CH4_concentration"],
     "f_frozen": ["land_tas", "permafrost_c"],
     "HL_CO3": ["sst", "HL_PCO2", "HL_pH"], "LL_CO3": ["sst", "LL_PCO2", "LL_pH"],
-    "CO3": ["sst", "HL_PCO2", "HL_pH", "LL_PCO2", "LL_pH"]}
+    "CO3": ["sst", "HL_PCO2", "HL_pH", "LL_PCO2", "LL_pH"],
+    # not in R's ALL_VARS(), but the reference's getData and outputstream know them
+    "HL_OmegaCa": ["sst", "HL_PCO2", "HL_pH"], "LL_OmegaCa": ["sst", "LL_PCO2", "LL_pH"],
+    "HL_OmegaAr": ["sst", "HL_PCO2", "HL_pH"], "LL_OmegaAr": ["sst", "LL_PCO2", "LL_pH"]}
 
 DERIVED_VARIABLES = (["RF_BC", "RF_OC", "RF_SO2", "RF_NH3", "RF_aci", "RF_vol", "RF_albedo",
                       "RF_misc", "RF_O3_trop", "RF_H2O_strat"]

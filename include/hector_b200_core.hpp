@@ -203,6 +203,8 @@ inline unit_types units_of(const std::string &v) {
       {"DIC", U_UMOL_KG}, {"pH", U_PH}, {"PCO2", U_UATM}, {"ML_ocean_c", U_PGC}, {"TAU_OH", U_YRS},
       {"HL_ocean_uptake", U_PGC_YR}, {"LL_ocean_uptake", U_PGC_YR}, {"rh_det", U_PGC_YR},
       {"rh_soil", U_PGC_YR},
+      {"HL_OmegaCa", U_UNITLESS}, {"LL_OmegaCa", U_UNITLESS}, {"HL_OmegaAr", U_UNITLESS},
+      {"LL_OmegaAr", U_UNITLESS}, {"baseyear", U_UNITLESS},
       {"f_frozen", U_UNITLESS}, {"HL_CO3", U_UMOL_KG}, {"LL_CO3", U_UMOL_KG}, {"CO3", U_UMOL_KG},
       {"rh_ch4", U_PGC_YR}, {"HL_pH", U_PH}, {"LL_pH", U_PH}, {"HL_PCO2", U_UATM},
       {"LL_PCO2", U_UATM}, {"CH4_concentration", U_PPBV_CH4}, {"N2O_concentration", U_PPBV_N2O},
@@ -678,6 +680,8 @@ class EnsembleCore {
         "IO_ocean_c", "DO_ocean_c", "RF_CH4", "RF_N2O", "rh_ch4", "NPP", "RH", "gmst",
         "ocean_tas", "heatflux_mixed", "heatflux_interior", "ocean_timesteps"};
     std::vector<std::string> names(all, all + sizeof all / sizeof all[0]);
+    if (biomes_.size() <= 1) /* the per-stash outputs of the outputstream (single biome only) */
+      for (const char *v : {"HL_ocean_uptake", "LL_ocean_uptake", "rh_det", "rh_soil"}) names.push_back(v);
     if (biomes_.size() > 1) { /* "<biome>.<name>": every biome's own pools and fluxes */
       static const char *const own[] = {"veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c", "NPP", "RH"};
       for (const std::string &b : biomes_)

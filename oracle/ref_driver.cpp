@@ -31,6 +31,7 @@
 #include "simpleNbox.hpp"
 #undef private
 #undef protected
+#include "csv_outputstream_visitor.hpp"
 #include "imodel_component.hpp"
 #include "ini_to_core_reader.hpp"
 #include "logger.hpp"
@@ -317,6 +318,31 @@ int ref_run_member(const char *ini_path, int n_over, const char **comps, const c
       }
     }
     if (run_seconds) *run_seconds = secs;
+  }
+  std::string keep = g_err;
+  ref_close(h);
+  g_err = keep;
+  return rc;
+}
+
+/* The reference's outputstream_<run>.csv (src/main.cpp:91-106: a CSVOutputStreamVisitor added
+ * to the core before prepareToRun) for a run from the ini's start date to `to_date`, written to
+ * `path`.  The text the compat visitor of include/compat is held to. */
+int ref_outputstream(const char *ini_path, double to_date, const char *path) {
+  int h = ref_open(ini_path);
+  if (h < 0) return -1;
+  int rc = 0;
+  try {
+    Core *core = Core::getcore(h);
+    std::ofstream f(path);
+    CSVOutputStreamVisitor visitor(f);
+    core->addVisitor(&visitor);
+    core->prepareToRun();
+    core->run(to_date < 0 ? core->getEndDate() : to_date);
+  } catch (h_exception &e) {
+    rc = fail(std::string("h_exception: ") + e.what());
+  } catch (std::exception &e) {
+    rc = fail(std::string("exception: ") + e.what());
   }
   std::string keep = g_err;
   ref_close(h);

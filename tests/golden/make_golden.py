@@ -686,8 +686,37 @@ def make_startdate():
                         perturbed_values=np.array([v for _, _, _, v in STARTDATE_PERTURBED]))
 
 
+OUTPUTSTREAM_YEARS = [1746, 1747, 1749, 1750, 1751, 1800, 1900, 2000, 2100]
+
+
+def make_outputstream():
+    """ref_outputstream_ssp245.txt: the rows the UNMODIFIED reference's CSVOutputStreamVisitor
+    writes for SSP2-4.5 (src/main.cpp:91-106 through oracle/ref_driver.cpp ref_outputstream), the
+    model years OUTPUTSTREAM_YEARS only (the whole file has 118 rows a year) -- row order,
+    component and variable names, units text and the four significant digits every value is
+    printed with (the forcing visitor sets precision(4) and returns early before the base year
+    without restoring it, src/csv_outputstream_visitor.cpp:143-147)."""
+    import ctypes as C
+    import tempfile
+    from oracle import ref
+    L = ref.lib()
+    L.ref_outputstream.argtypes = [C.c_char_p, C.c_double, C.c_char_p]
+    tmp = os.path.join(tempfile.mkdtemp(), "os.csv")
+    assert L.ref_outputstream(os.path.join(REF, "inst/input/hector_ssp245.ini").encode(), 2100.0,
+                              tmp.encode()) == 0, L.ref_last_error()
+    keep = []
+    for line in open(tmp).read().splitlines()[2:]:
+        c = line.split(",")
+        if c[2] == "0" and int(c[0]) in OUTPUTSTREAM_YEARS:
+            keep.append(line)
+    open(os.path.join(OUT, "ref_outputstream_ssp245.txt"), "w").write("\n".join(keep) + "\n")
+    print("outputstream rows kept:", len(keep))
+
+
 if __name__ == "__main__":
-    if "more" in sys.argv[1:]:
+    if "outputstream" in sys.argv[1:]:
+        make_outputstream()
+    elif "more" in sys.argv[1:]:
         make_more_outputs()
     elif "startdate" in sys.argv[1:]:
         make_startdate()
@@ -716,3 +745,4 @@ if __name__ == "__main__":
         make_picontrol()
         make_startdate()
         make_more_outputs()
+        make_outputstream()

@@ -86,10 +86,14 @@ def test_cli_runs_ssp245_and_matches_the_oracle(programs, tmp_path):
         assert run == "ssp245" and spin == "0"
         seen.setdefault(var, {})[int(y)] = (float(val), comp, units)
     assert set(seen["CO2_concentration"]) == set(range(1746, 2301))
-    for var, digits in (("CO2_concentration", 6), ("global_tas", 6), ("RF_tot", 4), ("HL_pH", 6),
-                        ("veg_c", 6), ("ocean_uptake", 6)):
+    # four significant digits everywhere, like the reference's own file (see the visitor's header)
+    for var, digits in (("CO2_concentration", 4), ("global_tas", 4), ("RF_tot", 4), ("HL_pH", 4),
+                        ("veg_c", 4), ("ocean_uptake", 4)):
         ref = out[port.OUT_NAMES.index(var)]
         for y in (1746, 1850, 2000, 2100, 2300):
+            if var == "RF_tot" and y < 1750:    # forcings are printed from the base year on
+                assert y not in seen[var]
+                continue
             got = seen[var][y][0]
             want = float("%.*g" % (digits, ref[y - 1746]))   # the stream's significant digits
             assert abs(got - want) <= 1.01 * 10.0 ** (np.floor(np.log10(max(abs(want), 1e-300))) - digits + 1) \
@@ -98,6 +102,28 @@ def test_cli_runs_ssp245_and_matches_the_oracle(programs, tmp_path):
     assert seen["RF_tot"][2100][1:] == ("forcing", "W/m2")
     # tracking is off in the shipped ini: the tracking file exists and is empty
     assert os.path.getsize(tmp_path / "output" / "tracking_ssp245.csv") == 0
+    # Row for row against the UNMODIFIED reference's own outputstream (tests/golden/
+    # ref_outputstream_ssp245.txt, nine model years): the same rows in the same order with the
+    # same component, variable and units text, values equal to the printed four digits (one unit
+    # of the last digit where 1e-10 of difference crosses a rounding boundary) -- but for the
+    # rows the engine has no number for
+    skipped = {"HL_downwelling", "HL_Revelle", "LL_Revelle", "atmos_c_residual", "slr", "slr_no_ice",
+               "sl_rc", "sl_rc_no_ice"}
+    ref_rows = [r for r in csv.reader(open(os.path.join(os.path.dirname(__file__), "golden",
+                                                        "ref_outputstream_ssp245.txt")))
+                if r[4] not in skipped]
+    years = sorted({int(r[0]) for r in ref_rows})
+    mine = [r for r in rows if int(r[0]) in years]
+    assert [r[:5] + r[6:] for r in mine] == [r[:5] + r[6:] for r in ref_rows]
+    worst = 0.0
+    for a, b in zip(mine, ref_rows):
+        got, want = float(a[5]), float(b[5])
+        ulp4 = 10.0 ** (np.floor(np.log10(max(abs(want), 1e-300))) - 3)
+        assert abs(got - want) <= 1.01 * ulp4 or abs(got - want) < 1e-12, (a, b)
+        worst = max(worst, abs(got - want) / ulp4 if want else 0.0)
+    same = sum(a[5] == b[5] for a, b in zip(mine, ref_rows))
+    print("outputstream rows compared: %d, textually identical values: %d" % (len(mine), same))
+    assert same >= 0.99 * len(mine)
 
 
 @pytest.mark.gpu
