@@ -1266,9 +1266,9 @@ int hx_set_scenario_series(hx_handle h, int32_t scenario_id, const char *name, i
   if (scenario_id < 0 || scenario_id >= h->nscen) return h->fail(HX_ERR_ARG, "bad scenario id");
   const int ci = Engine::find_constraint(name);
   if (ci >= 0) {
-    if (h->prepared && h->d_GP)
-      return h->fail(HX_ERR_UNSUPPORTED, "constraints cannot be added to a run with per-member N2O / "
-                                         "halocarbon parameters");
+    if (h->prepared && h->d_GP && (ci == CN_N2O || ci >= CN_HALO0))
+      return h->fail(HX_ERR_UNSUPPORTED, "an N2O or halocarbon concentration constraint cannot be added to a "
+                                         "run with per-member N2O / halocarbon parameters");
     /* a constraint series may cover any part of the run; NaN = no entry for that year */
     double *dst = h->cons[scenario_id].data() + (size_t)ci * h->nrow;
     for (int k = 0; k < n; ++k) { /* entries outside [year0, year0 + n) are kept */
@@ -1717,13 +1717,10 @@ int hx_prepare(hx_handle h) {
         const double *c = h->con(sc, series);
         for (int r = 0; r < nrow; ++r) gas_constraint = gas_constraint || c[r] == c[r];
       }
-    bool lo_active = h->pscalar[PI_LO_RATIO] != 0.0;
-    for (double v : h->pvec[PI_LO_RATIO]) lo_active = lo_active || v != 0.0;
-    if (tracking || nb > 1 || any_constraint || gas_constraint || lo_active ||
-        (h->cfg.flags & HX_FLAG_EXACT_ATTEMPTS))
-      return fail(HX_ERR_UNSUPPORTED, "per-member N2O / halocarbon parameters are available for plain "
-                                      "runs only (no tracking, biomes, constraints, lo_warming_ratio, "
-                                      "exact attempts)");
+    if (tracking || nb > 1 || gas_constraint || (h->cfg.flags & HX_FLAG_EXACT_ATTEMPTS))
+      return fail(HX_ERR_UNSUPPORTED, "per-member N2O / halocarbon parameters are not combined with carbon "
+                                      "tracking, biomes, N2O / halocarbon concentration constraints or "
+                                      "exact attempts");
     gas_tab.assign((size_t)h->nscen * nrow * HX_GAS_COLS, 0.0);
     for (int sc = 0; sc < h->nscen; ++sc) {
       const double *R = h->raw[sc].data();

@@ -1572,8 +1572,11 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
     return d.out_minimal ? launch_run_t<true, false, HX_TRACK_CTAS, false>(d, C, r0, r1, st)
                          : launch_run_t<true, false, HX_TRACK_CTAS>(d, C, r0, r1, st);
   }
-  if (d.GP) /* per-member N2O / halocarbon parameters: the GAS build (plain runs, every output) */
+  if (d.GP) { /* per-member N2O / halocarbon parameters: the GAS builds (every output) */
+    if (d.constrained > 1) return launch_run_t<false, true, 2, true, false, true, false, true>(d, C, r0, r1, st);
+    if (d.constrained) return launch_run_t<false, true, 2, true, false, false, false, true>(d, C, r0, r1, st);
     return launch_run_t<false, false, 2, true, false, false, false, true>(d, C, r0, r1, st);
+  }
   if (C.flags & HX_FLAG_EXACT_ATTEMPTS) { /* the builds that execute abandoned ODE attempts */
     if (d.constrained > 1) return launch_run_t<false, true, 2>(d, C, r0, r1, st); /* NBP: always exact */
     return d.constrained ? launch_run_t<false, true, 2, true, false, false, true>(d, C, r0, r1, st)

@@ -938,3 +938,69 @@ def test_parameter_responses_like_the_reference_tests():
     ratio3 = ens.fetch("land_tas", keep)[M - 1] / ens.fetch("ocean_tas", keep)[M - 1]
     assert (np.abs(3.0 - ratio3) <= 1e-5).all()
     ens.close()
+
+
+@pytest.mark.parametrize("kinds", [("CO2_constrain", "tas_constrain"), ("NBP_constrain", "CH4_constrain")],
+                         ids=["co2_tas", "nbp_ch4"])
+def test_per_member_gas_parameters_with_constraints(kinds):
+    """the GAS builds with the constraint machinery (with and without NBP) and a land-ocean ratio:
+    per-member N2O / halocarbon parameters together with user constraints against the oracle; an
+    N2O concentration constraint stays refused"""
+    from oracle import port
+    import hector_b200 as hb
+    from tests.test_gpu_fuzz import SRC
+    M = 16
+    rng = np.random.default_rng(43)
+    raw = util.scenarios()["ssp245"]
+    d = port.default_params()
+    per = {"N0": d.N0 * rng.uniform(0.97, 1.03, M), "TN2O0": d.TN2O0 * rng.uniform(0.9, 1.1, M),
+           "S": rng.uniform(2.0, 5.0, M), "lo_warming_ratio": np.where(rng.random(M) < 0.5, 1.5, 0.0)}
+    gases = ["CF4", "CFC12", "HFC23"]
+    gidx = [port.HALOS.index(g) for g in gases]
+    for g, k in zip(gases, gidx):
+        per[g + ".tau"] = d.halo_tau[k] * rng.uniform(0.7, 1.4, M)
+        per[g + ".rho"] = d.halo_rho[k] * rng.uniform(0.8, 1.2, M)
+    _, _, base, _, _ = port.run_member(raw)
+    spec = {}
+    for k in kinds:
+        series = base[port.OUT_NAMES.index(SRC[k])]
+        a = int(rng.integers(1850, 2050)); b = a + int(rng.integers(5, 40))
+        scale = 0.3 if k in ("NBP_constrain", "tas_constrain") else 0.03
+        spec[k] = {y: float(series[y - 1746] * (1 + scale * rng.normal())) for y in range(a, b + 1)}
+    outs = ["CO2_concentration", "global_tas", "RF_tot", "N2O_concentration", "RF_N2O", "NBP", "land_tas",
+            "ocean_timesteps"]
+    ens = hb.Ensemble(M, raw, outputs=outs)
+    for k, v in per.items():
+        ens.setvar(k, v)
+    for name, dd in spec.items():
+        ens.setvar_series(name, sorted(dd), [dd[y] for y in sorted(dd)])
+    ens.run()
+    st, fy = ens.status()
+    got = ens.fetchvars(_years(), outs)
+    worst = {}
+    for i in range(M):
+        p = port.default_params(N0=per["N0"][i], TN2O0=per["TN2O0"][i], S=per["S"][i],
+                                lo_warming_ratio=per["lo_warming_ratio"][i])
+        for g, k in zip(gases, gidx):
+            p.halo_tau[k] = per[g + ".tau"][i]
+            p.halo_rho[k] = per[g + ".rho"][i]
+        ost, ofy, out = port.run_member_constrained(raw, spec, params=p)
+        assert (ost != 0) == (st[i] != 0) and (ost == 0 or ofy == fy[i]), (i, ost, ofy, st[i], fy[i])
+        n = 555 if not ost else ofy - 1746
+        for v in outs:
+            ref = out[port.OUT_NAMES.index(v)][:n]
+            if v == "ocean_timesteps":
+                assert np.array_equal(got[v][i][:n], ref)
+            else:
+                worst[v] = max(worst.get(v, 0.0), util.parity_err(got[v][i][:n], ref, v))
+    print(kinds, {k: "%.2g" % e for k, e in worst.items()})
+    assert max(worst.values()) < TOL, worst
+    with pytest.raises(hb.HxError):                       # after prepare: refused at once
+        ens.setvar_series("N2O_constrain", [2000], [330.0])
+    ens.close()
+    bad = hb.Ensemble(4, raw)
+    bad.setvar("CF4.tau", np.full(4, 40000.0))
+    bad.setvar_series("N2O_constrain", [2000], [330.0])
+    with pytest.raises(hb.HxError):
+        bad.prepare()
+    bad.close()
