@@ -1568,6 +1568,9 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
                          : launch_run_t<false, false, 2, true, true, false>(d, C, r0, r1, st);
   }
   if (d.T) { /* carbon tracking: the record-only builds */
+    if (d.GP) /* ... with per-member N2O / halocarbon parameters */
+      return d.constrained ? launch_run_t<true, true, HX_TRACK_CTAS, true, false, true, false, true>(d, C, r0, r1, st)
+                           : launch_run_t<true, false, HX_TRACK_CTAS, true, false, false, false, true>(d, C, r0, r1, st);
     if (d.constrained) return launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st);
     return d.out_minimal ? launch_run_t<true, false, HX_TRACK_CTAS, false>(d, C, r0, r1, st)
                          : launch_run_t<true, false, HX_TRACK_CTAS>(d, C, r0, r1, st);

@@ -338,11 +338,29 @@ def test_per_member_n2o_and_halocarbon_parameters():
         rel = np.where(np.arange(1, 556) >= base, hrf[1:, k] - hrf[base, k], 0.0)
         assert np.max(np.abs(derived["FadjSF6"][i] - rel)) < 1e-12
     # what the GAS build cannot be combined with is refused, not ignored
-    bad = hb.Ensemble(4, raw, tracking_date=1800)
+    bad = hb.Ensemble(4, raw, biomes=["a", "b"])
     bad.setvar("CF4.tau", np.full(4, 40000.0))
     with pytest.raises(hb.HxError):
         bad.prepare()
     bad.close()
+    # with carbon tracking: same trajectories bit for bit, the oracle's source maps
+    trk = hb.Ensemble(M, raw, outputs=outs, tracking_date=1800, track_every=100)
+    for k, v in per.items():
+        trk.setvar(k, v)
+    trk.run()
+    g2 = trk.fetchvars(_years(), outs)
+    for v in outs:
+        assert np.array_equal(g2[v], got[v]), v
+    for i in (0, 7):
+        p = port.default_params(N0=per["N0"][i], UC_N2O=per["UC_N2O"][i], TN2O0=per["TN2O0"][i], S=per["S"][i])
+        for g, k in zip(gases, gidx):
+            p.halo_tau[k] = per[g + ".tau"][i]; p.halo_rho[k] = per[g + ".rho"][i]
+            p.halo_delta[k] = per[g + ".delta"][i]; p.halo_H0[k] = per[g + ".H0"][i]
+        ost, _, out, frac, mask = port.run_member_tracked(raw, 1800, p)
+        for y in (1900, 2300):
+            f, km = trk.fetch_tracking(y)
+            assert np.array_equal(km[i], mask[y - 1746]) and np.abs(f[i] - frac[y - 1746]).max() < 1e-12
+    trk.close()
     ens.close()
 
 
