@@ -1717,9 +1717,9 @@ int hx_prepare(hx_handle h) {
         const double *c = h->con(sc, series);
         for (int r = 0; r < nrow; ++r) gas_constraint = gas_constraint || c[r] == c[r];
       }
-    if (nb > 1 || gas_constraint || (h->cfg.flags & HX_FLAG_EXACT_ATTEMPTS))
+    if (gas_constraint || (h->cfg.flags & HX_FLAG_EXACT_ATTEMPTS))
       return fail(HX_ERR_UNSUPPORTED, "per-member N2O / halocarbon parameters are not combined with "
-                                      "biomes, N2O / halocarbon concentration constraints or exact attempts");
+                                      "N2O / halocarbon concentration constraints or exact attempts");
     gas_tab.assign((size_t)h->nscen * nrow * HX_GAS_COLS, 0.0);
     for (int sc = 0; sc < h->nscen; ++sc) {
       const double *R = h->raw[sc].data();

@@ -1560,6 +1560,11 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
   /* biome-split pools: general builds (constraints and every output; no tracking), with and
    * without the NBP machinery */
   if (d.BF) {
+    if (d.GP) { /* ... with per-member N2O / halocarbon parameters */
+      if (d.constrained > 1) return launch_run_t<false, true, 2, true, true, true, false, true>(d, C, r0, r1, st);
+      if (d.constrained) return launch_run_t<false, true, 2, true, true, false, false, true>(d, C, r0, r1, st);
+      return launch_run_t<false, false, 2, true, true, false, false, true>(d, C, r0, r1, st);
+    }
     if (d.constrained > 1) return launch_run_t<false, true, 2, true, true, true>(d, C, r0, r1, st);
     if (d.constrained) return launch_run_t<false, true, 2, true, true, false>(d, C, r0, r1, st);
     /* no constraint, no lo_warming_ratio: the biome loops without the constraint machinery;

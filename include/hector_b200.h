@@ -149,7 +149,7 @@ int hx_set_member_scenario(hx_handle h, const int32_t *scenario_of_member, int32
  * 127-136) -- are scalars by default, and their 27 series are then computed once per scenario on
  * the host.  Given per member (hx_set_param, before hx_prepare) they move the 27 recurrences
  * into the run kernel (its GAS builds): with CO2 / NBP / CH4 / RF_tot / tas constraints,
- * lo_warming_ratio and carbon tracking too; with biomes, an N2O or halocarbon concentration
+ * lo_warming_ratio, carbon tracking and biomes too; with an N2O or halocarbon concentration
  * constraint or HX_FLAG_EXACT_ATTEMPTS hx_prepare returns HX_ERR_UNSUPPORTED. */
 int hx_set_param_scalar(hx_handle h, const char *name, double value);
 int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_t n);

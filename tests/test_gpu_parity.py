@@ -338,7 +338,7 @@ def test_per_member_n2o_and_halocarbon_parameters():
         rel = np.where(np.arange(1, 556) >= base, hrf[1:, k] - hrf[base, k], 0.0)
         assert np.max(np.abs(derived["FadjSF6"][i] - rel)) < 1e-12
     # what the GAS build cannot be combined with is refused, not ignored
-    bad = hb.Ensemble(4, raw, biomes=["a", "b"])
+    bad = hb.Ensemble(4, raw, exact_attempts=True)
     bad.setvar("CF4.tau", np.full(4, 40000.0))
     with pytest.raises(hb.HxError):
         bad.prepare()
