@@ -1690,8 +1690,9 @@ int hx_prepare(hx_handle h) {
   const int nb = h->n_biomes;
   C.n_biomes = nb;
   for (int i = 0; i < HX_MAX_BIOMES; ++i) C.biome_order[i] = i;
-  if ((h->cfg.flags & HX_FLAG_EXACT_ATTEMPTS) && (tracking || nb > 1))
-    return fail(HX_ERR_UNSUPPORTED, "HX_FLAG_EXACT_ATTEMPTS is available for plain and constraint runs only");
+  if ((h->cfg.flags & HX_FLAG_EXACT_ATTEMPTS) && (tracking || nb > 1) && h->gas_per_member())
+    return fail(HX_ERR_UNSUPPORTED, "HX_FLAG_EXACT_ATTEMPTS with per-member N2O / halocarbon parameters is "
+                                    "available without tracking and biomes only");
   if (nb > 1) {
     if (tracking)
       return fail(HX_ERR_UNSUPPORTED, "carbon tracking with more than one biome is not implemented");
@@ -1717,9 +1718,9 @@ int hx_prepare(hx_handle h) {
         const double *c = h->con(sc, series);
         for (int r = 0; r < nrow; ++r) gas_constraint = gas_constraint || c[r] == c[r];
       }
-    if (gas_constraint || (h->cfg.flags & HX_FLAG_EXACT_ATTEMPTS))
+    if (gas_constraint)
       return fail(HX_ERR_UNSUPPORTED, "per-member N2O / halocarbon parameters are not combined with "
-                                      "N2O / halocarbon concentration constraints or exact attempts");
+                                      "N2O / halocarbon concentration constraints");
     gas_tab.assign((size_t)h->nscen * nrow * HX_GAS_COLS, 0.0);
     for (int sc = 0; sc < h->nscen; ++sc) {
       const double *R = h->raw[sc].data();

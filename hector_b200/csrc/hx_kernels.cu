@@ -1559,7 +1559,11 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
    * its map traffic, not by occupancy, and spills badly at 168 registers. */
   /* biome-split pools: general builds (constraints and every output; no tracking), with and
    * without the NBP machinery */
+  const bool exact = (C.flags & HX_FLAG_EXACT_ATTEMPTS) != 0;
   if (d.BF) {
+    if (!d.GP && exact && d.constrained <= 1) /* abandoned ODE attempts executed (the NBP build always does) */
+      return d.constrained ? launch_run_t<false, true, 2, true, true, false, true>(d, C, r0, r1, st)
+                           : launch_run_t<false, false, 2, true, true, false, true>(d, C, r0, r1, st);
     if (d.GP) { /* ... with per-member N2O / halocarbon parameters */
       if (d.constrained > 1) return launch_run_t<false, true, 2, true, true, true, false, true>(d, C, r0, r1, st);
       if (d.constrained) return launch_run_t<false, true, 2, true, true, false, false, true>(d, C, r0, r1, st);
@@ -1577,15 +1581,19 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
       return d.constrained ? launch_run_t<true, true, HX_TRACK_CTAS, true, false, true, false, true>(d, C, r0, r1, st)
                            : launch_run_t<true, false, HX_TRACK_CTAS, true, false, false, false, true>(d, C, r0, r1, st);
     if (d.constrained) return launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st);
+    if (exact) return launch_run_t<true, false, HX_TRACK_CTAS, true, false, false, true>(d, C, r0, r1, st);
     return d.out_minimal ? launch_run_t<true, false, HX_TRACK_CTAS, false>(d, C, r0, r1, st)
                          : launch_run_t<true, false, HX_TRACK_CTAS>(d, C, r0, r1, st);
   }
   if (d.GP) { /* per-member N2O / halocarbon parameters: the GAS builds (every output) */
     if (d.constrained > 1) return launch_run_t<false, true, 2, true, false, true, false, true>(d, C, r0, r1, st);
+    if (exact)
+      return d.constrained ? launch_run_t<false, true, 2, true, false, false, true, true>(d, C, r0, r1, st)
+                           : launch_run_t<false, false, 2, true, false, false, true, true>(d, C, r0, r1, st);
     if (d.constrained) return launch_run_t<false, true, 2, true, false, false, false, true>(d, C, r0, r1, st);
     return launch_run_t<false, false, 2, true, false, false, false, true>(d, C, r0, r1, st);
   }
-  if (C.flags & HX_FLAG_EXACT_ATTEMPTS) { /* the builds that execute abandoned ODE attempts */
+  if (exact) { /* the builds that execute abandoned ODE attempts */
     if (d.constrained > 1) return launch_run_t<false, true, 2>(d, C, r0, r1, st); /* NBP: always exact */
     return d.constrained ? launch_run_t<false, true, 2, true, false, false, true>(d, C, r0, r1, st)
                          : launch_run_t<false, false, 2, true, false, false, true>(d, C, r0, r1, st);

@@ -62,7 +62,8 @@ typedef struct hx_engine *hx_handle;
 #define HX_FLAG_EXACT_ATTEMPTS 4u /* execute the ODE attempts the reference abandons whenever one of
                                     their stage states could go negative (slower build of the run
                                     kernel; without it such a member stops with
-                                    HX_MEMBER_NEEDS_EXACT).  Plain and constraint runs only. */
+                                    HX_MEMBER_NEEDS_EXACT).  Also with carbon tracking, biomes or per-member
+                                    N2O / halocarbon parameters (not the latter with either of the former). */
 #define HX_FLAG_KEEP_ORDER 8u    /* keep members in caller order on the device (default: members of a
                                     scenario are re-ordered so that the members of a warp behave
                                     alike; outputs are in caller order either way) */
@@ -149,8 +150,8 @@ int hx_set_member_scenario(hx_handle h, const int32_t *scenario_of_member, int32
  * 127-136) -- are scalars by default, and their 27 series are then computed once per scenario on
  * the host.  Given per member (hx_set_param, before hx_prepare) they move the 27 recurrences
  * into the run kernel (its GAS builds): with CO2 / NBP / CH4 / RF_tot / tas constraints,
- * lo_warming_ratio, carbon tracking and biomes too; with an N2O or halocarbon concentration
- * constraint or HX_FLAG_EXACT_ATTEMPTS hx_prepare returns HX_ERR_UNSUPPORTED. */
+ * lo_warming_ratio, carbon tracking, biomes and HX_FLAG_EXACT_ATTEMPTS too; with an N2O or
+ * halocarbon concentration constraint hx_prepare returns HX_ERR_UNSUPPORTED. */
 int hx_set_param_scalar(hx_handle h, const char *name, double value);
 int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_t n);
 /* same, from a DEVICE pointer (no host round trip) */

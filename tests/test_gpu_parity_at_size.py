@@ -306,3 +306,57 @@ def test_tracked_record_groups_are_bit_identical(tmp_path):
     for k in outs + ["frac"]:
         assert np.array_equal(a[k].view(np.uint64), b[k].view(np.uint64)), k
     assert np.array_equal(a["mask"], b["mask"])
+
+
+def test_exact_attempts_with_tracking_and_biomes():
+    """HX_FLAG_EXACT_ATTEMPTS with carbon tracking and with biomes: the members the default
+    builds refuse to decide (status 10) get the oracle's verdict and failing year"""
+    from oracle import port
+    import hector_b200 as hb
+    raw = util.scenarios()["ssp585"]
+    rng = np.random.default_rng(77)
+    M = 512
+    draw = {"S": rng.uniform(4.5, 9.0, M), "q10_rh": rng.uniform(2.5, 5.0, M),
+            "beta": rng.uniform(0.01, 0.4, M), "diff": rng.uniform(0.1, 1.0, M),
+            "detritus_c": rng.uniform(3.0, 40.0, M), "veg_c": rng.uniform(60.0, 400.0, M)}
+    outs = ["CO2_concentration", "global_tas", "ocean_timesteps"]
+    # tracking: the same members, the same verdicts as the untracked exact build
+    st = {}
+    for exact in (False, True):
+        ens = hb.Ensemble(M, raw, outputs=outs, exact_attempts=exact, tracking_date=1750, track_every=0)
+        for k, v in draw.items():
+            ens.setvar(k, v)
+        ens.run()
+        st[exact] = ens.status()
+        ens.close()
+    undecided = np.nonzero(st[False][0] == 10)[0]
+    print("tracked: members the default build refuses to decide:", len(undecided))
+    assert (st[True][0] != 10).all()
+    for i in list(undecided) + list(range(0, M, 37)):
+        ost, ofy, out, _, _ = port.run_member(raw, **{k: float(v[i]) for k, v in draw.items()})
+        assert (ost != 0) == (st[True][0][i] != 0) and (ost == 0 or ofy == st[True][1][i]), (i, ost, ofy)
+    same = st[False][0] != 10
+    assert np.array_equal(st[False][0][same], st[True][0][same]) and np.array_equal(st[False][1][same], st[True][1][same])
+    # two biomes that split the same pools evenly: the exact build decides every member
+    Mb = 128
+    for exact in (False, True):
+        ens = hb.Ensemble(Mb, raw, outputs=outs, exact_attempts=exact, biomes=["north", "south"])
+        for b in ("north", "south"):
+            ens.set_biome(b, veg_c=draw["veg_c"][:Mb] / 2, detritus_c=draw["detritus_c"][:Mb] / 2, soil_c=917.0 / 2,
+                          permafrost_c=865.0 / 2, npp_flux0=56.2 / 2, beta=draw["beta"][:Mb],
+                          q10_rh=draw["q10_rh"][:Mb], f_nppv=0.35, f_nppd=0.60, f_litterd=0.98)
+        ens.setvar("S", draw["S"][:Mb]); ens.setvar("diff", draw["diff"][:Mb])
+        ens.run()
+        st[exact] = ens.status()
+        ens.close()
+    undecided = np.nonzero(st[False][0] == 10)[0]
+    print("biomes: members the default build refuses to decide:", len(undecided))
+    assert (st[True][0] != 10).all()
+    for i in list(undecided)[:6] + list(range(0, Mb, 16)):
+        p = port.default_params()
+        half = dict(veg_c=draw["veg_c"][i] / 2, detritus_c=draw["detritus_c"][i] / 2, soil_c=917.0 / 2,
+                    permafrost_c=865.0 / 2, npp_flux0=56.2 / 2, beta=draw["beta"][i], q10_rh=draw["q10_rh"][i],
+                    f_nppv=0.35, f_nppd=0.60, f_litterd=0.98)
+        p.set_biomes({"north": dict(half), "south": dict(half)})
+        ost, ofy, out, _ = port.run_member_biomes(raw, p, S=float(draw["S"][i]), diff=float(draw["diff"][i]))
+        assert (ost != 0) == (st[True][0][i] != 0) and (ost == 0 or ofy == st[True][1][i]), (i, ost, ofy, st[True][0][i], st[True][1][i])
