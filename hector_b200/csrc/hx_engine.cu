@@ -1738,9 +1738,6 @@ int hx_prepare(hx_handle h) {
   /* the per-stash outputs (hx_layout.h, "scratch rows X") */
   bool want_x = false;
   for (int id : h->out_sel) want_x = want_x || (id >= OUT_UPTAKE_HL && id <= OUT_RH_SOIL);
-  if (want_x && nb > 1)
-    return fail(HX_ERR_UNSUPPORTED, "HL_ocean_uptake / LL_ocean_uptake / rh_det / rh_soil are not "
-                                    "recorded with more than one biome");
   if (tracking) {
     /* slabs per tracked launch (launch_rows): up to 4, from the memory the device has free --
      * two buffers of rec_group slab records, at most 45 % of it (HX_TRK_GROUP overrides) */

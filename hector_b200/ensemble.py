@@ -104,7 +104,8 @@ BIOME_PARAMETERS = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "npp_flux0"
 BIOME_OUTPUTS = ["veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c", "NPP", "RH"]
 
 # Per-stash quantities the run kernel records on request (scratch rows in global memory, the
-# all-output builds only; single biome): selected and fetched like OUTPUT_VARIABLES
+# all-output builds only; rh_det / rh_soil summed over the biomes): selected and fetched like
+# OUTPUT_VARIABLES
 STASH_OUTPUTS = ["HL_ocean_uptake", "LL_ocean_uptake", "rh_det", "rh_soil"]
 
 # The rest of the reference's outputstream variables that are plain functions of recorded outputs

@@ -224,8 +224,8 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
  * land_tas and permafrost_c; single biome), HL_CO3, LL_CO3, CO3 and the calcite / aragonite
  * saturation states HL_OmegaCa, LL_OmegaCa, HL_OmegaAr, LL_OmegaAr (from the recorded pCO2, pH
  * and sst).  HL_ocean_uptake, LL_ocean_uptake, rh_det and rh_soil are RECORDED outputs: select them
- * with hx_select_outputs (single biome; they cost two scratch rows of global memory traffic per
- * stash, so they are not part of the default set). */
+ * with hx_select_outputs (they cost scratch rows of global memory traffic per stash, so they are
+ * not part of the default set; with biomes rh_det and rh_soil are the sums over the biomes). */
 int hx_fetch(hx_handle h, const char *name, const double *dates, int32_t n_dates, double *out);
 /* device-resident view: pointer to the [year][member_stride] block of `name` (year index 0 =
  * start_year+1); valid until hx_destroy.  For NCCL gathers / zero-copy consumers. */

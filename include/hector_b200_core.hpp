@@ -680,8 +680,7 @@ class EnsembleCore {
         "IO_ocean_c", "DO_ocean_c", "RF_CH4", "RF_N2O", "rh_ch4", "NPP", "RH", "gmst",
         "ocean_tas", "heatflux_mixed", "heatflux_interior", "ocean_timesteps"};
     std::vector<std::string> names(all, all + sizeof all / sizeof all[0]);
-    if (biomes_.size() <= 1) /* the per-stash outputs of the outputstream (single biome only) */
-      for (const char *v : {"HL_ocean_uptake", "LL_ocean_uptake", "rh_det", "rh_soil"}) names.push_back(v);
+    for (const char *v : {"HL_ocean_uptake", "LL_ocean_uptake", "rh_det", "rh_soil"}) names.push_back(v);
     if (biomes_.size() > 1) { /* "<biome>.<name>": every biome's own pools and fluxes */
       static const char *const own[] = {"veg_c", "detritus_c", "soil_c", "permafrost_c", "thawedp_c", "NPP", "RH"};
       for (const std::string &b : biomes_)

@@ -543,6 +543,28 @@ def make_biomes():
                         spec=np.array(json.dumps(spec)))
 
 
+def make_biomes_stash():
+    """ref_biomes_stash.npz: the per-stash outputs (HL_ocean_uptake, LL_ocean_uptake, rh_det,
+    rh_soil -- the latter two summed over the biomes) of the first two multi-biome cases of
+    ref_biomes.npz, from the UNMODIFIED reference"""
+    import tempfile
+    from oracle import ref
+    tmp = tempfile.mkdtemp()
+    V = ["HL_ocean_uptake", "LL_ocean_uptake", "rh_det", "rh_soil", "RH", "ocean_uptake"]
+    names, vals = [], []
+    for name in list(BIOME_CASES)[:2]:
+        scn, biomes, params = BIOME_CASES[name]
+        assert "q10_rh_all" not in params and name not in BIOME_CONSTRAINTS
+        ini = os.path.join(tmp, name + ".ini")
+        biome_ini(scn, biomes, ini)
+        ok, err, o, _ = ref.run_member(ini, dict(params), V)
+        assert ok, err
+        names.append(name); vals.append(o[:len(V)])
+    np.savez_compressed(os.path.join(OUT, "ref_biomes_stash.npz"), names=np.array(names),
+                        variables=np.array(V), values=np.array(vals))
+    print("biomes_stash", names)
+
+
 ALLPARAM_VARS = ["CO2_concentration", "global_tas", "RF_tot", "HL_pH", "CH4_concentration",
                  "N2O_concentration", "O3_concentration", "veg_c", "soil_c", "permafrost_c",
                  "ocean_c", "heatflux"]
@@ -714,7 +736,9 @@ def make_outputstream():
 
 
 if __name__ == "__main__":
-    if "outputstream" in sys.argv[1:]:
+    if "biomes_stash" in sys.argv[1:]:
+        make_biomes_stash()
+    elif "outputstream" in sys.argv[1:]:
         make_outputstream()
     elif "more" in sys.argv[1:]:
         make_more_outputs()
@@ -746,3 +770,4 @@ if __name__ == "__main__":
         make_startdate()
         make_more_outputs()
         make_outputstream()
+        make_biomes_stash()
