@@ -338,11 +338,22 @@ def test_per_member_n2o_and_halocarbon_parameters():
         rel = np.where(np.arange(1, 556) >= base, hrf[1:, k] - hrf[base, k], 0.0)
         assert np.max(np.abs(derived["FadjSF6"][i] - rel)) < 1e-12
     # what the GAS build cannot be combined with is refused, not ignored
-    bad = hb.Ensemble(4, raw, exact_attempts=True)
+    bad = hb.Ensemble(4, raw, exact_attempts=True, tracking_date=1800)
     bad.setvar("CF4.tau", np.full(4, 40000.0))
     with pytest.raises(hb.HxError):
         bad.prepare()
     bad.close()
+    ok = hb.Ensemble(4, raw, outputs=outs, exact_attempts=True)   # the exact GAS build exists
+    ok.setvar("CF4.tau", per["CF4.tau"][:4]); ok.setvar("S", per["S"][:4]); ok.setvar("N0", per["N0"][:4])
+    ok.setvar("UC_N2O", per["UC_N2O"][:4]); ok.setvar("TN2O0", per["TN2O0"][:4])
+    for g in gases:
+        for f in (".tau", ".rho", ".delta", ".H0"):
+            ok.setvar(g + f, per[g + f][:4])
+    ok.run()
+    g3 = ok.fetchvars(_years(), outs)
+    for v in outs:
+        assert np.array_equal(g3[v], got[v][:4]), v
+    ok.close()
     # with carbon tracking: same trajectories bit for bit, the oracle's source maps
     trk = hb.Ensemble(M, raw, outputs=outs, tracking_date=1800, track_every=100)
     for k, v in per.items():
@@ -782,6 +793,9 @@ def test_function_outputs_vs_reference_golden(case):
     for v in hb.FUNCTION_VARIABLES:
         got = ens.fetch(v, _years())
         assert np.array_equal(got[0], got[1])
+        if v not in case["values"]:      # the saturation states: only the outputstream prints them
+            assert v.endswith(("OmegaCa", "OmegaAr")) and (got[0] > 0.5).all() and (got[0] < 10).all()
+            continue                     # (pinned by tests/test_compat.py against the reference's file)
         ref = case["values"][v]
         worst[v] = float(np.max(np.abs(got[0] - ref) / np.maximum(np.abs(ref), 1e-3)))
     print({k: "%.2g" % e for k, e in sorted(worst.items(), key=lambda kv: -kv[1])})
