@@ -1152,6 +1152,10 @@ int Engine::fetch_functions(const char *name, const double *dates, int n_dates, 
 
 using hx::kParams;
 
+#ifndef HX_REORDER_MAX_OUTPUTS
+#define HX_REORDER_MAX_OUTPUTS 20
+#endif
+
 static int ensure_copy_stream(hx_engine *h) {
   if (h->copy_stream) return HX_OK;
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1611,7 +1615,14 @@ int hx_prepare(hx_handle h) {
       if (!h->pvec[pi].empty() && std::find(dims.begin(), dims.end(), pi) == dims.end()) dims.push_back(pi);
     for (int s = 0; s < h->nscen; ++s) {
       std::vector<int> &ix = of_scen[s];
-      if (!dims.empty() && !(h->cfg.flags & HX_FLAG_KEEP_ORDER)) {
+      /* ... at a price: the outputs are stored in API order, so a warp of re-ordered members
+       * scatters every output row it writes over 32 sectors.  Two outputs cost 1.8 GB of extra
+       * DRAM traffic against a 13 % faster year loop; with every output recorded the scattered
+       * stores take over (65 536 members: 52.3 ms re-ordered against 33.6 ms in caller order,
+       * the crossover near 20 outputs, tools/profile_outputs.py), so runs that record more than
+       * HX_REORDER_MAX_OUTPUTS variables keep the caller's order. */
+      const bool reorder = !(h->cfg.flags & HX_FLAG_KEEP_ORDER) && (int)h->out_sel.size() <= HX_REORDER_MAX_OUTPUTS;
+      if (!dims.empty() && reorder) {
         /* iterative k-d ordering: (lo, hi, depth) ranges split at the median of one parameter */
         struct Range { int lo, hi, depth; };
         std::vector<Range> todo(1, Range{0, (int)ix.size(), 0});
