@@ -1861,7 +1861,8 @@ int hx_prepare(hx_handle h) {
   d.slab_done = nullptr;
   d.out_minimal = 1;
   for (int s = 0; s < nsel; ++s)
-    if (h->out_sel[s] != OUT_CO2 && h->out_sel[s] != OUT_TAS) d.out_minimal = 0;
+    if (h->out_sel[s] == OUT_RF_TOT || h->out_sel[s] == OUT_RF_CO2) d.out_minimal = d.out_minimal ? 2 : 0;
+    else if (h->out_sel[s] != OUT_CO2 && h->out_sel[s] != OUT_TAS) d.out_minimal = 0;
 
   h->prepared = true; /* upload_param / set_param paths need the buffers */
   for (int pi = 0; pi < PI_COUNT; ++pi) {

@@ -630,7 +630,8 @@ __device__ __noinline__ void nan_fill_rows(const HxDev &d, int nyears, int col, 
 
 /* LAT: the build for ensembles so small that every warp has a scheduler to itself (latency of one
  * warp is all that counts; code size is not): see integrate<.., RKU> */
-template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES, bool NBP, bool EXACT, bool GAS, bool LAT>
+template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT, bool BIOMES, bool NBP, bool EXACT, bool GAS, bool LAT,
+          bool RF4>
 __global__ void __launch_bounds__(HX_BLOCK, MINCTAS)
 hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C, int r0, int r1) {
   /* dynamic shared memory (> 48 KB): scenario slabs | row 0 | chemistry constants | RK stages */
@@ -1220,10 +1221,15 @@ hx_run_kernel(const __grid_constant__ HxDev d, const __grid_constant__ HxConst C
   } while (0)
         EMIT(OUT_CO2, CO2_conc);
         EMIT(OUT_TAS, tas);
-        if (ALLOUT) { /* the default outputs (CO2, Tgav) have a build without the other thirty:
-                         less code in the year body is worth 5 % (36.5 -> 34.6 ms) */
+        if (ALLOUT || RF4) { /* R's default fetchvars are CO2, RF_tot, RF_CO2, Tgav (R/messages.R:47-52):
+                                the RF4 builds are the CO2 / Tgav-only ones plus these two rows
+                                (26.4 against 28.5 ms in the all-output build; the CO2 / Tgav-only
+                                build itself would lose 0.5 % carrying them) */
         EMIT(OUT_RF_TOT, rf_tot);
         EMIT(OUT_RF_CO2, rf_co2);
+        }
+        if (ALLOUT) { /* the default outputs have a build without the other thirty:
+                         less code in the year body is worth 5 % (36.5 -> 34.6 ms) */
         EMIT(OUT_HEATFLUX, heatflux);
         EMIT(OUT_OCEAN_C, mb.bDO + mb.bIO + mb.bLL + mb.bHL);
         if (d.out_slot[OUT_HL_PH] >= 0) EMIT(OUT_HL_PH, -hx_log10(mb.S[SI_H_HL * HX_TILE]));
@@ -1520,7 +1526,7 @@ cudaError_t launch_spinup_one(const HxDev &d, const HxConst &C, int member, cuda
   return cudaGetLastError();
 }
 template <bool TRACK, bool CONSTR, int MINCTAS, bool ALLOUT = true, bool BIOMES = false,
-          bool NBP = CONSTR, bool EXACT = false, bool GAS = false, bool LAT = false>
+          bool NBP = CONSTR, bool EXACT = false, bool GAS = false, bool LAT = false, bool RF4 = false>
 static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
   /* the function attribute and the occupancy are per device (context): one cache slot per
    * device ordinal, so that engines on several GPUs can live in one process */
@@ -1530,13 +1536,13 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   if (e0 != cudaSuccess) return e0;
   if (dev < 0 || dev >= HX_MAX_DEVICES) return cudaErrorInvalidDevice;
   if (!resident_of[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT>,
+    cudaError_t e = cudaFuncSetAttribute(hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT, RF4>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)run_smem_bytes<MINCTAS, LAT>());
     if (e != cudaSuccess) return e;
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT>,
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT, RF4>,
                                                       HX_BLOCK, run_smem_bytes<MINCTAS, LAT>());
     if (e != cudaSuccess) return e;
     resident_of[dev] = sms * (per_sm > 0 ? per_sm : 1);
@@ -1548,7 +1554,7 @@ static cudaError_t launch_run_t(const HxDev &d, const HxConst &C, int r0, int r1
   const int nslab = (r1 - r0 + HX_SLAB_YEARS - 1) / HX_SLAB_YEARS;
   cudaError_t e = cudaMemsetAsync(d.sched, 0, (size_t)(ntiles + 1 + nslab) * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT><<<grid, HX_BLOCK, run_smem_bytes<MINCTAS, LAT>(), st>>>(d, C, r0, r1);
+  hx_run_kernel<TRACK, CONSTR, MINCTAS, ALLOUT, BIOMES, NBP, EXACT, GAS, LAT, RF4><<<grid, HX_BLOCK, run_smem_bytes<MINCTAS, LAT>(), st>>>(d, C, r0, r1);
   return cudaGetLastError();
 }
 cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStream_t st) {
@@ -1573,7 +1579,7 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
     if (d.constrained) return launch_run_t<false, true, 2, true, true, false>(d, C, r0, r1, st);
     /* no constraint, no lo_warming_ratio: the biome loops without the constraint machinery;
      * CO2 / Tgav only: without the other outputs' code either */
-    return d.out_minimal ? launch_run_t<false, false, 2, false, true, false>(d, C, r0, r1, st)
+    return d.out_minimal == 1 ? launch_run_t<false, false, 2, false, true, false>(d, C, r0, r1, st)
                          : launch_run_t<false, false, 2, true, true, false>(d, C, r0, r1, st);
   }
   if (d.T) { /* carbon tracking: the record-only builds */
@@ -1582,7 +1588,7 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
                            : launch_run_t<true, false, HX_TRACK_CTAS, true, false, false, false, true>(d, C, r0, r1, st);
     if (d.constrained) return launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st);
     if (exact) return launch_run_t<true, false, HX_TRACK_CTAS, true, false, false, true>(d, C, r0, r1, st);
-    return d.out_minimal ? launch_run_t<true, false, HX_TRACK_CTAS, false>(d, C, r0, r1, st)
+    return d.out_minimal == 1 ? launch_run_t<true, false, HX_TRACK_CTAS, false>(d, C, r0, r1, st)
                          : launch_run_t<true, false, HX_TRACK_CTAS>(d, C, r0, r1, st);
   }
   if (d.GP) { /* per-member N2O / halocarbon parameters: the GAS builds (every output) */
@@ -1606,7 +1612,7 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
     return small ? launch_run_t<false, true, 2>(d, C, r0, r1, st)
                  : launch_run_t<false, true, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
   if (d.constrained) {   /* the other constraints, lo_warming_ratio: no NBP machinery */
-    if (d.out_minimal)
+    if (d.out_minimal == 1)
       return small ? launch_run_t<false, true, 2, false, false, false>(d, C, r0, r1, st)
                    : launch_run_t<false, true, HX_RUN_MIN_CTAS, false, false, false>(d, C, r0, r1, st);
     return small ? launch_run_t<false, true, 2, true, false, false>(d, C, r0, r1, st)
@@ -1616,9 +1622,12 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
   /* (HX_NO_LAT=1 keeps small ensembles on the general build: sanitizer runs of that build) */
   static const bool no_lat = std::getenv("HX_NO_LAT") != nullptr;
   const bool lone = !no_lat && d.Mpad / HX_BLOCK <= sms;
-  if (d.out_minimal)
+  if (d.out_minimal == 1)
     return lone ? launch_run_t<false, false, 2, false, false, false, false, false, true>(d, C, r0, r1, st)
                 : launch_run_t<false, false, HX_RUN_MIN_CTAS, false>(d, C, r0, r1, st);
+  if (d.out_minimal == 2) /* R's default four: the CO2 / Tgav-only builds plus RF_tot and RF_CO2 */
+    return lone ? launch_run_t<false, false, 2, false, false, false, false, false, true, true>(d, C, r0, r1, st)
+                : launch_run_t<false, false, HX_RUN_MIN_CTAS, false, false, false, false, false, false, true>(d, C, r0, r1, st);
   return lone ? launch_run_t<false, false, 2, true, false, false, false, false, true>(d, C, r0, r1, st)
               : launch_run_t<false, false, HX_RUN_MIN_CTAS>(d, C, r0, r1, st);
 }

@@ -59,7 +59,8 @@ struct HxDev {
                                    OUT_COUNT on are the per-biome outputs */
   int32_t constrained;      /* 0 none; 1 some scenario carries a CO2 / CH4 / RF_tot / tas
                                constraint or a member a lo_warming_ratio; 2 an NBP constraint */
-  int32_t out_minimal;      /* only CO2_concentration and/or global_tas are recorded */
+  int32_t out_minimal;      /* 1: only CO2_concentration and/or global_tas are recorded; 2: only those
+                               and RF_tot / RF_CO2 (R's default four); 0: anything else */
   int32_t n_out;            /* recorded outputs (slots of `out`) */
   /* hx_run_stream: [slabs of the launch] in mapped host memory, set to 1 when every tile has
    * finished the slab -- the host copies a slab's output rows out while later slabs still run

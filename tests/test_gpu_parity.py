@@ -1036,3 +1036,26 @@ def test_per_member_gas_parameters_with_constraints(kinds):
     with pytest.raises(hb.HxError):
         bad.prepare()
     bad.close()
+
+
+@pytest.mark.parametrize("M", [200, 40000], ids=["latency_build", "general_build"])
+def test_default_four_outputs_build_is_bit_identical(M):
+    """R's default fetchvars (CO2, RF_tot, RF_CO2, Tgav) takes the RF4 builds -- the CO2 / Tgav-only
+    builds plus two output rows: bit for bit what the all-output and the CO2 / Tgav-only builds
+    record, in the latency build (at most one CTA per SM) and in the general one"""
+    import hector_b200 as hb
+    r4 = ["CO2_concentration", "RF_tot", "RF_CO2", "global_tas"]
+    X = util.lhs(M, seed=5)
+    res = {}
+    for outs in (["CO2_concentration", "global_tas"], r4, r4 + ["veg_c"], ["RF_tot"]):
+        ens = _engine(M, outputs=outs)
+        for j, n in enumerate(["S", "q10_rh", "beta", "diff"]):
+            ens.setvar(n, X[:, j])
+        ens.run()
+        res[tuple(outs)] = ens.fetchvars(_years(), outs)
+        ens.close()
+    for v in r4:
+        assert np.array_equal(res[tuple(r4)][v], res[tuple(r4 + ["veg_c"])][v]), v
+    for v in ("CO2_concentration", "global_tas"):
+        assert np.array_equal(res[("CO2_concentration", "global_tas")][v], res[tuple(r4)][v]), v
+    assert np.array_equal(res[("RF_tot",)]["RF_tot"], res[tuple(r4)]["RF_tot"])
