@@ -13,7 +13,7 @@ HX_FLAG_NO_SPINUP = 2
 HX_FLAG_EXACT_ATTEMPTS = 4
 HX_FLAG_KEEP_ORDER = 8
 
-EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "hx_ini_string", "hx_destroy", "hx_last_error", "hx_set_stream", "hx_set_scenario_series",
+EXPORTS = ["hx_create", "hx_create_from_ini", "hx_ini_read", "hx_ini_scalar", "hx_ini_string", "hx_destroy", "hx_last_error", "hx_set_stream", "hx_set_scenario_series", "hx_set_param_member",
            "hx_set_scenario_table", "hx_set_member_scenario", "hx_set_param_scalar",
            "hx_set_param", "hx_set_param_device", "hx_get_param", "hx_select_outputs",
            "hx_prepare", "hx_run", "hx_run_stream", "hx_reset", "hx_reset_date", "hx_synchronize", "hx_fetch", "hx_output_device",
@@ -65,6 +65,7 @@ def lib():
     L.hx_set_member_scenario.argtypes = [vp, ip, C.c_int32]
     L.hx_set_param_scalar.argtypes = [vp, C.c_char_p, C.c_double]
     L.hx_set_param.argtypes = [vp, C.c_char_p, dp, C.c_int32]
+    L.hx_set_param_member.argtypes = [vp, C.c_char_p, C.c_int32, C.c_double]
     L.hx_set_param_device.argtypes = [vp, C.c_char_p, vp, C.c_int32]
     L.hx_get_param.argtypes = [vp, C.c_char_p, dp, C.c_int32]
     L.hx_select_outputs.argtypes = [vp, C.c_int32, C.POINTER(C.c_char_p)]

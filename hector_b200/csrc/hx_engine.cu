@@ -1492,6 +1492,38 @@ int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_
   return HX_OK;
 }
 
+/* one member's value of a per-member parameter (Core::sendMessage(M_SETDATA) addressed to one
+ * core of an ensemble): the host copy and, once prepared, the one device element */
+int hx_set_param_member(hx_handle h, const char *name, int32_t member, double value) {
+  if (!h || !name) return HX_ERR_ARG;
+  if (member < 0 || member >= h->M) return h->fail(HX_ERR_ARG, "member index out of range");
+  int ib, f;
+  const int pi = h->find_param(name);
+  const bool general = h->find_biome_param(name, ib, f) || pi < 0 || pi == PI_N0 || h->pvec_on_device_only[pi] ||
+                       (h->n_biomes > 1 && Engine::is_biome_replaced(pi));
+  if (general) { /* biome / gas parameters, device-resident vectors: through the whole vector */
+    std::vector<double> cur((size_t)h->M);
+    int rc = hx_get_param(h, name, cur.data(), h->M);
+    if (rc) return rc;
+    cur[member] = value;
+    return hx_set_param(h, name, cur.data(), h->M);
+  }
+  if (h->pvec[pi].empty()) h->pvec[pi].assign((size_t)h->M, h->pscalar[pi]);
+  h->pvec[pi][member] = value;
+  if (h->prepared) {
+    cudaSetDevice(h->cfg.device);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(h->d_P + HX_TILED(pi, h->dev_of_api[member], PD_COUNT), &value, sizeof(double),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return h->fail(HX_ERR_CUDA, std::string("hx_set_param_member: ") + cudaGetErrorString(e));
+    h->params_dirty = true;
+    h->dirty_from_row = 0;
+    if (Engine::affects_spinup(pi)) h->spinup_dirty = true;
+  }
+  return HX_OK;
+}
+
 int hx_set_param_device(hx_handle h, const char *name, const double *dev, int32_t n) {
   if (!h || !name || !dev) return HX_ERR_ARG;
   if (!h->prepared) return h->fail(HX_ERR_STATE, "hx_set_param_device needs hx_prepare first");

@@ -318,6 +318,10 @@ class Ensemble:
             v = np.ascontiguousarray(values, dtype=np.float64)
             self._chk(self.L.hx_set_param(self.h, name.encode(), _dp(v), v.size))
 
+    def setvar_member(self, name, member, value):
+        """setvar addressed to ONE member (the others keep their values)"""
+        self._chk(self.L.hx_set_param_member(self.h, name.encode(), int(member), float(value)))
+
     def setvar_series(self, name, years, values, scenario=0):
         """R setvar(core, dates, var, values): a dated input of one scenario -- an emissions
         series (must cover start..end) or a user constraint (CO2_constrain, NBP_constrain, tas_constrain,

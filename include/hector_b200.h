@@ -154,6 +154,9 @@ int hx_set_member_scenario(hx_handle h, const int32_t *scenario_of_member, int32
  * halocarbon concentration constraint hx_prepare returns HX_ERR_UNSUPPORTED. */
 int hx_set_param_scalar(hx_handle h, const char *name, double value);
 int hx_set_param(hx_handle h, const char *name, const double *per_member, int32_t n);
+/* one member's value (the other members keep theirs; a scalar parameter becomes per-member):
+ * Core::sendMessage(M_SETDATA, var, value) addressed to one core of an ensemble */
+int hx_set_param_member(hx_handle h, const char *name, int32_t member, double value);
 /* same, from a DEVICE pointer (no host round trip) */
 int hx_set_param_device(hx_handle h, const char *name, const double *per_member_dev, int32_t n);
 int hx_get_param(hx_handle h, const char *name, double *per_member_out, int32_t n);

@@ -455,11 +455,10 @@ class EnsembleCore {
       } else if (n_ == 1) {
         c = SetCall::scalar(datum, (double)v);
       } else {
+        /* one member of an ensemble: one element on the host and on the device (a journal
+         * entry of a few bytes, not the ensemble's whole vector) */
         if (member < 0 || member >= n_) HXB_THROW("member index out of range");
-        std::vector<double> cur(n_);
-        chk(hx_get_param(h_, engine_name(datum).c_str(), cur.data(), n_));
-        cur[member] = (double)v;
-        c = SetCall::members(datum, cur);
+        c = SetCall::one(datum, member, (double)v);
       }
       apply(c);
       journal_.push_back(c);
@@ -548,14 +547,16 @@ class EnsembleCore {
   /* one setData / sendMessage(SETDATA) / setMembers, kept so that an engine rebuilt for a new
    * biome list can be brought back to the same inputs */
   struct SetCall {
-    enum Kind { SCALAR, DATED, MEMBERS, TRACKING } kind = SCALAR;
+    enum Kind { SCALAR, DATED, MEMBERS, TRACKING, MEMBER } kind = SCALAR;
     std::string name;
     double date = 0.0, value = 0.0;
+    int member = 0;
     std::vector<double> per_member;
     static SetCall scalar(const std::string &n, double v) { SetCall c; c.kind = SCALAR; c.name = n; c.value = v; return c; }
     static SetCall dated(const std::string &n, double d, double v) { SetCall c; c.kind = DATED; c.name = n; c.date = d; c.value = v; return c; }
     static SetCall members(const std::string &n, const std::vector<double> &v) { SetCall c; c.kind = MEMBERS; c.name = n; c.per_member = v; return c; }
     static SetCall tracking(double v) { SetCall c; c.kind = TRACKING; c.value = v; return c; }
+    static SetCall one(const std::string &n, int m, double v) { SetCall c; c.kind = MEMBER; c.name = n; c.member = m; c.value = v; return c; }
   };
   void apply(const SetCall &c) {
     const std::string name = engine_name(c.name);
@@ -563,6 +564,7 @@ class EnsembleCore {
       case SetCall::TRACKING: chk(hx_set_tracking(h_, (int32_t)c.value, 1)); break; /* core.cpp:228-235 */
       case SetCall::DATED: chk(hx_set_scenario_series(h_, 0, name.c_str(), (int32_t)c.date, 1, &c.value)); break;
       case SetCall::MEMBERS: chk(hx_set_param(h_, name.c_str(), c.per_member.data(), (int32_t)c.per_member.size())); break;
+      case SetCall::MEMBER: chk(hx_set_param_member(h_, name.c_str(), (int32_t)c.member, c.value)); break;
       default: chk(hx_set_param_scalar(h_, name.c_str(), c.value));
     }
   }

@@ -1059,3 +1059,32 @@ def test_default_four_outputs_build_is_bit_identical(M):
     for v in ("CO2_concentration", "global_tas"):
         assert np.array_equal(res[("CO2_concentration", "global_tas")][v], res[tuple(r4)][v]), v
     assert np.array_equal(res[("RF_tot",)]["RF_tot"], res[tuple(r4)]["RF_tot"])
+
+
+def test_setvar_for_one_member():
+    """hx_set_param_member (Core::sendMessage(M_SETDATA) addressed to one core of an ensemble):
+    before and after prepare, scalar and per-member parameters, spin-up parameters -- equal to
+    setting the whole vector"""
+    import hector_b200 as hb
+    M = 6
+    S = np.array([2.0, 2.5, 3.0, 3.5, 4.0, 4.5])
+    a = _engine(M); b = _engine(M)
+    a.setvar("S", S)
+    for i in range(M):
+        b.setvar_member("S", i, S[i])
+    b.setvar_member("beta", 2, 0.4)                  # a scalar parameter becomes per-member
+    a.setvar("beta", np.where(np.arange(M) == 2, 0.4, a.getvar("beta")[0]))
+    for e in (a, b):
+        e.run(1900)
+    b.setvar_member("q10_rh", 4, 2.2); b.setvar_member("veg_c", 1, 500.0)   # after prepare; veg_c enters the spin-up
+    a.setvar("q10_rh", np.where(np.arange(M) == 4, 2.2, a.getvar("q10_rh")[0]))
+    a.setvar("veg_c", np.where(np.arange(M) == 1, 500.0, a.getvar("veg_c")[0]))
+    assert np.array_equal(a.getvar("veg_c"), b.getvar("veg_c")) and b.getvar("beta")[2] == 0.4
+    for e in (a, b):
+        e.reset(); e.run()
+    ya, yb = a.fetchvars(_years()), b.fetchvars(_years())
+    for v in ya:
+        assert np.array_equal(ya[v], yb[v]), v
+    with pytest.raises(hb.HxError):
+        b.setvar_member("S", M, 3.0)
+    a.close(); b.close()
