@@ -32,6 +32,20 @@ for v in want:
     d = np.abs(got[v][i] - ref)
     nz = np.nonzero(d > 0)[0]
     print("  first differing year", 1746 + int(nz[0]) if len(nz) else None, "n differing", len(nz))
+    # conditioning: the oracle against its own build with FMA contraction on the same member
+    import subprocess, tempfile
+    so = os.path.join(tempfile.mkdtemp(), "fma.so")
+    subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-fPIC", "-shared", "-mfma", "-ffp-contract=fast", "-o", so,
+                           os.path.join(os.path.dirname(port.__file__), "hector_oracle.c"), "-lm"])
+    keep = (port.SO, port._lib)
+    port.SO, port._lib = so, None
+    kw = {util.ALLPARAM_RANGES[n][0]: float(vals[n][i]) for n in vals}
+    _, _, out_fma = port.run_member_constrained(tabs[names[ms[i]]], specs[ms[i]], **kw)
+    port.SO, port._lib = keep
+    k = port.OUT_NAMES.index(v)
+    e_fma = np.abs(out_fma[k] - out[k]) / np.maximum(np.abs(out[k]), util.FLOOR.get(v, 1e-3))
+    print("  oracle vs its FMA build on this member: %s worst %.3g in %d  (engine vs oracle: %.3g)" % (
+        v, np.nanmax(e_fma), 1746 + int(np.nanargmax(e_fma)), e))
     for u in ["permafrost_c", "thawedp_c", "soil_c", "land_tas", "NBP", "atmos_co2" if "atmos_co2" in outs else "CO2_concentration"]:
         dd = np.abs(got[u][i] - out[port.OUT_NAMES.index(u)])
         print("  |gpu - oracle| %-18s" % u, " ".join("%d:%.1e" % (1746 + t, dd[t]) for t in list(range(0, 555, 30)) + list(range(478, 496))))
