@@ -6,6 +6,7 @@ from tests import test_gpu_fuzz as F
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 for s in range(first, first + n):
+    print('seed', s, flush=True)
     F.test_scenarios_constraints_and_all_parameters_together(s)
     F.test_tracking_with_scenarios_constraints_and_all_parameters(s + 50000, 1750 + (s * 37) % 300)
     F.test_random_biome_configurations_with_constraints(s + 90000)
