@@ -1088,3 +1088,39 @@ def test_setvar_for_one_member():
     with pytest.raises(hb.HxError):
         b.setvar_member("S", M, 3.0)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("case", util.ref_allparams(), ids=lambda c: c["name"])
+def test_all_parameters_vs_reference_golden(case):
+    """every scalar parameter and the tau / rho / delta of four halocarbons perturbed at once,
+    three SSPs, against committed runs of the UNMODIFIED reference (tests/golden/
+    ref_allparams.npz; tools/gpu_allparams_vs_reference.py): the per-scenario gas constants go
+    in as scalars (host series), once more per member (the GAS build) -- the same answers"""
+    import hector_b200 as hb
+    from oracle import port
+    names = {"preind_C_surface": "preind_surface_c", "preind_C_ID": "preind_interdeep_c"}
+    field = {"halo_tau": "tau", "halo_rho": "rho", "halo_delta": "delta"}
+    variables = list(case["values"])
+    got = {}
+    for per_member in (False, True):
+        ens = hb.Ensemble(2, util.scenarios()[case["scenario"]], outputs=variables)
+        for k, v in case["params"].items():
+            ens.setvar(names.get(k, k), float(v))
+        for key, v in case["halo"].items():
+            fld, idx = key[:-1].split("[")
+            nm = "%s.%s" % (port.HALOS[int(idx)], field[fld])
+            ens.setvar(nm, np.full(2, float(v)) if per_member else float(v))
+        ens.run()
+        assert (ens.status()[0] == 0).all()
+        got[per_member] = ens.fetchvars(_years(), variables)
+        ens.close()
+    worst = {}
+    for v in variables:
+        ref = case["values"][v]
+        for pm in (False, True):
+            if v == "ocean_timesteps":
+                assert np.array_equal(got[pm][v][0], ref), (v, pm)
+            else:
+                worst[v] = max(worst.get(v, 0.0), util.parity_err(got[pm][v][0], ref, v))
+    print({k: "%.2g" % e for k, e in sorted(worst.items(), key=lambda kv: -kv[1])[:5]})
+    assert max(worst.values()) < TOL, worst

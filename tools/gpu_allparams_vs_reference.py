@@ -1,6 +1,7 @@
 """GPU vs the committed all-parameter runs of the unmodified reference
 (tests/golden/ref_allparams.npz: every scalar parameter and four halocarbons' tau / rho / delta
-perturbed at once).  Companion of gpu_all_params_vs_oracle.py, also not yet run on a GPU; the
+perturbed at once).  Companion of gpu_all_params_vs_oracle.py (in the suite as
+tests/test_gpu_parity.py::test_all_parameters_vs_reference_golden); the
 per-scenario gas constants (N0, UC_N2O, TN2O0, halocarbon tables) go through
 hx_set_param_scalar, everything else per member.
 
