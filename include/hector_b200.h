@@ -66,7 +66,9 @@ typedef struct hx_engine *hx_handle;
                                     N2O / halocarbon parameters (not the latter with either of the former). */
 #define HX_FLAG_KEEP_ORDER 8u    /* keep members in caller order on the device (default: members of a
                                     scenario are re-ordered so that the members of a warp behave
-                                    alike; outputs are in caller order either way) */
+                                    alike; outputs are in caller order either way).  Runs that
+                                    record more than 20 variables keep the caller's order anyway:
+                                    their output rows then store coalesced, which is worth more */
 
 typedef struct {
   int32_t n_members;   /* ensemble members owned by this engine (this GPU's shard) */
