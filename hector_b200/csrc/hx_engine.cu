@@ -1733,9 +1733,6 @@ int hx_prepare(hx_handle h) {
   const int nb = h->n_biomes;
   C.n_biomes = nb;
   for (int i = 0; i < HX_MAX_BIOMES; ++i) C.biome_order[i] = i;
-  if ((h->cfg.flags & HX_FLAG_EXACT_ATTEMPTS) && (tracking || nb > 1) && h->gas_per_member())
-    return fail(HX_ERR_UNSUPPORTED, "HX_FLAG_EXACT_ATTEMPTS with per-member N2O / halocarbon parameters is "
-                                    "available without tracking and biomes only");
   if (nb > 1) {
     if (tracking)
       return fail(HX_ERR_UNSUPPORTED, "carbon tracking with more than one biome is not implemented");

@@ -1572,6 +1572,9 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
                            : launch_run_t<false, false, 2, true, true, false, true>(d, C, r0, r1, st);
     if (d.GP) { /* ... with per-member N2O / halocarbon parameters */
       if (d.constrained > 1) return launch_run_t<false, true, 2, true, true, true, false, true>(d, C, r0, r1, st);
+      if (exact)
+        return d.constrained ? launch_run_t<false, true, 2, true, true, false, true, true>(d, C, r0, r1, st)
+                             : launch_run_t<false, false, 2, true, true, false, true, true>(d, C, r0, r1, st);
       if (d.constrained) return launch_run_t<false, true, 2, true, true, false, false, true>(d, C, r0, r1, st);
       return launch_run_t<false, false, 2, true, true, false, false, true>(d, C, r0, r1, st);
     }
@@ -1583,9 +1586,11 @@ cudaError_t launch_run(const HxDev &d, const HxConst &C, int r0, int r1, cudaStr
                          : launch_run_t<false, false, 2, true, true, false>(d, C, r0, r1, st);
   }
   if (d.T) { /* carbon tracking: the record-only builds */
-    if (d.GP) /* ... with per-member N2O / halocarbon parameters */
-      return d.constrained ? launch_run_t<true, true, HX_TRACK_CTAS, true, false, true, false, true>(d, C, r0, r1, st)
-                           : launch_run_t<true, false, HX_TRACK_CTAS, true, false, false, false, true>(d, C, r0, r1, st);
+    if (d.GP) { /* ... with per-member N2O / halocarbon parameters */
+      if (d.constrained) return launch_run_t<true, true, HX_TRACK_CTAS, true, false, true, false, true>(d, C, r0, r1, st);
+      return exact ? launch_run_t<true, false, HX_TRACK_CTAS, true, false, false, true, true>(d, C, r0, r1, st)
+                   : launch_run_t<true, false, HX_TRACK_CTAS, true, false, false, false, true>(d, C, r0, r1, st);
+    }
     if (d.constrained) return launch_run_t<true, true, HX_TRACK_CTAS>(d, C, r0, r1, st);
     if (exact) return launch_run_t<true, false, HX_TRACK_CTAS, true, false, false, true>(d, C, r0, r1, st);
     return d.out_minimal == 1 ? launch_run_t<true, false, HX_TRACK_CTAS, false>(d, C, r0, r1, st)

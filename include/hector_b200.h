@@ -62,8 +62,7 @@ typedef struct hx_engine *hx_handle;
 #define HX_FLAG_EXACT_ATTEMPTS 4u /* execute the ODE attempts the reference abandons whenever one of
                                     their stage states could go negative (slower build of the run
                                     kernel; without it such a member stops with
-                                    HX_MEMBER_NEEDS_EXACT).  Also with carbon tracking, biomes or per-member
-                                    N2O / halocarbon parameters (not the latter with either of the former). */
+                                    HX_MEMBER_NEEDS_EXACT).  Every combination of features has such a build. */
 #define HX_FLAG_KEEP_ORDER 8u    /* keep members in caller order on the device (default: members of a
                                     scenario are re-ordered so that the members of a warp behave
                                     alike; outputs are in caller order either way).  Runs that

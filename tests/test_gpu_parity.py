@@ -338,11 +338,20 @@ def test_per_member_n2o_and_halocarbon_parameters():
         rel = np.where(np.arange(1, 556) >= base, hrf[1:, k] - hrf[base, k], 0.0)
         assert np.max(np.abs(derived["FadjSF6"][i] - rel)) < 1e-12
     # what the GAS build cannot be combined with is refused, not ignored
-    bad = hb.Ensemble(4, raw, exact_attempts=True, tracking_date=1800)
+    bad = hb.Ensemble(4, raw)                               # a gas constraint on top of per-member gas parameters
     bad.setvar("CF4.tau", np.full(4, 40000.0))
+    bad.setvar_series("CF4_constrain", [2000], [80.0])
     with pytest.raises(hb.HxError):
         bad.prepare()
     bad.close()
+    both = hb.Ensemble(4, raw, outputs=outs, exact_attempts=True, tracking_date=1800, track_every=100)
+    for k, v in per.items():                                 # exact attempts + tracking + gas parameters
+        both.setvar(k, v[:4])
+    both.run()
+    g4 = both.fetchvars(_years(), outs)
+    for v in outs:
+        assert np.array_equal(g4[v], got[v][:4]), v
+    both.close()
     ok = hb.Ensemble(4, raw, outputs=outs, exact_attempts=True)   # the exact GAS build exists
     ok.setvar("CF4.tau", per["CF4.tau"][:4]); ok.setvar("S", per["S"][:4]); ok.setvar("N0", per["N0"][:4])
     ok.setvar("UC_N2O", per["UC_N2O"][:4]); ok.setvar("TN2O0", per["TN2O0"][:4])
