@@ -973,6 +973,13 @@ int Engine::fetch_functions(const char *name, const double *dates, int n_dates, 
   Kind kind = F_NONE;
   for (const auto &e : tab)
     if (!strcmp(name, e.n)) kind = e.k;
+  int one_biome = -1; /* "<biome>.f_frozen": that biome's own fraction */
+  if (kind == F_NONE && n_biomes > 1) {
+    const char *dot = strchr(name, '.');
+    if (dot && !strcmp(dot + 1, "f_frozen"))
+      for (int ib = 0; ib < n_biomes; ++ib)
+        if (biome_names[ib] == std::string(name, dot - name)) { kind = F_FROZEN; one_biome = ib; }
+  }
   if (kind == F_NONE) return 0;
   rc = HX_OK;
   int rmax = 0;
@@ -1108,34 +1115,53 @@ int Engine::fetch_functions(const char *name, const double *dates, int n_dates, 
       break;
     }
     case F_FROZEN: {
-      if (n_biomes > 1) {
-        rc = fail(HX_ERR_UNSUPPORTED, "f_frozen with more than one biome is not derived");
-        return 1;
-      }
-      /* the fraction only moves while there is permafrost left, so walk every year up to the last
-       * one asked for */
-      std::vector<double> yrs(rmax), T, P, wf, mu, sigma;
-      for (int r = 0; r < rmax; ++r) yrs[r] = cfg.start_year + r;
-      T.resize((size_t)M * rmax); P.resize((size_t)M * rmax);
-      if ((rc = hx_fetch(self, "land_tas", yrs.data(), rmax, T.data())) ||
-          (rc = hx_fetch(self, "permafrost_c", yrs.data(), rmax, P.data())) ||
-          (rc = param(PI_WARMINGFACTOR, wf)) || (rc = param(PI_PF_MU, mu)) || (rc = param(PI_PF_SIGMA, sigma)))
-        return 1;
+      /* Per biome the fraction only moves while that biome has permafrost left, so every year up
+       * to the last one asked for is walked.  The datum without a biome prefix is the reference's
+       * weighted mean (simpleNbox.cpp:492-513): the biomes' fractions of the DATE weighted with
+       * their permafrost of the CURRENT date, and 1 when there is none in the system now. */
+      const int nbm = n_biomes > 1 ? n_biomes : 1;
+      std::vector<double> yrs(rmax + 1), T, now((size_t)M, 0.0);
+      for (int r = 0; r <= rmax; ++r) yrs[r] = cfg.start_year + r;
+      T.resize((size_t)M * rmax);
+      if ((rc = hx_fetch(self, "land_tas", yrs.data(), rmax, T.data()))) return 1;
       const double root_two = 1.41421356237309504880168872420969807856967187537694;
-      std::vector<double> f(rmax + 1);
-      for (int i = 0; i < M; ++i) {
-        f[0] = 1.0;
-        for (int r = 1; r <= rmax; ++r) { /* slowparameval of year r sees the year before */
-          const double Tb = T[(size_t)i * rmax + r - 1] * wf[i], perm = P[(size_t)i * rmax + r - 1];
-          f[r] = f[r - 1];
-          if (perm == perm && perm != 0.0) {
-            double cur = 1.0;
-            if (Tb > 0) cur = 1 - std::erfc(-((std::log(Tb) - mu[i]) / (sigma[i] * root_two))) / 2;
-            f[r] = cur;
-          } else if (!(perm == perm)) f[r] = perm;
+      const double today = cfg.start_year + cur_row;
+      std::vector<std::vector<double>> wnow(nbm, std::vector<double>((size_t)M)), fb(nbm, std::vector<double>(N));
+      std::vector<double> P((size_t)M * rmax), wf((size_t)M), mu((size_t)M), sigma((size_t)M), f(rmax + 1);
+      for (int ib = 0; ib < nbm; ++ib) {
+        const std::string pre = n_biomes > 1 ? biome_names[ib] + "." : std::string();
+        if ((rc = hx_fetch(self, (pre + "permafrost_c").c_str(), yrs.data(), rmax, P.data())) ||
+            (rc = hx_fetch(self, (pre + "permafrost_c").c_str(), &today, 1, wnow[ib].data())) ||
+            (rc = hx_get_param(self, (pre + "warmingfactor").c_str(), wf.data(), M)) ||
+            (rc = hx_get_param(self, (pre + "pf_mu").c_str(), mu.data(), M)) ||
+            (rc = hx_get_param(self, (pre + "pf_sigma").c_str(), sigma.data(), M)))
+          return 1;
+        for (int i = 0; i < M; ++i) {
+          f[0] = 1.0;
+          for (int r = 1; r <= rmax; ++r) { /* slowparameval of year r sees the year before */
+            const double Tb = T[(size_t)i * rmax + r - 1] * wf[i], perm = P[(size_t)i * rmax + r - 1];
+            f[r] = f[r - 1];
+            if (perm == perm && perm != 0.0) {
+              double cur = 1.0;
+              if (Tb > 0) cur = 1 - std::erfc(-((std::log(Tb) - mu[i]) / (sigma[i] * root_two))) / 2;
+              f[r] = cur;
+            } else if (!(perm == perm)) f[r] = perm;
+          }
+          for (int k = 0; k < n_dates; ++k) fb[ib][(size_t)i * n_dates + k] = f[(int)dates[k] - cfg.start_year];
+          now[i] += wnow[ib][i];
         }
-        for (int k = 0; k < n_dates; ++k) out[(size_t)i * n_dates + k] = f[(int)dates[k] - cfg.start_year];
       }
+      for (int i = 0; i < M; ++i)
+        for (int k = 0; k < n_dates; ++k) {
+          const size_t at = (size_t)i * n_dates + k;
+          double v = 1.0; /* no permafrost in the system now */
+          if (one_biome >= 0) v = fb[one_biome][at];
+          else if (now[i] > 0.0) {
+            v = 0.0;
+            for (int ib = 0; ib < nbm; ++ib) v += (wnow[ib][i] / now[i]) * fb[ib][at];
+          } else if (!(now[i] == now[i])) v = now[i];
+          out[at] = v;
+        }
       break;
     }
     default: break;

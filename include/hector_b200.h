@@ -225,7 +225,8 @@ int hx_run_stream(hx_handle h, double run_to_date, int32_t n_vars, const char *c
  * recorded ones (each needs those recorded): HL_sst, LL_sst (the box temperatures the year's
  * chemistry ran at, from sst), HL_DIC, LL_DIC, DIC, ML_ocean_c (from HL_ocean_c / LL_ocean_c),
  * pH, PCO2 (area-weighted surface means), TAU_OH (from CH4_concentration), f_frozen (from
- * land_tas and permafrost_c; single biome), HL_CO3, LL_CO3, CO3 and the calcite / aragonite
+ * land_tas and permafrost_c; with biomes "<biome>.f_frozen" from "<biome>.permafrost_c" and
+ * f_frozen their mean weighted with the permafrost of the current date), HL_CO3, LL_CO3, CO3 and the calcite / aragonite
  * saturation states HL_OmegaCa, LL_OmegaCa, HL_OmegaAr, LL_OmegaAr (from the recorded pCO2, pH
  * and sst).  HL_ocean_uptake, LL_ocean_uptake, rh_det and rh_soil are RECORDED outputs: select them
  * with hx_select_outputs (they cost scratch rows of global memory traffic per stash, so they are

@@ -565,6 +565,27 @@ def make_biomes_stash():
     print("biomes_stash", names)
 
 
+def make_biomes_frozen():
+    """ref_biomes_frozen.npz: f_frozen (the weighted mean of simpleNbox.cpp:492-513) and each
+    biome's own <biome>.f_frozen of the first two multi-biome cases of ref_biomes.npz, from the
+    UNMODIFIED reference"""
+    import tempfile
+    from oracle import ref
+    tmp = tempfile.mkdtemp()
+    names, variables, vals = [], [], []
+    for name in list(BIOME_CASES)[:2]:
+        scn, biomes, params = BIOME_CASES[name]
+        ini = os.path.join(tmp, name + ".ini")
+        biome_ini(scn, biomes, ini)
+        V = ["f_frozen"] + ["%s.f_frozen" % b for b in biomes]
+        ok, err, o, _ = ref.run_member(ini, dict(params), V)
+        assert ok, err
+        names.append(name); variables.append(",".join(V)); vals.append(np.asarray(o[:len(V)]))
+    np.savez_compressed(os.path.join(OUT, "ref_biomes_frozen.npz"), names=np.array(names),
+                        variables=np.array(variables), **{"values_%d" % k: v for k, v in enumerate(vals)})
+    print("biomes_frozen", names, [v.shape for v in vals])
+
+
 ALLPARAM_VARS = ["CO2_concentration", "global_tas", "RF_tot", "HL_pH", "CH4_concentration",
                  "N2O_concentration", "O3_concentration", "veg_c", "soil_c", "permafrost_c",
                  "ocean_c", "heatflux"]
@@ -736,8 +757,11 @@ def make_outputstream():
 
 
 if __name__ == "__main__":
-    if "biomes_stash" in sys.argv[1:]:
+    if "biomes_frozen" in sys.argv[1:]:
+        make_biomes_frozen()
+    elif "biomes_stash" in sys.argv[1:]:
         make_biomes_stash()
+        make_biomes_frozen()
     elif "outputstream" in sys.argv[1:]:
         make_outputstream()
     elif "more" in sys.argv[1:]:
@@ -771,3 +795,4 @@ if __name__ == "__main__":
         make_more_outputs()
         make_outputstream()
         make_biomes_stash()
+        make_biomes_frozen()

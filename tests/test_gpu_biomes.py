@@ -235,3 +235,28 @@ def test_stash_outputs_with_biomes():
         tot = got["HL_ocean_uptake"][0] + got["LL_ocean_uptake"][0]
         assert np.abs(tot - got["ocean_uptake"][0]).max() < 1e-12
         ens.close()
+
+
+def test_f_frozen_with_biomes():
+    """f_frozen of a multi-biome run is the reference's weighted mean (the biomes' fractions of the
+    date, weighted with their permafrost of the current date; simpleNbox.cpp:492-513) and
+    <biome>.f_frozen a biome's own (simpleNbox.cpp:634-645), against the unmodified reference
+    (tests/golden/ref_biomes_frozen.npz)"""
+    import os
+    import hector_b200 as hb
+    z = np.load(os.path.join(util.GOLDEN, "ref_biomes_frozen.npz"))
+    cases = {c["name"]: c for c in util.ref_biomes()}
+    for k, name in enumerate(z["names"]):
+        case = cases[str(name)]
+        V = str(z["variables"][k]).split(",")
+        assert V[1:] == ["%s.f_frozen" % b for b in case["biomes"]]
+        ens = _ensemble(hb, case, 2, ["land_tas"] + ["%s.permafrost_c" % b for b in case["biomes"]])
+        ens.run()
+        assert (ens.status()[0] == 0).all()
+        got = ens.fetchvars(YEARS, V)
+        ref = z["values_%d" % k]
+        assert ref[0].min() < 0.5 and (ref[1:] == 1.0).all(axis=1).any()  # thaw, and a biome with none
+        for j, v in enumerate(V):
+            for i in range(2):
+                assert np.abs(got[v][i] - ref[j]).max() < TOL, (name, v, np.abs(got[v][i] - ref[j]).max())
+        ens.close()
