@@ -111,7 +111,9 @@ STASH_OUTPUTS = ["HL_ocean_uptake", "LL_ocean_uptake", "rh_det", "rh_soil"]
 # The rest of the reference's outputstream variables that are plain functions of recorded outputs
 # (hx_fetch evaluates them on the host; each needs the outputs it depends on to be selected):
 # {variable: recorded outputs it needs}.  With OUTPUT_VARIABLES, STASH_OUTPUTS and
-# DERIVED_VARIABLES this is all of R's ALL_VARS().
+# DERIVED_VARIABLES this is all of R's ALL_VARS().  With biomes f_frozen needs every
+# "<biome>.permafrost_c" (it is their mean weighted with the current permafrost,
+# simpleNbox.cpp:492-513) and "<biome>.f_frozen" that biome's.
 FUNCTION_VARIABLES = {
     "HL_sst": ["sst"], "LL_sst": ["sst"], "HL_DIC": ["HL_ocean_c"], "LL_DIC": ["LL_ocean_c"],
     "DIC": ["HL_ocean_c", "LL_ocean_c"], "pH": ["HL_pH", "LL_pH"], "PCO2": ["HL_PCO2", "LL_PCO2"],
